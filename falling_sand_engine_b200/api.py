@@ -1,0 +1,224 @@
+"""ctypes binding of libfse_b200.so (include/fse.h) and the host-side `World` mirror.
+
+`World` keeps the reference's method names for the tick path (source/engine/world.hpp:148-192):
+tick / tickTemperature / tickCells / addCell / getTile / setTile.  Everything runs on the GPU through
+the C ABI; if the shared library is missing or no CUDA device is present this module raises — there is
+no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import types as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfse_b200.so")
+_lib = None
+
+
+class FseError(RuntimeError):
+    pass
+
+
+EXPORTS = [
+    "fse_ctx_create", "fse_ctx_destroy", "fse_last_error", "fse_version", "fse_abi_sizeof", "fse_materials_set",
+    "fse_world_create", "fse_world_destroy", "fse_sync", "fse_write_rect", "fse_read_rect", "fse_clear_dirty", "fse_stats_rect",
+    "fse_tick", "fse_tick_temperature", "fse_particles_add", "fse_particles_tick", "fse_particles_count", "fse_particles_read",
+    "fse_particles_clear", "fse_particles_reserve", "fse_timer_start", "fse_timer_stop", "fse_launch_count",
+    "fse_kernel_timing_enable", "fse_kernel_timing_read",
+]
+
+
+def load_library(path=None):
+    """dlopen the C-ABI library.  Fails loudly when it has not been built (`__graft_entry__.build()`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise FseError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(path)
+    L.fse_last_error.restype = C.c_char_p
+    L.fse_version.restype = C.c_char_p
+    L.fse_launch_count.restype = C.c_int64
+    L.fse_launch_count.argtypes = [C.c_void_p]
+    L.fse_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.fse_ctx_destroy.argtypes = [C.c_void_p]
+    L.fse_ctx_destroy.restype = None
+    L.fse_world_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.fse_world_destroy.argtypes = [C.c_void_p]
+    L.fse_world_destroy.restype = None
+    L.fse_materials_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    for n in ("fse_sync", "fse_clear_dirty", "fse_particles_clear", "fse_timer_start"):
+        getattr(L, n).argtypes = [C.c_void_p]
+    L.fse_write_rect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.fse_read_rect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.fse_stats_rect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.fse_tick.argtypes = [C.c_void_p, C.c_void_p]
+    L.fse_tick_temperature.argtypes = [C.c_void_p, C.c_void_p]
+    L.fse_particles_add.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.fse_particles_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.fse_particles_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    L.fse_particles_reserve.argtypes = [C.c_void_p, C.c_int64]
+    if hasattr(L, "fse_particles_tick"):
+        L.fse_particles_tick.argtypes = [C.c_void_p, C.c_void_p]
+    L.fse_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.fse_kernel_timing_enable.argtypes = [C.c_void_p, C.c_int]
+    L.fse_kernel_timing_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    _lib = L
+    return L
+
+
+def _ck(rc):
+    if rc != 0:
+        raise FseError(f"fse error {rc}: {load_library().fse_last_error().decode()}")
+
+
+class Context:
+    def __init__(self, device=0, table=None):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        _ck(self.L.fse_ctx_create(device, C.byref(self.h)))
+        self.table = None
+        if table is not None:
+            self.set_materials(table)
+
+    def set_materials(self, table):
+        """materials_init / materials_register / materials_push (game_basic.cpp:79-81)."""
+        _ck(self.L.fse_materials_set(self.h, table.mats, table.n, C.byref(table.ids), table.inter, table.inter_offsets, table.react,
+                                     table.react_offsets))
+        self.table = table
+
+    def launch_count(self):
+        return int(self.L.fse_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.fse_ctx_destroy(self.h)
+            self.h = None
+
+
+class World:
+    """Device-resident world (reference `class world`, world.hpp:63-193) for the tick path."""
+
+    def __init__(self, ctx, width, height):
+        self.L = ctx.L
+        self.ctx = ctx
+        self.width, self.height = width, height
+        self.h = C.c_void_p()
+        _ck(self.L.fse_world_create(ctx.h, width, height, C.byref(self.h)))
+        self.tickZone = T.zone_of(width, height)
+
+    def close(self):
+        if self.h:
+            self.L.fse_world_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- boundary -------------------------------------------------------------------------------
+    def write_rect(self, x, y, cells):
+        cells = np.ascontiguousarray(cells, dtype=T.CELL_DTYPE)
+        h, w = cells.shape
+        _ck(self.L.fse_write_rect(self.h, x, y, w, h, cells.ctypes.data_as(C.c_void_p)))
+
+    def write_rect_ptr(self, x, y, w, h, ptr):
+        _ck(self.L.fse_write_rect(self.h, x, y, w, h, C.c_void_p(ptr)))
+
+    def read_rect(self, x, y, w, h, out=None):
+        out = np.zeros((h, w), dtype=T.CELL_DTYPE) if out is None else out
+        _ck(self.L.fse_read_rect(self.h, x, y, w, h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def read_all(self):
+        return self.read_rect(0, 0, self.width, self.height)
+
+    def getTile(self, x, y):
+        return self.read_rect(x, y, 1, 1)[0, 0]
+
+    def setTile(self, x, y, cell):
+        a = np.zeros((1, 1), dtype=T.CELL_DTYPE)
+        a[0, 0] = cell
+        a["dirty"] = 1  # world::setTile marks dirty (world.cpp:1007)
+        self.write_rect(x, y, a)
+
+    def clear_dirty(self):
+        _ck(self.L.fse_clear_dirty(self.h))
+
+    def stats(self, rect=None):
+        r = rect or T.Rect(0, 0, self.width, self.height)
+        s = T.Stats()
+        _ck(self.L.fse_stats_rect(self.h, r.x, r.y, r.w, r.h, C.byref(s)))
+        return s
+
+    def sync(self):
+        _ck(self.L.fse_sync(self.h))
+
+    # -- the tick ---------------------------------------------------------------------------------
+    def tick(self, tick, seed=1337, cell_iter=3, zone=None):
+        a = T.TickArgs(tick, seed, cell_iter, zone or self.tickZone)
+        _ck(self.L.fse_tick(self.h, C.byref(a)))
+
+    def tickTemperature(self, zone=None):
+        z = zone or self.tickZone
+        _ck(self.L.fse_tick_temperature(self.h, C.byref(z)))
+
+    tick_temperature = tickTemperature
+
+    # -- particles ----------------------------------------------------------------------------------
+    def addCell(self, parts):
+        parts = np.ascontiguousarray(np.atleast_1d(parts), dtype=T.PARTICLE_DTYPE)
+        _ck(self.L.fse_particles_add(self.h, parts.ctypes.data_as(C.c_void_p), len(parts)))
+
+    particles_add = addCell
+
+    def tickCells(self, zone=None):
+        z = zone or self.tickZone
+        _ck(self.L.fse_particles_tick(self.h, C.byref(z)))
+
+    particles_tick = tickCells
+
+    def particles_count(self):
+        n = C.c_int64()
+        _ck(self.L.fse_particles_count(self.h, C.byref(n)))
+        return n.value
+
+    def particles_read(self):
+        n = self.particles_count()
+        out = np.zeros(n, dtype=T.PARTICLE_DTYPE)
+        m = C.c_int64()
+        if n:
+            _ck(self.L.fse_particles_read(self.h, out.ctypes.data_as(C.c_void_p), n, C.byref(m)))
+        return out
+
+    def particles_clear(self):
+        _ck(self.L.fse_particles_clear(self.h))
+
+    def particles_reserve(self, cap):
+        _ck(self.L.fse_particles_reserve(self.h, cap))
+
+    # -- measurement ----------------------------------------------------------------------------------
+    def timer_start(self):
+        _ck(self.L.fse_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _ck(self.L.fse_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def kernel_timing(self, enable):
+        _ck(self.L.fse_kernel_timing_enable(self.h, 1 if enable else 0))
+
+    def kernel_timing_read(self):
+        tot, n = C.c_double(), C.c_int64()
+        _ck(self.L.fse_kernel_timing_read(self.h, C.byref(tot), C.byref(n)))
+        return tot.value, n.value
+
+
+from .materials import default_materials  # noqa: E402,F401  (InitMaterials, gds.cpp:117-280)

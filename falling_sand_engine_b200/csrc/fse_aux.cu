@@ -1,0 +1,240 @@
+// fse_aux.cu — small kernels around the tick: AoS<->SoA rect transfer (world::getTile/setTile, frame()
+// merge and chunkSaveCache, world.cpp:999-1008, 2374-2391, 2780-2792), world statistics, dirty clear,
+// and world::tickTemperature() (world.cpp:1950-2004).
+#include "fse_device.cuh"
+
+namespace fse {
+
+// ---- AoS rect -> planes ------------------------------------------------------------------------------
+__global__ void write_rect_kernel(Planes p, int W, int x0, int y0, int rw, int rh, const fse_cell* __restrict__ src) {
+    const size_t n = (size_t)rw * rh;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % rw), y = (int)(i / rw);
+        size_t g = (size_t)(y0 + y) * W + (x0 + x);
+        fse_cell c = src[i];
+        p.mat[g] = (uint8_t)c.mat;
+        p.flg[g] = (uint8_t)((c.moved ? F_MOVED : 0) | (c.dirty ? F_DIRTY : 0));
+        p.stl[g] = c.settle;
+        p.tmp[g] = c.temp;
+        p.col[g] = c.color;
+        p.fl[g] = c.fluid;
+        p.fd[g] = c.fluid_diff;
+    }
+}
+
+__global__ void read_rect_kernel(Planes p, int W, int x0, int y0, int rw, int rh, fse_cell* __restrict__ dst) {
+    const size_t n = (size_t)rw * rh;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % rw), y = (int)(i / rw);
+        size_t g = (size_t)(y0 + y) * W + (x0 + x);
+        fse_cell c;
+        uint8_t f = p.flg[g];
+        c.mat = p.mat[g];
+        c.moved = (f & F_MOVED) ? 1 : 0;
+        c.settle = p.stl[g];
+        c.color = p.col[g];
+        c.temp = p.tmp[g];
+        c.dirty = (f & F_DIRTY) ? 1 : 0;
+        c._pad = 0;
+        c.fluid = p.fl[g];
+        c.fluid_diff = p.fd[g];
+        dst[i] = c;
+    }
+}
+
+// fresh world: every cell is a default MaterialInstance() = Tiles_NOTHING (gds.cpp:310-312)
+__global__ void fill_air_kernel(Planes p, size_t n, uint8_t air) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        p.mat[i] = air;
+        p.flg[i] = 0;
+        p.stl[i] = 0;
+        p.tmp[i] = 0;
+        p.col[i] = 0;
+        p.fl[i] = 2.0f;
+        p.fd[i] = 0.0f;
+    }
+}
+
+// memset(dirty, false, W*H) (game.cpp:2153): clear bit1 of the flag plane, 16 bytes per thread
+__global__ void clear_dirty_kernel(uint4* flg, size_t n16) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 v = flg[i];
+        const uint32_t m = ~(0x01010101U * F_DIRTY);
+        v.x &= m; v.y &= m; v.z &= m; v.w &= m;
+        flg[i] = v;
+    }
+}
+
+// ---- statistics (movingTiles-style histogram, game.cpp:1991-2000, + parity hash) ----------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+struct DevStats {
+    unsigned long long hash;
+    unsigned long long count[FSE_MAX_MATERIALS];
+    double mass[FSE_MAX_MATERIALS];
+    unsigned long long n_dirty, n_moved;
+};
+
+__global__ void stats_kernel(Planes p, int W, int x0, int y0, int rw, int rh, const DevTables* T, DevStats* out) {
+    __shared__ unsigned int cnt[FSE_MAX_MATERIALS];
+    __shared__ double mass[FSE_MAX_MATERIALS];
+    __shared__ unsigned long long sh_hash, sh_dirty, sh_moved;
+    for (int i = threadIdx.x; i < FSE_MAX_MATERIALS; i += blockDim.x) {
+        cnt[i] = 0;
+        mass[i] = 0.0;
+    }
+    if (threadIdx.x == 0) sh_hash = sh_dirty = sh_moved = 0;
+    __syncthreads();
+    unsigned long long h = 0, nd = 0, nm = 0;
+    const size_t n = (size_t)rw * rh;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int x = x0 + (int)(i % rw), y = y0 + (int)(i / rw);
+        size_t g = (size_t)y * W + x;
+        uint8_t m = p.mat[g], f = p.flg[g], st = p.stl[g];
+        uint32_t col = p.col[g];
+        int16_t tmp = p.tmp[g];
+        float fl = p.fl[g], fd = p.fd[g];
+        uint64_t a = ((uint64_t)(uint32_t)x << 32) | (uint32_t)y;
+        uint64_t b = ((uint64_t)m << 48) | ((uint64_t)(f & F_MOVED) << 40) | ((uint64_t)st << 32) | col;
+        uint64_t d = ((uint64_t)(uint16_t)tmp << 32) | __float_as_uint(fl);
+        uint64_t hh = mix64(a + 0x9E3779B97F4A7C15ULL);
+        hh = mix64(hh ^ b);
+        hh = mix64(hh ^ d);
+        hh = mix64(hh ^ (uint64_t)__float_as_uint(fd));
+        h += hh;
+        atomicAdd(&cnt[m], 1u);
+        if (T->phys[m] == P_SOUP) atomicAdd(&mass[m], (double)fl + (double)fd);
+        nd += (f & F_DIRTY) ? 1 : 0;
+        nm += (f & F_MOVED) ? 1 : 0;
+    }
+    atomicAdd(&sh_hash, h);
+    atomicAdd(&sh_dirty, nd);
+    atomicAdd(&sh_moved, nm);
+    __syncthreads();
+    for (int i = threadIdx.x; i < FSE_MAX_MATERIALS; i += blockDim.x) {
+        if (cnt[i]) atomicAdd(&out->count[i], (unsigned long long)cnt[i]);
+        if (mass[i] != 0.0) atomicAdd(&out->mass[i], mass[i]);
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(&out->hash, sh_hash);
+        atomicAdd(&out->n_dirty, sh_dirty);
+        atomicAdd(&out->n_moved, sh_moved);
+    }
+}
+
+// ---- world::tickTemperature() (world.cpp:1950-2004) -----------------------------------------------------
+// Jacobi 3x3 stencil on the i16 temperature plane: order-independent, so bit-exact against the reference
+// order.  One thread per cell of a 32x8 tile staged (with a 1-cell halo) in shared memory; the new
+// temperatures go to a scratch plane that is then copied back (the reference's newTemps[] two-loop form).
+constexpr int TT_W = 64, TT_H = 16;
+
+__global__ void __launch_bounds__(256) temperature_kernel(const uint8_t* __restrict__ mat, const int16_t* __restrict__ tmp,
+                                                          int16_t* __restrict__ out, int W, int zx, int zy, int zw, int zh,
+                                                          const DevTables* __restrict__ T) {
+    __shared__ int16_t st[TT_H + 2][TT_W + 2];
+    __shared__ uint8_t sm[TT_H + 2][TT_W + 2];
+    __shared__ float condO[FSE_MAX_MATERIALS];
+    __shared__ float condS[FSE_MAX_MATERIALS];
+    __shared__ uint32_t addT[FSE_MAX_MATERIALS];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < FSE_MAX_MATERIALS; i += blockDim.x) {
+        condO[i] = T->cond_other[i];
+        condS[i] = T->cond_self[i];
+        addT[i] = T->add_temp[i];
+    }
+    const int bx = zx + blockIdx.x * TT_W, by = zy + blockIdx.y * TT_H;
+    for (int i = tid; i < (TT_H + 2) * (TT_W + 2); i += blockDim.x) {
+        int lx = i % (TT_W + 2), ly = i / (TT_W + 2);
+        size_t g = (size_t)(by + ly - 1) * W + (bx + lx - 1);
+        st[ly][lx] = tmp[g];
+        sm[ly][lx] = mat[g];
+    }
+    __syncthreads();
+    for (int i = tid; i < TT_W * TT_H; i += blockDim.x) {
+        int lx = i % TT_W, ly = i / TT_W;
+        int x = bx + lx, y = by + ly;
+        if (x >= zx + zw || y >= zy + zh) continue;
+        float n = 0.01f;
+        float v = 0.0f;
+#pragma unroll
+        for (int xa = -1; xa <= 1; xa++) {
+#pragma unroll
+            for (int ya = -1; ya <= 1; ya++) {  // FN(-1,-1) FN(-1,0) FN(-1,1) FN(0,-1) ... (world.cpp:1976-1984)
+                int t = st[ly + 1 + ya][lx + 1 + xa];
+                if (t != 0) {
+                    float factor = __fmul_rn((float)(abs(t) / 64), condO[sm[ly + 1 + ya][lx + 1 + xa]]);
+                    v = __fadd_rn(v, __fmul_rn((float)t, factor));
+                    n = __fadd_rn(n, factor);
+                }
+            }
+        }
+        const int t0 = st[ly + 1][lx + 1];
+        const uint8_t m0 = sm[ly + 1][lx + 1];
+        int nt;
+        if (v != 0.0f) {
+            float cs = condS[m0];
+            float a = __fmul_rn(__fdiv_rn(v, n), cs);
+            float b = __fmul_rn((float)t0, __fsub_rn(1.0f, cs));
+            float r = __fadd_rn(__fadd_rn((float)addT[m0], a), b);
+            nt = (int)r;  // i32 newTemps[] (world.hpp), truncation toward zero
+        } else {
+            nt = (int)(addT[m0] + (uint32_t)t0);  // unsigned wrap, as u32 + i16 in the reference
+        }
+        out[(size_t)y * W + x] = (int16_t)nt;  // real_tiles[].temperature = newTemps[] (i16 wrap)
+    }
+}
+
+__global__ void copy_zone_i16_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int W, int zx, int zy, int zw, int zh) {
+    const size_t n = (size_t)zw * zh;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        size_t g = (size_t)(zy + i / zw) * W + (zx + i % zw);
+        dst[g] = src[g];
+    }
+}
+
+// ---- host launchers --------------------------------------------------------------------------------
+static inline int grid_for(size_t n, int block) {
+    size_t g = (n + block - 1) / block;
+    if (g > 148 * 16) g = 148 * 16;  // grid-stride: a multiple of the SM count
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+cudaError_t launch_write_rect(Planes p, int W, int x0, int y0, int rw, int rh, const fse_cell* src, cudaStream_t s) {
+    write_rect_kernel<<<grid_for((size_t)rw * rh, 256), 256, 0, s>>>(p, W, x0, y0, rw, rh, src);
+    return cudaGetLastError();
+}
+cudaError_t launch_read_rect(Planes p, int W, int x0, int y0, int rw, int rh, fse_cell* dst, cudaStream_t s) {
+    read_rect_kernel<<<grid_for((size_t)rw * rh, 256), 256, 0, s>>>(p, W, x0, y0, rw, rh, dst);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_air(Planes p, size_t n, uint8_t air, cudaStream_t s) {
+    fill_air_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, air);
+    return cudaGetLastError();
+}
+cudaError_t launch_clear_dirty(Planes p, size_t n, cudaStream_t s) {
+    clear_dirty_kernel<<<grid_for(n / 16, 256), 256, 0, s>>>(reinterpret_cast<uint4*>(p.flg), n / 16);
+    return cudaGetLastError();
+}
+cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, const DevTables* T, void* out, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(DevStats), s);
+    if (e != cudaSuccess) return e;
+    stats_kernel<<<grid_for((size_t)rw * rh, 256), 256, 0, s>>>(p, W, x0, y0, rw, rh, T, (DevStats*)out);
+    return cudaGetLastError();
+}
+size_t dev_stats_bytes() { return sizeof(DevStats); }
+
+cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int zx, int zy, int zw, int zh, const DevTables* T, cudaStream_t s) {
+    dim3 grid((zw + TT_W - 1) / TT_W, (zh + TT_H - 1) / TT_H);
+    temperature_kernel<<<grid, 256, 0, s>>>(p.mat, p.tmp, scratch, W, zx, zy, zw, zh, T);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    copy_zone_i16_kernel<<<grid_for((size_t)zw * zh, 256), 256, 0, s>>>(scratch, p.tmp, W, zx, zy, zw, zh);
+    return cudaGetLastError();
+}
+
+}  // namespace fse

@@ -1,0 +1,479 @@
+// fse_capi.cu — the C ABI of include/fse.h on top of the sm_100a kernels.
+// Host logic only: validation, device memory, launch sequencing (the 4 colours x cell_iter schedule of
+// world::tick, world.cpp:1050-1077), error mapping.  No CPU fallback exists: every entry point needs the GPU.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fse_device.cuh"
+#include "fse_internal.hpp"
+
+namespace fse {
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+}  // namespace fse
+
+using namespace fse;
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) return fail(FSE_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" {
+
+FSE_API const char* fse_last_error(void) { return g_err.c_str(); }
+FSE_API const char* fse_version(void) { return "fse-b200 0.1 (sm_100a)"; }
+
+FSE_API int fse_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(fse_material);
+        case 1: return (int)sizeof(fse_interaction);
+        case 2: return (int)sizeof(fse_special_ids);
+        case 3: return (int)sizeof(fse_cell);
+        case 4: return (int)sizeof(fse_rect);
+        case 5: return (int)sizeof(fse_tick_args);
+        case 6: return (int)sizeof(fse_particle);
+        case 7: return (int)sizeof(fse_stats);
+    }
+    return -1;
+}
+
+FSE_API int fse_ctx_create(int device, fse_ctx** out) {
+    if (!out) return fail(FSE_EINVAL, "fse_ctx_create: out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(FSE_ECUDA, "fse_ctx_create: no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(FSE_EINVAL, "fse_ctx_create: device %d out of range [0,%d)", device, n);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(FSE_ECUDA, "fse_ctx_create: device is sm_%d%d; kernels are built for sm_100a only", prop.major, prop.minor);
+    fse_ctx* c = new fse_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaMalloc(&c->d_tabs, sizeof(DevTables)));
+    *out = c;
+    return FSE_OK;
+}
+
+FSE_API void fse_ctx_destroy(fse_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_tabs);
+    cudaFree(c->d_inter);
+    cudaFree(c->d_inter_off);
+    cudaFree(c->d_react);
+    delete c;
+}
+
+FSE_API int64_t fse_launch_count(fse_ctx* c) { return c ? c->launches.load() : 0; }
+
+FSE_API int fse_materials_set(fse_ctx* c, const fse_material* tbl, int n, const fse_special_ids* ids, const fse_interaction* inter,
+                              const int32_t* inter_offsets, const fse_interaction* react, const int32_t* react_offsets) {
+    if (!c || !tbl || !ids) return fail(FSE_EINVAL, "fse_materials_set: null argument");
+    if (n < 1 || n > FSE_MAX_MATERIALS) return fail(FSE_EINVAL, "fse_materials_set: %d materials (device plane is u8: 1..%d)", n, FSE_MAX_MATERIALS);
+    const int sid[6] = {ids->air, ids->fire, ids->water, ids->lava, ids->steam, ids->obsidian};
+    for (int i = 0; i < 6; i++)
+        if (sid[i] < 0 || sid[i] >= n) return fail(FSE_EINVAL, "fse_materials_set: special id #%d = %d out of range", i, sid[i]);
+    if (tbl[ids->air].physics != FSE_AIR) return fail(FSE_EINVAL, "fse_materials_set: ids.air must have physics AIR");
+    if (tbl[ids->fire].physics != FSE_PASSABLE) return fail(FSE_EINVAL, "fse_materials_set: ids.fire must be PASSABLE (gds.cpp:107)");
+    CK(cudaSetDevice(c->device));
+    DevTables& h = c->h_tabs;
+    memset(&h, 0, sizeof h);
+    h.n = n;
+    h.air = ids->air; h.fire = ids->fire; h.water = ids->water; h.lava = ids->lava; h.steam = ids->steam; h.obsidian = ids->obsidian;
+    int n_inter = inter_offsets ? inter_offsets[n * n] : 0;
+    int n_react = react_offsets ? react_offsets[n] : 0;
+    int max_reach = 0;
+    for (int i = 0; i < n; i++) {
+        const fse_material& m = tbl[i];
+        if (m.physics < 0 || m.physics > 5) return fail(FSE_EINVAL, "material %d: physics %d", i, m.physics);
+        if (m.physics == FSE_SAND && (m.slipperyness < 1 || m.slipperyness > 255))
+            return fail(FSE_EINVAL, "material %d: SAND needs 1 <= slipperyness <= 255 (reference divides by it, world.cpp:1656)", i);
+        if (m.iterations < 0) return fail(FSE_EINVAL, "material %d: negative iterations", i);
+        h.phys[i] = (uint8_t)m.physics;
+        h.iters[i] = (uint8_t)(m.iterations > 255 ? 255 : m.iterations);
+        int nr = react_offsets ? react_offsets[i + 1] - react_offsets[i] : 0;
+        h.mflags[i] = (uint8_t)((m.interact ? MF_INTERACT : 0) | ((m.react && nr > 0) ? MF_REACT : 0));
+        h.slip[i] = (uint8_t)(m.slipperyness < 0 ? 0 : (m.slipperyness > 255 ? 255 : m.slipperyness));
+        h.maxstab[i] = m.slipperyness >= 1 ? (uint8_t)(int)(8 / sqrt((double)m.slipperyness) + 1) : 0;  // world.cpp:1630
+        h.alpha[i] = m.alpha;
+        h.ckind[i] = m.color_kind;
+        h.jshift[i] = m.jitter_shift;
+        h.jrange[i] = m.jitter_range;
+        h.ctemp[i] = m.create_temp;
+        h.density[i] = m.density;
+        h.color[i] = m.color;
+        h.add_temp[i] = m.add_temp;
+        h.cond_self[i] = m.conduction_self;
+        h.cond_other[i] = m.conduction_other;
+        h.react_off[i] = react_offsets ? react_offsets[i] : 0;
+    }
+    h.react_off[n] = n_react;
+    for (int i = n + 1; i <= FSE_MAX_MATERIALS; i++) h.react_off[i] = n_react;
+    for (int k = 0; k < n_react; k++) {
+        if (react[k].data2 >= (uint32_t)n) return fail(FSE_EINVAL, "reaction %d: product %u out of range", k, react[k].data2);
+    }
+    for (int a = 0; a < n && inter_offsets; a++)
+        for (int b = 0; b < n; b++)
+            for (int k = inter_offsets[a * n + b]; k < inter_offsets[a * n + b + 1]; k++) {
+                const fse_interaction& in = inter[k];
+                if (in.type != FSE_INTERACT_TRANSFORM_MATERIAL && in.type != FSE_INTERACT_SPAWN_MATERIAL) continue;
+                if (in.data1 < 0 || in.data1 >= n) return fail(FSE_EINVAL, "interaction %d: product %d out of range", k, in.data1);
+                if (!tbl[a].interact) continue;  // dead list: never consulted
+                int reach = (int)in.data2 + (abs(in.ofs_x) > abs(in.ofs_y) ? abs(in.ofs_x) : abs(in.ofs_y));
+                if (reach > max_reach) max_reach = reach;
+            }
+    if (max_reach > FSE_MAX_REACH)
+        return fail(FSE_EINVAL, "fse_materials_set: interaction reach %d exceeds FSE_MAX_REACH=%d (|ofs|+radius)", max_reach, FSE_MAX_REACH);
+    cudaFree(c->d_inter); c->d_inter = nullptr;
+    cudaFree(c->d_inter_off); c->d_inter_off = nullptr;
+    cudaFree(c->d_react); c->d_react = nullptr;
+    CK(cudaMalloc(&c->d_inter_off, sizeof(int32_t) * ((size_t)n * n + 1)));
+    if (inter_offsets) {
+        CK(cudaMemcpy(c->d_inter_off, inter_offsets, sizeof(int32_t) * ((size_t)n * n + 1), cudaMemcpyHostToDevice));
+    } else {
+        CK(cudaMemset(c->d_inter_off, 0, sizeof(int32_t) * ((size_t)n * n + 1)));
+    }
+    CK(cudaMalloc(&c->d_inter, sizeof(fse_interaction) * (size_t)(n_inter > 0 ? n_inter : 1)));
+    if (n_inter > 0) CK(cudaMemcpy(c->d_inter, inter, sizeof(fse_interaction) * n_inter, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_react, sizeof(fse_interaction) * (size_t)(n_react > 0 ? n_react : 1)));
+    if (n_react > 0) CK(cudaMemcpy(c->d_react, react, sizeof(fse_interaction) * n_react, cudaMemcpyHostToDevice));
+    h.react = c->d_react;
+    h.inter_off = c->d_inter_off;
+    h.inter = c->d_inter;
+    CK(cudaMemcpy(c->d_tabs, &h, sizeof h, cudaMemcpyHostToDevice));
+    c->has_materials = true;
+    c->max_reach = max_reach;
+    return FSE_OK;
+}
+
+// ---- world ---------------------------------------------------------------------------------------------
+static void free_world(fse_world* w) {
+    cudaFree(w->p.mat); cudaFree(w->p.flg); cudaFree(w->p.stl); cudaFree(w->p.tmp); cudaFree(w->p.col); cudaFree(w->p.fl); cudaFree(w->p.fd);
+    cudaFree(w->tmp_scratch); cudaFree(w->pbuf); cudaFree(w->pcount); cudaFree(w->d_stats); cudaFree(w->d_stage);
+    if (w->h_stats) cudaFreeHost(w->h_stats);
+    for (auto& ev : w->kt_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    if (w->ev0) cudaEventDestroy(w->ev0);
+    if (w->ev1) cudaEventDestroy(w->ev1);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+FSE_API int fse_world_create(fse_ctx* c, int32_t width, int32_t height, fse_world** out) {
+    if (!c || !out) return fail(FSE_EINVAL, "fse_world_create: null argument");
+    if (!c->has_materials) return fail(FSE_ESTATE, "fse_world_create: call fse_materials_set first (materials_init/push, game.lua:65-66)");
+    if (width < 3 * CHUNK || height < 3 * CHUNK || width % 16 || width > (1 << 18) || height > (1 << 18))
+        return fail(FSE_EINVAL, "fse_world_create: %dx%d (need >= %d, width multiple of 16, <= 262144)", width, height, 3 * CHUNK);
+    CK(cudaSetDevice(c->device));
+    fse_world* w = new fse_world();
+    w->ctx = c;
+    w->W = width;
+    w->H = height;
+    const size_t n = (size_t)width * height;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void**)&w->p.mat, n); A((void**)&w->p.flg, n); A((void**)&w->p.stl, n); A((void**)&w->p.tmp, n * 2); A((void**)&w->p.col, n * 4);
+    A((void**)&w->p.fl, n * 4); A((void**)&w->p.fd, n * 4); A((void**)&w->tmp_scratch, n * 2);
+    w->pcap = 1u << 20;
+    A((void**)&w->pbuf, sizeof(fse_particle) * (size_t)w->pcap);
+    A((void**)&w->pcount, 64);
+    A((void**)&w->d_stats, dev_stats_bytes());
+    if (e == cudaSuccess) e = cudaMallocHost(&w->h_stats, dev_stats_bytes());
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w->pcount, 0, 64, w->stream);
+    if (e == cudaSuccess) e = launch_fill_air(w->p, n, (uint8_t)c->h_tabs.air, w->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+    if (e != cudaSuccess) {
+        free_world(w);
+        return fail(e == cudaErrorMemoryAllocation ? FSE_ENOMEM : FSE_ECUDA, "fse_world_create(%d,%d): %s", width, height, cudaGetErrorString(e));
+    }
+    c->launches += 1;
+    *out = w;
+    return FSE_OK;
+}
+
+FSE_API void fse_world_destroy(fse_world* w) {
+    if (!w) return;
+    cudaSetDevice(w->ctx->device);
+    cudaStreamSynchronize(w->stream);
+    free_world(w);
+}
+
+FSE_API int fse_sync(fse_world* w) {
+    if (!w) return fail(FSE_EINVAL, "fse_sync: null world");
+    CK(cudaStreamSynchronize(w->stream));
+    return FSE_OK;
+}
+
+static int check_rect(fse_world* w, int x, int y, int rw, int rh, const char* who) {
+    if (rw <= 0 || rh <= 0 || x < 0 || y < 0 || (int64_t)x + rw > w->W || (int64_t)y + rh > w->H)
+        return fail(FSE_EINVAL, "%s: rect (%d,%d,%d,%d) outside %dx%d world", who, x, y, rw, rh, w->W, w->H);
+    return FSE_OK;
+}
+
+static int ensure_stage(fse_world* w, size_t cells) {
+    if (w->stage_cells >= cells) return FSE_OK;
+    cudaFree(w->d_stage);
+    w->d_stage = nullptr;
+    w->stage_cells = 0;
+    CK(cudaMalloc(&w->d_stage, cells * sizeof(fse_cell)));
+    w->stage_cells = cells;
+    return FSE_OK;
+}
+
+static const size_t STAGE_MAX_CELLS = (size_t)16 << 20;  // 320 MB of AoS staging at most
+
+FSE_API int fse_write_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, const fse_cell* cells) {
+    if (!w || !cells) return fail(FSE_EINVAL, "fse_write_rect: null argument");
+    if (int r = check_rect(w, x, y, rw, rh, "fse_write_rect")) return r;
+    CK(cudaSetDevice(w->ctx->device));
+    const int nmat = w->ctx->h_tabs.n;
+    int band = (int)(STAGE_MAX_CELLS / (size_t)rw);
+    if (band < 1) band = 1;
+    if (band > rh) band = rh;
+    if (int r = ensure_stage(w, (size_t)band * rw)) return r;
+    for (int yy = 0; yy < rh; yy += band) {
+        int hb = rh - yy < band ? rh - yy : band;
+        const fse_cell* src = cells + (size_t)yy * rw;
+        for (size_t i = 0; i < (size_t)hb * rw; i += 4099)  // cheap sampled validation of material ids
+            if (src[i].mat >= nmat) return fail(FSE_EINVAL, "fse_write_rect: cell material %u >= %d", src[i].mat, nmat);
+        CK(cudaMemcpyAsync(w->d_stage, src, (size_t)hb * rw * sizeof(fse_cell), cudaMemcpyHostToDevice, w->stream));
+        CK(launch_write_rect(w->p, w->W, x, y + yy, rw, hb, w->d_stage, w->stream));
+        w->ctx->launches += 1;
+        if (yy + band < rh) CK(cudaStreamSynchronize(w->stream));  // the staging buffer is reused
+    }
+    return FSE_OK;
+}
+
+FSE_API int fse_read_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, fse_cell* cells) {
+    if (!w || !cells) return fail(FSE_EINVAL, "fse_read_rect: null argument");
+    if (int r = check_rect(w, x, y, rw, rh, "fse_read_rect")) return r;
+    CK(cudaSetDevice(w->ctx->device));
+    int band = (int)(STAGE_MAX_CELLS / (size_t)rw);
+    if (band < 1) band = 1;
+    if (band > rh) band = rh;
+    if (int r = ensure_stage(w, (size_t)band * rw)) return r;
+    for (int yy = 0; yy < rh; yy += band) {
+        int hb = rh - yy < band ? rh - yy : band;
+        CK(launch_read_rect(w->p, w->W, x, y + yy, rw, hb, w->d_stage, w->stream));
+        w->ctx->launches += 1;
+        CK(cudaMemcpyAsync(cells + (size_t)yy * rw, w->d_stage, (size_t)hb * rw * sizeof(fse_cell), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaStreamSynchronize(w->stream));
+    }
+    return FSE_OK;
+}
+
+FSE_API int fse_clear_dirty(fse_world* w) {
+    if (!w) return fail(FSE_EINVAL, "fse_clear_dirty: null world");
+    CK(cudaSetDevice(w->ctx->device));
+    CK(launch_clear_dirty(w->p, (size_t)w->W * w->H, w->stream));
+    w->ctx->launches += 1;
+    return FSE_OK;
+}
+
+FSE_API int fse_stats_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, fse_stats* out) {
+    if (!w || !out) return fail(FSE_EINVAL, "fse_stats_rect: null argument");
+    if (int r = check_rect(w, x, y, rw, rh, "fse_stats_rect")) return r;
+    CK(cudaSetDevice(w->ctx->device));
+    CK(launch_stats(w->p, w->W, x, y, rw, rh, w->ctx->d_tabs, w->d_stats, w->stream));
+    w->ctx->launches += 1;
+    CK(cudaMemcpyAsync(w->h_stats, w->d_stats, dev_stats_bytes(), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    static_assert(sizeof(fse_stats) == 8 + 8 * FSE_MAX_MATERIALS * 2 + 16, "fse_stats layout");
+    memcpy(out, w->h_stats, sizeof(fse_stats));  // DevStats and fse_stats share one layout
+    return FSE_OK;
+}
+
+// ---- the tick: 4 colours x cell_iter (world.cpp:1050-1077) ----------------------------------------------------
+static int check_zone(fse_world* w, const fse_rect& z, const char* who) {
+    if (z.w <= 0 || z.h <= 0 || z.w % CHUNK || z.h % CHUNK)
+        return fail(FSE_EINVAL, "%s: tick zone %dx%d must be a positive multiple of %d (chunk tasks are whole chunks, world.cpp:1073-1086)", who,
+                    z.w, z.h, CHUNK);
+    if (z.x % 16 || z.x < 16 || z.y < 16 || z.x + z.w + 16 > w->W || z.y + z.h + 16 > w->H)
+        return fail(FSE_EINVAL, "%s: tick zone (%d,%d,%d,%d) needs x %% 16 == 0 and a >=16-cell margin inside the %dx%d world", who, z.x, z.y, z.w,
+                    z.h, w->W, w->H);
+    return FSE_OK;
+}
+
+FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
+    if (!w || !a) return fail(FSE_EINVAL, "fse_tick: null argument");
+    if (a->cell_iter < 0 || a->cell_iter > 4) return fail(FSE_EINVAL, "fse_tick: cell_iter %d (0..4; particle ids carry 2 bits)", a->cell_iter);
+    if (int r = check_zone(w, a->tick_zone, "fse_tick")) return r;
+    CK(cudaSetDevice(w->ctx->device));
+    const fse_rect z = a->tick_zone;
+    const int nx = z.w / CHUNK, ny = z.h / CHUNK;
+    for (int iter = 0; iter < a->cell_iter; iter++) {
+        for (int tk = 0; tk < 4; tk++) {
+            const int ofx = tk % 2;              // 0 1 0 1   (world.cpp:1059)
+            const int ofy = 1 - ((tk % 4) / 2);  // 1 1 0 0   (world.cpp:1060)
+            TickParams P;
+            P.p = w->p;
+            P.W = w->W;
+            P.H = w->H;
+            P.x0 = z.x + ofx * CHUNK;
+            P.y0 = z.y + ofy * CHUNK;
+            P.ncx = (nx - ofx + 1) / 2;
+            P.ncy = (ny - ofy + 1) / 2;
+            P.iter = iter;
+            P.rkey = rng_key(a->seed, a->tick, (uint32_t)iter);
+            P.tick = a->tick;
+            P.pbuf = w->pbuf;
+            P.pcount = w->pcount;
+            P.pcap = w->pcap;
+            P.tabs = w->ctx->d_tabs;
+            P.chunk_list = nullptr;
+            const int n_chunks = P.ncx * P.ncy;
+            if (n_chunks <= 0) continue;
+            std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+            if (w->kt_enabled) {
+                if (w->kt_used < w->kt_events.size()) {
+                    ev = w->kt_events[w->kt_used];
+                } else {
+                    CK(cudaEventCreate(&ev.first));
+                    CK(cudaEventCreate(&ev.second));
+                    w->kt_events.push_back(ev);
+                }
+                w->kt_used++;
+                CK(cudaEventRecord(ev.first, w->stream));
+            }
+            CK(launch_tick_phase(P, n_chunks, w->stream));
+            if (w->kt_enabled) CK(cudaEventRecord(ev.second, w->stream));
+            w->ctx->launches += 1;
+        }
+    }
+    w->ticks++;
+    return FSE_OK;
+}
+
+FSE_API int fse_tick_temperature(fse_world* w, const fse_rect* z) {
+    if (!w || !z) return fail(FSE_EINVAL, "fse_tick_temperature: null argument");
+    if (z->w <= 0 || z->h <= 0 || z->x < 1 || z->y < 1 || z->x + z->w + 1 > w->W || z->y + z->h + 1 > w->H)
+        return fail(FSE_EINVAL, "fse_tick_temperature: zone (%d,%d,%d,%d) needs a 1-cell margin inside the world", z->x, z->y, z->w, z->h);
+    CK(cudaSetDevice(w->ctx->device));
+    CK(launch_temperature(w->p, w->tmp_scratch, w->W, z->x, z->y, z->w, z->h, w->ctx->d_tabs, w->stream));
+    w->ctx->launches += 2;
+    return FSE_OK;
+}
+
+// ---- particles (container part; the integrator lives in fse_particles.cu) -------------------------------
+FSE_API int fse_particles_count(fse_world* w, int64_t* out) {
+    if (!w || !out) return fail(FSE_EINVAL, "fse_particles_count: null argument");
+    CK(cudaSetDevice(w->ctx->device));
+    unsigned int n = 0;
+    CK(cudaMemcpyAsync(&n, w->pcount, sizeof n, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    if (n > w->pcap) return fail(FSE_ESTATE, "particle pool overflow: %u spawned, capacity %u (fse_particles_reserve)", n, w->pcap);
+    *out = n;
+    return FSE_OK;
+}
+
+FSE_API int fse_particles_read(fse_world* w, fse_particle* out, int64_t cap, int64_t* n_out) {
+    if (!w || !n_out) return fail(FSE_EINVAL, "fse_particles_read: null argument");
+    int64_t n = 0;
+    if (int r = fse_particles_count(w, &n)) return r;
+    int64_t m = n < cap ? n : cap;
+    if (m > 0 && out) CK(cudaMemcpy(out, w->pbuf, sizeof(fse_particle) * (size_t)m, cudaMemcpyDeviceToHost));
+    *n_out = m;
+    return FSE_OK;
+}
+
+FSE_API int fse_particles_clear(fse_world* w) {
+    if (!w) return fail(FSE_EINVAL, "fse_particles_clear: null world");
+    CK(cudaSetDevice(w->ctx->device));
+    CK(cudaMemsetAsync(w->pcount, 0, sizeof(unsigned int), w->stream));
+    return FSE_OK;
+}
+
+FSE_API int fse_particles_reserve(fse_world* w, int64_t cap) {
+    if (!w || cap < 1 || cap > ((int64_t)1 << 30)) return fail(FSE_EINVAL, "fse_particles_reserve: bad capacity");
+    CK(cudaSetDevice(w->ctx->device));
+    int64_t n = 0;
+    if (int r = fse_particles_count(w, &n)) return r;
+    if (cap < n) return fail(FSE_EINVAL, "fse_particles_reserve: %lld live particles", (long long)n);
+    fse_particle* nb = nullptr;
+    CK(cudaMalloc(&nb, sizeof(fse_particle) * (size_t)cap));
+    if (n) CK(cudaMemcpy(nb, w->pbuf, sizeof(fse_particle) * (size_t)n, cudaMemcpyDeviceToDevice));
+    cudaFree(w->pbuf);
+    w->pbuf = nb;
+    w->pcap = (unsigned int)cap;
+    return FSE_OK;
+}
+
+FSE_API int fse_particles_add(fse_world* w, const fse_particle* p, int32_t n) {
+    if (!w || (!p && n > 0) || n < 0) return fail(FSE_EINVAL, "fse_particles_add: bad argument");
+    if (n == 0) return FSE_OK;
+    CK(cudaSetDevice(w->ctx->device));
+    int64_t have = 0;
+    if (int r = fse_particles_count(w, &have)) return r;
+    if (have + n > (int64_t)w->pcap) return fail(FSE_ENOMEM, "fse_particles_add: pool capacity %u exceeded", w->pcap);
+    std::vector<fse_particle> tmp(p, p + n);
+    for (int i = 0; i < n; i++) {
+        if (tmp[i].tile.mat >= w->ctx->h_tabs.n) return fail(FSE_EINVAL, "fse_particles_add: particle %d material out of range", i);
+        if (tmp[i].id == 0) tmp[i].id = (1ULL << 63) | (w->next_user_particle++);
+    }
+    CK(cudaMemcpy(w->pbuf + have, tmp.data(), sizeof(fse_particle) * (size_t)n, cudaMemcpyHostToDevice));
+    unsigned int total = (unsigned int)(have + n);
+    CK(cudaMemcpy(w->pcount, &total, sizeof total, cudaMemcpyHostToDevice));
+    return FSE_OK;
+}
+
+// ---- measurement ----------------------------------------------------------------------------------------
+FSE_API int fse_timer_start(fse_world* w) {
+    if (!w) return fail(FSE_EINVAL, "fse_timer_start: null world");
+    CK(cudaSetDevice(w->ctx->device));
+    CK(cudaEventRecord(w->ev0, w->stream));
+    return FSE_OK;
+}
+
+FSE_API int fse_timer_stop(fse_world* w, float* ms) {
+    if (!w || !ms) return fail(FSE_EINVAL, "fse_timer_stop: null argument");
+    CK(cudaSetDevice(w->ctx->device));
+    CK(cudaEventRecord(w->ev1, w->stream));
+    CK(cudaEventSynchronize(w->ev1));
+    CK(cudaEventElapsedTime(ms, w->ev0, w->ev1));
+    return FSE_OK;
+}
+
+FSE_API int fse_kernel_timing_enable(fse_world* w, int enable) {
+    if (!w) return fail(FSE_EINVAL, "fse_kernel_timing_enable: null world");
+    w->kt_enabled = enable != 0;
+    w->kt_used = 0;
+    return FSE_OK;
+}
+
+FSE_API int fse_kernel_timing_read(fse_world* w, double* total_ms, int64_t* launches) {
+    if (!w || !total_ms || !launches) return fail(FSE_EINVAL, "fse_kernel_timing_read: null argument");
+    CK(cudaSetDevice(w->ctx->device));
+    CK(cudaStreamSynchronize(w->stream));
+    double tot = 0;
+    for (size_t i = 0; i < w->kt_used; i++) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, w->kt_events[i].first, w->kt_events[i].second));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (int64_t)w->kt_used;
+    w->kt_used = 0;
+    return FSE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// fse_device.cuh — device-side data layout shared by the fse kernels (sm_100a).
+//
+// World state lives in HBM as structure-of-arrays planes, row-major x + y*W (y grows downward,
+// as in the reference: world.cpp:1001, gravity +y world.cpp:147):
+//   mat  u8   material id                         (MaterialInstance::mat->id, gds.hpp:209-210)
+//   flg  u8   bit0 moved (gds.hpp:214)  bit1 dirty (world::dirty[], world.hpp:131)
+//             bit7 tickVisited — only ever set in shared memory, never stored to HBM
+//   stl  u8   settleCount                         (gds.hpp:217)
+//   tmp  i16  temperature                         (gds.hpp:213)
+//   col  u32  color                               (gds.hpp:212)
+//   fl   f32  fluidAmount                         (gds.hpp:215)
+//   fd   f32  fluidAmountDiff                     (gds.hpp:216)
+// = 17 bytes per cell (the reference's AoS MaterialInstance is 40 bytes).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/fse.h"
+
+namespace fse {
+
+constexpr int CHUNK = 128;
+constexpr uint8_t F_MOVED = 0x01;
+constexpr uint8_t F_DIRTY = 0x02;
+constexpr uint8_t F_VISITED = 0x80;
+
+enum { P_AIR = 0, P_SOLID = 1, P_SAND = 2, P_SOUP = 3, P_GAS = 4, P_PASSABLE = 5 };
+
+// material flag bits in DevTables::mflags
+constexpr uint8_t MF_INTERACT = 0x01;
+constexpr uint8_t MF_REACT = 0x02;
+
+// RNG draw sites — same numbering as the reference-derived oracle (oracle/fse_oracle.hpp)
+enum Slot : uint32_t {
+    S_FIRE_EMBER = 1, S_FIRE_EMBER_VX = 2, S_FIRE_EMBER_VY = 3, S_FIRE_DIE = 4, S_FIRE_IGNITE0 = 5, S_FIRE_DIE_ALONE = 31,
+    S_SAND_HESITATE = 32, S_SAND_PART_VX = 33, S_SAND_PART_VY = 34, S_SAND_MOVED = 35, S_SAND_TX_SELF = 36, S_SAND_TX_L = 37,
+    S_SAND_TX_R = 38, S_SOUP_PART0 = 40, S_SOUP_SWAP_DOWN = 56, S_SOUP_SWAP_UP = 57, S_GAS1 = 58, S_SAND2_UNSTICK = 59,
+    S_SAND2_SHOULD = 60, S_SAND2_TX_SELF = 61, S_SAND2_TX_OTHER = 62, S_SAND2_LR = 63, S_SAND2_RESTICK = 64, S_GAS2 = 65,
+    S_GAS3 = 66, S_STEAM = 67, S_CREATE_COLOR = 68, S_PROBE_X = 69, S_PROBE_Y = 70, S_BRIDGE_VX = 71, S_BRIDGE_VY = 72,
+};
+
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t v) {
+    v ^= v >> 16; v *= 0x7feb352dU; v ^= v >> 15; v *= 0x846ca68bU; v ^= v >> 16;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t rng_key(uint32_t seed, uint32_t tick, uint32_t iter) {
+    return mix32(seed ^ mix32(tick * 0x9E3779B9U + iter * 0x85EBCA77U + 0x1234567U));
+}
+__host__ __device__ __forceinline__ uint32_t rng_cell(uint32_t key, int x, int y) {
+    return mix32(key ^ ((uint32_t)y * 0x9E3779B1U + (uint32_t)x));
+}
+__host__ __device__ __forceinline__ uint32_t rng_draw(uint32_t cellbase, uint32_t slot) {
+    return mix32(cellbase + slot * 0x9E3779B9U) >> 1;
+}
+__host__ __device__ __forceinline__ uint32_t pos_hash(int x, int y) {
+    return mix32((uint32_t)x * 0x9E3779B1U ^ mix32((uint32_t)y + 0x7F4A7C15U));
+}
+
+// Flattened material table in device memory (one per context).
+struct DevTables {
+    int n;
+    int air, fire, water, lava, steam, obsidian;
+    uint8_t phys[FSE_MAX_MATERIALS];
+    uint8_t iters[FSE_MAX_MATERIALS];    // Material::iterations clamped to 255
+    uint8_t mflags[FSE_MAX_MATERIALS];
+    uint8_t slip[FSE_MAX_MATERIALS];     // Material::slipperyness ("1 to ~127", world.cpp:1614)
+    uint8_t maxstab[FSE_MAX_MATERIALS];  // int(8 / sqrt(slipperyness) + 1), world.cpp:1630
+    uint8_t alpha[FSE_MAX_MATERIALS];
+    uint8_t ckind[FSE_MAX_MATERIALS], jshift[FSE_MAX_MATERIALS], jrange[FSE_MAX_MATERIALS];
+    int16_t ctemp[FSE_MAX_MATERIALS];
+    float density[FSE_MAX_MATERIALS];
+    uint32_t color[FSE_MAX_MATERIALS];
+    uint32_t add_temp[FSE_MAX_MATERIALS];
+    float cond_self[FSE_MAX_MATERIALS];
+    float cond_other[FSE_MAX_MATERIALS];
+    int32_t react_off[FSE_MAX_MATERIALS + 1];
+    const fse_interaction* react;   // device
+    const int32_t* inter_off;       // device, n*n+1
+    const fse_interaction* inter;   // device
+};
+
+struct Planes {
+    uint8_t* mat;
+    uint8_t* flg;
+    uint8_t* stl;
+    int16_t* tmp;
+    uint32_t* col;
+    float* fl;
+    float* fd;
+};
+
+// Arguments of one colour phase of one iteration (world.cpp:1057-1077).
+struct TickParams {
+    Planes p;
+    int W, H;
+    int x0, y0;        // first chunk origin of this colour
+    int ncx, ncy;      // chunks of this colour along x / y (stride 2*CHUNK)
+    int iter;
+    uint32_t rkey;     // rng_key(seed, tick, iter)
+    uint32_t tick;
+    fse_particle* pbuf;
+    unsigned int* pcount;
+    unsigned int pcap;
+    const DevTables* tabs;
+    const int* chunk_list;  // optional compacted list of (cxi | cyi << 16) (active-chunk pass); null = all
+};
+
+}  // namespace fse

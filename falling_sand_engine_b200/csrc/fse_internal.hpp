@@ -1,0 +1,64 @@
+// fse_internal.hpp — host-side state behind the opaque handles of include/fse.h.
+#pragma once
+#include <atomic>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "fse_device.cuh"
+
+struct fse_ctx {
+    int device = 0;
+    int sm_count = 0;
+    fse::DevTables h_tabs{};
+    fse::DevTables* d_tabs = nullptr;
+    fse_interaction* d_inter = nullptr;
+    int32_t* d_inter_off = nullptr;
+    fse_interaction* d_react = nullptr;
+    bool has_materials = false;
+    int max_reach = 0;
+    std::atomic<int64_t> launches{0};
+};
+
+struct fse_world {
+    fse_ctx* ctx = nullptr;
+    int W = 0, H = 0;
+    fse::Planes p{};
+    int16_t* tmp_scratch = nullptr;
+    cudaStream_t stream = nullptr;
+    // loose particles (world::cells)
+    fse_particle* pbuf = nullptr;
+    unsigned int* pcount = nullptr;  // [0] live count, [1..] scratch counters
+    unsigned int pcap = 0;
+    uint64_t next_user_particle = 1;
+    // particle settle scratch (fse_particles.cu)
+    void* part_scratch = nullptr;
+    size_t part_scratch_bytes = 0;
+    // stats / staging
+    void* d_stats = nullptr;
+    void* h_stats = nullptr;
+    fse_cell* d_stage = nullptr;
+    size_t stage_cells = 0;
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool kt_enabled = false;
+    size_t kt_used = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kt_events;
+    uint64_t ticks = 0;
+};
+
+namespace fse {
+extern thread_local std::string g_err;
+int fail(int code, const char* fmt, ...);
+
+size_t tick_smem_bytes();
+cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream);
+
+cudaError_t launch_write_rect(Planes p, int W, int x0, int y0, int rw, int rh, const fse_cell* src, cudaStream_t s);
+cudaError_t launch_read_rect(Planes p, int W, int x0, int y0, int rw, int rh, fse_cell* dst, cudaStream_t s);
+cudaError_t launch_fill_air(Planes p, size_t n, uint8_t air, cudaStream_t s);
+cudaError_t launch_clear_dirty(Planes p, size_t n, cudaStream_t s);
+cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, const DevTables* T, void* out, cudaStream_t s);
+size_t dev_stats_bytes();
+cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int zx, int zy, int zw, int zh, const DevTables* T, cudaStream_t s);
+}  // namespace fse

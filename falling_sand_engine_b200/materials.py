@@ -1,0 +1,158 @@
+"""The stock material table: InitMaterials()/RegisterMaterial()/PushMaterials()
+(source/engine/game_datastruct.cpp:69-300) flattened into the arguments of fse_materials_set.
+
+The reference draws its ten `Mat_0..9` materials and their interactions from libc rand() seeded with
+time(NULL) (game_utils/rng.cpp:9); here they come from a counter generator on `seed`, so a table is
+reproducible.  Texture-sampled colours (TilesCreate*, gds.cpp:344-470) become POSITIONAL colours.
+"""
+import ctypes as C
+
+from . import types as T
+
+NAMES = ["GENERIC_AIR", "GENERIC_SOLID", "GENERIC_SAND", "GENERIC_LIQUID", "GENERIC_GAS", "GENERIC_PASSABLE", "GENERIC_OBJECT",
+         "STONE", "GRASS", "DIRT", "SMOOTH_STONE", "COBBLE_STONE", "SMOOTH_DIRT", "COBBLE_DIRT", "SOFT_DIRT", "WATER", "LAVA",
+         "CLOUD", "GOLD_ORE", "GOLD_MOLTEN", "GOLD_SOLID", "IRON_ORE", "OBSIDIAN", "STEAM", "SOFT_DIRT_SAND", "FIRE",
+         "FLAT_COBBLE_STONE", "FLAT_COBBLE_DIRT"]
+ID = {n: i for i, n in enumerate(NAMES)}
+
+_M = 0xFFFFFFFF
+
+
+def _mix32(v):
+    v &= _M
+    v ^= v >> 16
+    v = (v * 0x7FEB352D) & _M
+    v ^= v >> 15
+    v = (v * 0x846CA68B) & _M
+    v ^= v >> 16
+    return v
+
+
+class _Rand:
+    def __init__(self, seed):
+        self.st = _mix32(seed ^ 0xA5A5A5A5)
+
+    def __call__(self):
+        self.st = _mix32(self.st + 0x9E3779B9)
+        return self.st >> 1
+
+
+def _mat(phys, slip, alpha, dens, iters, emit=0, emit_color=0, color=0xFFFFFFFF, kind=T.COLOR_FIXED, jshift=0, jrange=0, ctemp=0):
+    m = T.Material()
+    m.physics, m.slipperyness, m.alpha, m.density, m.iterations = phys, slip, alpha, dens, iters
+    m.emit, m.emit_color, m.color, m.color_kind = emit, emit_color, color, kind
+    m.jitter_shift, m.jitter_range, m.create_temp = jshift, jrange, ctemp
+    m.conduction_self = m.conduction_other = 1.0
+    return m
+
+
+def default_materials(seed=1337):
+    """InitMaterials() (gds.cpp:117-280) -> MaterialTable."""
+    FIX, JIT, POS = T.COLOR_FIXED, T.COLOR_JITTER, T.COLOR_POSITIONAL
+    A, SO, SA, LI, GA, PA = T.AIR, T.SOLID, T.SAND, T.SOUP, T.GAS, T.PASSABLE
+    mats = [
+        _mat(A, 0, 255, 0, 0, 16, 0, 0x000000),            # 0 GENERIC_AIR       gds.cpp:72
+        _mat(SO, 0, 255, 1, 0),                            # 1 GENERIC_SOLID
+        _mat(SA, 20, 255, 10, 2),                          # 2 GENERIC_SAND
+        _mat(LI, 0, 255, 1.5, 3),                          # 3 GENERIC_LIQUID
+        _mat(GA, 0, 255, -1, 1),                           # 4 GENERIC_GAS
+        _mat(PA, 0, 255, 0, 0),                            # 5 GENERIC_PASSABLE
+        _mat(T.OBJECT, 0, 255, 1000.0, 0),                 # 6 GENERIC_OBJECT
+        _mat(SO, 0, 255, 1, 0, color=0x808080, kind=POS),  # 7 STONE             gds.cpp:81
+        _mat(SA, 20, 255, 12, 1, color=(40 << 16) + (120 << 8) + 20, kind=JIT, jshift=8, jrange=20),   # 8 GRASS gds.cpp:358
+        _mat(SA, 8, 255, 15, 1, color=(60 << 16) + (40 << 8) + 20, kind=JIT, jshift=16, jrange=10),    # 9 DIRT  gds.cpp:365
+        _mat(SO, 0, 255, 1, 0, color=0x888888, kind=POS),  # 10 SMOOTH_STONE
+        _mat(SO, 0, 255, 1, 0, color=0x6B6B6B, kind=POS),  # 11 COBBLE_STONE
+        _mat(SO, 0, 255, 1, 0, color=0x6B4A2F, kind=POS),  # 12 SMOOTH_DIRT
+        _mat(SO, 0, 255, 1, 0, color=0x5A3D26, kind=POS),  # 13 COBBLE_DIRT
+        _mat(SO, 0, 255, 15, 2, color=0x7A5533, kind=POS),  # 14 SOFT_DIRT
+        _mat(LI, 0, 0x80, 1.5, 6, 40, 0x3000AFB5, 0x00B69F, ctemp=-1023),  # 15 WATER  gds.cpp:92,427
+        _mat(LI, 0, 0xC0, 2, 1, 40, 0xFFFF6900, 0xFF7C00, ctemp=1024),     # 16 LAVA   gds.cpp:93,433
+        _mat(SO, 0, 127, 1, 0, color=0xF0F0F0, kind=POS),  # 17 CLOUD
+        _mat(SA, 20, 255, 20, 2, 8, 0x804000, 0xD4AF37, POS),      # 18 GOLD_ORE
+        _mat(LI, 0, 255, 20, 2, 8, 0x6FFF9B40, 0xFFC84A, POS),     # 19 GOLD_MOLTEN
+        _mat(SO, 0, 255, 20, 2, 8, 0, 0xFFD700, POS),              # 20 GOLD_SOLID
+        _mat(SA, 20, 255, 20, 2, 8, 0x7F442F, 0x8A5A44, POS),      # 21 IRON_ORE
+        _mat(SO, 0, 255, 1, 0, color=0x2A1A3A, kind=POS),  # 22 OBSIDIAN
+        _mat(GA, 0, 255, -1, 1, color=0x666666),           # 23 STEAM            gds.cpp:475
+        _mat(SA, 8, 255, 15, 2),                           # 24 SOFT_DIRT_SAND
+        _mat(PA, 0, 255, 20, 1, color=(255 << 16) + (100 << 8) + 50, kind=JIT, jshift=8, jrange=50),   # 25 FIRE gds.cpp:477
+        _mat(SO, 0, 255, 1, 0, color=0x707070, kind=POS),  # 26 FLAT_COBBLE_STONE
+        _mat(SO, 0, 255, 1, 0, color=0x5E4128, kind=POS),  # 27 FLAT_COBBLE_DIRT
+    ]
+    # gds.cpp:124-141
+    mats[ID["GENERIC_AIR"]].conduction_self = mats[ID["GENERIC_AIR"]].conduction_other = 0.8
+    mats[ID["LAVA"]].conduction_self, mats[ID["LAVA"]].conduction_other, mats[ID["LAVA"]].add_temp = 0.5, 0.7, 2
+    mats[ID["COBBLE_STONE"]].conduction_self, mats[ID["COBBLE_STONE"]].conduction_other = 0.01, 0.4
+
+    rnd = _Rand(seed)
+    rand0 = len(mats)
+    for _ in range(10):  # gds.cpp:172-191
+        rgb = rnd() % 255
+        rgb = (rgb << 8) + rnd() % 255
+        rgb = (rgb << 8) + rnd() % 255
+        typ = (SA if rnd() % 2 == 0 else GA) if rnd() % 2 == 0 else LI
+        base = {SA: 5, LI: 4, GA: 3}[typ]
+        dens = C.c_float(base + (rnd() % 1000) / 1000.0).value
+        alpha = 255 if typ == SA else rnd() % 192 + 63
+        mats.append(_mat(typ, 10, alpha, dens, rnd() % 4 + 1, color=rgb))
+    # gds.cpp:263-269 scriptable test materials (ids 38..40)
+    mats.append(_mat(SA, 20, 255, 10, 2, color=(220 << 16) + (155 << 8) + 100, kind=JIT, jshift=8, jrange=30))
+    mats.append(_mat(SA, 20, 255, 10, 2, color=0xDCB464, kind=POS))
+    mats.append(_mat(LI, 0, 255, 1.5, 4, color=0x0000FF))
+    n = len(mats)
+
+    pair = {}
+    for i in range(10):  # gds.cpp:207-239
+        mid = rand0 + i
+        for _ in range(rnd() % 3 + 1):
+            while True:
+                imat = rand0 + rnd() % 10
+                if imat != mid:
+                    ty = rnd() % 2 + 1
+                    prod = rand0 + rnd() % 10
+                    rad = rnd() % 4
+                    ox = rnd() % 5 - 2
+                    oy = rnd() % 5 - 2
+                    pair.setdefault((mid, imat), []).append(T.Interaction(ty, prod, 0, rad, ox, oy))
+                    break
+    flat, offs = [], [0]
+    for a in range(n):
+        for b in range(n):
+            flat.extend(pair.get((a, b), []))
+            offs.append(len(flat))
+    rx = {  # gds.cpp:246-260
+        ID["LAVA"]: [T.Interaction(T.REACT_TEMPERATURE_BELOW, 512, 0, ID["OBSIDIAN"], 0, 0)],
+        ID["WATER"]: [T.Interaction(T.REACT_TEMPERATURE_ABOVE, 128, 0, ID["STEAM"], 0, 0)],
+        ID["GOLD_ORE"]: [T.Interaction(T.REACT_TEMPERATURE_ABOVE, 512, 0, ID["GOLD_MOLTEN"], 0, 0)],
+        ID["GOLD_MOLTEN"]: [T.Interaction(T.REACT_TEMPERATURE_BELOW, 128, 0, ID["GOLD_SOLID"], 0, 0)],
+    }
+    rflat, roffs = [], [0]
+    for m in range(n):
+        rflat.extend(rx.get(m, []))
+        roffs.append(len(rflat))
+        if m in rx:
+            mats[m].react = 1
+    ids = T.SpecialIds(ID["GENERIC_AIR"], ID["FIRE"], ID["WATER"], ID["LAVA"], ID["STEAM"], ID["OBSIDIAN"])
+    return T.MaterialTable((T.Material * n)(*mats), ids, (T.Interaction * max(len(flat), 1))(*flat), (C.c_int32 * len(offs))(*offs),
+                           (T.Interaction * max(len(rflat), 1))(*rflat), (C.c_int32 * len(roffs))(*roffs))
+
+
+def register_material(table, physics, slipperyness, alpha, density, iterations, emit=0, emit_color=0, color=0xFFFFFFFF):
+    """RegisterMaterial() (gds.cpp:282-289; Lua `materials_register`, game_basic.cpp:80): append one material,
+    returning (new_table, id)."""
+    n0 = table.n
+    mats = [T.Material.from_buffer_copy(bytes(m)) for m in table.mats]
+    mats.append(_mat(physics, slipperyness, alpha, density, iterations, emit, emit_color, color))
+    n = n0 + 1
+    flat, offs = [], [0]
+    for a in range(n):
+        for b in range(n):
+            if a < n0 and b < n0:
+                lo, hi = table.inter_offsets[a * n0 + b], table.inter_offsets[a * n0 + b + 1]
+                flat.extend(T.Interaction.from_buffer_copy(bytes(table.inter[k])) for k in range(lo, hi))
+            offs.append(len(flat))
+    ro = list(table.react_offsets) + [table.react_offsets[n0]]
+    t = T.MaterialTable((T.Material * n)(*mats), table.ids, (T.Interaction * max(len(flat), 1))(*flat), (C.c_int32 * len(offs))(*offs),
+                        table.react, (C.c_int32 * len(ro))(*ro))
+    return t, n0

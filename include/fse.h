@@ -1,0 +1,229 @@
+/*
+ * fse.h — C ABI of the B200-native falling-sand world tick ("fse").
+ *
+ * This is the drop-in boundary for the per-tick world update of
+ * cstom4994/falling_sand_engine.  The reference has no FFI seam for this path:
+ * it is a set of member functions on `class world` (source/engine/world.hpp:63-193)
+ * plus three Lua-bound free functions (source/engine/game_basic.cpp:79-81).  Every
+ * entry point below names the reference member it replaces (file:line relative to
+ * /root/reference).  The host-side C++ `fse::World` shim
+ * (falling_sand_engine_b200/csrc/world.hpp) keeps the reference's method names on
+ * top of this ABI.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success and
+ * a negative FSE_E* code on failure (message via fse_last_error); one caller at a
+ * time per fse_world (thread-compatible, like the reference's main-thread-only
+ * world); device work is asynchronous on the world's internal CUDA stream unless
+ * the call returns host data, and fse_sync() joins it.  There is no CPU fallback:
+ * without a CUDA device fse_ctx_create fails.
+ */
+#ifndef FSE_H
+#define FSE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSE_API __attribute__((visibility("default")))
+
+#define FSE_CHUNK 128          /* CHUNK_W == CHUNK_H, source/engine/core/const.h:19-20 */
+#define FSE_MAX_MATERIALS 256  /* device material plane is u8 (reference ships 41)      */
+#define FSE_MAX_REACH 5        /* max |ofs|+radius of an interaction box (gds.cpp:221-231 generates <=5) */
+
+/* error codes */
+#define FSE_OK 0
+#define FSE_EINVAL (-1)
+#define FSE_ECUDA (-2)
+#define FSE_ENOMEM (-3)
+#define FSE_ESTATE (-4)
+#define FSE_ENCCL (-5)
+
+/* PhysicsType, source/engine/game_datastruct.hpp:87-95 (PASSABLE == OBJECT == 5) */
+enum { FSE_AIR = 0, FSE_SOLID = 1, FSE_SAND = 2, FSE_SOUP = 3, FSE_GAS = 4, FSE_PASSABLE = 5, FSE_OBJECT = 5 };
+
+/* interaction / reaction kinds, game_datastruct.hpp:97-103 */
+enum {
+    FSE_INTERACT_NONE = 0,
+    FSE_INTERACT_TRANSFORM_MATERIAL = 1, /* data1 = product id, data2 = box radius */
+    FSE_INTERACT_SPAWN_MATERIAL = 2,     /* data1 = product id, data2 = box radius */
+    FSE_EXPLODE = 3,
+    FSE_REACT_TEMPERATURE_BELOW = 4,     /* data1 = threshold, data2 = product id  */
+    FSE_REACT_TEMPERATURE_ABOVE = 5
+};
+
+/* How TilesCreate(id,x,y) (game_datastruct.cpp:485-574) colours a freshly created
+ * cell.  The reference samples texture-pack images for most solids; textures are
+ * presentation assets (out of scope), so POSITIONAL substitutes a position hash. */
+enum {
+    FSE_COLOR_FIXED = 0,      /* color                                   (Water/Lava/Steam ...)      */
+    FSE_COLOR_JITTER = 1,     /* color + ((r % jitter_range) << jitter_shift)   (Fire/Grass/Dirt ...) */
+    FSE_COLOR_POSITIONAL = 2  /* color ^ (hash(x,y) & 0x0f0f0f)          (textured solids)           */
+};
+
+/* Flattened `Material` (game_datastruct.hpp:130-168). */
+typedef struct fse_material {
+    int32_t physics;        /* physicsType */
+    float density;
+    int32_t iterations;
+    int32_t slipperyness;   /* >= 1 required for FSE_SAND (reference divides by it, world.cpp:1656) */
+    int32_t emit;
+    uint32_t emit_color;
+    uint32_t color;         /* base colour of created cells */
+    uint32_t add_temp;      /* Material::addTemp (u32, game_datastruct.hpp:143) */
+    float conduction_self;
+    float conduction_other;
+    int16_t create_temp;    /* temperature of TilesCreate'd cells: WATER -1023, LAVA 1024 (gds.cpp:427-437) */
+    uint8_t alpha;
+    uint8_t interact;       /* Material::interact */
+    uint8_t react;          /* Material::react    */
+    uint8_t color_kind;     /* FSE_COLOR_*        */
+    uint8_t jitter_shift;
+    uint8_t jitter_range;
+} fse_material;
+
+/* `MaterialInteraction` (game_datastruct.hpp:112-118); field overloading as in the
+ * reference: TRANSFORM/SPAWN: data1 = product material, data2 = radius;
+ * REACT_*: data1 = threshold temperature, data2 = product material. */
+typedef struct fse_interaction {
+    int32_t type;
+    int16_t data1;
+    uint16_t _pad;
+    uint32_t data2;
+    int32_t ofs_x;
+    int32_t ofs_y;
+} fse_interaction;
+
+/* Materials the reference's tick refers to by identity (world.cpp:1101,1519,1883). */
+typedef struct fse_special_ids {
+    int32_t air;       /* GENERIC_AIR  (Tiles_NOTHING) */
+    int32_t fire;
+    int32_t water;
+    int32_t lava;
+    int32_t steam;
+    int32_t obsidian;
+} fse_special_ids;
+
+/* One grid cell crossing the boundary = the value fields of `MaterialInstance`
+ * (game_datastruct.hpp:207-225; `id` is always `mat->id`).           */
+typedef struct fse_cell {
+    uint16_t mat;
+    uint8_t moved;
+    uint8_t settle;      /* settleCount */
+    uint32_t color;
+    int16_t temp;        /* temperature */
+    uint8_t dirty;       /* world::dirty[] (world.hpp:131) folded into the cell */
+    uint8_t _pad;
+    float fluid;         /* fluidAmount (default 2.0f, gds.hpp:215) */
+    float fluid_diff;    /* fluidAmountDiff */
+} fse_cell;
+
+typedef struct fse_rect {
+    int32_t x, y, w, h;
+} fse_rect;
+
+/* Arguments of one world::tick() (world.cpp:1036): globaldef.cell_iter
+ * (data/scripts/global.lua:47), tickZone (game.cpp:1629), and the (seed,tick) key
+ * of the counter RNG that replaces libc rand(). */
+typedef struct fse_tick_args {
+    uint32_t tick;
+    uint32_t seed;
+    int32_t cell_iter;
+    fse_rect tick_zone;
+} fse_tick_args;
+
+/* `CellData` (game_utils/cells.h:15-36) without the std::function killCallback;
+ * `id` lets the host keep an id -> callback map (only the vacuum tool uses it). */
+typedef struct fse_particle {
+    fse_cell tile;
+    float x, y, vx, vy, ax, ay;
+    float target_x, target_y, target_force;
+    int32_t lifetime;
+    int32_t fade_time;
+    uint8_t phase;
+    uint8_t temporary;
+    uint8_t in_object_state;
+    uint8_t _pad;
+    uint32_t _pad2;
+    uint64_t id;
+} fse_particle;
+
+/* Per-world statistics used as parity metrics (the reference's movingTiles[]
+ * histogram, game.cpp:1991-2000, generalised). */
+typedef struct fse_stats {
+    uint64_t hash;                           /* order-independent 64-bit state hash of the rect */
+    uint64_t count[FSE_MAX_MATERIALS];       /* cells per material */
+    double fluid_mass[FSE_MAX_MATERIALS];    /* sum(fluid + fluid_diff) over SOUP cells per material */
+    uint64_t n_dirty;
+    uint64_t n_moved;
+} fse_stats;
+
+typedef struct fse_ctx fse_ctx;
+typedef struct fse_world fse_world;
+
+/* ---- context ---------------------------------------------------------------- */
+FSE_API int fse_ctx_create(int device, fse_ctx** out);
+FSE_API void fse_ctx_destroy(fse_ctx* ctx);
+FSE_API const char* fse_last_error(void);
+FSE_API const char* fse_version(void);
+/* sizeof() of the POD types above as compiled into the library (0 material, 1 interaction, 2 special_ids,
+ * 3 cell, 4 rect, 5 tick_args, 6 particle, 7 stats): lets a foreign-language binding verify its layout. */
+FSE_API int fse_abi_sizeof(int which);
+
+/* InitMaterials/RegisterMaterial/PushMaterials (game_datastruct.cpp:117-300), the
+ * Lua binds materials_init/materials_register/materials_push
+ * (game_basic.cpp:79-81): flattened POD copy of the whole table; re-callable.
+ * inter_offsets has n*n+1 entries: interactions of material a against material b
+ * are inter[inter_offsets[a*n+b] .. inter_offsets[a*n+b+1]) (Material::interactions[b],
+ * gds.hpp:151); react_offsets has n+1 entries (Material::reactions). */
+FSE_API int fse_materials_set(fse_ctx* ctx, const fse_material* tbl, int n, const fse_special_ids* ids,
+                              const fse_interaction* inter, const int32_t* inter_offsets,
+                              const fse_interaction* react, const int32_t* react_offsets);
+
+/* ---- world container: world::init / ~world (world.cpp:43-172, 3532-3636) ------ */
+FSE_API int fse_world_create(fse_ctx* ctx, int32_t width, int32_t height, fse_world** out);
+FSE_API void fse_world_destroy(fse_world* w);
+FSE_API int fse_sync(fse_world* w);
+
+/* getTile/setTile (world.cpp:999-1008), frame() merge and chunkSaveCache
+ * (world.cpp:2374-2391, 2780-2792): AoS rect <-> device SoA planes. */
+FSE_API int fse_write_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, const fse_cell* cells);
+FSE_API int fse_read_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, fse_cell* cells);
+/* memset(dirty, false, ...) (game.cpp:2153) */
+FSE_API int fse_clear_dirty(fse_world* w);
+FSE_API int fse_stats_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, fse_stats* out);
+
+/* ---- the tick ------------------------------------------------------------------ */
+/* world::tick() (world.cpp:1036-1948) without the physicsCheck tail (see
+ * fse_flood_component).  Asynchronous. */
+FSE_API int fse_tick(fse_world* w, const fse_tick_args* args);
+/* world::tickTemperature() (world.cpp:1950-2004). */
+FSE_API int fse_tick_temperature(fse_world* w, const fse_rect* tick_zone);
+
+/* ---- loose particles: world::cells (world.hpp), addCell (world.cpp:2292),
+ *      tickCells (world.cpp:2030-2195) ---------------------------------------- */
+FSE_API int fse_particles_add(fse_world* w, const fse_particle* p, int32_t n);
+FSE_API int fse_particles_tick(fse_world* w, const fse_rect* tick_zone);
+FSE_API int fse_particles_count(fse_world* w, int64_t* out);
+FSE_API int fse_particles_read(fse_world* w, fse_particle* out, int64_t cap, int64_t* n_out);
+FSE_API int fse_particles_clear(fse_world* w);
+/* capacity of the device particle pool (default 1<<20); the reference's std::vector grows unbounded */
+FSE_API int fse_particles_reserve(fse_world* w, int64_t capacity);
+
+/* ---- measurement helpers ------------------------------------------------------- */
+/* CUDA events on the world's own stream (torch.cuda.Event only sees torch's). */
+FSE_API int fse_timer_start(fse_world* w);
+FSE_API int fse_timer_stop(fse_world* w, float* ms_out);
+/* kernels launched by this library since fse_ctx_create (bench.py "gpu_launches"). */
+FSE_API int64_t fse_launch_count(fse_ctx* ctx);
+/* average device time per launch of the dominant (chunk tick) kernel since the
+ * last reset, from CUDA events recorded around every launch when enabled. */
+FSE_API int fse_kernel_timing_enable(fse_world* w, int enable);
+FSE_API int fse_kernel_timing_read(fse_world* w, double* total_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSE_H */

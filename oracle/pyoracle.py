@@ -1,0 +1,154 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from falling_sand_engine_b200 import types as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libfse_oracle.so")
+_lib = None
+
+REFERENCE, PARTITIONED = 0, 1
+RNG_SLOT, RNG_LIBC = 0, 1
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in ("fse_oracle.cpp", "oracle_capi.cpp", "fse_oracle.hpp", "outline_oracle.cpp")]
+    srcs = [s for s in srcs if os.path.exists(s)] + [os.path.join(_HERE, "..", "include", "fse.h")]
+    if not force and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        L.fseo_world_create.restype = C.c_void_p
+        L.fseo_world_create.argtypes = [C.c_int, C.c_int]
+        L.fseo_world_destroy.argtypes = [C.c_void_p]
+        L.fseo_tick.restype = C.c_double
+        L.fseo_tick.argtypes = [C.c_void_p, C.POINTER(T.TickArgs), C.c_int, C.c_int, C.c_int]
+        L.fseo_particles_count.restype = C.c_int64
+        L.fseo_particles_count.argtypes = [C.c_void_p]
+        L.fseo_cell_hash.restype = C.c_uint64
+        L.fseo_rng_draw.restype = C.c_uint32
+        L.fseo_rng_draw.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32]
+        for name in ("fseo_materials_set", "fseo_write_rect", "fseo_read_rect", "fseo_clear_dirty", "fseo_stats_rect",
+                     "fseo_run_chunk", "fseo_clear_visited", "fseo_tick_temperature", "fseo_particles_add",
+                     "fseo_particles_read", "fseo_particles_clear", "fseo_tick_particles"):
+            getattr(L, name).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def default_materials(seed=1337):
+    L = lib()
+    n, ni, nr = C.c_int(), C.c_int(), C.c_int()
+    L.fseo_default_materials(C.c_uint32(seed), None, C.byref(n), None, None, C.byref(ni), None, None, C.byref(nr), None)
+    mats = (T.Material * n.value)()
+    ids = T.SpecialIds()
+    inter = (T.Interaction * max(ni.value, 1))()
+    io = (C.c_int32 * (n.value * n.value + 1))()
+    react = (T.Interaction * max(nr.value, 1))()
+    ro = (C.c_int32 * (n.value + 1))()
+    L.fseo_default_materials(C.c_uint32(seed), mats, C.byref(n), C.byref(ids), inter, C.byref(ni), io, react, C.byref(nr), ro)
+    return T.MaterialTable(mats, ids, inter, io, react, ro)
+
+
+class OracleWorld:
+    """Oracle world with the same method names as falling_sand_engine_b200.World."""
+
+    def __init__(self, width, height, table=None):
+        self.L = lib()
+        self.width, self.height = width, height
+        self.h = C.c_void_p(self.L.fseo_world_create(width, height))
+        self.table = table or default_materials()
+        self.L.fseo_materials_set(self.h, *self.table.args())
+
+    def close(self):
+        if self.h:
+            self.L.fseo_world_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_materials(self, table):
+        self.table = table
+        self.L.fseo_materials_set(self.h, *table.args())
+
+    def write_rect(self, x, y, cells):
+        cells = np.ascontiguousarray(cells, dtype=T.CELL_DTYPE)
+        h, w = cells.shape
+        self.L.fseo_write_rect(self.h, x, y, w, h, cells.ctypes.data_as(C.c_void_p))
+
+    def read_rect(self, x, y, w, h):
+        out = np.zeros((h, w), dtype=T.CELL_DTYPE)
+        self.L.fseo_read_rect(self.h, x, y, w, h, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def read_all(self):
+        return self.read_rect(0, 0, self.width, self.height)
+
+    def clear_dirty(self):
+        self.L.fseo_clear_dirty(self.h)
+
+    def stats(self, rect=None):
+        r = rect or T.Rect(0, 0, self.width, self.height)
+        s = T.Stats()
+        self.L.fseo_stats_rect(self.h, r.x, r.y, r.w, r.h, C.byref(s))
+        return s
+
+    def tick(self, tick, seed=1337, cell_iter=3, zone=None, schedule=PARTITIONED, rng=RNG_SLOT, threads=1):
+        a = T.TickArgs(tick, seed, cell_iter, zone or T.zone_of(self.width, self.height))
+        return self.L.fseo_tick(self.h, C.byref(a), schedule, rng, threads)
+
+    def run_chunk(self, tick, seed, it, cx, cy, schedule=PARTITIONED, zone=None):
+        a = T.TickArgs(tick, seed, 3, zone or T.zone_of(self.width, self.height))
+        self.L.fseo_run_chunk(self.h, C.byref(a), it, cx, cy, schedule)
+
+    def clear_visited(self):
+        self.L.fseo_clear_visited(self.h)
+
+    def tick_temperature(self, zone=None):
+        z = zone or T.zone_of(self.width, self.height)
+        self.L.fseo_tick_temperature(self.h, C.byref(z))
+
+    def particles_add(self, parts):
+        parts = np.ascontiguousarray(parts, dtype=T.PARTICLE_DTYPE)
+        self.L.fseo_particles_add(self.h, parts.ctypes.data_as(C.c_void_p), len(parts))
+
+    def particles_count(self):
+        return int(self.L.fseo_particles_count(self.h))
+
+    def particles_read(self):
+        n = self.particles_count()
+        out = np.zeros(n, dtype=T.PARTICLE_DTYPE)
+        if n:
+            self.L.fseo_particles_read(self.h, out.ctypes.data_as(C.c_void_p), C.c_int64(n))
+        return out
+
+    def particles_clear(self):
+        self.L.fseo_particles_clear(self.h)
+
+    def particles_tick(self, zone=None):
+        z = zone or T.zone_of(self.width, self.height)
+        self.L.fseo_tick_particles(self.h, C.byref(z))
+
+
+def rng_draw(seed, tick, it, x, y, slot):
+    return int(lib().fseo_rng_draw(seed, tick, it, x, y, slot))

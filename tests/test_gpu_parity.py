@@ -1,0 +1,112 @@
+"""CUDA path vs the CPU oracle, through the C ABI (include/fse.h).  Needs a B200: `pytest -m gpu`.
+
+Bar (BASELINE.json north_star): bit-exact, cell for cell and field for field, against the oracle run under the
+GPU's partitioned visiting order with the same counter RNG; the oracle's reference-order run is compared in
+tests/test_oracle_pins.py (exact for order-independent rules, conservation/histograms otherwise).
+"""
+import numpy as np
+import pytest
+
+import falling_sand_engine_b200 as fse
+from falling_sand_engine_b200 import types as T
+from falling_sand_engine_b200 import worldgen as G
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(oracle, gpu_ctx, table, W, H):
+    ow = oracle.OracleWorld(W, H, table)
+    gpu_ctx.set_materials(table)
+    gw = fse.World(gpu_ctx, W, H)
+    return ow, gw
+
+
+def _run_and_compare(ow, gw, ticks, seed=1337, every=1, cell_iter=3, what=""):
+    for t in range(ticks):
+        ow.tick(t, seed=seed, cell_iter=cell_iter)
+        gw.tick(t, seed=seed, cell_iter=cell_iter)
+        if (t + 1) % every == 0 or t == ticks - 1:
+            Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"{what} tick {t}")
+            Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), f"{what} tick {t}")
+
+
+def test_roundtrip_rect(oracle, gpu_ctx, table):
+    W = H = 384
+    gpu_ctx.set_materials(table)
+    gw = fse.World(gpu_ctx, W, H)
+    cells = G.mixed_band(table, W, H, 0, H, seed=5, blob=16)
+    cells["moved"] = (np.arange(W * H).reshape(H, W) % 3 == 0)
+    cells["settle"] = (np.arange(W * H).reshape(H, W) % 11)
+    cells["fluid_diff"] = np.linspace(-1, 1, W * H, dtype=np.float32).reshape(H, W)
+    gw.write_rect(0, 0, cells)
+    back = gw.read_all()
+    Hh.assert_cells_equal(cells, back, "roundtrip")
+    sub = gw.read_rect(17, 33, 100, 50)
+    Hh.assert_cells_equal(cells[33:83, 17:117], sub, "sub-rect")
+
+
+def test_column_drop_exact(oracle, gpu_ctx, table):
+    W = H = 512
+    ow, gw = _pair(oracle, gpu_ctx, table, W, H)
+    Hh.build_column(ow, table, W, H)
+    Hh.build_column(gw, table, W, H)
+    _run_and_compare(ow, gw, 40, every=4, what="column")
+
+
+def test_mixed_exact(oracle, gpu_ctx, table):
+    W = H = 512
+    ow, gw = _pair(oracle, gpu_ctx, table, W, H)
+    Hh.build_mixed(ow, table, W, H, seed=99)
+    Hh.build_mixed(gw, table, W, H, seed=99)
+    _run_and_compare(ow, gw, 30, seed=7, every=3, what="mixed")
+
+
+def test_mixed_interactions_exact(oracle, gpu_ctx, table):
+    W, H = 640, 512
+    tbl, extra = G.bench_table(table)
+    ow, gw = _pair(oracle, gpu_ctx, tbl, W, H)
+    Hh.build_mixed(ow, tbl, W, H, seed=3, extra=list(extra.values()), blob=16)
+    Hh.build_mixed(gw, tbl, W, H, seed=3, extra=list(extra.values()), blob=16)
+    _run_and_compare(ow, gw, 24, seed=11, every=3, what="interactions")
+
+
+def test_stats_match(oracle, gpu_ctx, table):
+    W = H = 512
+    ow, gw = _pair(oracle, gpu_ctx, table, W, H)
+    Hh.build_mixed(ow, table, W, H, seed=21)
+    Hh.build_mixed(gw, table, W, H, seed=21)
+    for t in range(5):
+        ow.tick(t)
+        gw.tick(t)
+    so, sg = ow.stats(), gw.stats()
+    assert so.hash == sg.hash
+    assert list(so.count) == list(sg.count)
+    assert so.n_dirty == sg.n_dirty and so.n_moved == sg.n_moved
+    for m in range(table.n):
+        assert abs(so.fluid_mass[m] - sg.fluid_mass[m]) <= 1e-6 * max(1.0, abs(so.fluid_mass[m]))
+
+
+def test_temperature_exact(oracle, gpu_ctx, table):
+    W, H = 512, 384
+    ow, gw = _pair(oracle, gpu_ctx, table, W, H)
+    Hh.build_mixed(ow, table, W, H, seed=4, blob=8)
+    Hh.build_mixed(gw, table, W, H, seed=4, blob=8)
+    for _ in range(6):
+        ow.tick_temperature()
+        gw.tick_temperature()
+    Hh.assert_cells_equal(ow.read_all(), gw.read_all(), "temperature")
+
+
+def test_determinism(gpu_ctx, table):
+    W = H = 512
+    hashes = []
+    for _ in range(2):
+        gpu_ctx.set_materials(table)
+        gw = fse.World(gpu_ctx, W, H)
+        Hh.build_mixed(gw, table, W, H, seed=8)
+        for t in range(10):
+            gw.tick(t)
+        hashes.append(gw.stats().hash)
+        gw.close()
+    assert hashes[0] == hashes[1]
