@@ -101,18 +101,41 @@ FSE_API int fse_materials_set(fse_ctx* c, const fse_material* tbl, int n, const 
     int n_inter = inter_offsets ? inter_offsets[n * n] : 0;
     int n_react = react_offsets ? react_offsets[n] : 0;
     int max_reach = 0;
+    int n_irows = 0;
     for (int i = 0; i < n; i++) {
         const fse_material& m = tbl[i];
         if (m.physics < 0 || m.physics > 5) return fail(FSE_EINVAL, "material %d: physics %d", i, m.physics);
         if (m.physics == FSE_SAND && (m.slipperyness < 1 || m.slipperyness > 255))
             return fail(FSE_EINVAL, "material %d: SAND needs 1 <= slipperyness <= 255 (reference divides by it, world.cpp:1656)", i);
         if (m.iterations < 0) return fail(FSE_EINVAL, "material %d: negative iterations", i);
+        Lut& L = h.lut;
         h.phys[i] = (uint8_t)m.physics;
-        h.iters[i] = (uint8_t)(m.iterations > 255 ? 255 : m.iterations);
+        L.phys[i] = (uint8_t)m.physics;
+        L.iters[i] = (uint8_t)(m.iterations > 255 ? 255 : m.iterations);
         int nr = react_offsets ? react_offsets[i + 1] - react_offsets[i] : 0;
-        h.mflags[i] = (uint8_t)((m.interact ? MF_INTERACT : 0) | ((m.react && nr > 0) ? MF_REACT : 0));
-        h.slip[i] = (uint8_t)(m.slipperyness < 0 ? 0 : (m.slipperyness > 255 ? 255 : m.slipperyness));
-        h.maxstab[i] = m.slipperyness >= 1 ? (uint8_t)(int)(8 / sqrt((double)m.slipperyness) + 1) : 0;  // world.cpp:1630
+        L.mflags[i] = (uint8_t)((m.interact ? MF_INTERACT : 0) | ((m.react && nr > 0) ? MF_REACT : 0) | (nr > 1 ? MF_REACT_MULTI : 0));
+        L.slip[i] = (uint8_t)(m.slipperyness < 0 ? 0 : (m.slipperyness > 255 ? 255 : m.slipperyness));
+        L.maxstab[i] = m.slipperyness >= 1 ? (uint8_t)(int)(8 / sqrt((double)m.slipperyness) + 1) : 0;  // world.cpp:1630
+        L.dens[i] = m.density;
+        if (nr > 0) {
+            const fse_interaction& r0 = react[react_offsets[i]];
+            L.rx[i].thr = r0.data1;
+            L.rx[i].type = (uint8_t)r0.type;
+            L.rx[i].prod = (uint8_t)r0.data2;
+        }
+        if (m.interact && inter_offsets) {  // partner bitmap: which materials below trigger an interaction list
+            bool any = false;
+            for (int b = 0; b < n; b++) any |= inter_offsets[i * n + b + 1] > inter_offsets[i * n + b];
+            if (any) {
+                if (n_irows < LUT_IROWS) {
+                    for (int b = 0; b < n; b++)
+                        if (inter_offsets[i * n + b + 1] > inter_offsets[i * n + b]) L.ibits[n_irows][b >> 5] |= 1u << (b & 31);
+                    L.irow[i] = (uint8_t)(++n_irows);
+                } else {
+                    L.mflags[i] |= MF_INTERACT_SLOW;
+                }
+            }
+        }
         h.alpha[i] = m.alpha;
         h.ckind[i] = m.color_kind;
         h.jshift[i] = m.jitter_shift;

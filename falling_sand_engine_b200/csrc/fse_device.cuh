@@ -26,9 +26,26 @@ constexpr uint8_t F_VISITED = 0x80;
 
 enum { P_AIR = 0, P_SOLID = 1, P_SAND = 2, P_SOUP = 3, P_GAS = 4, P_PASSABLE = 5 };
 
-// material flag bits in DevTables::mflags
-constexpr uint8_t MF_INTERACT = 0x01;
-constexpr uint8_t MF_REACT = 0x02;
+// material flag bits in DevTables::mflags / Lut::mflags
+constexpr uint8_t MF_INTERACT = 0x01;       // Material::interact
+constexpr uint8_t MF_REACT = 0x02;          // Material::react && nReactions > 0
+constexpr uint8_t MF_REACT_MULTI = 0x04;    // more than one reaction: walk the list in global memory
+constexpr uint8_t MF_INTERACT_SLOW = 0x08;  // partner bitmap row overflowed: look nInteractions up in global memory
+constexpr int LUT_IROWS = 8;
+
+// Hot per-material constants, copied to shared memory by the tick kernel (built on the host in fse_materials_set).
+struct Lut {
+    uint8_t phys[FSE_MAX_MATERIALS];
+    uint8_t iters[FSE_MAX_MATERIALS];    // Material::iterations clamped to 255
+    uint8_t mflags[FSE_MAX_MATERIALS];
+    uint8_t slip[FSE_MAX_MATERIALS];     // Material::slipperyness ("1 to ~127", world.cpp:1614)
+    uint8_t maxstab[FSE_MAX_MATERIALS];  // int(8 / sqrt(slipperyness) + 1), world.cpp:1630
+    uint8_t irow[FSE_MAX_MATERIALS];     // 1-based row of ibits for an interacting material, 0 = none
+    float dens[FSE_MAX_MATERIALS];
+    struct Rx { int16_t thr; uint8_t type; uint8_t prod; } rx[FSE_MAX_MATERIALS];  // first reaction of the material
+    uint32_t ibits[LUT_IROWS][FSE_MAX_MATERIALS / 32];  // bit b of row r: nInteractions[b] > 0
+};
+static_assert(sizeof(Lut) % 16 == 0, "Lut is copied with 16-byte loads");
 
 // RNG draw sites — same numbering as the reference-derived oracle (oracle/fse_oracle.hpp)
 enum Slot : uint32_t {
@@ -58,13 +75,11 @@ __host__ __device__ __forceinline__ uint32_t pos_hash(int x, int y) {
 
 // Flattened material table in device memory (one per context).
 struct DevTables {
+    Lut lut;  // first member: 16-byte aligned
     int n;
     int air, fire, water, lava, steam, obsidian;
+    int _pad0;
     uint8_t phys[FSE_MAX_MATERIALS];
-    uint8_t iters[FSE_MAX_MATERIALS];    // Material::iterations clamped to 255
-    uint8_t mflags[FSE_MAX_MATERIALS];
-    uint8_t slip[FSE_MAX_MATERIALS];     // Material::slipperyness ("1 to ~127", world.cpp:1614)
-    uint8_t maxstab[FSE_MAX_MATERIALS];  // int(8 / sqrt(slipperyness) + 1), world.cpp:1630
     uint8_t alpha[FSE_MAX_MATERIALS];
     uint8_t ckind[FSE_MAX_MATERIALS], jshift[FSE_MAX_MATERIALS], jrange[FSE_MAX_MATERIALS];
     int16_t ctemp[FSE_MAX_MATERIALS];

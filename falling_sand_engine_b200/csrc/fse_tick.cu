@@ -48,15 +48,6 @@ constexpr float FLUID_MinFlow = 0.05f;
 constexpr float FLUID_MaxFlow = 8.0f;
 constexpr float FLUID_FlowSpeed = 1.0f;
 
-struct Lut {
-    uint8_t phys[FSE_MAX_MATERIALS];
-    uint8_t iters[FSE_MAX_MATERIALS];
-    uint8_t mflags[FSE_MAX_MATERIALS];
-    uint8_t slip[FSE_MAX_MATERIALS];
-    uint8_t maxstab[FSE_MAX_MATERIALS];
-    float dens[FSE_MAX_MATERIALS];
-};
-
 struct __align__(128) Smem {
     unsigned char ring[RING * ROW_BYTES];
     Lut lut;
@@ -85,6 +76,7 @@ struct Ctx {
     uint32_t rkey;
     uint32_t tick;
     int iter;
+    int nmat;
     int air, fire, water, lava, steam, obsidian;
 };
 
@@ -192,23 +184,28 @@ __device__ __forceinline__ CellR nothing(const Ctx& c) {
     r.fd = 0.0f;
     return r;
 }
-// TilesCreate(id, x, y) (game_datastruct.cpp:485-574) with the per-material policy of fse_material
-__device__ __noinline__ CellR create(const Ctx& c, int m, int x, int y) {
+// TilesCreate(id, x, y) (game_datastruct.cpp:485-574) with the per-material policy of fse_material.
+// The table walk is a rare path: kept out of line, result returned in registers (colour | temperature << 32).
+__device__ __noinline__ uint64_t create_color_temp(const DevTables* T, uint32_t rkey, int m, int x, int y) {
+    uint32_t col = T->color[m];
+    int kind = T->ckind[m];
+    if (kind == FSE_COLOR_JITTER) {
+        uint32_t rr = rng_draw(rng_cell(rkey, x, y), S_CREATE_COLOR);
+        uint32_t jr = T->jrange[m];
+        col = col + ((rr % (jr ? jr : 1u)) << T->jshift[m]);
+    } else if (kind == FSE_COLOR_POSITIONAL) {
+        col = col ^ (pos_hash(x, y) & 0x0f0f0fU);
+    }
+    return (uint64_t)col | ((uint64_t)(uint16_t)T->ctemp[m] << 32);
+}
+__device__ __forceinline__ CellR create(const Ctx& c, int m, int x, int y) {
+    const uint64_t ct = create_color_temp(c.T, c.rkey, m, x, y);
     CellR r;
     r.mat = (uint8_t)m;
     r.moved = 0;
     r.stl = 0;
-    r.tmp = c.T->ctemp[m];
-    uint32_t col = c.T->color[m];
-    int kind = c.T->ckind[m];
-    if (kind == FSE_COLOR_JITTER) {
-        uint32_t rr = rng_draw(rng_cell(c.rkey, x, y), S_CREATE_COLOR);
-        uint32_t jr = c.T->jrange[m];
-        col = col + ((rr % (jr ? jr : 1u)) << c.T->jshift[m]);
-    } else if (kind == FSE_COLOR_POSITIONAL) {
-        col = col ^ (pos_hash(x, y) & 0x0f0f0fU);
-    }
-    r.col = col;
+    r.tmp = (int16_t)(uint16_t)(ct >> 32);
+    r.col = (uint32_t)ct;
     r.fl = 2.0f;
     r.fd = 0.0f;
     return r;
@@ -231,32 +228,43 @@ __device__ __forceinline__ uint64_t particle_id(const Ctx& c, int x, int y, int 
            ((uint64_t)(x & 0x3ffff) << 4) | (uint64_t)(k & 15);
 }
 
-// cells.push_back(new CellData(tile, x, y, vx, vy, 0, ay)) (world.cpp:1110,1222,1298)
-__device__ __noinline__ void emit_particle(const Ctx& c, const CellR& t, float px, float py, float vx, float vy, float ay,
-                                           bool temporary, int lifetime, int fade, uint64_t id) {
-    unsigned int i = atomicAdd(c.pcount, 1u);
-    if (i >= c.pcap) return;  // counted; the host reports overflow
+// cells.push_back(new CellData(tile, x, y, vx, vy, 0, ay)) (world.cpp:1110,1222,1298).  Out of line, scalar
+// arguments only (no stack frame): packed = mat | moved << 8 | settle << 16, tmp in the high half.
+__device__ __noinline__ void emit_particle_raw(fse_particle* pbuf, unsigned int* pcount, unsigned int pcap, uint32_t packed, uint32_t col,
+                                               float fl, float fd, float px, float py, float vx, float vy, float ay, int lifetime,
+                                               int fade, uint64_t id) {
+    unsigned int i = atomicAdd(pcount, 1u);
+    if (i >= pcap) return;  // counted; the host reports overflow
     fse_particle p;
-    p.tile.mat = t.mat;
-    p.tile.moved = t.moved ? 1 : 0;
-    p.tile.settle = t.stl;
-    p.tile.color = t.col;
-    p.tile.temp = t.tmp;
+    p.tile.mat = (uint16_t)(packed & 0xff);
+    p.tile.moved = (uint8_t)((packed >> 8) & 1);
+    p.tile.settle = (uint8_t)((packed >> 16) & 0xff);
+    p.tile.color = col;
+    p.tile.temp = (int16_t)(fade >> 16);
     p.tile.dirty = 0;
     p.tile._pad = 0;
-    p.tile.fluid = t.fl;
-    p.tile.fluid_diff = t.fd;
+    p.tile.fluid = fl;
+    p.tile.fluid_diff = fd;
     p.x = px; p.y = py; p.vx = vx; p.vy = vy; p.ax = 0.0f; p.ay = ay;
     p.target_x = 0.0f; p.target_y = 0.0f; p.target_force = 0.0f;
     p.lifetime = lifetime;
-    p.fade_time = fade;
+    p.fade_time = fade & 0xffff;
     p.phase = 0;
-    p.temporary = temporary ? 1 : 0;
+    p.temporary = (uint8_t)((packed >> 24) & 1);
     p.in_object_state = 0;
     p._pad = 0;
     p._pad2 = 0;
     p.id = id;
-    c.pbuf[i] = p;
+    uint4* dst = reinterpret_cast<uint4*>(pbuf + i);
+    const uint4* src = reinterpret_cast<const uint4*>(&p);
+#pragma unroll
+    for (int q = 0; q < (int)(sizeof(fse_particle) / 16); q++) dst[q] = src[q];
+}
+__device__ __forceinline__ void emit_particle(const Ctx& c, const CellR& t, float px, float py, float vx, float vy, float ay,
+                                              bool temporary, int lifetime, int fade, uint64_t id) {
+    uint32_t packed = (uint32_t)t.mat | ((t.moved ? 1u : 0u) << 8) | ((uint32_t)t.stl << 16) | ((temporary ? 1u : 0u) << 24);
+    emit_particle_raw(c.pbuf, c.pcount, c.pcap, packed, t.col, t.fl, t.fd, px, py, vx, vy, ay, lifetime,
+                      (fade & 0xffff) | ((int)(uint16_t)t.tmp << 16), id);
 }
 
 // world.cpp:1021-1034
@@ -292,6 +300,51 @@ __device__ __forceinline__ void pour(const Ctx& c, int s, int j, int nbPhys, con
     }
 }
 
+// tile.mat->interact && nInteractions[below.id] > 0 (world.cpp:1153), from the shared-memory partner bitmap
+__device__ __forceinline__ bool has_interaction(const Ctx& c, uint8_t m, uint8_t mb) {
+    const uint8_t mf = c.L->mflags[m];
+    if (!(mf & MF_INTERACT)) return false;
+    if (mf & MF_INTERACT_SLOW) return c.T->inter_off[m * c.nmat + mb + 1] > c.T->inter_off[m * c.nmat + mb];
+    const int r = c.L->irow[m];
+    return r != 0 && ((c.L->ibits[r - 1][mb >> 5] >> (mb & 31)) & 1u);
+}
+
+// ---- FIRE (world.cpp:1101-1146), one fire cell handled by the whole warp: lane i < 25 owns neighbour
+// (xx, yy) = (i / 5 - 2, i % 5 - 2), the reference's loop order, so the RNG slots are identical.  Must be
+// called convergently; (s, jf, xf) are warp-uniform.
+__device__ void fire_coop(const Ctx& c, int s, int jf, int xf, int y, int lane) {
+    const uint8_t f0 = FLG(s, jf);
+    if (f0 & F_VISITED) return;  // 1091
+    if (c.iter >= (int)c.L->iters[c.fire]) {  // 1093-1096
+        if (lane == 0) FLG(s, jf) = f0 | F_VISITED;
+        return;
+    }
+    const uint32_t cb = rng_cell(c.rkey, xf, y);
+    // 1102-1107 edits a local copy that is never stored
+    if (lane == 0 && rng_draw(cb, S_FIRE_EMBER) % 10 == 0) {  // 1109-1119
+        CellR tile = ldc(c, s, jf);
+        float vx = ((int)(rng_draw(cb, S_FIRE_EMBER_VX) % 10) - 5) / 20.0f;
+        float vy = -((int)(rng_draw(cb, S_FIRE_EMBER_VY) % 10) / 10.0f) / 3.0f + -0.5f;
+        emit_particle(c, tile, (float)xf, (float)(y - 1), vx, vy, 0.01f, true, 30, 10, particle_id(c, xf, y, 15));
+    }
+    if (rng_draw(cb, S_FIRE_DIE) % 150 == 0) {  // 1121-1125
+        if (lane == 0) stc(c, s, jf, nothing(c), F_DIRTY | F_VISITED);
+        return;
+    }
+    bool solid = false;  // 1127-1144
+    int xx = 0, yy = 0, s2 = s;
+    if (lane < 25) {
+        xx = lane / 5 - 2;
+        yy = lane % 5 - 2;
+        s2 = rs(s, yy);
+        solid = PHYS(s2, jf + xx) == P_SOLID;
+    }
+    const bool foundAny = __any_sync(0xffffffffu, solid);
+    if (solid && rng_draw(cb, S_FIRE_IGNITE0 + lane) % 500 == 0)
+        stc(c, s2, jf + xx, create(c, c.fire, xf + xx, y + yy), F_DIRTY | F_VISITED);
+    if (!foundAny && lane == 0 && rng_draw(cb, S_FIRE_DIE_ALONE) % 120 == 0) stc(c, s, jf, nothing(c), F_DIRTY | F_VISITED);
+}
+
 // ---- pass 1: one cell (world.cpp:1089-1586) ----------------------------------------------------------
 __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
     uint8_t f0 = FLG(s, j);
@@ -306,42 +359,17 @@ __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
     const uint32_t cb = rng_cell(c.rkey, x, y);
     const int sb = rs(s, 1);  // row below
 
-    if (m == c.fire) {  // 1101-1146 (1102-1107 edits a local copy that is never stored)
-        if (rng_draw(cb, S_FIRE_EMBER) % 10 == 0) {  // 1109-1119
-            CellR tile = ldc(c, s, j);
-            float vx = ((int)(rng_draw(cb, S_FIRE_EMBER_VX) % 10) - 5) / 20.0f;
-            float vy = -((int)(rng_draw(cb, S_FIRE_EMBER_VY) % 10) / 10.0f) / 3.0f + -0.5f;
-            emit_particle(c, tile, (float)x, (float)(y - 1), vx, vy, 0.01f, true, 30, 10, particle_id(c, x, y, 15));
-        }
-        if (rng_draw(cb, S_FIRE_DIE) % 150 == 0) {  // 1121-1125
-            stc(c, s, j, nothing(c), F_DIRTY | F_VISITED);
-        } else {
-            bool foundAny = false;  // 1127-1144
-            for (int xx = -2; xx <= 2; xx++) {
-                for (int yy = -2; yy <= 2; yy++) {
-                    int s2 = rs(s, yy);
-                    if (PHYS(s2, j + xx) == P_SOLID) {
-                        foundAny = true;
-                        if (rng_draw(cb, S_FIRE_IGNITE0 + (xx + 2) * 5 + (yy + 2)) % 500 == 0) {
-                            stc(c, s2, j + xx, create(c, c.fire, x + xx, y + yy), F_DIRTY | F_VISITED);
-                        }
-                    }
-                }
-            }
-            if (!foundAny && rng_draw(cb, S_FIRE_DIE_ALONE) % 120 == 0) stc(c, s, j, nothing(c), F_DIRTY | F_VISITED);
-        }
-        return;  // FIRE is PASSABLE: none of the typed rules below applies
-    }
+    if (m == c.fire) return;  // FIRE cells are handled warp-cooperatively by fire_coop() (pass1_row)
 
     if (type == P_SAND) {  // 1148-1267
         const uint8_t mb = MAT(sb, j);
         const int below = c.L->phys[mb];
         const uint8_t mf = c.L->mflags[m];
 
-        if (mf & MF_INTERACT) {  // 1153-1179
-            const int n = c.T->n;
+        if ((mf & MF_INTERACT) && has_interaction(c, m, mb)) {  // 1153-1179
+            const int n = c.nmat;
             int lo = c.T->inter_off[m * n + mb], hi = c.T->inter_off[m * n + mb + 1];
-            if (hi > lo) {
+            {
                 for (int i = lo; i < hi; i++) {
                     fse_interaction in = c.T->inter[i];
                     int rad = (int)in.data2;
@@ -366,15 +394,26 @@ __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
         if (mf & MF_REACT) {  // 1181-1204
             bool react = false;
             const int16_t temp = TMP(s, j);
-            for (int i = c.T->react_off[m]; i < c.T->react_off[m + 1]; i++) {
-                fse_interaction in = c.T->react[i];
-                bool hit = (in.type == FSE_REACT_TEMPERATURE_BELOW && temp < in.data1) ||
-                           (in.type == FSE_REACT_TEMPERATURE_ABOVE && temp > in.data1);
+            if (!(mf & MF_REACT_MULTI)) {
+                const Lut::Rx rx = c.L->rx[m];
+                bool hit = (rx.type == FSE_REACT_TEMPERATURE_BELOW && temp < rx.thr) || (rx.type == FSE_REACT_TEMPERATURE_ABOVE && temp > rx.thr);
                 if (hit) {
-                    CellR n = create(c, (int)in.data2, x, y);
+                    CellR n = create(c, rx.prod, x, y);
                     n.tmp = temp;
                     stc(c, s, j, n, F_DIRTY | F_VISITED);
                     react = true;
+                }
+            } else {
+                for (int i = c.T->react_off[m]; i < c.T->react_off[m + 1]; i++) {
+                    fse_interaction in = c.T->react[i];
+                    bool hit = (in.type == FSE_REACT_TEMPERATURE_BELOW && temp < in.data1) ||
+                               (in.type == FSE_REACT_TEMPERATURE_ABOVE && temp > in.data1);
+                    if (hit) {
+                        CellR n = create(c, (int)in.data2, x, y);
+                        n.tmp = temp;
+                        stc(c, s, j, n, F_DIRTY | F_VISITED);
+                        react = true;
+                    }
                 }
             }
             if (react) return;
@@ -576,6 +615,11 @@ __device__ void visit2(const Ctx& c, int s, int j, int x, int y) {
         bool stoppedByFriction = !(f0 & F_MOVED);  // 1612
         const int slip = c.L->slip[m];
         bool nowMoved = (f0 & F_MOVED) != 0;  // real_tiles[idx].moved (the local `tile` copy keeps the old flag)
+        if (!(canL || canR)) {
+            // 1647-1654 fires whatever the pillar probe decides (an un-stick at 1637 is overwritten at 1648)
+            set_moved(c, s, j, false);
+            return;
+        }
         if (stoppedByFriction) {  // 1617-1645
             int drop = 0;
             for (int pil = 0; pil < 10; pil++) {
@@ -679,11 +723,11 @@ __device__ void pass1_row(const Ctx& c, int k, int cx, int cy, int lane) {
     const int s = slot_of_row(k);
     const int y = cy + CHUNK - 1 - k;
     const int jw = HX8 + 4 * lane;
-    // row-level vote: does any cell of this row act in pass 1?
+    // row-level vote: does any cell of this row act in pass 1, and does the row hold FIRE / interacting powders?
     uint32_t mw = ld_word(&MAT(s, jw));
     uint32_t fw = ld_word(&FLG(s, jw));
     uint32_t gate = 0;
-    bool act = false;
+    bool act = false, spec = false;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
         uint32_t m = (mw >> (8 * b)) & 0xff;
@@ -691,39 +735,53 @@ __device__ void pass1_row(const Ctx& c, int k, int cx, int cy, int lane) {
         bool gated = c.iter >= (int)c.L->iters[m];
         int ph = c.L->phys[m];
         if (!vis && gated) gate |= (uint32_t)F_VISITED << (8 * b);
-        if (!vis && !gated && (ph == P_SAND || ph == P_SOUP || ph == P_GAS || (int)m == c.fire)) act = true;
+        const bool fire = (int)m == c.fire;
+        if (!vis && !gated && (ph == P_SAND || ph == P_SOUP || ph == P_GAS || fire)) act = true;
+        if (fire || (c.L->mflags[m] & MF_INTERACT)) spec = true;
     }
     if (!__any_sync(0xffffffffu, act)) {
         // inert row: the only effect of pass 1 is tickVisited = true on cells past their iteration count (1093-1096)
         if (gate) *reinterpret_cast<uint32_t*>(&FLG(s, jw)) = fw | gate;
         return;
     }
+    const bool special_row = __any_sync(0xffffffffu, spec);
     const int sb = rs(s, 1);
     for (int cc = 0; cc < 4; cc++) {
         const int j = jw + cc;
         const int x = cx + 4 * lane + cc;
+        if (!special_row) {  // no FIRE and no interacting powder can exist in this row during this step
+            visit1(c, s, j, x, y);
+            __syncwarp();
+            continue;
+        }
         // classify at the start of the sub-step
         int phase = 0;
         const uint8_t m = MAT(s, j);
         if ((int)m == c.fire) {
             phase = 1 + (lane & 1);
-        } else if (c.L->phys[m] == P_SAND && (c.L->mflags[m] & MF_INTERACT)) {
-            const int n = c.T->n;
-            const uint8_t mb = MAT(sb, j);
-            if (c.T->inter_off[m * n + mb + 1] > c.T->inter_off[m * n + mb]) phase = 3 + (lane % 3);
+        } else if (c.L->phys[m] == P_SAND && has_interaction(c, m, MAT(sb, j))) {
+            phase = 3 + (lane % 3);
         }
         const unsigned special = __ballot_sync(0xffffffffu, phase != 0);
-        if (!special) {
-            visit1(c, s, j, x, y);
-        } else {
-            for (int ph = 0; ph < 6; ph++) {
+        if (phase == 0) visit1(c, s, j, x, y);
+        __syncwarp();
+        if (special) {
+            for (int ph = 1; ph <= 2; ph++) {  // FIRE cells: even lanes, then odd lanes (footprints +-2 columns, 8 apart)
+                unsigned fm = __ballot_sync(0xffffffffu, phase == ph);
+                while (fm) {
+                    const int src = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    fire_coop(c, s, jw - 4 * lane + 4 * src + cc, cx + 4 * src + cc, y, lane);
+                    __syncwarp();
+                }
+            }
+            for (int ph = 3; ph < 6; ph++) {  // interacting powders: lanes l % 3 (footprints +-5 columns, 12 apart)
                 if (__ballot_sync(0xffffffffu, phase == ph)) {
                     if (phase == ph) visit1(c, s, j, x, y);
                     __syncwarp();
                 }
             }
         }
-        __syncwarp();
     }
 }
 
@@ -824,13 +882,10 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
     const int cy = P.y0 + cyi * 2 * CHUNK;
 
     const DevTables* T = P.tabs;
-    for (int i = tid; i < FSE_MAX_MATERIALS; i += blockDim.x) {
-        S.lut.phys[i] = T->phys[i];
-        S.lut.iters[i] = T->iters[i];
-        S.lut.mflags[i] = T->mflags[i];
-        S.lut.slip[i] = T->slip[i];
-        S.lut.maxstab[i] = T->maxstab[i];
-        S.lut.dens[i] = T->density[i];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(&T->lut);
+        uint4* dst = reinterpret_cast<uint4*>(&S.lut);
+        for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
         for (int q = 0; q < RING; q++) mbar_init(&S.bar[q], 1);
@@ -849,6 +904,7 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
     c.rkey = P.rkey;
     c.tick = P.tick;
     c.iter = P.iter;
+    c.nmat = T->n;
     c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
 
     // prologue: rows -HALO_DN .. HALO_UP+PF-1
