@@ -191,6 +191,7 @@ FSE_API int fse_materials_set(fse_ctx* c, const fse_material* tbl, int n, const 
 static void free_world(fse_world* w) {
     cudaFree(w->p.mat); cudaFree(w->p.flg); cudaFree(w->p.stl); cudaFree(w->p.tmp); cudaFree(w->p.col); cudaFree(w->p.fl); cudaFree(w->p.fd);
     cudaFree(w->tmp_scratch); cudaFree(w->pbuf); cudaFree(w->pcount); cudaFree(w->d_stats); cudaFree(w->d_stage);
+    cudaFree(w->pbuf2); cudaFree(w->part_scratch); cudaFree(w->claim_keys); cudaFree(w->claim_vals);
     if (w->h_stats) cudaFreeHost(w->h_stats);
     for (auto& ev : w->kt_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (w->ev0) cudaEventDestroy(w->ev0);
@@ -436,6 +437,9 @@ FSE_API int fse_particles_reserve(fse_world* w, int64_t cap) {
     CK(cudaMalloc(&nb, sizeof(fse_particle) * (size_t)cap));
     if (n) CK(cudaMemcpy(nb, w->pbuf, sizeof(fse_particle) * (size_t)n, cudaMemcpyDeviceToDevice));
     cudaFree(w->pbuf);
+    cudaFree(w->pbuf2);
+    w->pbuf2 = nullptr;
+    w->pbuf2_bytes = 0;
     w->pbuf = nb;
     w->pcap = (unsigned int)cap;
     return FSE_OK;

@@ -34,6 +34,12 @@ struct fse_world {
     // particle settle scratch (fse_particles.cu)
     void* part_scratch = nullptr;
     size_t part_scratch_bytes = 0;
+    fse_particle* pbuf2 = nullptr;  // compaction target, swapped with pbuf every fse_particles_tick
+    size_t pbuf2_bytes = 0;
+    void* claim_keys = nullptr;
+    size_t claim_keys_bytes = 0;
+    void* claim_vals = nullptr;
+    size_t claim_vals_bytes = 0;
     // stats / staging
     void* d_stats = nullptr;
     void* h_stats = nullptr;
@@ -46,6 +52,8 @@ struct fse_world {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kt_events;
     uint64_t ticks = 0;
 };
+
+#define FSE_PARTICLE_ROUNDS 16  // deposit-resolution rounds per fse_particles_tick (losers retry next tick)
 
 namespace fse {
 extern thread_local std::string g_err;

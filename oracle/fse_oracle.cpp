@@ -948,6 +948,138 @@ void World::tick_particles(const Rect& tz) {
     cells.erase(std::remove_if(cells.begin(), cells.end(), [&](const Particle& c) { return c.y > H; }), cells.end());  // 2190
 }
 
+// ---- tickCells under the GPU's schedule (see header) ------------------------------------------
+void World::tick_particles_rounds(const Rect& tz, int max_rounds) {
+    const int W = width, H = height;
+    struct St {
+        int status = 0;  // 0 alive, 1 dead, 2 wants its start cell, 3 spiral search
+        Particle adv;
+        int lx = 0, ly = 0;
+        int sx = 0, sy = 0, sdx = 0, sdy = -1, sj = 0;
+        long cand = -1;
+        bool merge = false;
+    };
+    std::vector<St> st(cells.size());
+    // phase 1: integrate every particle against the unmodified grid (world.cpp:2032-2174)
+    for (size_t i = 0; i < cells.size(); i++) {
+        St& s = st[i];
+        Particle cur = cells[i];
+        s.status = 0;
+        do {
+            if (cur.temporary && cur.lifetime <= 0) { s.status = 1; break; }
+            if (cur.targetForce != 0) {
+                float tdx = cur.targetX - cur.x;
+                float tdy = cur.targetY - cur.y;
+                float normFac = sqrtf(tdx * tdx + tdy * tdy);
+                cur.vx += tdx / normFac * cur.targetForce;
+                cur.vy += tdy / normFac * cur.targetForce;
+                if (normFac < 100) {
+                    cur.vx *= 0.95f;
+                    cur.vy *= 0.95f;
+                }
+            }
+            int lx = (int)cur.x, ly = (int)cur.y;
+            s.lx = lx;
+            s.ly = ly;
+            if (cur.x < 0 || (int)(cur.x) >= W || cur.y < 0 || (int)(cur.y) >= H) { s.status = 1; break; }
+            if (!(lx >= tz.x && ly >= tz.y && lx < tz.x + tz.w && ly < tz.y + tz.h)) break;  // alive, untouched apart from attraction
+            cur.vx += cur.ax;
+            cur.vy += cur.ay;
+            int div = (int)((fabsf(cur.vx) + fabsf(cur.vy)) + 1);
+            float dvx = cur.vx / div;
+            float dvy = cur.vy / div;
+            bool done = false;
+            for (int k = 0; k < div && !done; k++) {
+                cur.x += dvx;
+                cur.y += dvy;
+                if (cur.x < 0 || (int)(cur.x) >= W || cur.y < 0 || (int)(cur.y) >= H) { s.status = 1; done = true; break; }
+                const Cell& here = tiles[(int)(cur.x) + (int)(cur.y) * W];
+                if (!cur.phase && here.mat->physicsType != AIR) {
+                    bool isObject = here.mat->physicsType == OBJECT;
+                    if (cur.inObjectState == 0) cur.inObjectState = isObject ? 1 : 2;
+                    else if (cur.inObjectState == 1 && !isObject) cur.inObjectState = 2;
+                    if (!isObject || cur.inObjectState == 2) {
+                        if (cur.temporary) { s.status = 1; done = true; break; }
+                        s.status = tiles[lx + ly * W].mat->physicsType != AIR ? 3 : 2;
+                        done = true;
+                        break;
+                    }
+                }
+            }
+            if (done) break;
+            if (cur.lifetime > 0) cur.lifetime--;
+        } while (false);
+        s.adv = cur;
+    }
+    // phase 2: deposit rounds, lowest id wins a contested cell
+    for (int r = 0; r < max_rounds; r++) {
+        std::vector<std::pair<long, uint64_t>> claims;
+        bool any = false;
+        for (size_t i = 0; i < cells.size(); i++) {
+            St& s = st[i];
+            if (s.status < 2) continue;
+            s.cand = -1;
+            s.merge = false;
+            const Particle& cur = s.adv;
+            if (s.status == 2) {
+                if (tiles[s.lx + s.ly * W].mat->physicsType == AIR) s.cand = s.lx + (long)s.ly * W;
+                else s.status = 3;
+            }
+            if (s.status == 3) {
+                while (s.sj < 32 * 32) {  // world.cpp:2116-2147 square spiral
+                    if ((-16 <= s.sx) && (s.sx <= 16) && (-16 <= s.sy) && (s.sy <= 16)) {
+                        int px = (int)(cur.x + s.sx), py = (int)(cur.y + s.sy);
+                        if (px >= 0 && py >= 0 && px < W && py < H) {
+                            const Cell& d = tiles[px + py * W];
+                            if (d.mat->physicsType == AIR) { s.cand = px + (long)py * W; break; }
+                            if (cur.tile.mat->physicsType == SOUP && cur.tile.mat == d.mat) { s.cand = px + (long)py * W; s.merge = true; break; }
+                        }
+                    }
+                    if ((s.sx == s.sy) || ((s.sx < 0) && (s.sx == -s.sy)) || ((s.sx > 0) && (s.sx == 1 - s.sy))) {
+                        int t = s.sdx;
+                        s.sdx = -s.sdy;
+                        s.sdy = t;
+                    }
+                    s.sx += s.sdx;
+                    s.sy += s.sdy;
+                    s.sj++;
+                }
+                if (s.cand < 0) {  // world.cpp:2154-2157: nothing free within the spiral -> bounce
+                    s.adv.vy = -4;
+                    s.adv.y -= 16;
+                    s.status = 0;
+                    continue;
+                }
+            }
+            claims.push_back({s.cand, cur.id});
+            any = true;
+        }
+        if (!any) break;
+        std::sort(claims.begin(), claims.end());
+        auto winner = [&](long cell) {
+            auto it = std::lower_bound(claims.begin(), claims.end(), std::make_pair(cell, (uint64_t)0));
+            return it->second;
+        };
+        for (size_t i = 0; i < cells.size(); i++) {
+            St& s = st[i];
+            if (s.status < 2 || s.cand < 0) continue;
+            if (winner(s.cand) != s.adv.id) continue;
+            if (s.merge) tiles[s.cand].fluidAmount += s.adv.tile.fluidAmount;  // 2131-2136
+            else tiles[s.cand] = s.adv.tile;                                   // 2127 / 2160
+            dirty[s.cand] = 1;
+            s.status = 1;
+        }
+    }
+    std::vector<Particle> keep;
+    for (size_t i = 0; i < cells.size(); i++) {
+        if (st[i].status == 1) continue;
+        const Particle& p = st[i].status == 0 ? st[i].adv : cells[i];  // still pending: retried next tick from its old state
+        if (p.y > H) continue;                                         // 2190
+        keep.push_back(p);
+    }
+    cells.swap(keep);
+}
+
 // ---- boundary helpers ------------------------------------------------------------------
 void World::write_rect(int x0, int y0, int w, int h, const fse_cell* src) {
     for (int y = 0; y < h; y++)

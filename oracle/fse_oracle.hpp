@@ -171,6 +171,10 @@ public:
     void tick_temperature(const Rect& zone);
     // world.cpp:2030-2195
     void tick_particles(const Rect& zone);
+    // Same per-particle rules under the GPU's deterministic schedule: every particle is integrated
+    // against the grid as it was at the start of the call, then deposits are resolved in rounds where the lowest
+    // particle id wins a contested cell.  Conflict-free particle sets give results identical to tick_particles().
+    void tick_particles_rounds(const Rect& zone, int max_rounds);
     void add_particle(const Particle& p) { cells.push_back(p); }
 
     // one chunk task under either schedule (exposed for the multi-process strip test, which

@@ -139,6 +139,12 @@ OAPI int fseo_tick_particles(void* p, const fse_rect* z) {
     return 0;
 }
 
+OAPI int fseo_tick_particles_rounds(void* p, const fse_rect* z, int max_rounds) {
+    Rect r{z->x, z->y, z->w, z->h};
+    ((World*)p)->tick_particles_rounds(r, max_rounds);
+    return 0;
+}
+
 OAPI void fseo_srand(unsigned s) { srand(s); }
 OAPI uint64_t fseo_cell_hash(int x, int y, const fse_cell* c) { return cell_hash(x, y, *c); }
 OAPI uint32_t fseo_rng_draw(uint32_t seed, uint32_t tick, uint32_t iter, int x, int y, uint32_t slot) {

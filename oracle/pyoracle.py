@@ -145,9 +145,14 @@ class OracleWorld:
     def particles_clear(self):
         self.L.fseo_particles_clear(self.h)
 
-    def particles_tick(self, zone=None):
+    def particles_tick(self, zone=None, schedule=PARTITIONED, max_rounds=16):
+        """tickCells: schedule=REFERENCE walks the list in order (world.cpp:2030-2195); PARTITIONED is the GPU's
+        snapshot + lowest-id-wins rounds."""
         z = zone or T.zone_of(self.width, self.height)
-        self.L.fseo_tick_particles(self.h, C.byref(z))
+        if schedule == REFERENCE:
+            self.L.fseo_tick_particles(self.h, C.byref(z))
+        else:
+            self.L.fseo_tick_particles_rounds(self.h, C.byref(z), max_rounds)
 
 
 def rng_draw(seed, tick, it, x, y, slot):

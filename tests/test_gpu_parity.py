@@ -71,6 +71,60 @@ def test_mixed_interactions_exact(oracle, gpu_ctx, table):
     _run_and_compare(ow, gw, 24, seed=11, every=3, what="interactions")
 
 
+def test_full_game_loop_exact(oracle, gpu_ctx, table):
+    """world::tick + tickCells (+ tickTemperature on tick % 4 == 2, game.cpp:2157) for 40 ticks: grid, dirty flags and
+    the particle pool stay bit-identical to the oracle under the partitioned schedule."""
+    W = H = 512
+    ow, gw = _pair(oracle, gpu_ctx, table, W, H)
+    Hh.build_column(ow, table, W, H)
+    Hh.build_column(gw, table, W, H)
+    for t in range(40):
+        for w in (ow, gw):
+            w.tick(t)
+            w.particles_tick()
+            if t % 4 == 2:
+                w.tick_temperature()
+        if t % 5 == 4:
+            Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"loop tick {t}")
+            Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), f"loop tick {t}")
+    assert gw.particles_count() > 0
+
+
+def test_particles_deposit_conflicts(oracle, gpu_ctx, table):
+    """Many particles aimed at the same few cells: exercises the claim rounds, the spiral search, liquid merging
+    and the bounce; conservation of cells + particles is checked as well."""
+    W = H = 384
+    ow, gw = _pair(oracle, gpu_ctx, table, W, H)
+    cells = Hh.empty_world_cells(table, W, H)
+    floor = G.cells_from_mat(table, np.full((8, W - 256), 7, dtype=np.uint16), 128, 250)
+    rng = np.random.default_rng(5)
+    n = 4000
+    parts = np.zeros(n, dtype=T.PARTICLE_DTYPE)
+    parts["x"] = 180 + rng.integers(0, 24, n)
+    parts["y"] = 200 + rng.integers(0, 30, n)
+    parts["vx"] = (rng.integers(0, 10, n) - 5) / 20.0
+    parts["vy"] = 1.0
+    parts["ay"] = 0.1
+    parts["fade_time"] = 60
+    parts["id"] = np.arange(1, n + 1)
+    is_water = rng.integers(0, 2, n) == 1
+    parts["tile"]["mat"] = np.where(is_water, 15, 2)
+    parts["tile"]["fluid"] = np.where(is_water, 0.25, 2.0)
+    parts["tile"]["color"] = 0x123456
+    for w in (ow, gw):
+        w.write_rect(0, 0, cells)
+        w.write_rect(128, 250, floor)
+        w.particles_add(parts)
+    for t in range(30):
+        ow.particles_tick()
+        gw.particles_tick()
+        Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"deposit tick {t}")
+        Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), f"deposit tick {t}")
+    s = gw.stats()
+    live = gw.particles_read()
+    assert s.count[2] + int((live["tile"]["mat"] == 2).sum()) == int((~is_water).sum())
+
+
 def test_stats_match(oracle, gpu_ctx, table):
     W = H = 512
     ow, gw = _pair(oracle, gpu_ctx, table, W, H)
