@@ -296,14 +296,15 @@ def run_ours(args):
     zone = world.tickZone
     n_particles = world.particles_count()
     world.particles_clear()
+    e2e_y0 = (world.own[0] if world_size > 1 else 0) + T.FSE_CHUNK
     barrier()
     t0 = time.perf_counter()
     for s in range(e2e_steps):
-        for i in range(n_chunks):  # top border row of chunks: where scrolled-in chunks land, outside the tickZone
-            world.write_rect_ptr(T.FSE_CHUNK * (1 + i), 0, T.FSE_CHUNK, T.FSE_CHUNK, pinned_np[i].ctypes.data)
+        for i in range(n_chunks):  # left border column of chunks (outside the tickZone), where scrolled-in chunks land
+            world.write_rect_ptr(0, e2e_y0 + T.FSE_CHUNK * i, T.FSE_CHUNK, T.FSE_CHUNK, pinned_np[i].ctypes.data)
         world.tick(tick_no, seed=args.seed, cell_iter=CELL_ITER)
         tick_no += 1
-        st = world.stats(T.Rect(zone.x, zone.y, zone.w, min(zone.h, 1024)))  # movingTiles-style histogram readback
+        st = world.stats(T.Rect(zone.x, e2e_y0, zone.w, 1024))  # movingTiles-style histogram readback
     barrier()
     e2e_s = time.perf_counter() - t0
     if dist:

@@ -79,7 +79,7 @@ struct DevStats {
     unsigned long long n_dirty, n_moved;
 };
 
-__global__ void stats_kernel(Planes p, int W, int x0, int y0, int rw, int rh, const DevTables* T, DevStats* out) {
+__global__ void stats_kernel(Planes p, int W, int x0, int y0, int rw, int rh, int yoff, const DevTables* T, DevStats* out) {
     __shared__ unsigned int cnt[FSE_MAX_MATERIALS];
     __shared__ double mass[FSE_MAX_MATERIALS];
     __shared__ unsigned long long sh_hash, sh_dirty, sh_moved;
@@ -98,7 +98,7 @@ __global__ void stats_kernel(Planes p, int W, int x0, int y0, int rw, int rh, co
         uint32_t col = p.col[g];
         int16_t tmp = p.tmp[g];
         float fl = p.fl[g], fd = p.fd[g];
-        uint64_t a = ((uint64_t)(uint32_t)x << 32) | (uint32_t)y;
+        uint64_t a = ((uint64_t)(uint32_t)x << 32) | (uint32_t)(y + yoff);  // hash on global coordinates
         uint64_t b = ((uint64_t)m << 48) | ((uint64_t)(f & F_MOVED) << 40) | ((uint64_t)st << 32) | col;
         uint64_t d = ((uint64_t)(uint16_t)tmp << 32) | __float_as_uint(fl);
         uint64_t hh = mix64(a + 0x9E3779B97F4A7C15ULL);
@@ -220,10 +220,10 @@ cudaError_t launch_clear_dirty(Planes p, size_t n, cudaStream_t s) {
     clear_dirty_kernel<<<grid_for(n / 16, 256), 256, 0, s>>>(reinterpret_cast<uint4*>(p.flg), n / 16);
     return cudaGetLastError();
 }
-cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, const DevTables* T, void* out, cudaStream_t s) {
+cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, int yoff, const DevTables* T, void* out, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(DevStats), s);
     if (e != cudaSuccess) return e;
-    stats_kernel<<<grid_for((size_t)rw * rh, 256), 256, 0, s>>>(p, W, x0, y0, rw, rh, T, (DevStats*)out);
+    stats_kernel<<<grid_for((size_t)rw * rh, 256), 256, 0, s>>>(p, W, x0, y0, rw, rh, yoff, T, (DevStats*)out);
     return cudaGetLastError();
 }
 size_t dev_stats_bytes() { return sizeof(DevStats); }

@@ -197,19 +197,22 @@ static void free_world(fse_world* w) {
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);
     if (w->stream) cudaStreamDestroy(w->stream);
+    if (w->comm_stream) cudaStreamDestroy(w->comm_stream);
+    if (w->ev_boundary) cudaEventDestroy(w->ev_boundary);
+    if (w->ev_comm) cudaEventDestroy(w->ev_comm);
+    cudaFree(w->d_chunk_lists);
     delete w;
 }
 
-FSE_API int fse_world_create(fse_ctx* c, int32_t width, int32_t height, fse_world** out) {
-    if (!c || !out) return fail(FSE_EINVAL, "fse_world_create: null argument");
-    if (!c->has_materials) return fail(FSE_ESTATE, "fse_world_create: call fse_materials_set first (materials_init/push, game.lua:65-66)");
-    if (width < 3 * CHUNK || height < 3 * CHUNK || width % 16 || width > (1 << 18) || height > (1 << 18))
-        return fail(FSE_EINVAL, "fse_world_create: %dx%d (need >= %d, width multiple of 16, <= 262144)", width, height, 3 * CHUNK);
+static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out) {
     CK(cudaSetDevice(c->device));
     fse_world* w = new fse_world();
     w->ctx = c;
     w->W = width;
     w->H = height;
+    w->Hglobal = height;
+    w->own_lo = 0;
+    w->own_hi = height;
     const size_t n = (size_t)width * height;
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
@@ -235,6 +238,65 @@ FSE_API int fse_world_create(fse_ctx* c, int32_t width, int32_t height, fse_worl
     return FSE_OK;
 }
 
+FSE_API int fse_world_create(fse_ctx* c, int32_t width, int32_t height, fse_world** out) {
+    if (!c || !out) return fail(FSE_EINVAL, "fse_world_create: null argument");
+    if (!c->has_materials) return fail(FSE_ESTATE, "fse_world_create: call fse_materials_set first (materials_init/push, game.lua:65-66)");
+    if (width < 3 * CHUNK || height < 3 * CHUNK || width % 16 || width > (1 << 18) || height > (1 << 18))
+        return fail(FSE_EINVAL, "fse_world_create: %dx%d (need >= %d, width multiple of 16, <= 262144)", width, height, 3 * CHUNK);
+    return make_world(c, width, height, out);
+}
+
+// One strip of a world partitioned across the ranks of fse_comm_init.  Cuts fall on chunk-row
+// boundaries of the default tickZone (y = 128 + 128*j); every rank keeps GHOST rows of its neighbours.
+static const int GHOST = 32;
+FSE_API int fse_strip_create(fse_ctx* c, int32_t width, int32_t height_global, fse_world** out) {
+    if (!c || !out) return fail(FSE_EINVAL, "fse_strip_create: null argument");
+    if (!c->has_materials) return fail(FSE_ESTATE, "fse_strip_create: call fse_materials_set first");
+    if (!c->nccl_comm && c->nranks > 1) return fail(FSE_ESTATE, "fse_strip_create: call fse_comm_init first");
+    if (width < 3 * CHUNK || width % 16 || width > (1 << 18) || height_global > (1 << 18) || height_global % CHUNK)
+        return fail(FSE_EINVAL, "fse_strip_create: %dx%d (width multiple of 16, height multiple of %d)", width, height_global, CHUNK);
+    const int nz = (height_global - 2 * CHUNK) / CHUNK;  // chunk rows of the tickZone
+    if (nz < c->nranks) return fail(FSE_EINVAL, "fse_strip_create: %d chunk rows cannot be split over %d ranks", nz, c->nranks);
+    const int j0 = (int)((int64_t)nz * c->rank / c->nranks), j1 = (int)((int64_t)nz * (c->rank + 1) / c->nranks);
+    const int own_lo = c->rank == 0 ? 0 : CHUNK + CHUNK * j0;
+    const int own_hi = c->rank == c->nranks - 1 ? height_global : CHUNK + CHUNK * j1;
+    const int y_off = own_lo - GHOST < 0 ? 0 : own_lo - GHOST;
+    const int y_end = own_hi + GHOST > height_global ? height_global : own_hi + GHOST;
+    fse_world* w = nullptr;
+    if (int r = make_world(c, width, y_end - y_off, &w)) return r;
+    w->strip = true;
+    w->y_off = y_off;
+    w->Hglobal = height_global;
+    w->own_lo = own_lo;
+    w->own_hi = own_hi;
+    cudaError_t e = cudaStreamCreateWithFlags(&w->comm_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->ev_boundary, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->ev_comm, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        free_world(w);
+        return fail(FSE_ECUDA, "fse_strip_create: %s", cudaGetErrorString(e));
+    }
+    *out = w;
+    return FSE_OK;
+}
+
+FSE_API int fse_strip_rows(fse_world* w, int32_t* own_lo, int32_t* own_hi, int32_t* held_lo, int32_t* held_hi) {
+    if (!w) return fail(FSE_EINVAL, "fse_strip_rows: null world");
+    if (own_lo) *own_lo = w->own_lo;
+    if (own_hi) *own_hi = w->own_hi;
+    if (held_lo) *held_lo = w->y_off;
+    if (held_hi) *held_hi = w->y_off + w->H;
+    return FSE_OK;
+}
+
+// Owner-authoritative refresh of the ghost rows (after edits outside fse_tick: write_rect, temperature, particles).
+FSE_API int fse_strip_refresh(fse_world* w) {
+    if (!w) return fail(FSE_EINVAL, "fse_strip_refresh: null world");
+    if (!w->strip || w->ctx->nranks == 1) return FSE_OK;
+    CK(cudaSetDevice(w->ctx->device));
+    return strip_refresh(w, w->stream);
+}
+
 FSE_API void fse_world_destroy(fse_world* w) {
     if (!w) return;
     cudaSetDevice(w->ctx->device);
@@ -248,9 +310,11 @@ FSE_API int fse_sync(fse_world* w) {
     return FSE_OK;
 }
 
+// Rects are in global coordinates; a strip world holds rows [y_off, y_off + H).
 static int check_rect(fse_world* w, int x, int y, int rw, int rh, const char* who) {
-    if (rw <= 0 || rh <= 0 || x < 0 || y < 0 || (int64_t)x + rw > w->W || (int64_t)y + rh > w->H)
-        return fail(FSE_EINVAL, "%s: rect (%d,%d,%d,%d) outside %dx%d world", who, x, y, rw, rh, w->W, w->H);
+    if (rw <= 0 || rh <= 0 || x < 0 || y < w->y_off || (int64_t)x + rw > w->W || (int64_t)y + rh > (int64_t)w->y_off + w->H)
+        return fail(FSE_EINVAL, "%s: rect (%d,%d,%d,%d) outside the held rows [%d,%d) of the %dx%d world", who, x, y, rw, rh, w->y_off,
+                    w->y_off + w->H, w->W, w->Hglobal);
     return FSE_OK;
 }
 
@@ -269,6 +333,7 @@ static const size_t STAGE_MAX_CELLS = (size_t)16 << 20;  // 320 MB of AoS stagin
 FSE_API int fse_write_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, const fse_cell* cells) {
     if (!w || !cells) return fail(FSE_EINVAL, "fse_write_rect: null argument");
     if (int r = check_rect(w, x, y, rw, rh, "fse_write_rect")) return r;
+    y -= w->y_off;
     CK(cudaSetDevice(w->ctx->device));
     const int nmat = w->ctx->h_tabs.n;
     int band = (int)(STAGE_MAX_CELLS / (size_t)rw);
@@ -291,6 +356,7 @@ FSE_API int fse_write_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32
 FSE_API int fse_read_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, fse_cell* cells) {
     if (!w || !cells) return fail(FSE_EINVAL, "fse_read_rect: null argument");
     if (int r = check_rect(w, x, y, rw, rh, "fse_read_rect")) return r;
+    y -= w->y_off;
     CK(cudaSetDevice(w->ctx->device));
     int band = (int)(STAGE_MAX_CELLS / (size_t)rw);
     if (band < 1) band = 1;
@@ -318,7 +384,7 @@ FSE_API int fse_stats_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32
     if (!w || !out) return fail(FSE_EINVAL, "fse_stats_rect: null argument");
     if (int r = check_rect(w, x, y, rw, rh, "fse_stats_rect")) return r;
     CK(cudaSetDevice(w->ctx->device));
-    CK(launch_stats(w->p, w->W, x, y, rw, rh, w->ctx->d_tabs, w->d_stats, w->stream));
+    CK(launch_stats(w->p, w->W, x, y - w->y_off, rw, rh, w->y_off, w->ctx->d_tabs, w->d_stats, w->stream));
     w->ctx->launches += 1;
     CK(cudaMemcpyAsync(w->h_stats, w->d_stats, dev_stats_bytes(), cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
@@ -332,9 +398,60 @@ static int check_zone(fse_world* w, const fse_rect& z, const char* who) {
     if (z.w <= 0 || z.h <= 0 || z.w % CHUNK || z.h % CHUNK)
         return fail(FSE_EINVAL, "%s: tick zone %dx%d must be a positive multiple of %d (chunk tasks are whole chunks, world.cpp:1073-1086)", who,
                     z.w, z.h, CHUNK);
-    if (z.x % 16 || z.x < 16 || z.y < 16 || z.x + z.w + 16 > w->W || z.y + z.h + 16 > w->H)
+    if (z.x % 16 || z.x < 16 || z.y < 16 || z.x + z.w + 16 > w->W || z.y + z.h + 16 > w->Hglobal)
         return fail(FSE_EINVAL, "%s: tick zone (%d,%d,%d,%d) needs x %% 16 == 0 and a >=16-cell margin inside the %dx%d world", who, z.x, z.y, z.w,
-                    z.h, w->W, w->H);
+                    z.h, w->W, w->Hglobal);
+    if (w->strip && (z.y - CHUNK) % CHUNK)
+        return fail(FSE_EINVAL, "%s: strip worlds are cut at y = 128 + 128*j; tick zone y=%d is not on that grid", who, z.y);
+    return FSE_OK;
+}
+
+struct KtScope {  // CUDA events around one launch of the dominant kernel (bench.py roofline)
+    fse_world* w;
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    int begin(cudaStream_t s) {
+        if (!w->kt_enabled) return FSE_OK;
+        if (w->kt_used < w->kt_events.size()) {
+            ev = w->kt_events[w->kt_used];
+        } else {
+            CK(cudaEventCreate(&ev.first));
+            CK(cudaEventCreate(&ev.second));
+            w->kt_events.push_back(ev);
+        }
+        w->kt_used++;
+        CK(cudaEventRecord(ev.first, s));
+        return FSE_OK;
+    }
+    int end(cudaStream_t s) {
+        if (w->kt_enabled) CK(cudaEventRecord(ev.second, s));
+        return FSE_OK;
+    }
+};
+
+// Per-phase chunk lists of a strip: [tk][0] = chunk rows touching a cut (launched first), [tk][1] = the rest.
+static int build_strip_lists(fse_world* w, const fse_rect& z, int j0, int j1) {
+    if (w->d_chunk_lists && memcmp(&w->list_zone, &z, sizeof z) == 0) return FSE_OK;
+    const int nx = z.w / CHUNK;
+    std::vector<int> all;
+    const bool up = w->ctx->rank > 0, down = w->ctx->rank + 1 < w->ctx->nranks;
+    for (int tk = 0; tk < 4; tk++) {
+        const int ofx = tk % 2, ofy = 1 - (tk / 2);
+        for (int part = 0; part < 2; part++) {
+            w->list_off[tk][part] = (int)all.size();
+            for (int j = j0; j < j1; j++) {
+                if ((j % 2) != ofy) continue;
+                const bool boundary = (up && j == j0) || (down && j == j1 - 1);
+                if (boundary != (part == 0)) continue;
+                for (int i = ofx; i < nx; i += 2) all.push_back((i / 2) | ((j / 2) << 16));
+            }
+            w->list_cnt[tk][part] = (int)all.size() - w->list_off[tk][part];
+        }
+    }
+    cudaFree(w->d_chunk_lists);
+    w->d_chunk_lists = nullptr;
+    CK(cudaMalloc(&w->d_chunk_lists, sizeof(int) * (all.size() + 1)));
+    if (!all.empty()) CK(cudaMemcpy(w->d_chunk_lists, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice));
+    w->list_zone = z;
     return FSE_OK;
 }
 
@@ -345,6 +462,18 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
     CK(cudaSetDevice(w->ctx->device));
     const fse_rect z = a->tick_zone;
     const int nx = z.w / CHUNK, ny = z.h / CHUNK;
+    // strip worlds: owned chunk rows [j0, j1) of the zone
+    int j0 = 0, j1 = ny;
+    if (w->strip) {
+        const int lo = w->ctx->rank == 0 ? z.y : w->own_lo, hi = w->ctx->rank == w->ctx->nranks - 1 ? z.y + z.h : w->own_hi;
+        j0 = (lo - z.y) / CHUNK;
+        j1 = (hi - z.y) / CHUNK;
+        if (j0 < 0) j0 = 0;
+        if (j1 > ny) j1 = ny;
+        if (int r = build_strip_lists(w, z, j0, j1)) return r;
+    }
+    const bool multi = w->strip && w->ctx->nranks > 1;
+    KtScope kt{w};
     for (int iter = 0; iter < a->cell_iter; iter++) {
         for (int tk = 0; tk < 4; tk++) {
             const int ofx = tk % 2;              // 0 1 0 1   (world.cpp:1059)
@@ -353,8 +482,9 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.p = w->p;
             P.W = w->W;
             P.H = w->H;
+            P.y_off = w->y_off;
             P.x0 = z.x + ofx * CHUNK;
-            P.y0 = z.y + ofy * CHUNK;
+            P.y0 = z.y - w->y_off + ofy * CHUNK;
             P.ncx = (nx - ofx + 1) / 2;
             P.ncy = (ny - ofy + 1) / 2;
             P.iter = iter;
@@ -365,36 +495,59 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.pcap = w->pcap;
             P.tabs = w->ctx->d_tabs;
             P.chunk_list = nullptr;
-            const int n_chunks = P.ncx * P.ncy;
-            if (n_chunks <= 0) continue;
-            std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-            if (w->kt_enabled) {
-                if (w->kt_used < w->kt_events.size()) {
-                    ev = w->kt_events[w->kt_used];
-                } else {
-                    CK(cudaEventCreate(&ev.first));
-                    CK(cudaEventCreate(&ev.second));
-                    w->kt_events.push_back(ev);
-                }
-                w->kt_used++;
-                CK(cudaEventRecord(ev.first, w->stream));
+            if (!w->strip) {
+                const int n_chunks = P.ncx * P.ncy;
+                if (n_chunks <= 0) continue;
+                if (int r = kt.begin(w->stream)) return r;
+                CK(launch_tick_phase(P, n_chunks, w->stream));
+                if (int r = kt.end(w->stream)) return r;
+                w->ctx->launches += 1;
+                continue;
             }
-            CK(launch_tick_phase(P, n_chunks, w->stream));
-            if (w->kt_enabled) CK(cudaEventRecord(ev.second, w->stream));
-            w->ctx->launches += 1;
+            // strip: boundary chunk rows first, halo rows over NCCL on the side stream, interior chunk rows meanwhile
+            P.y0 = z.y - w->y_off;  // chunk lists carry absolute (cxi, cyi) pairs: cy = y0 + cyi*256 (+128 via list parity)
+            P.x0 = z.x + ofx * CHUNK;
+            P.y0 += ofy * CHUNK;
+            if (int r = kt.begin(w->stream)) return r;
+            if (w->list_cnt[tk][0] > 0) {
+                P.chunk_list = w->d_chunk_lists + w->list_off[tk][0];
+                CK(launch_tick_phase(P, w->list_cnt[tk][0], w->stream));
+                w->ctx->launches += 1;
+            }
+            if (multi) {
+                CK(cudaEventRecord(w->ev_boundary, w->stream));
+                CK(cudaStreamWaitEvent(w->comm_stream, w->ev_boundary, 0));
+                if (int r = strip_exchange(w, ofy, j0, j1, z.y - w->y_off, w->comm_stream)) return r;
+                CK(cudaEventRecord(w->ev_comm, w->comm_stream));
+            }
+            if (w->list_cnt[tk][1] > 0) {
+                P.chunk_list = w->d_chunk_lists + w->list_off[tk][1];
+                CK(launch_tick_phase(P, w->list_cnt[tk][1], w->stream));
+                w->ctx->launches += 1;
+            }
+            if (int r = kt.end(w->stream)) return r;
+            if (multi) CK(cudaStreamWaitEvent(w->stream, w->ev_comm, 0));
         }
     }
     w->ticks++;
     return FSE_OK;
 }
 
-FSE_API int fse_tick_temperature(fse_world* w, const fse_rect* z) {
-    if (!w || !z) return fail(FSE_EINVAL, "fse_tick_temperature: null argument");
-    if (z->w <= 0 || z->h <= 0 || z->x < 1 || z->y < 1 || z->x + z->w + 1 > w->W || z->y + z->h + 1 > w->H)
+FSE_API int fse_tick_temperature(fse_world* w, const fse_rect* zg) {
+    if (!w || !zg) return fail(FSE_EINVAL, "fse_tick_temperature: null argument");
+    fse_rect zz = *zg;
+    if (w->strip) {  // own rows only; ghost rows are refreshed afterwards (owner-authoritative)
+        const int lo = zz.y > w->own_lo ? zz.y : w->own_lo, hi = zz.y + zz.h < w->own_hi ? zz.y + zz.h : w->own_hi;
+        zz.y = lo;
+        zz.h = hi - lo;
+    }
+    const fse_rect* z = &zz;
+    if (z->w <= 0 || z->h <= 0 || z->x < 1 || z->y - w->y_off < 1 || z->x + z->w + 1 > w->W || z->y - w->y_off + z->h + 1 > w->H)
         return fail(FSE_EINVAL, "fse_tick_temperature: zone (%d,%d,%d,%d) needs a 1-cell margin inside the world", z->x, z->y, z->w, z->h);
     CK(cudaSetDevice(w->ctx->device));
-    CK(launch_temperature(w->p, w->tmp_scratch, w->W, z->x, z->y, z->w, z->h, w->ctx->d_tabs, w->stream));
+    CK(launch_temperature(w->p, w->tmp_scratch, w->W, z->x, z->y - w->y_off, z->w, z->h, w->ctx->d_tabs, w->stream));
     w->ctx->launches += 2;
+    if (w->strip && w->ctx->nranks > 1) return strip_refresh(w, w->stream);
     return FSE_OK;
 }
 

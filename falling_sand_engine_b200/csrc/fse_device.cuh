@@ -108,7 +108,8 @@ struct Planes {
 struct TickParams {
     Planes p;
     int W, H;
-    int x0, y0;        // first chunk origin of this colour
+    int x0, y0;        // first chunk origin of this colour (local rows)
+    int y_off;         // global y of local row 0: strip worlds key the RNG on global coordinates
     int ncx, ncy;      // chunks of this colour along x / y (stride 2*CHUNK)
     int iter;
     uint32_t rkey;     // rng_key(seed, tick, iter)

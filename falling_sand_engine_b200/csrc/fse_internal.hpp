@@ -18,11 +18,23 @@ struct fse_ctx {
     bool has_materials = false;
     int max_reach = 0;
     std::atomic<int64_t> launches{0};
+    // multi-GPU (fse_comm.cu)
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
 };
 
 struct fse_world {
     fse_ctx* ctx = nullptr;
-    int W = 0, H = 0;
+    int W = 0, H = 0;  // local planes: H rows starting at global row y_off
+    // strip worlds (fse_strip_create): the world is Hglobal rows tall, this rank owns global rows [own_lo, own_hi)
+    // and holds [y_off, y_off + H) (owned rows + ghost rows).  Plain worlds: y_off = 0, Hglobal = H.
+    bool strip = false;
+    int y_off = 0, Hglobal = 0, own_lo = 0, own_hi = 0;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
+    int* d_chunk_lists = nullptr;  // cached per-phase boundary / interior chunk lists
+    fse_rect list_zone{0, 0, 0, 0};
+    int list_off[4][2]{}, list_cnt[4][2]{};
     fse::Planes p{};
     int16_t* tmp_scratch = nullptr;
     cudaStream_t stream = nullptr;
@@ -59,6 +71,8 @@ namespace fse {
 extern thread_local std::string g_err;
 int fail(int code, const char* fmt, ...);
 
+int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cudaStream_t s);
+int strip_refresh(fse_world* w, cudaStream_t s);
 size_t tick_smem_bytes();
 cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream);
 
@@ -66,7 +80,7 @@ cudaError_t launch_write_rect(Planes p, int W, int x0, int y0, int rw, int rh, c
 cudaError_t launch_read_rect(Planes p, int W, int x0, int y0, int rw, int rh, fse_cell* dst, cudaStream_t s);
 cudaError_t launch_fill_air(Planes p, size_t n, uint8_t air, cudaStream_t s);
 cudaError_t launch_clear_dirty(Planes p, size_t n, cudaStream_t s);
-cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, const DevTables* T, void* out, cudaStream_t s);
+cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, int yoff, const DevTables* T, void* out, cudaStream_t s);
 size_t dev_stats_bytes();
 cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int zx, int zy, int zw, int zh, const DevTables* T, cudaStream_t s);
 }  // namespace fse

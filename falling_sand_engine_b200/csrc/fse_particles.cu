@@ -225,6 +225,8 @@ using namespace fse;
 
 extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     if (!w || !z) return fail(FSE_EINVAL, "fse_particles_tick: null argument");
+    if (w->strip && w->ctx->nranks > 1)
+        return fail(FSE_ESTATE, "fse_particles_tick: particle migration between strips is not implemented yet (single-GPU worlds only)");
     CK(cudaSetDevice(w->ctx->device));
     unsigned int n = 0;
     CK(cudaMemcpyAsync(&n, w->pcount, sizeof n, cudaMemcpyDeviceToHost, w->stream));

@@ -77,6 +77,7 @@ struct Ctx {
     uint32_t tick;
     int iter;
     int nmat;
+    int yoff;  // global y of local row 0 (strip worlds), 0 otherwise
     int air, fire, water, lava, steam, obsidian;
 };
 
@@ -721,7 +722,7 @@ __device__ __forceinline__ uint32_t ld_word(const unsigned char* p) { return *re
 
 __device__ void pass1_row(const Ctx& c, int k, int cx, int cy, int lane) {
     const int s = slot_of_row(k);
-    const int y = cy + CHUNK - 1 - k;
+    const int y = cy + c.yoff + CHUNK - 1 - k;  // global row (RNG keys, particle positions)
     const int jw = HX8 + 4 * lane;
     // row-level vote: does any cell of this row act in pass 1, and does the row hold FIRE / interacting powders?
     uint32_t mw = ld_word(&MAT(s, jw));
@@ -787,7 +788,7 @@ __device__ void pass1_row(const Ctx& c, int k, int cx, int cy, int lane) {
 
 __device__ void pass2_row(const Ctx& c, int k, int cx, int cy, int lane) {
     const int s = slot_of_row(k);
-    const int y = cy + CHUNK - 1 - k;
+    const int y = cy + c.yoff + CHUNK - 1 - k;  // global row (RNG keys, particle positions)
     const int jw = HX8 + 4 * lane;
     uint32_t mw = ld_word(&MAT(s, jw));
     uint32_t fw = ld_word(&FLG(s, jw));
@@ -807,7 +808,7 @@ __device__ void pass2_row(const Ctx& c, int k, int cx, int cy, int lane) {
 
 __device__ void pass3_row(const Ctx& c, int k, int cx, int cy, int lane) {
     const int s = slot_of_row(k);
-    const int y = cy + CHUNK - 1 - k;
+    const int y = cy + c.yoff + CHUNK - 1 - k;  // global row (RNG keys, particle positions)
     const int jw = HX8 + 4 * lane;
     uint32_t mw = ld_word(&MAT(s, jw));
     uint32_t fw = ld_word(&FLG(s, jw));
@@ -905,6 +906,7 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
     c.tick = P.tick;
     c.iter = P.iter;
     c.nmat = T->n;
+    c.yoff = P.y_off;
     c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
 
     // prologue: rows -HALO_DN .. HALO_UP+PF-1

@@ -212,6 +212,21 @@ FSE_API int fse_particles_clear(fse_world* w);
 /* capacity of the device particle pool (default 1<<20); the reference's std::vector grows unbounded */
 FSE_API int fse_particles_reserve(fse_world* w, int64_t capacity);
 
+/* ---- multi-GPU: horizontal strips + NCCL halo rows (no reference counterpart) -----------
+ * One process per GPU.  Rank 0 makes a 128-byte id (fse_comm_unique_id), every rank gets it out of band and calls
+ * fse_comm_init; fse_strip_create then gives each rank the strip of chunk rows it owns plus ghost rows.  All rect /
+ * zone arguments stay in GLOBAL cell coordinates.  fse_tick on a strip world exchanges the rows around each cut after
+ * every colour phase (ncclSend/ncclRecv on a side stream, overlapped with the interior chunk rows); the result is
+ * bit-identical to the unpartitioned world. */
+FSE_API int fse_comm_unique_id(void* out128);
+FSE_API int fse_comm_init(fse_ctx* ctx, int rank, int nranks, const void* id128);
+FSE_API int fse_comm_destroy(fse_ctx* ctx);
+FSE_API int fse_strip_create(fse_ctx* ctx, int32_t width, int32_t height_global, fse_world** out);
+/* owned global rows [own_lo, own_hi) and held rows (owned + ghost) [held_lo, held_hi) */
+FSE_API int fse_strip_rows(fse_world* w, int32_t* own_lo, int32_t* own_hi, int32_t* held_lo, int32_t* held_hi);
+/* owner-authoritative ghost refresh after edits outside fse_tick (write_rect near a cut, particles) */
+FSE_API int fse_strip_refresh(fse_world* w);
+
 /* ---- measurement helpers ------------------------------------------------------- */
 /* CUDA events on the world's own stream (torch.cuda.Event only sees torch's). */
 FSE_API int fse_timer_start(fse_world* w);

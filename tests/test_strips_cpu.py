@@ -1,0 +1,66 @@
+"""Host-side logic of the multi-GPU path on CPU: strip layout, and the per-phase halo protocol run by two / three gloo
+ranks on oracle worlds must reproduce the single-process tick bit for bit (SURVEY.md §8c pin 8)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from falling_sand_engine_b200 import strips, types as T, worldgen as G
+from tests import helpers as Hh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_strip_layout_covers_world():
+    for H, n in ((1024, 2), (2048, 3), (8192, 8), (32768, 8), (640, 3)):
+        prev = 0
+        for r in range(n):
+            lo, hi, hlo, hhi, j0, j1 = strips.strip_layout(H, r, n)
+            assert lo == prev and hi > lo
+            assert hlo <= lo and hhi >= hi and 0 <= hlo and hhi <= H
+            if r > 0:
+                assert (lo - 128) % 128 == 0 and lo - hlo == strips.GHOST
+            assert j1 > j0
+            prev = hi
+        assert prev == H
+    with pytest.raises(ValueError):
+        strips.strip_layout(512, 0, 3)
+
+
+def test_phase_messages_pair_up():
+    H, n = 2048, 4
+    lay = [strips.strip_layout(H, r, n) for r in range(n)]
+    for ofy in (0, 1):
+        msgs = {r: strips.phase_messages(r, n, lay[r][4], lay[r][5], ofy) for r in range(n)}
+        for r in range(n):
+            for peer, kind, ylo, yhi in msgs[r]:
+                other = "recv" if kind == "send" else "send"
+                assert (r, other, ylo, yhi) in msgs[peer], (r, peer, kind, ylo, yhi)
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_strip_protocol_matches_single_world(oracle, table, tmp_path, nranks):
+    W, H, ticks = 384, 896, 6
+    out = str(tmp_path / "strip")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29500 + nranks), WORLD_SIZE=str(nranks), OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "strip_cpu_worker.py"), str(W), str(H), str(ticks), out],
+                              env=dict(env, RANK=str(r))) for r in range(nranks)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    ow = oracle.OracleWorld(W, H, table)
+    ow.write_rect(0, 0, G.mixed_band(table, W, H, 0, H, seed=77, blob=32))
+    for t in range(ticks):
+        ow.tick(t, seed=1337)
+    ref = ow.read_all()
+    rows = 0
+    parts = []
+    for r in range(nranks):
+        lo, hi = strips.strip_layout(H, r, nranks)[:2]
+        got = np.load(f"{out}.rank{r}.npy")
+        Hh.assert_cells_equal(ref[lo:hi], got, f"strip {r}/{nranks}")
+        rows += hi - lo
+        parts.append(np.load(f"{out}.parts{r}.npy"))
+    assert rows == H
+    Hh.assert_particles_equal(ow.particles_read(), np.concatenate(parts), "strip particles")
