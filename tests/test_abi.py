@@ -70,5 +70,5 @@ def test_worldgen_is_deterministic_and_band_independent():
     assert (whole["mat"][:128] == 1).all() and (whole["mat"][:, :128] == 1).all()  # GENERIC_SOLID border
     col = G.column_drop_band(t, 512, 512, 0, 512)
     assert (col["mat"] == 2).sum() > 0 and (col["mat"] == 15).sum() > 0
-    sp = G.sparse_band(t, 1024, 1024, 0, 1024)
-    assert (sp["mat"] == 7).mean() > 0.5
+    sp = G.sparse_band(t, 1024, 1024, 0, 1024, pockets=4)
+    assert np.isin(sp["mat"], (1, 7)).mean() > 0.7 and (sp["mat"] == 0).sum() > 0
