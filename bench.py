@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--active", type=int, default=-1, help="active-chunk tracking: 1 on, 0 off, -1 = on for --workload sparse")
     return ap.parse_args()
 
 
@@ -223,6 +224,9 @@ def run_ours(args):
         world = fse.World(ctx, W, H)
     zone_cells_total = (W - 2 * T.FSE_CHUNK) * (H - 2 * T.FSE_CHUNK)
     world.particles_reserve(1 << 25)
+    use_active = (args.active == 1 or (args.active < 0 and args.workload == "sparse")) and world_size == 1
+    if use_active:
+        world.active_enable(True)
 
     fn = band_fn(args, table, extra)
     y_lo, y_hi = world.owned_rows() if world_size > 1 else (0, H)
@@ -327,7 +331,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args, W, H, n), "cell_iter": CELL_ITER, "tick_zone": [W - 256, H - 256],
                        "ticks_per_s": args.steps / (ms * 1e-3), "l2": "state (17 B/cell, >=1.1 GB) is larger than the 126 MB L2",
-                       "parallelism": f"strips{n}" if n > 1 else "single"},
+                       "parallelism": f"strips{n}" if n > 1 else "single", "active_chunk_tracking": bool(use_active),
+                       "awake_chunks": list(world.active_stats()) if use_active else None},
             "roofline": roof,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,

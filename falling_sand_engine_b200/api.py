@@ -203,6 +203,17 @@ class World:
     def particles_reserve(self, cap):
         _ck(self.L.fse_particles_reserve(self.h, cap))
 
+    # -- active-region tracking (world::active / lastActive, world.hpp:131-133) ---------------------------
+    def active_enable(self, on=True):
+        self.L.fse_active_enable.argtypes = [C.c_void_p, C.c_int]
+        _ck(self.L.fse_active_enable(self.h, 1 if on else 0))
+
+    def active_stats(self):
+        self.L.fse_active_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        a, t = C.c_int64(), C.c_int64()
+        _ck(self.L.fse_active_stats(self.h, C.byref(a), C.byref(t)))
+        return a.value, t.value
+
     # -- measurement ----------------------------------------------------------------------------------
     def timer_start(self):
         _ck(self.L.fse_timer_start(self.h))

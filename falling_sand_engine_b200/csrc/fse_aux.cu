@@ -134,7 +134,7 @@ constexpr int TT_W = 64, TT_H = 16;
 
 __global__ void __launch_bounds__(256) temperature_kernel(const uint8_t* __restrict__ mat, const int16_t* __restrict__ tmp,
                                                           int16_t* __restrict__ out, int W, int zx, int zy, int zw, int zh,
-                                                          const DevTables* __restrict__ T) {
+                                                          const DevTables* __restrict__ T, uint8_t* awake, int acols, int yoff) {
     __shared__ int16_t st[TT_H + 2][TT_W + 2];
     __shared__ uint8_t sm[TT_H + 2][TT_W + 2];
     __shared__ float condO[FSE_MAX_MATERIALS];
@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(256) temperature_kernel(const uint8_t* __restr
             nt = (int)(addT[m0] + (uint32_t)t0);  // unsigned wrap, as u32 + i16 in the reference
         }
         out[(size_t)y * W + x] = (int16_t)nt;  // real_tiles[].temperature = newTemps[] (i16 wrap)
+        // active-region tracking: a temperature change can arm a reaction (world.cpp:1181-1204) in a sleeping chunk
+        if (awake && (int16_t)nt != (int16_t)t0 && (T->lut.mflags[m0] & MF_REACT)) awake[((y + yoff) / CHUNK) * acols + x / CHUNK] = 1;
     }
 }
 
@@ -228,9 +230,10 @@ cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, int yo
 }
 size_t dev_stats_bytes() { return sizeof(DevStats); }
 
-cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int zx, int zy, int zw, int zh, const DevTables* T, cudaStream_t s) {
+cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int zx, int zy, int zw, int zh, const DevTables* T, uint8_t* awake,
+                               int acols, int yoff, cudaStream_t s) {
     dim3 grid((zw + TT_W - 1) / TT_W, (zh + TT_H - 1) / TT_H);
-    temperature_kernel<<<grid, 256, 0, s>>>(p.mat, p.tmp, scratch, W, zx, zy, zw, zh, T);
+    temperature_kernel<<<grid, 256, 0, s>>>(p.mat, p.tmp, scratch, W, zx, zy, zw, zh, T, awake, acols, yoff);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     copy_zone_i16_kernel<<<grid_for((size_t)zw * zh, 256), 256, 0, s>>>(scratch, p.tmp, W, zx, zy, zw, zh);

@@ -201,6 +201,7 @@ static void free_world(fse_world* w) {
     if (w->ev_boundary) cudaEventDestroy(w->ev_boundary);
     if (w->ev_comm) cudaEventDestroy(w->ev_comm);
     cudaFree(w->d_chunk_lists);
+    cudaFree(w->d_awake); cudaFree(w->d_active_list); cudaFree(w->d_active_count);
     delete w;
 }
 
@@ -329,6 +330,7 @@ static int ensure_stage(fse_world* w, size_t cells) {
 }
 
 static const size_t STAGE_MAX_CELLS = (size_t)16 << 20;  // 320 MB of AoS staging at most
+static int wake_rect(fse_world* w, int x, int y_local, int rw, int rh);
 
 FSE_API int fse_write_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, const fse_cell* cells) {
     if (!w || !cells) return fail(FSE_EINVAL, "fse_write_rect: null argument");
@@ -347,6 +349,7 @@ FSE_API int fse_write_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32
             if (src[i].mat >= nmat) return fail(FSE_EINVAL, "fse_write_rect: cell material %u >= %d", src[i].mat, nmat);
         CK(cudaMemcpyAsync(w->d_stage, src, (size_t)hb * rw * sizeof(fse_cell), cudaMemcpyHostToDevice, w->stream));
         CK(launch_write_rect(w->p, w->W, x, y + yy, rw, hb, w->d_stage, w->stream));
+        if (int r = wake_rect(w, x, y + yy, rw, hb)) return r;
         w->ctx->launches += 1;
         if (yy + band < rh) CK(cudaStreamSynchronize(w->stream));  // the staging buffer is reused
     }
@@ -390,6 +393,52 @@ FSE_API int fse_stats_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32
     CK(cudaStreamSynchronize(w->stream));
     static_assert(sizeof(fse_stats) == 8 + 8 * FSE_MAX_MATERIALS * 2 + 16, "fse_stats layout");
     memcpy(out, w->h_stats, sizeof(fse_stats));  // DevStats and fse_stats share one layout
+    return FSE_OK;
+}
+
+// ---- active-region tracking ---------------------------------------------------------------------------------
+// wake every chunk a (local-coordinate) rect touches, with a 16-cell margin (footprints of the neighbours' rules)
+static int wake_rect(fse_world* w, int x, int y_local, int rw, int rh) {
+    if (!w->active_on) return FSE_OK;
+    const int yg = y_local + w->y_off;
+    int i0 = (x - 16) / CHUNK, i1 = (x + rw + 15) / CHUNK, j0 = (yg - 16) / CHUNK, j1 = (yg + rh + 15) / CHUNK;
+    if (i0 < 0) i0 = 0;
+    if (j0 < 0) j0 = 0;
+    if (i1 >= w->acols) i1 = w->acols - 1;
+    if (j1 >= w->arows) j1 = w->arows - 1;
+    if (i1 < i0 || j1 < j0) return FSE_OK;
+    CK(cudaMemset2DAsync(w->d_awake + (size_t)j0 * w->acols + i0, w->acols, 1, i1 - i0 + 1, j1 - j0 + 1, w->stream));
+    return FSE_OK;
+}
+
+// Turn per-chunk sleeping on/off.  While on, fse_tick compacts the awake chunks of each colour on the device and only
+// those run; the cell state is identical to a full sweep (dirty flags of sleeping chunks are not refreshed).
+FSE_API int fse_active_enable(fse_world* w, int enable) {
+    if (!w) return fail(FSE_EINVAL, "fse_active_enable: null world");
+    CK(cudaSetDevice(w->ctx->device));
+    if (enable && !w->d_awake) {
+        w->acols = w->W / CHUNK;
+        w->arows = w->Hglobal / CHUNK;
+        CK(cudaMalloc(&w->d_awake, (size_t)w->acols * w->arows));
+        CK(cudaMalloc(&w->d_active_list, sizeof(int) * ((size_t)w->acols * w->arows / 4 + w->acols + w->arows + 4)));
+        CK(cudaMalloc(&w->d_active_count, 64));
+    }
+    if (enable) CK(cudaMemsetAsync(w->d_awake, 1, (size_t)w->acols * w->arows, w->stream));
+    w->active_on = enable != 0;
+    return FSE_OK;
+}
+
+FSE_API int fse_active_stats(fse_world* w, int64_t* awake, int64_t* total) {
+    if (!w || !awake || !total) return fail(FSE_EINVAL, "fse_active_stats: null argument");
+    *total = 0;
+    *awake = 0;
+    if (!w->d_awake) return FSE_OK;
+    CK(cudaSetDevice(w->ctx->device));
+    std::vector<uint8_t> h((size_t)w->acols * w->arows);
+    CK(cudaMemcpyAsync(h.data(), w->d_awake, h.size(), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    *total = (int64_t)h.size();
+    for (uint8_t v : h) *awake += v != 0;
     return FSE_OK;
 }
 
@@ -495,9 +544,22 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.pcap = w->pcap;
             P.tabs = w->ctx->d_tabs;
             P.chunk_list = nullptr;
+            P.list_count = nullptr;
+            P.awake = nullptr;
+            P.acols = w->acols;
+            P.arows = w->arows;
+            P.never_sleep = 0;
             if (!w->strip) {
                 const int n_chunks = P.ncx * P.ncy;
                 if (n_chunks <= 0) continue;
+                if (w->active_on && z.x % CHUNK == 0 && z.y % CHUNK == 0) {
+                    CK(launch_compact_active(w->d_awake, w->acols, P.x0 / CHUNK, P.y0 / CHUNK, P.ncx, P.ncy, w->d_active_list,
+                                             w->d_active_count, w->stream));
+                    w->ctx->launches += 1;
+                    P.chunk_list = w->d_active_list;
+                    P.list_count = w->d_active_count;
+                    P.awake = w->d_awake;
+                }
                 if (int r = kt.begin(w->stream)) return r;
                 CK(launch_tick_phase(P, n_chunks, w->stream));
                 if (int r = kt.end(w->stream)) return r;
@@ -545,7 +607,8 @@ FSE_API int fse_tick_temperature(fse_world* w, const fse_rect* zg) {
     if (z->w <= 0 || z->h <= 0 || z->x < 1 || z->y - w->y_off < 1 || z->x + z->w + 1 > w->W || z->y - w->y_off + z->h + 1 > w->H)
         return fail(FSE_EINVAL, "fse_tick_temperature: zone (%d,%d,%d,%d) needs a 1-cell margin inside the world", z->x, z->y, z->w, z->h);
     CK(cudaSetDevice(w->ctx->device));
-    CK(launch_temperature(w->p, w->tmp_scratch, w->W, z->x, z->y - w->y_off, z->w, z->h, w->ctx->d_tabs, w->stream));
+    CK(launch_temperature(w->p, w->tmp_scratch, w->W, z->x, z->y - w->y_off, z->w, z->h, w->ctx->d_tabs, w->active_on ? w->d_awake : nullptr,
+                          w->acols, w->y_off, w->stream));
     w->ctx->launches += 2;
     if (w->strip && w->ctx->nranks > 1) return strip_refresh(w, w->stream);
     return FSE_OK;

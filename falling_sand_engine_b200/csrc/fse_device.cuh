@@ -118,7 +118,11 @@ struct TickParams {
     unsigned int* pcount;
     unsigned int pcap;
     const DevTables* tabs;
-    const int* chunk_list;  // optional compacted list of (cxi | cyi << 16) (active-chunk pass); null = all
+    const int* chunk_list;  // optional list of (cxi | cyi << 16) chunk coordinates of this colour; null = all
+    const int* list_count;  // optional device count of valid chunk_list entries (active-chunk pass; grid is over-provisioned)
+    uint8_t* awake;         // optional per-chunk awake flags over the whole world (acols x arows); null = tracking off
+    int acols, arows;
+    int never_sleep;        // strip worlds keep their cut-adjacent chunk rows awake
 };
 
 }  // namespace fse

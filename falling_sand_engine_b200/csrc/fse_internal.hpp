@@ -52,6 +52,12 @@ struct fse_world {
     size_t claim_keys_bytes = 0;
     void* claim_vals = nullptr;
     size_t claim_vals_bytes = 0;
+    // active-region tracking (fse_active_enable): awake flag per 128x128 chunk of the whole world
+    bool active_on = false;
+    uint8_t* d_awake = nullptr;
+    int acols = 0, arows = 0;
+    int* d_active_list = nullptr;   // compacted (cxi | cyi << 16) of the phase being launched
+    int* d_active_count = nullptr;
     // stats / staging
     void* d_stats = nullptr;
     void* h_stats = nullptr;
@@ -75,6 +81,7 @@ int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cuda
 int strip_refresh(fse_world* w, cudaStream_t s);
 size_t tick_smem_bytes();
 cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream);
+cudaError_t launch_compact_active(const uint8_t* awake, int acols, int ci0, int cj0, int ncx, int ncy, int* list, int* count, cudaStream_t s);
 
 cudaError_t launch_write_rect(Planes p, int W, int x0, int y0, int rw, int rh, const fse_cell* src, cudaStream_t s);
 cudaError_t launch_read_rect(Planes p, int W, int x0, int y0, int rw, int rh, fse_cell* dst, cudaStream_t s);
@@ -82,5 +89,6 @@ cudaError_t launch_fill_air(Planes p, size_t n, uint8_t air, cudaStream_t s);
 cudaError_t launch_clear_dirty(Planes p, size_t n, cudaStream_t s);
 cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, int yoff, const DevTables* T, void* out, cudaStream_t s);
 size_t dev_stats_bytes();
-cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int zx, int zy, int zw, int zh, const DevTables* T, cudaStream_t s);
+cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int zx, int zy, int zw, int zh, const DevTables* T, uint8_t* awake,
+                               int acols, int yoff, cudaStream_t s);
 }  // namespace fse

@@ -34,6 +34,8 @@ struct PArgs {
     long long* keys;
     unsigned long long* vals;
     unsigned int tmask;
+    uint8_t* awake;  // active-region flags (null = off)
+    int acols, arows;
 };
 
 __device__ __forceinline__ int phys_at(const PArgs& a, int x, int y) { return a.T->phys[a.p.mat[(size_t)y * a.W + x]]; }
@@ -188,6 +190,14 @@ __global__ void particles_commit_kernel(PArgs a) {
         a.p.fl[g] = t.fluid;
         a.p.fd[g] = t.fluid_diff;
     }
+    if (a.awake) {  // a deposit can un-settle the cells around it: wake the 3x3 chunks
+        const int ci = (int)(cand % a.W) / CHUNK, cj = (int)(cand / a.W) / CHUNK;
+        for (int dj = -1; dj <= 1; dj++)
+            for (int di = -1; di <= 1; di++) {
+                const int ni = ci + di, nj = cj + dj;
+                if (ni >= 0 && nj >= 0 && ni < a.acols && nj < a.arows) a.awake[nj * a.acols + ni] = 1;
+            }
+    }
     sp->status = 1;
 }
 
@@ -245,6 +255,8 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     a.n = n;
     a.counters = w->pcount;
     a.keys = nullptr; a.vals = nullptr; a.tmask = 0;
+    a.awake = w->active_on ? w->d_awake : nullptr;
+    a.acols = w->acols; a.arows = w->arows;
     const int B = 128;
     const int G = (int)((n + B - 1) / B);
     CK(cudaMemsetAsync(w->pcount + 1, 0, 2 * sizeof(unsigned int), w->stream));

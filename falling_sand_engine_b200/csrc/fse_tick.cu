@@ -52,7 +52,8 @@ struct __align__(128) Smem {
     unsigned char ring[RING * ROW_BYTES];
     Lut lut;
     unsigned long long bar[RING];
-    unsigned char rowmod[32];
+    unsigned char rowmod[32];  // row must be stored back (any plane or the dirty bit changed)
+    unsigned char rowchg[32];  // cell state other than the dirty bit changed (active-region tracking)
 };
 
 struct CellR {
@@ -69,6 +70,7 @@ struct Ctx {
     unsigned char* ring;
     const Lut* L;
     unsigned char* rowmod;
+    unsigned char* rowchg;
     const DevTables* T;
     fse_particle* pbuf;
     unsigned int* pcount;
@@ -158,6 +160,7 @@ __device__ __forceinline__ void stc(const Ctx& c, int s, int j, const CellR& r, 
     FL(s, j) = r.fl;
     FD(s, j) = r.fd;
     c.rowmod[s] = 1;
+    c.rowchg[s] = 1;
 }
 __device__ __forceinline__ void set_moved(const Ctx& c, int s, int j, bool v) {
     uint8_t f = FLG(s, j);
@@ -165,6 +168,7 @@ __device__ __forceinline__ void set_moved(const Ctx& c, int s, int j, bool v) {
     if (g != f) {
         FLG(s, j) = g;
         c.rowmod[s] = 1;
+        c.rowchg[s] = 1;
     }
 }
 __device__ __forceinline__ void set_bits(const Ctx& c, int s, int j, uint8_t bits) {  // dirty and/or visited
@@ -298,6 +302,7 @@ __device__ __forceinline__ void pour(const Ctx& c, int s, int j, int nbPhys, con
     } else {
         FD(s, j) = FD(s, j) + flow;
         c.rowmod[s] = 1;
+        c.rowchg[s] = 1;
     }
 }
 
@@ -452,6 +457,7 @@ __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
         if (tile.fl < FLUID_MinValue) {  // 1277-1281
             FL(s, j) = 0.0f;
             c.rowmod[s] = 1;
+            c.rowchg[s] = 1;
             return;
         }
         const uint8_t mb0 = MAT(sb, j);
@@ -673,10 +679,12 @@ __device__ void visit2(const Ctx& c, int s, int j, int x, int y) {
         if (a < FLUID_MinValue) {
             stc(c, s, j, nothing(c), F_DIRTY | F_VISITED);
         } else {
+            const float fd = FD(s, j);
             FL(s, j) = a;
             FD(s, j) = 0.0f;
             FLG(s, j) = f0 | F_DIRTY | F_VISITED;
             c.rowmod[s] = 1;
+            if (fd != 0.0f) c.rowchg[s] = 1;  // amount += 0 leaves the cell as it was (only dirty[] is re-set)
         }
     } else if (type == P_GAS) {  // 1799-1819
         const int st = rs(s, -1);
@@ -835,6 +843,7 @@ __device__ __forceinline__ void issue_row_load(const TickParams& P, Smem& S, int
     const size_t o8 = y * P.W + (cx - HX8);
     const size_t ow = y * P.W + (cx - HXW);
     S.rowmod[q] = 0;
+    S.rowchg[q] = 0;
     if (k < -HALO_WR) {  // probe-only rows: pass 2 reads material types down to y+10, nothing else
         mbar_expect_tx(bar, P8);
         bulk_g2s(row + OFF_MAT, P.p.mat + o8, P8, bar);
@@ -865,12 +874,56 @@ __device__ __forceinline__ void issue_row_store(const TickParams& P, Smem& S, in
     bulk_s2g(P.p.fd + ow, row + OFF_FD, PW * 4);
 }
 
+// ---- active-region tracking (new behaviour whose contract is "identical to a full sweep") --------------
+// A chunk may be skipped only if processing it again cannot change anything for ANY random draw.  When a finished row
+// leaves the ring the IO warp checks that each of its 128 cells is inert:
+//   AIR / SOLID / PASSABLE-but-not-FIRE : no rule applies;
+//   SAND : cannot sink below nor into either lower diagonal (world.cpp:1206, 1609-1610), moved == false (so pass 2 leaves
+//          it alone, 1647-1654), no pair interaction armed, its temperature reaction (if any) not firing;
+//   SOUP : settled (moved, 1307), fluidAmountDiff == 0, amount >= FLUID_MinValue, not over AIR (1283);
+//   GAS, FIRE : never inert (they roll dice every visit).
+// lane handles columns 4*lane .. 4*lane+3 of row slot q (qb = the row below).
+__device__ bool row_is_inert(const Ctx& c, int q, int qb, int lane) {
+    bool inert = true;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const int j = HX8 + 4 * lane + b;
+        const uint8_t m = MAT(q, j);
+        const int ph = c.L->phys[m];
+        if (ph == P_AIR || ph == P_SOLID) continue;
+        if (ph == P_PASSABLE) {
+            inert &= (int)m != c.fire;
+        } else if (ph == P_SAND) {
+            const float d = c.L->dens[m];
+            const uint8_t mf = c.L->mflags[m];
+            bool ok = !(FLG(q, j) & F_MOVED) && !can_sink(c, qb, j, d) && !can_sink(c, qb, j - 1, d) && !can_sink(c, qb, j + 1, d);
+            if (mf & MF_INTERACT) ok = ok && !has_interaction(c, m, MAT(qb, j));
+            if (mf & MF_REACT) {
+                if (mf & MF_REACT_MULTI) {
+                    ok = false;
+                } else {
+                    const Lut::Rx rx = c.L->rx[m];
+                    const int16_t t = TMP(q, j);
+                    ok = ok && !((rx.type == FSE_REACT_TEMPERATURE_BELOW && t < rx.thr) || (rx.type == FSE_REACT_TEMPERATURE_ABOVE && t > rx.thr));
+                }
+            }
+            inert &= ok;
+        } else if (ph == P_SOUP) {
+            inert &= (FLG(q, j) & F_MOVED) && FD(q, j) == 0.0f && FL(q, j) >= FLUID_MinValue && PHYS(qb, j) != P_AIR;
+        } else {
+            inert = false;
+        }
+    }
+    return inert;
+}
+
 __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constant__ TickParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     int cxi, cyi;
+    if (P.list_count && (int)blockIdx.x >= *P.list_count) return;  // over-provisioned grid of the active-chunk pass
     if (P.chunk_list) {
         int v = P.chunk_list[blockIdx.x];
         cxi = v & 0xffff;
@@ -898,6 +951,7 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
     c.ring = S.ring;
     c.L = &S.lut;
     c.rowmod = S.rowmod;
+    c.rowchg = S.rowchg;
     c.T = T;
     c.pbuf = P.pbuf;
     c.pcount = P.pcount;
@@ -915,6 +969,7 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
     }
     for (int k = -HALO_DN; k < HALO_UP; k++) mbar_wait(&S.bar[slot_of_row(k)], 0);
 
+    bool io_modified = false, io_inert = true;  // IO warp only (active-region tracking)
     for (int t = 0; t < N_STEPS; t++) {
         const int kw = t + HALO_UP;  // newest row this step may touch
         if (kw <= LAST_ROW) mbar_wait(&S.bar[slot_of_row(kw)], (uint32_t)(((kw + HALO_DN) / RING) & 1));
@@ -933,6 +988,8 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
             const int ks = t - STORE_LAG - 0;
             if (ks >= -HALO_WR && ks <= LAST_ROW) {
                 const int q = slot_of_row(ks);
+                if (P.awake && ks >= 0 && ks < CHUNK) io_inert &= row_is_inert(c, q, rs(q, 1), lane);
+                io_modified |= S.rowchg[q] != 0;
                 if (S.rowmod[q]) {
                     uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
                     for (int w = lane; w < P8 / 4; w += 32) fw[w] &= 0x7f7f7f7fU;  // tickVisited never reaches HBM
@@ -949,7 +1006,51 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
             }
         }
     }
-    if (warp == 3 && lane == 0) bulk_wait_all();
+    if (warp == 3) {
+        if (P.awake) {
+            // wake the 3x3 neighbourhood if anything changed; go to sleep if nothing changed and every cell is inert
+            const bool inert = __all_sync(0xffffffffu, io_inert);
+            const int ci = cx / CHUNK, cj = (cy + P.y_off) / CHUNK;
+            if (io_modified) {
+                if (lane < 9) {
+                    const int ni = ci + lane % 3 - 1, nj = cj + lane / 3 - 1;
+                    if (ni >= 0 && nj >= 0 && ni < P.acols && nj < P.arows) P.awake[nj * P.acols + ni] = 1;
+                }
+            } else if (inert && lane == 0 && !P.never_sleep) {
+                P.awake[cj * P.acols + ci] = 0;
+            }
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+}
+
+// ---- active-chunk compaction: awake chunks of one colour -> dense list + count (warp-aggregated append) --------------
+__global__ void compact_active_kernel(const uint8_t* __restrict__ awake, int acols, int ci0, int cj0, int ncx, int ncy, int* __restrict__ list,
+                                      int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = ncx * ncy;
+    bool on = false;
+    int v = 0;
+    if (i < n) {
+        const int cxi = i % ncx, cyi = i / ncx;
+        on = awake[(cj0 + 2 * cyi) * acols + (ci0 + 2 * cxi)] != 0;
+        v = cxi | (cyi << 16);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (on) list[base + __popc(m & ((1u << lane) - 1))] = v;
+}
+
+cudaError_t launch_compact_active(const uint8_t* awake, int acols, int ci0, int cj0, int ncx, int ncy, int* list, int* count, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    const int n = ncx * ncy;
+    compact_active_kernel<<<(n + 255) / 256, 256, 0, s>>>(awake, acols, ci0, cj0, ncx, ncy, list, count);
+    return cudaGetLastError();
 }
 
 // ---- host launcher ----------------------------------------------------------------------------------

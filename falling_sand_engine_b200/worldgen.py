@@ -218,8 +218,10 @@ def sparse_band(table, width, height, y0, rows, seed=1337, pockets=256):
     inner = (lx >= 8) & (lx < 120) & (ly >= 8) & (ly < 120)
     pk = np.broadcast_to(pocket & inner, mat.shape)
     mat[pk] = ids["AIR"]
-    sand_blk = np.broadcast_to(pocket & (lx >= 24) & (lx < 56) & (ly >= 16) & (ly < 48), mat.shape)
-    water_blk = np.broadcast_to(pocket & (lx >= 72) & (lx < 104) & (ly >= 16) & (ly < 48), mat.shape)
+    # a sand pillar and a water column standing on the pocket floor: they collapse / spread by the grid rules for
+    # hundreds of ticks (no free fall into particles), which keeps exactly the pocket chunks active
+    sand_blk = np.broadcast_to(pocket & (lx >= 40) & (lx < 46) & (ly >= 40) & (ly < 120), mat.shape)
+    water_blk = np.broadcast_to(pocket & (lx >= 80) & (lx < 88) & (ly >= 56) & (ly < 120), mat.shape)
     mat[sand_blk] = ids["GENERIC_SAND"]
     mat[water_blk] = ids["WATER"]
     # settled strata inside the rock: sealed sand and water lenses

@@ -212,6 +212,13 @@ FSE_API int fse_particles_clear(fse_world* w);
 /* capacity of the device particle pool (default 1<<20); the reference's std::vector grows unbounded */
 FSE_API int fse_particles_reserve(fse_world* w, int64_t capacity);
 
+/* ---- active-region tracking: world::active/lastActive (world.hpp:131-133) are allocated but dead in the reference
+ * (every writer is commented out), so the only contract is "same cells as a full sweep".  When
+ * enabled, each 128x128 chunk falls asleep once a pass over it changed nothing and every cell in it is provably
+ * inert, is woken by any write next to it, and fse_tick launches only the compacted list of awake chunks. */
+FSE_API int fse_active_enable(fse_world* w, int enable);
+FSE_API int fse_active_stats(fse_world* w, int64_t* awake_chunks, int64_t* total_chunks);
+
 /* ---- multi-GPU: horizontal strips + NCCL halo rows (no reference counterpart) -----------
  * One process per GPU.  Rank 0 makes a 128-byte id (fse_comm_unique_id), every rank gets it out of band and calls
  * fse_comm_init; fse_strip_create then gives each rank the strip of chunk rows it owns plus ghost rows.  All rect /

@@ -125,6 +125,55 @@ def test_particles_deposit_conflicts(oracle, gpu_ctx, table):
     assert s.count[2] + int((live["tile"]["mat"] == 2).sum()) == int((~is_water).sum())
 
 
+STATE_FIELDS = ["mat", "moved", "settle", "color", "temp", "fluid", "fluid_diff"]
+
+
+def test_active_tracking_equals_full_sweep(oracle, gpu_ctx, table):
+    """chunk sleeping has no reference behaviour to match beyond 'same cells as a full sweep'.  A sparse
+    world (sealed lenses of settled sand / water in rock + pockets of falling sand and water) is ticked with tracking
+    on, with tracking off, and by the oracle: identical cell state every few ticks (dirty flags of sleeping chunks are
+    not refreshed), and most chunks are asleep at the end."""
+    W, H = 1536, 1024
+    cells = G.sparse_band(table, W, H, 0, H, seed=11, pockets=6)
+    gpu_ctx.set_materials(table)
+    ga, gf = fse.World(gpu_ctx, W, H), fse.World(gpu_ctx, W, H)
+    ow = oracle.OracleWorld(W, H, table)
+    for w in (ga, gf, ow):
+        w.write_rect(0, 0, cells)
+    ga.active_enable(True)
+    awake0, total = ga.active_stats()
+    assert awake0 == total == (W // 128) * (H // 128)
+    for t in range(48):
+        for w in (ga, gf, ow):
+            w.tick(t)
+            w.particles_tick()
+            if t % 4 == 2:
+                w.tick_temperature()
+        if t % 8 == 7:
+            a, f, o = ga.read_all(), gf.read_all(), ow.read_all()
+            for fld in STATE_FIELDS:
+                assert a[fld].tobytes() == f[fld].tobytes() == o[fld].tobytes(), (t, fld)
+            Hh.assert_particles_equal(ga.particles_read(), gf.particles_read(), f"active tick {t}")
+    awake, total = ga.active_stats()
+    zone_chunks = (W // 128 - 2) * (H // 128 - 2)
+    awake_in_zone = awake - (total - zone_chunks)  # border chunks are never ticked, so they never fall asleep
+    assert 6 <= awake_in_zone <= 6 * 9, (awake_in_zone, zone_chunks)  # the 6 pockets (+ at most their 3x3 neighbourhoods)
+    # waking: drop a sand block into a sleeping region through the public write path and check it falls
+    blk = G.cells_from_mat(table, np.full((8, 8), 2, dtype=np.uint16), 700, 300)
+    air = G.cells_from_mat(table, np.zeros((60, 40), dtype=np.uint16), 690, 290)
+    for w in (ga, gf):
+        w.write_rect(690, 290, air)
+        w.write_rect(700, 300, blk)
+    for t in range(48, 60):
+        for w in (ga, gf):
+            w.tick(t)
+            w.particles_tick()
+    a, f = ga.read_all(), gf.read_all()
+    for fld in STATE_FIELDS:
+        assert a[fld].tobytes() == f[fld].tobytes(), fld
+    assert (a["mat"][300:308, 700:708] == 2).sum() < 64
+
+
 def test_stats_match(oracle, gpu_ctx, table):
     W = H = 512
     ow, gw = _pair(oracle, gpu_ctx, table, W, H)
