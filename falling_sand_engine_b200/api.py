@@ -203,6 +203,78 @@ class World:
     def particles_reserve(self, cap):
         _ck(self.L.fse_particles_reserve(self.h, cap))
 
+    # -- rigid-body bridge (game.cpp:1711-1815, 1896-1983) ---------------------------------------------------
+    def bodies_upload(self, bodies):
+        """bodies: list of (h, w) CELL_DTYPE arrays (RigidBody::tiles, index [ty, tx])."""
+        self._bodies = [np.ascontiguousarray(b, dtype=T.CELL_DTYPE) for b in bodies]
+        n = len(self._bodies)
+        descs = (T.BodyDesc * max(n, 1))()
+        for i, b in enumerate(self._bodies):
+            descs[i].w, descs[i].h = b.shape[1], b.shape[0]
+            descs[i].tiles = b.ctypes.data
+        self.L.fse_bodies_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        _ck(self.L.fse_bodies_upload(self.h, descs, n))
+
+    @staticmethod
+    def _xf(xforms):
+        xf = np.ascontiguousarray(xforms, dtype=np.float32).reshape(-1, 3)
+        return xf, len(xf)
+
+    def bodies_raster(self, xforms, tick=0, seed=1337):
+        xf, n = self._xf(xforms)
+        fb = np.zeros((n, 4), dtype=np.int32)
+        self.L.fse_bodies_raster.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]
+        _ck(self.L.fse_bodies_raster(self.h, xf.ctypes.data, n, tick, seed, fb.ctypes.data))
+        return fb
+
+    def bodies_erase(self, xforms):
+        xf, n = self._xf(xforms)
+        fb = np.zeros((n, 4), dtype=np.int32)
+        need = np.zeros(n, dtype=np.uint8)
+        self.L.fse_bodies_erase.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        _ck(self.L.fse_bodies_erase(self.h, xf.ctypes.data, n, fb.ctypes.data, need.ctypes.data))
+        return fb, need
+
+    def bodies_read(self, i):
+        out = np.zeros(self._bodies[i].shape, dtype=T.CELL_DTYPE)
+        self.L.fse_bodies_read.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        _ck(self.L.fse_bodies_read(self.h, i, out.ctypes.data))
+        return out
+
+    # -- fracture outlines (world.cpp:288-720, physics_math.cpp:1766-1965) and physicsCheck flood (world.cpp:3330) ------
+    def mask_outline(self, masks):
+        """masks: (n, h, w) uint8.  Returns (labels (n,h,w) int32, n_components (n,), contours: list per mask of (k,2) float arrays)."""
+        masks = np.ascontiguousarray(masks, dtype=np.uint8)
+        n, h, w = masks.shape
+        labels = np.zeros((n, h, w), dtype=np.int32)
+        ncomp = np.zeros(n, dtype=np.int32)
+        cap_pts, cap_c = int(masks.size) * 2 + 64, int(masks.size) // 2 + 64
+        pts = np.zeros((cap_pts, 2), dtype=np.float32)
+        pt_off = np.zeros(cap_c + 1, dtype=np.int32)
+        mask_off = np.zeros(n + 1, dtype=np.int32)
+        self.L.fse_mask_outline.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        _ck(self.L.fse_mask_outline(self.h, masks.ctypes.data, n, w, h, labels.ctypes.data, ncomp.ctypes.data, pts.ctypes.data, cap_pts,
+                                    pt_off.ctypes.data, cap_c, mask_off.ctypes.data))
+        contours = [[pts[pt_off[c]:pt_off[c + 1]].copy() for c in range(mask_off[m], mask_off[m + 1])] for m in range(n)]
+        return labels, ncomp, contours
+
+    def solid_mask(self, x, y, w, h):
+        out = np.zeros((h, w), dtype=np.uint8)
+        self.L.fse_solid_mask.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        _ck(self.L.fse_solid_mask(self.h, x, y, w, h, out.ctypes.data))
+        return out
+
+    def flood_component(self, x, y, cap=1000):
+        """physicsCheck(x, y): (count, bbox, pixel indices); count == cap + 1 means 'larger than cap'."""
+        cnt = C.c_int32()
+        bbox = np.zeros(4, dtype=np.int32)
+        pix = np.zeros(cap + 1, dtype=np.int32)
+        self.L.fse_flood_component.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
+        _ck(self.L.fse_flood_component(self.h, x, y, cap, C.byref(cnt), bbox.ctypes.data, pix.ctypes.data))
+        n = cnt.value
+        return n, bbox, pix[:n] if n <= cap else pix[:0]
+
     # -- active-region tracking (world::active / lastActive, world.hpp:131-133) ---------------------------
     def active_enable(self, on=True):
         self.L.fse_active_enable.argtypes = [C.c_void_p, C.c_int]

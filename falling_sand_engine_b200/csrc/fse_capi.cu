@@ -202,6 +202,8 @@ static void free_world(fse_world* w) {
     if (w->ev_comm) cudaEventDestroy(w->ev_comm);
     cudaFree(w->d_chunk_lists);
     cudaFree(w->d_awake); cudaFree(w->d_active_list); cudaFree(w->d_active_count);
+    fse_bodies_free(w);
+    cudaFree(w->outline_scratch);
     delete w;
 }
 

@@ -58,6 +58,11 @@ struct fse_world {
     int acols = 0, arows = 0;
     int* d_active_list = nullptr;   // compacted (cxi | cyi << 16) of the phase being launched
     int* d_active_count = nullptr;
+    // rigid-body bridge (fse_bodies.cu) and outline scratch (fse_outline.cu)
+    struct fse_bodies* bodies = nullptr;
+    int last_bridge_rounds = 0;
+    void* outline_scratch = nullptr;
+    size_t outline_scratch_bytes = 0;
     // stats / staging
     void* d_stats = nullptr;
     void* h_stats = nullptr;
@@ -70,6 +75,9 @@ struct fse_world {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kt_events;
     uint64_t ticks = 0;
 };
+
+struct fse_bodies;
+void fse_bodies_free(fse_world* w);
 
 #define FSE_PARTICLE_ROUNDS 16  // deposit-resolution rounds per fse_particles_tick (losers retry next tick)
 

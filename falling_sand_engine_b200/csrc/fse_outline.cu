@@ -1,0 +1,404 @@
+// fse_outline.cu — fracture detection and collider outlines on the GPU.
+//
+// Reference: world::updateRigidBodyHitbox / updateChunkMesh (source/engine/world.cpp:288-720, 722-959) trace every
+// perimeter of an alpha / SOLID mask with MarchingSquares::FindPerimeter and simplify it with Douglas-Peucker
+// (source/engine/physics/physics_math.cpp:1766-1965); world::physicsCheck (world.cpp:3330-3429) flood-fills a SOLID blob.
+// Here, per mask:
+//   * ccl_kernel            4-connected component labels (label = lowest pixel index of the component) by min-propagation
+//                           with pointer jumping in one CTA per mask;
+//   * contour_kernel        one thread per start candidate (world.cpp:412-451): it walks its marching-squares loop and
+//                           gives up as soon as it meets a lower-index candidate of the same loop, so exactly one thread
+//                           per loop survives — the order-free replacement of the reference's edgeSeen scan; the survivor
+//                           run-length-compresses the walk (physics_math.cpp:1951-1957), runs Douglas-Peucker with an
+//                           explicit stack (tolerance 1, first/last kept) and appends a contour record;
+//   * flood_kernel          bounded BFS (cap 1000) from a seed with a shared-memory hash set.
+// TPPL hole removal / ear clipping and b2Body creation stay on the host (they feed Box2D, which stays on the host).
+#include <algorithm>
+#include <vector>
+
+#include "fse_internal.hpp"
+
+namespace fse {
+
+// ---- marching squares (physics_math.cpp:1870-1949) -------------------------------------------------------------
+__device__ __forceinline__ bool ms_set(const uint8_t* d, int x, int y, int w, int h) {
+    return x <= 0 || x > w || y <= 0 || y > h ? false : d[(y - 1) * w + (x - 1)] != 0;
+}
+__device__ __forceinline__ int ms_value(const uint8_t* d, int x, int y, int w, int h) {
+    return (ms_set(d, x, y, w, h) ? 1 : 0) | (ms_set(d, x + 1, y, w, h) ? 2 : 0) | (ms_set(d, x, y + 1, w, h) ? 4 : 0) |
+           (ms_set(d, x + 1, y + 1, w, h) ? 8 : 0);
+}
+// direction codes: 1 East(1,0) 2 North(0,1) 3 West(-1,0) 4 South(0,-1); prev selects the branch at saddles 6 / 9
+__device__ __forceinline__ int ms_dir(int v, int prev) {
+    // nibble v of the constant = direction of case v: {0,2,1,1,3,2,-,1,4,-,4,4,3,2,3,0}
+    if (v == 6) return prev == 2 ? 3 : 1;
+    if (v == 9) return prev == 1 ? 2 : 4;
+    return (int)((0x0323440410231120ULL >> (4 * v)) & 0xF);
+}
+__device__ __forceinline__ int dir_dx(int d) { return d == 1 ? 1 : (d == 3 ? -1 : 0); }
+__device__ __forceinline__ int dir_dy(int d) { return d == 2 ? 1 : (d == 4 ? -1 : 0); }
+
+__device__ __forceinline__ bool is_candidate(const uint8_t* d, int i, int w, int h) {  // world.cpp:413-451
+    if (!d[i]) return false;
+    const int x = i % w, y = i / w;
+    int nb = 0;
+    if (x + 1 < w) nb += d[i + 1] != 0;
+    if (y + 1 < h) nb += d[i + w] != 0;
+    if (y + 1 < h && x + 1 < w) nb += d[i + w + 1] != 0;
+    if (nb == 3) return false;
+    const int v = ms_value(d, x, y, w, h);
+    return v != 0 && v != 15;
+}
+
+// physics_math.cpp:1813-1843
+__device__ __forceinline__ float p_distance(float x, float y, float x1, float y1, float x2, float y2) {
+    const float A = x - x1, B = y - y1, C = x2 - x1, D = y2 - y1;
+    const float dot = A * C + B * D;
+    const float len_sq = C * C + D * D;
+    float param = -1;
+    if (len_sq != 0) param = dot / len_sq;
+    float xx, yy;
+    if (param < 0) {
+        xx = x1;
+        yy = y1;
+    } else if (param > 1) {
+        xx = x2;
+        yy = y2;
+    } else {
+        xx = x1 + param * C;
+        yy = y1 + param * D;
+    }
+    const float dx = x - xx, dy = y - yy;
+    return sqrtf(dx * dx + dy * dy);
+}
+
+struct OutlineArgs {
+    const uint8_t* masks;
+    int n, w, h;
+    int32_t* labels;   // n*w*h
+    int* ncomp;        // n
+    float* pool;
+    unsigned int* pool_used;
+    unsigned int pool_cap;  // floats
+    int4* recs;        // {mask, candidate index, pool offset of the simplified points, n points}
+    unsigned int* n_recs;
+    unsigned int rec_cap;
+    int* overflow;
+};
+
+__global__ void ccl_kernel(OutlineArgs a) {
+    const int m = blockIdx.x;
+    const uint8_t* d = a.masks + (size_t)m * a.w * a.h;
+    int32_t* L = a.labels + (size_t)m * a.w * a.h;
+    const int n = a.w * a.h, w = a.w, h = a.h;
+    __shared__ int changed;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) L[i] = d[i] ? i : -1;
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) changed = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            int l = L[i];
+            if (l < 0) continue;
+            const int x = i % w, y = i / w;
+            int best = l;
+            if (x + 1 < w && L[i + 1] >= 0) best = min(best, L[i + 1]);
+            if (x > 0 && L[i - 1] >= 0) best = min(best, L[i - 1]);
+            if (y + 1 < h && L[i + w] >= 0) best = min(best, L[i + w]);
+            if (y > 0 && L[i - w] >= 0) best = min(best, L[i - w]);
+            best = min(best, L[best]);  // pointer jumping
+            if (best < l) {
+                L[i] = best;
+                atomicMin(&L[l], best);  // pull the old representative along
+                changed = 1;
+            }
+        }
+        __syncthreads();
+        if (!changed) break;
+        __syncthreads();
+    }
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine += L[i] == i;
+    atomicAdd(&cnt, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) a.ncomp[m] = cnt;
+}
+
+__global__ void contour_kernel(OutlineArgs a) {
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = a.w * a.h;
+    if (gi >= a.n * per) return;
+    const int m = gi / per, i = gi % per, w = a.w, h = a.h;
+    const uint8_t* d = a.masks + (size_t)m * per;
+    if (!is_candidate(d, i, w, h)) return;
+    const int sx = i % w, sy = i / w;
+    // first walk: canonical? how many direction runs?
+    int x = sx, y = sy, prev = 0, runs = 0;
+    do {
+        const int v = ms_value(d, x, y, w, h);
+        const int dir = ms_dir(v, prev);
+        if (!(x == sx && y == sy && prev == 0) && x >= 0 && y >= 0 && x < w && y < h) {
+            const int j = x + y * w;
+            if (j < i && is_candidate(d, j, w, h) && ms_dir(v, 0) == dir) return;  // a lower candidate owns this loop
+        }
+        if (dir != prev) runs++;
+        prev = dir;
+        x += dir_dx(dir);
+        y -= dir_dy(dir);
+    } while (x != sx || y != sy);
+    // scratch: px[runs] py[runs] mark[runs] stack[2*runs] out[2*runs]  (floats / ints of the same size)
+    const unsigned int need = 7u * (unsigned int)runs;
+    const unsigned int off = atomicAdd(a.pool_used, need);
+    if (off + need > a.pool_cap) {
+        atomicExch(a.overflow, 1);
+        return;
+    }
+    float* px = a.pool + off;
+    float* py = px + runs;
+    int* mark = reinterpret_cast<int*>(py + runs);
+    int* stack = mark + runs;
+    float* out = reinterpret_cast<float*>(stack + 2 * runs);
+    // second walk: one vertex at the end of every run (world.cpp:483-485)
+    x = sx; y = sy; prev = 0;
+    int k = -1;
+    do {
+        const int dir = ms_dir(ms_value(d, x, y, w, h), prev);
+        if (dir != prev) k++;
+        prev = dir;
+        x += dir_dx(dir);
+        y -= dir_dy(dir);
+        px[k] = (float)x;
+        py[k] = (float)y;
+    } while (x != sx || y != sy);
+    const int np = runs;
+    for (int q = 0; q < np; q++) mark[q] = 1;
+    if (np > 2) {  // simplify(worldMesh, 1) (physics_math.cpp:1766-1811), explicit stack instead of recursion
+        int sp = 0;
+        stack[sp++] = 0;
+        stack[sp++] = np - 1;
+        while (sp > 0) {
+            const int jj = stack[--sp], ii = stack[--sp];
+            if (ii + 1 == jj) continue;
+            float maxd = -1.0f;
+            int maxi = ii;
+            for (int q = ii + 1; q < jj; q++) {
+                const float dist = p_distance(px[q], py[q], px[ii], py[ii], px[jj], py[jj]);
+                if (dist > maxd) {
+                    maxd = dist;
+                    maxi = q;
+                }
+            }
+            if (maxd <= 1.0f) {
+                for (int q = ii + 1; q < jj; q++) mark[q] = 0;
+            } else {
+                stack[sp++] = ii; stack[sp++] = maxi;
+                stack[sp++] = maxi; stack[sp++] = jj;
+            }
+        }
+    }
+    int kept = 0;
+    for (int q = 0; q < np; q++)
+        if (mark[q]) {
+            out[2 * kept] = px[q];
+            out[2 * kept + 1] = py[q];
+            kept++;
+        }
+    if (kept < 3) return;  // world.cpp:490
+    const unsigned int r = atomicAdd(a.n_recs, 1u);
+    if (r >= a.rec_cap) {
+        atomicExch(a.overflow, 1);
+        return;
+    }
+    a.recs[r] = make_int4(m, i, (int)(off + 5u * (unsigned int)runs), kept);
+}
+
+__global__ void solid_mask_kernel(const uint8_t* mat, const DevTables* T, int W, int x0, int y0, int rw, int rh, uint8_t* out) {
+    const size_t n = (size_t)rw * rh;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = T->phys[mat[(size_t)(y0 + i / rw) * W + (x0 + i % rw)]] == P_SOLID;
+}
+
+// physicsCheck_flood (world.cpp:3413-3429): wavefront BFS of the 4-connected SOLID component, one CTA.
+constexpr int FLOOD_HASH = 8192;
+__global__ void flood_kernel(const uint8_t* mat, const DevTables* T, int W, int H, int sx, int sy, int cap, int* out_pixels, int* out_count) {
+    __shared__ int table[FLOOD_HASH];
+    __shared__ int q_head, q_tail, q_next;
+    for (int i = threadIdx.x; i < FLOOD_HASH; i += blockDim.x) table[i] = -1;
+    if (threadIdx.x == 0) {
+        q_head = 0;
+        q_tail = 0;
+        *out_count = 0;
+    }
+    __syncthreads();
+    if (T->phys[mat[(size_t)sy * W + sx]] != P_SOLID) return;
+    if (threadIdx.x == 0) {
+        const int p = sx + sy * W;
+        table[(unsigned)(p * 2654435761u) % FLOOD_HASH] = p;
+        out_pixels[0] = p;
+        q_tail = 1;
+    }
+    __syncthreads();
+    for (;;) {
+        const int head = q_head, tail = q_tail;
+        if (head >= tail || tail > cap) break;
+        if (threadIdx.x == 0) q_next = tail;
+        __syncthreads();
+        for (int f = head + threadIdx.x / 4; f < tail; f += blockDim.x / 4) {
+            const int p = out_pixels[f];
+            const int px = p % W, py = p / W, d = threadIdx.x & 3;
+            const int nx = px + (d == 0) - (d == 2), ny = py + (d == 1) - (d == 3);
+            if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
+            if (T->phys[mat[(size_t)ny * W + nx]] != P_SOLID) continue;
+            const int q = nx + ny * W;
+            unsigned hsh = (unsigned)(q * 2654435761u) % FLOOD_HASH;
+            bool fresh = false;
+            for (int probe = 0; probe < FLOOD_HASH; probe++) {
+                const int old = atomicCAS(&table[hsh], -1, q);
+                if (old == -1) { fresh = true; break; }
+                if (old == q) break;
+                hsh = (hsh + 1) % FLOOD_HASH;
+            }
+            if (fresh) {
+                const int slot = atomicAdd(&q_next, 1);
+                if (slot <= cap) out_pixels[slot] = q;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            q_head = tail;
+            q_tail = q_next;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_count = q_tail > cap ? cap + 1 : q_tail;
+}
+
+static cudaError_t grow_scratch(fse_world* w, size_t need) {
+    if (w->outline_scratch_bytes >= need) return cudaSuccess;
+    cudaFree(w->outline_scratch);
+    w->outline_scratch = nullptr;
+    w->outline_scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&w->outline_scratch, need);
+    if (e == cudaSuccess) w->outline_scratch_bytes = need;
+    return e;
+}
+
+}  // namespace fse
+
+using namespace fse;
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) return fail(FSE_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int32_t n_masks, int32_t mw, int32_t mh, int32_t* labels,
+                                        int32_t* n_components, float* pts, int32_t cap_pts, int32_t* pt_off, int32_t cap_contours,
+                                        int32_t* mask_off) {
+    if (!w || !masks || n_masks < 1 || mw < 1 || mh < 1 || mw > 2048 || mh > 2048 || !pts || !pt_off || !mask_off)
+        return fail(FSE_EINVAL, "fse_mask_outline: bad argument");
+    CK(cudaSetDevice(w->ctx->device));
+    const size_t per = (size_t)mw * mh, total = per * n_masks;
+    const unsigned int pool_cap = (unsigned int)std::min<size_t>((size_t)1 << 30, 16 * total + 4096);
+    const unsigned int rec_cap = (unsigned int)std::min<size_t>((size_t)1 << 26, total / 2 + 1024);
+    // scratch layout: masks | labels | ncomp | counters | recs | pool
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    size_t o_masks = 0, o_labels = up(total), o_ncomp = up(o_labels + total * 4), o_cnt = up(o_ncomp + (size_t)n_masks * 4),
+           o_recs = o_cnt + 256, o_pool = up(o_recs + (size_t)rec_cap * 16), bytes = o_pool + (size_t)pool_cap * 4;
+    CK(grow_scratch(w, bytes));
+    char* base = (char*)w->outline_scratch;
+    OutlineArgs a;
+    a.masks = (const uint8_t*)(base + o_masks);
+    a.n = n_masks; a.w = mw; a.h = mh;
+    a.labels = (int32_t*)(base + o_labels);
+    a.ncomp = (int*)(base + o_ncomp);
+    a.pool_used = (unsigned int*)(base + o_cnt);
+    a.n_recs = a.pool_used + 1;
+    a.overflow = (int*)(a.pool_used + 2);
+    a.recs = (int4*)(base + o_recs);
+    a.rec_cap = rec_cap;
+    a.pool = (float*)(base + o_pool);
+    a.pool_cap = pool_cap;
+    CK(cudaMemcpyAsync(base + o_masks, masks, total, cudaMemcpyHostToDevice, w->stream));
+    CK(cudaMemsetAsync(base + o_cnt, 0, 256, w->stream));
+    ccl_kernel<<<n_masks, 256, 0, w->stream>>>(a);
+    CK(cudaGetLastError());
+    contour_kernel<<<(unsigned int)((total + 127) / 128), 128, 0, w->stream>>>(a);
+    CK(cudaGetLastError());
+    w->ctx->launches += 2;
+    unsigned int hc[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(hc, base + o_cnt, sizeof hc, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    if (hc[2]) return fail(FSE_ENOMEM, "fse_mask_outline: contour scratch overflow (%u floats, %u contours)", hc[0], hc[1]);
+    const unsigned int nrec = hc[1];
+    std::vector<int4> recs(nrec);
+    std::vector<float> pool(hc[0]);
+    if (nrec) CK(cudaMemcpy(recs.data(), a.recs, sizeof(int4) * nrec, cudaMemcpyDeviceToHost));
+    if (hc[0]) CK(cudaMemcpy(pool.data(), a.pool, sizeof(float) * hc[0], cudaMemcpyDeviceToHost));
+    if (labels) CK(cudaMemcpy(labels, a.labels, total * 4, cudaMemcpyDeviceToHost));
+    if (n_components) CK(cudaMemcpy(n_components, a.ncomp, (size_t)n_masks * 4, cudaMemcpyDeviceToHost));
+    std::sort(recs.begin(), recs.end(), [](const int4& p, const int4& q) { return p.x != q.x ? p.x < q.x : p.y < q.y; });  // discovery order
+    size_t npts = 0;
+    for (auto& r : recs) npts += r.w;
+    if ((int64_t)nrec > cap_contours || (int64_t)npts > cap_pts)
+        return fail(FSE_ENOMEM, "fse_mask_outline: %u contours / %zu points exceed the caller's capacity (%d / %d)", nrec, npts, cap_contours, cap_pts);
+    size_t c = 0, o = 0;
+    for (int m = 0; m < n_masks; m++) {
+        mask_off[m] = (int32_t)c;
+        while (c < nrec && recs[c].x == m) {
+            pt_off[c] = (int32_t)o;
+            memcpy(pts + 2 * o, pool.data() + recs[c].z, sizeof(float) * 2 * recs[c].w);
+            o += recs[c].w;
+            c++;
+        }
+    }
+    mask_off[n_masks] = (int32_t)c;
+    pt_off[c] = (int32_t)o;
+    return FSE_OK;
+}
+
+extern "C" FSE_API int fse_solid_mask(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, uint8_t* mask) {
+    if (!w || !mask || rw <= 0 || rh <= 0 || x < 0 || y < w->y_off || x + rw > w->W || y + rh > w->y_off + w->H)
+        return fail(FSE_EINVAL, "fse_solid_mask: bad rect");
+    CK(cudaSetDevice(w->ctx->device));
+    CK(grow_scratch(w, (size_t)rw * rh));
+    solid_mask_kernel<<<148 * 4, 256, 0, w->stream>>>(w->p.mat, w->ctx->d_tabs, w->W, x, y - w->y_off, rw, rh, (uint8_t*)w->outline_scratch);
+    CK(cudaGetLastError());
+    w->ctx->launches += 1;
+    CK(cudaMemcpyAsync(mask, w->outline_scratch, (size_t)rw * rh, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return FSE_OK;
+}
+
+extern "C" FSE_API int fse_flood_component(fse_world* w, int32_t x, int32_t y, int32_t cap, int32_t* count, int32_t* bbox, int32_t* pixels) {
+    if (!w || !count || cap < 1 || cap > FLOOD_HASH / 4) return fail(FSE_EINVAL, "fse_flood_component: bad argument (cap <= %d)", FLOOD_HASH / 4);
+    *count = 0;
+    if (x < 0 || y < w->y_off || x >= w->W || y >= w->y_off + w->H) return FSE_OK;  // getTile(x,y) out of range: TEST_SOLID but no flood
+    CK(cudaSetDevice(w->ctx->device));
+    CK(grow_scratch(w, sizeof(int) * (size_t)(cap + 8)));
+    int* d_pix = (int*)w->outline_scratch;
+    int* d_cnt = d_pix + cap + 4;
+    flood_kernel<<<1, 256, 0, w->stream>>>(w->p.mat, w->ctx->d_tabs, w->W, w->H, x, y - w->y_off, cap, d_pix, d_cnt);
+    CK(cudaGetLastError());
+    w->ctx->launches += 1;
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, d_cnt, sizeof n, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    *count = n;
+    if (n == 0 || n > cap) return FSE_OK;
+    std::vector<int> px(n);
+    CK(cudaMemcpy(px.data(), d_pix, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    std::sort(px.begin(), px.end());
+    int bb[4] = {w->W, w->Hglobal, 0, 0};
+    for (int i = 0; i < n; i++) {
+        const int cx = px[i] % w->W, cy = px[i] / w->W + w->y_off;
+        bb[0] = std::min(bb[0], cx); bb[1] = std::min(bb[1], cy); bb[2] = std::max(bb[2], cx); bb[3] = std::max(bb[3], cy);
+        if (pixels) pixels[i] = cx + cy * w->W;
+    }
+    if (bbox) memcpy(bbox, bb, sizeof bb);
+    return FSE_OK;
+}

@@ -58,6 +58,10 @@ class Rect(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32)]
 
 
+class BodyDesc(C.Structure):
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("tiles", C.c_void_p)]
+
+
 class TickArgs(C.Structure):
     _fields_ = [("tick", C.c_uint32), ("seed", C.c_uint32), ("cell_iter", C.c_int32), ("tick_zone", Rect)]
 

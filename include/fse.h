@@ -212,6 +212,45 @@ FSE_API int fse_particles_clear(fse_world* w);
 /* capacity of the device particle pool (default 1<<20); the reference's std::vector grows unbounded */
 FSE_API int fse_particles_reserve(fse_world* w, int64_t capacity);
 
+/* ---- rigid-body bridge: the raster / erase loops of game::tick (game.cpp:1711-1815, 1896-1983) ---------------
+ * Box2D stays on the host (north_star); the host keeps b2Body poses and sends one fse_xform per body per tick.
+ * fse_body_desc mirrors RigidBody::matWidth / matHeight / tiles (game/player.hpp:15-65); AIR tiles are empty. */
+typedef struct fse_body_desc {
+    int32_t w, h;
+    const fse_cell* tiles; /* w*h, index tx + ty*w */
+} fse_body_desc;
+typedef struct fse_xform {
+    float x, y, angle; /* b2Body::GetPosition() / GetAngle() */
+} fse_xform;
+typedef struct fse_body_feedback {
+    int32_t sand_hits;  /* displaced SAND cells: host damps v *= 0.99, w *= 0.98 per hit (game.cpp:1796-1797) */
+    int32_t soup_hits;  /* displaced SOUP cells: v *= 0.998, w *= 0.99 (game.cpp:1806-1807)                    */
+    int32_t placed;     /* raster: pixels stamped; erase: pixels lifted back                                   */
+    int32_t destroyed;  /* erase: pixels found missing (tile becomes AIR, game.cpp:1959-1965)                  */
+} fse_body_feedback;
+/* replace the device copy of all bodies' tiles (once, and whenever the host changes a body) */
+FSE_API int fse_bodies_upload(fse_world* w, const fse_body_desc* bodies, int32_t n);
+/* stamp every body pixel into the grid, displacing sand/liquid into particles */
+FSE_API int fse_bodies_raster(fse_world* w, const fse_xform* xf, int32_t n, uint32_t tick, uint32_t seed, fse_body_feedback* out);
+/* lift the pixels back out; tiles that are gone are cleared; needs_update[b] = 1 as in game.cpp:1982 */
+FSE_API int fse_bodies_erase(fse_world* w, const fse_xform* xf, int32_t n, fse_body_feedback* out, uint8_t* needs_update);
+FSE_API int fse_bodies_read(fse_world* w, int32_t body, fse_cell* tiles_out);
+
+/* ---- fracture / hitbox outlines: updateRigidBodyHitbox, updateChunkMesh (world.cpp:288-720, 722-959) with
+ * MarchingSquares::FindPerimeter + simplify(...,1) (physics_math.cpp:1766-1965), physicsCheck flood (world.cpp:3330-3429).
+ * The device labels 4-connected components and extracts + simplifies every contour; TPPL hole removal / ear clipping
+ * and b2Body creation stay on the host.  `masks` holds n_masks images of w*h bytes (non-zero = solid pixel).
+ * labels (optional, n_masks*w*h int32): lowest pixel index of the pixel's component, -1 for empty pixels.
+ * Contours come back flattened: contour k of mask m is pts[2*pt_off[c] .. 2*pt_off[c+1]) with c = mask_off[m] + k. */
+FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int32_t n_masks, int32_t mw, int32_t mh, int32_t* labels,
+                             int32_t* n_components, float* pts, int32_t cap_pts, int32_t* pt_off, int32_t cap_contours,
+                             int32_t* mask_off);
+/* SOLID mask of a world rect (updateChunkMesh's input, world.cpp:722-760), written to `mask` (rw*rh bytes) */
+FSE_API int fse_solid_mask(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, uint8_t* mask);
+/* physicsCheck(x,y): size / bbox {minx,miny,maxx,maxy} / sorted pixel indices (x + y*width) of the 4-connected SOLID
+ * component at (x,y); *count = cap+1 when it exceeds cap, 0 when the seed is not SOLID.  pixels may be NULL. */
+FSE_API int fse_flood_component(fse_world* w, int32_t x, int32_t y, int32_t cap, int32_t* count, int32_t* bbox, int32_t* pixels);
+
 /* ---- active-region tracking: world::active/lastActive (world.hpp:131-133) are allocated but dead in the reference
  * (every writer is commented out), so the only contract is "same cells as a full sweep".  When
  * enabled, each 128x128 chunk falls asleep once a pass over it changed nothing and every cell in it is provably

@@ -1,0 +1,373 @@
+// bridge_oracle.cpp — CPU oracle (TEST INFRASTRUCTURE ONLY) for the rigid-body <-> grid bridge and the fracture outline
+// pipeline.  Citations relative to /root/reference/source/engine.
+//
+//   raster / erase        game.cpp:1711-1815 / 1896-1983 (sequential: bodies in order, pixels tx-major)
+//   marching squares      physics/physics_math.cpp:1870-1965 (value / FindPerimeter, saddles 6 and 9 by previous direction)
+//   Douglas-Peucker       physics/physics_math.cpp:1766-1843 (simplify / simplify_section / pDistance, tolerance 1)
+//   contour discovery     world.cpp:399-509 (updateRigidBodyHitbox) — see outlines() for the one documented deviation
+//   flood fill            world.cpp:3330-3429 (physicsCheck + 4-way flood, cap 1000)
+//   component labels      no reference counterpart (the reference assigns pixels by nearest triangle centroid,
+//                         world.cpp:587-610); north_star prescribes 4-connected labelling, checked against this CCL.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "fse_oracle.hpp"
+
+namespace fseo {
+
+enum { AIR = 0, SOLID = 1, SAND = 2, SOUP = 3 };
+
+static Cell from_pod(World* w, const fse_cell& s) {
+    Cell d;
+    d.mat = &w->mats[s.mat];
+    d.id = s.mat;
+    d.color = s.color;
+    d.temperature = s.temp;
+    d.moved = s.moved != 0;
+    d.settleCount = s.settle;
+    d.fluidAmount = s.fluid;
+    d.fluidAmountDiff = s.fluid_diff;
+    return d;
+}
+static void to_pod(const Cell& s, fse_cell& d) {
+    std::memset(&d, 0, sizeof d);
+    d.mat = (uint16_t)s.mat->id;
+    d.color = s.color;
+    d.temp = s.temperature;
+    d.moved = s.moved;
+    d.settle = s.settleCount;
+    d.fluid = s.fluidAmount;
+    d.fluid_diff = s.fluidAmountDiff;
+}
+
+static const int DIRS[5][2] = {{0, 0}, {1, 0}, {-1, 0}, {0, 1}, {0, -1}};  // game.cpp:1766
+
+// game.cpp:1711-1815.  tiles: per body w*h fse_cell (AIR = empty).  feedback[4*b] = {sand hits, soup hits, placed, 0}.
+void bodies_raster(World* W, int n, const int* bw, const int* bh, fse_cell* const* tiles, const fse_xform* xf, uint32_t tick,
+                   uint32_t seed, int32_t* feedback) {
+    const uint32_t key = rng_key(seed, tick, 7);
+    for (int b = 0; b < n; b++) {
+        const float x = xf[b].x, y = xf[b].y;
+        const float s = std::sin(xf[b].angle), c = std::cos(xf[b].angle);
+        int32_t* fb = feedback + 4 * b;
+        fb[0] = fb[1] = fb[2] = fb[3] = 0;
+        for (int tx = 0; tx < bw[b]; tx++)
+            for (int ty = 0; ty < bh[b]; ty++) {
+                const fse_cell& rm = tiles[b][tx + ty * bw[b]];
+                if ((int)rm.mat == W->ids.air) continue;
+                int wx = (int)(tx * c - (ty + 1) * s + x);
+                int wy = (int)(tx * s + (ty + 1) * c + y);
+                for (auto& d : DIRS) {
+                    int wxd = wx + d[0], wyd = wy + d[1];
+                    if (wxd < 0 || wyd < 0 || wxd >= W->width || wyd >= W->height) continue;
+                    Cell& cell = W->tiles[wxd + wyd * W->width];
+                    int ph = cell.mat->physicsType;
+                    if (ph == AIR) {
+                        cell = from_pod(W, rm);
+                        W->dirty[wxd + wyd * W->width] = 1;
+                        fb[2]++;
+                        break;
+                    } else if (ph == SAND || ph == SOUP) {
+                        Particle p;  // game.cpp:1791 / 1801: the displaced cell is thrown up as a loose particle
+                        p.tile = cell;
+                        p.x = (float)wxd;
+                        p.y = (float)(wyd - 3);
+                        uint32_t cb = rng_cell(key, b, tx + ty * bw[b]);
+                        p.vx = (float)(((int)(rng_draw(cb, S_BRIDGE_VX) % 10) - 5) / 10.0f);
+                        p.vy = (float)(-(int)(rng_draw(cb, S_BRIDGE_VY) % 5 + 5) / 10.0f);
+                        p.ax = 0;
+                        p.ay = 0.1f;
+                        p.id = (2ULL << 62) | ((uint64_t)(tick & 0xffff) << 40) | ((uint64_t)(b & 0xfffff) << 20) |
+                               (uint64_t)((tx + ty * bw[b]) & 0xfffff);
+                        W->add_particle(p);
+                        cell = from_pod(W, rm);
+                        W->dirty[wxd + wyd * W->width] = 1;
+                        fb[ph == SAND ? 0 : 1]++;
+                        fb[2]++;
+                        break;
+                    }
+                }
+            }
+    }
+}
+
+// game.cpp:1896-1983.  feedback[4*b+3] = pixels destroyed.
+void bodies_erase(World* W, int n, const int* bw, const int* bh, fse_cell* const* tiles, const fse_xform* xf, int32_t* feedback) {
+    for (int b = 0; b < n; b++) {
+        const float x = xf[b].x, y = xf[b].y;
+        const float s = std::sin(xf[b].angle), c = std::cos(xf[b].angle);
+        int32_t* fb = feedback + 4 * b;
+        fb[0] = fb[1] = fb[2] = fb[3] = 0;
+        for (int tx = 0; tx < bw[b]; tx++)
+            for (int ty = 0; ty < bh[b]; ty++) {
+                fse_cell& rm = tiles[b][tx + ty * bw[b]];
+                if ((int)rm.mat == W->ids.air) continue;
+                int wx = (int)(tx * c - (ty + 1) * s + x);
+                int wy = (int)(tx * s + (ty + 1) * c + y);
+                bool found = false;
+                for (auto& d : DIRS) {
+                    int wxd = wx + d[0], wyd = wy + d[1];
+                    if (wxd < 0 || wyd < 0 || wxd >= W->width || wyd >= W->height) continue;
+                    Cell& cell = W->tiles[wxd + wyd * W->width];
+                    if (cell.mat->id == rm.mat) {  // .id == rmat.id: any cell of the same material
+                        to_pod(cell, rm);
+                        cell = W->nothing();
+                        W->dirty[wxd + wyd * W->width] = 1;
+                        found = true;
+                        fb[2]++;
+                        break;
+                    }
+                }
+                if (!found) {  // game.cpp:1959-1965
+                    if (wx >= 0 && wy >= 0 && wx < W->width && wy < W->height && (int)W->tiles[wx + wy * W->width].mat->id == W->ids.air) {
+                        Cell nn = W->nothing();
+                        to_pod(nn, rm);
+                        fb[3]++;
+                    }
+                }
+            }
+    }
+}
+
+// ---- marching squares (physics_math.cpp:1893-1965) ----------------------------------------------------------
+static inline bool isSet(int x, int y, int w, int h, const uint8_t* d) { return x <= 0 || x > w || y <= 0 || y > h ? false : d[(y - 1) * w + (x - 1)] != 0; }
+static inline int msValue(int x, int y, int w, int h, const uint8_t* d) {
+    int sum = 0;
+    if (isSet(x, y, w, h, d)) sum |= 1;
+    if (isSet(x + 1, y, w, h, d)) sum |= 2;
+    if (isSet(x, y + 1, w, h, d)) sum |= 4;
+    if (isSet(x + 1, y + 1, w, h, d)) sum |= 8;
+    return sum;
+}
+// direction codes: 0 none, 1 East(1,0), 2 North(0,1), 3 West(-1,0), 4 South(0,-1)
+static inline int msDir(int v, int prev) {
+    switch (v) {
+        case 1: return 2;
+        case 2: return 1;
+        case 3: return 1;
+        case 4: return 3;
+        case 5: return 2;
+        case 6: return prev == 2 ? 3 : 1;
+        case 7: return 1;
+        case 8: return 4;
+        case 9: return prev == 1 ? 2 : 4;
+        case 10: return 4;
+        case 11: return 4;
+        case 12: return 3;
+        case 13: return 2;
+        case 14: return 3;
+    }
+    return 0;
+}
+static const int DX[5] = {0, 1, 0, -1, 0}, DY[5] = {0, 0, 1, 0, -1};
+
+// physics_math.cpp:1813-1843
+static float pDistance(float x, float y, float x1, float y1, float x2, float y2) {
+    float A = x - x1, B = y - y1, C = x2 - x1, D = y2 - y1;
+    float dot = A * C + B * D;
+    float len_sq = C * C + D * D;
+    float param = -1;
+    if (len_sq != 0) param = dot / len_sq;
+    float xx, yy;
+    if (param < 0) {
+        xx = x1;
+        yy = y1;
+    } else if (param > 1) {
+        xx = x2;
+        yy = y2;
+    } else {
+        xx = x1 + param * C;
+        yy = y1 + param * D;
+    }
+    float dx = x - xx, dy = y - yy;
+    return std::sqrt(dx * dx + dy * dy);
+}
+// physics_math.cpp:1766-1811 (the `omitted` guard only ever sees pts.size(), it is passed by value)
+static void simplify_section(const std::vector<float>& px, const std::vector<float>& py, float tol, size_t i, size_t j, std::vector<char>& mark) {
+    if (px.size() <= 2) return;
+    if (i + 1 == j) return;
+    float maxd = -1.0f;
+    size_t maxi = i;
+    for (size_t k = i + 1; k < j; k++) {
+        float d = pDistance(px[k], py[k], px[i], py[i], px[j], py[j]);
+        if (d > maxd) {
+            maxd = d;
+            maxi = k;
+        }
+    }
+    if (maxd <= tol) {
+        for (size_t k = i + 1; k < j; k++) mark[k] = 0;
+    } else {
+        simplify_section(px, py, tol, i, maxi, mark);
+        simplify_section(px, py, tol, maxi, j, mark);
+    }
+}
+
+// Contours of a w*h mask.  Discovery follows world.cpp:412-451: a start candidate is a set pixel whose right / down /
+// down-right neighbours are not all set and whose vertex value is not 0 or 15; FindPerimeter runs from it.  The
+// reference suppresses re-tracing with an `edgeSeen` pixel map updated while it scans (world.cpp:442, 464-481); here
+// a loop is emitted once, from the lowest-index candidate that lies on it (same loops and start points except for
+// edgeSeen's index-clamping artefacts at the mask border) — that rule is order-free, so the GPU can apply it in parallel.
+// Output: for each contour, simplified points (x0,y0,x1,y1,...), in discovery order.
+void outlines(const uint8_t* data, int w, int h, std::vector<std::vector<float>>& out) {
+    out.clear();
+    const int size = w * h;
+    auto is_cand = [&](int i) {
+        if (!data[i]) return false;
+        int x = i % w, y = i / w, nb = 0;
+        if (x + 1 < w) nb += data[i + 1] != 0;
+        if (y + 1 < h) nb += data[i + w] != 0;
+        if (y + 1 < h && x + 1 < w) nb += data[i + w + 1] != 0;
+        if (nb == 3) return false;
+        int v = msValue(x, y, w, h, data);
+        return v != 0 && v != 15;
+    };
+    for (int i = 0; i < size; i++) {
+        if (!is_cand(i)) continue;
+        const int sx = i % w, sy = i / w;
+        // trace (FindPerimeter, physics_math.cpp:1893-1965)
+        std::vector<int> dirs, lens;
+        int x = sx, y = sy, prev = 0;
+        bool canonical = true;
+        do {
+            int d = msDir(msValue(x, y, w, h, data), prev);
+            if (!(x == sx && y == sy && prev == 0)) {
+                // does a lower-index candidate start this same loop from here?
+                if (x >= 0 && y >= 0 && x < w && y < h) {
+                    int j = x + y * w;
+                    if (j < i && is_cand(j) && msDir(msValue(x, y, w, h, data), 0) == d) {
+                        canonical = false;
+                        break;
+                    }
+                }
+            }
+            if (d == prev) lens.back()++;
+            else {
+                dirs.push_back(d);
+                lens.push_back(1);
+                prev = d;
+            }
+            x += DX[d];
+            y -= DY[d];
+        } while (x != sx || y != sy);
+        if (!canonical) continue;
+        std::vector<float> px, py;
+        float lx = (float)sx, ly = (float)sy;
+        for (size_t k = 0; k < dirs.size(); k++) {  // world.cpp:483-485
+            lx += (float)(DX[dirs[k]] * lens[k]);
+            ly -= (float)(DY[dirs[k]] * lens[k]);
+            px.push_back(lx);
+            py.push_back(ly);
+        }
+        std::vector<char> mark(px.size(), 1);
+        if (!px.empty()) simplify_section(px, py, 1.0f, 0, px.size() - 1, mark);  // world.cpp:488
+        std::vector<float> poly;
+        for (size_t k = 0; k < px.size(); k++)
+            if (mark[k]) {
+                poly.push_back(px[k]);
+                poly.push_back(py[k]);
+            }
+        if (poly.size() < 6) continue;  // world.cpp:490: fewer than 3 points
+        out.push_back(poly);
+    }
+}
+
+// 4-connected component labels: label = lowest row-major pixel index of the component, -1 for unset pixels.
+int ccl(const uint8_t* data, int w, int h, int32_t* labels) {
+    const int n = w * h;
+    std::vector<int> stack;
+    for (int i = 0; i < n; i++) labels[i] = -1;
+    int count = 0;
+    for (int i = 0; i < n; i++) {
+        if (!data[i] || labels[i] >= 0) continue;
+        count++;
+        stack.assign(1, i);
+        labels[i] = i;
+        while (!stack.empty()) {
+            int p = stack.back();
+            stack.pop_back();
+            int x = p % w, y = p / w;
+            const int nb[4] = {x + 1 < w ? p + 1 : -1, y + 1 < h ? p + w : -1, x > 0 ? p - 1 : -1, y > 0 ? p - w : -1};
+            for (int q : nb)
+                if (q >= 0 && data[q] && labels[q] < 0) {
+                    labels[q] = i;
+                    stack.push_back(q);
+                }
+        }
+    }
+    return count;
+}
+
+// world.cpp:3330-3429: size, bounding box and pixels of the 4-connected SOLID component at (x, y); count = cap+1 when it
+// is larger than cap (the reference then does nothing), 0 when the seed is not SOLID.
+int flood_component(World* W, int x, int y, int cap, int* bbox, int32_t* pixels) {
+    if (x < 0 || y < 0 || x >= W->width || y >= W->height) return 0;
+    if (W->tiles[x + y * W->width].mat->physicsType != SOLID) return 0;
+    std::vector<int> stack{x + y * W->width}, seen;
+    std::vector<char> vis((size_t)W->width * W->height, 0);
+    vis[stack[0]] = 1;
+    while (!stack.empty()) {
+        int p = stack.back();
+        stack.pop_back();
+        seen.push_back(p);
+        if ((int)seen.size() > cap) return cap + 1;
+        int px = p % W->width, py = p / W->width;
+        const int nb[4][2] = {{px + 1, py}, {px, py + 1}, {px - 1, py}, {px, py - 1}};
+        for (auto& q : nb) {
+            if (q[0] < 0 || q[1] < 0 || q[0] >= W->width || q[1] >= W->height) continue;
+            int qi = q[0] + q[1] * W->width;
+            if (!vis[qi] && W->tiles[qi].mat->physicsType == SOLID) {
+                vis[qi] = 1;
+                stack.push_back(qi);
+            }
+        }
+    }
+    std::sort(seen.begin(), seen.end());
+    bbox[0] = W->width; bbox[1] = W->height; bbox[2] = 0; bbox[3] = 0;
+    for (size_t k = 0; k < seen.size(); k++) {
+        int px = seen[k] % W->width, py = seen[k] / W->width;
+        bbox[0] = std::min(bbox[0], px); bbox[1] = std::min(bbox[1], py);
+        bbox[2] = std::max(bbox[2], px); bbox[3] = std::max(bbox[3], py);
+        if (pixels) pixels[k] = seen[k];
+    }
+    return (int)seen.size();
+}
+
+}  // namespace fseo
+
+using namespace fseo;
+extern "C" {
+#define OAPI __attribute__((visibility("default")))
+
+OAPI int fseo_bodies_raster(void* p, int n, const int* bw, const int* bh, fse_cell* const* tiles, const fse_xform* xf, uint32_t tick,
+                            uint32_t seed, int32_t* feedback) {
+    bodies_raster((World*)p, n, bw, bh, tiles, xf, tick, seed, feedback);
+    return 0;
+}
+OAPI int fseo_bodies_erase(void* p, int n, const int* bw, const int* bh, fse_cell* const* tiles, const fse_xform* xf, int32_t* feedback) {
+    bodies_erase((World*)p, n, bw, bh, tiles, xf, feedback);
+    return 0;
+}
+// Flattened contours: pts (x,y pairs) and offsets[n_contours+1] in points; returns n_contours (or -needed if caps too small).
+OAPI int fseo_outlines(const uint8_t* data, int w, int h, float* pts, int cap_pts, int32_t* offsets, int cap_contours) {
+    std::vector<std::vector<float>> out;
+    outlines(data, w, h, out);
+    int total = 0;
+    for (auto& c : out) total += (int)c.size() / 2;
+    if ((int)out.size() > cap_contours || total > cap_pts) return -std::max((int)out.size(), total);
+    int o = 0;
+    for (size_t k = 0; k < out.size(); k++) {
+        offsets[k] = o;
+        std::memcpy(pts + 2 * o, out[k].data(), out[k].size() * sizeof(float));
+        o += (int)out[k].size() / 2;
+    }
+    offsets[out.size()] = o;
+    return (int)out.size();
+}
+OAPI int fseo_ccl(const uint8_t* data, int w, int h, int32_t* labels) { return ccl(data, w, h, labels); }
+OAPI int fseo_flood_component(void* p, int x, int y, int cap, int* bbox, int32_t* pixels) {
+    return flood_component((World*)p, x, y, cap, bbox, pixels);
+}
+}

@@ -20,7 +20,7 @@ RNG_SLOT, RNG_LIBC = 0, 1
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("fse_oracle.cpp", "oracle_capi.cpp", "fse_oracle.hpp", "outline_oracle.cpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("fse_oracle.cpp", "oracle_capi.cpp", "fse_oracle.hpp", "bridge_oracle.cpp")]
     srcs = [s for s in srcs if os.path.exists(s)] + [os.path.join(_HERE, "..", "include", "fse.h")]
     if not force and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return _LIB_PATH
@@ -153,6 +153,59 @@ class OracleWorld:
             self.L.fseo_tick_particles(self.h, C.byref(z))
         else:
             self.L.fseo_tick_particles_rounds(self.h, C.byref(z), max_rounds)
+
+
+def _body_args(bodies):
+    n = len(bodies)
+    bw = (C.c_int * max(n, 1))(*[b.shape[1] for b in bodies])
+    bh = (C.c_int * max(n, 1))(*[b.shape[0] for b in bodies])
+    ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in bodies])
+    return n, bw, bh, ptrs
+
+
+def bodies_raster(world, bodies, xforms, tick=0, seed=1337):
+    """game.cpp:1711-1815 on an OracleWorld; `bodies` = list of (h, w) CELL_DTYPE arrays (modified in place by erase)."""
+    n, bw, bh, ptrs = _body_args(bodies)
+    xf = np.ascontiguousarray(xforms, dtype=np.float32).reshape(-1, 3)
+    fb = np.zeros((n, 4), dtype=np.int32)
+    lib().fseo_bodies_raster(world.h, n, bw, bh, ptrs, xf.ctypes.data_as(C.c_void_p), C.c_uint32(tick), C.c_uint32(seed),
+                             fb.ctypes.data_as(C.c_void_p))
+    return fb
+
+
+def bodies_erase(world, bodies, xforms):
+    n, bw, bh, ptrs = _body_args(bodies)
+    xf = np.ascontiguousarray(xforms, dtype=np.float32).reshape(-1, 3)
+    fb = np.zeros((n, 4), dtype=np.int32)
+    lib().fseo_bodies_erase(world.h, n, bw, bh, ptrs, xf.ctypes.data_as(C.c_void_p), fb.ctypes.data_as(C.c_void_p))
+    return fb
+
+
+def outlines(mask):
+    """Contours of one (h, w) uint8 mask: list of (k, 2) float32 arrays (FindPerimeter + simplify(.., 1))."""
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    h, w = mask.shape
+    cap_p, cap_c = mask.size * 2 + 64, mask.size // 2 + 64
+    pts = np.zeros((cap_p, 2), dtype=np.float32)
+    off = np.zeros(cap_c + 1, dtype=np.int32)
+    n = lib().fseo_outlines(mask.ctypes.data_as(C.c_void_p), w, h, pts.ctypes.data_as(C.c_void_p), cap_p, off.ctypes.data_as(C.c_void_p), cap_c)
+    assert n >= 0
+    return [pts[off[k]:off[k + 1]].copy() for k in range(n)]
+
+
+def ccl(mask):
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    h, w = mask.shape
+    labels = np.zeros((h, w), dtype=np.int32)
+    n = lib().fseo_ccl(mask.ctypes.data_as(C.c_void_p), w, h, labels.ctypes.data_as(C.c_void_p))
+    return labels, n
+
+
+def flood_component(world, x, y, cap=1000):
+    bbox = np.zeros(4, dtype=np.int32)
+    pix = np.zeros(cap + 1, dtype=np.int32)
+    n = lib().fseo_flood_component(world.h, x, y, cap, bbox.ctypes.data_as(C.c_void_p), pix.ctypes.data_as(C.c_void_p))
+    return n, bbox, pix[:n] if n <= cap else pix[:0]
 
 
 def rng_draw(seed, tick, it, x, y, slot):

@@ -1,0 +1,99 @@
+"""CPU pins of the rigid-body bridge and outline oracle (SURVEY.md §8c pins 6 and 7)."""
+import numpy as np
+import pytest
+
+from falling_sand_engine_b200 import types as T
+from falling_sand_engine_b200 import worldgen as G
+from tests import helpers as Hh
+
+
+def make_body(table, w, h, mat=22, seed=1, fill=0.7):
+    """A w x h body of `mat` (OBSIDIAN) with hashed holes."""
+    hh = G.hash2(seed, np.arange(w, dtype=np.uint32)[None, :], np.arange(h, dtype=np.uint32)[:, None])
+    m = np.where((hh % np.uint32(100)) < int(fill * 100), mat, 0).astype(np.uint16)
+    return G.cells_from_mat(table, np.broadcast_to(m, (h, w)).copy(), 0, 0, seed)
+
+
+def test_marching_squares_square_and_orientation(oracle):
+    """Pin 6: a filled rectangle gives one closed 4-corner contour; Douglas-Peucker keeps >= 2 points and the corners."""
+    m = np.zeros((12, 16), dtype=np.uint8)
+    m[3:9, 4:12] = 1
+    cs = oracle.outlines(m)
+    assert len(cs) == 1
+    pts = cs[0]
+    # the reference starts at the first pixel whose right/down/diagonal neighbours are not all set — the top-right
+    # pixel (11,3) — and keeps the first and last vertex of the walk, so the start vertex stays on the top edge
+    # (vertex value 12 -> West, physics_math.cpp:1939); Douglas-Peucker (tolerance 1) then drops the corner (12,3), which
+    # lies 0.99 px from the chord (12,9)-(11,3)
+    assert pts.tolist() == [[4.0, 3.0], [4.0, 9.0], [12.0, 9.0], [11.0, 3.0]]
+    area2 = float(np.sum(pts[:, 0] * np.roll(pts[:, 1], -1) - np.roll(pts[:, 0], -1) * pts[:, 1]))
+    assert abs(abs(area2) - 2 * 8 * 6) <= 2 * 3.5
+
+
+def test_marching_squares_all_16_cases_close(oracle):
+    """Every 2x2 neighbourhood case occurs in a random mask; each traced loop is closed, axis-aligned and simplification
+    never invents points."""
+    rng = np.random.default_rng(3)
+    m = (rng.random((40, 40)) < 0.55).astype(np.uint8)
+    cs = oracle.outlines(m)
+    assert len(cs) >= 5
+    for pts in cs:
+        assert len(pts) >= 3
+        assert (pts >= 0).all() and (pts[:, 0] <= 40).all() and (pts[:, 1] <= 40).all()
+        assert np.all(pts == np.round(pts))
+
+
+def test_ccl_counts_components(oracle):
+    m = np.zeros((10, 10), dtype=np.uint8)
+    m[0:3, 0:3] = 1
+    m[5:8, 5:8] = 1
+    m[3, 3] = 1   # touches the first block only diagonally: a separate 4-connected component
+    labels, n = oracle.ccl(m)
+    assert n == 3
+    assert labels[0, 0] == 0 and labels[2, 2] == 0 and labels[3, 3] == 33 and labels[5, 5] == 55 and labels[9, 9] == -1
+
+
+def test_raster_erase_round_trip_is_identity(oracle, table):
+    """Pin 7: raster then erase of a static body on an empty grid restores both the grid and the body."""
+    W = H = 384
+    ow = oracle.OracleWorld(W, H, table)
+    ow.write_rect(0, 0, Hh.empty_world_cells(table, W, H))
+    before = ow.read_all()
+    body = make_body(table, 24, 20, fill=1.0)
+    orig = body.copy()
+    for angle in (0.0, 0.4, 1.3):
+        xf = [(180.0, 170.0, angle)]
+        fb = oracle.bodies_raster(ow, [body], xf)
+        assert fb[0, 2] > 0.9 * 24 * 20
+        grid = ow.read_all()
+        assert int((grid["mat"] == 22).sum()) == fb[0, 2]
+        fb2 = oracle.bodies_erase(ow, [body], xf)
+        assert fb2[0, 2] == fb[0, 2]
+        after = ow.read_all()
+        for f in ("mat", "color", "temp", "fluid"):
+            assert np.array_equal(after[f], before[f]), (angle, f)
+        if angle == 0.0:
+            assert fb[0, 2] == 24 * 20 and body.tobytes() == orig.tobytes()
+        body = orig.copy()
+
+
+def test_raster_displaces_sand_into_particles(oracle, table):
+    W = H = 384
+    ow = oracle.OracleWorld(W, H, table)
+    ow.write_rect(0, 0, Hh.empty_world_cells(table, W, H))
+    ow.write_rect(170, 170, G.cells_from_mat(table, np.full((10, 40), 2, dtype=np.uint16), 170, 170))
+    body = make_body(table, 16, 16, fill=1.0)
+    fb = oracle.bodies_raster(ow, [body], [(180.0, 165.0, 0.0)])
+    assert fb[0, 0] > 0 and ow.particles_count() == fb[0, 0]
+    assert int((ow.read_all()["mat"] == 2).sum()) + ow.particles_count() == 400
+
+
+def test_flood_component_sizes(oracle, table):
+    W = H = 384
+    ow = oracle.OracleWorld(W, H, table)
+    ow.write_rect(0, 0, Hh.empty_world_cells(table, W, H))
+    ow.write_rect(200, 200, G.cells_from_mat(table, np.full((5, 7), 7, dtype=np.uint16), 200, 200))
+    n, bbox, pix = oracle.flood_component(ow, 203, 202)
+    assert n == 35 and list(bbox) == [200, 200, 206, 204] and len(pix) == 35
+    assert oracle.flood_component(ow, 150, 150)[0] == 0          # AIR seed
+    assert oracle.flood_component(ow, 10, 10)[0] == 1001         # the solid border is larger than the cap

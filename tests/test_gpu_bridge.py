@@ -1,0 +1,138 @@
+"""Rigid-body bridge, fracture outlines and flood fill on the GPU vs the CPU oracle (bit-exact).  `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+import falling_sand_engine_b200 as fse
+from falling_sand_engine_b200 import types as T
+from falling_sand_engine_b200 import worldgen as G
+from tests import helpers as Hh
+from tests.test_bridge_cpu import make_body
+
+pytestmark = pytest.mark.gpu
+
+
+def _bodies(table, n, rng, size=(12, 33)):
+    bodies, xf = [], []
+    for i in range(n):
+        w, h = int(rng.integers(*size)), int(rng.integers(*size))
+        bodies.append(make_body(table, w, h, seed=100 + i, fill=0.7 if i % 3 else 1.0))
+        xf.append((float(rng.uniform(160, 850)), float(rng.uniform(160, 600)), float(rng.uniform(-3.1, 3.1))))
+    return bodies, np.array(xf, dtype=np.float32)
+
+
+def test_raster_erase_exact_and_sequential_order(oracle, gpu_ctx, table):
+    """Overlapping bodies over sand, water and air: the dependency rounds must reproduce the sequential loops
+    (game.cpp:1711-1815, 1896-1983) exactly — grid, body tiles, feedback counters and spawned particles."""
+    W, H = 1024, 768
+    gpu_ctx.set_materials(table)
+    gw, ow = fse.World(gpu_ctx, W, H), oracle.OracleWorld(W, H, table)
+    cells = G.mixed_band(table, W, H, 0, H, seed=21, air_frac=0.6, blob=48)
+    rng = np.random.default_rng(7)
+    bodies, xf = _bodies(table, 60, rng)
+    xf[1, :2] = xf[0, :2] + 5       # two pairs of overlapping bodies: cross-body order matters
+    xf[3, :2] = xf[2, :2] + (3, -2)
+    for w in (gw, ow):
+        w.write_rect(0, 0, cells)
+    ob = [b.copy() for b in bodies]
+    gw.bodies_upload(bodies)
+    for tick in range(3):
+        fb_o = oracle.bodies_raster(ow, ob, xf, tick=tick)
+        fb_g = gw.bodies_raster(xf, tick=tick)
+        assert np.array_equal(fb_o, fb_g), tick
+        Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"raster {tick}")
+        Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), f"raster {tick}")
+        for w in (gw, ow):
+            w.tick(tick)
+        fe_o = oracle.bodies_erase(ow, ob, xf)
+        fe_g, need = gw.bodies_erase(xf)
+        assert np.array_equal(fe_o, fe_g) and need.all()
+        Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"erase {tick}")
+        for i in range(len(bodies)):
+            assert gw.bodies_read(i).tobytes() == ob[i].tobytes(), (tick, i)
+        xf[:, 1] += 1.5       # bodies drift down a little between ticks (the host's Box2D step)
+        xf[:, 2] += 0.05
+
+
+def test_round_trip_identity_on_empty_grid(gpu_ctx, table):
+    W = H = 384
+    gpu_ctx.set_materials(table)
+    gw = fse.World(gpu_ctx, W, H)
+    gw.write_rect(0, 0, Hh.empty_world_cells(table, W, H))
+    before = gw.read_all()
+    body = make_body(table, 24, 20, fill=1.0)
+    gw.bodies_upload([body])
+    xf = [(180.0, 170.0, 0.0)]
+    fb = gw.bodies_raster(xf)
+    assert fb[0, 2] == 480
+    fe, _ = gw.bodies_erase(xf)
+    assert fe[0, 2] == 480 and fe[0, 3] == 0
+    after = gw.read_all()
+    for f in ("mat", "color", "temp", "fluid", "moved"):
+        assert np.array_equal(after[f], before[f]), f
+    assert gw.bodies_read(0).tobytes() == body.tobytes()
+
+
+def test_outlines_and_labels_match_oracle(oracle, gpu_ctx, table):
+    gpu_ctx.set_materials(table)
+    gw = fse.World(gpu_ctx, 384, 384)
+    rng = np.random.default_rng(11)
+    masks = []
+    for k in range(24):
+        m = (rng.random((48, 64)) < (0.35 + 0.02 * k)).astype(np.uint8)
+        if k % 4 == 0:
+            m[10:30, 8:50] = 1
+            m[15:20, 20:30] = 0  # a hole
+        if k % 5 == 0:
+            m[:, :] = 0
+            m[5:40, 5:9] = 1     # a crack: two separate pieces
+            m[5:40, 11:60] = 1
+        masks.append(m)
+    masks = np.stack(masks)
+    labels, ncomp, contours = gw.mask_outline(masks)
+    for k in range(len(masks)):
+        lo, no = oracle.ccl(masks[k])
+        assert no == ncomp[k], k
+        assert np.array_equal(lo, labels[k]), k
+        co = oracle.outlines(masks[k])
+        assert len(co) == len(contours[k]), (k, len(co), len(contours[k]))
+        for a, b in zip(co, contours[k]):
+            assert a.tobytes() == b.tobytes(), k
+    assert ncomp[5] == 2  # the cracked plate fell into two pieces
+
+
+def test_chunk_solid_mask_outline(oracle, gpu_ctx, table):
+    """updateChunkMesh (world.cpp:722-959): SOLID mask of a 128x128 chunk -> contours."""
+    W = H = 512
+    gpu_ctx.set_materials(table)
+    gw = fse.World(gpu_ctx, W, H)
+    cells = G.mixed_band(table, W, H, 0, H, seed=5, blob=24)
+    gw.write_rect(0, 0, cells)
+    phys = table.physics()
+    m = gw.solid_mask(128, 128, 128, 128)
+    assert np.array_equal(m, (phys[cells["mat"][128:256, 128:256]] == T.SOLID).astype(np.uint8))
+    labels, ncomp, contours = gw.mask_outline(m[None])
+    co = oracle.outlines(m)
+    assert len(co) == len(contours[0]) > 0
+    for a, b in zip(co, contours[0]):
+        assert a.tobytes() == b.tobytes()
+
+
+def test_flood_component_matches_oracle(oracle, gpu_ctx, table):
+    W = H = 512
+    gpu_ctx.set_materials(table)
+    gw, ow = fse.World(gpu_ctx, W, H), oracle.OracleWorld(W, H, table)
+    cells = Hh.empty_world_cells(table, W, H)
+    rng = np.random.default_rng(2)
+    blob = (rng.random((60, 60)) < 0.62)
+    cells["mat"][200:260, 200:260] = np.where(blob, 7, 0)
+    cells["mat"][300, 150:400] = 7          # a 250-long line: many BFS wavefronts
+    cells["mat"][320:360, 150:190] = 7      # 1600 cells: over the cap
+    for w in (gw, ow):
+        w.write_rect(0, 0, cells)
+    seeds = [(x, y) for y in range(200, 260, 7) for x in range(200, 260, 7)] + [(200, 300), (399, 300), (160, 330), (10, 10), (140, 140)]
+    for (x, y) in seeds:
+        no, bo, po = oracle.flood_component(ow, x, y)
+        ng, bg, pg = gw.flood_component(x, y)
+        assert no == ng, (x, y, no, ng)
+        if 0 < no <= 1000:
+            assert list(bo) == list(bg) and np.array_equal(po, pg), (x, y)
