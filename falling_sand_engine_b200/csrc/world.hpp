@@ -1,0 +1,154 @@
+// world.hpp — header-only C++ host shim over include/fse.h that keeps the reference's `class world` method names for
+// the tick path (source/engine/world.hpp:148-192).  This is the piece a maintainer drops next to the reference's
+// world.cpp: every method forwards to one C-ABI call; errors become exceptions because the
+// reference's methods return void.  Links against libfse_b200.so only — no CUDA headers needed by the caller.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fse.h"
+
+namespace fse_host {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+inline void check(int rc) {
+    if (rc != FSE_OK) throw Error(std::string("fse: ") + fse_last_error());
+}
+
+// MaterialInstance value fields (game_datastruct.hpp:207-225) <-> fse_cell
+using Cell = fse_cell;
+
+// Flattened result of InitMaterials()/RegisterMaterial()/PushMaterials() (game_datastruct.cpp:117-300).  The reference's
+// Lua binds materials_init / materials_register / materials_push (game_basic.cpp:79-81) fill this table on the host.
+struct MaterialTable {
+    std::vector<fse_material> mats;
+    fse_special_ids ids{};
+    std::vector<fse_interaction> inter;   // grouped by (material, other material)
+    std::vector<int32_t> inter_offsets;   // n*n+1
+    std::vector<fse_interaction> react;   // grouped by material
+    std::vector<int32_t> react_offsets;   // n+1
+
+    // RegisterMaterial(s_id, name, index_name, physicsType, slipperyness, alpha, density, iterations, emit, emitColor, color)
+    int materials_register(int physicsType, int slipperyness, uint8_t alpha, float density, int iterations, int emit, uint32_t emitColor,
+                           uint32_t color) {
+        const int n0 = (int)mats.size(), n = n0 + 1;
+        fse_material m{};
+        m.physics = physicsType; m.slipperyness = slipperyness; m.alpha = alpha; m.density = density; m.iterations = iterations;
+        m.emit = emit; m.emit_color = emitColor; m.color = color; m.conduction_self = 1.0f; m.conduction_other = 1.0f;
+        mats.push_back(m);
+        std::vector<int32_t> io((size_t)n * n + 1, 0);
+        std::vector<fse_interaction> flat;
+        for (int a = 0; a < n; a++)
+            for (int b = 0; b < n; b++) {
+                if (a < n0 && b < n0 && !inter_offsets.empty())
+                    for (int k = inter_offsets[a * n0 + b]; k < inter_offsets[a * n0 + b + 1]; k++) flat.push_back(inter[k]);
+                io[(size_t)a * n + b + 1] = (int32_t)flat.size();
+            }
+        inter.swap(flat);
+        inter_offsets.swap(io);
+        react_offsets.resize(n + 1, react_offsets.empty() ? 0 : react_offsets.back());
+        return n0;
+    }
+};
+
+class Context {
+public:
+    explicit Context(int device = 0) { check(fse_ctx_create(device, &h_)); }
+    ~Context() { fse_ctx_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    // materials_push(): hand the whole table to the device
+    void materials_push(const MaterialTable& t) {
+        check(fse_materials_set(h_, t.mats.data(), (int)t.mats.size(), &t.ids, t.inter.empty() ? nullptr : t.inter.data(),
+                                t.inter_offsets.empty() ? nullptr : t.inter_offsets.data(), t.react.empty() ? nullptr : t.react.data(),
+                                t.react_offsets.empty() ? nullptr : t.react_offsets.data()));
+    }
+    fse_ctx* handle() const { return h_; }
+
+private:
+    fse_ctx* h_ = nullptr;
+};
+
+// Mirror of the reference's `class world` for the tick path.
+class world {
+public:
+    uint16_t width = 0, height = 0;  // world.hpp:121-122 (the C ABI itself takes int32)
+    fse_rect tickZone{};             // world.hpp zone; game.cpp:1629 keeps it one chunk inside the grid
+    uint32_t tickCt = 0;
+    uint32_t seed = 1337;            // replaces srand(time(NULL)) (game_utils/rng.cpp:9)
+    int cell_iter = 3;               // globaldef.cell_iter (data/scripts/global.lua:47)
+
+    // world::init(path, w, h, ...) (world.cpp:43-172)
+    void init(Context& ctx, int w, int h) {
+        check(fse_world_create(ctx.handle(), w, h, &h_));
+        width = (uint16_t)w;
+        height = (uint16_t)h;
+        tickZone = {FSE_CHUNK, FSE_CHUNK, w - 2 * FSE_CHUNK, h - 2 * FSE_CHUNK};
+    }
+    ~world() { fse_world_destroy(h_); }
+
+    // world.cpp:999-1008
+    Cell getTile(int x, int y) {
+        Cell c{};
+        if (x < 0 || x >= width || y < 0 || y >= height) {  // Tiles_TEST_SOLID
+            c.mat = 1;
+            c.color = 0xff0000;
+            c.fluid = 2.0f;
+            return c;
+        }
+        check(fse_read_rect(h_, x, y, 1, 1, &c));
+        return c;
+    }
+    void setTile(int x, int y, Cell c) {
+        if (x < 0 || x >= width || y < 0 || y >= height) return;
+        c.dirty = 1;
+        check(fse_write_rect(h_, x, y, 1, 1, &c));
+    }
+    // frame() merge (world.cpp:2374-2391) / chunkSaveCache (2780-2792): whole chunks in and out
+    void writeChunk(int cx, int cy, const Cell* cells) { check(fse_write_rect(h_, cx, cy, FSE_CHUNK, FSE_CHUNK, cells)); }
+    void readChunk(int cx, int cy, Cell* cells) { check(fse_read_rect(h_, cx, cy, FSE_CHUNK, FSE_CHUNK, cells)); }
+
+    // world::tick() (world.cpp:1036-1948)
+    void tick() {
+        fse_tick_args a{tickCt, seed, cell_iter, tickZone};
+        check(fse_tick(h_, &a));
+        tickCt++;
+    }
+    void tickTemperature() { check(fse_tick_temperature(h_, &tickZone)); }  // world.cpp:1950
+    void tickCells() { check(fse_particles_tick(h_, &tickZone)); }          // world.cpp:2030
+    void addCell(const fse_particle& p) { check(fse_particles_add(h_, &p, 1)); }  // world.cpp:2292
+
+    // game.cpp:1711-1815 / 1896-1983; `damp` applies the velocity damping the reference does inline
+    template <class Damp>
+    void rasterBodies(const std::vector<fse_xform>& xf, Damp damp) {
+        std::vector<fse_body_feedback> fb(xf.size());
+        check(fse_bodies_raster(h_, xf.data(), (int)xf.size(), tickCt, seed, fb.data()));
+        for (size_t i = 0; i < xf.size(); i++)
+            damp(i, std::pow(0.99f, (float)fb[i].sand_hits) * std::pow(0.998f, (float)fb[i].soup_hits),
+                 std::pow(0.98f, (float)fb[i].sand_hits) * std::pow(0.99f, (float)fb[i].soup_hits));
+    }
+    void eraseBodies(const std::vector<fse_xform>& xf, std::vector<uint8_t>& needsUpdate) {
+        needsUpdate.assign(xf.size(), 0);
+        check(fse_bodies_erase(h_, xf.data(), (int)xf.size(), nullptr, needsUpdate.data()));
+    }
+    // world::physicsCheck(x, y) (world.cpp:3330): returns the component size (cap+1 = too large, 0 = not solid)
+    int physicsCheck(int x, int y, std::vector<int32_t>& pixels, int32_t bbox[4]) {
+        int32_t n = 0;
+        pixels.assign(1001, 0);
+        check(fse_flood_component(h_, x, y, 1000, &n, bbox, pixels.data()));
+        pixels.resize(n <= 1000 ? n : 0);
+        return n;
+    }
+    void sync() { check(fse_sync(h_)); }
+    fse_world* handle() const { return h_; }
+
+private:
+    fse_world* h_ = nullptr;
+};
+
+}  // namespace fse_host
