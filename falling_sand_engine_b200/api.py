@@ -110,6 +110,7 @@ class World:
         self.h = C.c_void_p()
         _ck(self.L.fse_world_create(ctx.h, width, height, C.byref(self.h)))
         self.tickZone = T.zone_of(width, height)
+        self.schedule = 1
 
     def close(self):
         if self.h:
@@ -164,6 +165,12 @@ class World:
     def tick(self, tick, seed=1337, cell_iter=3, zone=None):
         a = T.TickArgs(tick, seed, cell_iter, zone or self.tickZone)
         _ck(self.L.fse_tick(self.h, C.byref(a)))
+
+    def set_schedule(self, schedule):
+        """0 = 4 interleaved column classes (oracle PARTITIONED), 1 = simultaneous rows (oracle ROWS, default)."""
+        self.L.fse_set_schedule.argtypes = [C.c_void_p, C.c_int]
+        _ck(self.L.fse_set_schedule(self.h, schedule))
+        self.schedule = schedule
 
     def tickTemperature(self, zone=None):
         z = zone or self.tickZone

@@ -506,6 +506,12 @@ static int build_strip_lists(fse_world* w, const fse_rect& z, int j0, int j1) {
     return FSE_OK;
 }
 
+FSE_API int fse_set_schedule(fse_world* w, int schedule) {
+    if (!w || (schedule != FSE_SCHEDULE_CLASSES && schedule != FSE_SCHEDULE_ROWS)) return fail(FSE_EINVAL, "fse_set_schedule: bad argument");
+    w->schedule = schedule;
+    return FSE_OK;
+}
+
 FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
     if (!w || !a) return fail(FSE_EINVAL, "fse_tick: null argument");
     if (a->cell_iter < 0 || a->cell_iter > 4) return fail(FSE_EINVAL, "fse_tick: cell_iter %d (0..4; particle ids carry 2 bits)", a->cell_iter);
@@ -551,6 +557,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.acols = w->acols;
             P.arows = w->arows;
             P.never_sleep = 0;
+            P.schedule = w->schedule;
             if (!w->strip) {
                 const int n_chunks = P.ncx * P.ncy;
                 if (n_chunks <= 0) continue;

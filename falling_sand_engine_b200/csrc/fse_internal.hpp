@@ -74,6 +74,7 @@ struct fse_world {
     size_t kt_used = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kt_events;
     uint64_t ticks = 0;
+    int schedule = FSE_SCHEDULE_ROWS;
 };
 
 struct fse_bodies;

@@ -835,15 +835,16 @@ __device__ void pass3_row(const Ctx& c, int k, int cx, int cy, int lane) {
 }
 
 // ---- IO: one row in, one row out ------------------------------------------------------------------------
-__device__ __forceinline__ void issue_row_load(const TickParams& P, Smem& S, int k, int cx, int cy) {
+__device__ __forceinline__ void issue_row_load_any(const TickParams& P, unsigned char* ring, unsigned long long* bars, unsigned char* rowmod,
+                                                   unsigned char* rowchg, int k, int cx, int cy) {
     const int q = slot_of_row(k);
     const size_t y = (size_t)(cy + CHUNK - 1 - k);
-    unsigned char* row = S.ring + q * ROW_BYTES;
-    unsigned long long* bar = &S.bar[q];
+    unsigned char* row = ring + q * ROW_BYTES;
+    unsigned long long* bar = &bars[q];
     const size_t o8 = y * P.W + (cx - HX8);
     const size_t ow = y * P.W + (cx - HXW);
-    S.rowmod[q] = 0;
-    S.rowchg[q] = 0;
+    rowmod[q] = 0;
+    rowchg[q] = 0;
     if (k < -HALO_WR) {  // probe-only rows: pass 2 reads material types down to y+10, nothing else
         mbar_expect_tx(bar, P8);
         bulk_g2s(row + OFF_MAT, P.p.mat + o8, P8, bar);
@@ -859,10 +860,14 @@ __device__ __forceinline__ void issue_row_load(const TickParams& P, Smem& S, int
     bulk_g2s(row + OFF_FD, P.p.fd + ow, PW * 4, bar);
 }
 
-__device__ __forceinline__ void issue_row_store(const TickParams& P, Smem& S, int k, int cx, int cy) {
+__device__ __forceinline__ void issue_row_load(const TickParams& P, Smem& S, int k, int cx, int cy) {
+    issue_row_load_any(P, S.ring, S.bar, S.rowmod, S.rowchg, k, cx, cy);
+}
+
+__device__ __forceinline__ void issue_row_store_any(const TickParams& P, unsigned char* ring, int k, int cx, int cy) {
     const int q = slot_of_row(k);
     const size_t y = (size_t)(cy + CHUNK - 1 - k);
-    unsigned char* row = S.ring + q * ROW_BYTES;
+    unsigned char* row = ring + q * ROW_BYTES;
     const size_t o8 = y * P.W + (cx - HX8);
     const size_t ow = y * P.W + (cx - HXW);
     bulk_s2g(P.p.mat + o8, row + OFF_MAT, P8);
@@ -916,6 +921,8 @@ __device__ bool row_is_inert(const Ctx& c, int q, int qb, int lane) {
     }
     return inert;
 }
+
+__device__ __forceinline__ void issue_row_store(const TickParams& P, Smem& S, int k, int cx, int cy) { issue_row_store_any(P, S.ring, k, cx, cy); }
 
 __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constant__ TickParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1053,18 +1060,29 @@ cudaError_t launch_compact_active(const uint8_t* awake, int acols, int ci0, int 
     return cudaGetLastError();
 }
 
+}  // namespace fse
+
+#include "fse_tick_rows.cuh"
+
+namespace fse {
+
 // ---- host launcher ----------------------------------------------------------------------------------
-size_t tick_smem_bytes() { return sizeof(Smem); }
+size_t tick_smem_bytes() { return sizeof(SmemRows); }
 
 cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tick_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tick_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemRows));
+        if (e != cudaSuccess) return e;
         configured = true;
     }
     if (n_chunks <= 0) return cudaSuccess;
-    tick_chunk_kernel<<<n_chunks, 128, sizeof(Smem), stream>>>(P);
+    if (P.schedule == FSE_SCHEDULE_ROWS)
+        tick_rows_kernel<<<n_chunks, ROWS_THREADS, sizeof(SmemRows), stream>>>(P);
+    else
+        tick_chunk_kernel<<<n_chunks, 128, sizeof(Smem), stream>>>(P);
     return cudaGetLastError();
 }
 

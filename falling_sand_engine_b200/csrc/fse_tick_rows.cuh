@@ -1,0 +1,826 @@
+// fse_tick_rows.cuh — "simultaneous rows" schedule of the chunk tick; included by fse_tick.cu.
+//
+// Same chunk colours, passes, bottom-up rows and pass lags as tick_chunk_kernel, but a row step of a pass is executed by
+// 64 threads (2 columns each) that first DECIDE from the state before the step and then COMMIT:
+//   pass 1:  D | bar | C1 own column + publish horizontal flows/pokes | bar | C2 targets gather (left then right), hand
+//            back what no longer fits | bar | refunds + C3 area effects (FIRE, water-on-lava, pair interactions; serial,
+//            lowest source column first — rare)
+//   pass 2:  D + destination claims (atomicMin of the source column) | bar | C winners move, liquid diff applied | bar | pokes
+//   pass 3:  D + claims | bar | C
+// The CPU oracle restates exactly this (oracle/rows_oracle.cpp, Schedule::ROWS); tests require bit-equality.
+#pragma once
+
+namespace fse {
+
+constexpr int ROWS_THREADS = 224;  // 2 warps per pass + IO warp
+enum Act { A_NONE = 0, A_MARK, A_REACT, A_SAND_PART, A_SAND_SWAP, A_SOUP_ZERO, A_SOUP_PART, A_SOUP_FLOW, A_SOUP_SWAPDOWN, A_GAS_UP, A_FIRE, A_INTERACT };
+
+// decision bits
+constexpr uint32_t DB_COIN = 1u << 4, DB_POKEL = 1u << 5, DB_POKER = 1u << 6, DB_MOVED = 1u << 7, DB_CHANGED = 1u << 8, DB_SWAPUP = 1u << 9,
+                   DB_WL = 1u << 10, DB_BOTSOUP = 1u << 11, DB_TOPSOUP = 1u << 12, DB_LEFTSOUP = 1u << 13, DB_RIGHTSOUP = 1u << 14,
+                   DB_EMBER = 1u << 15, DB_DIE = 1u << 16;
+struct Dec1 {
+    uint32_t bits;   // act in bits 0..3, flags above, stl_new / product / below-material in bits 24..31
+    float fd_new, fD, fL, fR, fU;  // FIRE: fL carries the ignite mask
+};
+
+struct RowScratch {
+    float outL[CHUNK + 2], outR[CHUNK + 2], refL[CHUNK + 2], refR[CHUNK + 2];
+    uint32_t area_arg[CHUNK];
+    int claimDn[2][CHUNK + 2], claimUp[2][CHUNK + 2], claim3[2][CHUNK + 2];
+    uint8_t chg[CHUNK + 2], pkL[CHUNK + 2], pkR[CHUNK + 2], area_kind[CHUNK], poke2[CHUNK];
+    uint8_t areaClaim[11][P8];  // serial C3: claimant column + 1 (0 = free)
+    int p1_any[2], p1_area[2], p2_any[2], p2_poke[2], p3_any[2];
+};
+
+struct __align__(128) SmemRows {
+    unsigned char ring[RING * ROW_BYTES];
+    Lut lut;
+    unsigned long long bar[RING];
+    unsigned char rowmod[32];
+    unsigned char rowchg[32];
+    RowScratch rs;
+};
+
+__device__ __forceinline__ void pass_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__device__ __forceinline__ float clampflow(float flow, float cap, bool speed) {
+    if (speed && flow > FLUID_MinFlow) flow *= FLUID_FlowSpeed;
+    flow = fmaxf(flow, 0.0f);
+    if (flow > fminf(FLUID_MaxFlow, cap)) flow = fminf(FLUID_MaxFlow, cap);
+    return flow;
+}
+
+// ---- pass 1: decide (world.cpp:1089-1586, read-only) ------------------------------------------------------------------
+__device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
+    Dec1 d;
+    d.bits = A_NONE;
+    d.fd_new = d.fD = d.fL = d.fR = d.fU = 0.0f;
+    const uint8_t f0 = FLG(s, j);
+    if (f0 & F_VISITED) return d;
+    const uint8_t m = MAT(s, j);
+    if (c.iter >= (int)c.L->iters[m]) {
+        d.bits = A_MARK;
+        return d;
+    }
+    const int type = c.L->phys[m];
+    if (type == P_AIR || type == P_SOLID) return d;
+    const uint32_t cb = rng_cell(c.rkey, x, y);
+    const int sb = rs(s, 1);
+    if ((int)m == c.fire) {  // 1101-1146
+        uint32_t bits = A_FIRE, ignite = 0;
+        if (rng_draw(cb, S_FIRE_EMBER) % 10 == 0) bits |= DB_EMBER;
+        if (rng_draw(cb, S_FIRE_DIE) % 150 == 0) {
+            bits |= DB_DIE;
+        } else {
+            bool found = false;
+            for (int xx = -2; xx <= 2; xx++)
+                for (int yy = -2; yy <= 2; yy++)
+                    if (PHYS(rs(s, yy), j + xx) == P_SOLID) {
+                        found = true;
+                        const int k = (xx + 2) * 5 + (yy + 2);
+                        if (rng_draw(cb, S_FIRE_IGNITE0 + k) % 500 == 0) ignite |= 1u << k;
+                    }
+            if (!found && rng_draw(cb, S_FIRE_DIE_ALONE) % 120 == 0) bits |= DB_DIE;
+        }
+        d.bits = bits;
+        d.fL = __uint_as_float(ignite);
+        return d;
+    }
+    if (type == P_SAND) {  // 1148-1267
+        const uint8_t mb = MAT(sb, j);
+        const int bt = c.L->phys[mb];
+        const uint8_t mf = c.L->mflags[m];
+        if ((mf & MF_INTERACT) && has_interaction(c, m, mb)) {
+            d.bits = A_INTERACT | ((uint32_t)mb << 24);
+            return d;
+        }
+        if (mf & MF_REACT) {
+            const int16_t temp = TMP(s, j);
+            int prod = -1;
+            if (!(mf & MF_REACT_MULTI)) {
+                const Lut::Rx rx = c.L->rx[m];
+                if ((rx.type == FSE_REACT_TEMPERATURE_BELOW && temp < rx.thr) || (rx.type == FSE_REACT_TEMPERATURE_ABOVE && temp > rx.thr)) prod = rx.prod;
+            } else {
+                for (int i = c.T->react_off[m]; i < c.T->react_off[m + 1]; i++) {
+                    const fse_interaction in = c.T->react[i];
+                    if ((in.type == FSE_REACT_TEMPERATURE_BELOW && temp < in.data1) || (in.type == FSE_REACT_TEMPERATURE_ABOVE && temp > in.data1))
+                        prod = (int)in.data2;
+                }
+            }
+            if (prod >= 0) {
+                d.bits = A_REACT | ((uint32_t)prod << 24);
+                return d;
+            }
+        }
+        const float myDens = c.L->dens[m];
+        if (!(bt == P_AIR || (bt != P_SOLID && c.L->dens[mb] < myDens))) return d;
+        const bool canL = can_sink(c, sb, j - 1, myDens), canR = can_sink(c, sb, j + 1, myDens);
+        if ((canL || canR) && rng_draw(cb, S_SAND_HESITATE) % 20 == 0) return d;
+        uint32_t bits;
+        if (bt == P_AIR && PHYS(rs(s, 2), j) == P_AIR && PHYS(rs(s, 3), j) == P_AIR && PHYS(rs(s, 4), j) == P_AIR) {
+            bits = A_SAND_PART;
+        } else {
+            bits = A_SAND_SWAP;
+            if (rng_draw(cb, S_SAND_MOVED) % 2 == 0) bits |= DB_COIN;
+        }
+        if (rng_draw(cb, S_SAND_TX_SELF) % 2 == 0) {
+            if (rng_draw(cb, S_SAND_TX_L) % 2 == 0) bits |= DB_POKEL;
+            if (rng_draw(cb, S_SAND_TX_R) % 2 == 0) bits |= DB_POKER;
+        }
+        d.bits = bits;
+        return d;
+    }
+    if (type == P_SOUP) {  // 1269-1537
+        const float fl = FL(s, j);
+        if (fl == 0.0f) return d;
+        if (fl < FLUID_MinValue) {
+            d.bits = A_SOUP_ZERO;
+            return d;
+        }
+        const uint8_t mb0 = MAT(sb, j);
+        const int bph = c.L->phys[mb0];
+        if ((double)fl > 0.005 && bph == P_AIR && PHYS(rs(s, 2), j) == P_AIR && PHYS(rs(s, 3), j) == P_AIR && PHYS(rs(s, 4), j) == P_AIR) {
+            d.bits = A_SOUP_PART;
+            return d;
+        }
+        if (f0 & F_MOVED) return d;
+        const float start = fl;
+        float rem = fl;
+        float fd = FD(s, j);
+        const bool airBelow = bph == P_AIR;
+        uint32_t bits = A_SOUP_FLOW;
+        if (bph == P_SOUP) bits |= DB_BOTSOUP;
+        bool early = false;
+        const float bottomFl = FL(sb, j);
+        if ((airBelow && c.iter <= 2) || mb0 == m) {  // 1315-1334
+            const float dst = bph == P_SOUP ? bottomFl : 0.0f;
+            float flow = vertical_flow(start, dst) - dst;
+            flow = clampflow(flow, start, bottomFl > 0);
+            if (flow != 0) {
+                rem -= flow;
+                fd -= flow;
+                d.fD = flow;
+            }
+        } else if (c.iter == 0 && bph == P_SOUP && mb0 != m) {  // 1335-1341
+            if (rng_draw(cb, S_SOUP_SWAP_DOWN) % 10 == 0) {
+                d.bits = A_SOUP_SWAPDOWN;
+                return d;
+            }
+        }
+        if (rem < FLUID_MinValue) {
+            fd -= rem;
+            early = true;
+        }
+        const uint8_t ml = MAT(s, j - 1), mr = MAT(s, j + 1);
+        const int lph = c.L->phys[ml], rph = c.L->phys[mr];
+        if (lph == P_SOUP) bits |= DB_LEFTSOUP;
+        if (rph == P_SOUP) bits |= DB_RIGHTSOUP;
+        const bool canL = (lph == P_AIR || ml == m) && !airBelow;
+        const bool canR = (rph == P_AIR || mr == m) && !airBelow;
+        if (!early && canL) {  // 1355-1375
+            const float dst = lph == P_SOUP ? FL(s, j - 1) : 0.0f;
+            const float flow = clampflow((rem - dst) / (canR ? 3.0f : 2.0f), rem, true);
+            if (flow != 0) {
+                rem -= flow;
+                fd -= flow;
+                d.fL = flow;
+            }
+        }
+        if (!early && rem < FLUID_MinValue) {
+            fd -= rem;
+            early = true;
+        }
+        if (!early && canR) {  // 1383-1403
+            const float dst = rph == P_SOUP ? FL(s, j + 1) : 0.0f;
+            const float flow = clampflow((rem - dst) / 2.0f, rem, true);
+            if (flow != 0) {
+                rem -= flow;
+                fd -= flow;
+                d.fR = flow;
+            }
+        }
+        if (!early && rem < FLUID_MinValue) {
+            fd -= rem;
+            early = true;
+        }
+        const int st = rs(s, -1);
+        const uint8_t mt = MAT(st, j);
+        const int tph = c.L->phys[mt];
+        if (tph == P_SOUP) bits |= DB_TOPSOUP;
+        bool swapUp = false;
+        if (!early) {
+            if (tph == P_AIR || mt == m) {  // 1413-1432
+                const float dst = tph == P_SOUP ? FL(st, j) : 0.0f;
+                const float flow = clampflow(rem - vertical_flow(rem, dst), rem, true);
+                if (flow != 0) {
+                    rem -= flow;
+                    fd -= flow;
+                    d.fU = flow;
+                }
+            } else if (c.iter == 0 && tph == P_SOUP && mt != m) {  // 1433-1439
+                if (rng_draw(cb, S_SOUP_SWAP_UP) % 10 == 0) swapUp = true;
+            }
+        }
+        if (!early && !swapUp && rem < FLUID_MinValue) {
+            fd -= rem;
+            early = true;
+        }
+        d.fd_new = fd;
+        uint8_t stl = STL(s, j);
+        bool moved = (f0 & F_MOVED) != 0;
+        if (swapUp) bits |= DB_SWAPUP;
+        if (!early && !swapUp) {
+            if (start == rem) {  // 1447-1451
+                stl = (uint8_t)(stl + 1);
+                if (stl >= 10) moved = true;
+            } else {
+                bits |= DB_CHANGED;
+            }
+            if ((int)m == c.water && (int)mb0 == c.lava) bits |= DB_WL;  // 1519
+        }
+        if (moved) bits |= DB_MOVED;
+        d.bits = bits | ((uint32_t)stl << 24);
+        return d;
+    }
+    if (type == P_GAS) {  // 1569-1585
+        const int st = rs(s, -1);
+        if (PHYS(st, j) == P_AIR && !((PHYS(st, j - 1) == P_AIR || PHYS(st, j + 1) == P_AIR) && rng_draw(cb, S_GAS1) % 2 == 0)) d.bits = A_GAS_UP;
+    }
+    return d;
+}
+
+// own-column commit; k = column index in the scratch arrays (j - HX8 + 1)
+__device__ void commit1(const Ctx& c, RowScratch& R, const Dec1& d, int s, int j, int x, int y) {
+    const int k = j - HX8 + 1;
+    const int act = d.bits & 15;
+    float oL = 0.0f, oR = 0.0f;
+    uint8_t chg = 0, pkL = 0, pkR = 0, akind = 0;
+    uint32_t aarg = 0;
+    const int sb = rs(s, 1), st = rs(s, -1);
+    switch (act) {
+        case A_MARK:
+            FLG(s, j) = FLG(s, j) | F_VISITED;
+            break;
+        case A_REACT: {
+            const int16_t t = TMP(s, j);
+            CellR n = create(c, (int)(d.bits >> 24), x, y);
+            n.tmp = t;
+            stc(c, s, j, n, F_DIRTY | F_VISITED);
+            break;
+        }
+        case A_SAND_PART:
+        case A_SAND_SWAP: {
+            CellR tile = ldc(c, s, j);
+            const CellR below = ldc(c, sb, j);
+            stc(c, s, j, below, F_DIRTY);
+            if (act == A_SAND_PART) {
+                const uint32_t cb = rng_cell(c.rkey, x, y);
+                const float vx = ((int)(rng_draw(cb, S_SAND_PART_VX) % 10) - 5) / 20.0f;
+                const float vy = -((int)(rng_draw(cb, S_SAND_PART_VY) % 2) + 3) / 10.0f + 1.5f;
+                emit_particle(c, tile, (float)x, (float)(y + 1), vx, vy, 0.1f, false, 0, 60, particle_id(c, x, y, 14));
+            } else {
+                if (d.bits & DB_COIN) tile.moved = 1;
+                stc(c, sb, j, tile, F_DIRTY | F_VISITED);
+            }
+            pkL = (d.bits & DB_POKEL) ? 1 : 0;
+            pkR = (d.bits & DB_POKER) ? 1 : 0;
+            break;
+        }
+        case A_SOUP_ZERO:
+            FL(s, j) = 0.0f;
+            c.rowmod[s] = 1;
+            c.rowchg[s] = 1;
+            break;
+        case A_SOUP_PART: {
+            const CellR tile = ldc(c, s, j);
+            stc(c, s, j, nothing(c), F_DIRTY);
+            int n = (int)(tile.fl / 4);
+            if (n < 1) n = 1;
+            const uint32_t cb = rng_cell(c.rkey, x, y);
+            for (int i = 0; i < n; i++) {
+                CellR nt = fresh_fluid(tile);
+                nt.fl = tile.fl / n;
+                const float vx = ((int)(rng_draw(cb, S_SOUP_PART0 + 2 * (i & 7)) % 10) - 5) / 30.0f;
+                const float vy = -((int)(rng_draw(cb, S_SOUP_PART0 + 2 * (i & 7) + 1) % 2) + 3) / 10.0f + 1.0f;
+                emit_particle(c, nt, (float)x, (float)(y + 1), vx, vy, 0.1f, false, 0, 60, particle_id(c, x, y, i & 7));
+            }
+            break;
+        }
+        case A_SOUP_SWAPDOWN: {
+            const CellR tile = ldc(c, s, j), bottom = ldc(c, sb, j);
+            stc(c, s, j, bottom, 0);
+            stc(c, sb, j, tile, 0);
+            break;
+        }
+        case A_SOUP_FLOW: {
+            CellR tile = ldc(c, s, j);
+            tile.fd = d.fd_new;
+            tile.stl = (uint8_t)(d.bits >> 24);
+            tile.moved = (d.bits & DB_MOVED) ? 1 : 0;
+            if (d.fD != 0) pour(c, sb, j, PHYS(sb, j), tile, d.fD);
+            if (d.fU != 0) pour(c, st, j, PHYS(st, j), tile, d.fU);
+            if (d.bits & DB_SWAPUP) {  // 1433-1439
+                const CellR top = ldc(c, st, j);
+                stc(c, s, j, top, 0);
+                stc(c, st, j, tile, 0);
+            } else {
+                stc(c, s, j, tile, (d.bits & DB_CHANGED) ? F_DIRTY : 0);
+                if (d.bits & DB_CHANGED) {  // 1452-1458, vertical neighbours
+                    if (d.bits & DB_TOPSOUP) set_moved(c, st, j, false);
+                    if (d.bits & DB_BOTSOUP) set_moved(c, sb, j, false);
+                    chg = (uint8_t)(((d.bits & DB_LEFTSOUP) ? 1 : 0) | ((d.bits & DB_RIGHTSOUP) ? 2 : 0));
+                }
+                if (d.bits & DB_WL) akind = 2;
+            }
+            oL = d.fL;
+            oR = d.fR;
+            break;
+        }
+        case A_GAS_UP: {
+            const CellR tile = ldc(c, s, j), up = ldc(c, st, j);
+            stc(c, s, j, up, F_DIRTY);
+            stc(c, st, j, tile, F_DIRTY | F_VISITED);
+            break;
+        }
+        case A_FIRE: {
+            if (d.bits & DB_EMBER) {  // 1109-1119
+                const CellR tile = ldc(c, s, j);
+                const uint32_t cb = rng_cell(c.rkey, x, y);
+                const float vx = ((int)(rng_draw(cb, S_FIRE_EMBER_VX) % 10) - 5) / 20.0f;
+                const float vy = -((int)(rng_draw(cb, S_FIRE_EMBER_VY) % 10) / 10.0f) / 3.0f + -0.5f;
+                emit_particle(c, tile, (float)x, (float)(y - 1), vx, vy, 0.01f, true, 30, 10, particle_id(c, x, y, 15));
+            }
+            aarg = __float_as_uint(d.fL) | ((d.bits & DB_DIE) ? (1u << 25) : 0);
+            if (aarg) akind = 1;
+            break;
+        }
+        case A_INTERACT:
+            akind = 3;
+            aarg = d.bits >> 24;
+            break;
+        default:
+            break;
+    }
+    R.outL[k] = oL;
+    R.outR[k] = oR;
+    R.refL[k] = 0.0f;
+    R.refR[k] = 0.0f;
+    R.chg[k] = chg;
+    R.pkL[k] = pkL;
+    R.pkR[k] = pkR;
+    R.area_kind[k - 1] = akind;
+    R.area_arg[k - 1] = aarg;
+}
+
+// C2: column k (scratch index) of row slot s receives its horizontal inflows, un-settle flags and, for the row below, pokes
+__device__ void gather1(const Ctx& c, RowScratch& R, int s, int k) {
+    const int j = k - 1 + HX8;
+    const float inL = k > 0 ? R.outR[k - 1] : 0.0f, inR = k < CHUNK + 1 ? R.outL[k + 1] : 0.0f;
+    if (inL != 0 || inR != 0) {
+        const uint8_t m = MAT(s, j);
+        const int ph = c.L->phys[m];
+        if (ph == P_AIR) {
+            if (inL != 0) {
+                CellR n = fresh_fluid(ldc(c, s, j - 1));
+                n.fd = inL;
+                if (inR != 0) {
+                    if (MAT(s, j + 1) == n.mat) n.fd = n.fd + inR;
+                    else R.refL[k + 1] = inR;
+                }
+                stc(c, s, j, n, 0);
+            } else {
+                CellR n = fresh_fluid(ldc(c, s, j + 1));
+                n.fd = inR;
+                stc(c, s, j, n, 0);
+            }
+        } else {
+            if (inL != 0) {
+                if (ph == P_SOUP && MAT(s, j - 1) == m) {
+                    FD(s, j) = FD(s, j) + inL;
+                    c.rowmod[s] = 1;
+                    c.rowchg[s] = 1;
+                } else {
+                    R.refR[k - 1] = inL;
+                }
+            }
+            if (inR != 0) {
+                if (ph == P_SOUP && MAT(s, j + 1) == m) {
+                    FD(s, j) = FD(s, j) + inR;
+                    c.rowmod[s] = 1;
+                    c.rowchg[s] = 1;
+                } else {
+                    R.refL[k + 1] = inR;
+                }
+            }
+        }
+    }
+    if (((k > 0 && (R.chg[k - 1] & 2)) || (k < CHUNK + 1 && (R.chg[k + 1] & 1))) && PHYS(s, j) == P_SOUP) set_moved(c, s, j, false);
+    if ((k > 0 && R.pkR[k - 1]) || (k < CHUNK + 1 && R.pkL[k + 1])) {
+        const int sb = rs(s, 1);
+        if (PHYS(sb, j) == P_SAND) set_moved(c, sb, j, true);
+    }
+}
+
+// C3 (serial, one thread): area effects in ascending source column; the first claimant of a cell wins it
+__device__ void area_effects(const Ctx& c, RowScratch& R, int s, int cx, int y) {
+    for (int r = 0; r < 11; r++)
+        for (int q = 0; q < P8; q++) R.areaClaim[r][q] = 0;
+    auto claim = [&](int i, int tj, int dy) {  // dy in -5..5 rows below(+)/above(-)
+        uint8_t& e = R.areaClaim[dy + 5][tj];
+        if (e == 0) e = (uint8_t)(i + 1);
+    };
+    auto mine = [&](int i, int tj, int dy) { return R.areaClaim[dy + 5][tj] == (uint8_t)(i + 1); };
+    for (int pass = 0; pass < 2; pass++)
+        for (int i = 0; i < CHUNK; i++) {
+            const int kind = R.area_kind[i];
+            if (!kind) continue;
+            const int j = HX8 + i, x = cx + i;
+            const uint32_t arg = R.area_arg[i];
+            if (kind == 1) {  // FIRE: burn out / ignite (1121-1144)
+                const bool die = (arg >> 25) & 1;
+                if (pass == 0) {
+                    if (die) claim(i, j, 0);
+                    for (int kk = 0; kk < 25; kk++)
+                        if ((arg >> kk) & 1) claim(i, j + kk / 5 - 2, kk % 5 - 2);
+                } else {
+                    for (int kk = 0; kk < 25; kk++) {
+                        const int xx = kk / 5 - 2, yy = kk % 5 - 2;
+                        if (((arg >> kk) & 1) && mine(i, j + xx, yy)) stc(c, rs(s, yy), j + xx, create(c, c.fire, x + xx, y + yy), F_DIRTY | F_VISITED);
+                    }
+                    if (die && mine(i, j, 0)) stc(c, s, j, nothing(c), F_DIRTY | F_VISITED);
+                }
+            } else if (kind == 2) {  // water on lava (1519-1537)
+                if (pass == 0) {
+                    for (int xx = -1; xx <= 1; xx++)
+                        for (int yy = 0; yy <= 2; yy++) claim(i, j + xx, yy);
+                } else {
+                    if (mine(i, j, 0)) stc(c, s, j, create(c, c.steam, x, y), F_DIRTY);
+                    if (mine(i, j, 1)) stc(c, rs(s, 1), j, create(c, c.obsidian, x, y + 1), F_DIRTY | F_VISITED);
+                    for (int xx = -1; xx <= 1; xx++)
+                        for (int yy = 0; yy <= 2; yy++)
+                            if (mine(i, j + xx, yy) && (int)MAT(rs(s, yy), j + xx) == c.lava)
+                                stc(c, rs(s, yy), j + xx, create(c, c.obsidian, x + xx, y + yy), F_DIRTY | F_VISITED);
+                }
+            } else {  // pair interactions (1153-1179): the list of the material the source had when it decided
+                int mb, msrc;
+                if (pass == 0) {
+                    msrc = MAT(s, j);
+                    mb = (int)(arg & 0xff);
+                    R.area_arg[i] = (uint32_t)mb | ((uint32_t)msrc << 8);
+                    claim(i, j, 0);
+                } else {
+                    if (!mine(i, j, 0)) continue;  // a lower-column effect rewrote the source: its list is void
+                    mb = (int)(arg & 0xff);
+                    msrc = (int)((arg >> 8) & 0xff);
+                }
+                const int lo = c.T->inter_off[msrc * c.nmat + mb], hi = c.T->inter_off[msrc * c.nmat + mb + 1];
+                for (int q = lo; q < hi; q++) {
+                    const fse_interaction in = c.T->inter[q];
+                    const int rad = (int)in.data2;
+                    if (in.type != FSE_INTERACT_TRANSFORM_MATERIAL && in.type != FSE_INTERACT_SPAWN_MATERIAL) continue;
+                    for (int xx = in.ofs_x - rad; xx <= in.ofs_x + rad; xx++)
+                        for (int yy = in.ofs_y - rad; yy <= in.ofs_y + rad; yy++) {
+                            if (pass == 0) {
+                                claim(i, j + xx, yy);
+                            } else if (mine(i, j + xx, yy)) {
+                                const int tm = MAT(rs(s, yy), j + xx);
+                                const bool hit = in.type == FSE_INTERACT_TRANSFORM_MATERIAL ? tm == mb : ((xx == 0 && yy == 0) || tm == c.air);
+                                if (hit) stc(c, rs(s, yy), j + xx, create(c, in.data1, x + xx, y + yy), F_DIRTY | F_VISITED);
+                            }
+                        }
+                }
+            }
+        }
+}
+
+__device__ void pass1_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int t) {
+    const int s = slot_of_row(k);
+    const int y = cy + c.yoff + CHUNK - 1 - k;
+    const int par = k & 1;
+    const int jA = HX8 + t, jB = HX8 + 64 + t;
+    if (t == 0) {
+        R.p1_any[par ^ 1] = 0;
+        R.p1_area[par ^ 1] = 0;
+    }
+    const Dec1 dA = decide1(c, s, jA, cx + t, y);
+    const Dec1 dB = decide1(c, s, jB, cx + 64 + t, y);
+    const int aA = dA.bits & 15, aB = dB.bits & 15;
+    if (aA | aB) R.p1_any[par] = 1;
+    if (aA == A_FIRE || aA == A_INTERACT || (dA.bits & DB_WL) || aB == A_FIRE || aB == A_INTERACT || (dB.bits & DB_WL)) R.p1_area[par] = 1;
+    pass_bar(1);
+    if (!R.p1_any[par]) return;
+    commit1(c, R, dA, s, jA, cx + t, y);
+    commit1(c, R, dB, s, jB, cx + 64 + t, y);
+    pass_bar(1);
+    gather1(c, R, s, 1 + t);
+    gather1(c, R, s, 65 + t);
+    if (t == 0) gather1(c, R, s, 0);
+    if (t == 63) gather1(c, R, s, CHUNK + 1);
+    pass_bar(1);
+    // refunds to the sources, left flow first
+    {
+        const int kA = 1 + t, kB = 65 + t;
+        if (R.refL[kA] != 0) { FD(s, jA) = FD(s, jA) + R.refL[kA]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
+        if (R.refR[kA] != 0) { FD(s, jA) = FD(s, jA) + R.refR[kA]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
+        if (R.refL[kB] != 0) { FD(s, jB) = FD(s, jB) + R.refL[kB]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
+        if (R.refR[kB] != 0) { FD(s, jB) = FD(s, jB) + R.refR[kB]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
+    }
+    if (R.p1_area[par]) {
+        pass_bar(1);
+        if (t == 0) area_effects(c, R, s, cx, y);
+    }
+}
+
+// ---- pass 2 (world.cpp:1594-1820) ----------------------------------------------------------------------------------------
+// decision: bits 0..2 act (0 none, 1 moved=false, 2 slide, 3 liquid apply, 4 gas diagonal), bit 3 dir right, 4 riser, 5 restick, 6 poke
+__device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
+    const uint8_t f0 = FLG(s, j);
+    if (f0 & F_VISITED) return 0;
+    const uint8_t m = MAT(s, j);
+    const int type = c.L->phys[m];
+    if (type == P_SAND) {
+        const int sb = rs(s, 1);
+        const float myDens = c.L->dens[m];
+        const bool canL = can_sink(c, sb, j - 1, myDens), canR = can_sink(c, sb, j + 1, myDens);
+        if (!(canL || canR)) return 1;
+        const uint32_t cb = rng_cell(c.rkey, x, y);
+        bool stopped = !(f0 & F_MOVED);
+        const int slip = c.L->slip[m];
+        if (stopped) {
+            int drop = 0;
+            for (int pil = 0; pil < 10; pil++) {
+                const int sp = rs(s, 1 + pil);
+                if (PHYS(sp, j - 1) == P_AIR || PHYS(sp, j + 1) == P_AIR) drop++;
+            }
+            const int dd = drop + 1 - (int)c.L->maxstab[m];
+            if (dd > 0) {
+                const int chance = 1000 / dd;
+                if (chance < 1000 && rng_draw(cb, S_SAND2_UNSTICK) % chance == 0) stopped = false;
+            }
+        }
+        if (stopped) return 1;
+        const bool should = rng_draw(cb, S_SAND2_SHOULD) % (2 * slip) != 0;
+        uint32_t bits = 0;
+        if (should && rng_draw(cb, S_SAND2_TX_SELF) % 2 == 0 && rng_draw(cb, S_SAND2_TX_OTHER) % 2 == 0) bits |= 64;
+        int dir = 0;
+        if (should && canL && (!canR || rng_draw(cb, S_SAND2_LR) % 2 == 0)) dir = -1;
+        else if (should && canR) dir = 1;
+        if (!dir) return 1 | bits;
+        bits |= 2;
+        if (dir > 0) bits |= 8;
+        if (PHYS(s, j + dir) == P_AIR) bits |= 16;
+        if (rng_draw(cb, S_SAND2_RESTICK) % (20 * slip) == 0) bits |= 32;
+        return bits;
+    }
+    if (type == P_SOUP) return 3;
+    if (type == P_GAS) {
+        const int st = rs(s, -1);
+        const int aL = PHYS(st, j - 1), aR = PHYS(st, j + 1);
+        if (aL == P_AIR && !(aR == P_AIR && rng_draw(rng_cell(c.rkey, x, y), S_GAS2) % 2 == 0)) return 4;
+        if (aR == P_AIR) return 4 | 8;
+    }
+    return 0;
+}
+
+__device__ void commit2(const Ctx& c, RowScratch& R, uint32_t d, int s, int j, int par) {
+    const int act = d & 7, i = j - HX8, dir = (d & 8) ? 1 : -1;
+    uint8_t poke = 0;
+    if (act == 1) {
+        set_moved(c, s, j, false);
+        poke = (d & 64) ? 1 : 0;
+    } else if (act == 2) {
+        poke = (d & 64) ? 1 : 0;
+        if (R.claimDn[par][i + 1 + dir] == i) {
+            const int sb = rs(s, 1), jd = j + dir;
+            CellR tile = ldc(c, s, j);
+            const CellR diag = ldc(c, sb, jd);
+            if (d & 16) {
+                stc(c, s, jd, diag, dir < 0 ? (uint8_t)(F_DIRTY | F_VISITED) : F_DIRTY);
+                stc(c, s, j, nothing(c), F_DIRTY);
+            } else {
+                stc(c, s, j, diag, F_DIRTY | F_VISITED);
+            }
+            if (d & 32) tile.moved = 0;
+            stc(c, sb, jd, tile, F_DIRTY | F_VISITED);
+        }
+    } else if (act == 3) {  // 1728-1745
+        const float fd = FD(s, j);
+        const float a = FL(s, j) + fd;
+        if (a < FLUID_MinValue) {
+            stc(c, s, j, nothing(c), F_DIRTY | F_VISITED);
+        } else {
+            FL(s, j) = a;
+            FD(s, j) = 0.0f;
+            FLG(s, j) = FLG(s, j) | F_DIRTY | F_VISITED;
+            c.rowmod[s] = 1;
+            if (fd != 0.0f) c.rowchg[s] = 1;
+        }
+    } else if (act == 4) {
+        if (R.claimUp[par][i + 1 + dir] == i) {
+            const int st = rs(s, -1), jd = j + dir;
+            const CellR tile = ldc(c, s, j), other = ldc(c, st, jd);
+            stc(c, s, j, other, F_DIRTY);
+            stc(c, st, jd, tile, F_DIRTY | F_VISITED);
+        }
+    }
+    R.poke2[i] = poke;
+}
+
+__device__ void pass2_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int t) {
+    const int s = slot_of_row(k);
+    const int y = cy + c.yoff + CHUNK - 1 - k;
+    const int par = k & 1;
+    const int jA = HX8 + t, jB = HX8 + 64 + t;
+    // reset next row's claim slots and flags (their last readers finished before the previous step barrier)
+    R.claimDn[par ^ 1][1 + t] = 1 << 30; R.claimDn[par ^ 1][65 + t] = 1 << 30;
+    R.claimUp[par ^ 1][1 + t] = 1 << 30; R.claimUp[par ^ 1][65 + t] = 1 << 30;
+    if (t == 0) {
+        R.claimDn[par ^ 1][0] = R.claimUp[par ^ 1][0] = 1 << 30;
+        R.claimDn[par ^ 1][CHUNK + 1] = R.claimUp[par ^ 1][CHUNK + 1] = 1 << 30;
+        R.p2_any[par ^ 1] = 0;
+        R.p2_poke[par ^ 1] = 0;
+    }
+    const uint32_t dA = decide2(c, s, jA, cx + t, y), dB = decide2(c, s, jB, cx + 64 + t, y);
+    if (dA | dB) R.p2_any[par] = 1;
+    if ((dA | dB) & 64) R.p2_poke[par] = 1;
+    if ((dA & 7) == 2) atomicMin(&R.claimDn[par][t + 1 + ((dA & 8) ? 1 : -1)], t);
+    if ((dA & 7) == 4) atomicMin(&R.claimUp[par][t + 1 + ((dA & 8) ? 1 : -1)], t);
+    if ((dB & 7) == 2) atomicMin(&R.claimDn[par][64 + t + 1 + ((dB & 8) ? 1 : -1)], 64 + t);
+    if ((dB & 7) == 4) atomicMin(&R.claimUp[par][64 + t + 1 + ((dB & 8) ? 1 : -1)], 64 + t);
+    pass_bar(2);
+    if (!R.p2_any[par]) return;
+    commit2(c, R, dA, s, jA, par);
+    commit2(c, R, dB, s, jB, par);
+    if (R.p2_poke[par]) {  // 1658-1673: "moved" handed to the sand below, after the slides
+        pass_bar(2);
+        const int sb = rs(s, 1);
+        if (R.poke2[t] && PHYS(sb, jA) == P_SAND) set_moved(c, sb, jA, true);
+        if (R.poke2[64 + t] && PHYS(sb, jB) == P_SAND) set_moved(c, sb, jB, true);
+    }
+}
+
+// ---- pass 3 (world.cpp:1828-1891) ----------------------------------------------------------------------------------------
+__device__ int decide3(const Ctx& c, int s, int j, int x, int y) {  // 0 none, -1 / +1 move, 2 steam condenses
+    if (FLG(s, j) & F_VISITED) return 0;
+    const uint8_t m = MAT(s, j);
+    if (c.L->phys[m] != P_GAS) return 0;
+    const int l = PHYS(s, j - 1), r = PHYS(s, j + 1);
+    const uint32_t cb = rng_cell(c.rkey, x, y);
+    if (l == P_AIR && !(r == P_AIR && rng_draw(cb, S_GAS3) % 2 == 0)) return -1;
+    if (r == P_AIR) return 1;
+    if ((int)m == c.steam && rng_draw(cb, S_STEAM) % 10 == 0) return 2;
+    return 0;
+}
+
+__device__ void commit3(const Ctx& c, RowScratch& R, int d, int s, int j, int x, int y, int par) {
+    const int i = j - HX8;
+    if (d == 2) {
+        stc(c, s, j, create(c, c.water, x, y), F_DIRTY);
+    } else if (d != 0 && R.claim3[par][i + 1 + d] == i) {
+        const CellR tile = ldc(c, s, j), other = ldc(c, s, j + d);
+        stc(c, s, j, other, F_DIRTY);
+        stc(c, s, j + d, tile, F_DIRTY | F_VISITED);
+    }
+}
+
+__device__ void pass3_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int t) {
+    const int s = slot_of_row(k);
+    const int y = cy + c.yoff + CHUNK - 1 - k;
+    const int par = k & 1;
+    const int jA = HX8 + t, jB = HX8 + 64 + t;
+    R.claim3[par ^ 1][1 + t] = 1 << 30;
+    R.claim3[par ^ 1][65 + t] = 1 << 30;
+    if (t == 0) {
+        R.claim3[par ^ 1][0] = 1 << 30;
+        R.claim3[par ^ 1][CHUNK + 1] = 1 << 30;
+        R.p3_any[par ^ 1] = 0;
+    }
+    const int dA = decide3(c, s, jA, cx + t, y), dB = decide3(c, s, jB, cx + 64 + t, y);
+    if (dA | dB) R.p3_any[par] = 1;
+    if (dA == 1 || dA == -1) atomicMin(&R.claim3[par][t + 1 + dA], t);
+    if (dB == 1 || dB == -1) atomicMin(&R.claim3[par][64 + t + 1 + dB], 64 + t);
+    pass_bar(3);
+    if (!R.p3_any[par]) return;
+    commit3(c, R, dA, s, jA, cx + t, y, par);
+    commit3(c, R, dB, s, jB, cx + 64 + t, y, par);
+}
+
+__global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid_constant__ TickParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemRows& S = *reinterpret_cast<SmemRows*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int role = warp >> 1;  // 0,1,2 = pass 1,2,3; 3 = IO (warp 6)
+    const int t = tid & 63;
+
+    int cxi, cyi;
+    if (P.list_count && (int)blockIdx.x >= *P.list_count) return;
+    if (P.chunk_list) {
+        int v = P.chunk_list[blockIdx.x];
+        cxi = v & 0xffff;
+        cyi = v >> 16;
+    } else {
+        cxi = blockIdx.x % P.ncx;
+        cyi = blockIdx.x / P.ncx;
+    }
+    const int cx = P.x0 + cxi * 2 * CHUNK;
+    const int cy = P.y0 + cyi * 2 * CHUNK;
+
+    const DevTables* T = P.tabs;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(&T->lut);
+        uint4* dst = reinterpret_cast<uint4*>(&S.lut);
+        for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+        uint32_t* z = reinterpret_cast<uint32_t*>(&S.rs);
+        for (int i = tid; i < (int)(sizeof(RowScratch) / 4); i += blockDim.x) z[i] = 0;
+    }
+    __syncthreads();
+    if (tid < CHUNK + 2) {
+        for (int b = 0; b < 2; b++) {
+            S.rs.claimDn[b][tid] = 1 << 30;
+            S.rs.claimUp[b][tid] = 1 << 30;
+            S.rs.claim3[b][tid] = 1 << 30;
+        }
+    }
+    if (tid == 0) {
+        for (int q = 0; q < RING; q++) mbar_init(&S.bar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    Ctx c;
+    c.ring = S.ring;
+    c.L = &S.lut;
+    c.rowmod = S.rowmod;
+    c.rowchg = S.rowchg;
+    c.T = T;
+    c.pbuf = P.pbuf;
+    c.pcount = P.pcount;
+    c.pcap = P.pcap;
+    c.rkey = P.rkey;
+    c.tick = P.tick;
+    c.iter = P.iter;
+    c.nmat = T->n;
+    c.yoff = P.y_off;
+    c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
+
+    const bool io = warp == 6;
+    if (io && lane == 0) {
+        for (int k = -HALO_DN; k < HALO_UP + PF; k++) issue_row_load_any(P, S.ring, S.bar, S.rowmod, S.rowchg, k, cx, cy);
+    }
+    for (int k = -HALO_DN; k < HALO_UP; k++) mbar_wait(&S.bar[slot_of_row(k)], 0);
+
+    bool io_modified = false, io_inert = true;
+    for (int st = 0; st < N_STEPS; st++) {
+        const int kw = st + HALO_UP;
+        if (kw <= LAST_ROW) mbar_wait(&S.bar[slot_of_row(kw)], (uint32_t)(((kw + HALO_DN) / RING) & 1));
+        fence_proxy_async();
+        __syncthreads();
+        if (role == 0) {
+            if (st < CHUNK) pass1_rows(c, S.rs, st, cx, cy, t);
+        } else if (role == 1) {
+            const int k = st - L12;
+            if (k >= 0 && k < CHUNK) pass2_rows(c, S.rs, k, cx, cy, t);
+        } else if (role == 2) {
+            const int k = st - L12 - L23;
+            if (k >= 0 && k < CHUNK) pass3_rows(c, S.rs, k, cx, cy, t);
+        } else if (io) {
+            const int ks = st - STORE_LAG;
+            if (ks >= -HALO_WR && ks <= LAST_ROW) {
+                const int q = slot_of_row(ks);
+                if (P.awake && ks >= 0 && ks < CHUNK) io_inert &= row_is_inert(c, q, rs(q, 1), lane);
+                io_modified |= S.rowchg[q] != 0;
+                if (S.rowmod[q]) {
+                    uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
+                    for (int w = lane; w < P8 / 4; w += 32) fw[w] &= 0x7f7f7f7fU;
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) issue_row_store_any(P, S.ring, ks, cx, cy);
+                }
+                if (lane == 0) bulk_commit();
+            }
+            const int kl = st + HALO_UP + PF;
+            if (kl <= LAST_ROW && lane == 0) {
+                bulk_wait_read<1>();
+                issue_row_load_any(P, S.ring, S.bar, S.rowmod, S.rowchg, kl, cx, cy);
+            }
+        }
+    }
+    if (io) {
+        if (P.awake) {
+            const bool inert = __all_sync(0xffffffffu, io_inert);
+            const int ci = cx / CHUNK, cj = (cy + P.y_off) / CHUNK;
+            if (io_modified) {
+                if (lane < 9) {
+                    const int ni = ci + lane % 3 - 1, nj = cj + lane / 3 - 1;
+                    if (ni >= 0 && nj >= 0 && ni < P.acols && nj < P.arows) P.awake[nj * P.acols + ni] = 1;
+                }
+            } else if (inert && lane == 0 && !P.never_sleep) {
+                P.awake[cj * P.acols + ci] = 0;
+            }
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+}
+
+}  // namespace fse

@@ -196,6 +196,11 @@ FSE_API int fse_clear_dirty(fse_world* w);
 FSE_API int fse_stats_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, fse_stats* out);
 
 /* ---- the tick ------------------------------------------------------------------ */
+/* In-row visiting order of the chunk tick: both keep the reference's chunk colours, passes and
+ * bottom-up rows; each has a bit-exact CPU restatement in oracle/. */
+#define FSE_SCHEDULE_CLASSES 0 /* 4 interleaved column classes, rules executed in place           */
+#define FSE_SCHEDULE_ROWS 1    /* whole row decides from the pre-step state, then commits (default) */
+FSE_API int fse_set_schedule(fse_world* w, int schedule);
 /* world::tick() (world.cpp:1036-1948) without the physicsCheck tail (see
  * fse_flood_component).  Asynchronous. */
 FSE_API int fse_tick(fse_world* w, const fse_tick_args* args);

@@ -769,8 +769,10 @@ void World::clear_visited() {
 void World::run_chunk(int cx, int cy, int iter, Schedule sched, std::vector<Particle>& out) {
     if (sched == Schedule::REFERENCE)
         chunk_reference(cx, cy, iter, out);
-    else
+    else if (sched == Schedule::PARTITIONED)
         chunk_partitioned(cx, cy, iter, out);
+    else
+        chunk_rows(cx, cy, iter, out);
 }
 
 // ---- world::tick() (world.cpp:1036-1948, without the physicsCheck tail) -------------

@@ -25,6 +25,9 @@
 //     classes (x mod 4 = 0,1,2,3), with FIRE cells and interacting SAND cells of a class
 //     deferred to sub-phases whose members are >= 8 / >= 12 columns apart.
 //     Every order-independent rule gives bit-identical results under both schedules.
+//   * Schedule::ROWS        — the GPU's "simultaneous rows" schedule (rows_oracle.cpp): identical at
+//     chunk/pass/row level; all 128 cells of a row decide from the state before the row step, then commit: own-column
+//     writes first, horizontal liquid flows gathered by their targets in a fixed order, contested cells go to the lowest x.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -35,7 +38,7 @@
 namespace fseo {
 
 enum class RngMode { SLOT = 0, LIBC = 1 };
-enum class Schedule { REFERENCE = 0, PARTITIONED = 1 };
+enum class Schedule { REFERENCE = 0, PARTITIONED = 1, ROWS = 2 };
 
 // RNG draw sites.  Values are part of the cross-implementation contract
 // (the CUDA kernels use the same numbers).
@@ -208,6 +211,8 @@ private:
     void visit3(int x, int y);
     void chunk_reference(int cx, int cy, int iter, std::vector<Particle>& out);
     void chunk_partitioned(int cx, int cy, int iter, std::vector<Particle>& out);
+    void chunk_rows(int cx, int cy, int iter, std::vector<Particle>& out);  // rows_oracle.cpp
+    friend struct RowsImpl;
     uint64_t particle_id(int x, int y, int iter, int k) const;
 };
 

@@ -57,7 +57,7 @@ OAPI int fseo_stats_rect(void* p, int x, int y, int w, int h, fse_stats* out) {
 // schedule: 0 reference, 1 partitioned; rng: 0 slot, 1 libc; returns wall seconds of tick() alone.
 OAPI double fseo_tick(void* p, const fse_tick_args* a, int schedule, int rng, int threads) {
     auto t0 = std::chrono::steady_clock::now();
-    ((World*)p)->tick(*a, schedule ? Schedule::PARTITIONED : Schedule::REFERENCE, rng ? RngMode::LIBC : RngMode::SLOT, threads);
+    ((World*)p)->tick(*a, (Schedule)schedule, rng ? RngMode::LIBC : RngMode::SLOT, threads);
     auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
 }
@@ -67,7 +67,7 @@ OAPI int fseo_run_chunk(void* p, const fse_tick_args* a, int iter, int cx, int c
     World* w = (World*)p;
     std::vector<Particle> out;
     w->set_iteration(a->seed, a->tick, iter, RngMode::SLOT);
-    w->run_chunk(cx, cy, iter, schedule ? Schedule::PARTITIONED : Schedule::REFERENCE, out);
+    w->run_chunk(cx, cy, iter, (Schedule)schedule, out);
     for (auto& q : out) w->add_particle(q);
     return 0;
 }

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libfse_oracle.so")
 _lib = None
 
-REFERENCE, PARTITIONED = 0, 1
+REFERENCE, PARTITIONED, ROWS = 0, 1, 2
 RNG_SLOT, RNG_LIBC = 0, 1
 
 
@@ -75,6 +75,7 @@ class OracleWorld:
         self.h = C.c_void_p(self.L.fseo_world_create(width, height))
         self.table = table or default_materials()
         self.L.fseo_materials_set(self.h, *self.table.args())
+        self.default_schedule = ROWS  # the product's default in-row schedule (FSE_SCHEDULE_ROWS)
 
     def close(self):
         if self.h:
@@ -113,11 +114,13 @@ class OracleWorld:
         self.L.fseo_stats_rect(self.h, r.x, r.y, r.w, r.h, C.byref(s))
         return s
 
-    def tick(self, tick, seed=1337, cell_iter=3, zone=None, schedule=PARTITIONED, rng=RNG_SLOT, threads=1):
+    def tick(self, tick, seed=1337, cell_iter=3, zone=None, schedule=None, rng=RNG_SLOT, threads=1):
+        schedule = self.default_schedule if schedule is None else schedule
         a = T.TickArgs(tick, seed, cell_iter, zone or T.zone_of(self.width, self.height))
         return self.L.fseo_tick(self.h, C.byref(a), schedule, rng, threads)
 
-    def run_chunk(self, tick, seed, it, cx, cy, schedule=PARTITIONED, zone=None):
+    def run_chunk(self, tick, seed, it, cx, cy, schedule=None, zone=None):
+        schedule = self.default_schedule if schedule is None else schedule
         a = T.TickArgs(tick, seed, 3, zone or T.zone_of(self.width, self.height))
         self.L.fseo_run_chunk(self.h, C.byref(a), it, cx, cy, schedule)
 

@@ -15,10 +15,15 @@ from tests import helpers as Hh
 pytestmark = pytest.mark.gpu
 
 
-def _pair(oracle, gpu_ctx, table, W, H):
+SCHEDULES = {"rows": (1, 2), "classes": (0, 1)}  # name -> (FSE_SCHEDULE_*, oracle Schedule)
+
+
+def _pair(oracle, gpu_ctx, table, W, H, sched="rows"):
     ow = oracle.OracleWorld(W, H, table)
     gpu_ctx.set_materials(table)
     gw = fse.World(gpu_ctx, W, H)
+    gw.set_schedule(SCHEDULES[sched][0])
+    ow.default_schedule = SCHEDULES[sched][1]
     return ow, gw
 
 
@@ -46,26 +51,29 @@ def test_roundtrip_rect(oracle, gpu_ctx, table):
     Hh.assert_cells_equal(cells[33:83, 17:117], sub, "sub-rect")
 
 
-def test_column_drop_exact(oracle, gpu_ctx, table):
+@pytest.mark.parametrize("sched", ["rows", "classes"])
+def test_column_drop_exact(oracle, gpu_ctx, table, sched):
     W = H = 512
-    ow, gw = _pair(oracle, gpu_ctx, table, W, H)
+    ow, gw = _pair(oracle, gpu_ctx, table, W, H, sched)
     Hh.build_column(ow, table, W, H)
     Hh.build_column(gw, table, W, H)
     _run_and_compare(ow, gw, 40, every=4, what="column")
 
 
-def test_mixed_exact(oracle, gpu_ctx, table):
+@pytest.mark.parametrize("sched", ["rows", "classes"])
+def test_mixed_exact(oracle, gpu_ctx, table, sched):
     W = H = 512
-    ow, gw = _pair(oracle, gpu_ctx, table, W, H)
+    ow, gw = _pair(oracle, gpu_ctx, table, W, H, sched)
     Hh.build_mixed(ow, table, W, H, seed=99)
     Hh.build_mixed(gw, table, W, H, seed=99)
     _run_and_compare(ow, gw, 30, seed=7, every=3, what="mixed")
 
 
-def test_mixed_interactions_exact(oracle, gpu_ctx, table):
+@pytest.mark.parametrize("sched", ["rows", "classes"])
+def test_mixed_interactions_exact(oracle, gpu_ctx, table, sched):
     W, H = 640, 512
     tbl, extra = G.bench_table(table)
-    ow, gw = _pair(oracle, gpu_ctx, tbl, W, H)
+    ow, gw = _pair(oracle, gpu_ctx, tbl, W, H, sched)
     Hh.build_mixed(ow, tbl, W, H, seed=3, extra=list(extra.values()), blob=16)
     Hh.build_mixed(gw, tbl, W, H, seed=3, extra=list(extra.values()), blob=16)
     _run_and_compare(ow, gw, 24, seed=11, every=3, what="interactions")
