@@ -506,6 +506,27 @@ static int build_strip_lists(fse_world* w, const fse_rect& z, int j0, int j1) {
     return FSE_OK;
 }
 
+// Profiling aid (not part of the reference surface): accumulate, per warp role of tick_rows_kernel, the cycles spent working
+// between step barriers.  out[0..3] = pass1, pass2, pass3, IO cycles; out[4] = chunks processed.
+FSE_API int fse_debug_role_cycles(fse_world* w, int enable, unsigned long long* out) {
+    if (!w) return fail(FSE_EINVAL, "fse_debug_role_cycles: null world");
+    CK(cudaSetDevice(w->ctx->device));
+    if (enable && !w->d_dbg) {
+        CK(cudaMalloc(&w->d_dbg, 128));
+        CK(cudaMemset(w->d_dbg, 0, 128));
+    }
+    if (out && w->d_dbg) {
+        CK(cudaStreamSynchronize(w->stream));
+        CK(cudaMemcpy(out, w->d_dbg, 96, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(w->d_dbg, 0, 128));
+    }
+    if (!enable && w->d_dbg) {
+        cudaFree(w->d_dbg);
+        w->d_dbg = nullptr;
+    }
+    return FSE_OK;
+}
+
 FSE_API int fse_set_schedule(fse_world* w, int schedule) {
     if (!w || (schedule != FSE_SCHEDULE_CLASSES && schedule != FSE_SCHEDULE_ROWS)) return fail(FSE_EINVAL, "fse_set_schedule: bad argument");
     w->schedule = schedule;
@@ -558,6 +579,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.arows = w->arows;
             P.never_sleep = 0;
             P.schedule = w->schedule;
+            P.dbg = w->d_dbg;
             if (!w->strip) {
                 const int n_chunks = P.ncx * P.ncy;
                 if (n_chunks <= 0) continue;

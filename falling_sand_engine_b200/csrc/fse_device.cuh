@@ -123,6 +123,7 @@ struct TickParams {
     uint8_t* awake;         // optional per-chunk awake flags over the whole world (acols x arows); null = tracking off
     int acols, arows;
     int never_sleep;        // strip worlds keep their cut-adjacent chunk rows awake
+    unsigned long long* dbg; // optional role-cycle counters (profiling aid), null otherwise
     int schedule;           // FSE_SCHEDULE_CLASSES (4 interleaved column classes) or FSE_SCHEDULE_ROWS (simultaneous rows)
 };
 

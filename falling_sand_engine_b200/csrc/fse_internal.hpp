@@ -75,6 +75,7 @@ struct fse_world {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kt_events;
     uint64_t ticks = 0;
     int schedule = FSE_SCHEDULE_ROWS;
+    unsigned long long* d_dbg = nullptr;
 };
 
 struct fse_bodies;

@@ -149,18 +149,25 @@ __device__ __forceinline__ CellR ldc(const Ctx& c, int s, int j) {
     r.fd = FD(s, j);
     return r;
 }
-// real_tiles[i] = cell (+ dirty[i] / tickVisited[i] = true as requested by `setbits`)
-__device__ __forceinline__ void stc(const Ctx& c, int s, int j, const CellR& r, uint8_t setbits) {
-    MAT(s, j) = r.mat;
-    uint8_t f = FLG(s, j);
-    FLG(s, j) = (uint8_t)((f & (F_DIRTY | F_VISITED)) | (r.moved ? F_MOVED : 0) | setbits);
-    STL(s, j) = r.stl;
-    TMP(s, j) = r.tmp;
-    COL(s, j) = r.col;
-    FL(s, j) = r.fl;
-    FD(s, j) = r.fd;
+// real_tiles[i] = cell (+ dirty[i] / tickVisited[i] = true as requested by `setbits`).  Out of line on purpose: the rule
+// code stores cells at ~40 places and the kernel is instruction-cache bound (profiles/r1_tick_ncu.md), so one copy of the
+// store sequence beats 40 inlined ones.  p0 = mat | stl << 8 | tmp << 16, p1 = moved | setbits << 8.
+__device__ __forceinline__ void stc_raw(const Ctx* cp, int s, int j, uint32_t p0, uint32_t p1, uint32_t col, float fl, float fd) {
+    const Ctx& c = *cp;
+    MAT(s, j) = (uint8_t)p0;
+    const uint8_t f = FLG(s, j);
+    FLG(s, j) = (uint8_t)((f & (F_DIRTY | F_VISITED)) | (p1 & 0xff) | ((p1 >> 8) & 0xff));
+    STL(s, j) = (uint8_t)(p0 >> 8);
+    TMP(s, j) = (int16_t)(p0 >> 16);
+    COL(s, j) = col;
+    FL(s, j) = fl;
+    FD(s, j) = fd;
     c.rowmod[s] = 1;
     c.rowchg[s] = 1;
+}
+__device__ __forceinline__ void stc(const Ctx& c, int s, int j, const CellR& r, uint8_t setbits) {
+    stc_raw(&c, s, j, (uint32_t)r.mat | ((uint32_t)r.stl << 8) | ((uint32_t)(uint16_t)r.tmp << 16), (r.moved ? 1u : 0u) | ((uint32_t)setbits << 8),
+            r.col, r.fl, r.fd);
 }
 __device__ __forceinline__ void set_moved(const Ctx& c, int s, int j, bool v) {
     uint8_t f = FLG(s, j);

@@ -9,10 +9,11 @@
 //   pass 3:  D + claims | bar | C
 // The CPU oracle restates exactly this (oracle/rows_oracle.cpp, Schedule::ROWS); tests require bit-equality.
 #pragma once
+#include <cstddef>
 
 namespace fse {
 
-constexpr int ROWS_THREADS = 224;  // 2 warps per pass + IO warp
+constexpr int ROWS_THREADS = 320;  // warps 0-3 pass 1, 4-7 pass 2 (one column per thread), warp 8 pass 3, warp 9 IO
 enum Act { A_NONE = 0, A_MARK, A_REACT, A_SAND_PART, A_SAND_SWAP, A_SOUP_ZERO, A_SOUP_PART, A_SOUP_FLOW, A_SOUP_SWAPDOWN, A_GAS_UP, A_FIRE, A_INTERACT };
 
 // decision bits
@@ -28,27 +29,49 @@ struct RowScratch {
     float outL[CHUNK + 2], outR[CHUNK + 2], refL[CHUNK + 2], refR[CHUNK + 2];
     uint32_t area_arg[CHUNK];
     int claimDn[2][CHUNK + 2], claimUp[2][CHUNK + 2], claim3[2][CHUNK + 2];
-    uint8_t chg[CHUNK + 2], pkL[CHUNK + 2], pkR[CHUNK + 2], area_kind[CHUNK], poke2[CHUNK];
-    uint8_t areaClaim[11][P8];  // serial C3: claimant column + 1 (0 = free)
     int p1_any[2], p1_area[2], p2_any[2], p2_poke[2], p3_any[2];
+    long long dbg_arrival[2][4];
+    long long dbg_phase[6];  // profiling aid: clock at which each role finished its step (double-buffered)
+    uint32_t area_mask[2][4];   // columns of this row with an area effect to apply (bit i = column i)
+    uint8_t areaClaim[11][P8];  // serial C3: claimant column + 1 (0 = free); 4-byte aligned (cleared as words)
+    uint8_t chg[CHUNK + 2], pkL[CHUNK + 2], pkR[CHUNK + 2], area_kind[CHUNK], poke2[CHUNK];
 };
+static_assert(offsetof(RowScratch, areaClaim) % 4 == 0, "areaClaim is cleared with 32-bit stores");
 
 struct __align__(128) SmemRows {
     unsigned char ring[RING * ROW_BYTES];
     Lut lut;
+    Ctx ctx;  // CTA-uniform context, kept in shared memory so the rule code needs no registers for it
     unsigned long long bar[RING];
     unsigned char rowmod[32];
     unsigned char rowchg[32];
     RowScratch rs;
 };
 
-__device__ __forceinline__ void pass_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pass_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 __device__ __forceinline__ float clampflow(float flow, float cap, bool speed) {
     if (speed && flow > FLUID_MinFlow) flow *= FLUID_FlowSpeed;
     flow = fmaxf(flow, 0.0f);
     if (flow > fminf(FLUID_MaxFlow, cap)) flow = fminf(FLUID_MaxFlow, cap);
     return flow;
+}
+
+// FIRE decision (world.cpp:1101-1146) for the fire cell at (s, jf), evaluated by the whole warp: lane i < 25 owns neighbour
+// (xx, yy) = (i / 5 - 2, i % 5 - 2) — the reference's loop order, so the RNG slots are the same.  Returns the decision bits
+// (A_FIRE | DB_EMBER | DB_DIE) and the ignite mask; every lane gets the same values.
+__device__ __forceinline__ uint32_t decide_fire_coop(const Ctx& c, int s, int jf, int xf, int y, int lane, uint32_t& ignite) {
+    const uint32_t cb = rng_cell(c.rkey, xf, y);
+    uint32_t bits = A_FIRE;
+    ignite = 0;
+    if (rng_draw(cb, S_FIRE_EMBER) % 10 == 0) bits |= DB_EMBER;
+    if (rng_draw(cb, S_FIRE_DIE) % 150 == 0) return bits | DB_DIE;
+    bool solid = false;
+    if (lane < 25) solid = PHYS(rs(s, lane % 5 - 2), jf + lane / 5 - 2) == P_SOLID;
+    const unsigned solids = __ballot_sync(0xffffffffu, solid);
+    ignite = __ballot_sync(0xffffffffu, solid && rng_draw(cb, S_FIRE_IGNITE0 + lane) % 500 == 0);
+    if (!solids && rng_draw(cb, S_FIRE_DIE_ALONE) % 120 == 0) bits |= DB_DIE;
+    return bits;
 }
 
 // ---- pass 1: decide (world.cpp:1089-1586, read-only) ------------------------------------------------------------------
@@ -67,24 +90,8 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
     if (type == P_AIR || type == P_SOLID) return d;
     const uint32_t cb = rng_cell(c.rkey, x, y);
     const int sb = rs(s, 1);
-    if ((int)m == c.fire) {  // 1101-1146
-        uint32_t bits = A_FIRE, ignite = 0;
-        if (rng_draw(cb, S_FIRE_EMBER) % 10 == 0) bits |= DB_EMBER;
-        if (rng_draw(cb, S_FIRE_DIE) % 150 == 0) {
-            bits |= DB_DIE;
-        } else {
-            bool found = false;
-            for (int xx = -2; xx <= 2; xx++)
-                for (int yy = -2; yy <= 2; yy++)
-                    if (PHYS(rs(s, yy), j + xx) == P_SOLID) {
-                        found = true;
-                        const int k = (xx + 2) * 5 + (yy + 2);
-                        if (rng_draw(cb, S_FIRE_IGNITE0 + k) % 500 == 0) ignite |= 1u << k;
-                    }
-            if (!found && rng_draw(cb, S_FIRE_DIE_ALONE) % 120 == 0) bits |= DB_DIE;
-        }
-        d.bits = bits;
-        d.fL = __uint_as_float(ignite);
+    if ((int)m == c.fire) {  // 1101-1146: filled in warp-cooperatively by the caller (decide_fire_coop)
+        d.bits = A_FIRE;
         return d;
     }
     if (type == P_SAND) {  // 1148-1267
@@ -374,7 +381,7 @@ __device__ void commit1(const Ctx& c, RowScratch& R, const Dec1& d, int s, int j
 }
 
 // C2: column k (scratch index) of row slot s receives its horizontal inflows, un-settle flags and, for the row below, pokes
-__device__ void gather1(const Ctx& c, RowScratch& R, int s, int k) {
+__device__ __noinline__ void gather1(const Ctx& c, RowScratch& R, int s, int k) {
     const int j = k - 1 + HX8;
     const float inL = k > 0 ? R.outR[k - 1] : 0.0f, inR = k < CHUNK + 1 ? R.outL[k + 1] : 0.0f;
     if (inL != 0 || inR != 0) {
@@ -423,16 +430,16 @@ __device__ void gather1(const Ctx& c, RowScratch& R, int s, int k) {
 }
 
 // C3 (serial, one thread): area effects in ascending source column; the first claimant of a cell wins it
-__device__ void area_effects(const Ctx& c, RowScratch& R, int s, int cx, int y) {
-    for (int r = 0; r < 11; r++)
-        for (int q = 0; q < P8; q++) R.areaClaim[r][q] = 0;
+__device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, int cx, int y, int par) {
     auto claim = [&](int i, int tj, int dy) {  // dy in -5..5 rows below(+)/above(-)
         uint8_t& e = R.areaClaim[dy + 5][tj];
         if (e == 0) e = (uint8_t)(i + 1);
     };
     auto mine = [&](int i, int tj, int dy) { return R.areaClaim[dy + 5][tj] == (uint8_t)(i + 1); };
     for (int pass = 0; pass < 2; pass++)
-        for (int i = 0; i < CHUNK; i++) {
+        for (int wd = 0; wd < 4; wd++)
+            for (uint32_t mk = R.area_mask[par][wd]; mk; mk &= mk - 1) {
+            const int i = wd * 32 + __ffs(mk) - 1;
             const int kind = R.area_kind[i];
             if (!kind) continue;
             const int j = HX8 + i, x = cx + i;
@@ -498,37 +505,62 @@ __device__ void pass1_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, i
     const int s = slot_of_row(k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
-    const int jA = HX8 + t, jB = HX8 + 64 + t;
+    const int lane = t & 31;
+    const int j = HX8 + t;
     if (t == 0) {
         R.p1_any[par ^ 1] = 0;
         R.p1_area[par ^ 1] = 0;
+        R.area_mask[par ^ 1][0] = R.area_mask[par ^ 1][1] = R.area_mask[par ^ 1][2] = R.area_mask[par ^ 1][3] = 0;
     }
-    const Dec1 dA = decide1(c, s, jA, cx + t, y);
-    const Dec1 dB = decide1(c, s, jB, cx + 64 + t, y);
-    const int aA = dA.bits & 15, aB = dB.bits & 15;
-    if (aA | aB) R.p1_any[par] = 1;
-    if (aA == A_FIRE || aA == A_INTERACT || (dA.bits & DB_WL) || aB == A_FIRE || aB == A_INTERACT || (dB.bits & DB_WL)) R.p1_area[par] = 1;
+    const long long T0 = clock64();
+    Dec1 d = decide1(c, s, j, cx + t, y);
+    {  // FIRE cells of this warp's 32 columns, one at a time, all lanes helping
+        unsigned fm = __ballot_sync(0xffffffffu, (d.bits & 15) == A_FIRE);
+#pragma unroll 1
+        while (fm) {
+            const int src = __ffs(fm) - 1;
+            fm &= fm - 1;
+            const int tt = (t & ~31) + src;
+            uint32_t ignite;
+            const uint32_t bits = decide_fire_coop(c, s, HX8 + tt, cx + tt, y, lane, ignite);
+            if (lane == src) {
+                d.bits = bits;
+                d.fL = __uint_as_float(ignite);
+            }
+        }
+    }
+    const int a = d.bits & 15;
+    if (a) R.p1_any[par] = 1;
+    if ((a == A_FIRE && ((d.bits & DB_DIE) || __float_as_uint(d.fL))) || a == A_INTERACT || (d.bits & DB_WL)) {
+        atomicOr(&R.area_mask[par][t >> 5], 1u << (t & 31));
+        R.p1_area[par] = 1;
+    }
+    const long long T0b = clock64();
     pass_bar(1);
-    if (!R.p1_any[par]) return;
-    commit1(c, R, dA, s, jA, cx + t, y);
-    commit1(c, R, dB, s, jB, cx + 64 + t, y);
+    if (!R.p1_any[par]) {
+        if (t == 0) { R.dbg_phase[0] += clock64() - T0; R.dbg_phase[5] += T0b - T0; }
+        return;
+    }
+    const long long T1 = clock64();
+    commit1(c, R, d, s, j, cx + t, y);
     pass_bar(1);
+    const long long T2 = R.refL[1 + t] == 12345.0f ? 0 : clock64();
     gather1(c, R, s, 1 + t);
-    gather1(c, R, s, 65 + t);
     if (t == 0) gather1(c, R, s, 0);
-    if (t == 63) gather1(c, R, s, CHUNK + 1);
+    if (t == CHUNK - 1) gather1(c, R, s, CHUNK + 1);
     pass_bar(1);
-    // refunds to the sources, left flow first
-    {
-        const int kA = 1 + t, kB = 65 + t;
-        if (R.refL[kA] != 0) { FD(s, jA) = FD(s, jA) + R.refL[kA]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
-        if (R.refR[kA] != 0) { FD(s, jA) = FD(s, jA) + R.refR[kA]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
-        if (R.refL[kB] != 0) { FD(s, jB) = FD(s, jB) + R.refL[kB]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
-        if (R.refR[kB] != 0) { FD(s, jB) = FD(s, jB) + R.refR[kB]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
+    const long long T3 = R.refL[1 + t] == 12345.0f ? 0 : clock64();
+    if (t == 0) { R.dbg_phase[0] += T1 - T0; R.dbg_phase[1] += T2 - T1; R.dbg_phase[2] += T3 - T2; R.dbg_phase[4] += 1; R.dbg_phase[5] += T0b - T0; }
+    {  // refunds to the sources, left flow first
+        const int kk = 1 + t;
+        if (R.refL[kk] != 0) { FD(s, j) = FD(s, j) + R.refL[kk]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
+        if (R.refR[kk] != 0) { FD(s, j) = FD(s, j) + R.refR[kk]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
     }
     if (R.p1_area[par]) {
+        uint32_t* cl = reinterpret_cast<uint32_t*>(&R.areaClaim[0][0]);
+        for (int q = t; q < 11 * P8 / 4; q += CHUNK) cl[q] = 0;
         pass_bar(1);
-        if (t == 0) area_effects(c, R, s, cx, y);
+        if (t == 0) area_effects(c, R, s, cx, y, par);
     }
 }
 
@@ -549,6 +581,7 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
         const int slip = c.L->slip[m];
         if (stopped) {
             int drop = 0;
+#pragma unroll 1
             for (int pil = 0; pil < 10; pil++) {
                 const int sp = rs(s, 1 + pil);
                 if (PHYS(sp, j - 1) == P_AIR || PHYS(sp, j + 1) == P_AIR) drop++;
@@ -631,32 +664,28 @@ __device__ void pass2_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, i
     const int s = slot_of_row(k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
-    const int jA = HX8 + t, jB = HX8 + 64 + t;
+    const int j = HX8 + t;
     // reset next row's claim slots and flags (their last readers finished before the previous step barrier)
-    R.claimDn[par ^ 1][1 + t] = 1 << 30; R.claimDn[par ^ 1][65 + t] = 1 << 30;
-    R.claimUp[par ^ 1][1 + t] = 1 << 30; R.claimUp[par ^ 1][65 + t] = 1 << 30;
+    R.claimDn[par ^ 1][1 + t] = 1 << 30;
+    R.claimUp[par ^ 1][1 + t] = 1 << 30;
     if (t == 0) {
         R.claimDn[par ^ 1][0] = R.claimUp[par ^ 1][0] = 1 << 30;
         R.claimDn[par ^ 1][CHUNK + 1] = R.claimUp[par ^ 1][CHUNK + 1] = 1 << 30;
         R.p2_any[par ^ 1] = 0;
         R.p2_poke[par ^ 1] = 0;
     }
-    const uint32_t dA = decide2(c, s, jA, cx + t, y), dB = decide2(c, s, jB, cx + 64 + t, y);
-    if (dA | dB) R.p2_any[par] = 1;
-    if ((dA | dB) & 64) R.p2_poke[par] = 1;
-    if ((dA & 7) == 2) atomicMin(&R.claimDn[par][t + 1 + ((dA & 8) ? 1 : -1)], t);
-    if ((dA & 7) == 4) atomicMin(&R.claimUp[par][t + 1 + ((dA & 8) ? 1 : -1)], t);
-    if ((dB & 7) == 2) atomicMin(&R.claimDn[par][64 + t + 1 + ((dB & 8) ? 1 : -1)], 64 + t);
-    if ((dB & 7) == 4) atomicMin(&R.claimUp[par][64 + t + 1 + ((dB & 8) ? 1 : -1)], 64 + t);
+    const uint32_t d = decide2(c, s, j, cx + t, y);
+    if (d) R.p2_any[par] = 1;
+    if (d & 64) R.p2_poke[par] = 1;
+    if ((d & 7) == 2) atomicMin(&R.claimDn[par][t + 1 + ((d & 8) ? 1 : -1)], t);
+    if ((d & 7) == 4) atomicMin(&R.claimUp[par][t + 1 + ((d & 8) ? 1 : -1)], t);
     pass_bar(2);
     if (!R.p2_any[par]) return;
-    commit2(c, R, dA, s, jA, par);
-    commit2(c, R, dB, s, jB, par);
+    commit2(c, R, d, s, j, par);
     if (R.p2_poke[par]) {  // 1658-1673: "moved" handed to the sand below, after the slides
         pass_bar(2);
         const int sb = rs(s, 1);
-        if (R.poke2[t] && PHYS(sb, jA) == P_SAND) set_moved(c, sb, jA, true);
-        if (R.poke2[64 + t] && PHYS(sb, jB) == P_SAND) set_moved(c, sb, jB, true);
+        if (R.poke2[t] && PHYS(sb, j) == P_SAND) set_moved(c, sb, j, true);
     }
 }
 
@@ -684,34 +713,41 @@ __device__ void commit3(const Ctx& c, RowScratch& R, int d, int s, int j, int x,
     }
 }
 
-__device__ void pass3_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int t) {
+__device__ void pass3_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int lane) {
     const int s = slot_of_row(k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
-    const int jA = HX8 + t, jB = HX8 + 64 + t;
-    R.claim3[par ^ 1][1 + t] = 1 << 30;
-    R.claim3[par ^ 1][65 + t] = 1 << 30;
-    if (t == 0) {
-        R.claim3[par ^ 1][0] = 1 << 30;
-        R.claim3[par ^ 1][CHUNK + 1] = 1 << 30;
-        R.p3_any[par ^ 1] = 0;
+    // quick vote: any unvisited GAS in this row?
+    bool gas = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int j = HX8 + lane + 32 * q;
+        gas |= !(FLG(s, j) & F_VISITED) && PHYS(s, j) == P_GAS;
     }
-    const int dA = decide3(c, s, jA, cx + t, y), dB = decide3(c, s, jB, cx + 64 + t, y);
-    if (dA | dB) R.p3_any[par] = 1;
-    if (dA == 1 || dA == -1) atomicMin(&R.claim3[par][t + 1 + dA], t);
-    if (dB == 1 || dB == -1) atomicMin(&R.claim3[par][64 + t + 1 + dB], 64 + t);
-    pass_bar(3);
-    if (!R.p3_any[par]) return;
-    commit3(c, R, dA, s, jA, cx + t, y, par);
-    commit3(c, R, dB, s, jB, cx + 64 + t, y, par);
+    if (!__any_sync(0xffffffffu, gas)) return;
+    for (int q = lane; q < CHUNK + 2; q += 32) R.claim3[par][q] = 1 << 30;
+    __syncwarp();
+    int d[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int i = lane + 32 * q;
+        d[q] = decide3(c, s, HX8 + i, cx + i, y);
+        if (d[q] == 1 || d[q] == -1) atomicMin(&R.claim3[par][i + 1 + d[q]], i);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int i = lane + 32 * q;
+        commit3(c, R, d[q], s, HX8 + i, cx + i, y, par);
+    }
 }
 
 __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid_constant__ TickParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemRows& S = *reinterpret_cast<SmemRows*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int role = warp >> 1;  // 0,1,2 = pass 1,2,3; 3 = IO (warp 6)
-    const int t = tid & 63;
+    const int role = warp < 4 ? 0 : (warp < 8 ? 1 : (warp == 8 ? 2 : 3));  // pass 1, pass 2, pass 3, IO
+    const int t = tid & 127;
 
     int cxi, cyi;
     if (P.list_count && (int)blockIdx.x >= *P.list_count) return;
@@ -748,34 +784,43 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
     }
     __syncthreads();
 
-    Ctx c;
-    c.ring = S.ring;
-    c.L = &S.lut;
-    c.rowmod = S.rowmod;
-    c.rowchg = S.rowchg;
-    c.T = T;
-    c.pbuf = P.pbuf;
-    c.pcount = P.pcount;
-    c.pcap = P.pcap;
-    c.rkey = P.rkey;
-    c.tick = P.tick;
-    c.iter = P.iter;
-    c.nmat = T->n;
-    c.yoff = P.y_off;
-    c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
+    Ctx& c = S.ctx;
+    if (tid == 0) {
+        c.ring = S.ring;
+        c.L = &S.lut;
+        c.rowmod = S.rowmod;
+        c.rowchg = S.rowchg;
+        c.T = T;
+        c.pbuf = P.pbuf;
+        c.pcount = P.pcount;
+        c.pcap = P.pcap;
+        c.rkey = P.rkey;
+        c.tick = P.tick;
+        c.iter = P.iter;
+        c.nmat = T->n;
+        c.yoff = P.y_off;
+        c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
+    }
+    __syncthreads();
 
-    const bool io = warp == 6;
+    const bool io = warp == 9;
     if (io && lane == 0) {
         for (int k = -HALO_DN; k < HALO_UP + PF; k++) issue_row_load_any(P, S.ring, S.bar, S.rowmod, S.rowchg, k, cx, cy);
     }
     for (int k = -HALO_DN; k < HALO_UP; k++) mbar_wait(&S.bar[slot_of_row(k)], 0);
 
     bool io_modified = false, io_inert = true;
+    long long dbg_acc = 0;
     for (int st = 0; st < N_STEPS; st++) {
         const int kw = st + HALO_UP;
         if (kw <= LAST_ROW) mbar_wait(&S.bar[slot_of_row(kw)], (uint32_t)(((kw + HALO_DN) / RING) & 1));
         fence_proxy_async();
         __syncthreads();
+        long long clk0 = 0;
+        if (P.dbg) {  // the step barrier released when the slowest role of the previous step arrived
+            const long long* a = S.rs.dbg_arrival[(st & 1) ^ 1];
+            clk0 = max(max(a[0], a[1]), max(a[2], a[3]));
+        }
         if (role == 0) {
             if (st < CHUNK) pass1_rows(c, S.rs, st, cx, cy, t);
         } else if (role == 1) {
@@ -783,7 +828,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
             if (k >= 0 && k < CHUNK) pass2_rows(c, S.rs, k, cx, cy, t);
         } else if (role == 2) {
             const int k = st - L12 - L23;
-            if (k >= 0 && k < CHUNK) pass3_rows(c, S.rs, k, cx, cy, t);
+            if (k >= 0 && k < CHUNK) pass3_rows(c, S.rs, k, cx, cy, lane);
         } else if (io) {
             const int ks = st - STORE_LAG;
             if (ks >= -HALO_WR && ks <= LAST_ROW) {
@@ -805,6 +850,17 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
                 issue_row_load_any(P, S.ring, S.bar, S.rowmod, S.rowchg, kl, cx, cy);
             }
         }
+        if (P.dbg) {
+            const long long now = clock64();
+            if (st > 0) dbg_acc += now - clk0;
+            if ((tid & 127) == 0 || tid == 256 || tid == 288) S.rs.dbg_arrival[st & 1][role] = now;
+        }
+    }
+    if (P.dbg && (tid == 0 || tid == 128 || tid == 256 || tid == 288)) atomicAdd(&P.dbg[role], (unsigned long long)dbg_acc);
+    if (P.dbg && tid == 0) {
+        atomicAdd(&P.dbg[4], 1ULL);
+        for (int q = 0; q < 6; q++)
+            if (q != 3) atomicAdd(&P.dbg[5 + q], (unsigned long long)S.rs.dbg_phase[q]);
     }
     if (io) {
         if (P.awake) {

@@ -288,6 +288,8 @@ FSE_API int64_t fse_launch_count(fse_ctx* ctx);
  * last reset, from CUDA events recorded around every launch when enabled. */
 FSE_API int fse_kernel_timing_enable(fse_world* w, int enable);
 FSE_API int fse_kernel_timing_read(fse_world* w, double* total_ms, int64_t* launches);
+/* profiling aid: cycles each warp role of the tick kernel spent working between step barriers (out[0..3]) and chunks (out[4]) */
+FSE_API int fse_debug_role_cycles(fse_world* w, int enable, unsigned long long* out);
 
 #ifdef __cplusplus
 }
