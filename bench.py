@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
-    ap.add_argument("--schedule", default="default", choices=["default", "rows", "classes"], help="in-row schedule of the tick kernel")
+    ap.add_argument("--schedule", default="default", choices=["default", "rows", "rows_fused", "classes"], help="in-row schedule of the tick kernel")
     ap.add_argument("--active", type=int, default=-1, help="active-chunk tracking: 1 on, 0 off, -1 = on for --workload sparse")
     return ap.parse_args()
 
@@ -226,7 +226,7 @@ def run_ours(args):
     zone_cells_total = (W - 2 * T.FSE_CHUNK) * (H - 2 * T.FSE_CHUNK)
     world.particles_reserve(1 << 25)
     if args.schedule != "default":
-        world.set_schedule(1 if args.schedule == "rows" else 0)
+        world.set_schedule({"classes": 0, "rows": 1, "rows_fused": 2}[args.schedule])
     use_active = (args.active == 1 or (args.active < 0 and args.workload == "sparse")) and world_size == 1
     if use_active:
         world.active_enable(True)

@@ -528,8 +528,9 @@ FSE_API int fse_debug_role_cycles(fse_world* w, int enable, unsigned long long* 
 }
 
 FSE_API int fse_set_schedule(fse_world* w, int schedule) {
-    if (!w || (schedule != FSE_SCHEDULE_CLASSES && schedule != FSE_SCHEDULE_ROWS)) return fail(FSE_EINVAL, "fse_set_schedule: bad argument");
-    w->schedule = schedule;
+    if (!w || schedule < FSE_SCHEDULE_CLASSES || schedule > FSE_SCHEDULE_ROWS_FUSED) return fail(FSE_EINVAL, "fse_set_schedule: bad argument");
+    w->schedule = schedule == FSE_SCHEDULE_ROWS_FUSED ? FSE_SCHEDULE_ROWS : schedule;
+    w->fused = schedule == FSE_SCHEDULE_ROWS_FUSED;
     return FSE_OK;
 }
 
@@ -580,6 +581,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.never_sleep = 0;
             P.schedule = w->schedule;
             P.dbg = w->d_dbg;
+            P.fused = w->fused;
             if (!w->strip) {
                 const int n_chunks = P.ncx * P.ncy;
                 if (n_chunks <= 0) continue;

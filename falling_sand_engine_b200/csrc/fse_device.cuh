@@ -124,6 +124,7 @@ struct TickParams {
     int acols, arows;
     int never_sleep;        // strip worlds keep their cut-adjacent chunk rows awake
     unsigned long long* dbg; // optional role-cycle counters (profiling aid), null otherwise
+    int fused;              // rows schedule: 1 = single fused kernel (all passes pipelined), 0 = one kernel per pass
     int schedule;           // FSE_SCHEDULE_CLASSES (4 interleaved column classes) or FSE_SCHEDULE_ROWS (simultaneous rows)
 };
 

@@ -76,6 +76,7 @@ struct fse_world {
     uint64_t ticks = 0;
     int schedule = FSE_SCHEDULE_ROWS;
     unsigned long long* d_dbg = nullptr;
+    int fused = 0;  // rows schedule: fused single kernel instead of one kernel per pass (FSE_ROWS_FUSED=1 or profiling)
 };
 
 struct fse_bodies;

@@ -80,6 +80,8 @@ struct Ctx {
     int iter;
     int nmat;
     int yoff;  // global y of local row 0 (strip worlds), 0 otherwise
+    int ringn, ringmask, koff;  // ring geometry of the running kernel (rows kernels): slot(k) = (k + koff) mod ringn
+    unsigned char* rowvis;      // row got tickVisited marks only (per-pass kernels persist them through HBM)
     int air, fire, water, lava, steam, obsidian;
 };
 
@@ -1083,10 +1085,18 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(tick_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemRows));
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tick_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPass));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPass));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPass));
+        if (e != cudaSuccess) return e;
         configured = true;
     }
     if (n_chunks <= 0) return cudaSuccess;
-    if (P.schedule == FSE_SCHEDULE_ROWS)
+    if (P.schedule == FSE_SCHEDULE_ROWS && !P.awake && !P.fused) {  // one kernel per pass
+        tick_pass_kernel<1><<<n_chunks, PassGeom<1>::THREADS, sizeof(SmemPass), stream>>>(P);
+        tick_pass_kernel<2><<<n_chunks, PassGeom<2>::THREADS, sizeof(SmemPass), stream>>>(P);
+        tick_pass_kernel<3><<<n_chunks, PassGeom<3>::THREADS, sizeof(SmemPass), stream>>>(P);
+    } else if (P.schedule == FSE_SCHEDULE_ROWS)
         tick_rows_kernel<<<n_chunks, ROWS_THREADS, sizeof(SmemRows), stream>>>(P);
     else
         tick_chunk_kernel<<<n_chunks, 128, sizeof(Smem), stream>>>(P);

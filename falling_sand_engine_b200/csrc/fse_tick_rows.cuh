@@ -45,8 +45,18 @@ struct __align__(128) SmemRows {
     unsigned long long bar[RING];
     unsigned char rowmod[32];
     unsigned char rowchg[32];
+    unsigned char rowvis[32];
     RowScratch rs;
 };
+
+// ring geometry from the context (the fused kernel uses 28 rows, the per-pass kernels 16)
+__device__ __forceinline__ int rsn(const Ctx& c, int s, int dy) {
+    int v = s - dy;
+    if (v < 0) v += c.ringn;
+    if (v >= c.ringn) v -= c.ringn;
+    return v;
+}
+__device__ __forceinline__ int slotk(const Ctx& c, int k) { return c.ringmask ? ((k + c.koff) & c.ringmask) : ((k + c.koff) % c.ringn); }
 
 __device__ __forceinline__ void pass_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
@@ -67,7 +77,7 @@ __device__ __forceinline__ uint32_t decide_fire_coop(const Ctx& c, int s, int jf
     if (rng_draw(cb, S_FIRE_EMBER) % 10 == 0) bits |= DB_EMBER;
     if (rng_draw(cb, S_FIRE_DIE) % 150 == 0) return bits | DB_DIE;
     bool solid = false;
-    if (lane < 25) solid = PHYS(rs(s, lane % 5 - 2), jf + lane / 5 - 2) == P_SOLID;
+    if (lane < 25) solid = PHYS(rsn(c, s, lane % 5 - 2), jf + lane / 5 - 2) == P_SOLID;
     const unsigned solids = __ballot_sync(0xffffffffu, solid);
     ignite = __ballot_sync(0xffffffffu, solid && rng_draw(cb, S_FIRE_IGNITE0 + lane) % 500 == 0);
     if (!solids && rng_draw(cb, S_FIRE_DIE_ALONE) % 120 == 0) bits |= DB_DIE;
@@ -89,7 +99,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
     const int type = c.L->phys[m];
     if (type == P_AIR || type == P_SOLID) return d;
     const uint32_t cb = rng_cell(c.rkey, x, y);
-    const int sb = rs(s, 1);
+    const int sb = rsn(c, s, 1);
     if ((int)m == c.fire) {  // 1101-1146: filled in warp-cooperatively by the caller (decide_fire_coop)
         d.bits = A_FIRE;
         return d;
@@ -125,7 +135,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
         const bool canL = can_sink(c, sb, j - 1, myDens), canR = can_sink(c, sb, j + 1, myDens);
         if ((canL || canR) && rng_draw(cb, S_SAND_HESITATE) % 20 == 0) return d;
         uint32_t bits;
-        if (bt == P_AIR && PHYS(rs(s, 2), j) == P_AIR && PHYS(rs(s, 3), j) == P_AIR && PHYS(rs(s, 4), j) == P_AIR) {
+        if (bt == P_AIR && PHYS(rsn(c, s, 2), j) == P_AIR && PHYS(rsn(c, s, 3), j) == P_AIR && PHYS(rsn(c, s, 4), j) == P_AIR) {
             bits = A_SAND_PART;
         } else {
             bits = A_SAND_SWAP;
@@ -147,7 +157,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
         }
         const uint8_t mb0 = MAT(sb, j);
         const int bph = c.L->phys[mb0];
-        if ((double)fl > 0.005 && bph == P_AIR && PHYS(rs(s, 2), j) == P_AIR && PHYS(rs(s, 3), j) == P_AIR && PHYS(rs(s, 4), j) == P_AIR) {
+        if ((double)fl > 0.005 && bph == P_AIR && PHYS(rsn(c, s, 2), j) == P_AIR && PHYS(rsn(c, s, 3), j) == P_AIR && PHYS(rsn(c, s, 4), j) == P_AIR) {
             d.bits = A_SOUP_PART;
             return d;
         }
@@ -211,7 +221,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
             fd -= rem;
             early = true;
         }
-        const int st = rs(s, -1);
+        const int st = rsn(c, s, -1);
         const uint8_t mt = MAT(st, j);
         const int tph = c.L->phys[mt];
         if (tph == P_SOUP) bits |= DB_TOPSOUP;
@@ -251,7 +261,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
         return d;
     }
     if (type == P_GAS) {  // 1569-1585
-        const int st = rs(s, -1);
+        const int st = rsn(c, s, -1);
         if (PHYS(st, j) == P_AIR && !((PHYS(st, j - 1) == P_AIR || PHYS(st, j + 1) == P_AIR) && rng_draw(cb, S_GAS1) % 2 == 0)) d.bits = A_GAS_UP;
     }
     return d;
@@ -264,10 +274,11 @@ __device__ void commit1(const Ctx& c, RowScratch& R, const Dec1& d, int s, int j
     float oL = 0.0f, oR = 0.0f;
     uint8_t chg = 0, pkL = 0, pkR = 0, akind = 0;
     uint32_t aarg = 0;
-    const int sb = rs(s, 1), st = rs(s, -1);
+    const int sb = rsn(c, s, 1), st = rsn(c, s, -1);
     switch (act) {
         case A_MARK:
             FLG(s, j) = FLG(s, j) | F_VISITED;
+            c.rowvis[s] = 1;
             break;
         case A_REACT: {
             const int16_t t = TMP(s, j);
@@ -424,7 +435,7 @@ __device__ __noinline__ void gather1(const Ctx& c, RowScratch& R, int s, int k) 
     }
     if (((k > 0 && (R.chg[k - 1] & 2)) || (k < CHUNK + 1 && (R.chg[k + 1] & 1))) && PHYS(s, j) == P_SOUP) set_moved(c, s, j, false);
     if ((k > 0 && R.pkR[k - 1]) || (k < CHUNK + 1 && R.pkL[k + 1])) {
-        const int sb = rs(s, 1);
+        const int sb = rsn(c, s, 1);
         if (PHYS(sb, j) == P_SAND) set_moved(c, sb, j, true);
     }
 }
@@ -453,7 +464,7 @@ __device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, in
                 } else {
                     for (int kk = 0; kk < 25; kk++) {
                         const int xx = kk / 5 - 2, yy = kk % 5 - 2;
-                        if (((arg >> kk) & 1) && mine(i, j + xx, yy)) stc(c, rs(s, yy), j + xx, create(c, c.fire, x + xx, y + yy), F_DIRTY | F_VISITED);
+                        if (((arg >> kk) & 1) && mine(i, j + xx, yy)) stc(c, rsn(c, s, yy), j + xx, create(c, c.fire, x + xx, y + yy), F_DIRTY | F_VISITED);
                     }
                     if (die && mine(i, j, 0)) stc(c, s, j, nothing(c), F_DIRTY | F_VISITED);
                 }
@@ -463,11 +474,11 @@ __device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, in
                         for (int yy = 0; yy <= 2; yy++) claim(i, j + xx, yy);
                 } else {
                     if (mine(i, j, 0)) stc(c, s, j, create(c, c.steam, x, y), F_DIRTY);
-                    if (mine(i, j, 1)) stc(c, rs(s, 1), j, create(c, c.obsidian, x, y + 1), F_DIRTY | F_VISITED);
+                    if (mine(i, j, 1)) stc(c, rsn(c, s, 1), j, create(c, c.obsidian, x, y + 1), F_DIRTY | F_VISITED);
                     for (int xx = -1; xx <= 1; xx++)
                         for (int yy = 0; yy <= 2; yy++)
-                            if (mine(i, j + xx, yy) && (int)MAT(rs(s, yy), j + xx) == c.lava)
-                                stc(c, rs(s, yy), j + xx, create(c, c.obsidian, x + xx, y + yy), F_DIRTY | F_VISITED);
+                            if (mine(i, j + xx, yy) && (int)MAT(rsn(c, s, yy), j + xx) == c.lava)
+                                stc(c, rsn(c, s, yy), j + xx, create(c, c.obsidian, x + xx, y + yy), F_DIRTY | F_VISITED);
                 }
             } else {  // pair interactions (1153-1179): the list of the material the source had when it decided
                 int mb, msrc;
@@ -491,9 +502,9 @@ __device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, in
                             if (pass == 0) {
                                 claim(i, j + xx, yy);
                             } else if (mine(i, j + xx, yy)) {
-                                const int tm = MAT(rs(s, yy), j + xx);
+                                const int tm = MAT(rsn(c, s, yy), j + xx);
                                 const bool hit = in.type == FSE_INTERACT_TRANSFORM_MATERIAL ? tm == mb : ((xx == 0 && yy == 0) || tm == c.air);
-                                if (hit) stc(c, rs(s, yy), j + xx, create(c, in.data1, x + xx, y + yy), F_DIRTY | F_VISITED);
+                                if (hit) stc(c, rsn(c, s, yy), j + xx, create(c, in.data1, x + xx, y + yy), F_DIRTY | F_VISITED);
                             }
                         }
                 }
@@ -502,7 +513,7 @@ __device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, in
 }
 
 __device__ void pass1_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int t) {
-    const int s = slot_of_row(k);
+    const int s = slotk(c, k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
     const int lane = t & 31;
@@ -572,7 +583,7 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
     const uint8_t m = MAT(s, j);
     const int type = c.L->phys[m];
     if (type == P_SAND) {
-        const int sb = rs(s, 1);
+        const int sb = rsn(c, s, 1);
         const float myDens = c.L->dens[m];
         const bool canL = can_sink(c, sb, j - 1, myDens), canR = can_sink(c, sb, j + 1, myDens);
         if (!(canL || canR)) return 1;
@@ -583,7 +594,7 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
             int drop = 0;
 #pragma unroll 1
             for (int pil = 0; pil < 10; pil++) {
-                const int sp = rs(s, 1 + pil);
+                const int sp = rsn(c, s, 1 + pil);
                 if (PHYS(sp, j - 1) == P_AIR || PHYS(sp, j + 1) == P_AIR) drop++;
             }
             const int dd = drop + 1 - (int)c.L->maxstab[m];
@@ -608,7 +619,7 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
     }
     if (type == P_SOUP) return 3;
     if (type == P_GAS) {
-        const int st = rs(s, -1);
+        const int st = rsn(c, s, -1);
         const int aL = PHYS(st, j - 1), aR = PHYS(st, j + 1);
         if (aL == P_AIR && !(aR == P_AIR && rng_draw(rng_cell(c.rkey, x, y), S_GAS2) % 2 == 0)) return 4;
         if (aR == P_AIR) return 4 | 8;
@@ -625,7 +636,7 @@ __device__ void commit2(const Ctx& c, RowScratch& R, uint32_t d, int s, int j, i
     } else if (act == 2) {
         poke = (d & 64) ? 1 : 0;
         if (R.claimDn[par][i + 1 + dir] == i) {
-            const int sb = rs(s, 1), jd = j + dir;
+            const int sb = rsn(c, s, 1), jd = j + dir;
             CellR tile = ldc(c, s, j);
             const CellR diag = ldc(c, sb, jd);
             if (d & 16) {
@@ -651,7 +662,7 @@ __device__ void commit2(const Ctx& c, RowScratch& R, uint32_t d, int s, int j, i
         }
     } else if (act == 4) {
         if (R.claimUp[par][i + 1 + dir] == i) {
-            const int st = rs(s, -1), jd = j + dir;
+            const int st = rsn(c, s, -1), jd = j + dir;
             const CellR tile = ldc(c, s, j), other = ldc(c, st, jd);
             stc(c, s, j, other, F_DIRTY);
             stc(c, st, jd, tile, F_DIRTY | F_VISITED);
@@ -661,7 +672,7 @@ __device__ void commit2(const Ctx& c, RowScratch& R, uint32_t d, int s, int j, i
 }
 
 __device__ void pass2_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int t) {
-    const int s = slot_of_row(k);
+    const int s = slotk(c, k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
     const int j = HX8 + t;
@@ -684,7 +695,7 @@ __device__ void pass2_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, i
     commit2(c, R, d, s, j, par);
     if (R.p2_poke[par]) {  // 1658-1673: "moved" handed to the sand below, after the slides
         pass_bar(2);
-        const int sb = rs(s, 1);
+        const int sb = rsn(c, s, 1);
         if (R.poke2[t] && PHYS(sb, j) == P_SAND) set_moved(c, sb, j, true);
     }
 }
@@ -714,7 +725,7 @@ __device__ void commit3(const Ctx& c, RowScratch& R, int d, int s, int j, int x,
 }
 
 __device__ void pass3_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int lane) {
-    const int s = slot_of_row(k);
+    const int s = slotk(c, k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
     // quick vote: any unvisited GAS in this row?
@@ -799,6 +810,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
         c.iter = P.iter;
         c.nmat = T->n;
         c.yoff = P.y_off;
+        c.ringn = RING;
+        c.ringmask = 0;
+        c.koff = HALO_DN;
+        c.rowvis = S.rowvis;
         c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
     }
     __syncthreads();
@@ -807,13 +822,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
     if (io && lane == 0) {
         for (int k = -HALO_DN; k < HALO_UP + PF; k++) issue_row_load_any(P, S.ring, S.bar, S.rowmod, S.rowchg, k, cx, cy);
     }
-    for (int k = -HALO_DN; k < HALO_UP; k++) mbar_wait(&S.bar[slot_of_row(k)], 0);
+    for (int k = -HALO_DN; k < HALO_UP; k++) mbar_wait(&S.bar[slotk(c, k)], 0);
 
     bool io_modified = false, io_inert = true;
     long long dbg_acc = 0;
     for (int st = 0; st < N_STEPS; st++) {
         const int kw = st + HALO_UP;
-        if (kw <= LAST_ROW) mbar_wait(&S.bar[slot_of_row(kw)], (uint32_t)(((kw + HALO_DN) / RING) & 1));
+        if (kw <= LAST_ROW) mbar_wait(&S.bar[slotk(c, kw)], (uint32_t)(((kw + HALO_DN) / RING) & 1));
         fence_proxy_async();
         __syncthreads();
         long long clk0 = 0;
@@ -832,8 +847,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
         } else if (io) {
             const int ks = st - STORE_LAG;
             if (ks >= -HALO_WR && ks <= LAST_ROW) {
-                const int q = slot_of_row(ks);
-                if (P.awake && ks >= 0 && ks < CHUNK) io_inert &= row_is_inert(c, q, rs(q, 1), lane);
+                const int q = slotk(c, ks);
+                if (P.awake && ks >= 0 && ks < CHUNK) io_inert &= row_is_inert(c, q, rsn(c, q, 1), lane);
                 io_modified |= S.rowchg[q] != 0;
                 if (S.rowmod[q]) {
                     uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
@@ -877,6 +892,190 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
         }
         if (lane == 0) bulk_wait_all();
     }
+}
+
+// ======================================================================================================================
+// Per-pass kernels ("3K"): the same rows schedule, one kernel per pass.  The fused kernel above keeps 28 rows of a chunk in
+// shared memory (86 KB -> 2 CTAs/SM) and is bound by the latency of the pass-1 row chain; with one pass per kernel the window
+// is 16 rows (53 KB -> 4 CTAs/SM), the instruction footprint is a third, and twice as many chunks are in flight per SM.  The
+// price is that a chunk streams through HBM three times (108 instead of 36 B per cell-update) — affordable, the tick is
+// latency bound, not bandwidth bound (profiles/r1_tick_ncu.md).  tickVisited marks of the chunk's own cells travel between
+// the three kernels in bit 7 of the flag plane; pass 3 clears them, so they never outlive a colour phase.
+constexpr int RN3 = 16;
+constexpr int PF3 = 3;
+
+struct __align__(128) SmemPass {
+    unsigned char ring[RN3 * ROW_BYTES];
+    Lut lut;
+    Ctx ctx;
+    unsigned long long bar[RN3];
+    unsigned char rowmod[32];
+    unsigned char rowchg[32];
+    unsigned char rowvis[32];
+    RowScratch rs;
+};
+
+template <int PASS>
+struct PassGeom {
+    static constexpr int KMIN = PASS == 1 ? -5 : (PASS == 2 ? -10 : 0);  // lowest row (below the chunk) that is read
+    static constexpr int FULL_LO = PASS == 1 ? -5 : (PASS == 2 ? -1 : 0);  // rows >= FULL_LO carry all planes and may be written
+    static constexpr int UP = PASS == 1 ? 5 : (PASS == 2 ? 1 : 0);          // rows above the current one that are touched
+    static constexpr int LAST = CHUNK - 1 + UP;
+    static constexpr int SL = UP + 1;                                       // a row is final SL steps after its own step
+    static constexpr int THREADS = PASS == 3 ? 64 : 160;
+};
+
+template <int PASS>
+__device__ __forceinline__ void pass_row_load(const TickParams& P, SmemPass& S, int k, int cx, int cy) {
+    using G = PassGeom<PASS>;
+    const int q = (k - G::KMIN) & (RN3 - 1);
+    const size_t y = (size_t)(cy + CHUNK - 1 - k);
+    unsigned char* row = S.ring + q * ROW_BYTES;
+    unsigned long long* bar = &S.bar[q];
+    const size_t o8 = y * P.W + (cx - HX8);
+    const size_t ow = y * P.W + (cx - HXW);
+    S.rowmod[q] = 0;
+    S.rowchg[q] = 0;
+    S.rowvis[q] = 0;
+    if (k < G::FULL_LO) {
+        mbar_expect_tx(bar, P8);
+        bulk_g2s(row + OFF_MAT, P.p.mat + o8, P8, bar);
+        return;
+    }
+    mbar_expect_tx(bar, ROW_BYTES);
+    bulk_g2s(row + OFF_MAT, P.p.mat + o8, P8, bar);
+    bulk_g2s(row + OFF_FLG, P.p.flg + o8, P8, bar);
+    bulk_g2s(row + OFF_STL, P.p.stl + o8, P8, bar);
+    bulk_g2s(row + OFF_TMP, P.p.tmp + ow, PW * 2, bar);
+    bulk_g2s(row + OFF_COL, P.p.col + ow, PW * 4, bar);
+    bulk_g2s(row + OFF_FL, P.p.fl + ow, PW * 4, bar);
+    bulk_g2s(row + OFF_FD, P.p.fd + ow, PW * 4, bar);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 4) tick_pass_kernel(const __grid_constant__ TickParams P) {
+    using G = PassGeom<PASS>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemPass& S = *reinterpret_cast<SmemPass*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int IO_WARP = G::THREADS / 32 - 1;
+    const bool io = warp == IO_WARP;
+
+    int cxi, cyi;
+    if (P.list_count && (int)blockIdx.x >= *P.list_count) return;
+    if (P.chunk_list) {
+        int v = P.chunk_list[blockIdx.x];
+        cxi = v & 0xffff;
+        cyi = v >> 16;
+    } else {
+        cxi = blockIdx.x % P.ncx;
+        cyi = blockIdx.x / P.ncx;
+    }
+    const int cx = P.x0 + cxi * 2 * CHUNK;
+    const int cy = P.y0 + cyi * 2 * CHUNK;
+
+    const DevTables* T = P.tabs;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(&T->lut);
+        uint4* dst = reinterpret_cast<uint4*>(&S.lut);
+        for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+        uint32_t* z = reinterpret_cast<uint32_t*>(&S.rs);
+        for (int i = tid; i < (int)(sizeof(RowScratch) / 4); i += blockDim.x) z[i] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < CHUNK + 2; i += blockDim.x)
+        for (int b = 0; b < 2; b++) {
+            S.rs.claimDn[b][i] = 1 << 30;
+            S.rs.claimUp[b][i] = 1 << 30;
+            S.rs.claim3[b][i] = 1 << 30;
+        }
+    Ctx& c = S.ctx;
+    if (tid == 0) {
+        for (int q = 0; q < RN3; q++) mbar_init(&S.bar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        c.ring = S.ring;
+        c.L = &S.lut;
+        c.rowmod = S.rowmod;
+        c.rowchg = S.rowchg;
+        c.rowvis = S.rowvis;
+        c.T = T;
+        c.pbuf = P.pbuf;
+        c.pcount = P.pcount;
+        c.pcap = P.pcap;
+        c.rkey = P.rkey;
+        c.tick = P.tick;
+        c.iter = P.iter;
+        c.nmat = T->n;
+        c.yoff = P.y_off;
+        c.ringn = RN3;
+        c.ringmask = RN3 - 1;
+        c.koff = -G::KMIN;
+        c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
+    }
+    __syncthreads();
+
+    if (io && lane == 0) {
+        for (int k = G::KMIN; k < G::UP + PF3; k++) pass_row_load<PASS>(P, S, k, cx, cy);
+    }
+    for (int k = G::KMIN; k < G::UP; k++) mbar_wait(&S.bar[(k - G::KMIN) & (RN3 - 1)], (uint32_t)(((k - G::KMIN) >> 4) & 1));
+
+    const int n_steps = G::LAST + G::SL + 1;
+    for (int st = 0; st < n_steps; st++) {
+        const int kw = st + G::UP;
+        if (kw <= G::LAST) mbar_wait(&S.bar[(kw - G::KMIN) & (RN3 - 1)], (uint32_t)(((kw - G::KMIN) >> 4) & 1));
+        fence_proxy_async();
+        __syncthreads();
+        if (!io) {
+            if (st < CHUNK) {
+                if (PASS == 1) pass1_rows(c, S.rs, st, cx, cy, tid);
+                else if (PASS == 2) pass2_rows(c, S.rs, st, cx, cy, tid);
+                else pass3_rows(c, S.rs, st, cx, cy, lane);
+            }
+        } else {
+            const int ks = st - G::SL;
+            if (ks >= G::FULL_LO && ks <= G::LAST) {
+                const int q = (ks - G::KMIN) & (RN3 - 1);
+                uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
+                const bool core_row = ks >= 0 && ks < CHUNK;
+                bool had_vis = false;
+                for (int w = lane; w < P8 / 4; w += 32) {
+                    const uint32_t v = fw[w];
+                    // tickVisited of the chunk's own cells survives passes 1 and 2 (the later passes need it); everything else is cleared
+                    const bool keep = PASS != 3 && core_row && w >= HX8 / 4 && w < (HX8 + CHUNK) / 4;
+                    if (!keep && (v & 0x80808080U)) {
+                        fw[w] = v & 0x7f7f7f7fU;
+                        had_vis = true;
+                    }
+                }
+                const bool vis_store = PASS == 3 ? __any_sync(0xffffffffu, had_vis) != 0 && core_row : S.rowvis[q] != 0;
+                const bool all_store = S.rowmod[q] != 0;
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && (all_store || vis_store)) {
+                    const size_t y = (size_t)(cy + CHUNK - 1 - ks);
+                    unsigned char* row = S.ring + q * ROW_BYTES;
+                    const size_t o8 = y * P.W + (cx - HX8);
+                    const size_t ow = y * P.W + (cx - HXW);
+                    bulk_s2g(P.p.flg + o8, row + OFF_FLG, P8);
+                    if (all_store) {
+                        bulk_s2g(P.p.mat + o8, row + OFF_MAT, P8);
+                        bulk_s2g(P.p.stl + o8, row + OFF_STL, P8);
+                        bulk_s2g(P.p.tmp + ow, row + OFF_TMP, PW * 2);
+                        bulk_s2g(P.p.col + ow, row + OFF_COL, PW * 4);
+                        bulk_s2g(P.p.fl + ow, row + OFF_FL, PW * 4);
+                        bulk_s2g(P.p.fd + ow, row + OFF_FD, PW * 4);
+                    }
+                }
+                if (lane == 0) bulk_commit();
+            }
+            const int kl = st + G::UP + PF3;
+            if (kl <= G::LAST && lane == 0) {
+                bulk_wait_read<1>();
+                pass_row_load<PASS>(P, S, kl, cx, cy);
+            }
+        }
+    }
+    if (io && lane == 0) bulk_wait_all();
 }
 
 }  // namespace fse

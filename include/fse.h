@@ -200,6 +200,7 @@ FSE_API int fse_stats_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32
  * bottom-up rows; each has a bit-exact CPU restatement in oracle/. */
 #define FSE_SCHEDULE_CLASSES 0 /* 4 interleaved column classes, rules executed in place           */
 #define FSE_SCHEDULE_ROWS 1    /* whole row decides from the pre-step state, then commits (default) */
+#define FSE_SCHEDULE_ROWS_FUSED 2 /* same results as ROWS, all three passes pipelined in one kernel      */
 FSE_API int fse_set_schedule(fse_world* w, int schedule);
 /* world::tick() (world.cpp:1036-1948) without the physicsCheck tail (see
  * fse_flood_component).  Asynchronous. */

@@ -15,7 +15,7 @@ from tests import helpers as Hh
 pytestmark = pytest.mark.gpu
 
 
-SCHEDULES = {"rows": (1, 2), "classes": (0, 1)}  # name -> (FSE_SCHEDULE_*, oracle Schedule)
+SCHEDULES = {"rows": (1, 2), "rows_fused": (2, 2), "classes": (0, 1)}  # name -> (FSE_SCHEDULE_*, oracle Schedule)
 
 
 def _pair(oracle, gpu_ctx, table, W, H, sched="rows"):
@@ -51,7 +51,7 @@ def test_roundtrip_rect(oracle, gpu_ctx, table):
     Hh.assert_cells_equal(cells[33:83, 17:117], sub, "sub-rect")
 
 
-@pytest.mark.parametrize("sched", ["rows", "classes"])
+@pytest.mark.parametrize("sched", ["rows", "rows_fused", "classes"])
 def test_column_drop_exact(oracle, gpu_ctx, table, sched):
     W = H = 512
     ow, gw = _pair(oracle, gpu_ctx, table, W, H, sched)
@@ -60,7 +60,7 @@ def test_column_drop_exact(oracle, gpu_ctx, table, sched):
     _run_and_compare(ow, gw, 40, every=4, what="column")
 
 
-@pytest.mark.parametrize("sched", ["rows", "classes"])
+@pytest.mark.parametrize("sched", ["rows", "rows_fused", "classes"])
 def test_mixed_exact(oracle, gpu_ctx, table, sched):
     W = H = 512
     ow, gw = _pair(oracle, gpu_ctx, table, W, H, sched)
@@ -69,7 +69,7 @@ def test_mixed_exact(oracle, gpu_ctx, table, sched):
     _run_and_compare(ow, gw, 30, seed=7, every=3, what="mixed")
 
 
-@pytest.mark.parametrize("sched", ["rows", "classes"])
+@pytest.mark.parametrize("sched", ["rows", "rows_fused", "classes"])
 def test_mixed_interactions_exact(oracle, gpu_ctx, table, sched):
     W, H = 640, 512
     tbl, extra = G.bench_table(table)
