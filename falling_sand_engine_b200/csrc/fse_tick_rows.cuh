@@ -29,7 +29,7 @@ struct RowScratch {
     float outL[CHUNK + 2], outR[CHUNK + 2], refL[CHUNK + 2], refR[CHUNK + 2];
     uint32_t area_arg[CHUNK];
     int claimDn[2][CHUNK + 2], claimUp[2][CHUNK + 2], claim3[2][CHUNK + 2];
-    int p1_any[2], p1_area[2], p2_any[2], p2_poke[2], p3_any[2];
+    int p1_any[2], p1_area[2], p1_horiz[2], p2_any[2], p2_poke[2], p3_any[2];
     long long dbg_arrival[2][4];
     long long dbg_phase[6];  // profiling aid: clock at which each role finished its step (double-buffered)
     uint32_t area_mask[2][4];   // columns of this row with an area effect to apply (bit i = column i)
@@ -50,13 +50,25 @@ struct __align__(128) SmemRows {
 };
 
 // ring geometry from the context (the fused kernel uses 28 rows, the per-pass kernels 16)
-__device__ __forceinline__ int rsn(const Ctx& c, int s, int dy) {
+template <int RN>
+__device__ __forceinline__ int rsn(int s, int dy) {
+    if ((RN & (RN - 1)) == 0) return (s - dy) & (RN - 1);
     int v = s - dy;
-    if (v < 0) v += c.ringn;
-    if (v >= c.ringn) v -= c.ringn;
+    if (v < 0) v += RN;
+    if (v >= RN) v -= RN;
     return v;
 }
-__device__ __forceinline__ int slotk(const Ctx& c, int k) { return c.ringmask ? ((k + c.koff) & c.ringmask) : ((k + c.koff) % c.ringn); }
+template <int RN>
+__device__ __forceinline__ int slotk(const Ctx& c, int k) { return (RN & (RN - 1)) == 0 ? ((k + c.koff) & (RN - 1)) : ((k + c.koff) % RN); }
+
+// optional pass-1 phase clocks (scripts/role_cycles.py); compiled out unless FSE_ROLE_CYCLES is defined
+#ifdef FSE_ROLE_CYCLES
+#define FSE_P1_CLOCK(name) const long long name = clock64()
+#define FSE_P1_PHASE(slot, since) do { if (t == 0) R.dbg_phase[slot] += clock64() - (since); } while (0)
+#else
+#define FSE_P1_CLOCK(name) do { } while (0)
+#define FSE_P1_PHASE(slot, since) do { } while (0)
+#endif
 
 __device__ __forceinline__ void pass_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
@@ -70,6 +82,7 @@ __device__ __forceinline__ float clampflow(float flow, float cap, bool speed) {
 // FIRE decision (world.cpp:1101-1146) for the fire cell at (s, jf), evaluated by the whole warp: lane i < 25 owns neighbour
 // (xx, yy) = (i / 5 - 2, i % 5 - 2) — the reference's loop order, so the RNG slots are the same.  Returns the decision bits
 // (A_FIRE | DB_EMBER | DB_DIE) and the ignite mask; every lane gets the same values.
+template <int RN>
 __device__ __forceinline__ uint32_t decide_fire_coop(const Ctx& c, int s, int jf, int xf, int y, int lane, uint32_t& ignite) {
     const uint32_t cb = rng_cell(c.rkey, xf, y);
     uint32_t bits = A_FIRE;
@@ -77,7 +90,7 @@ __device__ __forceinline__ uint32_t decide_fire_coop(const Ctx& c, int s, int jf
     if (rng_draw(cb, S_FIRE_EMBER) % 10 == 0) bits |= DB_EMBER;
     if (rng_draw(cb, S_FIRE_DIE) % 150 == 0) return bits | DB_DIE;
     bool solid = false;
-    if (lane < 25) solid = PHYS(rsn(c, s, lane % 5 - 2), jf + lane / 5 - 2) == P_SOLID;
+    if (lane < 25) solid = PHYS(rsn<RN>(s, lane % 5 - 2), jf + lane / 5 - 2) == P_SOLID;
     const unsigned solids = __ballot_sync(0xffffffffu, solid);
     ignite = __ballot_sync(0xffffffffu, solid && rng_draw(cb, S_FIRE_IGNITE0 + lane) % 500 == 0);
     if (!solids && rng_draw(cb, S_FIRE_DIE_ALONE) % 120 == 0) bits |= DB_DIE;
@@ -85,6 +98,7 @@ __device__ __forceinline__ uint32_t decide_fire_coop(const Ctx& c, int s, int jf
 }
 
 // ---- pass 1: decide (world.cpp:1089-1586, read-only) ------------------------------------------------------------------
+template <int RN>
 __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
     Dec1 d;
     d.bits = A_NONE;
@@ -99,7 +113,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
     const int type = c.L->phys[m];
     if (type == P_AIR || type == P_SOLID) return d;
     const uint32_t cb = rng_cell(c.rkey, x, y);
-    const int sb = rsn(c, s, 1);
+    const int sb = rsn<RN>(s, 1);
     if ((int)m == c.fire) {  // 1101-1146: filled in warp-cooperatively by the caller (decide_fire_coop)
         d.bits = A_FIRE;
         return d;
@@ -135,7 +149,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
         const bool canL = can_sink(c, sb, j - 1, myDens), canR = can_sink(c, sb, j + 1, myDens);
         if ((canL || canR) && rng_draw(cb, S_SAND_HESITATE) % 20 == 0) return d;
         uint32_t bits;
-        if (bt == P_AIR && PHYS(rsn(c, s, 2), j) == P_AIR && PHYS(rsn(c, s, 3), j) == P_AIR && PHYS(rsn(c, s, 4), j) == P_AIR) {
+        if (bt == P_AIR && PHYS(rsn<RN>(s, 2), j) == P_AIR && PHYS(rsn<RN>(s, 3), j) == P_AIR && PHYS(rsn<RN>(s, 4), j) == P_AIR) {
             bits = A_SAND_PART;
         } else {
             bits = A_SAND_SWAP;
@@ -157,7 +171,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
         }
         const uint8_t mb0 = MAT(sb, j);
         const int bph = c.L->phys[mb0];
-        if ((double)fl > 0.005 && bph == P_AIR && PHYS(rsn(c, s, 2), j) == P_AIR && PHYS(rsn(c, s, 3), j) == P_AIR && PHYS(rsn(c, s, 4), j) == P_AIR) {
+        if ((double)fl > 0.005 && bph == P_AIR && PHYS(rsn<RN>(s, 2), j) == P_AIR && PHYS(rsn<RN>(s, 3), j) == P_AIR && PHYS(rsn<RN>(s, 4), j) == P_AIR) {
             d.bits = A_SOUP_PART;
             return d;
         }
@@ -221,7 +235,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
             fd -= rem;
             early = true;
         }
-        const int st = rsn(c, s, -1);
+        const int st = rsn<RN>(s, -1);
         const uint8_t mt = MAT(st, j);
         const int tph = c.L->phys[mt];
         if (tph == P_SOUP) bits |= DB_TOPSOUP;
@@ -261,20 +275,21 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
         return d;
     }
     if (type == P_GAS) {  // 1569-1585
-        const int st = rsn(c, s, -1);
+        const int st = rsn<RN>(s, -1);
         if (PHYS(st, j) == P_AIR && !((PHYS(st, j - 1) == P_AIR || PHYS(st, j + 1) == P_AIR) && rng_draw(cb, S_GAS1) % 2 == 0)) d.bits = A_GAS_UP;
     }
     return d;
 }
 
 // own-column commit; k = column index in the scratch arrays (j - HX8 + 1)
-__device__ void commit1(const Ctx& c, RowScratch& R, const Dec1& d, int s, int j, int x, int y) {
+template <int RN>
+__device__ void commit1(const Ctx& c, RowScratch& R, const Dec1& d, int s, int j, int x, int y, int par) {
     const int k = j - HX8 + 1;
     const int act = d.bits & 15;
     float oL = 0.0f, oR = 0.0f;
     uint8_t chg = 0, pkL = 0, pkR = 0, akind = 0;
     uint32_t aarg = 0;
-    const int sb = rsn(c, s, 1), st = rsn(c, s, -1);
+    const int sb = rsn<RN>(s, 1), st = rsn<RN>(s, -1);
     switch (act) {
         case A_MARK:
             FLG(s, j) = FLG(s, j) | F_VISITED;
@@ -380,6 +395,7 @@ __device__ void commit1(const Ctx& c, RowScratch& R, const Dec1& d, int s, int j
         default:
             break;
     }
+    if (oL != 0 || oR != 0 || chg || pkL || pkR) R.p1_horiz[par] = 1;
     R.outL[k] = oL;
     R.outR[k] = oR;
     R.refL[k] = 0.0f;
@@ -392,6 +408,7 @@ __device__ void commit1(const Ctx& c, RowScratch& R, const Dec1& d, int s, int j
 }
 
 // C2: column k (scratch index) of row slot s receives its horizontal inflows, un-settle flags and, for the row below, pokes
+template <int RN>
 __device__ __noinline__ void gather1(const Ctx& c, RowScratch& R, int s, int k) {
     const int j = k - 1 + HX8;
     const float inL = k > 0 ? R.outR[k - 1] : 0.0f, inR = k < CHUNK + 1 ? R.outL[k + 1] : 0.0f;
@@ -435,12 +452,13 @@ __device__ __noinline__ void gather1(const Ctx& c, RowScratch& R, int s, int k) 
     }
     if (((k > 0 && (R.chg[k - 1] & 2)) || (k < CHUNK + 1 && (R.chg[k + 1] & 1))) && PHYS(s, j) == P_SOUP) set_moved(c, s, j, false);
     if ((k > 0 && R.pkR[k - 1]) || (k < CHUNK + 1 && R.pkL[k + 1])) {
-        const int sb = rsn(c, s, 1);
+        const int sb = rsn<RN>(s, 1);
         if (PHYS(sb, j) == P_SAND) set_moved(c, sb, j, true);
     }
 }
 
 // C3 (serial, one thread): area effects in ascending source column; the first claimant of a cell wins it
+template <int RN>
 __device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, int cx, int y, int par) {
     auto claim = [&](int i, int tj, int dy) {  // dy in -5..5 rows below(+)/above(-)
         uint8_t& e = R.areaClaim[dy + 5][tj];
@@ -464,7 +482,7 @@ __device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, in
                 } else {
                     for (int kk = 0; kk < 25; kk++) {
                         const int xx = kk / 5 - 2, yy = kk % 5 - 2;
-                        if (((arg >> kk) & 1) && mine(i, j + xx, yy)) stc(c, rsn(c, s, yy), j + xx, create(c, c.fire, x + xx, y + yy), F_DIRTY | F_VISITED);
+                        if (((arg >> kk) & 1) && mine(i, j + xx, yy)) stc(c, rsn<RN>(s, yy), j + xx, create(c, c.fire, x + xx, y + yy), F_DIRTY | F_VISITED);
                     }
                     if (die && mine(i, j, 0)) stc(c, s, j, nothing(c), F_DIRTY | F_VISITED);
                 }
@@ -474,11 +492,11 @@ __device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, in
                         for (int yy = 0; yy <= 2; yy++) claim(i, j + xx, yy);
                 } else {
                     if (mine(i, j, 0)) stc(c, s, j, create(c, c.steam, x, y), F_DIRTY);
-                    if (mine(i, j, 1)) stc(c, rsn(c, s, 1), j, create(c, c.obsidian, x, y + 1), F_DIRTY | F_VISITED);
+                    if (mine(i, j, 1)) stc(c, rsn<RN>(s, 1), j, create(c, c.obsidian, x, y + 1), F_DIRTY | F_VISITED);
                     for (int xx = -1; xx <= 1; xx++)
                         for (int yy = 0; yy <= 2; yy++)
-                            if (mine(i, j + xx, yy) && (int)MAT(rsn(c, s, yy), j + xx) == c.lava)
-                                stc(c, rsn(c, s, yy), j + xx, create(c, c.obsidian, x + xx, y + yy), F_DIRTY | F_VISITED);
+                            if (mine(i, j + xx, yy) && (int)MAT(rsn<RN>(s, yy), j + xx) == c.lava)
+                                stc(c, rsn<RN>(s, yy), j + xx, create(c, c.obsidian, x + xx, y + yy), F_DIRTY | F_VISITED);
                 }
             } else {  // pair interactions (1153-1179): the list of the material the source had when it decided
                 int mb, msrc;
@@ -502,9 +520,9 @@ __device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, in
                             if (pass == 0) {
                                 claim(i, j + xx, yy);
                             } else if (mine(i, j + xx, yy)) {
-                                const int tm = MAT(rsn(c, s, yy), j + xx);
+                                const int tm = MAT(rsn<RN>(s, yy), j + xx);
                                 const bool hit = in.type == FSE_INTERACT_TRANSFORM_MATERIAL ? tm == mb : ((xx == 0 && yy == 0) || tm == c.air);
-                                if (hit) stc(c, rsn(c, s, yy), j + xx, create(c, in.data1, x + xx, y + yy), F_DIRTY | F_VISITED);
+                                if (hit) stc(c, rsn<RN>(s, yy), j + xx, create(c, in.data1, x + xx, y + yy), F_DIRTY | F_VISITED);
                             }
                         }
                 }
@@ -512,8 +530,9 @@ __device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, in
         }
 }
 
+template <int RN>
 __device__ void pass1_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int t) {
-    const int s = slotk(c, k);
+    const int s = slotk<RN>(c, k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
     const int lane = t & 31;
@@ -521,10 +540,11 @@ __device__ void pass1_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, i
     if (t == 0) {
         R.p1_any[par ^ 1] = 0;
         R.p1_area[par ^ 1] = 0;
+        R.p1_horiz[par ^ 1] = 0;
         R.area_mask[par ^ 1][0] = R.area_mask[par ^ 1][1] = R.area_mask[par ^ 1][2] = R.area_mask[par ^ 1][3] = 0;
     }
-    const long long T0 = clock64();
-    Dec1 d = decide1(c, s, j, cx + t, y);
+    FSE_P1_CLOCK(T0);
+    Dec1 d = decide1<RN>(c, s, j, cx + t, y);
     {  // FIRE cells of this warp's 32 columns, one at a time, all lanes helping
         unsigned fm = __ballot_sync(0xffffffffu, (d.bits & 15) == A_FIRE);
 #pragma unroll 1
@@ -533,57 +553,64 @@ __device__ void pass1_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, i
             fm &= fm - 1;
             const int tt = (t & ~31) + src;
             uint32_t ignite;
-            const uint32_t bits = decide_fire_coop(c, s, HX8 + tt, cx + tt, y, lane, ignite);
+            const uint32_t bits = decide_fire_coop<RN>(c, s, HX8 + tt, cx + tt, y, lane, ignite);
             if (lane == src) {
                 d.bits = bits;
                 d.fL = __uint_as_float(ignite);
             }
         }
     }
-    const int a = d.bits & 15;
+    int a = d.bits & 15;
+    if (a == A_MARK) {  // iterations exhausted (1095): only the cell's own visited bit, which no decision of this step reads
+        FLG(s, j) = FLG(s, j) | F_VISITED;
+        c.rowvis[s] = 1;
+        d.bits = a = A_NONE;
+    }
     if (a) R.p1_any[par] = 1;
     if ((a == A_FIRE && ((d.bits & DB_DIE) || __float_as_uint(d.fL))) || a == A_INTERACT || (d.bits & DB_WL)) {
         atomicOr(&R.area_mask[par][t >> 5], 1u << (t & 31));
         R.p1_area[par] = 1;
     }
-    const long long T0b = clock64();
     pass_bar(1);
     if (!R.p1_any[par]) {
-        if (t == 0) { R.dbg_phase[0] += clock64() - T0; R.dbg_phase[5] += T0b - T0; }
+        FSE_P1_PHASE(0, T0);
         return;
     }
-    const long long T1 = clock64();
-    commit1(c, R, d, s, j, cx + t, y);
+    FSE_P1_CLOCK(T1);
+    FSE_P1_PHASE(0, T0);
+    commit1<RN>(c, R, d, s, j, cx + t, y, par);
     pass_bar(1);
-    const long long T2 = R.refL[1 + t] == 12345.0f ? 0 : clock64();
-    gather1(c, R, s, 1 + t);
-    if (t == 0) gather1(c, R, s, 0);
-    if (t == CHUNK - 1) gather1(c, R, s, CHUNK + 1);
-    pass_bar(1);
-    const long long T3 = R.refL[1 + t] == 12345.0f ? 0 : clock64();
-    if (t == 0) { R.dbg_phase[0] += T1 - T0; R.dbg_phase[1] += T2 - T1; R.dbg_phase[2] += T3 - T2; R.dbg_phase[4] += 1; R.dbg_phase[5] += T0b - T0; }
-    {  // refunds to the sources, left flow first
+    FSE_P1_CLOCK(T2);
+    FSE_P1_PHASE(1, T1);
+    if (R.p1_horiz[par]) {  // somebody published a horizontal flow, an un-settle flag or a poke
+        gather1<RN>(c, R, s, 1 + t);
+        if (t == 0) gather1<RN>(c, R, s, 0);
+        if (t == CHUNK - 1) gather1<RN>(c, R, s, CHUNK + 1);
+        pass_bar(1);
+        // refunds to the sources, left flow first
         const int kk = 1 + t;
         if (R.refL[kk] != 0) { FD(s, j) = FD(s, j) + R.refL[kk]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
         if (R.refR[kk] != 0) { FD(s, j) = FD(s, j) + R.refR[kk]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
     }
+    FSE_P1_PHASE(2, T2);
     if (R.p1_area[par]) {
         uint32_t* cl = reinterpret_cast<uint32_t*>(&R.areaClaim[0][0]);
         for (int q = t; q < 11 * P8 / 4; q += CHUNK) cl[q] = 0;
         pass_bar(1);
-        if (t == 0) area_effects(c, R, s, cx, y, par);
+        if (t == 0) area_effects<RN>(c, R, s, cx, y, par);
     }
 }
 
 // ---- pass 2 (world.cpp:1594-1820) ----------------------------------------------------------------------------------------
 // decision: bits 0..2 act (0 none, 1 moved=false, 2 slide, 3 liquid apply, 4 gas diagonal), bit 3 dir right, 4 riser, 5 restick, 6 poke
+template <int RN>
 __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
     const uint8_t f0 = FLG(s, j);
     if (f0 & F_VISITED) return 0;
     const uint8_t m = MAT(s, j);
     const int type = c.L->phys[m];
     if (type == P_SAND) {
-        const int sb = rsn(c, s, 1);
+        const int sb = rsn<RN>(s, 1);
         const float myDens = c.L->dens[m];
         const bool canL = can_sink(c, sb, j - 1, myDens), canR = can_sink(c, sb, j + 1, myDens);
         if (!(canL || canR)) return 1;
@@ -594,7 +621,7 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
             int drop = 0;
 #pragma unroll 1
             for (int pil = 0; pil < 10; pil++) {
-                const int sp = rsn(c, s, 1 + pil);
+                const int sp = rsn<RN>(s, 1 + pil);
                 if (PHYS(sp, j - 1) == P_AIR || PHYS(sp, j + 1) == P_AIR) drop++;
             }
             const int dd = drop + 1 - (int)c.L->maxstab[m];
@@ -619,7 +646,7 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
     }
     if (type == P_SOUP) return 3;
     if (type == P_GAS) {
-        const int st = rsn(c, s, -1);
+        const int st = rsn<RN>(s, -1);
         const int aL = PHYS(st, j - 1), aR = PHYS(st, j + 1);
         if (aL == P_AIR && !(aR == P_AIR && rng_draw(rng_cell(c.rkey, x, y), S_GAS2) % 2 == 0)) return 4;
         if (aR == P_AIR) return 4 | 8;
@@ -627,6 +654,7 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
     return 0;
 }
 
+template <int RN>
 __device__ void commit2(const Ctx& c, RowScratch& R, uint32_t d, int s, int j, int par) {
     const int act = d & 7, i = j - HX8, dir = (d & 8) ? 1 : -1;
     uint8_t poke = 0;
@@ -636,7 +664,7 @@ __device__ void commit2(const Ctx& c, RowScratch& R, uint32_t d, int s, int j, i
     } else if (act == 2) {
         poke = (d & 64) ? 1 : 0;
         if (R.claimDn[par][i + 1 + dir] == i) {
-            const int sb = rsn(c, s, 1), jd = j + dir;
+            const int sb = rsn<RN>(s, 1), jd = j + dir;
             CellR tile = ldc(c, s, j);
             const CellR diag = ldc(c, sb, jd);
             if (d & 16) {
@@ -662,7 +690,7 @@ __device__ void commit2(const Ctx& c, RowScratch& R, uint32_t d, int s, int j, i
         }
     } else if (act == 4) {
         if (R.claimUp[par][i + 1 + dir] == i) {
-            const int st = rsn(c, s, -1), jd = j + dir;
+            const int st = rsn<RN>(s, -1), jd = j + dir;
             const CellR tile = ldc(c, s, j), other = ldc(c, st, jd);
             stc(c, s, j, other, F_DIRTY);
             stc(c, st, jd, tile, F_DIRTY | F_VISITED);
@@ -671,8 +699,9 @@ __device__ void commit2(const Ctx& c, RowScratch& R, uint32_t d, int s, int j, i
     R.poke2[i] = poke;
 }
 
+template <int RN>
 __device__ void pass2_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int t) {
-    const int s = slotk(c, k);
+    const int s = slotk<RN>(c, k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
     const int j = HX8 + t;
@@ -685,17 +714,17 @@ __device__ void pass2_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, i
         R.p2_any[par ^ 1] = 0;
         R.p2_poke[par ^ 1] = 0;
     }
-    const uint32_t d = decide2(c, s, j, cx + t, y);
+    const uint32_t d = decide2<RN>(c, s, j, cx + t, y);
     if (d) R.p2_any[par] = 1;
     if (d & 64) R.p2_poke[par] = 1;
     if ((d & 7) == 2) atomicMin(&R.claimDn[par][t + 1 + ((d & 8) ? 1 : -1)], t);
     if ((d & 7) == 4) atomicMin(&R.claimUp[par][t + 1 + ((d & 8) ? 1 : -1)], t);
     pass_bar(2);
     if (!R.p2_any[par]) return;
-    commit2(c, R, d, s, j, par);
+    commit2<RN>(c, R, d, s, j, par);
     if (R.p2_poke[par]) {  // 1658-1673: "moved" handed to the sand below, after the slides
         pass_bar(2);
-        const int sb = rsn(c, s, 1);
+        const int sb = rsn<RN>(s, 1);
         if (R.poke2[t] && PHYS(sb, j) == P_SAND) set_moved(c, sb, j, true);
     }
 }
@@ -724,8 +753,9 @@ __device__ void commit3(const Ctx& c, RowScratch& R, int d, int s, int j, int x,
     }
 }
 
+template <int RN>
 __device__ void pass3_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int lane) {
-    const int s = slotk(c, k);
+    const int s = slotk<RN>(c, k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
     // quick vote: any unvisited GAS in this row?
@@ -822,13 +852,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
     if (io && lane == 0) {
         for (int k = -HALO_DN; k < HALO_UP + PF; k++) issue_row_load_any(P, S.ring, S.bar, S.rowmod, S.rowchg, k, cx, cy);
     }
-    for (int k = -HALO_DN; k < HALO_UP; k++) mbar_wait(&S.bar[slotk(c, k)], 0);
+    for (int k = -HALO_DN; k < HALO_UP; k++) mbar_wait(&S.bar[slotk<RING>(c, k)], 0);
 
     bool io_modified = false, io_inert = true;
     long long dbg_acc = 0;
     for (int st = 0; st < N_STEPS; st++) {
         const int kw = st + HALO_UP;
-        if (kw <= LAST_ROW) mbar_wait(&S.bar[slotk(c, kw)], (uint32_t)(((kw + HALO_DN) / RING) & 1));
+        if (kw <= LAST_ROW) mbar_wait(&S.bar[slotk<RING>(c, kw)], (uint32_t)(((kw + HALO_DN) / RING) & 1));
         fence_proxy_async();
         __syncthreads();
         long long clk0 = 0;
@@ -837,18 +867,18 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
             clk0 = max(max(a[0], a[1]), max(a[2], a[3]));
         }
         if (role == 0) {
-            if (st < CHUNK) pass1_rows(c, S.rs, st, cx, cy, t);
+            if (st < CHUNK) pass1_rows<RING>(c, S.rs, st, cx, cy, t);
         } else if (role == 1) {
             const int k = st - L12;
-            if (k >= 0 && k < CHUNK) pass2_rows(c, S.rs, k, cx, cy, t);
+            if (k >= 0 && k < CHUNK) pass2_rows<RING>(c, S.rs, k, cx, cy, t);
         } else if (role == 2) {
             const int k = st - L12 - L23;
-            if (k >= 0 && k < CHUNK) pass3_rows(c, S.rs, k, cx, cy, lane);
+            if (k >= 0 && k < CHUNK) pass3_rows<RING>(c, S.rs, k, cx, cy, lane);
         } else if (io) {
             const int ks = st - STORE_LAG;
             if (ks >= -HALO_WR && ks <= LAST_ROW) {
-                const int q = slotk(c, ks);
-                if (P.awake && ks >= 0 && ks < CHUNK) io_inert &= row_is_inert(c, q, rsn(c, q, 1), lane);
+                const int q = slotk<RING>(c, ks);
+                if (P.awake && ks >= 0 && ks < CHUNK) io_inert &= row_is_inert(c, q, rsn<RING>(q, 1), lane);
                 io_modified |= S.rowchg[q] != 0;
                 if (S.rowmod[q]) {
                     uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
@@ -1027,9 +1057,9 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 4) tick_pass_kernel(c
         __syncthreads();
         if (!io) {
             if (st < CHUNK) {
-                if (PASS == 1) pass1_rows(c, S.rs, st, cx, cy, tid);
-                else if (PASS == 2) pass2_rows(c, S.rs, st, cx, cy, tid);
-                else pass3_rows(c, S.rs, st, cx, cy, lane);
+                if (PASS == 1) pass1_rows<RN3>(c, S.rs, st, cx, cy, tid);
+                else if (PASS == 2) pass2_rows<RN3>(c, S.rs, st, cx, cy, tid);
+                else pass3_rows<RN3>(c, S.rs, st, cx, cy, lane);
             }
         } else {
             const int ks = st - G::SL;
