@@ -1085,17 +1085,16 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(tick_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemRows));
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(tick_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPass));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPass));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPass));
+        e = cudaFuncSetAttribute(tick_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPass<1>));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPass<2>));
         if (e != cudaSuccess) return e;
         configured = true;
     }
     if (n_chunks <= 0) return cudaSuccess;
     if (P.schedule == FSE_SCHEDULE_ROWS && !P.awake && !P.fused) {  // one kernel per pass
-        tick_pass_kernel<1><<<n_chunks, PassGeom<1>::THREADS, sizeof(SmemPass), stream>>>(P);
-        tick_pass_kernel<2><<<n_chunks, PassGeom<2>::THREADS, sizeof(SmemPass), stream>>>(P);
-        tick_pass_kernel<3><<<n_chunks, PassGeom<3>::THREADS, sizeof(SmemPass), stream>>>(P);
+        tick_pass_kernel<1><<<n_chunks, PassGeom<1>::THREADS, sizeof(SmemPass<1>), stream>>>(P);
+        tick_pass_kernel<2><<<n_chunks, PassGeom<2>::THREADS, sizeof(SmemPass<2>), stream>>>(P);
+        tick_pass3_kernel<<<n_chunks * (CHUNK / 4), 128, 0, stream>>>(P);
     } else if (P.schedule == FSE_SCHEDULE_ROWS)
         tick_rows_kernel<<<n_chunks, ROWS_THREADS, sizeof(SmemRows), stream>>>(P);
     else

@@ -25,18 +25,30 @@ struct Dec1 {
     float fd_new, fD, fL, fR, fU;  // FIRE: fL carries the ignite mask
 };
 
-struct RowScratch {
+// per-row scratch of each pass (shared memory); the fused kernel carries all three, a per-pass kernel only its own
+struct Scratch1 {
     float outL[CHUNK + 2], outR[CHUNK + 2], refL[CHUNK + 2], refR[CHUNK + 2];
     uint32_t area_arg[CHUNK];
-    int claimDn[2][CHUNK + 2], claimUp[2][CHUNK + 2], claim3[2][CHUNK + 2];
-    int p1_any[2], p1_area[2], p1_horiz[2], p2_any[2], p2_poke[2], p3_any[2];
-    long long dbg_arrival[2][4];
-    long long dbg_phase[6];  // profiling aid: clock at which each role finished its step (double-buffered)
+    uint32_t hf[CHUNK + 2];  // what each column published in C1 (see commit1); entries 0 and CHUNK + 1 stay 0
+    int p1_any[2], p1_area[2], p1_horiz[2];
     uint32_t area_mask[2][4];   // columns of this row with an area effect to apply (bit i = column i)
     uint8_t areaClaim[11][P8];  // serial C3: claimant column + 1 (0 = free); 4-byte aligned (cleared as words)
-    uint8_t chg[CHUNK + 2], pkL[CHUNK + 2], pkR[CHUNK + 2], area_kind[CHUNK], poke2[CHUNK];
+    uint8_t area_kind[CHUNK];
+    long long dbg_phase[6];     // profiling aid (FSE_ROLE_CYCLES)
 };
-static_assert(offsetof(RowScratch, areaClaim) % 4 == 0, "areaClaim is cleared with 32-bit stores");
+struct Scratch2 {
+    int claimDn[2][CHUNK + 2], claimUp[2][CHUNK + 2];
+    int p2_any[2], p2_poke[2];
+    uint8_t poke2[CHUNK];
+};
+struct Scratch3 {
+    int claim3[2][CHUNK + 2];
+};
+struct RowScratch : Scratch1, Scratch2, Scratch3 {
+    long long dbg_arrival[2][4];  // profiling aid: clock at which each role finished its step (double-buffered)
+};
+static_assert(offsetof(Scratch1, areaClaim) % 4 == 0, "areaClaim is cleared with 32-bit stores");
+static_assert(sizeof(Scratch1) % 4 == 0 && sizeof(Scratch2) % 4 == 0 && sizeof(Scratch3) % 4 == 0, "scratch is cleared with 32-bit stores");
 
 struct __align__(128) SmemRows {
     unsigned char ring[RING * ROW_BYTES];
@@ -283,7 +295,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
 
 // own-column commit; k = column index in the scratch arrays (j - HX8 + 1)
 template <int RN>
-__device__ void commit1(const Ctx& c, RowScratch& R, const Dec1& d, int s, int j, int x, int y, int par) {
+__device__ void commit1(const Ctx& c, Scratch1& R, const Dec1& d, int s, int j, int x, int y, int par) {
     const int k = j - HX8 + 1;
     const int act = d.bits & 15;
     float oL = 0.0f, oR = 0.0f;
@@ -395,23 +407,27 @@ __device__ void commit1(const Ctx& c, RowScratch& R, const Dec1& d, int s, int j
         default:
             break;
     }
-    if (oL != 0 || oR != 0 || chg || pkL || pkR) R.p1_horiz[par] = 1;
-    R.outL[k] = oL;
-    R.outR[k] = oR;
-    R.refL[k] = 0.0f;
-    R.refR[k] = 0.0f;
-    R.chg[k] = chg;
-    R.pkL[k] = pkL;
-    R.pkR[k] = pkR;
-    R.area_kind[k - 1] = akind;
-    R.area_arg[k - 1] = aarg;
+    // publish: bit 0/1 flow to the left/right, bit 2/3 un-settle the left/right soup neighbour, bit 4/5 poke the sand below-left/right
+    const uint32_t h = (oL != 0 ? 1u : 0u) | (oR != 0 ? 2u : 0u) | ((uint32_t)chg << 2) | ((uint32_t)pkL << 4) | ((uint32_t)pkR << 5);
+    R.hf[k] = h;
+    if (h) {
+        R.p1_horiz[par] = 1;
+        if (h & 1) R.outL[k] = oL;
+        if (h & 2) R.outR[k] = oR;
+    }
+    if (akind) {
+        R.area_kind[k - 1] = akind;
+        R.area_arg[k - 1] = aarg;
+    }
 }
 
 // C2: column k (scratch index) of row slot s receives its horizontal inflows, un-settle flags and, for the row below, pokes
 template <int RN>
-__device__ __noinline__ void gather1(const Ctx& c, RowScratch& R, int s, int k) {
+__device__ __forceinline__ void gather1(const Ctx& c, Scratch1& R, int s, int k) {
+    const uint32_t hl = k > 0 ? R.hf[k - 1] : 0u, hr = k < CHUNK + 1 ? R.hf[k + 1] : 0u;
+    if (!((hl & (2u | 8u | 32u)) | (hr & (1u | 4u | 16u)))) return;
     const int j = k - 1 + HX8;
-    const float inL = k > 0 ? R.outR[k - 1] : 0.0f, inR = k < CHUNK + 1 ? R.outL[k + 1] : 0.0f;
+    const float inL = (hl & 2) ? R.outR[k - 1] : 0.0f, inR = (hr & 1) ? R.outL[k + 1] : 0.0f;
     if (inL != 0 || inR != 0) {
         const uint8_t m = MAT(s, j);
         const int ph = c.L->phys[m];
@@ -450,8 +466,8 @@ __device__ __noinline__ void gather1(const Ctx& c, RowScratch& R, int s, int k) 
             }
         }
     }
-    if (((k > 0 && (R.chg[k - 1] & 2)) || (k < CHUNK + 1 && (R.chg[k + 1] & 1))) && PHYS(s, j) == P_SOUP) set_moved(c, s, j, false);
-    if ((k > 0 && R.pkR[k - 1]) || (k < CHUNK + 1 && R.pkL[k + 1])) {
+    if (((hl & 8) || (hr & 4)) && PHYS(s, j) == P_SOUP) set_moved(c, s, j, false);
+    if ((hl & 32) || (hr & 16)) {
         const int sb = rsn<RN>(s, 1);
         if (PHYS(sb, j) == P_SAND) set_moved(c, sb, j, true);
     }
@@ -459,7 +475,7 @@ __device__ __noinline__ void gather1(const Ctx& c, RowScratch& R, int s, int k) 
 
 // C3 (serial, one thread): area effects in ascending source column; the first claimant of a cell wins it
 template <int RN>
-__device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, int cx, int y, int par) {
+__device__ __noinline__ void area_effects(const Ctx& c, Scratch1& R, int s, int cx, int y, int par) {
     auto claim = [&](int i, int tj, int dy) {  // dy in -5..5 rows below(+)/above(-)
         uint8_t& e = R.areaClaim[dy + 5][tj];
         if (e == 0) e = (uint8_t)(i + 1);
@@ -531,7 +547,7 @@ __device__ __noinline__ void area_effects(const Ctx& c, RowScratch& R, int s, in
 }
 
 template <int RN>
-__device__ void pass1_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int t) {
+__device__ void pass1_rows(const Ctx& c, Scratch1& R, int k, int cx, int cy, int t) {
     const int s = slotk<RN>(c, k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
@@ -589,8 +605,10 @@ __device__ void pass1_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, i
         pass_bar(1);
         // refunds to the sources, left flow first
         const int kk = 1 + t;
-        if (R.refL[kk] != 0) { FD(s, j) = FD(s, j) + R.refL[kk]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
-        if (R.refR[kk] != 0) { FD(s, j) = FD(s, j) + R.refR[kk]; c.rowmod[s] = 1; c.rowchg[s] = 1; }
+        const float rl = R.refL[kk], rr = R.refR[kk];
+        if (rl != 0) { FD(s, j) = FD(s, j) + rl; R.refL[kk] = 0.0f; }
+        if (rr != 0) { FD(s, j) = FD(s, j) + rr; R.refR[kk] = 0.0f; }
+        if (rl != 0 || rr != 0) { c.rowmod[s] = 1; c.rowchg[s] = 1; }
     }
     FSE_P1_PHASE(2, T2);
     if (R.p1_area[par]) {
@@ -655,7 +673,7 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
 }
 
 template <int RN>
-__device__ void commit2(const Ctx& c, RowScratch& R, uint32_t d, int s, int j, int par) {
+__device__ void commit2(const Ctx& c, Scratch2& R, uint32_t d, int s, int j, int par) {
     const int act = d & 7, i = j - HX8, dir = (d & 8) ? 1 : -1;
     uint8_t poke = 0;
     if (act == 1) {
@@ -700,7 +718,7 @@ __device__ void commit2(const Ctx& c, RowScratch& R, uint32_t d, int s, int j, i
 }
 
 template <int RN>
-__device__ void pass2_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int t) {
+__device__ void pass2_rows(const Ctx& c, Scratch2& R, int k, int cx, int cy, int t) {
     const int s = slotk<RN>(c, k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
@@ -742,7 +760,7 @@ __device__ int decide3(const Ctx& c, int s, int j, int x, int y) {  // 0 none, -
     return 0;
 }
 
-__device__ void commit3(const Ctx& c, RowScratch& R, int d, int s, int j, int x, int y, int par) {
+__device__ void commit3(const Ctx& c, Scratch3& R, int d, int s, int j, int x, int y, int par) {
     const int i = j - HX8;
     if (d == 2) {
         stc(c, s, j, create(c, c.water, x, y), F_DIRTY);
@@ -754,7 +772,7 @@ __device__ void commit3(const Ctx& c, RowScratch& R, int d, int s, int j, int x,
 }
 
 template <int RN>
-__device__ void pass3_rows(const Ctx& c, RowScratch& R, int k, int cx, int cy, int lane) {
+__device__ void pass3_rows(const Ctx& c, Scratch3& R, int k, int cx, int cy, int lane) {
     const int s = slotk<RN>(c, k);
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
@@ -925,40 +943,50 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
 }
 
 // ======================================================================================================================
-// Per-pass kernels ("3K"): the same rows schedule, one kernel per pass.  The fused kernel above keeps 28 rows of a chunk in
+// Per-pass kernels: the same rows schedule, one kernel per pass.  The fused kernel above keeps 28 rows of a chunk in
 // shared memory (86 KB -> 2 CTAs/SM) and is bound by the latency of the pass-1 row chain; with one pass per kernel the window
-// is 16 rows (53 KB -> 4 CTAs/SM), the instruction footprint is a third, and twice as many chunks are in flight per SM.  The
-// price is that a chunk streams through HBM three times (108 instead of 36 B per cell-update) — affordable, the tick is
-// latency bound, not bandwidth bound (profiles/r1_tick_ncu.md).  tickVisited marks of the chunk's own cells travel between
-// the three kernels in bit 7 of the flag plane; pass 3 clears them, so they never outlive a colour phase.
-constexpr int RN3 = 16;
-constexpr int PF3 = 3;
+// is 13-14 rows (42 KB -> 5 CTAs/SM), the instruction footprint is a third, and more chunks are in flight per SM.  The
+// price is that a chunk streams through HBM more than once — affordable, the tick is latency bound, not bandwidth bound
+// (profiles/r1_tick_ncu.md).  tickVisited marks of the chunk's own cells travel between the kernels in bit 7 of the flag
+// plane; pass 3 clears them, so they never outlive a colour phase.
+//   pass 1, pass 2: one CTA per chunk (4 compute warps + 1 IO warp), rows bottom-up through a shared-memory window
+//   pass 3: its rows do not depend on each other (a gas cell only looks at and moves within its own row), so it runs one
+//           warp per row straight on global memory
+template <int PASS>
+struct PassGeom {
+    static constexpr int KMIN = PASS == 1 ? -5 : -10;     // lowest row (below the chunk) that is read
+    static constexpr int FULL_LO = PASS == 1 ? -5 : -1;   // rows >= FULL_LO carry all planes and may be written
+    static constexpr int UP = PASS == 1 ? 5 : 1;          // rows above the current one that are touched
+    static constexpr int LAST = CHUNK - 1 + UP;
+    static constexpr int SL = UP + 1;                     // a row is final SL steps after its own step
+    static constexpr int RN = PASS == 1 ? 13 : 14;        // rows in the window: live rows + one row in flight each way
+    static constexpr int PF = 2;                          // rows loaded ahead of the step that needs them
+    static constexpr int THREADS = 160;
+};
+// pass 1: live rows st-5..st+5; the row loaded at step st (st+7) takes the slot of row st-6, whose store is issued in the same step
+// pass 2: live rows st-10..st+1; the row loaded at step st (st+3) takes the slot of row st-11
+static_assert(PassGeom<1>::UP + PassGeom<1>::PF - PassGeom<1>::RN == -PassGeom<1>::SL, "pass 1 window");
+static_assert(PassGeom<2>::UP + PassGeom<2>::PF - PassGeom<2>::RN < PassGeom<2>::KMIN, "pass 2 window");
 
+template <int PASS> struct PassScratch { typedef Scratch1 type; };
+template <> struct PassScratch<2> { typedef Scratch2 type; };
+
+template <int PASS>
 struct __align__(128) SmemPass {
-    unsigned char ring[RN3 * ROW_BYTES];
+    unsigned char ring[PassGeom<PASS>::RN * ROW_BYTES];
     Lut lut;
     Ctx ctx;
-    unsigned long long bar[RN3];
+    unsigned long long bar[PassGeom<PASS>::RN];
     unsigned char rowmod[32];
     unsigned char rowchg[32];
     unsigned char rowvis[32];
-    RowScratch rs;
+    typename PassScratch<PASS>::type rs;
 };
 
 template <int PASS>
-struct PassGeom {
-    static constexpr int KMIN = PASS == 1 ? -5 : (PASS == 2 ? -10 : 0);  // lowest row (below the chunk) that is read
-    static constexpr int FULL_LO = PASS == 1 ? -5 : (PASS == 2 ? -1 : 0);  // rows >= FULL_LO carry all planes and may be written
-    static constexpr int UP = PASS == 1 ? 5 : (PASS == 2 ? 1 : 0);          // rows above the current one that are touched
-    static constexpr int LAST = CHUNK - 1 + UP;
-    static constexpr int SL = UP + 1;                                       // a row is final SL steps after its own step
-    static constexpr int THREADS = PASS == 3 ? 64 : 160;
-};
-
-template <int PASS>
-__device__ __forceinline__ void pass_row_load(const TickParams& P, SmemPass& S, int k, int cx, int cy) {
+__device__ __forceinline__ void pass_row_load(const TickParams& P, SmemPass<PASS>& S, int k, int cx, int cy) {
     using G = PassGeom<PASS>;
-    const int q = (k - G::KMIN) & (RN3 - 1);
+    const int q = (k - G::KMIN) % G::RN;
     const size_t y = (size_t)(cy + CHUNK - 1 - k);
     unsigned char* row = S.ring + q * ROW_BYTES;
     unsigned long long* bar = &S.bar[q];
@@ -983,13 +1011,12 @@ __device__ __forceinline__ void pass_row_load(const TickParams& P, SmemPass& S, 
 }
 
 template <int PASS>
-__global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 4) tick_pass_kernel(const __grid_constant__ TickParams P) {
+__global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 5) tick_pass_kernel(const __grid_constant__ TickParams P) {
     using G = PassGeom<PASS>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    SmemPass& S = *reinterpret_cast<SmemPass*>(smem_raw);
+    SmemPass<PASS>& S = *reinterpret_cast<SmemPass<PASS>*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int IO_WARP = G::THREADS / 32 - 1;
-    const bool io = warp == IO_WARP;
+    const bool io = warp == G::THREADS / 32 - 1;
 
     int cxi, cyi;
     if (P.list_count && (int)blockIdx.x >= *P.list_count) return;
@@ -1010,18 +1037,17 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 4) tick_pass_kernel(c
         uint4* dst = reinterpret_cast<uint4*>(&S.lut);
         for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
         uint32_t* z = reinterpret_cast<uint32_t*>(&S.rs);
-        for (int i = tid; i < (int)(sizeof(RowScratch) / 4); i += blockDim.x) z[i] = 0;
+        for (int i = tid; i < (int)(sizeof(S.rs) / 4); i += blockDim.x) z[i] = 0;
     }
     __syncthreads();
-    for (int i = tid; i < CHUNK + 2; i += blockDim.x)
-        for (int b = 0; b < 2; b++) {
-            S.rs.claimDn[b][i] = 1 << 30;
-            S.rs.claimUp[b][i] = 1 << 30;
-            S.rs.claim3[b][i] = 1 << 30;
-        }
+    if (PASS == 2) {
+        Scratch2& R2 = reinterpret_cast<Scratch2&>(S.rs);
+        for (int i = tid; i < CHUNK + 2; i += blockDim.x)
+            for (int b = 0; b < 2; b++) R2.claimDn[b][i] = R2.claimUp[b][i] = 1 << 30;
+    }
     Ctx& c = S.ctx;
     if (tid == 0) {
-        for (int q = 0; q < RN3; q++) mbar_init(&S.bar[q], 1);
+        for (int q = 0; q < G::RN; q++) mbar_init(&S.bar[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         c.ring = S.ring;
         c.L = &S.lut;
@@ -1037,48 +1063,43 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 4) tick_pass_kernel(c
         c.iter = P.iter;
         c.nmat = T->n;
         c.yoff = P.y_off;
-        c.ringn = RN3;
-        c.ringmask = RN3 - 1;
+        c.ringn = G::RN;
+        c.ringmask = 0;
         c.koff = -G::KMIN;
         c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
     }
     __syncthreads();
 
+    // row k lives in slot (k - KMIN) % RN and is the ((k - KMIN) / RN)-th user of that slot's mbarrier
     if (io && lane == 0) {
-        for (int k = G::KMIN; k < G::UP + PF3; k++) pass_row_load<PASS>(P, S, k, cx, cy);
+        for (int k = G::KMIN; k < G::UP + G::PF; k++) pass_row_load<PASS>(P, S, k, cx, cy);
     }
-    for (int k = G::KMIN; k < G::UP; k++) mbar_wait(&S.bar[(k - G::KMIN) & (RN3 - 1)], (uint32_t)(((k - G::KMIN) >> 4) & 1));
+    for (int k = G::KMIN; k < G::UP; k++) mbar_wait(&S.bar[(k - G::KMIN) % G::RN], (uint32_t)(((k - G::KMIN) / G::RN) & 1));
 
     const int n_steps = G::LAST + G::SL + 1;
     for (int st = 0; st < n_steps; st++) {
         const int kw = st + G::UP;
-        if (kw <= G::LAST) mbar_wait(&S.bar[(kw - G::KMIN) & (RN3 - 1)], (uint32_t)(((kw - G::KMIN) >> 4) & 1));
+        if (kw <= G::LAST) mbar_wait(&S.bar[(kw - G::KMIN) % G::RN], (uint32_t)(((kw - G::KMIN) / G::RN) & 1));
         fence_proxy_async();
         __syncthreads();
         if (!io) {
             if (st < CHUNK) {
-                if (PASS == 1) pass1_rows<RN3>(c, S.rs, st, cx, cy, tid);
-                else if (PASS == 2) pass2_rows<RN3>(c, S.rs, st, cx, cy, tid);
-                else pass3_rows<RN3>(c, S.rs, st, cx, cy, lane);
+                if (PASS == 1) pass1_rows<G::RN>(c, reinterpret_cast<Scratch1&>(S.rs), st, cx, cy, tid);
+                else pass2_rows<G::RN>(c, reinterpret_cast<Scratch2&>(S.rs), st, cx, cy, tid);
             }
         } else {
             const int ks = st - G::SL;
             if (ks >= G::FULL_LO && ks <= G::LAST) {
-                const int q = (ks - G::KMIN) & (RN3 - 1);
+                const int q = (ks - G::KMIN) % G::RN;
                 uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
                 const bool core_row = ks >= 0 && ks < CHUNK;
-                bool had_vis = false;
                 for (int w = lane; w < P8 / 4; w += 32) {
-                    const uint32_t v = fw[w];
-                    // tickVisited of the chunk's own cells survives passes 1 and 2 (the later passes need it); everything else is cleared
-                    const bool keep = PASS != 3 && core_row && w >= HX8 / 4 && w < (HX8 + CHUNK) / 4;
-                    if (!keep && (v & 0x80808080U)) {
-                        fw[w] = v & 0x7f7f7f7fU;
-                        had_vis = true;
-                    }
+                    // tickVisited of the chunk's own cells goes to HBM (the later passes need it); halo cells are cleared
+                    const bool keep = core_row && w >= HX8 / 4 && w < (HX8 + CHUNK) / 4;
+                    if (!keep) fw[w] &= 0x7f7f7f7fU;
                 }
-                const bool vis_store = PASS == 3 ? __any_sync(0xffffffffu, had_vis) != 0 && core_row : S.rowvis[q] != 0;
                 const bool all_store = S.rowmod[q] != 0;
+                const bool vis_store = S.rowvis[q] != 0;
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && (all_store || vis_store)) {
@@ -1095,17 +1116,117 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 4) tick_pass_kernel(c
                         bulk_s2g(P.p.fl + ow, row + OFF_FL, PW * 4);
                         bulk_s2g(P.p.fd + ow, row + OFF_FD, PW * 4);
                     }
+                    bulk_commit();
                 }
-                if (lane == 0) bulk_commit();
             }
-            const int kl = st + G::UP + PF3;
+            const int kl = st + G::UP + G::PF;
             if (kl <= G::LAST && lane == 0) {
-                bulk_wait_read<1>();
+                bulk_wait_read<0>();  // the slot may be the one whose store was just issued (pass 1)
                 pass_row_load<PASS>(P, S, kl, cx, cy);
             }
         }
     }
     if (io && lane == 0) bulk_wait_all();
+}
+
+// ---- pass 3 on global memory: one warp per chunk row, lane l owns columns 4l..4l+3 (world.cpp:1828-1891) ---------------------
+// A gas cell moves sideways into an AIR neighbour of its own row (left first, coin flip when both are free) or, if it is
+// STEAM and boxed in, condenses with probability 1/10.  All cells decide from the row as pass 2 left it; a contested AIR
+// cell goes to the lower source column, i.e. a left-mover at i loses exactly when cell i-2 moves right.  Visited bits are
+// dropped from the whole row afterwards (the colour phase is over).
+__global__ void __launch_bounds__(128) tick_pass3_kernel(const __grid_constant__ TickParams P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x >> 5;
+    const int r = ((blockIdx.x & 31) << 2) + warp;  // memory row inside the chunk
+    int cxi, cyi;
+    if (P.list_count && chunk >= *P.list_count) return;
+    if (P.chunk_list) {
+        int v = P.chunk_list[chunk];
+        cxi = v & 0xffff;
+        cyi = v >> 16;
+    } else {
+        cxi = chunk % P.ncx;
+        cyi = chunk / P.ncx;
+    }
+    const int cx = P.x0 + cxi * 2 * CHUNK;
+    const int ym = P.y0 + cyi * 2 * CHUNK + r;
+    const int y = ym + P.y_off;
+    const DevTables* T = P.tabs;
+    const uint8_t* phys = T->lut.phys;
+    const size_t base = (size_t)ym * P.W + cx;
+    uint32_t* flgw = reinterpret_cast<uint32_t*>(P.p.flg + base) + lane;
+    const uint32_t fw = *flgw;
+    const uint32_t mw = *(reinterpret_cast<const uint32_t*>(P.p.mat + base) + lane);
+    const bool hadvis = (fw & 0x80808080U) != 0;
+    int ph[4];
+    bool gas = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        ph[q] = __ldg(phys + ((mw >> (8 * q)) & 0xff));
+        gas |= ph[q] == P_GAS && !((fw >> (8 * q)) & F_VISITED);
+    }
+    if (!__any_sync(0xffffffffu, gas)) {
+        if (hadvis) *flgw = fw & 0x7f7f7f7fU;
+        return;
+    }
+    // phys of the columns left of q = 0 and right of q = 3
+    int phL = __shfl_up_sync(0xffffffffu, ph[3], 1), phR = __shfl_down_sync(0xffffffffu, ph[0], 1);
+    if (lane == 0) phL = __ldg(phys + P.p.mat[base - 1]);
+    if (lane == 31) phR = __ldg(phys + P.p.mat[base + CHUNK]);
+    int d[4];
+    uint32_t rm = 0;  // bit q: cell q moves right
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        d[q] = 0;
+        if (ph[q] != P_GAS || ((fw >> (8 * q)) & F_VISITED)) continue;
+        const int l = q == 0 ? phL : ph[q - 1], rr = q == 3 ? phR : ph[q + 1];
+        const int m = (mw >> (8 * q)) & 0xff;
+        const uint32_t cb = rng_cell(P.rkey, cx + 4 * lane + q, y);
+        if (l == P_AIR && !(rr == P_AIR && rng_draw(cb, S_GAS3) % 2 == 0)) d[q] = -1;
+        else if (rr == P_AIR) d[q] = 1;
+        else if (m == T->steam && rng_draw(cb, S_STEAM) % 10 == 0) d[q] = 2;
+        if (d[q] == 1) rm |= 1u << q;
+    }
+    uint32_t rmPrev = __shfl_up_sync(0xffffffffu, rm, 1);
+    if (lane == 0) rmPrev = 0;
+    if (hadvis) *flgw = fw & 0x7f7f7f7fU;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (d[q] == 0) continue;
+        const size_t a = base + 4 * lane + q;
+        if (d[q] == 2) {  // 1884-1888
+            const uint64_t ct = create_color_temp(T, P.rkey, T->water, cx + 4 * lane + q, y);
+            P.p.mat[a] = (uint8_t)T->water;
+            P.p.flg[a] = F_DIRTY;
+            P.p.stl[a] = 0;
+            P.p.tmp[a] = (int16_t)(uint16_t)(ct >> 32);
+            P.p.col[a] = (uint32_t)ct;
+            P.p.fl[a] = 2.0f;
+            P.p.fd[a] = 0.0f;
+            continue;
+        }
+        if (d[q] == -1) {  // the AIR cell on the left is contested by the cell two columns to the left moving right
+            const bool lost = q >= 2 ? ((rm >> (q - 2)) & 1) : ((rmPrev >> (q + 2)) & 1);
+            if (lost) continue;
+        }
+        const size_t b = a + d[q];
+        const uint8_t fa = P.p.flg[a], fb = P.p.flg[b];
+        const uint8_t ma = P.p.mat[a], mb = P.p.mat[b];
+        const uint8_t sa = P.p.stl[a], sb = P.p.stl[b];
+        const int16_t ta = P.p.tmp[a], tb = P.p.tmp[b];
+        const uint32_t ca = P.p.col[a], cb2 = P.p.col[b];
+        const float la = P.p.fl[a], lb = P.p.fl[b];
+        const float da = P.p.fd[a], db = P.p.fd[b];
+        P.p.mat[a] = mb; P.p.mat[b] = ma;
+        P.p.flg[a] = (uint8_t)(F_DIRTY | (fb & F_MOVED));
+        P.p.flg[b] = (uint8_t)(F_DIRTY | (fa & F_MOVED));
+        P.p.stl[a] = sb; P.p.stl[b] = sa;
+        P.p.tmp[a] = tb; P.p.tmp[b] = ta;
+        P.p.col[a] = cb2; P.p.col[b] = ca;
+        P.p.fl[a] = lb; P.p.fl[b] = la;
+        P.p.fd[a] = db; P.p.fd[b] = da;
+    }
 }
 
 }  // namespace fse
