@@ -35,7 +35,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("FSE_B200_LIB") or LIB_PATH
     if not os.path.exists(path):
         raise FseError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(nvcc, sm_100a). There is no CPU fallback.")

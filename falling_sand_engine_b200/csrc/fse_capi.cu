@@ -594,9 +594,10 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                     P.awake = w->d_awake;
                 }
                 if (int r = kt.begin(w->stream)) return r;
-                CK(launch_tick_phase(P, n_chunks, w->stream));
+                int nl = 0;
+                CK(launch_tick_phase(P, n_chunks, w->stream, &nl));
                 if (int r = kt.end(w->stream)) return r;
-                w->ctx->launches += 1;
+                w->ctx->launches += nl;
                 continue;
             }
             // strip: boundary chunk rows first, halo rows over NCCL on the side stream, interior chunk rows meanwhile
@@ -606,8 +607,9 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             if (int r = kt.begin(w->stream)) return r;
             if (w->list_cnt[tk][0] > 0) {
                 P.chunk_list = w->d_chunk_lists + w->list_off[tk][0];
-                CK(launch_tick_phase(P, w->list_cnt[tk][0], w->stream));
-                w->ctx->launches += 1;
+                int nl = 0;
+                CK(launch_tick_phase(P, w->list_cnt[tk][0], w->stream, &nl));
+                w->ctx->launches += nl;
             }
             if (multi) {
                 CK(cudaEventRecord(w->ev_boundary, w->stream));
@@ -617,8 +619,9 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             }
             if (w->list_cnt[tk][1] > 0) {
                 P.chunk_list = w->d_chunk_lists + w->list_off[tk][1];
-                CK(launch_tick_phase(P, w->list_cnt[tk][1], w->stream));
-                w->ctx->launches += 1;
+                int nl = 0;
+                CK(launch_tick_phase(P, w->list_cnt[tk][1], w->stream, &nl));
+                w->ctx->launches += nl;
             }
             if (int r = kt.end(w->stream)) return r;
             if (multi) CK(cudaStreamWaitEvent(w->stream, w->ev_comm, 0));

@@ -91,7 +91,7 @@ int fail(int code, const char* fmt, ...);
 int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cudaStream_t s);
 int strip_refresh(fse_world* w, cudaStream_t s);
 size_t tick_smem_bytes();
-cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream);
+cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched);  // *launched = kernels enqueued
 cudaError_t launch_compact_active(const uint8_t* awake, int acols, int ci0, int cj0, int ncx, int ncy, int* list, int* count, cudaStream_t s);
 
 cudaError_t launch_write_rect(Planes p, int W, int x0, int y0, int rw, int rh, const fse_cell* src, cudaStream_t s);

@@ -48,12 +48,27 @@ constexpr float FLUID_MinFlow = 0.05f;
 constexpr float FLUID_MaxFlow = 8.0f;
 constexpr float FLUID_FlowSpeed = 1.0f;
 
-struct __align__(128) Smem {
-    unsigned char ring[RING * ROW_BYTES];
+// Every tick kernel starts its dynamic shared memory with the same head, so the rule code reaches the material LUT, the row
+// flags and the row window at compile-time offsets (plain LDS/STS, no pointer loads).
+struct SmemHead {
     Lut lut;
-    unsigned long long bar[RING];
     unsigned char rowmod[32];  // row must be stored back (any plane or the dirty bit changed)
     unsigned char rowchg[32];  // cell state other than the dirty bit changed (active-region tracking)
+    unsigned char rowvis[32];  // row got tickVisited marks only (per-pass kernels persist them through HBM)
+    unsigned char pad_[32];
+};
+static_assert(sizeof(SmemHead) % 128 == 0, "the row window behind the head must stay 128-byte aligned");
+extern __shared__ __align__(128) unsigned char fse_smem[];
+#define LUTP (reinterpret_cast<const Lut*>(fse_smem))
+#define ROWMOD (fse_smem + offsetof(SmemHead, rowmod))
+#define ROWCHG (fse_smem + offsetof(SmemHead, rowchg))
+#define ROWVIS (fse_smem + offsetof(SmemHead, rowvis))
+#define RINGP (fse_smem + sizeof(SmemHead))
+
+struct __align__(128) Smem {
+    SmemHead h;
+    unsigned char ring[RING * ROW_BYTES];
+    unsigned long long bar[RING];
 };
 
 struct CellR {
@@ -67,10 +82,6 @@ struct CellR {
 };
 
 struct Ctx {
-    unsigned char* ring;
-    const Lut* L;
-    unsigned char* rowmod;
-    unsigned char* rowchg;
     const DevTables* T;
     fse_particle* pbuf;
     unsigned int* pcount;
@@ -81,7 +92,6 @@ struct Ctx {
     int nmat;
     int yoff;  // global y of local row 0 (strip worlds), 0 otherwise
     int ringn, ringmask, koff;  // ring geometry of the running kernel (rows kernels): slot(k) = (k + koff) mod ringn
-    unsigned char* rowvis;      // row got tickVisited marks only (per-pass kernels persist them through HBM)
     int air, fire, water, lava, steam, obsidian;
 };
 
@@ -131,14 +141,14 @@ __device__ __forceinline__ int rs(int s, int dy) {  // slot of the row dy below 
     if (v >= RING) v -= RING;
     return v;
 }
-#define MAT(s, j) (c.ring[(s) * ROW_BYTES + OFF_MAT + (j)])
-#define FLG(s, j) (c.ring[(s) * ROW_BYTES + OFF_FLG + (j)])
-#define STL(s, j) (c.ring[(s) * ROW_BYTES + OFF_STL + (j)])
-#define TMP(s, j) (*reinterpret_cast<int16_t*>(c.ring + (s) * ROW_BYTES + OFF_TMP + ((j) - (HX8 - HXW)) * 2))
-#define COL(s, j) (*reinterpret_cast<uint32_t*>(c.ring + (s) * ROW_BYTES + OFF_COL + ((j) - (HX8 - HXW)) * 4))
-#define FL(s, j) (*reinterpret_cast<float*>(c.ring + (s) * ROW_BYTES + OFF_FL + ((j) - (HX8 - HXW)) * 4))
-#define FD(s, j) (*reinterpret_cast<float*>(c.ring + (s) * ROW_BYTES + OFF_FD + ((j) - (HX8 - HXW)) * 4))
-#define PHYS(s, j) (c.L->phys[MAT(s, j)])
+#define MAT(s, j) (RINGP[(s) * ROW_BYTES + OFF_MAT + (j)])
+#define FLG(s, j) (RINGP[(s) * ROW_BYTES + OFF_FLG + (j)])
+#define STL(s, j) (RINGP[(s) * ROW_BYTES + OFF_STL + (j)])
+#define TMP(s, j) (*reinterpret_cast<int16_t*>(RINGP + (s) * ROW_BYTES + OFF_TMP + ((j) - (HX8 - HXW)) * 2))
+#define COL(s, j) (*reinterpret_cast<uint32_t*>(RINGP + (s) * ROW_BYTES + OFF_COL + ((j) - (HX8 - HXW)) * 4))
+#define FL(s, j) (*reinterpret_cast<float*>(RINGP + (s) * ROW_BYTES + OFF_FL + ((j) - (HX8 - HXW)) * 4))
+#define FD(s, j) (*reinterpret_cast<float*>(RINGP + (s) * ROW_BYTES + OFF_FD + ((j) - (HX8 - HXW)) * 4))
+#define PHYS(s, j) (LUTP->phys[MAT(s, j)])
 
 __device__ __forceinline__ CellR ldc(const Ctx& c, int s, int j) {
     CellR r;
@@ -164,8 +174,8 @@ __device__ __forceinline__ void stc_raw(const Ctx* cp, int s, int j, uint32_t p0
     COL(s, j) = col;
     FL(s, j) = fl;
     FD(s, j) = fd;
-    c.rowmod[s] = 1;
-    c.rowchg[s] = 1;
+    ROWMOD[s] = 1;
+    ROWCHG[s] = 1;
 }
 __device__ __forceinline__ void stc(const Ctx& c, int s, int j, const CellR& r, uint8_t setbits) {
     stc_raw(&c, s, j, (uint32_t)r.mat | ((uint32_t)r.stl << 8) | ((uint32_t)(uint16_t)r.tmp << 16), (r.moved ? 1u : 0u) | ((uint32_t)setbits << 8),
@@ -176,14 +186,14 @@ __device__ __forceinline__ void set_moved(const Ctx& c, int s, int j, bool v) {
     uint8_t g = v ? (f | F_MOVED) : (f & ~F_MOVED);
     if (g != f) {
         FLG(s, j) = g;
-        c.rowmod[s] = 1;
-        c.rowchg[s] = 1;
+        ROWMOD[s] = 1;
+        ROWCHG[s] = 1;
     }
 }
 __device__ __forceinline__ void set_bits(const Ctx& c, int s, int j, uint8_t bits) {  // dirty and/or visited
     uint8_t f = FLG(s, j);
     FLG(s, j) = f | bits;
-    if ((bits & F_DIRTY) && !(f & F_DIRTY)) c.rowmod[s] = 1;
+    if ((bits & F_DIRTY) && !(f & F_DIRTY)) ROWMOD[s] = 1;
 }
 
 // Tiles_NOTHING (game_datastruct.cpp:312)
@@ -298,8 +308,8 @@ __device__ __forceinline__ float vertical_flow(float remaining, float dest) {
 // canMoveBelow* (world.cpp:1206,1214-1215,1609-1610)
 __device__ __forceinline__ bool can_sink(const Ctx& c, int s, int j, float myDensity) {
     uint8_t m = MAT(s, j);
-    int t = c.L->phys[m];
-    return t == P_AIR || (t != P_SOLID && c.L->dens[m] < myDensity);
+    int t = LUTP->phys[m];
+    return t == P_AIR || (t != P_SOLID && LUTP->dens[m] < myDensity);
 }
 
 // one liquid outflow into a neighbour (world.cpp:1324-1333 and its three siblings)
@@ -310,18 +320,18 @@ __device__ __forceinline__ void pour(const Ctx& c, int s, int j, int nbPhys, con
         stc(c, s, j, n, 0);
     } else {
         FD(s, j) = FD(s, j) + flow;
-        c.rowmod[s] = 1;
-        c.rowchg[s] = 1;
+        ROWMOD[s] = 1;
+        ROWCHG[s] = 1;
     }
 }
 
 // tile.mat->interact && nInteractions[below.id] > 0 (world.cpp:1153), from the shared-memory partner bitmap
 __device__ __forceinline__ bool has_interaction(const Ctx& c, uint8_t m, uint8_t mb) {
-    const uint8_t mf = c.L->mflags[m];
+    const uint8_t mf = LUTP->mflags[m];
     if (!(mf & MF_INTERACT)) return false;
     if (mf & MF_INTERACT_SLOW) return c.T->inter_off[m * c.nmat + mb + 1] > c.T->inter_off[m * c.nmat + mb];
-    const int r = c.L->irow[m];
-    return r != 0 && ((c.L->ibits[r - 1][mb >> 5] >> (mb & 31)) & 1u);
+    const int r = LUTP->irow[m];
+    return r != 0 && ((LUTP->ibits[r - 1][mb >> 5] >> (mb & 31)) & 1u);
 }
 
 // ---- FIRE (world.cpp:1101-1146), one fire cell handled by the whole warp: lane i < 25 owns neighbour
@@ -330,7 +340,7 @@ __device__ __forceinline__ bool has_interaction(const Ctx& c, uint8_t m, uint8_t
 __device__ void fire_coop(const Ctx& c, int s, int jf, int xf, int y, int lane) {
     const uint8_t f0 = FLG(s, jf);
     if (f0 & F_VISITED) return;  // 1091
-    if (c.iter >= (int)c.L->iters[c.fire]) {  // 1093-1096
+    if (c.iter >= (int)LUTP->iters[c.fire]) {  // 1093-1096
         if (lane == 0) FLG(s, jf) = f0 | F_VISITED;
         return;
     }
@@ -365,11 +375,11 @@ __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
     uint8_t f0 = FLG(s, j);
     if (f0 & F_VISITED) return;  // 1091
     const uint8_t m = MAT(s, j);
-    if (c.iter >= (int)c.L->iters[m]) {  // 1093-1096
+    if (c.iter >= (int)LUTP->iters[m]) {  // 1093-1096
         FLG(s, j) = f0 | F_VISITED;
         return;
     }
-    const int type = c.L->phys[m];
+    const int type = LUTP->phys[m];
     if (type == P_AIR || type == P_SOLID) return;  // no rule matches (FIRE is PASSABLE)
     const uint32_t cb = rng_cell(c.rkey, x, y);
     const int sb = rs(s, 1);  // row below
@@ -378,8 +388,8 @@ __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
 
     if (type == P_SAND) {  // 1148-1267
         const uint8_t mb = MAT(sb, j);
-        const int below = c.L->phys[mb];
-        const uint8_t mf = c.L->mflags[m];
+        const int below = LUTP->phys[mb];
+        const uint8_t mf = LUTP->mflags[m];
 
         if ((mf & MF_INTERACT) && has_interaction(c, m, mb)) {  // 1153-1179
             const int n = c.nmat;
@@ -410,7 +420,7 @@ __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
             bool react = false;
             const int16_t temp = TMP(s, j);
             if (!(mf & MF_REACT_MULTI)) {
-                const Lut::Rx rx = c.L->rx[m];
+                const Lut::Rx rx = LUTP->rx[m];
                 bool hit = (rx.type == FSE_REACT_TEMPERATURE_BELOW && temp < rx.thr) || (rx.type == FSE_REACT_TEMPERATURE_ABOVE && temp > rx.thr);
                 if (hit) {
                     CellR n = create(c, rx.prod, x, y);
@@ -433,8 +443,8 @@ __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
             }
             if (react) return;
         }
-        const float myDens = c.L->dens[m];
-        bool canMoveBelow = (below == P_AIR || (below != P_SOLID && c.L->dens[mb] < myDens));  // 1206
+        const float myDens = LUTP->dens[m];
+        bool canMoveBelow = (below == P_AIR || (below != P_SOLID && LUTP->dens[mb] < myDens));  // 1206
         if (!canMoveBelow) return;
         bool canL = can_sink(c, sb, j - 1, myDens);
         bool canR = can_sink(c, sb, j + 1, myDens);
@@ -465,12 +475,12 @@ __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
         if (tile.fl == 0.0f) return;  // 1275
         if (tile.fl < FLUID_MinValue) {  // 1277-1281
             FL(s, j) = 0.0f;
-            c.rowmod[s] = 1;
-            c.rowchg[s] = 1;
+            ROWMOD[s] = 1;
+            ROWCHG[s] = 1;
             return;
         }
         const uint8_t mb0 = MAT(sb, j);
-        const int bottomPhys = c.L->phys[mb0];
+        const int bottomPhys = LUTP->phys[mb0];
         if ((double)tile.fl > 0.005 && bottomPhys == P_AIR && PHYS(rs(s, 2), j) == P_AIR && PHYS(rs(s, 3), j) == P_AIR &&
             PHYS(rs(s, 4), j) == P_AIR) {  // 1283-1305
             stc(c, s, j, nothing(c), F_DIRTY);
@@ -517,7 +527,7 @@ __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
             return;
         }
         const uint8_t ml = MAT(s, j - 1), mr = MAT(s, j + 1);
-        const int leftPhys = c.L->phys[ml], rightPhys = c.L->phys[mr];
+        const int leftPhys = LUTP->phys[ml], rightPhys = LUTP->phys[mr];
         const float leftFl = FL(s, j - 1), rightFl = FL(s, j + 1);
         const bool canMoveLeft = (leftPhys == P_AIR || ml == m) && !airBelow;    // 1350
         const bool canMoveRight = (rightPhys == P_AIR || mr == m) && !airBelow;  // 1353
@@ -557,7 +567,7 @@ __device__ void visit1(const Ctx& c, int s, int j, int x, int y) {
         }
         const int st = rs(s, -1);  // row above
         const uint8_t mt = MAT(st, j);
-        const int topPhys = c.L->phys[mt];
+        const int topPhys = LUTP->phys[mt];
         if (topPhys == P_AIR || mt == m) {  // 1413-1432
             float dstFl = topPhys == P_SOUP ? FL(st, j) : 0.0f;
             float flow = remainingValue - vertical_flow(remainingValue, dstFl);
@@ -621,15 +631,15 @@ __device__ void visit2(const Ctx& c, int s, int j, int x, int y) {
     const uint8_t f0 = FLG(s, j);
     if (f0 & F_VISITED) return;  // 1596
     const uint8_t m = MAT(s, j);
-    const int type = c.L->phys[m];
+    const int type = LUTP->phys[m];
     if (type == P_SAND) {  // 1602-1727
         const uint32_t cb = rng_cell(c.rkey, x, y);
         const int sb = rs(s, 1);
-        const float myDens = c.L->dens[m];
+        const float myDens = LUTP->dens[m];
         const bool canL = can_sink(c, sb, j - 1, myDens);
         const bool canR = can_sink(c, sb, j + 1, myDens);
         bool stoppedByFriction = !(f0 & F_MOVED);  // 1612
-        const int slip = c.L->slip[m];
+        const int slip = LUTP->slip[m];
         bool nowMoved = (f0 & F_MOVED) != 0;  // real_tiles[idx].moved (the local `tile` copy keeps the old flag)
         if (!(canL || canR)) {
             // 1647-1654 fires whatever the pillar probe decides (an un-stick at 1637 is overwritten at 1648)
@@ -642,7 +652,7 @@ __device__ void visit2(const Ctx& c, int s, int j, int x, int y) {
                 int sp = rs(s, 1 + pil);
                 if (PHYS(sp, j - 1) == P_AIR || PHYS(sp, j + 1) == P_AIR) drop++;
             }
-            int d = drop + 1 - (int)c.L->maxstab[m];
+            int d = drop + 1 - (int)LUTP->maxstab[m];
             if (d > 0) {
                 int chance = 1000 / d;
                 if (chance < 1000 && rng_draw(cb, S_SAND2_UNSTICK) % chance == 0) {
@@ -692,8 +702,8 @@ __device__ void visit2(const Ctx& c, int s, int j, int x, int y) {
             FL(s, j) = a;
             FD(s, j) = 0.0f;
             FLG(s, j) = f0 | F_DIRTY | F_VISITED;
-            c.rowmod[s] = 1;
-            if (fd != 0.0f) c.rowchg[s] = 1;  // amount += 0 leaves the cell as it was (only dirty[] is re-set)
+            ROWMOD[s] = 1;
+            if (fd != 0.0f) ROWCHG[s] = 1;  // amount += 0 leaves the cell as it was (only dirty[] is re-set)
         }
     } else if (type == P_GAS) {  // 1799-1819
         const int st = rs(s, -1);
@@ -716,7 +726,7 @@ __device__ void visit2(const Ctx& c, int s, int j, int x, int y) {
 __device__ void visit3(const Ctx& c, int s, int j, int x, int y) {
     if (FLG(s, j) & F_VISITED) return;  // 1830
     const uint8_t m = MAT(s, j);
-    if (c.L->phys[m] != P_GAS) return;
+    if (LUTP->phys[m] != P_GAS) return;
     int l = PHYS(s, j - 1), r = PHYS(s, j + 1);
     const uint32_t cb = rng_cell(c.rkey, x, y);
     int jd = 0;
@@ -750,12 +760,12 @@ __device__ void pass1_row(const Ctx& c, int k, int cx, int cy, int lane) {
     for (int b = 0; b < 4; b++) {
         uint32_t m = (mw >> (8 * b)) & 0xff;
         bool vis = (fw >> (8 * b)) & F_VISITED;
-        bool gated = c.iter >= (int)c.L->iters[m];
-        int ph = c.L->phys[m];
+        bool gated = c.iter >= (int)LUTP->iters[m];
+        int ph = LUTP->phys[m];
         if (!vis && gated) gate |= (uint32_t)F_VISITED << (8 * b);
         const bool fire = (int)m == c.fire;
         if (!vis && !gated && (ph == P_SAND || ph == P_SOUP || ph == P_GAS || fire)) act = true;
-        if (fire || (c.L->mflags[m] & MF_INTERACT)) spec = true;
+        if (fire || (LUTP->mflags[m] & MF_INTERACT)) spec = true;
     }
     if (!__any_sync(0xffffffffu, act)) {
         // inert row: the only effect of pass 1 is tickVisited = true on cells past their iteration count (1093-1096)
@@ -777,7 +787,7 @@ __device__ void pass1_row(const Ctx& c, int k, int cx, int cy, int lane) {
         const uint8_t m = MAT(s, j);
         if ((int)m == c.fire) {
             phase = 1 + (lane & 1);
-        } else if (c.L->phys[m] == P_SAND && has_interaction(c, m, MAT(sb, j))) {
+        } else if (LUTP->phys[m] == P_SAND && has_interaction(c, m, MAT(sb, j))) {
             phase = 3 + (lane % 3);
         }
         const unsigned special = __ballot_sync(0xffffffffu, phase != 0);
@@ -812,7 +822,7 @@ __device__ void pass2_row(const Ctx& c, int k, int cx, int cy, int lane) {
     bool act = false;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
-        int ph = c.L->phys[(mw >> (8 * b)) & 0xff];
+        int ph = LUTP->phys[(mw >> (8 * b)) & 0xff];
         bool vis = (fw >> (8 * b)) & F_VISITED;
         if (!vis && (ph == P_SAND || ph == P_SOUP || ph == P_GAS)) act = true;
     }
@@ -832,7 +842,7 @@ __device__ void pass3_row(const Ctx& c, int k, int cx, int cy, int lane) {
     bool act = false;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
-        int ph = c.L->phys[(mw >> (8 * b)) & 0xff];
+        int ph = LUTP->phys[(mw >> (8 * b)) & 0xff];
         bool vis = (fw >> (8 * b)) & F_VISITED;
         if (!vis && ph == P_GAS) act = true;
     }
@@ -870,7 +880,7 @@ __device__ __forceinline__ void issue_row_load_any(const TickParams& P, unsigned
 }
 
 __device__ __forceinline__ void issue_row_load(const TickParams& P, Smem& S, int k, int cx, int cy) {
-    issue_row_load_any(P, S.ring, S.bar, S.rowmod, S.rowchg, k, cx, cy);
+    issue_row_load_any(P, S.ring, S.bar, S.h.rowmod, S.h.rowchg, k, cx, cy);
 }
 
 __device__ __forceinline__ void issue_row_store_any(const TickParams& P, unsigned char* ring, int k, int cx, int cy) {
@@ -903,20 +913,20 @@ __device__ bool row_is_inert(const Ctx& c, int q, int qb, int lane) {
     for (int b = 0; b < 4; b++) {
         const int j = HX8 + 4 * lane + b;
         const uint8_t m = MAT(q, j);
-        const int ph = c.L->phys[m];
+        const int ph = LUTP->phys[m];
         if (ph == P_AIR || ph == P_SOLID) continue;
         if (ph == P_PASSABLE) {
             inert &= (int)m != c.fire;
         } else if (ph == P_SAND) {
-            const float d = c.L->dens[m];
-            const uint8_t mf = c.L->mflags[m];
+            const float d = LUTP->dens[m];
+            const uint8_t mf = LUTP->mflags[m];
             bool ok = !(FLG(q, j) & F_MOVED) && !can_sink(c, qb, j, d) && !can_sink(c, qb, j - 1, d) && !can_sink(c, qb, j + 1, d);
             if (mf & MF_INTERACT) ok = ok && !has_interaction(c, m, MAT(qb, j));
             if (mf & MF_REACT) {
                 if (mf & MF_REACT_MULTI) {
                     ok = false;
                 } else {
-                    const Lut::Rx rx = c.L->rx[m];
+                    const Lut::Rx rx = LUTP->rx[m];
                     const int16_t t = TMP(q, j);
                     ok = ok && !((rx.type == FSE_REACT_TEMPERATURE_BELOW && t < rx.thr) || (rx.type == FSE_REACT_TEMPERATURE_ABOVE && t > rx.thr));
                 }
@@ -934,7 +944,7 @@ __device__ bool row_is_inert(const Ctx& c, int q, int qb, int lane) {
 __device__ __forceinline__ void issue_row_store(const TickParams& P, Smem& S, int k, int cx, int cy) { issue_row_store_any(P, S.ring, k, cx, cy); }
 
 __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constant__ TickParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* const smem_raw = fse_smem;
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -954,7 +964,7 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
     const DevTables* T = P.tabs;
     {
         const uint4* src = reinterpret_cast<const uint4*>(&T->lut);
-        uint4* dst = reinterpret_cast<uint4*>(&S.lut);
+        uint4* dst = reinterpret_cast<uint4*>(&S.h.lut);
         for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
@@ -964,10 +974,6 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
     __syncthreads();
 
     Ctx c;
-    c.ring = S.ring;
-    c.L = &S.lut;
-    c.rowmod = S.rowmod;
-    c.rowchg = S.rowchg;
     c.T = T;
     c.pbuf = P.pbuf;
     c.pcount = P.pcount;
@@ -1005,8 +1011,8 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
             if (ks >= -HALO_WR && ks <= LAST_ROW) {
                 const int q = slot_of_row(ks);
                 if (P.awake && ks >= 0 && ks < CHUNK) io_inert &= row_is_inert(c, q, rs(q, 1), lane);
-                io_modified |= S.rowchg[q] != 0;
-                if (S.rowmod[q]) {
+                io_modified |= S.h.rowchg[q] != 0;
+                if (S.h.rowmod[q]) {
                     uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
                     for (int w = lane; w < P8 / 4; w += 32) fw[w] &= 0x7f7f7f7fU;  // tickVisited never reaches HBM
                     fence_proxy_async();
@@ -1078,7 +1084,8 @@ namespace fse {
 // ---- host launcher ----------------------------------------------------------------------------------
 size_t tick_smem_bytes() { return sizeof(SmemRows); }
 
-cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream) {
+cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched) {
+    *launched = 0;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tick_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
@@ -1095,10 +1102,15 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         tick_pass_kernel<1><<<n_chunks, PassGeom<1>::THREADS, sizeof(SmemPass<1>), stream>>>(P);
         tick_pass_kernel<2><<<n_chunks, PassGeom<2>::THREADS, sizeof(SmemPass<2>), stream>>>(P);
         tick_pass3_kernel<<<n_chunks * (CHUNK / 4), 128, 0, stream>>>(P);
+        *launched = 3;
     } else if (P.schedule == FSE_SCHEDULE_ROWS)
+{
         tick_rows_kernel<<<n_chunks, ROWS_THREADS, sizeof(SmemRows), stream>>>(P);
-    else
+        *launched = 1;
+    } else {
         tick_chunk_kernel<<<n_chunks, 128, sizeof(Smem), stream>>>(P);
+        *launched = 1;
+    }
     return cudaGetLastError();
 }
 

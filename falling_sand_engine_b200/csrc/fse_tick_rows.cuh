@@ -34,7 +34,7 @@ struct Scratch1 {
     uint32_t area_mask[2][4];   // columns of this row with an area effect to apply (bit i = column i)
     uint8_t areaClaim[11][P8];  // serial C3: claimant column + 1 (0 = free); 4-byte aligned (cleared as words)
     uint8_t area_kind[CHUNK];
-    long long dbg_phase[6];     // profiling aid (FSE_ROLE_CYCLES)
+    long long dbg_phase[10];    // profiling aid (FSE_ROLE_CYCLES): cycles of D, C1, C2, area, -, D own; rows seen, active, with gather, with area
 };
 struct Scratch2 {
     int claimDn[2][CHUNK + 2], claimUp[2][CHUNK + 2];
@@ -51,13 +51,10 @@ static_assert(offsetof(Scratch1, areaClaim) % 4 == 0, "areaClaim is cleared with
 static_assert(sizeof(Scratch1) % 4 == 0 && sizeof(Scratch2) % 4 == 0 && sizeof(Scratch3) % 4 == 0, "scratch is cleared with 32-bit stores");
 
 struct __align__(128) SmemRows {
+    SmemHead h;
     unsigned char ring[RING * ROW_BYTES];
-    Lut lut;
     Ctx ctx;  // CTA-uniform context, kept in shared memory so the rule code needs no registers for it
     unsigned long long bar[RING];
-    unsigned char rowmod[32];
-    unsigned char rowchg[32];
-    unsigned char rowvis[32];
     RowScratch rs;
 };
 
@@ -77,7 +74,9 @@ __device__ __forceinline__ int slotk(const Ctx& c, int k) { return (RN & (RN - 1
 #ifdef FSE_ROLE_CYCLES
 #define FSE_P1_CLOCK(name) const long long name = clock64()
 #define FSE_P1_PHASE(slot, since) do { if (t == 0) R.dbg_phase[slot] += clock64() - (since); } while (0)
+#define FSE_P1_COUNT(slot) do { if (t == 0) R.dbg_phase[slot] += 1; } while (0)
 #else
+#define FSE_P1_COUNT(slot) do { } while (0)
 #define FSE_P1_CLOCK(name) do { } while (0)
 #define FSE_P1_PHASE(slot, since) do { } while (0)
 #endif
@@ -118,11 +117,11 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
     const uint8_t f0 = FLG(s, j);
     if (f0 & F_VISITED) return d;
     const uint8_t m = MAT(s, j);
-    if (c.iter >= (int)c.L->iters[m]) {
+    if (c.iter >= (int)LUTP->iters[m]) {
         d.bits = A_MARK;
         return d;
     }
-    const int type = c.L->phys[m];
+    const int type = LUTP->phys[m];
     if (type == P_AIR || type == P_SOLID) return d;
     const uint32_t cb = rng_cell(c.rkey, x, y);
     const int sb = rsn<RN>(s, 1);
@@ -132,8 +131,8 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
     }
     if (type == P_SAND) {  // 1148-1267
         const uint8_t mb = MAT(sb, j);
-        const int bt = c.L->phys[mb];
-        const uint8_t mf = c.L->mflags[m];
+        const int bt = LUTP->phys[mb];
+        const uint8_t mf = LUTP->mflags[m];
         if ((mf & MF_INTERACT) && has_interaction(c, m, mb)) {
             d.bits = A_INTERACT | ((uint32_t)mb << 24);
             return d;
@@ -142,7 +141,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
             const int16_t temp = TMP(s, j);
             int prod = -1;
             if (!(mf & MF_REACT_MULTI)) {
-                const Lut::Rx rx = c.L->rx[m];
+                const Lut::Rx rx = LUTP->rx[m];
                 if ((rx.type == FSE_REACT_TEMPERATURE_BELOW && temp < rx.thr) || (rx.type == FSE_REACT_TEMPERATURE_ABOVE && temp > rx.thr)) prod = rx.prod;
             } else {
                 for (int i = c.T->react_off[m]; i < c.T->react_off[m + 1]; i++) {
@@ -156,8 +155,8 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
                 return d;
             }
         }
-        const float myDens = c.L->dens[m];
-        if (!(bt == P_AIR || (bt != P_SOLID && c.L->dens[mb] < myDens))) return d;
+        const float myDens = LUTP->dens[m];
+        if (!(bt == P_AIR || (bt != P_SOLID && LUTP->dens[mb] < myDens))) return d;
         const bool canL = can_sink(c, sb, j - 1, myDens), canR = can_sink(c, sb, j + 1, myDens);
         if ((canL || canR) && rng_draw(cb, S_SAND_HESITATE) % 20 == 0) return d;
         uint32_t bits;
@@ -182,7 +181,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
             return d;
         }
         const uint8_t mb0 = MAT(sb, j);
-        const int bph = c.L->phys[mb0];
+        const int bph = LUTP->phys[mb0];
         if ((double)fl > 0.005 && bph == P_AIR && PHYS(rsn<RN>(s, 2), j) == P_AIR && PHYS(rsn<RN>(s, 3), j) == P_AIR && PHYS(rsn<RN>(s, 4), j) == P_AIR) {
             d.bits = A_SOUP_PART;
             return d;
@@ -216,7 +215,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
             early = true;
         }
         const uint8_t ml = MAT(s, j - 1), mr = MAT(s, j + 1);
-        const int lph = c.L->phys[ml], rph = c.L->phys[mr];
+        const int lph = LUTP->phys[ml], rph = LUTP->phys[mr];
         if (lph == P_SOUP) bits |= DB_LEFTSOUP;
         if (rph == P_SOUP) bits |= DB_RIGHTSOUP;
         const bool canL = (lph == P_AIR || ml == m) && !airBelow;
@@ -249,7 +248,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
         }
         const int st = rsn<RN>(s, -1);
         const uint8_t mt = MAT(st, j);
-        const int tph = c.L->phys[mt];
+        const int tph = LUTP->phys[mt];
         if (tph == P_SOUP) bits |= DB_TOPSOUP;
         bool swapUp = false;
         if (!early) {
@@ -305,7 +304,7 @@ __device__ void commit1(const Ctx& c, Scratch1& R, const Dec1& d, int s, int j, 
     switch (act) {
         case A_MARK:
             FLG(s, j) = FLG(s, j) | F_VISITED;
-            c.rowvis[s] = 1;
+            ROWVIS[s] = 1;
             break;
         case A_REACT: {
             const int16_t t = TMP(s, j);
@@ -334,8 +333,8 @@ __device__ void commit1(const Ctx& c, Scratch1& R, const Dec1& d, int s, int j, 
         }
         case A_SOUP_ZERO:
             FL(s, j) = 0.0f;
-            c.rowmod[s] = 1;
-            c.rowchg[s] = 1;
+            ROWMOD[s] = 1;
+            ROWCHG[s] = 1;
             break;
         case A_SOUP_PART: {
             const CellR tile = ldc(c, s, j);
@@ -430,7 +429,7 @@ __device__ __forceinline__ void gather1(const Ctx& c, Scratch1& R, int s, int k)
     const float inL = (hl & 2) ? R.outR[k - 1] : 0.0f, inR = (hr & 1) ? R.outL[k + 1] : 0.0f;
     if (inL != 0 || inR != 0) {
         const uint8_t m = MAT(s, j);
-        const int ph = c.L->phys[m];
+        const int ph = LUTP->phys[m];
         if (ph == P_AIR) {
             if (inL != 0) {
                 CellR n = fresh_fluid(ldc(c, s, j - 1));
@@ -449,8 +448,8 @@ __device__ __forceinline__ void gather1(const Ctx& c, Scratch1& R, int s, int k)
             if (inL != 0) {
                 if (ph == P_SOUP && MAT(s, j - 1) == m) {
                     FD(s, j) = FD(s, j) + inL;
-                    c.rowmod[s] = 1;
-                    c.rowchg[s] = 1;
+                    ROWMOD[s] = 1;
+                    ROWCHG[s] = 1;
                 } else {
                     R.refR[k - 1] = inL;
                 }
@@ -458,8 +457,8 @@ __device__ __forceinline__ void gather1(const Ctx& c, Scratch1& R, int s, int k)
             if (inR != 0) {
                 if (ph == P_SOUP && MAT(s, j + 1) == m) {
                     FD(s, j) = FD(s, j) + inR;
-                    c.rowmod[s] = 1;
-                    c.rowchg[s] = 1;
+                    ROWMOD[s] = 1;
+                    ROWCHG[s] = 1;
                 } else {
                     R.refL[k + 1] = inR;
                 }
@@ -579,7 +578,7 @@ __device__ void pass1_rows(const Ctx& c, Scratch1& R, int k, int cx, int cy, int
     int a = d.bits & 15;
     if (a == A_MARK) {  // iterations exhausted (1095): only the cell's own visited bit, which no decision of this step reads
         FLG(s, j) = FLG(s, j) | F_VISITED;
-        c.rowvis[s] = 1;
+        ROWVIS[s] = 1;
         d.bits = a = A_NONE;
     }
     if (a) R.p1_any[par] = 1;
@@ -587,17 +586,18 @@ __device__ void pass1_rows(const Ctx& c, Scratch1& R, int k, int cx, int cy, int
         atomicOr(&R.area_mask[par][t >> 5], 1u << (t & 31));
         R.p1_area[par] = 1;
     }
+    FSE_P1_PHASE(5, T0);  // own decide time of warp 0
     pass_bar(1);
-    if (!R.p1_any[par]) {
-        FSE_P1_PHASE(0, T0);
-        return;
-    }
     FSE_P1_CLOCK(T1);
-    FSE_P1_PHASE(0, T0);
+    FSE_P1_PHASE(0, T0);  // decide incl. waiting for the slowest warp
+    FSE_P1_COUNT(6);
+    if (!R.p1_any[par]) return;
+    FSE_P1_COUNT(7);
     commit1<RN>(c, R, d, s, j, cx + t, y, par);
     pass_bar(1);
     FSE_P1_CLOCK(T2);
     FSE_P1_PHASE(1, T1);
+    if (R.p1_horiz[par]) FSE_P1_COUNT(8);
     if (R.p1_horiz[par]) {  // somebody published a horizontal flow, an un-settle flag or a poke
         gather1<RN>(c, R, s, 1 + t);
         if (t == 0) gather1<RN>(c, R, s, 0);
@@ -608,14 +608,17 @@ __device__ void pass1_rows(const Ctx& c, Scratch1& R, int k, int cx, int cy, int
         const float rl = R.refL[kk], rr = R.refR[kk];
         if (rl != 0) { FD(s, j) = FD(s, j) + rl; R.refL[kk] = 0.0f; }
         if (rr != 0) { FD(s, j) = FD(s, j) + rr; R.refR[kk] = 0.0f; }
-        if (rl != 0 || rr != 0) { c.rowmod[s] = 1; c.rowchg[s] = 1; }
+        if (rl != 0 || rr != 0) { ROWMOD[s] = 1; ROWCHG[s] = 1; }
     }
     FSE_P1_PHASE(2, T2);
     if (R.p1_area[par]) {
         uint32_t* cl = reinterpret_cast<uint32_t*>(&R.areaClaim[0][0]);
         for (int q = t; q < 11 * P8 / 4; q += CHUNK) cl[q] = 0;
         pass_bar(1);
+        FSE_P1_CLOCK(T3);
+        FSE_P1_COUNT(9);
         if (t == 0) area_effects<RN>(c, R, s, cx, y, par);
+        FSE_P1_PHASE(3, T3);
     }
 }
 
@@ -626,15 +629,15 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
     const uint8_t f0 = FLG(s, j);
     if (f0 & F_VISITED) return 0;
     const uint8_t m = MAT(s, j);
-    const int type = c.L->phys[m];
+    const int type = LUTP->phys[m];
     if (type == P_SAND) {
         const int sb = rsn<RN>(s, 1);
-        const float myDens = c.L->dens[m];
+        const float myDens = LUTP->dens[m];
         const bool canL = can_sink(c, sb, j - 1, myDens), canR = can_sink(c, sb, j + 1, myDens);
         if (!(canL || canR)) return 1;
         const uint32_t cb = rng_cell(c.rkey, x, y);
         bool stopped = !(f0 & F_MOVED);
-        const int slip = c.L->slip[m];
+        const int slip = LUTP->slip[m];
         if (stopped) {
             int drop = 0;
 #pragma unroll 1
@@ -642,7 +645,7 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
                 const int sp = rsn<RN>(s, 1 + pil);
                 if (PHYS(sp, j - 1) == P_AIR || PHYS(sp, j + 1) == P_AIR) drop++;
             }
-            const int dd = drop + 1 - (int)c.L->maxstab[m];
+            const int dd = drop + 1 - (int)LUTP->maxstab[m];
             if (dd > 0) {
                 const int chance = 1000 / dd;
                 if (chance < 1000 && rng_draw(cb, S_SAND2_UNSTICK) % chance == 0) stopped = false;
@@ -703,8 +706,8 @@ __device__ void commit2(const Ctx& c, Scratch2& R, uint32_t d, int s, int j, int
             FL(s, j) = a;
             FD(s, j) = 0.0f;
             FLG(s, j) = FLG(s, j) | F_DIRTY | F_VISITED;
-            c.rowmod[s] = 1;
-            if (fd != 0.0f) c.rowchg[s] = 1;
+            ROWMOD[s] = 1;
+            if (fd != 0.0f) ROWCHG[s] = 1;
         }
     } else if (act == 4) {
         if (R.claimUp[par][i + 1 + dir] == i) {
@@ -751,7 +754,7 @@ __device__ void pass2_rows(const Ctx& c, Scratch2& R, int k, int cx, int cy, int
 __device__ int decide3(const Ctx& c, int s, int j, int x, int y) {  // 0 none, -1 / +1 move, 2 steam condenses
     if (FLG(s, j) & F_VISITED) return 0;
     const uint8_t m = MAT(s, j);
-    if (c.L->phys[m] != P_GAS) return 0;
+    if (LUTP->phys[m] != P_GAS) return 0;
     const int l = PHYS(s, j - 1), r = PHYS(s, j + 1);
     const uint32_t cb = rng_cell(c.rkey, x, y);
     if (l == P_AIR && !(r == P_AIR && rng_draw(cb, S_GAS3) % 2 == 0)) return -1;
@@ -802,7 +805,7 @@ __device__ void pass3_rows(const Ctx& c, Scratch3& R, int k, int cx, int cy, int
 }
 
 __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid_constant__ TickParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* const smem_raw = fse_smem;
     SmemRows& S = *reinterpret_cast<SmemRows*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int role = warp < 4 ? 0 : (warp < 8 ? 1 : (warp == 8 ? 2 : 3));  // pass 1, pass 2, pass 3, IO
@@ -824,7 +827,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
     const DevTables* T = P.tabs;
     {
         const uint4* src = reinterpret_cast<const uint4*>(&T->lut);
-        uint4* dst = reinterpret_cast<uint4*>(&S.lut);
+        uint4* dst = reinterpret_cast<uint4*>(&S.h.lut);
         for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
         uint32_t* z = reinterpret_cast<uint32_t*>(&S.rs);
         for (int i = tid; i < (int)(sizeof(RowScratch) / 4); i += blockDim.x) z[i] = 0;
@@ -845,10 +848,6 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
 
     Ctx& c = S.ctx;
     if (tid == 0) {
-        c.ring = S.ring;
-        c.L = &S.lut;
-        c.rowmod = S.rowmod;
-        c.rowchg = S.rowchg;
         c.T = T;
         c.pbuf = P.pbuf;
         c.pcount = P.pcount;
@@ -861,14 +860,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
         c.ringn = RING;
         c.ringmask = 0;
         c.koff = HALO_DN;
-        c.rowvis = S.rowvis;
         c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
     }
     __syncthreads();
 
     const bool io = warp == 9;
     if (io && lane == 0) {
-        for (int k = -HALO_DN; k < HALO_UP + PF; k++) issue_row_load_any(P, S.ring, S.bar, S.rowmod, S.rowchg, k, cx, cy);
+        for (int k = -HALO_DN; k < HALO_UP + PF; k++) issue_row_load_any(P, S.ring, S.bar, S.h.rowmod, S.h.rowchg, k, cx, cy);
     }
     for (int k = -HALO_DN; k < HALO_UP; k++) mbar_wait(&S.bar[slotk<RING>(c, k)], 0);
 
@@ -897,8 +895,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
             if (ks >= -HALO_WR && ks <= LAST_ROW) {
                 const int q = slotk<RING>(c, ks);
                 if (P.awake && ks >= 0 && ks < CHUNK) io_inert &= row_is_inert(c, q, rsn<RING>(q, 1), lane);
-                io_modified |= S.rowchg[q] != 0;
-                if (S.rowmod[q]) {
+                io_modified |= S.h.rowchg[q] != 0;
+                if (S.h.rowmod[q]) {
                     uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
                     for (int w = lane; w < P8 / 4; w += 32) fw[w] &= 0x7f7f7f7fU;
                     fence_proxy_async();
@@ -910,7 +908,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
             const int kl = st + HALO_UP + PF;
             if (kl <= LAST_ROW && lane == 0) {
                 bulk_wait_read<1>();
-                issue_row_load_any(P, S.ring, S.bar, S.rowmod, S.rowchg, kl, cx, cy);
+                issue_row_load_any(P, S.ring, S.bar, S.h.rowmod, S.h.rowchg, kl, cx, cy);
             }
         }
         if (P.dbg) {
@@ -952,6 +950,18 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
 //   pass 1, pass 2: one CTA per chunk (4 compute warps + 1 IO warp), rows bottom-up through a shared-memory window
 //   pass 3: its rows do not depend on each other (a gas cell only looks at and moves within its own row), so it runs one
 //           warp per row straight on global memory
+#ifndef FSE_P1_RN
+#define FSE_P1_RN 13
+#endif
+#ifndef FSE_P2_RN
+#define FSE_P2_RN 14
+#endif
+#ifndef FSE_PASS_PF
+#define FSE_PASS_PF 2
+#endif
+#ifndef FSE_PASS_MINB
+#define FSE_PASS_MINB 5
+#endif
 template <int PASS>
 struct PassGeom {
     static constexpr int KMIN = PASS == 1 ? -5 : -10;     // lowest row (below the chunk) that is read
@@ -959,13 +969,13 @@ struct PassGeom {
     static constexpr int UP = PASS == 1 ? 5 : 1;          // rows above the current one that are touched
     static constexpr int LAST = CHUNK - 1 + UP;
     static constexpr int SL = UP + 1;                     // a row is final SL steps after its own step
-    static constexpr int RN = PASS == 1 ? 13 : 14;        // rows in the window: live rows + one row in flight each way
-    static constexpr int PF = 2;                          // rows loaded ahead of the step that needs them
+    static constexpr int RN = PASS == 1 ? FSE_P1_RN : FSE_P2_RN;  // rows in the window: live rows + rows in flight
+    static constexpr int PF = FSE_PASS_PF;                // rows loaded ahead of the step that needs them
     static constexpr int THREADS = 160;
 };
 // pass 1: live rows st-5..st+5; the row loaded at step st (st+7) takes the slot of row st-6, whose store is issued in the same step
 // pass 2: live rows st-10..st+1; the row loaded at step st (st+3) takes the slot of row st-11
-static_assert(PassGeom<1>::UP + PassGeom<1>::PF - PassGeom<1>::RN == -PassGeom<1>::SL, "pass 1 window");
+static_assert(PassGeom<1>::UP + PassGeom<1>::PF - PassGeom<1>::RN <= -PassGeom<1>::SL, "pass 1 window");
 static_assert(PassGeom<2>::UP + PassGeom<2>::PF - PassGeom<2>::RN < PassGeom<2>::KMIN, "pass 2 window");
 
 template <int PASS> struct PassScratch { typedef Scratch1 type; };
@@ -973,13 +983,10 @@ template <> struct PassScratch<2> { typedef Scratch2 type; };
 
 template <int PASS>
 struct __align__(128) SmemPass {
+    SmemHead h;
     unsigned char ring[PassGeom<PASS>::RN * ROW_BYTES];
-    Lut lut;
     Ctx ctx;
     unsigned long long bar[PassGeom<PASS>::RN];
-    unsigned char rowmod[32];
-    unsigned char rowchg[32];
-    unsigned char rowvis[32];
     typename PassScratch<PASS>::type rs;
 };
 
@@ -992,9 +999,9 @@ __device__ __forceinline__ void pass_row_load(const TickParams& P, SmemPass<PASS
     unsigned long long* bar = &S.bar[q];
     const size_t o8 = y * P.W + (cx - HX8);
     const size_t ow = y * P.W + (cx - HXW);
-    S.rowmod[q] = 0;
-    S.rowchg[q] = 0;
-    S.rowvis[q] = 0;
+    S.h.rowmod[q] = 0;
+    S.h.rowchg[q] = 0;
+    S.h.rowvis[q] = 0;
     if (k < G::FULL_LO) {
         mbar_expect_tx(bar, P8);
         bulk_g2s(row + OFF_MAT, P.p.mat + o8, P8, bar);
@@ -1011,9 +1018,9 @@ __device__ __forceinline__ void pass_row_load(const TickParams& P, SmemPass<PASS
 }
 
 template <int PASS>
-__global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 5) tick_pass_kernel(const __grid_constant__ TickParams P) {
+__global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_pass_kernel(const __grid_constant__ TickParams P) {
     using G = PassGeom<PASS>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* const smem_raw = fse_smem;
     SmemPass<PASS>& S = *reinterpret_cast<SmemPass<PASS>*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool io = warp == G::THREADS / 32 - 1;
@@ -1034,7 +1041,7 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 5) tick_pass_kernel(c
     const DevTables* T = P.tabs;
     {
         const uint4* src = reinterpret_cast<const uint4*>(&T->lut);
-        uint4* dst = reinterpret_cast<uint4*>(&S.lut);
+        uint4* dst = reinterpret_cast<uint4*>(&S.h.lut);
         for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
         uint32_t* z = reinterpret_cast<uint32_t*>(&S.rs);
         for (int i = tid; i < (int)(sizeof(S.rs) / 4); i += blockDim.x) z[i] = 0;
@@ -1049,11 +1056,6 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 5) tick_pass_kernel(c
     if (tid == 0) {
         for (int q = 0; q < G::RN; q++) mbar_init(&S.bar[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        c.ring = S.ring;
-        c.L = &S.lut;
-        c.rowmod = S.rowmod;
-        c.rowchg = S.rowchg;
-        c.rowvis = S.rowvis;
         c.T = T;
         c.pbuf = P.pbuf;
         c.pcount = P.pcount;
@@ -1072,6 +1074,7 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 5) tick_pass_kernel(c
 
     // row k lives in slot (k - KMIN) % RN and is the ((k - KMIN) / RN)-th user of that slot's mbarrier
     if (io && lane == 0) {
+#pragma unroll 1
         for (int k = G::KMIN; k < G::UP + G::PF; k++) pass_row_load<PASS>(P, S, k, cx, cy);
     }
     for (int k = G::KMIN; k < G::UP; k++) mbar_wait(&S.bar[(k - G::KMIN) % G::RN], (uint32_t)(((k - G::KMIN) / G::RN) & 1));
@@ -1098,8 +1101,8 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 5) tick_pass_kernel(c
                     const bool keep = core_row && w >= HX8 / 4 && w < (HX8 + CHUNK) / 4;
                     if (!keep) fw[w] &= 0x7f7f7f7fU;
                 }
-                const bool all_store = S.rowmod[q] != 0;
-                const bool vis_store = S.rowvis[q] != 0;
+                const bool all_store = S.h.rowmod[q] != 0;
+                const bool vis_store = S.h.rowvis[q] != 0;
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && (all_store || vis_store)) {
@@ -1121,11 +1124,19 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, 5) tick_pass_kernel(c
             }
             const int kl = st + G::UP + G::PF;
             if (kl <= G::LAST && lane == 0) {
-                bulk_wait_read<0>();  // the slot may be the one whose store was just issued (pass 1)
+                // the slot to fill may be the one whose store was issued a moment ago (pass 1 with the tightest window)
+                if (G::UP + G::PF - G::RN == -G::SL) bulk_wait_read<0>();
+                else bulk_wait_read<1>();
                 pass_row_load<PASS>(P, S, kl, cx, cy);
             }
         }
     }
+#ifdef FSE_ROLE_CYCLES
+    if (PASS == 1 && P.dbg && tid == 0) {
+        atomicAdd(&P.dbg[0], 1ULL);
+        for (int q = 0; q < 10; q++) atomicAdd(&P.dbg[1 + q], (unsigned long long)reinterpret_cast<Scratch1&>(S.rs).dbg_phase[q]);
+    }
+#endif
     if (io && lane == 0) bulk_wait_all();
 }
 
