@@ -640,7 +640,7 @@ __device__ uint32_t decide2(const Ctx& c, int s, int j, int x, int y) {
         const int slip = LUTP->slip[m];
         if (stopped) {
             int drop = 0;
-#pragma unroll 1
+#pragma unroll
             for (int pil = 0; pil < 10; pil++) {
                 const int sp = rsn<RN>(s, 1 + pil);
                 if (PHYS(sp, j - 1) == P_AIR || PHYS(sp, j + 1) == P_AIR) drop++;
@@ -990,31 +990,43 @@ struct __align__(128) SmemPass {
     typename PassScratch<PASS>::type rs;
 };
 
+// The IO warp moves a row with one bulk copy per plane; lane p < 7 owns plane p (mat, flg, stl, tmp, col, fl, fd), so the
+// seven copies of a row are issued side by side instead of one after the other by a single thread.
+struct PlaneIO {
+    unsigned char* g;     // plane base + first column of the chunk's window, in bytes
+    size_t row_stride;    // bytes per world row
+    uint32_t soff;        // offset of the plane inside a shared-memory row
+    uint32_t bytes;       // bytes per window row
+};
+__device__ __forceinline__ PlaneIO plane_io(const TickParams& P, int lane, int cx) {
+    PlaneIO io;
+    const int es = lane < 3 ? 1 : (lane == 3 ? 2 : 4);
+    unsigned char* base = lane == 0 ? (unsigned char*)P.p.mat : lane == 1 ? (unsigned char*)P.p.flg : lane == 2 ? (unsigned char*)P.p.stl
+                        : lane == 3 ? (unsigned char*)P.p.tmp : lane == 4 ? (unsigned char*)P.p.col : lane == 5 ? (unsigned char*)P.p.fl
+                                                                                                               : (unsigned char*)P.p.fd;
+    io.g = base + (size_t)(cx - (lane < 3 ? HX8 : HXW)) * es;
+    io.row_stride = (size_t)P.W * es;
+    io.soff = lane == 0 ? OFF_MAT : lane == 1 ? OFF_FLG : lane == 2 ? OFF_STL : lane == 3 ? OFF_TMP : lane == 4 ? OFF_COL : lane == 5 ? OFF_FL : OFF_FD;
+    io.bytes = (lane < 3 ? P8 : PW) * es;
+    return io;
+}
+
+// whole IO warp: load row k of the chunk into its slot (rows below FULL_LO: material plane only)
 template <int PASS>
-__device__ __forceinline__ void pass_row_load(const TickParams& P, SmemPass<PASS>& S, int k, int cx, int cy) {
+__device__ __forceinline__ void pass_row_load(SmemPass<PASS>& S, const PlaneIO& io, int lane, int k, int cy) {
     using G = PassGeom<PASS>;
     const int q = (k - G::KMIN) % G::RN;
-    const size_t y = (size_t)(cy + CHUNK - 1 - k);
-    unsigned char* row = S.ring + q * ROW_BYTES;
     unsigned long long* bar = &S.bar[q];
-    const size_t o8 = y * P.W + (cx - HX8);
-    const size_t ow = y * P.W + (cx - HXW);
-    S.h.rowmod[q] = 0;
-    S.h.rowchg[q] = 0;
-    S.h.rowvis[q] = 0;
-    if (k < G::FULL_LO) {
-        mbar_expect_tx(bar, P8);
-        bulk_g2s(row + OFF_MAT, P.p.mat + o8, P8, bar);
-        return;
+    const bool mat_only = k < G::FULL_LO;
+    if (lane == 0) {
+        S.h.rowmod[q] = 0;
+        S.h.rowchg[q] = 0;
+        S.h.rowvis[q] = 0;
+        mbar_expect_tx(bar, mat_only ? P8 : ROW_BYTES);
     }
-    mbar_expect_tx(bar, ROW_BYTES);
-    bulk_g2s(row + OFF_MAT, P.p.mat + o8, P8, bar);
-    bulk_g2s(row + OFF_FLG, P.p.flg + o8, P8, bar);
-    bulk_g2s(row + OFF_STL, P.p.stl + o8, P8, bar);
-    bulk_g2s(row + OFF_TMP, P.p.tmp + ow, PW * 2, bar);
-    bulk_g2s(row + OFF_COL, P.p.col + ow, PW * 4, bar);
-    bulk_g2s(row + OFF_FL, P.p.fl + ow, PW * 4, bar);
-    bulk_g2s(row + OFF_FD, P.p.fd + ow, PW * 4, bar);
+    __syncwarp();
+    if (lane < (mat_only ? 1 : 7))
+        bulk_g2s(S.ring + q * ROW_BYTES + io.soff, io.g + (size_t)(cy + CHUNK - 1 - k) * io.row_stride, io.bytes, bar);
 }
 
 template <int PASS>
@@ -1073,9 +1085,10 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
     __syncthreads();
 
     // row k lives in slot (k - KMIN) % RN and is the ((k - KMIN) / RN)-th user of that slot's mbarrier
-    if (io && lane == 0) {
+    const PlaneIO pio = plane_io(P, lane < 7 ? lane : 0, cx);
+    if (io) {
 #pragma unroll 1
-        for (int k = G::KMIN; k < G::UP + G::PF; k++) pass_row_load<PASS>(P, S, k, cx, cy);
+        for (int k = G::KMIN; k < G::UP + G::PF; k++) pass_row_load<PASS>(S, pio, lane, k, cy);
     }
     for (int k = G::KMIN; k < G::UP; k++) mbar_wait(&S.bar[(k - G::KMIN) % G::RN], (uint32_t)(((k - G::KMIN) / G::RN) & 1));
 
@@ -1105,29 +1118,17 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
                 const bool vis_store = S.h.rowvis[q] != 0;
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0 && (all_store || vis_store)) {
-                    const size_t y = (size_t)(cy + CHUNK - 1 - ks);
-                    unsigned char* row = S.ring + q * ROW_BYTES;
-                    const size_t o8 = y * P.W + (cx - HX8);
-                    const size_t ow = y * P.W + (cx - HXW);
-                    bulk_s2g(P.p.flg + o8, row + OFF_FLG, P8);
-                    if (all_store) {
-                        bulk_s2g(P.p.mat + o8, row + OFF_MAT, P8);
-                        bulk_s2g(P.p.stl + o8, row + OFF_STL, P8);
-                        bulk_s2g(P.p.tmp + ow, row + OFF_TMP, PW * 2);
-                        bulk_s2g(P.p.col + ow, row + OFF_COL, PW * 4);
-                        bulk_s2g(P.p.fl + ow, row + OFF_FL, PW * 4);
-                        bulk_s2g(P.p.fd + ow, row + OFF_FD, PW * 4);
-                    }
+                if (all_store ? lane < 7 : (vis_store && lane == 1)) {
+                    bulk_s2g(pio.g + (size_t)(cy + CHUNK - 1 - ks) * pio.row_stride, S.ring + q * ROW_BYTES + pio.soff, pio.bytes);
                     bulk_commit();
                 }
             }
             const int kl = st + G::UP + G::PF;
-            if (kl <= G::LAST && lane == 0) {
-                // the slot to fill may be the one whose store was issued a moment ago (pass 1 with the tightest window)
-                if (G::UP + G::PF - G::RN == -G::SL) bulk_wait_read<0>();
-                else bulk_wait_read<1>();
-                pass_row_load<PASS>(P, S, kl, cx, cy);
+            if (kl <= G::LAST) {
+                // each lane waits until its own stores have left shared memory: the slot to fill may be the one whose store was
+                // issued a moment ago (pass 1 with the tightest window), and bulk groups are per thread
+                bulk_wait_read<0>();
+                pass_row_load<PASS>(S, pio, lane, kl, cy);
             }
         }
     }
@@ -1137,7 +1138,7 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
         for (int q = 0; q < 10; q++) atomicAdd(&P.dbg[1 + q], (unsigned long long)reinterpret_cast<Scratch1&>(S.rs).dbg_phase[q]);
     }
 #endif
-    if (io && lane == 0) bulk_wait_all();
+    if (io) bulk_wait_all();
 }
 
 // ---- pass 3 on global memory: one warp per chunk row, lane l owns columns 4l..4l+3 (world.cpp:1828-1891) ---------------------
