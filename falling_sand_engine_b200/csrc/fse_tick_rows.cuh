@@ -472,20 +472,31 @@ __device__ __forceinline__ void gather1(const Ctx& c, Scratch1& R, int s, int k)
     }
 }
 
-// C3 (serial, one thread): area effects in ascending source column; the first claimant of a cell wins it
+// C3: area effects (FIRE burn-out / ignition, water on lava, pair interactions).  Every source column first claims the cells
+// it wants to rewrite — a contested cell goes to the lowest source column, as if the sources ran one after the other in
+// ascending x — then (after a barrier) rewrites the cells it owns.  pass = 0: claim, pass = 1: apply.
+__device__ __forceinline__ void area_claim_min(Scratch1& R, int tj, int dy, int i) {  // dy in -5..5 rows below(+)/above(-)
+    uint8_t* cell = &R.areaClaim[dy + 5][tj];
+    uint32_t* w = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(cell) & ~(uintptr_t)3);
+    const int sh = (int)(reinterpret_cast<uintptr_t>(cell) & 3) * 8;
+    const uint32_t v = (uint32_t)(i + 1);
+    uint32_t old = *w;
+    while (true) {
+        const uint32_t b = (old >> sh) & 0xffu;
+        if (b != 0 && b <= v) return;
+        const uint32_t prev = atomicCAS(w, old, (old & ~(0xffu << sh)) | (v << sh));
+        if (prev == old) return;
+        old = prev;
+    }
+}
 template <int RN>
-__device__ __noinline__ void area_effects(const Ctx& c, Scratch1& R, int s, int cx, int y, int par) {
-    auto claim = [&](int i, int tj, int dy) {  // dy in -5..5 rows below(+)/above(-)
-        uint8_t& e = R.areaClaim[dy + 5][tj];
-        if (e == 0) e = (uint8_t)(i + 1);
-    };
-    auto mine = [&](int i, int tj, int dy) { return R.areaClaim[dy + 5][tj] == (uint8_t)(i + 1); };
-    for (int pass = 0; pass < 2; pass++)
-        for (int wd = 0; wd < 4; wd++)
-            for (uint32_t mk = R.area_mask[par][wd]; mk; mk &= mk - 1) {
-            const int i = wd * 32 + __ffs(mk) - 1;
+__device__ __noinline__ void area_effects(const Ctx& c, Scratch1& R, int s, int cx, int y, int i, int pass) {
+    auto claim = [&](int i_, int tj, int dy) { area_claim_min(R, tj, dy, i_); };
+    auto mine = [&](int i_, int tj, int dy) { return R.areaClaim[dy + 5][tj] == (uint8_t)(i_ + 1); };
+    {
+        {
             const int kind = R.area_kind[i];
-            if (!kind) continue;
+            if (!kind) return;
             const int j = HX8 + i, x = cx + i;
             const uint32_t arg = R.area_arg[i];
             if (kind == 1) {  // FIRE: burn out / ignite (1121-1144)
@@ -521,7 +532,7 @@ __device__ __noinline__ void area_effects(const Ctx& c, Scratch1& R, int s, int 
                     R.area_arg[i] = (uint32_t)mb | ((uint32_t)msrc << 8);
                     claim(i, j, 0);
                 } else {
-                    if (!mine(i, j, 0)) continue;  // a lower-column effect rewrote the source: its list is void
+                    if (!mine(i, j, 0)) return;  // a lower-column effect rewrote the source: its list is void
                     mb = (int)(arg & 0xff);
                     msrc = (int)((arg >> 8) & 0xff);
                 }
@@ -543,6 +554,7 @@ __device__ __noinline__ void area_effects(const Ctx& c, Scratch1& R, int s, int 
                 }
             }
         }
+    }
 }
 
 template <int RN>
@@ -617,7 +629,10 @@ __device__ void pass1_rows(const Ctx& c, Scratch1& R, int k, int cx, int cy, int
         pass_bar(1);
         FSE_P1_CLOCK(T3);
         FSE_P1_COUNT(9);
-        if (t == 0) area_effects<RN>(c, R, s, cx, y, par);
+        const bool src = (R.area_mask[par][t >> 5] >> (t & 31)) & 1;
+        if (src) area_effects<RN>(c, R, s, cx, y, t, 0);
+        pass_bar(1);
+        if (src) area_effects<RN>(c, R, s, cx, y, t, 1);
         FSE_P1_PHASE(3, T3);
     }
 }
