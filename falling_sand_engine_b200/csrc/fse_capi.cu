@@ -5,7 +5,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -196,6 +198,11 @@ static void free_world(fse_world* w) {
     for (auto& ev : w->kt_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);
+    for (int q = 0; q < 3; q++) {
+        if (w->fork.aux[q]) cudaStreamDestroy(w->fork.aux[q]);
+        if (w->fork.ev_join[q]) cudaEventDestroy(w->fork.ev_join[q]);
+    }
+    if (w->fork.ev_fork) cudaEventDestroy(w->fork.ev_fork);
     if (w->stream) cudaStreamDestroy(w->stream);
     if (w->comm_stream) cudaStreamDestroy(w->comm_stream);
     if (w->ev_boundary) cudaEventDestroy(w->ev_boundary);
@@ -227,6 +234,13 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     A((void**)&w->d_stats, dev_stats_bytes());
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_stats, dev_stats_bytes());
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+    w->fork.parts = 3;
+    if (const char* env = getenv("FSE_TICK_PARTS")) w->fork.parts = std::min(4, std::max(1, atoi(env)));
+    for (int q = 0; q < 3; q++) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->fork.aux[q], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->fork.ev_join[q], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->fork.ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
     if (e == cudaSuccess) e = cudaMemsetAsync(w->pcount, 0, 64, w->stream);
@@ -582,6 +596,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.schedule = w->schedule;
             P.dbg = w->d_dbg;
             P.fused = w->fused;
+            P.chunk_base = 0;
             if (!w->strip) {
                 const int n_chunks = P.ncx * P.ncy;
                 if (n_chunks <= 0) continue;
@@ -595,7 +610,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                 }
                 if (int r = kt.begin(w->stream)) return r;
                 int nl = 0;
-                CK(launch_tick_phase(P, n_chunks, w->stream, &nl));
+                CK(launch_tick_phase(P, n_chunks, w->stream, &nl, &w->fork));
                 if (int r = kt.end(w->stream)) return r;
                 w->ctx->launches += nl;
                 continue;
@@ -608,7 +623,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             if (w->list_cnt[tk][0] > 0) {
                 P.chunk_list = w->d_chunk_lists + w->list_off[tk][0];
                 int nl = 0;
-                CK(launch_tick_phase(P, w->list_cnt[tk][0], w->stream, &nl));
+                CK(launch_tick_phase(P, w->list_cnt[tk][0], w->stream, &nl, nullptr));
                 w->ctx->launches += nl;
             }
             if (multi) {
@@ -620,7 +635,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             if (w->list_cnt[tk][1] > 0) {
                 P.chunk_list = w->d_chunk_lists + w->list_off[tk][1];
                 int nl = 0;
-                CK(launch_tick_phase(P, w->list_cnt[tk][1], w->stream, &nl));
+                CK(launch_tick_phase(P, w->list_cnt[tk][1], w->stream, &nl, &w->fork));
                 w->ctx->launches += nl;
             }
             if (int r = kt.end(w->stream)) return r;

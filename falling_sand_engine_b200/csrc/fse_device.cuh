@@ -124,8 +124,16 @@ struct TickParams {
     int acols, arows;
     int never_sleep;        // strip worlds keep their cut-adjacent chunk rows awake
     unsigned long long* dbg; // optional role-cycle counters (profiling aid), null otherwise
+    int chunk_base;         // first chunk (index into the phase's chunk grid or list) of this launch
     int fused;              // rows schedule: 1 = single fused kernel (all passes pipelined), 0 = one kernel per pass
     int schedule;           // FSE_SCHEDULE_CLASSES (4 interleaved column classes) or FSE_SCHEDULE_ROWS (simultaneous rows)
+};
+
+// extra streams + events for running the parts of a colour phase side by side (nullptr: single stream)
+struct TickFork {
+    int parts;  // 1..4 parts of a phase run side by side; part 0 on the caller's stream
+    cudaStream_t aux[3];
+    cudaEvent_t ev_fork, ev_join[3];
 };
 
 }  // namespace fse

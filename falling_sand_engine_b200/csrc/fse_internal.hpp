@@ -38,6 +38,7 @@ struct fse_world {
     fse::Planes p{};
     int16_t* tmp_scratch = nullptr;
     cudaStream_t stream = nullptr;
+    fse::TickFork fork{};
     // loose particles (world::cells)
     fse_particle* pbuf = nullptr;
     unsigned int* pcount = nullptr;  // [0] live count, [1..] scratch counters
@@ -91,7 +92,7 @@ int fail(int code, const char* fmt, ...);
 int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cudaStream_t s);
 int strip_refresh(fse_world* w, cudaStream_t s);
 size_t tick_smem_bytes();
-cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched);  // *launched = kernels enqueued
+cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched, const TickFork* fork);  // *launched = kernels enqueued
 cudaError_t launch_compact_active(const uint8_t* awake, int acols, int ci0, int cj0, int ncx, int ncy, int* list, int* count, cudaStream_t s);
 
 cudaError_t launch_write_rect(Planes p, int W, int x0, int y0, int rw, int rh, const fse_cell* src, cudaStream_t s);

@@ -1084,7 +1084,7 @@ namespace fse {
 // ---- host launcher ----------------------------------------------------------------------------------
 size_t tick_smem_bytes() { return sizeof(SmemRows); }
 
-cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched) {
+cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched, const TickFork* fork) {
     *launched = 0;
     static bool configured = false;
     if (!configured) {
@@ -1099,10 +1099,28 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
     }
     if (n_chunks <= 0) return cudaSuccess;
     if (P.schedule == FSE_SCHEDULE_ROWS && !P.awake && !P.fused) {  // one kernel per pass
-        tick_pass_kernel<1><<<n_chunks, PassGeom<1>::THREADS, sizeof(SmemPass<1>), stream>>>(P);
-        tick_pass_kernel<2><<<n_chunks, PassGeom<2>::THREADS, sizeof(SmemPass<2>), stream>>>(P);
-        tick_pass3_kernel<<<n_chunks * (CHUNK / 4), 128, 0, stream>>>(P);
-        *launched = 3;
+        // The three passes of a chunk only depend on each other, so the phase is cut into parts that run on their own streams:
+        // while the last pass-1 CTAs of one part drain, another part's pass 2 already fills the SMs (the kernels are latency
+        // bound and a phase is only ~1.3 waves of CTAs).
+        const int parts = (fork && n_chunks >= 256) ? fork->parts : 1;
+        TickParams Q = P;
+        if (parts > 1) {
+            cudaEventRecord(fork->ev_fork, stream);
+            for (int q = 1; q < parts; q++) cudaStreamWaitEvent(fork->aux[q - 1], fork->ev_fork, 0);
+        }
+        for (int q = 0; q < parts; q++) {
+            cudaStream_t st = q ? fork->aux[q - 1] : stream;
+            const int lo = (int)((long long)n_chunks * q / parts), hi = (int)((long long)n_chunks * (q + 1) / parts);
+            Q.chunk_base = P.chunk_base + lo;
+            tick_pass_kernel<1><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>), st>>>(Q);
+            tick_pass_kernel<2><<<hi - lo, PassGeom<2>::THREADS, sizeof(SmemPass<2>), st>>>(Q);
+            tick_pass3_kernel<<<(hi - lo) * (CHUNK / 4), 128, 0, st>>>(Q);
+            *launched += 3;
+        }
+        for (int q = 1; q < parts; q++) {
+            cudaEventRecord(fork->ev_join[q - 1], fork->aux[q - 1]);
+            cudaStreamWaitEvent(stream, fork->ev_join[q - 1], 0);
+        }
     } else if (P.schedule == FSE_SCHEDULE_ROWS)
 {
         tick_rows_kernel<<<n_chunks, ROWS_THREADS, sizeof(SmemRows), stream>>>(P);

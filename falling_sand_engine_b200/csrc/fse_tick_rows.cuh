@@ -1053,14 +1053,15 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
     const bool io = warp == G::THREADS / 32 - 1;
 
     int cxi, cyi;
-    if (P.list_count && (int)blockIdx.x >= *P.list_count) return;
+    const int bid = (int)blockIdx.x + P.chunk_base;
+    if (P.list_count && bid >= *P.list_count) return;
     if (P.chunk_list) {
-        int v = P.chunk_list[blockIdx.x];
+        int v = P.chunk_list[bid];
         cxi = v & 0xffff;
         cyi = v >> 16;
     } else {
-        cxi = blockIdx.x % P.ncx;
-        cyi = blockIdx.x / P.ncx;
+        cxi = bid % P.ncx;
+        cyi = bid / P.ncx;
     }
     const int cx = P.x0 + cxi * 2 * CHUNK;
     const int cy = P.y0 + cyi * 2 * CHUNK;
@@ -1163,7 +1164,7 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
 // dropped from the whole row afterwards (the colour phase is over).
 __global__ void __launch_bounds__(128) tick_pass3_kernel(const __grid_constant__ TickParams P) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int chunk = blockIdx.x >> 5;
+    const int chunk = (int)(blockIdx.x >> 5) + P.chunk_base;
     const int r = ((blockIdx.x & 31) << 2) + warp;  // memory row inside the chunk
     int cxi, cyi;
     if (P.list_count && chunk >= *P.list_count) return;

@@ -16,7 +16,7 @@ table, extra = bench.make_table()
 ids = G._names(table)
 phys = np.array([m.physics for m in table.mats], dtype=np.int32)
 ctx = fse.Context(0, table)
-fam = {"none": [], "interacting powders": [-2], "plain powders": [-3], "gases": [T.GAS]}
+fam = {"none": [], "interacting powders": [-2], "plain powders": [-3], "gases": [T.GAS], "liquids": [T.SOUP], "fire": [-1], "everything": [T.SAND, T.SOUP, T.GAS, -1]}
 xids = np.array(sorted(extra.values()))
 print(f"{N}x{N} mixed, schedule {sched}; family replaced by AIR -> ms/tick (ticks 5..8)")
 for name, kill in fam.items():
