@@ -286,7 +286,9 @@ FSE_API int fse_strip_create(fse_ctx* c, int32_t width, int32_t height_global, f
     w->Hglobal = height_global;
     w->own_lo = own_lo;
     w->own_hi = own_hi;
-    cudaError_t e = cudaStreamCreateWithFlags(&w->comm_stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&w->comm_stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->ev_boundary, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->ev_comm, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -620,18 +622,20 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.x0 = z.x + ofx * CHUNK;
             P.y0 += ofy * CHUNK;
             if (int r = kt.begin(w->stream)) return r;
+            // boundary chunks and the halo exchange run on the (high-priority) side stream, next to the interior chunks: all
+            // chunks of a colour phase are independent, only the next phase needs both
+            CK(cudaEventRecord(w->ev_boundary, w->stream));
+            CK(cudaStreamWaitEvent(w->comm_stream, w->ev_boundary, 0));
             if (w->list_cnt[tk][0] > 0) {
                 P.chunk_list = w->d_chunk_lists + w->list_off[tk][0];
                 int nl = 0;
-                CK(launch_tick_phase(P, w->list_cnt[tk][0], w->stream, &nl, nullptr));
+                CK(launch_tick_phase(P, w->list_cnt[tk][0], w->comm_stream, &nl, nullptr));
                 w->ctx->launches += nl;
             }
             if (multi) {
-                CK(cudaEventRecord(w->ev_boundary, w->stream));
-                CK(cudaStreamWaitEvent(w->comm_stream, w->ev_boundary, 0));
                 if (int r = strip_exchange(w, ofy, j0, j1, z.y - w->y_off, w->comm_stream)) return r;
-                CK(cudaEventRecord(w->ev_comm, w->comm_stream));
             }
+            CK(cudaEventRecord(w->ev_comm, w->comm_stream));
             if (w->list_cnt[tk][1] > 0) {
                 P.chunk_list = w->d_chunk_lists + w->list_off[tk][1];
                 int nl = 0;
@@ -639,7 +643,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                 w->ctx->launches += nl;
             }
             if (int r = kt.end(w->stream)) return r;
-            if (multi) CK(cudaStreamWaitEvent(w->stream, w->ev_comm, 0));
+            CK(cudaStreamWaitEvent(w->stream, w->ev_comm, 0));
         }
     }
     w->ticks++;

@@ -10,6 +10,7 @@
 // 32 cells processed together are >= 4 columns apart and every +-1-column rule commutes.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (strict FP like the reference, xmake.lua:38).
+#include <cstdlib>
 #include "fse_device.cuh"
 
 namespace fse {
@@ -1092,8 +1093,8 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(tick_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemRows));
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(tick_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPass<1>));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemPass<2>));
+        e = cudaFuncSetAttribute(tick_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -1102,6 +1103,7 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         // The three passes of a chunk only depend on each other, so the phase is cut into parts that run on their own streams:
         // while the last pass-1 CTAs of one part drain, another part's pass 2 already fills the SMs (the kernels are latency
         // bound and a phase is only ~1.3 waves of CTAs).
+        static const int pad = getenv("FSE_PASS_SMEM_PAD") ? atoi(getenv("FSE_PASS_SMEM_PAD")) : 0;  // occupancy experiments
         const int parts = (fork && n_chunks >= 256) ? fork->parts : 1;
         TickParams Q = P;
         if (parts > 1) {
@@ -1112,8 +1114,8 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
             cudaStream_t st = q ? fork->aux[q - 1] : stream;
             const int lo = (int)((long long)n_chunks * q / parts), hi = (int)((long long)n_chunks * (q + 1) / parts);
             Q.chunk_base = P.chunk_base + lo;
-            tick_pass_kernel<1><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>), st>>>(Q);
-            tick_pass_kernel<2><<<hi - lo, PassGeom<2>::THREADS, sizeof(SmemPass<2>), st>>>(Q);
+            tick_pass_kernel<1><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>) + pad, st>>>(Q);
+            tick_pass_kernel<2><<<hi - lo, PassGeom<2>::THREADS, sizeof(SmemPass<2>) + pad, st>>>(Q);
             tick_pass3_kernel<<<(hi - lo) * (CHUNK / 4), 128, 0, st>>>(Q);
             *launched += 3;
         }
