@@ -26,6 +26,9 @@ if ROOT not in sys.path:
 
 CELL_ITER = 3
 ALGO_BYTES_PER_CELL_UPDATE = 36  # 18 B state read + 18 B written per cell per iteration
+KERNEL_OF = {"default": "one colour phase = fse::tick_pass_kernel<1> + tick_pass_kernel<2> + tick_pass3_kernel", "rows_fused": "fse::tick_rows_kernel",
+             "classes": "fse::tick_chunk_kernel"}
+KERNEL_OF["rows"] = KERNEL_OF["default"]
 METRIC = "Gcell-updates/sec (device-timed) at 1/2/4/8 B200; % HBM roofline"
 UNIT = "Gcell-updates/s"
 
@@ -271,7 +274,8 @@ def run_ours(args):
         ms = float(tms.item())
     value = CELL_ITER * zone_cells_total * args.steps / (ms * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (chunk tick), from CUDA events around every launch in the timed region ----
+    # ---- roofline of the dominant kernels (the chunk tick of one colour phase = pass-1 + pass-2 + pass-3 kernels; one
+    #      "launch" below is one phase), from CUDA events around every phase in the timed region ----
     peak, peak_src = peaks()
     own_zone_cells = zone_cells_total // max(world_size, 1)
     algo_bytes = ALGO_BYTES_PER_CELL_UPDATE * CELL_ITER * own_zone_cells * args.steps  # all launches of this rank
@@ -281,11 +285,11 @@ def run_ours(args):
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get("tick_chunk_kernel_bytes_per_launch")
+                traffic = json.load(f).get("tick_phase_bytes_per_launch")
         except Exception:
             traffic = None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "peak_source": peak_src, "kernel": "fse::tick_chunk_kernel", "launches": k_launches,
+            "peak_source": peak_src, "kernel": KERNEL_OF.get(args.schedule, KERNEL_OF["default"]), "launches": k_launches,
             "avg_launch_ms": k_ms / max(k_launches, 1),
             "algorithmic_bytes_per_launch": algo_bytes / max(k_launches, 1)}
 
