@@ -528,13 +528,13 @@ FSE_API int fse_debug_role_cycles(fse_world* w, int enable, unsigned long long* 
     if (!w) return fail(FSE_EINVAL, "fse_debug_role_cycles: null world");
     CK(cudaSetDevice(w->ctx->device));
     if (enable && !w->d_dbg) {
-        CK(cudaMalloc(&w->d_dbg, 128));
-        CK(cudaMemset(w->d_dbg, 0, 128));
+        CK(cudaMalloc(&w->d_dbg, 512));
+        CK(cudaMemset(w->d_dbg, 0, 512));
     }
     if (out && w->d_dbg) {
         CK(cudaStreamSynchronize(w->stream));
-        CK(cudaMemcpy(out, w->d_dbg, 96, cudaMemcpyDeviceToHost));
-        CK(cudaMemset(w->d_dbg, 0, 128));
+        CK(cudaMemcpy(out, w->d_dbg, 256, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(w->d_dbg, 0, 512));
     }
     if (!enable && w->d_dbg) {
         cudaFree(w->d_dbg);

@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
 //   pass 3: its rows do not depend on each other (a gas cell only looks at and moves within its own row), so it runs one
 //           warp per row straight on global memory
 #ifndef FSE_P1_RN
-#define FSE_P1_RN 13
+#define FSE_P1_RN 14
 #endif
 #ifndef FSE_P2_RN
 #define FSE_P2_RN 14
@@ -988,7 +988,7 @@ struct PassGeom {
     static constexpr int PF = FSE_PASS_PF;                // rows loaded ahead of the step that needs them
     static constexpr int THREADS = 160;
 };
-// pass 1: live rows st-5..st+5; the row loaded at step st (st+7) takes the slot of row st-6, whose store is issued in the same step
+// pass 1: live rows st-5..st+5; the row loaded at step st (st+7) takes the slot of row st-7, whose store was issued a step earlier
 // pass 2: live rows st-10..st+1; the row loaded at step st (st+3) takes the slot of row st-11
 static_assert(PassGeom<1>::UP + PassGeom<1>::PF - PassGeom<1>::RN <= -PassGeom<1>::SL, "pass 1 window");
 static_assert(PassGeom<2>::UP + PassGeom<2>::PF - PassGeom<2>::RN < PassGeom<2>::KMIN, "pass 2 window");
@@ -1109,11 +1109,23 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
     for (int k = G::KMIN; k < G::UP; k++) mbar_wait(&S.bar[(k - G::KMIN) % G::RN], (uint32_t)(((k - G::KMIN) / G::RN) & 1));
 
     const int n_steps = G::LAST + G::SL + 1;
+#ifdef FSE_ROLE_CYCLES
+    long long dbg_t[4] = {0, 0, 0, 0};  // mbarrier wait, step barrier, step work, steps
+#define FSE_STEP_CLOCK(i, since) do { const long long now_ = clock64(); dbg_t[i] += now_ - (since); (since) = now_; } while (0)
+    long long dbg_c = clock64();
+#else
+#define FSE_STEP_CLOCK(i, since) do { } while (0)
+#endif
     for (int st = 0; st < n_steps; st++) {
+        FSE_STEP_CLOCK(2, dbg_c);
         const int kw = st + G::UP;
         if (kw <= G::LAST) mbar_wait(&S.bar[(kw - G::KMIN) % G::RN], (uint32_t)(((kw - G::KMIN) / G::RN) & 1));
+        FSE_STEP_CLOCK(0, dbg_c);
+#ifndef FSE_EXP_NO_TOP_FENCE
         fence_proxy_async();
+#endif
         __syncthreads();
+        FSE_STEP_CLOCK(1, dbg_c);
         if (!io) {
             if (st < CHUNK) {
                 if (PASS == 1) pass1_rows<G::RN>(c, reinterpret_cast<Scratch1&>(S.rs), st, cx, cy, tid);
@@ -1134,16 +1146,16 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
                 const bool vis_store = S.h.rowvis[q] != 0;
                 fence_proxy_async();
                 __syncwarp();
-                if (all_store ? lane < 7 : (vis_store && lane == 1)) {
+                if (all_store ? lane < 7 : (vis_store && lane == 1))
                     bulk_s2g(pio.g + (size_t)(cy + CHUNK - 1 - ks) * pio.row_stride, S.ring + q * ROW_BYTES + pio.soff, pio.bytes);
-                    bulk_commit();
-                }
             }
+            bulk_commit();  // one (possibly empty) bulk group per lane and step, so wait_group counts steps
             const int kl = st + G::UP + G::PF;
             if (kl <= G::LAST) {
-                // each lane waits until its own stores have left shared memory: the slot to fill may be the one whose store was
-                // issued a moment ago (pass 1 with the tightest window), and bulk groups are per thread
-                bulk_wait_read<0>();
+                // each lane waits until its own stores out of the slot to fill have left shared memory (bulk groups are per
+                // thread): with one spare row in the window that store was issued a step ago and this does not stall
+                if (G::UP + G::PF - G::RN < -G::SL) bulk_wait_read<1>();
+                else bulk_wait_read<0>();
                 pass_row_load<PASS>(S, pio, lane, kl, cy);
             }
         }
@@ -1152,6 +1164,12 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
     if (PASS == 1 && P.dbg && tid == 0) {
         atomicAdd(&P.dbg[0], 1ULL);
         for (int q = 0; q < 10; q++) atomicAdd(&P.dbg[1 + q], (unsigned long long)reinterpret_cast<Scratch1&>(S.rs).dbg_phase[q]);
+    }
+    if (P.dbg && (tid == 0 || tid == G::THREADS - 32)) {  // compute thread 0 and IO lane 0: where the step time goes
+        unsigned long long* o = P.dbg + 16 + (PASS - 1) * 8 + (tid ? 4 : 0);
+        FSE_STEP_CLOCK(2, dbg_c);
+        for (int q = 0; q < 3; q++) atomicAdd(&o[q], (unsigned long long)dbg_t[q]);
+        atomicAdd(&o[3], 1ULL);
     }
 #endif
     if (io) bulk_wait_all();

@@ -5,12 +5,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, falling_sand_engine_b200 as fse
 from falling_sand_engine_b200 import worldgen as G
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+workload = sys.argv[2] if len(sys.argv) > 2 else "mixed"
 table, extra = bench.make_table()
 ctx = fse.Context(0, table); w = fse.World(ctx, size, size); w.particles_reserve(1 << 25)
-G.fill_world(w, functools.partial(G.mixed_band, table, seed=1337, extra=list(extra.values())), size, size, band_rows=1024)
+if workload == "mixed":
+    G.fill_world(w, functools.partial(G.mixed_band, table, seed=1337, extra=list(extra.values())), size, size, band_rows=1024)
 for t in range(5): w.tick(t)
 w.L.fse_debug_role_cycles.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-out = (C.c_uint64 * 12)()
+out = (C.c_uint64 * 32)()
 w.L.fse_debug_role_cycles(w.h, 1, None)
 for t in range(5, 8): w.tick(t)
 w.L.fse_debug_role_cycles(w.h, 1, out)
@@ -18,3 +20,8 @@ n = max(out[0], 1)
 print("chunk passes", out[0])
 print("per chunk: D+wait %.0f (warp 0 own D %.0f)  C1+bar %.0f  C2+bar %.0f  area %.0f cycles" % (out[1]/n, out[6]/n, out[2]/n, out[3]/n, out[4]/n))
 print("rows per chunk: seen %.1f  active %.1f  with gather %.1f  with area %.1f" % (out[7]/n, out[8]/n, out[9]/n, out[10]/n))
+for ps in (0, 1):
+    for who, off in (("compute thread 0", 0), ("IO lane 0", 4)):
+        o = out[16 + ps * 8 + off: 16 + ps * 8 + off + 4]
+        m = max(o[3], 1)
+        print("pass %d %-16s per chunk: mbarrier wait %.0f  step barrier %.0f  work %.0f cycles" % (ps + 1, who, o[0] / m, o[1] / m, o[2] / m))
