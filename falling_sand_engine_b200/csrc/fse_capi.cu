@@ -209,6 +209,7 @@ static void free_world(fse_world* w) {
     if (w->ev_comm) cudaEventDestroy(w->ev_comm);
     cudaFree(w->d_chunk_lists);
     cudaFree(w->d_awake); cudaFree(w->d_active_list); cudaFree(w->d_active_count);
+    cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list);
     fse_bodies_free(w);
     cudaFree(w->outline_scratch);
     delete w;
@@ -234,7 +235,10 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     A((void**)&w->d_stats, dev_stats_bytes());
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_stats, dev_stats_bytes());
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+    if (const char* env = getenv("FSE_TICK_LPT")) w->lpt_on = atoi(env) != 0;
     w->fork.parts = 3;
+    w->fork.min_chunks = 256;
+    if (const char* env = getenv("FSE_TICK_MIN_CHUNKS")) w->fork.min_chunks = std::max(1, atoi(env));
     if (const char* env = getenv("FSE_TICK_PARTS")) w->fork.parts = std::min(4, std::max(1, atoi(env)));
     for (int q = 0; q < 3; q++) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->fork.aux[q], cudaStreamNonBlocking);
@@ -599,6 +603,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.dbg = w->d_dbg;
             P.fused = w->fused;
             P.chunk_base = 0;
+            P.chunk_cost = nullptr;
             if (!w->strip) {
                 const int n_chunks = P.ncx * P.ncy;
                 if (n_chunks <= 0) continue;
@@ -610,9 +615,33 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                     P.list_count = w->d_active_count;
                     P.awake = w->d_awake;
                 }
+                // longest-first order from the cycles pass 1 took on each chunk of this colour the last time (per-pass kernels)
+                const bool lpt = w->lpt_on && !P.chunk_list && w->schedule == FSE_SCHEDULE_ROWS && !w->fused && n_chunks >= w->fork.min_chunks;
+                if (lpt) {
+                    if (n_chunks > w->lpt_cap) {
+                        cudaFree(w->d_lpt_cost);
+                        cudaFree(w->d_lpt_list);
+                        w->d_lpt_cost = nullptr;
+                        w->d_lpt_list = nullptr;
+                        w->lpt_cap = 0;
+                        CK(cudaMalloc((void**)&w->d_lpt_cost, sizeof(unsigned int) * 4 * (size_t)n_chunks));
+                        CK(cudaMalloc((void**)&w->d_lpt_list, sizeof(int) * 4 * (size_t)n_chunks));
+                        w->lpt_cap = n_chunks;
+                        memset(w->lpt_sig, 0, sizeof(w->lpt_sig));
+                    }
+                    const int sig[4] = {P.x0, P.y0, P.ncx, P.ncy};
+                    if (memcmp(sig, w->lpt_sig[tk], sizeof(sig)) == 0) P.chunk_list = w->d_lpt_list + (size_t)tk * w->lpt_cap;
+                    P.chunk_cost = w->d_lpt_cost + (size_t)tk * w->lpt_cap;
+                }
                 if (int r = kt.begin(w->stream)) return r;
                 int nl = 0;
                 CK(launch_tick_phase(P, n_chunks, w->stream, &nl, &w->fork));
+                if (lpt) {
+                    CK(launch_lpt_build(P.chunk_cost, n_chunks, P.ncx, w->d_lpt_list + (size_t)tk * w->lpt_cap, w->stream));
+                    nl += 1;
+                    const int sig[4] = {P.x0, P.y0, P.ncx, P.ncy};
+                    memcpy(w->lpt_sig[tk], sig, sizeof(sig));
+                }
                 if (int r = kt.end(w->stream)) return r;
                 w->ctx->launches += nl;
                 continue;

@@ -124,6 +124,7 @@ struct TickParams {
     int acols, arows;
     int never_sleep;        // strip worlds keep their cut-adjacent chunk rows awake
     unsigned long long* dbg; // optional role-cycle counters (profiling aid), null otherwise
+    unsigned int* chunk_cost; // optional: pass 1 records the cycles each chunk took (cost[cyi * ncx + cxi]) for the next tick's ordering
     int chunk_base;         // first chunk (index into the phase's chunk grid or list) of this launch
     int fused;              // rows schedule: 1 = single fused kernel (all passes pipelined), 0 = one kernel per pass
     int schedule;           // FSE_SCHEDULE_CLASSES (4 interleaved column classes) or FSE_SCHEDULE_ROWS (simultaneous rows)
@@ -132,6 +133,7 @@ struct TickParams {
 // extra streams + events for running the parts of a colour phase side by side (nullptr: single stream)
 struct TickFork {
     int parts;  // 1..4 parts of a phase run side by side; part 0 on the caller's stream
+    int min_chunks;  // phases with fewer chunks are launched whole (default 256; FSE_TICK_MIN_CHUNKS)
     cudaStream_t aux[3];
     cudaEvent_t ev_fork, ev_join[3];
 };

@@ -59,6 +59,12 @@ struct fse_world {
     int acols = 0, arows = 0;
     int* d_active_list = nullptr;   // compacted (cxi | cyi << 16) of the phase being launched
     int* d_active_count = nullptr;
+    // longest-first chunk order of the per-pass tick kernels: per colour, last tick's pass-1 cycles and the list built from them
+    unsigned int* d_lpt_cost = nullptr;
+    int* d_lpt_list = nullptr;
+    int lpt_cap = 0;            // chunks per colour the buffers hold
+    int lpt_sig[4][4]{};        // (x0, y0, ncx, ncy) the list of a colour was built for; ncx = 0: no list yet
+    bool lpt_on = true;
     // rigid-body bridge (fse_bodies.cu) and outline scratch (fse_outline.cu)
     struct fse_bodies* bodies = nullptr;
     int last_bridge_rounds = 0;
@@ -92,6 +98,7 @@ int fail(int code, const char* fmt, ...);
 int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cudaStream_t s);
 int strip_refresh(fse_world* w, cudaStream_t s);
 size_t tick_smem_bytes();
+cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream);
 cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched, const TickFork* fork);  // *launched = kernels enqueued
 cudaError_t launch_compact_active(const uint8_t* awake, int acols, int ci0, int cj0, int ncx, int ncy, int* list, int* count, cudaStream_t s);
 

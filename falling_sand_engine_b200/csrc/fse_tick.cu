@@ -1104,7 +1104,7 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         // while the last pass-1 CTAs of one part drain, another part's pass 2 already fills the SMs (the kernels are latency
         // bound and a phase is only ~1.3 waves of CTAs).
         static const int pad = getenv("FSE_PASS_SMEM_PAD") ? atoi(getenv("FSE_PASS_SMEM_PAD")) : 0;  // occupancy experiments
-        const int parts = (fork && n_chunks >= 256) ? fork->parts : 1;
+        const int parts = (fork && n_chunks >= fork->min_chunks) ? fork->parts : 1;
         TickParams Q = P;
         if (parts > 1) {
             cudaEventRecord(fork->ev_fork, stream);
@@ -1131,6 +1131,11 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         tick_chunk_kernel<<<n_chunks, 128, sizeof(Smem), stream>>>(P);
         *launched = 1;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream) {
+    lpt_build_kernel<<<1, 1024, 0, stream>>>(cost, n, ncx, list);
     return cudaGetLastError();
 }
 

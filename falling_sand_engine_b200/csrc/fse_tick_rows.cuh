@@ -1065,6 +1065,7 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
     }
     const int cx = P.x0 + cxi * 2 * CHUNK;
     const int cy = P.y0 + cyi * 2 * CHUNK;
+    const long long t_begin = (PASS == 1 && P.chunk_cost) ? clock64() : 0;
 
     const DevTables* T = P.tabs;
     {
@@ -1172,6 +1173,7 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
         atomicAdd(&o[3], 1ULL);
     }
 #endif
+    if (PASS == 1 && P.chunk_cost && tid == 0) P.chunk_cost[cyi * P.ncx + cxi] = (unsigned int)(clock64() - t_begin);
     if (io) bulk_wait_all();
 }
 
@@ -1272,6 +1274,36 @@ __global__ void __launch_bounds__(128) tick_pass3_kernel(const __grid_constant__
         P.p.col[a] = cb2; P.p.col[b] = ca;
         P.p.fl[a] = lb; P.p.fl[b] = la;
         P.p.fd[a] = db; P.p.fd[b] = da;
+    }
+}
+
+// Longest-first launch order for the next tick: chunks of a colour are binned by the cycles pass 1 took on them this tick
+// (64 bins, heaviest bin first).  A phase is ~1.3 waves of CTAs, so starting the expensive chunks first shortens its tail;
+// chunks of a phase are independent, the order cannot change results.
+__global__ void __launch_bounds__(1024) lpt_build_kernel(const unsigned int* cost, int n, int ncx, int* list) {
+    __shared__ unsigned int hist[64], base[64], maxc;
+    const int tid = threadIdx.x;
+    if (tid < 64) hist[tid] = 0;
+    if (tid == 0) maxc = 0;
+    __syncthreads();
+    unsigned int m = 0;
+    for (int i = tid; i < n; i += blockDim.x) m = max(m, cost[i]);
+    atomicMax(&maxc, m);
+    __syncthreads();
+    const unsigned long long scale = (unsigned long long)maxc + 1;
+    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[63 - (int)((unsigned long long)cost[i] * 64 / scale)], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int acc = 0;
+        for (int b = 0; b < 64; b++) {
+            base[b] = acc;
+            acc += hist[b];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const unsigned int pos = atomicAdd(&base[63 - (int)((unsigned long long)cost[i] * 64 / scale)], 1u);
+        list[pos] = (i % ncx) | ((i / ncx) << 16);
     }
 }
 

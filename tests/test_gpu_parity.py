@@ -221,3 +221,15 @@ def test_determinism(gpu_ctx, table):
         hashes.append(gw.stats().hash)
         gw.close()
     assert hashes[0] == hashes[1]
+
+
+def test_phase_parts_and_longest_first_order_do_not_change_results(oracle, gpu_ctx, table, monkeypatch):
+    """Large worlds cut a colour phase into parts on separate streams and launch the chunks longest-first (last tick's
+    pass-1 cycles).  Chunks of a phase are independent, so neither may change a single bit: force both on a small world."""
+    monkeypatch.setenv("FSE_TICK_MIN_CHUNKS", "1")
+    W = H = 1280
+    tbl, extra = G.bench_table(table)
+    ow, gw = _pair(oracle, gpu_ctx, tbl, W, H, "rows")
+    Hh.build_mixed(ow, tbl, W, H, seed=5, extra=list(extra.values()))
+    Hh.build_mixed(gw, tbl, W, H, seed=5, extra=list(extra.values()))
+    _run_and_compare(ow, gw, 6, seed=3, what="parts + longest-first")
