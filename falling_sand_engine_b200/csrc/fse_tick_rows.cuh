@@ -130,8 +130,12 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
         return d;
     }
     if (type == P_SAND) {  // 1148-1267
-        const uint8_t mb = MAT(sb, j);
-        const int bt = LUTP->phys[mb];
+        // neighbourhood up front (independent shared-memory reads, see the liquid branch)
+        const uint8_t mb = MAT(sb, j), mbl = MAT(sb, j - 1), mbr = MAT(sb, j + 1);
+        const uint8_t m2 = MAT(rsn<RN>(s, 2), j), m3 = MAT(rsn<RN>(s, 3), j), m4 = MAT(rsn<RN>(s, 4), j);
+        const int bt = LUTP->phys[mb], btl = LUTP->phys[mbl], btr = LUTP->phys[mbr];
+        const float myDens = LUTP->dens[m], densB = LUTP->dens[mb], densL = LUTP->dens[mbl], densR = LUTP->dens[mbr];
+        const bool deepAir = LUTP->phys[m2] == P_AIR && LUTP->phys[m3] == P_AIR && LUTP->phys[m4] == P_AIR;
         const uint8_t mf = LUTP->mflags[m];
         if ((mf & MF_INTERACT) && has_interaction(c, m, mb)) {
             d.bits = A_INTERACT | ((uint32_t)mb << 24);
@@ -155,46 +159,54 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
                 return d;
             }
         }
-        const float myDens = LUTP->dens[m];
-        if (!(bt == P_AIR || (bt != P_SOLID && LUTP->dens[mb] < myDens))) return d;
-        const bool canL = can_sink(c, sb, j - 1, myDens), canR = can_sink(c, sb, j + 1, myDens);
-        if ((canL || canR) && rng_draw(cb, S_SAND_HESITATE) % 20 == 0) return d;
+        if (!(bt == P_AIR || (bt != P_SOLID && densB < myDens))) return d;
+        // the grain can fall: all five draws at once (pure functions of the cell; independent hash chains overlap)
+        const uint32_t rHes = rng_draw(cb, S_SAND_HESITATE), rMov = rng_draw(cb, S_SAND_MOVED), rSelf = rng_draw(cb, S_SAND_TX_SELF),
+                       rL = rng_draw(cb, S_SAND_TX_L), rR = rng_draw(cb, S_SAND_TX_R);
+        const bool canL = btl == P_AIR || (btl != P_SOLID && densL < myDens), canR = btr == P_AIR || (btr != P_SOLID && densR < myDens);
+        if ((canL || canR) && rHes % 20 == 0) return d;
         uint32_t bits;
-        if (bt == P_AIR && PHYS(rsn<RN>(s, 2), j) == P_AIR && PHYS(rsn<RN>(s, 3), j) == P_AIR && PHYS(rsn<RN>(s, 4), j) == P_AIR) {
+        if (bt == P_AIR && deepAir) {
             bits = A_SAND_PART;
         } else {
             bits = A_SAND_SWAP;
-            if (rng_draw(cb, S_SAND_MOVED) % 2 == 0) bits |= DB_COIN;
+            if (rMov % 2 == 0) bits |= DB_COIN;
         }
-        if (rng_draw(cb, S_SAND_TX_SELF) % 2 == 0) {
-            if (rng_draw(cb, S_SAND_TX_L) % 2 == 0) bits |= DB_POKEL;
-            if (rng_draw(cb, S_SAND_TX_R) % 2 == 0) bits |= DB_POKER;
+        if (rSelf % 2 == 0) {
+            if (rL % 2 == 0) bits |= DB_POKEL;
+            if (rR % 2 == 0) bits |= DB_POKER;
         }
         d.bits = bits;
         return d;
     }
     if (type == P_SOUP) {  // 1269-1537
+        // the whole neighbourhood is read up front: the decision below is a chain of short branches, and with the loads hoisted
+        // their shared-memory latencies overlap instead of adding up
+        const int st = rsn<RN>(s, -1);
         const float fl = FL(s, j);
+        const uint8_t mb0 = MAT(sb, j), ml = MAT(s, j - 1), mr = MAT(s, j + 1), mt = MAT(st, j);
+        const uint8_t m2 = MAT(rsn<RN>(s, 2), j), m3 = MAT(rsn<RN>(s, 3), j), m4 = MAT(rsn<RN>(s, 4), j);
+        const float bottomFl = FL(sb, j), leftFl = FL(s, j - 1), rightFl = FL(s, j + 1), topFl = FL(st, j);
+        float fd = FD(s, j);
+        uint8_t stl = STL(s, j);
+        const int bph = LUTP->phys[mb0], lph = LUTP->phys[ml], rph = LUTP->phys[mr], tph = LUTP->phys[mt];
+        const bool deepAir = LUTP->phys[m2] == P_AIR && LUTP->phys[m3] == P_AIR && LUTP->phys[m4] == P_AIR;
         if (fl == 0.0f) return d;
         if (fl < FLUID_MinValue) {
             d.bits = A_SOUP_ZERO;
             return d;
         }
-        const uint8_t mb0 = MAT(sb, j);
-        const int bph = LUTP->phys[mb0];
-        if ((double)fl > 0.005 && bph == P_AIR && PHYS(rsn<RN>(s, 2), j) == P_AIR && PHYS(rsn<RN>(s, 3), j) == P_AIR && PHYS(rsn<RN>(s, 4), j) == P_AIR) {
+        if ((double)fl > 0.005 && bph == P_AIR && deepAir) {
             d.bits = A_SOUP_PART;
             return d;
         }
         if (f0 & F_MOVED) return d;
         const float start = fl;
         float rem = fl;
-        float fd = FD(s, j);
         const bool airBelow = bph == P_AIR;
         uint32_t bits = A_SOUP_FLOW;
         if (bph == P_SOUP) bits |= DB_BOTSOUP;
         bool early = false;
-        const float bottomFl = FL(sb, j);
         if ((airBelow && c.iter <= 2) || mb0 == m) {  // 1315-1334
             const float dst = bph == P_SOUP ? bottomFl : 0.0f;
             float flow = vertical_flow(start, dst) - dst;
@@ -214,14 +226,12 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
             fd -= rem;
             early = true;
         }
-        const uint8_t ml = MAT(s, j - 1), mr = MAT(s, j + 1);
-        const int lph = LUTP->phys[ml], rph = LUTP->phys[mr];
         if (lph == P_SOUP) bits |= DB_LEFTSOUP;
         if (rph == P_SOUP) bits |= DB_RIGHTSOUP;
         const bool canL = (lph == P_AIR || ml == m) && !airBelow;
         const bool canR = (rph == P_AIR || mr == m) && !airBelow;
         if (!early && canL) {  // 1355-1375
-            const float dst = lph == P_SOUP ? FL(s, j - 1) : 0.0f;
+            const float dst = lph == P_SOUP ? leftFl : 0.0f;
             const float flow = clampflow((rem - dst) / (canR ? 3.0f : 2.0f), rem, true);
             if (flow != 0) {
                 rem -= flow;
@@ -234,7 +244,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
             early = true;
         }
         if (!early && canR) {  // 1383-1403
-            const float dst = rph == P_SOUP ? FL(s, j + 1) : 0.0f;
+            const float dst = rph == P_SOUP ? rightFl : 0.0f;
             const float flow = clampflow((rem - dst) / 2.0f, rem, true);
             if (flow != 0) {
                 rem -= flow;
@@ -246,14 +256,11 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
             fd -= rem;
             early = true;
         }
-        const int st = rsn<RN>(s, -1);
-        const uint8_t mt = MAT(st, j);
-        const int tph = LUTP->phys[mt];
         if (tph == P_SOUP) bits |= DB_TOPSOUP;
         bool swapUp = false;
         if (!early) {
             if (tph == P_AIR || mt == m) {  // 1413-1432
-                const float dst = tph == P_SOUP ? FL(st, j) : 0.0f;
+                const float dst = tph == P_SOUP ? topFl : 0.0f;
                 const float flow = clampflow(rem - vertical_flow(rem, dst), rem, true);
                 if (flow != 0) {
                     rem -= flow;
@@ -269,7 +276,6 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
             early = true;
         }
         d.fd_new = fd;
-        uint8_t stl = STL(s, j);
         bool moved = (f0 & F_MOVED) != 0;
         if (swapUp) bits |= DB_SWAPUP;
         if (!early && !swapUp) {

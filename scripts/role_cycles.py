@@ -8,9 +8,19 @@ size = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 workload = sys.argv[2] if len(sys.argv) > 2 else "mixed"
 table, extra = bench.make_table()
 ctx = fse.Context(0, table); w = fse.World(ctx, size, size); w.particles_reserve(1 << 25)
+import numpy as np
+ids = G._names(table)
 if workload == "mixed":
     G.fill_world(w, functools.partial(G.mixed_band, table, seed=1337, extra=list(extra.values())), size, size, band_rows=1024)
-for t in range(5): w.tick(t)
+elif workload != "air":
+    ys, xs = np.mgrid[0:size, 0:size].astype(np.uint32)
+    A, S, WAT, GAS = ids["AIR"], ids["GENERIC_SAND"], ids["WATER"], ids["GENERIC_GAS"]
+    mat = {"water": lambda: np.full(xs.shape, WAT), "sand3": lambda: np.where(ys % 3 == 0, S, A), "waterhalf": lambda: np.where(xs % 2 == 0, WAT, A),
+           "gas16": lambda: np.where((xs * 7 + ys * 13) % 16 == 0, GAS, A)}[workload]().astype(np.uint16)
+    G.border_fill(mat, 0, 0, size, size, ids["GENERIC_SOLID"])
+    for y0 in range(0, size, 1024):
+        w.write_rect(0, y0, G.cells_from_mat(table, mat[y0:y0 + 1024], 0, y0, 7))
+for t in range(2 if workload != 'mixed' else 5): w.tick(t)
 w.L.fse_debug_role_cycles.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 out = (C.c_uint64 * 32)()
 w.L.fse_debug_role_cycles(w.h, 1, None)
