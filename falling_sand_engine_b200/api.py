@@ -249,6 +249,11 @@ class World:
         return out
 
     # -- fracture outlines (world.cpp:288-720, physics_math.cpp:1766-1965) and physicsCheck flood (world.cpp:3330) ------
+    def explosion(self, x, y, radius, tick=0, seed=1337):
+        """world::explosion(x, y, radius) (world.cpp:2294-2332)."""
+        self.L.fse_explosion.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32]
+        _ck(self.L.fse_explosion(self.h, x, y, radius, tick, seed))
+
     def mask_outline(self, masks):
         """masks: (n, h, w) uint8.  Returns (labels (n,h,w) int32, n_components (n,), contours: list per mask of (k,2) float arrays)."""
         masks = np.ascontiguousarray(masks, dtype=np.uint8)

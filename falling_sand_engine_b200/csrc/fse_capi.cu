@@ -209,7 +209,7 @@ static void free_world(fse_world* w) {
     if (w->ev_comm) cudaEventDestroy(w->ev_comm);
     cudaFree(w->d_chunk_lists);
     cudaFree(w->d_awake); cudaFree(w->d_active_list); cudaFree(w->d_active_count);
-    cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list);
+    cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list); cudaFree(w->d_chunk_state);
     fse_bodies_free(w);
     cudaFree(w->outline_scratch);
     delete w;
@@ -444,6 +444,8 @@ FSE_API int fse_active_enable(fse_world* w, int enable) {
         CK(cudaMalloc(&w->d_awake, (size_t)w->acols * w->arows));
         CK(cudaMalloc(&w->d_active_list, sizeof(int) * ((size_t)w->acols * w->arows / 4 + w->acols + w->arows + 4)));
         CK(cudaMalloc(&w->d_active_count, 64));
+        CK(cudaMalloc((void**)&w->d_chunk_state, sizeof(unsigned int) * (size_t)w->acols * w->arows));
+        if (const char* env = getenv("FSE_ACTIVE_FUSED")) w->active_fused = atoi(env) != 0;
     }
     if (enable) CK(cudaMemsetAsync(w->d_awake, 1, (size_t)w->acols * w->arows, w->stream));
     w->active_on = enable != 0;
@@ -604,6 +606,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.fused = w->fused;
             P.chunk_base = 0;
             P.chunk_cost = nullptr;
+            P.chunk_state = nullptr;
             if (!w->strip) {
                 const int n_chunks = P.ncx * P.ncy;
                 if (n_chunks <= 0) continue;
@@ -614,6 +617,9 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                     P.chunk_list = w->d_active_list;
                     P.list_count = w->d_active_count;
                     P.awake = w->d_awake;
+                    // per-pass kernels record what they saw per chunk and a small kernel updates the flags after pass 3;
+                    // FSE_ACTIVE_FUSED=1 keeps the single fused kernel (shorter chain when only a few chunks are awake)
+                    if (w->schedule == FSE_SCHEDULE_ROWS && !w->fused && !w->active_fused) P.chunk_state = w->d_chunk_state;
                 }
                 // longest-first order from the cycles pass 1 took on each chunk of this colour the last time (per-pass kernels)
                 const bool lpt = w->lpt_on && !P.chunk_list && w->schedule == FSE_SCHEDULE_ROWS && !w->fused && n_chunks >= w->fork.min_chunks;
@@ -804,3 +810,7 @@ FSE_API int fse_kernel_timing_read(fse_world* w, double* total_ms, int64_t* laun
 }
 
 }  // extern "C"
+
+namespace fse {
+int fse_wake_rect(fse_world* w, int x, int y_local, int rw, int rh) { return ::wake_rect(w, x, y_local, rw, rh); }
+}  // namespace fse

@@ -54,6 +54,7 @@ enum Slot : uint32_t {
     S_SAND_TX_R = 38, S_SOUP_PART0 = 40, S_SOUP_SWAP_DOWN = 56, S_SOUP_SWAP_UP = 57, S_GAS1 = 58, S_SAND2_UNSTICK = 59,
     S_SAND2_SHOULD = 60, S_SAND2_TX_SELF = 61, S_SAND2_TX_OTHER = 62, S_SAND2_LR = 63, S_SAND2_RESTICK = 64, S_GAS2 = 65,
     S_GAS3 = 66, S_STEAM = 67, S_CREATE_COLOR = 68, S_PROBE_X = 69, S_PROBE_Y = 70, S_BRIDGE_VX = 71, S_BRIDGE_VY = 72,
+    S_EXPL_KEEP = 73, S_EXPL_VX = 74, S_EXPL_VY = 75,
 };
 
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t v) {
@@ -124,6 +125,7 @@ struct TickParams {
     int acols, arows;
     int never_sleep;        // strip worlds keep their cut-adjacent chunk rows awake
     unsigned long long* dbg; // optional role-cycle counters (profiling aid), null otherwise
+    unsigned int* chunk_state; // per-pass kernels with active tracking: bit 0 = a pass changed cell state, bit 1 = not inert (acols x arows)
     unsigned int* chunk_cost; // optional: pass 1 records the cycles each chunk took (cost[cyi * ncx + cxi]) for the next tick's ordering
     int chunk_base;         // first chunk (index into the phase's chunk grid or list) of this launch
     int fused;              // rows schedule: 1 = single fused kernel (all passes pipelined), 0 = one kernel per pass

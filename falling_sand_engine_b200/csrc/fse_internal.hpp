@@ -59,6 +59,8 @@ struct fse_world {
     int acols = 0, arows = 0;
     int* d_active_list = nullptr;   // compacted (cxi | cyi << 16) of the phase being launched
     int* d_active_count = nullptr;
+    unsigned int* d_chunk_state = nullptr;  // per-pass kernels: what the passes of the running phase saw in each chunk
+    bool active_fused = false;             // FSE_ACTIVE_FUSED=1: active-chunk phases use the fused kernel
     // longest-first chunk order of the per-pass tick kernels: per colour, last tick's pass-1 cycles and the list built from them
     unsigned int* d_lpt_cost = nullptr;
     int* d_lpt_list = nullptr;
@@ -94,6 +96,7 @@ void fse_bodies_free(fse_world* w);
 namespace fse {
 extern thread_local std::string g_err;
 int fail(int code, const char* fmt, ...);
+int fse_wake_rect(fse_world* w, int x, int y_local, int rw, int rh);  // wake the chunks under a rect of local rows (active tracking)
 
 int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cudaStream_t s);
 int strip_refresh(fse_world* w, cudaStream_t s);

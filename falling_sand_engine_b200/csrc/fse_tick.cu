@@ -1099,7 +1099,7 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         configured = true;
     }
     if (n_chunks <= 0) return cudaSuccess;
-    if (P.schedule == FSE_SCHEDULE_ROWS && !P.awake && !P.fused) {  // one kernel per pass
+    if (P.schedule == FSE_SCHEDULE_ROWS && !P.fused && (!P.awake || P.chunk_state)) {  // one kernel per pass
         // The three passes of a chunk only depend on each other, so the phase is cut into parts that run on their own streams:
         // while the last pass-1 CTAs of one part drain, another part's pass 2 already fills the SMs (the kernels are latency
         // bound and a phase is only ~1.3 waves of CTAs).
@@ -1122,6 +1122,10 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         for (int q = 1; q < parts; q++) {
             cudaEventRecord(fork->ev_join[q - 1], fork->aux[q - 1]);
             cudaStreamWaitEvent(stream, fork->ev_join[q - 1], 0);
+        }
+        if (P.awake && P.chunk_state && P.chunk_list) {  // a sleeping chunk can only be woken by a neighbour's record, so the
+            apply_chunk_state_kernel<<<(n_chunks + 127) / 128, 128, 0, stream>>>(P, n_chunks);  // flags change after all passes
+            *launched += 1;
         }
     } else if (P.schedule == FSE_SCHEDULE_ROWS)
 {

@@ -1116,6 +1116,7 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
     for (int k = G::KMIN; k < G::UP; k++) mbar_wait(&S.bar[(k - G::KMIN) % G::RN], (uint32_t)(((k - G::KMIN) / G::RN) & 1));
 
     const int n_steps = G::LAST + G::SL + 1;
+    bool io_modified = false, io_inert = true;  // active-chunk tracking (IO warp): see tick_chunk_kernel
 #ifdef FSE_ROLE_CYCLES
     long long dbg_t[4] = {0, 0, 0, 0};  // mbarrier wait, step barrier, step work, steps
 #define FSE_STEP_CLOCK(i, since) do { const long long now_ = clock64(); dbg_t[i] += now_ - (since); (since) = now_; } while (0)
@@ -1151,6 +1152,11 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
                 }
                 const bool all_store = S.h.rowmod[q] != 0;
                 const bool vis_store = S.h.rowvis[q] != 0;
+                if (P.chunk_state) {
+                    io_modified |= S.h.rowchg[q] != 0;
+                    // rows are final for passes 1 and 2 here; pass 3 only moves GAS, which is never inert anyway
+                    if (PASS == 2 && core_row) io_inert &= row_is_inert(c, q, rsn<G::RN>(q, 1), lane);
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (all_store ? lane < 7 : (vis_store && lane == 1))
@@ -1180,6 +1186,12 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
     }
 #endif
     if (PASS == 1 && P.chunk_cost && tid == 0) P.chunk_cost[cyi * P.ncx + cxi] = (unsigned int)(clock64() - t_begin);
+    if (io && P.chunk_state) {
+        const bool inert = __all_sync(0xffffffffu, io_inert);
+        const unsigned int st = (io_modified ? 1u : 0u) | ((PASS == 2 && !inert) ? 2u : 0u);
+        unsigned int* slot = P.chunk_state + ((cy + P.y_off) / CHUNK) * P.acols + cx / CHUNK;
+        if (lane == 0) *slot = PASS == 1 ? st : (*slot | st);  // pass 1 starts the record, pass 2 adds to it (same stream)
+    }
     if (io) bulk_wait_all();
 }
 
@@ -1245,6 +1257,10 @@ __global__ void __launch_bounds__(128) tick_pass3_kernel(const __grid_constant__
     if (lane == 0) rmPrev = 0;
     if (hadvis) *flgw = fw & 0x7f7f7f7fU;
     __syncwarp();
+    if (P.chunk_state) {  // any decision changes a cell (a lost contest is rare; counting it as a change only keeps the chunk awake)
+        const bool acts = d[0] | d[1] | d[2] | d[3];
+        if (__any_sync(0xffffffffu, acts) && lane == 0) atomicOr(P.chunk_state + (y / CHUNK) * P.acols + cx / CHUNK, 1u);
+    }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         if (d[q] == 0) continue;
@@ -1280,6 +1296,24 @@ __global__ void __launch_bounds__(128) tick_pass3_kernel(const __grid_constant__
         P.p.col[a] = cb2; P.p.col[b] = ca;
         P.p.fl[a] = lb; P.p.fl[b] = la;
         P.p.fd[a] = db; P.p.fd[b] = da;
+    }
+}
+
+// Active-chunk bookkeeping after the three passes of a phase (per-pass kernels): wake the 3x3 chunks around a chunk whose state
+// changed, put a chunk to sleep when nothing changed and every cell is provably inert (same rule as tick_chunk_kernel).
+__global__ void apply_chunk_state_kernel(const TickParams P, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (P.list_count && i >= *P.list_count)) return;
+    const int v = P.chunk_list[i];
+    const int ci = (P.x0 + (v & 0xffff) * 2 * CHUNK) / CHUNK, cj = (P.y0 + (v >> 16) * 2 * CHUNK + P.y_off) / CHUNK;
+    const unsigned int st = P.chunk_state[cj * P.acols + ci];
+    if (st & 1u) {
+        for (int q = 0; q < 9; q++) {
+            const int ni = ci + q % 3 - 1, nj = cj + q / 3 - 1;
+            if (ni >= 0 && nj >= 0 && ni < P.acols && nj < P.arows) P.awake[nj * P.acols + ni] = 1;
+        }
+    } else if (!(st & 2u) && !P.never_sleep) {
+        P.awake[cj * P.acols + ci] = 0;
     }
 }
 

@@ -242,6 +242,12 @@ FSE_API int fse_bodies_raster(fse_world* w, const fse_xform* xf, int32_t n, uint
 FSE_API int fse_bodies_erase(fse_world* w, const fse_xform* xf, int32_t n, fse_body_feedback* out, uint8_t* needs_update);
 FSE_API int fse_bodies_read(fse_world* w, int32_t body, fse_cell* tiles_out);
 
+/* `world::explosion(cx, cy, radius)` (world.cpp:2294-2332): every non-AIR cell within `radius` of (cx, cy) is removed — SOLID
+ * cells and 6 in 10 of the others vanish, the rest leave as loose particles (colour darkened to a quarter, spawned one cell
+ * lower, thrown outward) — and every non-SOLID cell of the ring out to 2*radius is thrown outward as a particle.  Cells decide
+ * independently; rand() is replaced by the counter RNG keyed on (seed, tick, x, y).  Not available on multi-rank strips. */
+FSE_API int fse_explosion(fse_world* w, int32_t cx, int32_t cy, int32_t radius, uint32_t tick, uint32_t seed);
+
 /* ---- fracture / hitbox outlines: updateRigidBodyHitbox, updateChunkMesh (world.cpp:288-720, 722-959) with
  * MarchingSquares::FindPerimeter + simplify(...,1) (physics_math.cpp:1766-1965), physicsCheck flood (world.cpp:3330-3429).
  * The device labels 4-connected components and extracts + simplifies every contour; TPPL hole removal / ear clipping

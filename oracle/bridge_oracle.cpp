@@ -339,11 +339,58 @@ int flood_component(World* W, int x, int y, int cap, int* bbox, int32_t* pixels)
 
 using namespace fseo;
 extern "C" {
+// world::explosion (world.cpp:2294-2332) with rand() replaced by the counter RNG keyed on (seed, tick, x, y) — cells decide
+// independently, so the loop order is immaterial.
+void explosion(World* w, int cx, int cy, int radius, uint32_t tick, uint32_t seed) {
+    const uint32_t rkey = rng_key(seed, tick, 7u);
+    const int outer = radius * 2;
+    for (int x = cx - outer; x < cx + outer; x++) {
+        for (int y = cy - outer; y < cy + outer; y++) {
+            if (x < 0 || y < 0 || x >= w->width || y >= w->height) continue;  // getTile OOB = TEST_SOLID, setTile OOB ignored (world.cpp:999-1008)
+            Cell tile = w->tiles[x + (size_t)y * w->width];
+            if (tile.mat->physicsType == 0) continue;
+            const int dx = x - cx, dy = y - cy;
+            const uint32_t cb = rng_cell(rkey, x, y);
+            bool particle = false, inner = false;
+            if (dx * dx + dy * dy < radius * radius) {
+                inner = true;
+                if (!(tile.mat->physicsType == 1 || rng_draw(cb, S_EXPL_KEEP) % 10 < 6)) particle = true;
+            } else if (dx * dx + dy * dy < outer * outer && tile.mat->physicsType != 1) {
+                particle = true;
+            } else {
+                continue;
+            }
+            if (particle) {
+                Particle p;
+                if (inner) {
+                    const uint32_t r = (tile.color >> 16) & 0xFF, g = (tile.color >> 8) & 0xFF, b = tile.color & 0xFF;
+                    tile.color = ((r / 4) << 16) | ((g / 4) << 8) | (b / 4);
+                }
+                p.tile = tile;
+                p.x = (float)x;
+                p.y = (float)(inner ? y + 1 : y);
+                p.vx = dx / 10.0f + ((int)(rng_draw(cb, S_EXPL_VX) % 10) - 5) / 10.0f;
+                p.vy = dy / 6.0f + ((int)(rng_draw(cb, S_EXPL_VY) % 10) - 5) / 10.0f;
+                p.ax = 0;
+                p.ay = 0.1f;
+                p.id = (3ULL << 62) | ((uint64_t)(tick & 0x3fffff) << 40) | ((uint64_t)(y & 0xfffff) << 20) | (uint64_t)(x & 0xfffff);
+                w->cells.push_back(p);
+            }
+            w->tiles[x + (size_t)y * w->width] = w->nothing();
+            w->dirty[x + (size_t)y * w->width] = 1;
+        }
+    }
+}
+
 #define OAPI __attribute__((visibility("default")))
 
 OAPI int fseo_bodies_raster(void* p, int n, const int* bw, const int* bh, fse_cell* const* tiles, const fse_xform* xf, uint32_t tick,
                             uint32_t seed, int32_t* feedback) {
     bodies_raster((World*)p, n, bw, bh, tiles, xf, tick, seed, feedback);
+    return 0;
+}
+OAPI int fseo_explosion(void* p, int cx, int cy, int radius, uint32_t tick, uint32_t seed) {
+    explosion((World*)p, cx, cy, radius, tick, seed);
     return 0;
 }
 OAPI int fseo_bodies_erase(void* p, int n, const int* bw, const int* bh, fse_cell* const* tiles, const fse_xform* xf, int32_t* feedback) {

@@ -74,6 +74,9 @@ enum Slot : uint32_t {
     S_PROBE_Y = 70,         // world.cpp:1931
     S_BRIDGE_VX = 71,       // game.cpp:1791
     S_BRIDGE_VY = 72,       // game.cpp:1792
+    S_EXPL_KEEP = 73,       // world.cpp:2306
+    S_EXPL_VX = 74,         // world.cpp:2320 / 2324
+    S_EXPL_VY = 75,
 };
 
 static inline uint32_t mix32(uint32_t v) {

@@ -176,6 +176,12 @@ def bodies_raster(world, bodies, xforms, tick=0, seed=1337):
     return fb
 
 
+def explosion(world, cx, cy, radius, tick=0, seed=1337):
+    """world::explosion (world.cpp:2294-2332)."""
+    lib().fseo_explosion.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
+    lib().fseo_explosion(world.h, cx, cy, radius, tick, seed)
+
+
 def bodies_erase(world, bodies, xforms):
     n, bw, bh, ptrs = _body_args(bodies)
     xf = np.ascontiguousarray(xforms, dtype=np.float32).reshape(-1, 3)

@@ -97,3 +97,37 @@ def test_flood_component_sizes(oracle, table):
     assert n == 35 and list(bbox) == [200, 200, 206, 204] and len(pix) == 35
     assert oracle.flood_component(ow, 150, 150)[0] == 0          # AIR seed
     assert oracle.flood_component(ow, 10, 10)[0] == 1001         # the solid border is larger than the cap
+
+
+def test_explosion_conserves_what_it_throws(oracle, table):
+    """world.cpp:2294-2332: inside the radius SOLID always vanishes and other cells vanish 6 times in 10; survivors and every
+    non-SOLID cell of the ring out to 2r leave as particles.  AIR afterwards inside r; SOLID untouched in the ring."""
+    from oracle import pyoracle as O
+    W = H = 256
+    ow = oracle.OracleWorld(W, H, table)
+    SAND, STONE, AIR = 2, 7, 0
+    mat = np.full((H, W), SAND, dtype=np.uint16)
+    mat[:, 128:] = STONE
+    cells = G.cells_from_mat(table, mat, 0, 0, 3)
+    ow.write_rect(0, 0, cells)
+    r = 20
+    O.explosion(ow, 128, 128, r, tick=5, seed=9)
+    after = ow.read_all()
+    parts = ow.particles_read()
+    ys, xs = np.mgrid[0:H, 0:W]
+    d2 = (xs - 128) ** 2 + (ys - 128) ** 2
+    sq = (np.abs(xs - 128 + 0.5) < 2 * r) & (np.abs(ys - 128 + 0.5) < 2 * r)  # the loop covers [c-2r, c+2r)
+    inner = d2 < r * r
+    ring = (~inner) & (d2 < 4 * r * r) & sq
+    assert (after["mat"][inner & sq] == AIR).all()
+    assert (after["mat"][ring & (mat == STONE)] == STONE).all()
+    assert (after["mat"][ring & (mat == SAND)] == AIR).all()
+    assert (after["mat"][~(inner | ring)] == mat[~(inner | ring)]).all()
+    n_ring = int((ring & (mat == SAND)).sum())
+    n_inner_sand = int((inner & sq & (mat == SAND)).sum())
+    n_parts = len(parts)
+    assert n_ring <= n_parts <= n_ring + n_inner_sand
+    kept = n_parts - n_ring
+    assert 0.3 * n_inner_sand < kept < 0.5 * n_inner_sand  # 4 in 10 survive as particles
+    assert (parts["tile"]["mat"] == SAND).all()
+    assert len(np.unique(parts["id"])) == n_parts

@@ -136,3 +136,24 @@ def test_flood_component_matches_oracle(oracle, gpu_ctx, table):
         assert no == ng, (x, y, no, ng)
         if 0 < no <= 1000:
             assert list(bo) == list(bg) and np.array_equal(po, pg), (x, y)
+
+
+def test_explosion_exact(oracle, gpu_ctx, table):
+    """fse_explosion vs the oracle restatement of world::explosion: identical grid, dirty flags and particle set."""
+    from oracle import pyoracle as O
+    W, H = 640, 512
+    tbl, extra = G.bench_table(table)
+    gpu_ctx.set_materials(tbl)
+    ow, gw = oracle.OracleWorld(W, H, tbl), fse.World(gpu_ctx, W, H)
+    Hh.build_mixed(ow, tbl, W, H, seed=21, extra=list(extra.values()), blob=16)
+    Hh.build_mixed(gw, tbl, W, H, seed=21, extra=list(extra.values()), blob=16)
+    for (cx, cy, r) in ((300, 250, 24), (10, 10, 12), (630, 500, 30)):  # the last two reach over the world border
+        O.explosion(ow, cx, cy, r, tick=3, seed=77)
+        gw.explosion(cx, cy, r, tick=3, seed=77)
+    Hh.assert_cells_equal(ow.read_all(), gw.read_all(), "explosion")
+    Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), "explosion particles")
+    for t in range(4):  # and the thrown particles land identically
+        ow.tick(t); gw.tick(t)
+        ow.particles_tick(); gw.particles_tick()
+    Hh.assert_cells_equal(ow.read_all(), gw.read_all(), "after explosion")
+    Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), "particles after explosion")

@@ -136,11 +136,13 @@ def test_particles_deposit_conflicts(oracle, gpu_ctx, table):
 STATE_FIELDS = ["mat", "moved", "settle", "color", "temp", "fluid", "fluid_diff"]
 
 
-def test_active_tracking_equals_full_sweep(oracle, gpu_ctx, table):
+@pytest.mark.parametrize("fused", ["0", "1"])  # per-pass kernels + state kernel / single fused kernel
+def test_active_tracking_equals_full_sweep(oracle, gpu_ctx, table, monkeypatch, fused):
     """chunk sleeping has no reference behaviour to match beyond 'same cells as a full sweep'.  A sparse
     world (sealed lenses of settled sand / water in rock + pockets of falling sand and water) is ticked with tracking
     on, with tracking off, and by the oracle: identical cell state every few ticks (dirty flags of sleeping chunks are
     not refreshed), and most chunks are asleep at the end."""
+    monkeypatch.setenv("FSE_ACTIVE_FUSED", fused)
     W, H = 1536, 1024
     cells = G.sparse_band(table, W, H, 0, H, seed=11, pockets=6)
     gpu_ctx.set_materials(table)
