@@ -236,6 +236,12 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_stats, dev_stats_bytes());
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
     if (const char* env = getenv("FSE_TICK_LPT")) w->lpt_on = atoi(env) != 0;
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        w->fused_max_chunks = 2 * sms;  // tick_rows_kernel: 2 CTAs per SM
+        if (const char* env = getenv("FSE_FUSED_MAX_CHUNKS")) w->fused_max_chunks = atoi(env);
+    }
     w->fork.parts = 3;
     w->fork.min_chunks = 256;
     if (const char* env = getenv("FSE_TICK_MIN_CHUNKS")) w->fork.min_chunks = std::max(1, atoi(env));
@@ -604,6 +610,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.schedule = w->schedule;
             P.dbg = w->d_dbg;
             P.fused = w->fused;
+            P.fused_max_chunks = w->fused_max_chunks;
             P.chunk_base = 0;
             P.chunk_cost = nullptr;
             P.chunk_state = nullptr;

@@ -129,6 +129,7 @@ struct TickParams {
     unsigned int* chunk_cost; // optional: pass 1 records the cycles each chunk took (cost[cyi * ncx + cxi]) for the next tick's ordering
     int chunk_base;         // first chunk (index into the phase's chunk grid or list) of this launch
     int fused;              // rows schedule: 1 = single fused kernel (all passes pipelined), 0 = one kernel per pass
+    int fused_max_chunks;   // rows schedule: phases of at most this many chunks run in the fused kernel anyway (one wave of it)
     int schedule;           // FSE_SCHEDULE_CLASSES (4 interleaved column classes) or FSE_SCHEDULE_ROWS (simultaneous rows)
 };
 

@@ -60,6 +60,7 @@ struct fse_world {
     int* d_active_list = nullptr;   // compacted (cxi | cyi << 16) of the phase being launched
     int* d_active_count = nullptr;
     unsigned int* d_chunk_state = nullptr;  // per-pass kernels: what the passes of the running phase saw in each chunk
+    int fused_max_chunks = 296;            // phases this small run in the fused kernel (FSE_FUSED_MAX_CHUNKS)
     bool active_fused = false;             // FSE_ACTIVE_FUSED=1: active-chunk phases use the fused kernel
     // longest-first chunk order of the per-pass tick kernels: per colour, last tick's pass-1 cycles and the list built from them
     unsigned int* d_lpt_cost = nullptr;

@@ -1099,7 +1099,10 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         configured = true;
     }
     if (n_chunks <= 0) return cudaSuccess;
-    if (P.schedule == FSE_SCHEDULE_ROWS && !P.fused && (!P.awake || P.chunk_state)) {  // one kernel per pass
+    // The fused kernel keeps 2 chunks per SM in flight and its chain is the longest pass, not the sum of the three: a phase that
+    // fits one wave of it (small worlds, the cut-adjacent chunk rows of a strip) is faster there.  Results are identical.
+    const bool small = !P.awake && n_chunks <= P.fused_max_chunks;
+    if (P.schedule == FSE_SCHEDULE_ROWS && !P.fused && !small && (!P.awake || P.chunk_state)) {  // one kernel per pass
         // The three passes of a chunk only depend on each other, so the phase is cut into parts that run on their own streams:
         // while the last pass-1 CTAs of one part drain, another part's pass 2 already fills the SMs (the kernels are latency
         // bound and a phase is only ~1.3 waves of CTAs).

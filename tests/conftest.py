@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# The library runs colour phases that fit one wave of the fused kernel in that kernel (small worlds).  The test worlds are all
+# that small, so force the per-pass kernels here ("rows" = per-pass, "rows_fused" = fused); one test removes the override.
+os.environ.setdefault("FSE_FUSED_MAX_CHUNKS", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -235,3 +235,17 @@ def test_phase_parts_and_longest_first_order_do_not_change_results(oracle, gpu_c
     Hh.build_mixed(ow, tbl, W, H, seed=5, extra=list(extra.values()))
     Hh.build_mixed(gw, tbl, W, H, seed=5, extra=list(extra.values()))
     _run_and_compare(ow, gw, 6, seed=3, what="parts + longest-first")
+
+
+def test_small_phases_pick_the_fused_kernel_with_identical_results(oracle, gpu_ctx, table, monkeypatch):
+    """Default kernel selection (no override): a 640x512 world has 2-3 chunks per colour phase, far below one wave of the fused
+    kernel, so the rows schedule runs there; results must not depend on the choice."""
+    monkeypatch.delenv("FSE_FUSED_MAX_CHUNKS", raising=False)
+    W, H = 640, 512
+    ow, gw = _pair(oracle, gpu_ctx, table, W, H, "rows")
+    Hh.build_mixed(ow, table, W, H, seed=17)
+    Hh.build_mixed(gw, table, W, H, seed=17)
+    _run_and_compare(ow, gw, 3, seed=5, what="automatic kernel choice")
+    n0 = gpu_ctx.launch_count()
+    gw.tick(3, seed=5)
+    assert gpu_ctx.launch_count() - n0 == 12  # one (fused) kernel per colour phase
