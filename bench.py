@@ -289,7 +289,10 @@ def run_ours(args):
         except Exception:
             traffic = None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "peak_source": peak_src, "kernel": KERNEL_OF.get(args.schedule, KERNEL_OF["default"]), "launches": k_launches,
+            "peak_source": peak_src,
+            "kernel": ("fse::tick_graph_kernel (one launch = one whole tick: 4 colours x cell_iter phases as a task graph over the chunks, passes 1-3 per chunk)"
+                       if k_launches == args.steps else KERNEL_OF.get(args.schedule, KERNEL_OF["default"])),
+            "launches": k_launches,
             "avg_launch_ms": k_ms / max(k_launches, 1),
             "algorithmic_bytes_per_launch": algo_bytes / max(k_launches, 1)}
 

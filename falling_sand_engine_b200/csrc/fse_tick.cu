@@ -1141,6 +1141,19 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
     return cudaGetLastError();
 }
 
+cudaError_t launch_tick_graph(const GraphParams& G, int grid, cudaStream_t stream) {
+    static bool configured = false;
+    constexpr size_t smem = sizeof(SmemPass<1>) > sizeof(SmemPass<2>) ? sizeof(SmemPass<1>) : sizeof(SmemPass<2>);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tick_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    graph_init_kernel<<<64, 256, 0, stream>>>(G);
+    tick_graph_kernel<<<grid, PassGeom<1>::THREADS, smem, stream>>>(G);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream) {
     lpt_build_kernel<<<1, 1024, 0, stream>>>(cost, n, ncx, list);
     return cudaGetLastError();

@@ -15,13 +15,28 @@ from tests import helpers as Hh
 pytestmark = pytest.mark.gpu
 
 
-SCHEDULES = {"rows": (1, 2), "rows_fused": (2, 2), "classes": (0, 1)}  # name -> (FSE_SCHEDULE_*, oracle Schedule)
+# name -> (FSE_SCHEDULE_*, oracle Schedule).  "rows" = one launch per pass and colour phase (default), "rows_graph" = the same
+# schedule with the whole tick as one task-graph launch (tick_graph_kernel, FSE_TICK_GRAPH=1)
+SCHEDULES = {"rows": (1, 2), "rows_graph": (1, 2), "rows_fused": (2, 2), "classes": (0, 1)}
+ALL_SCHEDULES = ["rows", "rows_graph", "rows_fused", "classes"]
 
 
 def _pair(oracle, gpu_ctx, table, W, H, sched="rows"):
     ow = oracle.OracleWorld(W, H, table)
     gpu_ctx.set_materials(table)
-    gw = fse.World(gpu_ctx, W, H)
+    import os
+
+    old = os.environ.get("FSE_TICK_GRAPH")
+    if sched == "rows_graph":
+        os.environ["FSE_TICK_GRAPH"] = "1"  # read by fse_world_create
+    try:
+        gw = fse.World(gpu_ctx, W, H)
+    finally:
+        if sched == "rows_graph":
+            if old is None:
+                del os.environ["FSE_TICK_GRAPH"]
+            else:
+                os.environ["FSE_TICK_GRAPH"] = old
     gw.set_schedule(SCHEDULES[sched][0])
     ow.default_schedule = SCHEDULES[sched][1]
     return ow, gw
@@ -51,7 +66,7 @@ def test_roundtrip_rect(oracle, gpu_ctx, table):
     Hh.assert_cells_equal(cells[33:83, 17:117], sub, "sub-rect")
 
 
-@pytest.mark.parametrize("sched", ["rows", "rows_fused", "classes"])
+@pytest.mark.parametrize("sched", ALL_SCHEDULES)
 def test_column_drop_exact(oracle, gpu_ctx, table, sched):
     W = H = 512
     ow, gw = _pair(oracle, gpu_ctx, table, W, H, sched)
@@ -60,7 +75,7 @@ def test_column_drop_exact(oracle, gpu_ctx, table, sched):
     _run_and_compare(ow, gw, 40, every=4, what="column")
 
 
-@pytest.mark.parametrize("sched", ["rows", "rows_fused", "classes"])
+@pytest.mark.parametrize("sched", ALL_SCHEDULES)
 def test_mixed_exact(oracle, gpu_ctx, table, sched):
     W = H = 512
     ow, gw = _pair(oracle, gpu_ctx, table, W, H, sched)
@@ -69,7 +84,7 @@ def test_mixed_exact(oracle, gpu_ctx, table, sched):
     _run_and_compare(ow, gw, 30, seed=7, every=3, what="mixed")
 
 
-@pytest.mark.parametrize("sched", ["rows", "rows_fused", "classes"])
+@pytest.mark.parametrize("sched", ALL_SCHEDULES)
 def test_mixed_interactions_exact(oracle, gpu_ctx, table, sched):
     W, H = 640, 512
     tbl, extra = G.bench_table(table)
@@ -235,6 +250,23 @@ def test_phase_parts_and_longest_first_order_do_not_change_results(oracle, gpu_c
     Hh.build_mixed(ow, tbl, W, H, seed=5, extra=list(extra.values()))
     Hh.build_mixed(gw, tbl, W, H, seed=5, extra=list(extra.values()))
     _run_and_compare(ow, gw, 6, seed=3, what="parts + longest-first")
+
+
+@pytest.mark.parametrize("ctas_per_sm", ["1", "5"])
+def test_tick_graph_kernel_exact_for_any_grid(oracle, gpu_ctx, table, monkeypatch, ctas_per_sm):
+    """The whole-tick task-graph launch: 12 phases x 16-25 chunks on a 1280^2 world, with 148 CTAs (every CTA pops many
+    tasks off the ready queue) and with more CTAs than tasks of a phase (most of them wait for a queue slot to be filled).
+    Same chunk-level order as the per-phase launches, so bit-exact against the oracle."""
+    monkeypatch.setenv("FSE_GRAPH_CTAS_PER_SM", ctas_per_sm)
+    W = H = 1280
+    tbl, extra = G.bench_table(table)
+    ow, gw = _pair(oracle, gpu_ctx, tbl, W, H, "rows_graph")
+    Hh.build_mixed(ow, tbl, W, H, seed=5, extra=list(extra.values()))
+    Hh.build_mixed(gw, tbl, W, H, seed=5, extra=list(extra.values()))
+    _run_and_compare(ow, gw, 6, seed=3, what="task graph")
+    n0 = gpu_ctx.launch_count()
+    gw.tick(6, seed=3)
+    assert gpu_ctx.launch_count() - n0 == 2  # queue initialisation + the tick kernel
 
 
 def test_small_phases_pick_the_fused_kernel_with_identical_results(oracle, gpu_ctx, table, monkeypatch):
