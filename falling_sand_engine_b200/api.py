@@ -6,6 +6,7 @@ the C ABI; if the shared library is missing or no CUDA device is present this mo
 no CPU fallback.
 """
 import ctypes as C
+import time
 import os
 
 import numpy as np
@@ -266,8 +267,10 @@ class World:
         mask_off = np.zeros(n + 1, dtype=np.int32)
         self.L.fse_mask_outline.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        t0 = time.perf_counter()
         _ck(self.L.fse_mask_outline(self.h, masks.ctypes.data, n, w, h, labels.ctypes.data, ncomp.ctypes.data, pts.ctypes.data, cap_pts,
                                     pt_off.ctypes.data, cap_c, mask_off.ctypes.data))
+        self.last_outline_s = time.perf_counter() - t0  # the C-ABI call alone (scripts/bench_bodies.py)
         contours = [[pts[pt_off[c]:pt_off[c + 1]].copy() for c in range(mask_off[m], mask_off[m + 1])] for m in range(n)]
         return labels, ncomp, contours
 

@@ -7,6 +7,11 @@
 // cells).  In a round, every pending pixel publishes its rank on its footprint cells with atomicMin; a pixel acts only if
 // it holds the minimum on all five, i.e. when no earlier pixel that could still change one of its cells is pending.  Pixels
 // that act in the same round have disjoint footprints, so the outcome equals the sequential loop.
+//
+// One launch per call: a CTA takes the next body (atomic ticket, so bodies start in index order), waits for the lower-index
+// bodies whose footprint box overlaps its own to finish — bodies that do not overlap commute, overlapping ones keep the
+// reference's body order — and then runs the rounds of its own pixels between block barriers, with the claim map of its
+// footprint box in shared memory (boxes up to 64x64 cells; larger bodies use a claim plane in global memory).
 #include <cmath>
 #include <vector>
 
@@ -37,22 +42,11 @@ struct BodyArgs {
     uint8_t* awake;
     int acols, arows;
     int n_pixels;
+    int4* aabb;              // per body: footprint box (x0, y0, x1, y1), inclusive
+    unsigned int* done;      // per body: 1 once all its pixels have acted
+    unsigned int* ticket;    // [0] next body, [1] most rounds any body needed
 };
 
-// rank -> (body, tx, ty) in the reference's visiting order (tx outer, ty inner)
-__device__ __forceinline__ bool locate(const BodyArgs& a, int r, int& b, int& tx, int& ty) {
-    int lo = 0, hi = a.n_bodies - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (a.off[mid] <= r) lo = mid;
-        else hi = mid - 1;
-    }
-    b = lo;
-    const int o = r - a.off[b];
-    tx = o / a.bh[b];
-    ty = o % a.bh[b];
-    return true;
-}
 __device__ __forceinline__ void world_pos(const BodyArgs& a, int b, int tx, int ty, int& wx, int& wy) {
     const float4 t = a.xf[b];  // x, y, s, c
     wx = (int)(tx * t.w - (ty + 1) * t.z + t.x);  // game.cpp:1763
@@ -60,32 +54,24 @@ __device__ __forceinline__ void world_pos(const BodyArgs& a, int b, int tx, int 
 }
 __constant__ int c_dirs[5][2] = {{0, 0}, {1, 0}, {-1, 0}, {0, 1}, {0, -1}};  // game.cpp:1766
 
-__global__ void bodies_init_kernel(BodyArgs a) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n_pixels) return;
-    int b, tx, ty;
-    locate(a, r, b, tx, ty);
-    const bool live = a.tiles[a.off[b] + tx + ty * a.bw[b]].mat != a.air;
-    a.pending[r] = live ? 1 : 0;
-    if (live) atomicAdd(&a.counters[4], 1u);
-}
-
-__global__ void bodies_mark_kernel(BodyArgs a, int reset) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n_pixels || !a.pending[r]) return;
-    if (reset && a.pending[r] == 2) {  // acted in the round that just ended: free its footprint, then retire
-        a.pending[r] = 0;
+// footprint box of a body: every candidate cell of every pixel, with one cell of slack for the float -> int truncation
+__global__ void bodies_aabb_kernel(BodyArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) a.ticket[0] = a.ticket[1] = 0;
+    if (b >= a.n_bodies) return;
+    const float4 t = a.xf[b];
+    float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f;
+    for (int q = 0; q < 4; q++) {
+        const float tx = (q & 1) ? (float)(a.bw[b] - 1) : 0.0f, ty1 = (q & 2) ? (float)a.bh[b] : 1.0f;
+        const float fx = tx * t.w - ty1 * t.z + t.x, fy = tx * t.z + ty1 * t.w + t.y;
+        x0 = fminf(x0, fx); x1 = fmaxf(x1, fx);
+        y0 = fminf(y0, fy); y1 = fmaxf(y1, fy);
     }
-    int b, tx, ty, wx, wy;
-    locate(a, r, b, tx, ty);
-    world_pos(a, b, tx, ty, wx, wy);
-#pragma unroll
-    for (int d = 0; d < 5; d++) {
-        const int x = wx + c_dirs[d][0], y = wy + c_dirs[d][1];
-        if (x < 0 || y < 0 || x >= a.W || y >= a.H) continue;
-        if (reset) a.claim[(size_t)y * a.W + x] = 0xffffffffu;
-        else atomicMin(&a.claim[(size_t)y * a.W + x], (uint32_t)r);
-    }
+    const float lim = 1.0e9f;
+    x0 = fmaxf(fminf(x0, lim), -lim); x1 = fmaxf(fminf(x1, lim), -lim);
+    y0 = fmaxf(fminf(y0, lim), -lim); y1 = fmaxf(fminf(y1, lim), -lim);
+    a.aabb[b] = make_int4((int)floorf(x0) - 3, (int)floorf(y0) - 3, (int)ceilf(x1) + 3, (int)ceilf(y1) + 3);
+    a.done[b] = 0;
 }
 
 __device__ __forceinline__ void wake3x3(const BodyArgs& a, int x, int y) {
@@ -109,46 +95,37 @@ __device__ __forceinline__ void write_cell(const BodyArgs& a, size_t g, const fs
 }
 __device__ __forceinline__ fse_cell read_cell(const BodyArgs& a, size_t g) {
     fse_cell c;
-    const uint8_t f = a.p.flg[g];
-    c.mat = a.p.mat[g];
+    const uint8_t f = __ldcg(a.p.flg + g);
+    c.mat = __ldcg(a.p.mat + g);
     c.moved = (f & F_MOVED) ? 1 : 0;
-    c.settle = a.p.stl[g];
-    c.color = a.p.col[g];
-    c.temp = a.p.tmp[g];
+    c.settle = __ldcg(a.p.stl + g);
+    c.color = __ldcg(a.p.col + g);
+    c.temp = __ldcg(a.p.tmp + g);
     c.dirty = 0;
     c._pad = 0;
-    c.fluid = a.p.fl[g];
-    c.fluid_diff = a.p.fd[g];
+    c.fluid = __ldcg(a.p.fl + g);
+    c.fluid_diff = __ldcg(a.p.fd + g);
     return c;
 }
 
+__device__ __forceinline__ unsigned int bodies_ld_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// one pixel acts (game.cpp:1768-1811 raster, 1918-1965 erase); grid cells are read at L2 (another SM may have written them)
 template <bool ERASE>
-__global__ void bodies_act_kernel(BodyArgs a) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n_pixels || a.pending[r] != 1) return;
-    int b, tx, ty, wx, wy;
-    locate(a, r, b, tx, ty);
-    world_pos(a, b, tx, ty, wx, wy);
-    bool mine = true;
-#pragma unroll
-    for (int d = 0; d < 5; d++) {
-        const int x = wx + c_dirs[d][0], y = wy + c_dirs[d][1];
-        if (x < 0 || y < 0 || x >= a.W || y >= a.H) continue;
-        mine &= a.claim[(size_t)y * a.W + x] == (uint32_t)r;
-    }
-    if (!mine) {
-        atomicAdd(&a.counters[5], 1u);  // still pending after this round
-        return;
-    }
+__device__ __forceinline__ void body_pixel_act(const BodyArgs& a, int b, int tx, int ty, int wx, int wy) {
     fse_cell* tile = &a.tiles[a.off[b] + tx + ty * a.bw[b]];
     const fse_cell rm = *tile;
     int4* fb = &a.feedback[b];
     if (!ERASE) {
-        for (int d = 0; d < 5; d++) {  // game.cpp:1768-1811
+        for (int d = 0; d < 5; d++) {
             const int x = wx + c_dirs[d][0], y = wy + c_dirs[d][1];
             if (x < 0 || y < 0 || x >= a.W || y >= a.H) continue;
             const size_t g = (size_t)y * a.W + x;
-            const int ph = a.T->phys[a.p.mat[g]];
+            const int ph = a.T->phys[__ldcg(a.p.mat + g)];
             if (ph == P_AIR) {
                 write_cell(a, g, rm);
                 atomicAdd(&fb->z, 1);
@@ -180,11 +157,11 @@ __global__ void bodies_act_kernel(BodyArgs a) {
         }
     } else {
         bool found = false;
-        for (int d = 0; d < 5; d++) {  // game.cpp:1918-1957
+        for (int d = 0; d < 5; d++) {
             const int x = wx + c_dirs[d][0], y = wy + c_dirs[d][1];
             if (x < 0 || y < 0 || x >= a.W || y >= a.H) continue;
             const size_t g = (size_t)y * a.W + x;
-            if (a.p.mat[g] == rm.mat) {  // .id == rmat.id (any cell of the same material)
+            if (__ldcg(a.p.mat + g) == rm.mat) {  // .id == rmat.id (any cell of the same material)
                 *tile = read_cell(a, g);
                 fse_cell nothing;
                 memset(&nothing, 0, sizeof nothing);
@@ -197,7 +174,7 @@ __global__ void bodies_act_kernel(BodyArgs a) {
                 break;
             }
         }
-        if (!found && wx >= 0 && wy >= 0 && wx < a.W && wy < a.H && a.p.mat[(size_t)wy * a.W + wx] == a.air) {  // 1959-1965
+        if (!found && wx >= 0 && wy >= 0 && wx < a.W && wy < a.H && __ldcg(a.p.mat + (size_t)wy * a.W + wx) == a.air) {  // 1959-1965
             fse_cell nothing;
             memset(&nothing, 0, sizeof nothing);
             nothing.mat = (uint16_t)a.air;
@@ -206,7 +183,98 @@ __global__ void bodies_act_kernel(BodyArgs a) {
             atomicAdd(&fb->w, 1);
         }
     }
-    a.pending[r] = 2;  // acted; its footprint is released by the reset pass
+}
+
+constexpr int BODY_TB = 256;
+constexpr int BODY_SCLAIM = 64 * 64;  // cells of a footprint box whose claim map fits shared memory
+
+template <bool ERASE>
+__global__ void __launch_bounds__(BODY_TB) bodies_body_kernel(BodyArgs a) {
+    __shared__ uint32_t s_claim[BODY_SCLAIM];
+    __shared__ int s_b;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_b = (int)atomicAdd(&a.ticket[0], 1u);
+    __syncthreads();
+    const int b = s_b;
+    if (b >= a.n_bodies) return;
+    const int4 box = a.aabb[b];
+    const int bwid = a.bw[b], bhei = a.bh[b], npix = bwid * bhei, off = a.off[b];
+    // the reference's body order matters only between bodies that can touch the same cells
+    for (int j = tid; j < b; j += BODY_TB) {
+        const int4 o = a.aabb[j];
+        if (o.x <= box.z && box.x <= o.z && o.y <= box.w && box.y <= o.w)
+            while (bodies_ld_acquire(a.done + j) == 0u) __nanosleep(100);
+    }
+    __threadfence();
+    const int aw = box.z - box.x + 1, ah = box.w - box.y + 1;
+    const bool smem = (long long)aw * ah <= BODY_SCLAIM;
+    if (smem)
+        for (int i = tid; i < aw * ah; i += BODY_TB) s_claim[i] = 0xffffffffu;
+    for (int o = tid; o < npix; o += BODY_TB) {
+        const int tx = o / bhei, ty = o % bhei;
+        a.pending[off + o] = a.tiles[off + tx + ty * bwid].mat != a.air ? 1 : 0;
+    }
+    __syncthreads();
+    // claim word of world cell (x, y); cells outside the world are never claimed
+    auto claim_at = [&](int x, int y) -> uint32_t* {
+        return smem ? &s_claim[(y - box.y) * aw + (x - box.x)] : &a.claim[(size_t)y * a.W + x];
+    };
+    int rounds = 0;
+    for (;;) {
+        bool any = false;
+        for (int o = tid; o < npix; o += BODY_TB) {  // pending pixels publish their rank on their footprint
+            if (!a.pending[off + o]) continue;
+            any = true;
+            int wx, wy;
+            world_pos(a, b, o / bhei, o % bhei, wx, wy);
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                const int x = wx + c_dirs[d][0], y = wy + c_dirs[d][1];
+                if (x < 0 || y < 0 || x >= a.W || y >= a.H) continue;
+                atomicMin(claim_at(x, y), (uint32_t)o);
+            }
+        }
+        if (!__syncthreads_or(any)) break;
+        rounds++;
+        for (int o = tid; o < npix; o += BODY_TB) {  // a pixel that holds all five cells acts
+            if (!a.pending[off + o]) continue;
+            const int tx = o / bhei, ty = o % bhei;
+            int wx, wy;
+            world_pos(a, b, tx, ty, wx, wy);
+            bool mine = true;
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                const int x = wx + c_dirs[d][0], y = wy + c_dirs[d][1];
+                if (x < 0 || y < 0 || x >= a.W || y >= a.H) continue;
+                mine &= (smem ? *claim_at(x, y) : __ldcg(claim_at(x, y))) == (uint32_t)o;
+            }
+            if (!mine) continue;
+            body_pixel_act<ERASE>(a, b, tx, ty, wx, wy);
+            a.pending[off + o] = 2;
+        }
+        __syncthreads();
+        for (int o = tid; o < npix; o += BODY_TB) {  // footprints are released; pixels that acted retire
+            const uint8_t st = a.pending[off + o];
+            if (!st) continue;
+            if (st == 2) a.pending[off + o] = 0;
+            int wx, wy;
+            world_pos(a, b, o / bhei, o % bhei, wx, wy);
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                const int x = wx + c_dirs[d][0], y = wy + c_dirs[d][1];
+                if (x < 0 || y < 0 || x >= a.W || y >= a.H) continue;
+                *claim_at(x, y) = 0xffffffffu;
+            }
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicMax(&a.ticket[1], (unsigned int)rounds);
+        __threadfence();
+        atomicExch(a.done + b, 1u);
+    }
 }
 
 }  // namespace fse
@@ -228,10 +296,14 @@ struct fse_bodies {
     uint8_t* d_pending = nullptr;
     uint32_t* d_claim = nullptr;
     int4* d_feedback = nullptr;
+    int4* d_aabb = nullptr;
+    unsigned int* d_done = nullptr;  // [n] done flags, then the ticket and the round maximum
+    bool big = false;                // some body's footprint box may exceed the shared-memory claim map: claim plane in global memory
     void release() {
         cudaFree(d_off); cudaFree(d_bw); cudaFree(d_bh); cudaFree(d_tiles); cudaFree(d_xf); cudaFree(d_pending); cudaFree(d_claim);
-        cudaFree(d_feedback);
+        cudaFree(d_feedback); cudaFree(d_aabb); cudaFree(d_done);
         d_off = d_bw = d_bh = nullptr; d_tiles = nullptr; d_xf = nullptr; d_pending = nullptr; d_claim = nullptr; d_feedback = nullptr;
+        d_aabb = nullptr; d_done = nullptr;
     }
 };
 
@@ -254,6 +326,7 @@ extern "C" FSE_API int fse_bodies_upload(fse_world* w, const fse_body_desc* bodi
     B->release();
     B->d_claim = keep_claim;
     B->n = n;
+    B->big = false;
     B->off.assign(n + 1, 0);
     B->bw.resize(n);
     B->bh.resize(n);
@@ -263,6 +336,8 @@ extern "C" FSE_API int fse_bodies_upload(fse_world* w, const fse_body_desc* bodi
         B->bw[i] = bodies[i].w;
         B->bh[i] = bodies[i].h;
         B->off[i + 1] = B->off[i] + bodies[i].w * bodies[i].h;
+        const double side = std::ceil(std::hypot((double)bodies[i].w, (double)bodies[i].h + 1.0)) + 8.0;  // bound of bodies_aabb_kernel's box
+        if (side * side > (double)BODY_SCLAIM) B->big = true;
     }
     B->n_pixels = B->off[n];
     if (n == 0) return FSE_OK;
@@ -275,7 +350,9 @@ extern "C" FSE_API int fse_bodies_upload(fse_world* w, const fse_body_desc* bodi
     CK(cudaMalloc(&B->d_xf, sizeof(float4) * n));
     CK(cudaMalloc(&B->d_pending, (size_t)B->n_pixels));
     CK(cudaMalloc(&B->d_feedback, sizeof(int4) * n));
-    if (!B->d_claim) {
+    CK(cudaMalloc(&B->d_aabb, sizeof(int4) * n));
+    CK(cudaMalloc(&B->d_done, sizeof(unsigned int) * (n + 2)));
+    if (B->big && !B->d_claim) {
         CK(cudaMalloc(&B->d_claim, sizeof(uint32_t) * (size_t)w->W * w->H));
         CK(cudaMemsetAsync(B->d_claim, 0xff, sizeof(uint32_t) * (size_t)w->W * w->H, w->stream));
     }
@@ -297,35 +374,25 @@ static int run_bridge(fse_world* w, const fse_xform* xf, int32_t n, uint32_t tic
     for (int i = 0; i < n; i++) h[i] = make_float4(xf[i].x, xf[i].y, std::sin(xf[i].angle), std::cos(xf[i].angle));  // game.cpp:1763-1764 on the host's libm
     CK(cudaMemcpyAsync(B->d_xf, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, w->stream));
     CK(cudaMemsetAsync(B->d_feedback, 0, sizeof(int4) * n, w->stream));
-    CK(cudaMemsetAsync(w->pcount + 4, 0, 2 * sizeof(unsigned int), w->stream));
     BodyArgs a;
     a.p = w->p; a.T = w->ctx->d_tabs; a.W = w->W; a.H = w->H;
     a.n_bodies = n; a.off = B->d_off; a.bw = B->d_bw; a.bh = B->d_bh; a.tiles = B->d_tiles; a.xf = B->d_xf;
-    a.pending = B->d_pending; a.claim = B->d_claim; a.counters = w->pcount; a.feedback = B->d_feedback;
+    a.pending = B->d_pending; a.claim = B->d_claim; a.counters = nullptr; a.feedback = B->d_feedback;
     a.pbuf = w->pbuf; a.pcount = w->pcount; a.pcap = w->pcap;
     a.rkey = rng_key(seed, tick, 7); a.tick = tick; a.air = w->ctx->h_tabs.air;
     a.awake = w->active_on ? w->d_awake : nullptr; a.acols = w->acols; a.arows = w->arows;
     a.n_pixels = B->n_pixels;
-    const int TB = 256, G = (B->n_pixels + TB - 1) / TB;
-    bodies_init_kernel<<<G, TB, 0, w->stream>>>(a);
+    a.aabb = B->d_aabb; a.done = B->d_done; a.ticket = B->d_done + n;
+    bodies_aabb_kernel<<<(n + 127) / 128, 128, 0, w->stream>>>(a);
+    bodies_body_kernel<ERASE><<<n, BODY_TB, 0, w->stream>>>(a);
     CK(cudaGetLastError());
-    w->ctx->launches += 1;
-    unsigned int pending = 0;
-    CK(cudaMemcpyAsync(&pending, w->pcount + 4, sizeof pending, cudaMemcpyDeviceToHost, w->stream));
-    CK(cudaStreamSynchronize(w->stream));
-    int rounds = 0;
-    while (pending > 0) {
-        if (++rounds > 100000) return fail(FSE_ESTATE, "bodies: dependency rounds did not converge");
-        CK(cudaMemsetAsync(w->pcount + 5, 0, sizeof(unsigned int), w->stream));
-        bodies_mark_kernel<<<G, TB, 0, w->stream>>>(a, 0);
-        bodies_act_kernel<ERASE><<<G, TB, 0, w->stream>>>(a);
-        bodies_mark_kernel<<<G, TB, 0, w->stream>>>(a, 1);
-        CK(cudaGetLastError());
-        w->ctx->launches += 3;
-        CK(cudaMemcpyAsync(&pending, w->pcount + 5, sizeof pending, cudaMemcpyDeviceToHost, w->stream));
+    w->ctx->launches += 2;
+    if (out) {  // the feedback read below joins the stream anyway: report the rounds of the slowest body with it
+        unsigned int rounds = 0;
+        CK(cudaMemcpyAsync(&rounds, B->d_done + n + 1, sizeof rounds, cudaMemcpyDeviceToHost, w->stream));
         CK(cudaStreamSynchronize(w->stream));
+        w->last_bridge_rounds = (int)rounds;
     }
-    w->last_bridge_rounds = rounds;
     if (out) {
         std::vector<int4> fb(n);
         CK(cudaMemcpy(fb.data(), B->d_feedback, sizeof(int4) * n, cudaMemcpyDeviceToHost));

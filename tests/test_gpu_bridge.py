@@ -53,6 +53,34 @@ def test_raster_erase_exact_and_sequential_order(oracle, gpu_ctx, table):
         xf[:, 2] += 0.05
 
 
+def test_large_bodies_use_the_global_claim_plane(oracle, gpu_ctx, table):
+    """Bodies whose footprint box exceeds the 64x64 shared-memory claim map (here 70x60 and 90x40) run their rounds on the claim
+    plane in global memory; they overlap each other and two small bodies, so body order and both claim paths are exercised."""
+    W, H = 768, 640
+    gpu_ctx.set_materials(table)
+    gw, ow = fse.World(gpu_ctx, W, H), oracle.OracleWorld(W, H, table)
+    cells = G.mixed_band(table, W, H, 0, H, seed=5, air_frac=0.6, blob=48)
+    bodies = [make_body(table, 20, 24, seed=1, fill=0.8), make_body(table, 70, 60, seed=2, fill=0.7), make_body(table, 90, 40, seed=3, fill=1.0),
+              make_body(table, 16, 16, seed=4, fill=1.0)]
+    xf = np.array([(300.0, 300.0, 0.3), (310.0, 290.0, -0.7), (330.0, 320.0, 1.9), (335.0, 300.0, 0.0)], dtype=np.float32)
+    for w in (gw, ow):
+        w.write_rect(0, 0, cells)
+    ob = [b.copy() for b in bodies]
+    gw.bodies_upload(bodies)
+    for tick in range(2):
+        assert np.array_equal(oracle.bodies_raster(ow, ob, xf, tick=tick), gw.bodies_raster(xf, tick=tick))
+        Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"raster {tick}")
+        Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), f"raster {tick}")
+        fe_o = oracle.bodies_erase(ow, ob, xf)
+        fe_g, _ = gw.bodies_erase(xf)
+        assert np.array_equal(fe_o, fe_g)
+        Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"erase {tick}")
+        for i in range(len(bodies)):
+            assert gw.bodies_read(i).tobytes() == ob[i].tobytes(), (tick, i)
+        xf[:, 1] += 2.0
+        xf[:, 2] += 0.11
+
+
 def test_round_trip_identity_on_empty_grid(gpu_ctx, table):
     W = H = 384
     gpu_ctx.set_materials(table)
