@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=8192, help="world width (and per-GPU strip height)")
+    ap.add_argument("--height", type=int, default=0, help="world height (per-GPU strip height with --gpus N); 0 = --size")
     ap.add_argument("--workload", default="mixed", choices=["mixed", "column", "sparse"])
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -217,14 +218,15 @@ def run_ours(args):
     table, extra = make_table()
     ctx = fse.Context(local_rank, table)
     W = args.size
+    rows = args.height or args.size
     if world_size > 1:
         from falling_sand_engine_b200 import strips
 
-        Htot = 2 * T.FSE_CHUNK + (args.size - 2 * T.FSE_CHUNK) * world_size  # fixed tickZone rows per GPU ("weak")
+        Htot = 2 * T.FSE_CHUNK + (rows - 2 * T.FSE_CHUNK) * world_size  # fixed tickZone rows per GPU ("weak")
         world = strips.StripWorld(ctx, W, Htot, rank, world_size, dist)
         H = Htot
     else:
-        H = args.size
+        H = rows
         world = fse.World(ctx, W, H)
     zone_cells_total = (W - 2 * T.FSE_CHUNK) * (H - 2 * T.FSE_CHUNK)
     world.particles_reserve(1 << 25)
