@@ -13,6 +13,8 @@
 // reference's body order — and then runs the rounds of its own pixels between block barriers, with the claim map of its
 // footprint box in shared memory (boxes up to 64x64 cells; larger bodies use a claim plane in global memory).
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "fse_internal.hpp"
@@ -57,7 +59,7 @@ __constant__ int c_dirs[5][2] = {{0, 0}, {1, 0}, {-1, 0}, {0, 1}, {0, -1}};  // 
 // footprint box of a body: every candidate cell of every pixel, with one cell of slack for the float -> int truncation
 __global__ void bodies_aabb_kernel(BodyArgs a) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b == 0) a.ticket[0] = a.ticket[1] = 0;
+    if (b == 0) a.ticket[0] = a.ticket[1] = a.ticket[2] = a.ticket[3] = a.ticket[4] = a.ticket[5] = 0;
     if (b >= a.n_bodies) return;
     const float4 t = a.xf[b];
     float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f;
@@ -116,7 +118,7 @@ __device__ __forceinline__ unsigned int bodies_ld_acquire(const unsigned int* p)
 
 // one pixel acts (game.cpp:1768-1811 raster, 1918-1965 erase); grid cells are read at L2 (another SM may have written them)
 template <bool ERASE>
-__device__ __forceinline__ void body_pixel_act(const BodyArgs& a, int b, int tx, int ty, int wx, int wy) {
+__device__ __noinline__ void body_pixel_act(const BodyArgs& a, int b, int tx, int ty, int wx, int wy) {
     fse_cell* tile = &a.tiles[a.off[b] + tx + ty * a.bw[b]];
     const fse_cell rm = *tile;
     int4* fb = &a.feedback[b];
@@ -185,11 +187,108 @@ __device__ __forceinline__ void body_pixel_act(const BodyArgs& a, int b, int tx,
     }
 }
 
-constexpr int BODY_TB = 256;
+// release the higher-rank neighbours of body pixel (tx, ty) whose footprint meets its own (bit order: see the fast path below)
+__device__ __forceinline__ void body_release(int* s_cnt, uint32_t dep, int tx, int ty, int bhei) {
+    int bit = 0;
+    for (int dx = 0; dx <= 3; dx++)
+        for (int dy = (dx == 0 ? 1 : -3); dy <= 3; dy++, bit++)
+            if ((dep >> bit) & 1u) atomicSub(&s_cnt[(tx + dx) * bhei + ty + dy], 1);
+}
+
+// body_pixel_act for the fast path: the material plane of the footprint box is staged in shared memory (s_mat), so a pixel
+// decides without a trip to HBM and its neighbours are released as soon as its stores are issued; the full cell is only read
+// from the grid where the reference copies it (displaced sand / liquid, erased pixels).
+template <bool ERASE>
+__device__ __noinline__ void body_pixel_act_fast(const BodyArgs& a, int b, int tx, int ty, int lx, int ly, int4 box, int aw, uint8_t* s_mat,
+                                                 int* s_cnt, uint32_t dep, int bhei) {
+    fse_cell* tile = &a.tiles[a.off[b] + tx + ty * a.bw[b]];
+    const fse_cell rm = *tile;
+    int4* fb = &a.feedback[b];
+    const int wx = lx + box.x, wy = ly + box.y;
+    if (!ERASE) {
+        for (int d = 0; d < 5; d++) {
+            const int x = wx + c_dirs[d][0], y = wy + c_dirs[d][1];
+            if (x < 0 || y < 0 || x >= a.W || y >= a.H) continue;
+            uint8_t* sm = &s_mat[(ly + c_dirs[d][1]) * aw + lx + c_dirs[d][0]];
+            const size_t g = (size_t)y * a.W + x;
+            const int ph = a.T->phys[*sm];
+            if (ph == P_AIR) {
+                write_cell(a, g, rm);
+                *sm = (uint8_t)rm.mat;
+                atomicAdd(&fb->z, 1);
+                wake3x3(a, x, y);
+                break;
+            } else if (ph == P_SAND || ph == P_SOUP) {
+                const unsigned int i = atomicAdd(a.pcount, 1u);
+                if (i < a.pcap) {  // the displaced cell is thrown up as a loose particle (game.cpp:1791 / 1801)
+                    fse_particle p;
+                    memset(&p, 0, sizeof p);
+                    p.tile = read_cell(a, g);
+                    p.x = (float)x;
+                    p.y = (float)(y - 3);
+                    const int pix = tx + ty * a.bw[b];
+                    const uint32_t cb = rng_cell(a.rkey, b, pix);
+                    p.vx = (float)(((int)(rng_draw(cb, S_BRIDGE_VX) % 10) - 5) / 10.0f);
+                    p.vy = (float)(-(int)(rng_draw(cb, S_BRIDGE_VY) % 5 + 5) / 10.0f);
+                    p.ay = 0.1f;
+                    p.fade_time = 60;
+                    p.id = (2ULL << 62) | ((uint64_t)(a.tick & 0xffff) << 40) | ((uint64_t)(b & 0xfffff) << 20) | (uint64_t)(pix & 0xfffff);
+                    a.pbuf[i] = p;
+                }
+                write_cell(a, g, rm);
+                *sm = (uint8_t)rm.mat;
+                atomicAdd(ph == P_SAND ? &fb->x : &fb->y, 1);
+                atomicAdd(&fb->z, 1);
+                wake3x3(a, x, y);
+                break;
+            }
+        }
+        __threadfence_block();
+        body_release(s_cnt, dep, tx, ty, bhei);
+    } else {
+        bool found = false;
+        fse_cell got;
+        for (int d = 0; d < 5; d++) {
+            const int x = wx + c_dirs[d][0], y = wy + c_dirs[d][1];
+            if (x < 0 || y < 0 || x >= a.W || y >= a.H) continue;
+            uint8_t* sm = &s_mat[(ly + c_dirs[d][1]) * aw + lx + c_dirs[d][0]];
+            if (*sm == rm.mat) {  // .id == rmat.id (any cell of the same material)
+                const size_t g = (size_t)y * a.W + x;
+                got = read_cell(a, g);
+                fse_cell nothing;
+                memset(&nothing, 0, sizeof nothing);
+                nothing.mat = (uint16_t)a.air;
+                nothing.fluid = 2.0f;
+                write_cell(a, g, nothing);
+                *sm = (uint8_t)a.air;
+                atomicAdd(&fb->z, 1);
+                wake3x3(a, x, y);
+                found = true;
+                break;
+            }
+        }
+        const bool lost = !found && wx >= 0 && wy >= 0 && wx < a.W && wy < a.H && s_mat[ly * aw + lx] == a.air;  // 1959-1965
+        __threadfence_block();
+        body_release(s_cnt, dep, tx, ty, bhei);
+        if (found) {
+            *tile = got;  // waits for the cell's loads; the neighbours are already on their way
+        } else if (lost) {
+            fse_cell nothing;
+            memset(&nothing, 0, sizeof nothing);
+            nothing.mat = (uint16_t)a.air;
+            nothing.fluid = 2.0f;
+            *tile = nothing;
+            atomicAdd(&fb->w, 1);
+        }
+    }
+}
+
+constexpr int BODY_TB = 128;
+constexpr int BODY_PPT = 8;   // pixels per thread kept in registers (bodies up to BODY_TB * BODY_PPT pixels)
 constexpr int BODY_SCLAIM = 64 * 64;  // cells of a footprint box whose claim map fits shared memory
 
 template <bool ERASE>
-__global__ void __launch_bounds__(BODY_TB) bodies_body_kernel(BodyArgs a) {
+__global__ void __launch_bounds__(BODY_TB, 8) bodies_body_kernel(BodyArgs a) {
     __shared__ uint32_t s_claim[BODY_SCLAIM];
     __shared__ int s_b;
     const int tid = threadIdx.x;
@@ -197,6 +296,7 @@ __global__ void __launch_bounds__(BODY_TB) bodies_body_kernel(BodyArgs a) {
     __syncthreads();
     const int b = s_b;
     if (b >= a.n_bodies) return;
+
     const int4 box = a.aabb[b];
     const int bwid = a.bw[b], bhei = a.bh[b], npix = bwid * bhei, off = a.off[b];
     // the reference's body order matters only between bodies that can touch the same cells
@@ -206,9 +306,14 @@ __global__ void __launch_bounds__(BODY_TB) bodies_body_kernel(BodyArgs a) {
             while (bodies_ld_acquire(a.done + j) == 0u) __nanosleep(100);
     }
     __threadfence();
+#ifdef FSE_BODIES_CYCLES  // profiling aid: cycles of the setup and of the rounds, summed over bodies (FSE_BODIES_DEBUG=1 prints them)
+    __syncthreads();
+    long long c1 = clock64();
+#endif
     const int aw = box.z - box.x + 1, ah = box.w - box.y + 1;
     const bool smem = (long long)aw * ah <= BODY_SCLAIM;
-    if (smem)
+    const bool fast = smem && npix <= BODY_TB * BODY_PPT;
+    if (smem && !fast)
         for (int i = tid; i < aw * ah; i += BODY_TB) s_claim[i] = 0xffffffffu;
     for (int o = tid; o < npix; o += BODY_TB) {
         const int tx = o / bhei, ty = o % bhei;
@@ -220,6 +325,80 @@ __global__ void __launch_bounds__(BODY_TB) bodies_body_kernel(BodyArgs a) {
         return smem ? &s_claim[(y - box.y) * aw + (x - box.x)] : &a.claim[(size_t)y * a.W + x];
     };
     int rounds = 0;
+    if (fast) {
+        // common case (bodies up to 1024 pixels, box up to 64x64).  Two footprints share a cell exactly when their centres are at
+        // Manhattan distance <= 2, and two body pixels can only land that close when they are less than 4 apart in the body
+        // (rotation keeps the distance, truncation moves a coordinate by < 1): every pixel counts the live lower-rank pixels of
+        // its 7x7 body neighbourhood whose footprint meets its own, acts when that count is 0 — all earlier pixels that could
+        // still change one of its cells are done, the same condition as holding the minimum on all five cells — and then
+        // releases its higher-rank neighbours.  No claim map, one counter read per pending pixel and round.
+        uint32_t* s_pos = s_claim;                                  // x | y << 8 inside the box, bit 16 live
+        int* s_cnt = reinterpret_cast<int*>(s_claim + BODY_TB * BODY_PPT);
+        uint8_t* s_mat = reinterpret_cast<uint8_t*>(s_claim + 2 * BODY_TB * BODY_PPT);  // material plane of the box (<= 64 x 64 bytes)
+        for (int i = tid; i < aw * ah; i += BODY_TB) {
+            const int x = box.x + i % aw, y = box.y + i / aw;
+            s_mat[i] = (x >= 0 && y >= 0 && x < a.W && y < a.H) ? __ldcg(a.p.mat + (size_t)y * a.W + x) : (uint8_t)0;
+        }
+        const float4 t = a.xf[b];
+        uint32_t px[BODY_PPT], dep[BODY_PPT];  // px: position | state << 16 (1 pending, 0 done or dead); dep: higher-rank neighbours to release
+#pragma unroll
+        for (int k = 0; k < BODY_PPT; k++) {
+            const int o = tid + k * BODY_TB;
+            px[k] = dep[k] = 0;
+            if (o < npix) {
+                const int tx = o / bhei, ty = o % bhei;
+                const int wx = (int)(tx * t.w - (ty + 1) * t.z + t.x);  // game.cpp:1763
+                const int wy = (int)(tx * t.z + (ty + 1) * t.w + t.y);  // game.cpp:1764
+                px[k] = (uint32_t)(wx - box.x) | ((uint32_t)(wy - box.y) << 8) | ((uint32_t)a.pending[off + o] << 16);
+                s_pos[o] = px[k];
+                s_cnt[o] = 0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BODY_PPT; k++) {
+            if (!(px[k] >> 16)) continue;
+            const int o = tid + k * BODY_TB;
+            const int tx = o / bhei, ty = o % bhei;
+            const int lx = px[k] & 0xff, ly = (px[k] >> 8) & 0xff;
+            int lower = 0, bit = 0;
+            for (int dx = -3; dx <= 3; dx++)
+                for (int dy = -3; dy <= 3; dy++) {
+                    if (dx == 0 && dy == 0) continue;
+                    const bool higher = dx > 0 || (dx == 0 && dy > 0);  // rank = tx * h + ty
+                    const int ux = tx + dx, uy = ty + dy;
+                    if (ux >= 0 && uy >= 0 && ux < bwid && uy < bhei) {
+                        const uint32_t q = s_pos[ux * bhei + uy];
+                        if ((q >> 16) && abs((int)(q & 0xff) - lx) + abs((int)((q >> 8) & 0xff) - ly) <= 2) {
+                            if (higher) dep[k] |= 1u << bit;
+                            else lower++;
+                        }
+                    }
+                    if (higher) bit++;
+                }
+            s_cnt[o] = lower;
+        }
+        __syncthreads();
+#ifdef FSE_BODIES_CYCLES
+        if (tid == 0) atomicAdd(&a.ticket[3], (unsigned int)((clock64() - c1) >> 4));
+        c1 = clock64();
+#endif
+        for (;;) {
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < BODY_PPT; k++) {
+                if (!(px[k] >> 16)) continue;
+                any = true;
+                const int o = tid + k * BODY_TB;
+                if (*reinterpret_cast<volatile int*>(&s_cnt[o]) != 0) continue;
+                const int tx = o / bhei, ty = o % bhei;
+                body_pixel_act_fast<ERASE>(a, b, tx, ty, (int)(px[k] & 0xff), (int)((px[k] >> 8) & 0xff), box, aw, s_mat, s_cnt, dep[k], bhei);
+                px[k] &= 0xffffu;
+            }
+            if (!__syncthreads_or(any)) break;
+            rounds++;
+        }
+    } else
     for (;;) {
         bool any = false;
         for (int o = tid; o < npix; o += BODY_TB) {  // pending pixels publish their rank on their footprint
@@ -270,6 +449,12 @@ __global__ void __launch_bounds__(BODY_TB) bodies_body_kernel(BodyArgs a) {
     }
     __threadfence();
     __syncthreads();
+#ifdef FSE_BODIES_CYCLES
+    if (tid == 0) {
+        atomicAdd(&a.ticket[4], (unsigned int)((clock64() - c1) >> 4));
+        atomicAdd(&a.ticket[5], (unsigned int)rounds);
+    }
+#endif
     if (tid == 0) {
         atomicMax(&a.ticket[1], (unsigned int)rounds);
         __threadfence();
@@ -351,7 +536,7 @@ extern "C" FSE_API int fse_bodies_upload(fse_world* w, const fse_body_desc* bodi
     CK(cudaMalloc(&B->d_pending, (size_t)B->n_pixels));
     CK(cudaMalloc(&B->d_feedback, sizeof(int4) * n));
     CK(cudaMalloc(&B->d_aabb, sizeof(int4) * n));
-    CK(cudaMalloc(&B->d_done, sizeof(unsigned int) * (n + 2)));
+    CK(cudaMalloc(&B->d_done, sizeof(unsigned int) * (n + 8)));
     if (B->big && !B->d_claim) {
         CK(cudaMalloc(&B->d_claim, sizeof(uint32_t) * (size_t)w->W * w->H));
         CK(cudaMemsetAsync(B->d_claim, 0xff, sizeof(uint32_t) * (size_t)w->W * w->H, w->stream));
@@ -392,6 +577,12 @@ static int run_bridge(fse_world* w, const fse_xform* xf, int32_t n, uint32_t tic
         CK(cudaMemcpyAsync(&rounds, B->d_done + n + 1, sizeof rounds, cudaMemcpyDeviceToHost, w->stream));
         CK(cudaStreamSynchronize(w->stream));
         w->last_bridge_rounds = (int)rounds;
+        if (getenv("FSE_BODIES_DEBUG")) {
+            unsigned int t[6];
+            cudaMemcpy(t, B->d_done + n, sizeof t, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "bodies %s: %d bodies, slowest body took %u rounds; per body: setup %.0f cycles, rounds %.0f cycles, %.1f rounds\n",
+                    ERASE ? "erase" : "raster", n, rounds, 16.0 * t[3] / n, 16.0 * t[4] / n, (double)t[5] / n);
+        }
     }
     if (out) {
         std::vector<int4> fb(n);
