@@ -129,7 +129,10 @@ def make_table():
 
 
 def workload_name(args, W, H, n):
-    base = {"mixed": "8192x8192 mixed powders/liquids/gases with fire and Lua-table reactions (BASELINE configs[1])",
+    mixed = ("8192x8192 mixed powders/liquids/gases with fire and Lua-table reactions (BASELINE configs[1])" if (W, H) == (8192, 8192) or n > 1 and W == 8192
+             else "mixed powders/liquids/gases with fire and Lua-table reactions, generator of BASELINE configs[1]"
+             + (" (configs[2]: 32768-wide world, strip-partitioned)" if W == 32768 else ""))
+    base = {"mixed": mixed,
             "column": "sand/water/stone column drop (BASELINE configs[0])",
             "sparse": "mostly-settled sparse-activity world (BASELINE configs[4])"}[args.workload]
     return f"{base}; world {W}x{H} cells over {n} GPU(s)"

@@ -203,12 +203,15 @@ static void free_world(fse_world* w) {
         if (w->fork.ev_join[q]) cudaEventDestroy(w->fork.ev_join[q]);
     }
     if (w->fork.ev_fork) cudaEventDestroy(w->fork.ev_fork);
+    cudaFree(w->fork.pair_sync);
     if (w->stream) cudaStreamDestroy(w->stream);
     if (w->comm_stream) cudaStreamDestroy(w->comm_stream);
     if (w->ev_boundary) cudaEventDestroy(w->ev_boundary);
     if (w->ev_comm) cudaEventDestroy(w->ev_comm);
     cudaFree(w->d_chunk_lists);
     cudaFree(w->d_awake); cudaFree(w->d_active_list); cudaFree(w->d_active_count);
+    if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
+    if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);
     cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list); cudaFree(w->d_chunk_state); cudaFree(w->d_graph_done);
     fse_bodies_free(w);
     cudaFree(w->outline_scratch);
@@ -248,6 +251,10 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     w->fork.min_chunks = 256;
     if (const char* env = getenv("FSE_TICK_MIN_CHUNKS")) w->fork.min_chunks = std::max(1, atoi(env));
     if (const char* env = getenv("FSE_TICK_PARTS")) w->fork.parts = std::min(4, std::max(1, atoi(env)));
+    w->fork.pairs = 0;  // tick_pair_kernel: measured slower than the plain per-pass launches; FSE_TICK_PAIRS=n turns it on
+    if (const char* env = getenv("FSE_TICK_PAIRS")) w->fork.pairs = std::min(4096, std::max(0, atoi(env)));
+    w->fork.pair_sync = nullptr;
+    if (w->fork.pairs > 0 && cudaMalloc((void**)&w->fork.pair_sync, sizeof(unsigned int) * (size_t)(w->fork.pairs + 1)) != cudaSuccess) w->fork.pairs = 0;
     for (int q = 0; q < 3; q++) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->fork.aux[q], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->fork.ev_join[q], cudaEventDisableTiming);

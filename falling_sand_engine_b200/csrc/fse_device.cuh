@@ -151,6 +151,8 @@ struct TickFork {
     int min_chunks;  // phases with fewer chunks are launched whole (default 256; FSE_TICK_MIN_CHUNKS)
     cudaStream_t aux[3];
     cudaEvent_t ev_fork, ev_join[3];
+    int pairs;                // heaviest chunks of a phase run as pipelined pass-1 / pass-2 CTA pairs (tick_pair_kernel); 0 = off
+    unsigned int* pair_sync;  // device: ticket | pass-1 progress per pair (pairs + 1 words)
 };
 
 }  // namespace fse

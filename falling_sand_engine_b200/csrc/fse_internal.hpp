@@ -79,6 +79,8 @@ struct fse_world {
     int last_bridge_rounds = 0;
     void* outline_scratch = nullptr;
     size_t outline_scratch_bytes = 0;
+    void *outline_pinned = nullptr, *outline_pinned2 = nullptr;  // pinned host staging of fse_mask_outline
+    size_t outline_pinned_bytes = 0, outline_pinned2_bytes = 0;
     // stats / staging
     void* d_stats = nullptr;
     void* h_stats = nullptr;

@@ -323,24 +323,50 @@ extern "C" FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int3
     a.rec_cap = rec_cap;
     a.pool = (float*)(base + o_pool);
     a.pool_cap = pool_cap;
-    CK(cudaMemcpyAsync(base + o_masks, masks, total, cudaMemcpyHostToDevice, w->stream));
+    // host traffic goes through one pinned staging buffer (masks in; counters, labels, component counts out in one batch;
+    // contour records and points after the counts are known): pageable cudaMemcpy calls cost several ms on 2000 masks
+    const size_t st_labels = up(total), st_ncomp = up(st_labels + total * 4), st_cnt = up(st_ncomp + (size_t)n_masks * 4), st_fixed = st_cnt + 256;
+    if (w->outline_pinned_bytes < st_fixed) {
+        if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
+        w->outline_pinned = nullptr;
+        w->outline_pinned_bytes = 0;
+        CK(cudaMallocHost(&w->outline_pinned, st_fixed));
+        w->outline_pinned_bytes = st_fixed;
+    }
+    char* pin = (char*)w->outline_pinned;
+    memcpy(pin, masks, total);
+    CK(cudaMemcpyAsync(base + o_masks, pin, total, cudaMemcpyHostToDevice, w->stream));
     CK(cudaMemsetAsync(base + o_cnt, 0, 256, w->stream));
     ccl_kernel<<<n_masks, 256, 0, w->stream>>>(a);
     CK(cudaGetLastError());
     contour_kernel<<<(unsigned int)((total + 127) / 128), 128, 0, w->stream>>>(a);
     CK(cudaGetLastError());
     w->ctx->launches += 2;
-    unsigned int hc[3] = {0, 0, 0};
-    CK(cudaMemcpyAsync(hc, base + o_cnt, sizeof hc, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(pin + st_cnt, base + o_cnt, 12, cudaMemcpyDeviceToHost, w->stream));
+    if (labels) CK(cudaMemcpyAsync(pin + st_labels, a.labels, total * 4, cudaMemcpyDeviceToHost, w->stream));
+    if (n_components) CK(cudaMemcpyAsync(pin + st_ncomp, a.ncomp, (size_t)n_masks * 4, cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
+    unsigned int hc[3];
+    memcpy(hc, pin + st_cnt, sizeof hc);
     if (hc[2]) return fail(FSE_ENOMEM, "fse_mask_outline: contour scratch overflow (%u floats, %u contours)", hc[0], hc[1]);
     const unsigned int nrec = hc[1];
-    std::vector<int4> recs(nrec);
-    std::vector<float> pool(hc[0]);
-    if (nrec) CK(cudaMemcpy(recs.data(), a.recs, sizeof(int4) * nrec, cudaMemcpyDeviceToHost));
-    if (hc[0]) CK(cudaMemcpy(pool.data(), a.pool, sizeof(float) * hc[0], cudaMemcpyDeviceToHost));
-    if (labels) CK(cudaMemcpy(labels, a.labels, total * 4, cudaMemcpyDeviceToHost));
-    if (n_components) CK(cudaMemcpy(n_components, a.ncomp, (size_t)n_masks * 4, cudaMemcpyDeviceToHost));
+    const size_t var_bytes = up(sizeof(int4) * (size_t)nrec) + sizeof(float) * (size_t)hc[0];
+    if (w->outline_pinned2_bytes < var_bytes) {
+        if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);
+        w->outline_pinned2 = nullptr;
+        w->outline_pinned2_bytes = 0;
+        CK(cudaMallocHost(&w->outline_pinned2, var_bytes + var_bytes / 2 + 4096));
+        w->outline_pinned2_bytes = var_bytes + var_bytes / 2 + 4096;
+    }
+    int4* recs_p = (int4*)w->outline_pinned2;
+    const float* pool_p = (const float*)((char*)w->outline_pinned2 + up(sizeof(int4) * (size_t)nrec));
+    if (nrec) CK(cudaMemcpyAsync(recs_p, a.recs, sizeof(int4) * nrec, cudaMemcpyDeviceToHost, w->stream));
+    if (hc[0]) CK(cudaMemcpyAsync((void*)pool_p, a.pool, sizeof(float) * hc[0], cudaMemcpyDeviceToHost, w->stream));
+    if (labels) memcpy(labels, pin + st_labels, total * 4);  // overlaps the two copies above
+    if (n_components) memcpy(n_components, pin + st_ncomp, (size_t)n_masks * 4);
+    CK(cudaStreamSynchronize(w->stream));
+    std::vector<int4> recs(recs_p, recs_p + nrec);
+    struct { const float* p; const float* data() const { return p; } } pool{pool_p};
     std::sort(recs.begin(), recs.end(), [](const int4& p, const int4& q) { return p.x != q.x ? p.x < q.x : p.y < q.y; });  // discovery order
     size_t npts = 0;
     for (auto& r : recs) npts += r.w;

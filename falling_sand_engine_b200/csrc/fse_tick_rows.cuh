@@ -833,14 +833,15 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
     const int t = tid & 127;
 
     int cxi, cyi;
-    if (P.list_count && (int)blockIdx.x >= *P.list_count) return;
+    const int bid = (int)blockIdx.x + P.chunk_base;
+    if (P.list_count && bid >= *P.list_count) return;
     if (P.chunk_list) {
-        int v = P.chunk_list[blockIdx.x];
+        int v = P.chunk_list[bid];
         cxi = v & 0xffff;
         cyi = v >> 16;
     } else {
-        cxi = blockIdx.x % P.ncx;
-        cyi = blockIdx.x / P.ncx;
+        cxi = bid % P.ncx;
+        cyi = bid / P.ncx;
     }
     const int cx = P.x0 + cxi * 2 * CHUNK;
     const int cy = P.y0 + cyi * 2 * CHUNK;
@@ -1057,7 +1058,7 @@ __device__ __forceinline__ void pass_row_load(SmemPass<PASS>& S, const PlaneIO& 
 // PIPE (tick_graph_kernel): the passes of a chunk visit run as CTAs side by side.  The pass-1 CTA publishes in *prog how many of
 // its rows (counted from row FULL_LO, bottom-up) have reached HBM for good — prog_base + count, monotonic over the tick — and the
 // pass-2 CTA loads a row only when that count covers it, so it trails pass 1 by about a dozen rows instead of a whole chunk.
-constexpr int PIPE_D = 3;  // bulk groups (= steps) a store may still be in flight when progress is published
+constexpr int PIPE_D = 8;  // bulk groups (= steps) a store may still be in flight when progress is published
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1074,15 +1075,17 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     // pass 2: row k may be loaded once pass 1 has published it (rows below -5 are never written by pass 1)
     auto wait_row = [&](int k, int lane_) {
         if (PIPE && PASS == 2) {
+            bool polled = false;
             if (lane_ == 0 && k >= PassGeom<1>::FULL_LO) {
                 const unsigned int need = prog_base + (unsigned int)(k - PassGeom<1>::FULL_LO + 1);
                 while (prog_seen < need) {
+                    polled = true;
                     prog_seen = ld_acquire_u32(prog);
                     if (prog_seen < need) __nanosleep(64);
                 }
             }
-            __syncwarp();
-            asm volatile("fence.proxy.async;" ::: "memory");
+            // the proxy fence orders this lane's bulk loads behind lane 0's acquire; rows covered by an earlier poll need none
+            if (__shfl_sync(0xffffffffu, polled ? 1 : 0, 0)) asm volatile("fence.proxy.async;" ::: "memory");
         }
     };
     unsigned char* const smem_raw = fse_smem;
@@ -1188,13 +1191,16 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                 wait_row(kl, lane);
                 pass_row_load<PASS>(S, pio, lane, kl, cy);
             }
-            if (PIPE && PASS == 1 && st >= PIPE_D + G::SL) {
-                // the stores of the steps up to st - PIPE_D have completed: rows FULL_LO .. st - PIPE_D - SL are final in HBM
+            if (PIPE && PASS == 1 && st >= PIPE_D + G::SL && (st & 3) == 0) {
+                // the stores of the steps up to st - PIPE_D have completed: rows FULL_LO .. st - PIPE_D - SL are final in HBM.
+                // Every lane waits for its own plane's bulk groups; lane 0 publishes for all of them (one fence per 4 steps)
                 asm volatile("cp.async.bulk.wait_group %0;" ::"n"(PIPE_D) : "memory");
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __threadfence();
                 __syncwarp();
-                if (lane == 0) st_release_u32(prog, prog_base + (unsigned int)(st - PIPE_D - G::SL - G::FULL_LO + 1));
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    st_release_u32(prog, prog_base + (unsigned int)(st - PIPE_D - G::SL - G::FULL_LO + 1));
+                }
             }
         }
     }
@@ -1470,6 +1476,44 @@ __global__ void __launch_bounds__(PassGeom<1>::THREADS, FSE_PASS_MINB) tick_grap
             }
         }
     }
+}
+
+// The heaviest chunks of a colour phase as CTA pairs (per-phase launches, longest-first list).  In the per-pass launches a
+// chunk's pass 2 cannot start before the whole pass-1 kernel of its part has drained, so the heaviest chunks — they decide when
+// the phase ends — run their three passes strictly one after the other.  Here the first `pairs` chunks of the list get two
+// CTAs each: pass 1, and pass 2 trailing it through the progress counter (run_pass PIPE) with pass 3 at its end.  Tickets are
+// handed out in order, so the pass-1 CTA of a pair is always resident before its pass-2 CTA can wait for it.
+__global__ void __launch_bounds__(PassGeom<1>::THREADS, FSE_PASS_MINB) tick_pair_kernel(const __grid_constant__ TickParams P, unsigned int* sync) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    volatile unsigned int* s_task = reinterpret_cast<volatile unsigned int*>(fse_smem + offsetof(SmemHead, pad_));
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(&P.tabs->lut);
+        uint4* dst = reinterpret_cast<uint4*>(fse_smem);
+        for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) s_task[0] = atomicAdd(sync, 1u);
+    __syncthreads();
+    const unsigned int t = s_task[0];
+    const int idx = (int)(t >> 1), bid = idx + P.chunk_base;
+    int cxi, cyi;
+    if (P.chunk_list) {
+        const int v = P.chunk_list[bid];
+        cxi = v & 0xffff;
+        cyi = v >> 16;
+    } else {
+        cxi = bid % P.ncx;
+        cyi = bid / P.ncx;
+    }
+    const int cx = P.x0 + cxi * 2 * CHUNK, cy = P.y0 + cyi * 2 * CHUNK;
+    unsigned int* const prog = sync + 1 + idx;
+    if (!(t & 1u)) {
+        run_pass<1, true>(P, cx, cy, P.iter, P.rkey, P.chunk_cost ? P.chunk_cost + cyi * P.ncx + cxi : nullptr, prog, 0u);
+        return;
+    }
+    run_pass<2, true>(P, cx, cy, P.iter, P.rkey, nullptr, prog, 0u);
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    for (int r = warp; r < CHUNK; r += PassGeom<1>::THREADS / 32) pass3_row_global(P, P.rkey, cx, cy + r, lane);
 }
 
 // Active-chunk bookkeeping after the three passes of a phase (per-pass kernels): wake the 3x3 chunks around a chunk whose state

@@ -244,6 +244,7 @@ def test_phase_parts_and_longest_first_order_do_not_change_results(oracle, gpu_c
     """Large worlds cut a colour phase into parts on separate streams and launch the chunks longest-first (last tick's
     pass-1 cycles).  Chunks of a phase are independent, so neither may change a single bit: force both on a small world."""
     monkeypatch.setenv("FSE_TICK_MIN_CHUNKS", "1")
+    monkeypatch.setenv("FSE_TICK_PAIRS", "6")  # the heaviest chunks of a phase as pipelined pass-1 / pass-2 CTA pairs (tick_pair_kernel)
     W = H = 1280
     tbl, extra = G.bench_table(table)
     ow, gw = _pair(oracle, gpu_ctx, tbl, W, H, "rows")
