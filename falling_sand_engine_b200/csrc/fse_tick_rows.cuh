@@ -118,7 +118,7 @@ __device__ Dec1 decide1(const Ctx& c, int s, int j, int x, int y) {
     if (f0 & F_VISITED) return d;
     const uint8_t m = MAT(s, j);
     if (c.iter >= (int)LUTP->iters[m]) {
-        d.bits = A_MARK;
+        d.bits = A_MARK | ((uint32_t)f0 << 16);  // the caller marks the cell without reading its flag byte again
         return d;
     }
     const int type = LUTP->phys[m];
@@ -595,7 +595,7 @@ __device__ void pass1_rows(const Ctx& c, Scratch1& R, int k, int cx, int cy, int
     }
     int a = d.bits & 15;
     if (a == A_MARK) {  // iterations exhausted (1095): only the cell's own visited bit, which no decision of this step reads
-        FLG(s, j) = FLG(s, j) | F_VISITED;
+        FLG(s, j) = (uint8_t)((d.bits >> 16) | F_VISITED);
         ROWVIS[s] = 1;
         d.bits = a = A_NONE;
     }
@@ -1146,7 +1146,8 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     for (int st = 0; st < n_steps; st++) {
         FSE_STEP_CLOCK(2, dbg_c);
         const int kw = st + G::UP;
-        if (kw <= G::LAST) mbar_wait(&S.bar[(kw - G::KMIN) % G::RN], (uint32_t)(((kw - G::KMIN) / G::RN) & 1));
+        // the IO warp never reads the row that is about to become live: only the compute warps wait for it
+        if (kw <= G::LAST && !io) mbar_wait(&S.bar[(kw - G::KMIN) % G::RN], (uint32_t)(((kw - G::KMIN) / G::RN) & 1));
         FSE_STEP_CLOCK(0, dbg_c);
 #ifndef FSE_EXP_NO_TOP_FENCE
         fence_proxy_async();
@@ -1164,13 +1165,17 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                 const int q = (ks - G::KMIN) % G::RN;
                 uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
                 const bool core_row = ks >= 0 && ks < CHUNK;
-                for (int w = lane; w < P8 / 4; w += 32) {
-                    // tickVisited of the chunk's own cells goes to HBM (the later passes need it); halo cells are cleared
-                    const bool keep = core_row && w >= HX8 / 4 && w < (HX8 + CHUNK) / 4;
-                    if (!keep) fw[w] &= 0x7f7f7f7fU;
-                }
                 const bool all_store = S.h.rowmod[q] != 0;
                 const bool vis_store = S.h.rowvis[q] != 0;
+                // tickVisited of the chunk's own cells goes to HBM (the later passes need it); halo cells are cleared.  Only rows
+                // that are stored need it; a core row has 4 + 4 halo words (one word per lane 0..7), other rows are cleared whole
+                if (all_store || vis_store) {
+                    if (core_row) {
+                        if (lane < 2 * (HX8 / 4)) fw[lane < HX8 / 4 ? lane : (HX8 + CHUNK) / 4 + lane - HX8 / 4] &= 0x7f7f7f7fU;
+                    } else {
+                        for (int w = lane; w < P8 / 4; w += 32) fw[w] &= 0x7f7f7f7fU;
+                    }
+                }
                 if (P.chunk_state) {
                     io_modified |= S.h.rowchg[q] != 0;
                     // rows are final for passes 1 and 2 here; pass 3 only moves GAS, which is never inert anyway
