@@ -250,6 +250,33 @@ class World:
         return out
 
     # -- fracture outlines (world.cpp:288-720, physics_math.cpp:1766-1965) and physicsCheck flood (world.cpp:3330) ------
+    # -- render planes / camera scroll (game.cpp:1994-2060, world.cpp:2454-2478) ---------------------------
+    def pixels_enable(self, on=True):
+        self.L.fse_pixels_enable.argtypes = [C.c_void_p, C.c_int]
+        _ck(self.L.fse_pixels_enable(self.h, 1 if on else 0))
+
+    def render_dirty(self, want_stats=True):
+        """Refresh the texels of all dirty cells; returns (dirty, fire, movingTiles) or None when want_stats is False."""
+        self.L.fse_render_dirty.argtypes = [C.c_void_p, C.c_void_p]
+        if not want_stats:
+            _ck(self.L.fse_render_dirty(self.h, None))
+            return None
+        st = T.RenderStats()
+        _ck(self.L.fse_render_dirty(self.h, C.byref(st)))
+        return st.dirty, st.fire, np.ctypeslib.as_array(st.moving).copy()
+
+    def pixels_read(self, which, rect=None):
+        r = rect or T.Rect(0, 0, self.width, self.height)
+        out = np.zeros((r.h, r.w, 4), dtype=np.uint8)
+        self.L.fse_pixels_read.argtypes = [C.c_void_p, C.c_int] + [C.c_int32] * 4 + [C.c_void_p]
+        _ck(self.L.fse_pixels_read(self.h, which, r.x, r.y, r.w, r.h, out.ctypes.data))
+        return out
+
+    def scroll(self, dx, dy):
+        """world::tickChunks: shift the grid and the loose particles by (dx, dy)."""
+        self.L.fse_scroll.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        _ck(self.L.fse_scroll(self.h, dx, dy))
+
     def explosion(self, x, y, radius, tick=0, seed=1337):
         """world::explosion(x, y, radius) (world.cpp:2294-2332)."""
         self.L.fse_explosion.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32]

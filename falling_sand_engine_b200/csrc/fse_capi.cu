@@ -50,6 +50,7 @@ FSE_API int fse_abi_sizeof(int which) {
         case 5: return (int)sizeof(fse_tick_args);
         case 6: return (int)sizeof(fse_particle);
         case 7: return (int)sizeof(fse_stats);
+        case 8: return (int)sizeof(fse_render_stats);
     }
     return -1;
 }
@@ -146,6 +147,7 @@ FSE_API int fse_materials_set(fse_ctx* c, const fse_material* tbl, int n, const 
         h.density[i] = m.density;
         h.color[i] = m.color;
         h.add_temp[i] = m.add_temp;
+        h.emit_color[i] = m.emit_color;
         h.cond_self[i] = m.conduction_self;
         h.cond_other[i] = m.conduction_other;
         h.react_off[i] = react_offsets ? react_offsets[i] : 0;
@@ -210,6 +212,7 @@ static void free_world(fse_world* w) {
     if (w->ev_comm) cudaEventDestroy(w->ev_comm);
     cudaFree(w->d_chunk_lists);
     cudaFree(w->d_awake); cudaFree(w->d_active_list); cudaFree(w->d_active_count);
+    cudaFree(w->d_pixels); cudaFree(w->d_render_stats); cudaFree(w->scroll_scratch);
     if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
     if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);
     cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list); cudaFree(w->d_chunk_state); cudaFree(w->d_graph_done);

@@ -87,6 +87,7 @@ struct DevTables {
     float density[FSE_MAX_MATERIALS];
     uint32_t color[FSE_MAX_MATERIALS];
     uint32_t add_temp[FSE_MAX_MATERIALS];
+    uint32_t emit_color[FSE_MAX_MATERIALS];  // Material::emitColor (render planes, fse_render.cu)
     float cond_self[FSE_MAX_MATERIALS];
     float cond_other[FSE_MAX_MATERIALS];
     int32_t react_off[FSE_MAX_MATERIALS + 1];

@@ -81,6 +81,11 @@ struct fse_world {
     size_t outline_scratch_bytes = 0;
     void *outline_pinned = nullptr, *outline_pinned2 = nullptr;  // pinned host staging of fse_mask_outline
     size_t outline_pinned_bytes = 0, outline_pinned2_bytes = 0;
+    // render planes (fse_render.cu): main | fire | emission RGBA, W*H words each; scroll scratch (largest plane)
+    uint32_t* d_pixels = nullptr;
+    void* d_render_stats = nullptr;
+    void* scroll_scratch = nullptr;
+    size_t scroll_scratch_bytes = 0;
     // stats / staging
     void* d_stats = nullptr;
     void* h_stats = nullptr;

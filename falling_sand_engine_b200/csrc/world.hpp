@@ -144,6 +144,16 @@ public:
         pixels.resize(n <= 1000 ? n : 0);
         return n;
     }
+    // world::explosion(x, y, r) (world.cpp:2294)
+    void explosion(int x, int y, int r) { check(fse_explosion(h_, x, y, r, tickCt, seed)); }
+    // world::tickChunks() grid + particle shift (world.cpp:2454-2478, 2579-2582); chunk load / save stays with the caller
+    void scroll(int changeX, int changeY) { check(fse_scroll(h_, changeX, changeY)); }
+    // the dirty -> texture loop of game::tick (game.cpp:1994-2060) followed by memset(dirty) (game.cpp:2153)
+    void renderDirty(fse_render_stats* movingTiles = nullptr) {
+        check(fse_pixels_enable(h_, 1));
+        check(fse_render_dirty(h_, movingTiles));
+        check(fse_clear_dirty(h_));
+    }
     void sync() { check(fse_sync(h_)); }
     fse_world* handle() const { return h_; }
 

@@ -76,6 +76,10 @@ class Stats(C.Structure):
     ]
 
 
+class RenderStats(C.Structure):
+    _fields_ = [("dirty", C.c_int64), ("fire", C.c_int64), ("moving", C.c_int64 * FSE_MAX_MATERIALS)]
+
+
 # fse_cell (20 bytes)
 CELL_DTYPE = np.dtype(
     {

@@ -248,6 +248,33 @@ FSE_API int fse_bodies_read(fse_world* w, int32_t body, fse_cell* tiles_out);
  * independently; rand() is replaced by the counter RNG keyed on (seed, tick, x, y).  Not available on multi-rank strips. */
 FSE_API int fse_explosion(fse_world* w, int32_t cx, int32_t cy, int32_t radius, uint32_t tick, uint32_t seed);
 
+/* ---- render planes: the dirty -> texture loop of game::tick (game.cpp:1994-2060).  Every cell whose dirty
+ * flag is set refreshes its texel in three device-resident RGBA8 planes (byte order r, g, b, a as the reference fills
+ * dpixels_ar): main (colour + material alpha; AIR = transparent black), fire (only FIRE cells write it, AIR clears it,
+ * other materials leave it alone) and emission (Material::emitColor).  movingTiles[mat] counts the dirty cells per
+ * material (game.cpp:1998-2000).  The flow texture is not produced (the tick does not keep flowX / flowY).  Dirty flags
+ * are left set, as in the reference (fse_clear_dirty = game.cpp:2153). */
+typedef struct fse_render_stats {
+    int64_t dirty;                       /* hadDirty: number of dirty cells */
+    int64_t fire;                        /* hadFire: dirty FIRE cells */
+    int64_t moving[FSE_MAX_MATERIALS];   /* movingTiles */
+} fse_render_stats;
+enum { FSE_PIXELS_MAIN = 0, FSE_PIXELS_FIRE = 1, FSE_PIXELS_EMISSION = 2 };
+/* allocate (zeroed: transparent) / free the three planes */
+FSE_API int fse_pixels_enable(fse_world* w, int enable);
+/* refresh the texels of all dirty cells; `out` may be null (no host sync then) */
+FSE_API int fse_render_dirty(fse_world* w, fse_render_stats* out);
+/* copy a rect of one plane to the host, rw*rh*4 bytes */
+FSE_API int fse_pixels_read(fse_world* w, int which, int32_t x, int32_t y, int32_t rw, int32_t rh, uint8_t* rgba);
+/* device pointer of a plane (W*H RGBA8, row-major) for CUDA-GL interop or further kernels; null when disabled */
+FSE_API void* fse_pixels_device(fse_world* w, int which);
+
+/* ---- camera scroll: the grid shift of world::tickChunks (world.cpp:2454-2478, 2579-2582).  Every cell
+ * moves by (dx, dy); cells whose source lies outside the world keep their old content (the reference's in-place copy),
+ * dirty flags stay where they are (world::dirty is not shifted), loose particles move along.  Chunk load / save around
+ * the scroll stays with the host (fse_write_rect / fse_read_rect).  Not available on multi-rank strips. */
+FSE_API int fse_scroll(fse_world* w, int32_t dx, int32_t dy);
+
 /* ---- fracture / hitbox outlines: updateRigidBodyHitbox, updateChunkMesh (world.cpp:288-720, 722-959) with
  * MarchingSquares::FindPerimeter + simplify(...,1) (physics_math.cpp:1766-1965), physicsCheck flood (world.cpp:3330-3429).
  * The device labels 4-connected components and extracts + simplifies every contour; TPPL hole removal / ear clipping

@@ -389,6 +389,70 @@ OAPI int fseo_bodies_raster(void* p, int n, const int* bw, const int* bh, fse_ce
     bodies_raster((World*)p, n, bw, bh, tiles, xf, tick, seed, feedback);
     return 0;
 }
+// The dirty -> texture loop of game::tick (game.cpp:1994-2060), flow texture left out (the tick keeps no flowX / flowY).
+// px_main / px_fire / px_emis: width*height RGBA8 texels in the reference's byte order (r, g, b, a).
+void render_dirty(const World* w, uint8_t* px_main, uint8_t* px_fire, uint8_t* px_emis, int64_t* moving, int64_t* had) {
+    had[0] = had[1] = 0;
+    for (int i = 0; i < w->n_materials(); i++) moving[i] = 0;
+    for (int i = 0; i < w->width * w->height; i++) {
+        const unsigned int offset = (unsigned int)i * 4;
+        if (!w->dirty[i]) continue;
+        had[0]++;
+        const Cell& t = w->tiles[i];
+        moving[t.mat->id]++;
+        if (t.mat->physicsType == AIR) {
+            for (int q = 0; q < 4; q++) px_main[offset + q] = px_fire[offset + q] = px_emis[offset + q] = 0;  // ME_ALPHA_TRANSPARENT = 0
+            continue;
+        }
+        const uint32_t color = t.color, emit = t.mat->emitColor;
+        px_main[offset + 2] = (color >> 0) & 0xff;
+        px_main[offset + 1] = (color >> 8) & 0xff;
+        px_main[offset + 0] = (color >> 16) & 0xff;
+        px_main[offset + 3] = t.mat->alpha;
+        px_emis[offset + 2] = (emit >> 0) & 0xff;
+        px_emis[offset + 1] = (emit >> 8) & 0xff;
+        px_emis[offset + 0] = (emit >> 16) & 0xff;
+        px_emis[offset + 3] = (emit >> 24) & 0xff;
+        if ((int)t.mat->id == w->ids.fire) {
+            px_fire[offset + 2] = (color >> 0) & 0xff;
+            px_fire[offset + 1] = (color >> 8) & 0xff;
+            px_fire[offset + 0] = (color >> 16) & 0xff;
+            px_fire[offset + 3] = t.mat->alpha;
+            had[1]++;
+        }
+    }
+}
+
+// The grid shift of world::tickChunks (world.cpp:2454-2478) and the particle shift (2579-2582), loops as in the reference.
+void scroll(World* w, int changeX, int changeY) {
+    const int width = w->width, height = w->height;
+    if (changeX != 0 || changeY != 0) {
+        const bool revX = changeX > 0, revY = changeY > 0;
+        for (int y = 0; y < height; y++) {
+            const int oldY = revY ? (height - y - 1) : y;
+            const int newY = oldY + changeY;
+            if (newY < 0 || newY >= height) continue;
+            for (int x = 0; x < width; x++) {
+                const int oldX = revX ? (width - x - 1) : x;
+                const int newX = oldX + changeX;
+                if (newX >= 0 && newX < width) w->tiles[newX + newY * width] = w->tiles[oldX + oldY * width];
+            }
+        }
+        for (auto& p : w->cells) {
+            p.x += changeX;
+            p.y += changeY;
+        }
+    }
+}
+
+OAPI int fseo_render_dirty(void* p, uint8_t* px_main, uint8_t* px_fire, uint8_t* px_emis, int64_t* moving, int64_t* had) {
+    render_dirty((const World*)p, px_main, px_fire, px_emis, moving, had);
+    return 0;
+}
+OAPI int fseo_scroll(void* p, int dx, int dy) {
+    scroll((World*)p, dx, dy);
+    return 0;
+}
 OAPI int fseo_explosion(void* p, int cx, int cy, int radius, uint32_t tick, uint32_t seed) {
     explosion((World*)p, cx, cy, radius, tick, seed);
     return 0;

@@ -176,6 +176,22 @@ def bodies_raster(world, bodies, xforms, tick=0, seed=1337):
     return fb
 
 
+def render_dirty(world, planes):
+    """game.cpp:1994-2060 on the oracle world; planes = (main, fire, emission) uint8 arrays (h, w, 4), updated in place.
+    Returns (dirty cells, dirty FIRE cells, movingTiles[n_materials])."""
+    moving = np.zeros(256, dtype=np.int64)
+    had = np.zeros(2, dtype=np.int64)
+    lib().fseo_render_dirty.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    lib().fseo_render_dirty(world.h, planes[0].ctypes.data, planes[1].ctypes.data, planes[2].ctypes.data, moving.ctypes.data, had.ctypes.data)
+    return int(had[0]), int(had[1]), moving
+
+
+def scroll(world, dx, dy):
+    """world::tickChunks grid + particle shift (world.cpp:2454-2478, 2579-2582)."""
+    lib().fseo_scroll.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib().fseo_scroll(world.h, dx, dy)
+
+
 def explosion(world, cx, cy, radius, tick=0, seed=1337):
     """world::explosion (world.cpp:2294-2332)."""
     lib().fseo_explosion.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32]

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_pod_sizes_match_the_compiled_library():
     L = api.load_library()
     want = {0: C.sizeof(T.Material), 1: C.sizeof(T.Interaction), 2: C.sizeof(T.SpecialIds), 3: T.CELL_DTYPE.itemsize,
-            4: C.sizeof(T.Rect), 5: C.sizeof(T.TickArgs), 6: T.PARTICLE_DTYPE.itemsize, 7: C.sizeof(T.Stats)}
+            4: C.sizeof(T.Rect), 5: C.sizeof(T.TickArgs), 6: T.PARTICLE_DTYPE.itemsize, 7: C.sizeof(T.Stats), 8: C.sizeof(T.RenderStats)}
     for k, v in want.items():
         assert L.fse_abi_sizeof(k) == v, (k, L.fse_abi_sizeof(k), v)
     assert T.CELL_DTYPE.itemsize == 20 and T.PARTICLE_DTYPE.itemsize == 80

@@ -131,3 +131,57 @@ def test_explosion_conserves_what_it_throws(oracle, table):
     assert 0.3 * n_inner_sand < kept < 0.5 * n_inner_sand  # 4 in 10 survive as particles
     assert (parts["tile"]["mat"] == SAND).all()
     assert len(np.unique(parts["id"])) == n_parts
+
+
+def test_render_dirty_known_answers(oracle, table):
+    """game.cpp:1994-2060 on hand-made cells: byte order r, g, b, a; AIR clears all three planes; only FIRE writes the fire plane
+    (other materials leave it alone); emission is Material::emitColor; clean cells are not touched; movingTiles counts per material."""
+    from oracle import pyoracle as O
+    W, H = 8, 4
+    ow = oracle.OracleWorld(W, H, table)
+    cells = Hh.empty_world_cells(table, W, H)
+    cells["mat"][1, 1], cells["color"][1, 1] = 15, 0x112233   # WATER: alpha 0x80, emit 0x3000AFB5
+    cells["mat"][1, 2], cells["color"][1, 2] = 25, 0xFF6432   # FIRE: alpha 255
+    cells["mat"][1, 3] = 0                                    # AIR
+    cells["mat"][1, 4], cells["color"][1, 4] = 2, 0xABCDEF    # SAND, written clean below
+    cells["dirty"][:] = 0
+    cells["dirty"][1, 1:4] = 1
+    ow.write_rect(0, 0, cells)
+    planes = [np.full((H, W, 4), 7, dtype=np.uint8) for _ in range(3)]
+    dirty, fire, moving = O.render_dirty(ow, planes)
+    assert (dirty, fire) == (3, 1) and moving[15] == 1 and moving[25] == 1 and moving[0] == 1 and moving.sum() == 3
+    assert planes[0][1, 1].tolist() == [0x11, 0x22, 0x33, 0x80] and planes[2][1, 1].tolist() == [0x00, 0xAF, 0xB5, 0x30]
+    assert planes[1][1, 1].tolist() == [7, 7, 7, 7]                                   # not FIRE: fire plane untouched
+    assert planes[0][1, 2].tolist() == [0xFF, 0x64, 0x32, 255] == planes[1][1, 2].tolist()
+    assert all(p[1, 3].tolist() == [0, 0, 0, 0] for p in planes)                      # AIR: transparent black everywhere
+    assert all(p[1, 4].tolist() == [7, 7, 7, 7] for p in planes)                      # clean cell: untouched
+    assert ow.read_all()["dirty"].sum() == 3                                          # dirty flags stay (game.cpp:2153 clears them later)
+
+
+@pytest.mark.parametrize("dx,dy", [(3, 0), (-2, 1), (0, -3), (5, 4), (-300, 0)])
+def test_scroll_is_a_shift_that_keeps_unsourced_cells(oracle, table, dx, dy):
+    """world.cpp:2454-2478: every cell moves by (dx, dy); cells without a source inside the world keep their content; particles
+    move along (2579-2582)."""
+    from oracle import pyoracle as O
+    W, H = 40, 24
+    ow = oracle.OracleWorld(W, H, table)
+    rng = np.random.default_rng(1)
+    mat = rng.integers(0, 28, size=(H, W)).astype(np.uint16)
+    cells = G.cells_from_mat(table, mat, 0, 0, 5)
+    cells["temp"] = rng.integers(-100, 100, size=(H, W))
+    ow.write_rect(0, 0, cells)
+    parts = np.zeros(2, dtype=T.PARTICLE_DTYPE)
+    parts["x"], parts["y"], parts["id"] = [5.5, 30.0], [7.25, 20.0], [1, 2]
+    ow.particles_add(parts)
+    before = ow.read_all()
+    O.scroll(ow, dx, dy)
+    after = ow.read_all()
+    ys, xs = np.mgrid[0:H, 0:W]
+    sy, sx = ys - dy, xs - dx
+    ok = (sx >= 0) & (sx < W) & (sy >= 0) & (sy < H)
+    for f in ("mat", "color", "temp", "fluid", "moved", "settle"):
+        want = before[f].copy()
+        want[ok] = before[f][sy[ok], sx[ok]]
+        assert np.array_equal(after[f], want), f
+    p = ow.particles_read()
+    assert np.allclose(np.sort(p["x"]), np.sort(parts["x"] + dx)) and np.allclose(np.sort(p["y"]), np.sort(parts["y"] + dy))

@@ -185,3 +185,55 @@ def test_explosion_exact(oracle, gpu_ctx, table):
         ow.particles_tick(); gw.particles_tick()
     Hh.assert_cells_equal(ow.read_all(), gw.read_all(), "after explosion")
     Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), "particles after explosion")
+
+
+def test_render_dirty_exact(oracle, gpu_ctx, table):
+    """fse_render_dirty vs the oracle restatement of the dirty -> texture loop (game.cpp:1994-2060): the three RGBA planes, the
+    movingTiles histogram and the dirty / fire counts after ticks of a mixed world; clean cells keep their old texels."""
+    from oracle import pyoracle as O
+    W, H = 640, 512
+    tbl, extra = G.bench_table(table)
+    gpu_ctx.set_materials(tbl)
+    ow, gw = oracle.OracleWorld(W, H, tbl), fse.World(gpu_ctx, W, H)
+    ow.default_schedule = 2
+    Hh.build_mixed(ow, tbl, W, H, seed=4, extra=list(extra.values()))
+    Hh.build_mixed(gw, tbl, W, H, seed=4, extra=list(extra.values()))
+    gw.pixels_enable(True)
+    planes = [np.zeros((H, W, 4), dtype=np.uint8) for _ in range(3)]
+    for t in range(3):
+        ow.clear_dirty()
+        gw.clear_dirty()
+        ow.tick(t, seed=2)
+        gw.tick(t, seed=2)
+        d_o, f_o, m_o = O.render_dirty(ow, planes)
+        d_g, f_g, m_g = gw.render_dirty()
+        assert (d_o, f_o) == (d_g, f_g) and d_o > 0 and np.array_equal(m_o, m_g), t
+        for which in range(3):
+            assert np.array_equal(planes[which], gw.pixels_read(which)), (t, which)
+    assert f_o > 0
+    sub = gw.pixels_read(0, T.Rect(100, 60, 33, 17))
+    assert np.array_equal(sub, planes[0][60:77, 100:133])
+
+
+@pytest.mark.parametrize("dx,dy", [(128, 0), (-128, 256), (7, -5), (0, 1), (-1000, 3)])
+def test_scroll_exact(oracle, gpu_ctx, table, dx, dy):
+    """fse_scroll vs the oracle's restatement of the tickChunks shift: cells, dirty flags (not shifted) and particles."""
+    from oracle import pyoracle as O
+    W, H = 640, 512
+    gpu_ctx.set_materials(table)
+    ow, gw = oracle.OracleWorld(W, H, table), fse.World(gpu_ctx, W, H)
+    Hh.build_mixed(ow, table, W, H, seed=12)
+    Hh.build_mixed(gw, table, W, H, seed=12)
+    parts = np.zeros(3, dtype=T.PARTICLE_DTYPE)
+    parts["x"], parts["y"], parts["id"] = [5.5, 300.0, 639.0], [7.25, 200.0, 500.0], [1, 2, 3]
+    parts["tile"]["mat"] = 2
+    for w in (ow, gw):
+        w.tick(0)
+        w.particles_add(parts)
+    O.scroll(ow, dx, dy)
+    gw.scroll(dx, dy)
+    Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"scroll {dx},{dy}")
+    Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), "scroll particles")
+    ow.tick(1)
+    gw.tick(1)
+    Hh.assert_cells_equal(ow.read_all(), gw.read_all(), "tick after scroll")
