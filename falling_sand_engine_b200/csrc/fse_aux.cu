@@ -130,13 +130,18 @@ __global__ void stats_kernel(Planes p, int W, int x0, int y0, int rw, int rh, in
 // Jacobi 3x3 stencil on the i16 temperature plane: order-independent, so bit-exact against the reference
 // order.  One thread per cell of a 32x8 tile staged (with a 1-cell halo) in shared memory; the new
 // temperatures go to a scratch plane that is then copied back (the reference's newTemps[] two-loop form).
-constexpr int TT_W = 64, TT_H = 16;
+constexpr int TT_W = 128, TT_H = 16, TT_P = TT_W + 4;  // outputs per block; row pitch of the shared-memory tile (130 used)
 
+// Each loaded cell's contribution is computed once — factor = float(abs(t) / 64) * conductionOther(mat), t * factor — and every
+// output cell then adds the nine (t * factor, factor) pairs of its neighbourhood in the reference's order (xa outer, ya inner,
+// world.cpp:1976-1984).  A neighbour with t == 0, which the reference skips, contributes (+-0, 0): adding it leaves v and n
+// unchanged bit for bit, so no branch is needed.  A thread walks 8 rows of one column with the 3 x 3 window in registers.
 __global__ void __launch_bounds__(256) temperature_kernel(const uint8_t* __restrict__ mat, const int16_t* __restrict__ tmp,
-                                                          int16_t* __restrict__ out, int W, int zx, int zy, int zw, int zh,
+                                                          int16_t* __restrict__ out, int W, int H, int zx, int zy, int zw, int zh,
                                                           const DevTables* __restrict__ T, uint8_t* awake, int acols, int yoff) {
-    __shared__ int16_t st[TT_H + 2][TT_W + 2];
-    __shared__ uint8_t sm[TT_H + 2][TT_W + 2];
+    __shared__ float2 sc[TT_H + 2][TT_P];   // (t * factor, factor)
+    __shared__ int16_t st[TT_H + 2][TT_P];
+    __shared__ uint8_t sm[TT_H + 2][TT_P];
     __shared__ float condO[FSE_MAX_MATERIALS];
     __shared__ float condS[FSE_MAX_MATERIALS];
     __shared__ uint32_t addT[FSE_MAX_MATERIALS];
@@ -146,47 +151,69 @@ __global__ void __launch_bounds__(256) temperature_kernel(const uint8_t* __restr
         condS[i] = T->cond_self[i];
         addT[i] = T->add_temp[i];
     }
-    const int bx = zx + blockIdx.x * TT_W, by = zy + blockIdx.y * TT_H;
-    for (int i = tid; i < (TT_H + 2) * (TT_W + 2); i += blockDim.x) {
-        int lx = i % (TT_W + 2), ly = i / (TT_W + 2);
-        size_t g = (size_t)(by + ly - 1) * W + (bx + lx - 1);
-        st[ly][lx] = tmp[g];
-        sm[ly][lx] = mat[g];
-    }
     __syncthreads();
-    for (int i = tid; i < TT_W * TT_H; i += blockDim.x) {
-        int lx = i % TT_W, ly = i / TT_W;
-        int x = bx + lx, y = by + ly;
-        if (x >= zx + zw || y >= zy + zh) continue;
-        float n = 0.01f;
-        float v = 0.0f;
+    const int bx = zx + blockIdx.x * TT_W, by = zy + blockIdx.y * TT_H;
+    auto load = [&](int ly, int lx) {  // tile cell (ly, lx) <- world cell (by + ly - 1, bx + lx - 1)
+        const int gx = bx + lx - 1, gy = by + ly - 1;
+        int t = 0;
+        uint8_t m = 0;
+        if (gx < W && gy < H) {  // tiles may hang over the zone; those cells feed no output inside it
+            const size_t g = (size_t)gy * W + gx;
+            t = tmp[g];
+            m = mat[g];
+        }
+        const float factor = __fmul_rn((float)(abs(t) / 64), condO[m]);
+        st[ly][lx] = (int16_t)t;
+        sm[ly][lx] = m;
+        sc[ly][lx] = make_float2(__fmul_rn((float)t, factor), factor);
+    };
+    for (int r = tid >> 7; r < TT_H + 2; r += 2) load(r, 1 + (tid & 127));      // the 128 middle columns, two rows per sweep
+    if (tid < 2 * (TT_H + 2)) load(tid >> 1, (tid & 1) ? TT_W + 1 : 0);          // the two halo columns
+    __syncthreads();
+    const int lx = tid & 127, ly0 = (tid >> 7) * (TT_H / 2);
+    const int x = bx + lx;
+    if (x >= zx + zw) return;
+    float2 w0[3], w1[3], w2[3];  // window rows y-1, y, y+1; index = xa + 1
 #pragma unroll
-        for (int xa = -1; xa <= 1; xa++) {
+    for (int q = 0; q < 3; q++) {
+        w0[q] = sc[ly0][lx + q];
+        w1[q] = sc[ly0 + 1][lx + q];
+    }
 #pragma unroll
-            for (int ya = -1; ya <= 1; ya++) {  // FN(-1,-1) FN(-1,0) FN(-1,1) FN(0,-1) ... (world.cpp:1976-1984)
-                int t = st[ly + 1 + ya][lx + 1 + xa];
-                if (t != 0) {
-                    float factor = __fmul_rn((float)(abs(t) / 64), condO[sm[ly + 1 + ya][lx + 1 + xa]]);
-                    v = __fadd_rn(v, __fmul_rn((float)t, factor));
-                    n = __fadd_rn(n, factor);
-                }
+    for (int k = 0; k < TT_H / 2; k++) {
+        const int ly = ly0 + k, y = by + ly;
+#pragma unroll
+        for (int q = 0; q < 3; q++) w2[q] = sc[ly + 2][lx + q];
+        if (y < zy + zh) {
+            float n = 0.01f;
+            float v = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {  // xa = q - 1; ya = -1, 0, 1
+                v = __fadd_rn(v, w0[q].x); n = __fadd_rn(n, w0[q].y);
+                v = __fadd_rn(v, w1[q].x); n = __fadd_rn(n, w1[q].y);
+                v = __fadd_rn(v, w2[q].x); n = __fadd_rn(n, w2[q].y);
             }
+            const int t0 = st[ly + 1][lx + 1];
+            const uint8_t m0 = sm[ly + 1][lx + 1];
+            int nt;
+            if (v != 0.0f) {
+                float cs = condS[m0];
+                float a = __fmul_rn(__fdiv_rn(v, n), cs);
+                float b = __fmul_rn((float)t0, __fsub_rn(1.0f, cs));
+                float r = __fadd_rn(__fadd_rn((float)addT[m0], a), b);
+                nt = (int)r;  // i32 newTemps[] (world.hpp), truncation toward zero
+            } else {
+                nt = (int)(addT[m0] + (uint32_t)t0);  // unsigned wrap, as u32 + i16 in the reference
+            }
+            out[(size_t)y * W + x] = (int16_t)nt;  // real_tiles[].temperature = newTemps[] (i16 wrap)
+            // active-region tracking: a temperature change can arm a reaction (world.cpp:1181-1204) in a sleeping chunk
+            if (awake && (int16_t)nt != (int16_t)t0 && (T->lut.mflags[m0] & MF_REACT)) awake[((y + yoff) / CHUNK) * acols + x / CHUNK] = 1;
         }
-        const int t0 = st[ly + 1][lx + 1];
-        const uint8_t m0 = sm[ly + 1][lx + 1];
-        int nt;
-        if (v != 0.0f) {
-            float cs = condS[m0];
-            float a = __fmul_rn(__fdiv_rn(v, n), cs);
-            float b = __fmul_rn((float)t0, __fsub_rn(1.0f, cs));
-            float r = __fadd_rn(__fadd_rn((float)addT[m0], a), b);
-            nt = (int)r;  // i32 newTemps[] (world.hpp), truncation toward zero
-        } else {
-            nt = (int)(addT[m0] + (uint32_t)t0);  // unsigned wrap, as u32 + i16 in the reference
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            w0[q] = w1[q];
+            w1[q] = w2[q];
         }
-        out[(size_t)y * W + x] = (int16_t)nt;  // real_tiles[].temperature = newTemps[] (i16 wrap)
-        // active-region tracking: a temperature change can arm a reaction (world.cpp:1181-1204) in a sleeping chunk
-        if (awake && (int16_t)nt != (int16_t)t0 && (T->lut.mflags[m0] & MF_REACT)) awake[((y + yoff) / CHUNK) * acols + x / CHUNK] = 1;
     }
 }
 
@@ -230,10 +257,10 @@ cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, int yo
 }
 size_t dev_stats_bytes() { return sizeof(DevStats); }
 
-cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int zx, int zy, int zw, int zh, const DevTables* T, uint8_t* awake,
+cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int H, int zx, int zy, int zw, int zh, const DevTables* T, uint8_t* awake,
                                int acols, int yoff, cudaStream_t s) {
     dim3 grid((zw + TT_W - 1) / TT_W, (zh + TT_H - 1) / TT_H);
-    temperature_kernel<<<grid, 256, 0, s>>>(p.mat, p.tmp, scratch, W, zx, zy, zw, zh, T, awake, acols, yoff);
+    temperature_kernel<<<grid, 256, 0, s>>>(p.mat, p.tmp, scratch, W, H, zx, zy, zw, zh, T, awake, acols, yoff);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     copy_zone_i16_kernel<<<grid_for((size_t)zw * zh, 256), 256, 0, s>>>(scratch, p.tmp, W, zx, zy, zw, zh);

@@ -766,7 +766,7 @@ FSE_API int fse_tick_temperature(fse_world* w, const fse_rect* zg) {
     if (z->w <= 0 || z->h <= 0 || z->x < 1 || z->y - w->y_off < 1 || z->x + z->w + 1 > w->W || z->y - w->y_off + z->h + 1 > w->H)
         return fail(FSE_EINVAL, "fse_tick_temperature: zone (%d,%d,%d,%d) needs a 1-cell margin inside the world", z->x, z->y, z->w, z->h);
     CK(cudaSetDevice(w->ctx->device));
-    CK(launch_temperature(w->p, w->tmp_scratch, w->W, z->x, z->y - w->y_off, z->w, z->h, w->ctx->d_tabs, w->active_on ? w->d_awake : nullptr,
+    CK(launch_temperature(w->p, w->tmp_scratch, w->W, w->H, z->x, z->y - w->y_off, z->w, z->h, w->ctx->d_tabs, w->active_on ? w->d_awake : nullptr,
                           w->acols, w->y_off, w->stream));
     w->ctx->launches += 2;
     if (w->strip && w->ctx->nranks > 1) return strip_refresh(w, w->stream);

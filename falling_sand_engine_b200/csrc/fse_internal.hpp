@@ -126,6 +126,6 @@ cudaError_t launch_fill_air(Planes p, size_t n, uint8_t air, cudaStream_t s);
 cudaError_t launch_clear_dirty(Planes p, size_t n, cudaStream_t s);
 cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, int yoff, const DevTables* T, void* out, cudaStream_t s);
 size_t dev_stats_bytes();
-cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int zx, int zy, int zw, int zh, const DevTables* T, uint8_t* awake,
+cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int H, int zx, int zy, int zw, int zh, const DevTables* T, uint8_t* awake,
                                int acols, int yoff, cudaStream_t s);
 }  // namespace fse
