@@ -111,6 +111,9 @@ FSE_API int fse_materials_set(fse_ctx* c, const fse_material* tbl, int n, const 
         if (m.physics == FSE_SAND && (m.slipperyness < 1 || m.slipperyness > 255))
             return fail(FSE_EINVAL, "material %d: SAND needs 1 <= slipperyness <= 255 (reference divides by it, world.cpp:1656)", i);
         if (m.iterations < 0) return fail(FSE_EINVAL, "material %d: negative iterations", i);
+        if (!std::isfinite(m.conduction_self) || !std::isfinite(m.conduction_other) || !std::isfinite(m.density))
+            return fail(FSE_EINVAL, "material %d: conduction / density must be finite (the temperature kernel adds the zero contribution of a "
+                                    "neighbour at temperature 0 instead of skipping it, world.cpp:1976)", i);
         Lut& L = h.lut;
         h.phys[i] = (uint8_t)m.physics;
         L.phys[i] = (uint8_t)m.physics;

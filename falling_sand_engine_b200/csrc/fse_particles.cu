@@ -217,7 +217,7 @@ static cudaError_t grow(void** p, size_t* have, size_t need) {
     cudaFree(*p);
     *p = nullptr;
     *have = 0;
-    size_t n = need + need / 4;
+    size_t n = need + need / 2 + (1 << 20);  // head room: a growing particle pool should not reallocate on every call
     cudaError_t e = cudaMalloc(p, n);
     if (e == cudaSuccess) *have = n;
     return e;

@@ -282,3 +282,36 @@ def test_small_phases_pick_the_fused_kernel_with_identical_results(oracle, gpu_c
     n0 = gpu_ctx.launch_count()
     gw.tick(3, seed=5)
     assert gpu_ctx.launch_count() - n0 == 12  # one (fused) kernel per colour phase
+
+
+@pytest.mark.parametrize("seed", [11, 23, 37])
+@pytest.mark.parametrize("sched", ["rows", "rows_graph", "rows_fused"])
+def test_random_worlds_long_runs(oracle, gpu_ctx, table, sched, seed):
+    """Longer runs of the whole game loop (tick + tickCells + tickTemperature every 4th tick + camera scroll + render planes) on
+    small-blob worlds of different seeds and shapes: every plane, the particle pool and the textures stay bit-identical."""
+    from oracle import pyoracle as O
+    W, H = 512 + 128 * (seed % 3), 384 + 128 * (seed % 2)
+    tbl, extra = G.bench_table(table)
+    ow, gw = _pair(oracle, gpu_ctx, tbl, W, H, sched)
+    Hh.build_mixed(ow, tbl, W, H, seed=seed, extra=list(extra.values()), blob=16)
+    Hh.build_mixed(gw, tbl, W, H, seed=seed, extra=list(extra.values()), blob=16)
+    gw.pixels_enable(True)
+    planes = [np.zeros((H, W, 4), dtype=np.uint8) for _ in range(3)]
+    for t in range(30):
+        for w in (ow, gw):
+            w.tick(t, seed=seed)
+            w.particles_tick()
+            if t % 4 == 2:
+                w.tick_temperature()
+        if t == 13:
+            O.scroll(ow, -128, 0)
+            gw.scroll(-128, 0)
+        O.render_dirty(ow, planes)
+        gw.render_dirty(want_stats=False)
+        ow.clear_dirty()
+        gw.clear_dirty()
+        if t % 6 == 5:
+            Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"{sched} seed {seed} tick {t}")
+            Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), f"{sched} seed {seed} tick {t}")
+            for which in range(3):
+                assert np.array_equal(planes[which], gw.pixels_read(which)), (t, which)
