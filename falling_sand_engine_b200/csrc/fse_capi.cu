@@ -560,7 +560,7 @@ FSE_API int fse_debug_role_cycles(fse_world* w, int enable, unsigned long long* 
     }
     if (out && w->d_dbg) {
         CK(cudaStreamSynchronize(w->stream));
-        CK(cudaMemcpy(out, w->d_dbg, 256, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out, w->d_dbg, 512, cudaMemcpyDeviceToHost));
         CK(cudaMemset(w->d_dbg, 0, 512));
     }
     if (!enable && w->d_dbg) {

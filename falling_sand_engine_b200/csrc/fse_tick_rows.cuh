@@ -981,6 +981,9 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
 #ifndef FSE_PASS_PF
 #define FSE_PASS_PF 2
 #endif
+#ifndef FSE_P2_PF
+#define FSE_P2_PF FSE_PASS_PF
+#endif
 #ifndef FSE_PASS_MINB
 #define FSE_PASS_MINB 5
 #endif
@@ -992,9 +995,15 @@ struct PassGeom {
     static constexpr int LAST = CHUNK - 1 + UP;
     static constexpr int SL = UP + 1;                     // a row is final SL steps after its own step
     static constexpr int RN = PASS == 1 ? FSE_P1_RN : FSE_P2_RN;  // rows in the window: live rows + rows in flight
-    static constexpr int PF = FSE_PASS_PF;                // rows loaded ahead of the step that needs them
-    static constexpr int THREADS = 160;
+    static constexpr int PF = PASS == 1 ? FSE_PASS_PF : FSE_P2_PF;  // rows loaded ahead of the step that needs them
+    // pass 2 is bound by its IO warp (7 bulk copies per row are issued one lane after the other, ~90 cycles each): there the
+    // store side and the load side get a warp each.  Pass 1 (72 registers) stays at 5 warps to keep 5 CTAs per SM.
+    static constexpr int THREADS = PASS == 2 ? 192 : 160;
 };
+// A slot that is loaded at step st was stored at step st + UP + PF - RN + SL.  With two IO warps the loader does not see the storer's
+// bulk groups; it relies on the storer's wait_group.read 1 of the step before (ordered by the step barrier), which covers stores
+// issued two or more steps ago.
+static_assert(PassGeom<2>::UP + PassGeom<2>::PF - PassGeom<2>::RN + PassGeom<2>::SL <= -2, "pass 2: split IO warps need the slot's store two steps old");
 // pass 1: live rows st-5..st+5; the row loaded at step st (st+7) takes the slot of row st-7, whose store was issued a step earlier
 // pass 2: live rows st-10..st+1; the row loaded at step st (st+3) takes the slot of row st-11
 static_assert(PassGeom<1>::UP + PassGeom<1>::PF - PassGeom<1>::RN <= -PassGeom<1>::SL, "pass 1 window");
@@ -1091,7 +1100,8 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     unsigned char* const smem_raw = fse_smem;
     SmemPass<PASS>& S = *reinterpret_cast<SmemPass<PASS>*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool io = warp == G::THREADS / 32 - 1;
+    // warps 0-3 compute; warp 4 stores rows back; the last warp loads rows (the same warp in a 160-thread CTA)
+    const bool io = warp >= 4, io_store = warp == 4, io_load = warp == (int)(blockDim.x >> 5) - 1;
     const long long t_begin = (PASS == 1 && cost_slot) ? clock64() : 0;
     const DevTables* T = P.tabs;
     {
@@ -1125,7 +1135,7 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     __syncthreads();
     // row k lives in slot (k - KMIN) % RN and is the ((k - KMIN) / RN)-th user of that slot's mbarrier
     const PlaneIO pio = plane_io(P, lane < 7 ? lane : 0, cx);
-    if (io) {
+    if (io_load) {
 #pragma unroll 1
         for (int k = G::KMIN; k < G::UP + G::PF; k++) {
             wait_row(k, lane);
@@ -1138,6 +1148,7 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     bool io_modified = false, io_inert = true;  // active-chunk tracking (IO warp): see tick_chunk_kernel
 #ifdef FSE_ROLE_CYCLES
     long long dbg_t[4] = {0, 0, 0, 0};  // mbarrier wait, step barrier, step work, steps
+    long long dbg_io[3] = {0, 0, 0};    // IO lane 0: store side, wait for the slot's old store to leave shared memory, load issue
 #define FSE_STEP_CLOCK(i, since) do { const long long now_ = clock64(); dbg_t[i] += now_ - (since); (since) = now_; } while (0)
     long long dbg_c = clock64();
 #else
@@ -1160,8 +1171,14 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                 else pass2_rows<G::RN>(c, reinterpret_cast<Scratch2&>(S.rs), st, cx, cy, tid);
             }
         } else {
+#ifdef FSE_ROLE_CYCLES
+            long long io_c = clock64();
+#define FSE_IO_CLOCK(i) do { const long long now_ = clock64(); dbg_io[i] += now_ - io_c; io_c = now_; } while (0)
+#else
+#define FSE_IO_CLOCK(i) do { } while (0)
+#endif
             const int ks = st - G::SL;
-            if (ks >= G::FULL_LO && ks <= G::LAST) {
+            if (io_store && ks >= G::FULL_LO && ks <= G::LAST) {
                 const int q = (ks - G::KMIN) % G::RN;
                 uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
                 const bool core_row = ks >= 0 && ks < CHUNK;
@@ -1186,17 +1203,24 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                 if (all_store ? lane < 7 : (vis_store && lane == 1))
                     bulk_s2g(pio.g + (size_t)(cy + CHUNK - 1 - ks) * pio.row_stride, S.ring + q * ROW_BYTES + pio.soff, pio.bytes);
             }
-            bulk_commit();  // one (possibly empty) bulk group per lane and step, so wait_group counts steps
             const int kl = st + G::UP + G::PF;
-            if (kl <= G::LAST) {
-                // each lane waits until its own stores out of the slot to fill have left shared memory (bulk groups are per
-                // thread): with one spare row in the window that store was issued a step ago and this does not stall
-                if (G::UP + G::PF - G::RN < -G::SL) bulk_wait_read<1>();
-                else bulk_wait_read<0>();
+            if (io_store) {
+                bulk_commit();  // one (possibly empty) bulk group per lane and step, so wait_group counts steps
+                FSE_IO_CLOCK(0);
+                if (kl <= G::LAST) {
+                    // each lane waits until its own stores out of the slot to fill have left shared memory (bulk groups are per
+                    // thread): with one spare row in the window that store was issued a step ago and this does not stall
+                    if (G::UP + G::PF - G::RN < -G::SL) bulk_wait_read<1>();
+                    else bulk_wait_read<0>();
+                }
+                FSE_IO_CLOCK(1);
+            }
+            if (io_load && kl <= G::LAST) {
                 wait_row(kl, lane);
                 pass_row_load<PASS>(S, pio, lane, kl, cy);
+                FSE_IO_CLOCK(2);
             }
-            if (PIPE && PASS == 1 && st >= PIPE_D + G::SL && (st & 3) == 0) {
+            if (PIPE && PASS == 1 && io_store && st >= PIPE_D + G::SL && (st & 3) == 0) {
                 // the stores of the steps up to st - PIPE_D have completed: rows FULL_LO .. st - PIPE_D - SL are final in HBM.
                 // Every lane waits for its own plane's bulk groups; lane 0 publishes for all of them (one fence per 4 steps)
                 asm volatile("cp.async.bulk.wait_group %0;" ::"n"(PIPE_D) : "memory");
@@ -1214,22 +1238,23 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
         atomicAdd(&P.dbg[0], 1ULL);
         for (int q = 0; q < 10; q++) atomicAdd(&P.dbg[1 + q], (unsigned long long)reinterpret_cast<Scratch1&>(S.rs).dbg_phase[q]);
     }
-    if (P.dbg && (tid == 0 || tid == G::THREADS - 32)) {  // compute thread 0 and IO lane 0: where the step time goes
+    if (P.dbg && (tid == 0 || tid == 128)) {  // compute thread 0 and (store) IO lane 0: where the step time goes
         unsigned long long* o = P.dbg + 16 + (PASS - 1) * 8 + (tid ? 4 : 0);
         FSE_STEP_CLOCK(2, dbg_c);
         for (int q = 0; q < 3; q++) atomicAdd(&o[q], (unsigned long long)dbg_t[q]);
         atomicAdd(&o[3], 1ULL);
+        if (tid) for (int q = 0; q < 3; q++) atomicAdd(&P.dbg[32 + (PASS - 1) * 4 + q], (unsigned long long)dbg_io[q]);
     }
 #endif
     if (PASS == 1 && cost_slot && tid == 0) *cost_slot = (unsigned int)(clock64() - t_begin);
-    if (io && P.chunk_state) {
+    if (io_store && P.chunk_state) {
         const bool inert = __all_sync(0xffffffffu, io_inert);
         const unsigned int st = (io_modified ? 1u : 0u) | ((PASS == 2 && !inert) ? 2u : 0u);
         unsigned int* slot = P.chunk_state + ((cy + P.y_off) / CHUNK) * P.acols + cx / CHUNK;
         if (lane == 0) *slot = PASS == 1 ? st : (*slot | st);  // pass 1 starts the record, pass 2 adds to it (same stream)
     }
-    if (io) bulk_wait_all();
-    if (PIPE && PASS == 1 && io) {
+    if (io_store) bulk_wait_all();
+    if (PIPE && PASS == 1 && io_store) {
         asm volatile("fence.proxy.async;" ::: "memory");
         __threadfence();
         __syncwarp();

@@ -22,7 +22,7 @@ elif workload != "air":
         w.write_rect(0, y0, G.cells_from_mat(table, mat[y0:y0 + 1024], 0, y0, 7))
 for t in range(2 if workload != 'mixed' else 5): w.tick(t)
 w.L.fse_debug_role_cycles.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-out = (C.c_uint64 * 32)()
+out = (C.c_uint64 * 64)()
 w.L.fse_debug_role_cycles(w.h, 1, None)
 for t in range(5, 8): w.tick(t)
 w.L.fse_debug_role_cycles(w.h, 1, out)
@@ -35,3 +35,7 @@ for ps in (0, 1):
         o = out[16 + ps * 8 + off: 16 + ps * 8 + off + 4]
         m = max(o[3], 1)
         print("pass %d %-16s per chunk: mbarrier wait %.0f  step barrier %.0f  work %.0f cycles" % (ps + 1, who, o[0] / m, o[1] / m, o[2] / m))
+for ps in (0, 1):
+    m = max(out[16 + ps * 8 + 4 + 3], 1)
+    o = out[32 + ps * 4: 32 + ps * 4 + 3]
+    print("pass %d IO lane 0 per chunk: store side %.0f  wait for the old store to leave the slot %.0f  load issue %.0f cycles" % (ps + 1, o[0] / m, o[1] / m, o[2] / m))
