@@ -546,6 +546,7 @@ static int build_strip_lists(fse_world* w, const fse_rect& z, int j0, int j1) {
     CK(cudaMalloc(&w->d_chunk_lists, sizeof(int) * (all.size() + 1)));
     if (!all.empty()) CK(cudaMemcpy(w->d_chunk_lists, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice));
     w->list_zone = z;
+    memset(w->lpt_sig, 0, sizeof(w->lpt_sig));
     return FSE_OK;
 }
 
@@ -744,9 +745,38 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             }
             CK(cudaEventRecord(w->ev_comm, w->comm_stream));
             if (w->list_cnt[tk][1] > 0) {
-                P.chunk_list = w->d_chunk_lists + w->list_off[tk][1];
+                const int n_int = w->list_cnt[tk][1], n_grid = P.ncx * P.ncy;
+                const int* base_list = w->d_chunk_lists + w->list_off[tk][1];
+                P.chunk_list = base_list;
+                // longest-first order of the interior chunks, as on plain worlds: the cost array covers the colour's whole chunk grid,
+                // the sorted list only this rank's interior chunks
+                const bool lpt = w->lpt_on && w->schedule == FSE_SCHEDULE_ROWS && !w->fused && n_int >= w->fork.min_chunks && n_int > w->fused_max_chunks;
+                if (lpt) {
+                    if (n_grid > w->lpt_cap) {
+                        cudaFree(w->d_lpt_cost);
+                        cudaFree(w->d_lpt_list);
+                        w->d_lpt_cost = nullptr;
+                        w->d_lpt_list = nullptr;
+                        w->lpt_cap = 0;
+                        CK(cudaMalloc((void**)&w->d_lpt_cost, sizeof(unsigned int) * 4 * (size_t)n_grid));
+                        CK(cudaMalloc((void**)&w->d_lpt_list, sizeof(int) * 4 * (size_t)n_grid));
+                        CK(cudaMemsetAsync(w->d_lpt_cost, 0, sizeof(unsigned int) * 4 * (size_t)n_grid, w->stream));
+                        w->lpt_cap = n_grid;
+                        memset(w->lpt_sig, 0, sizeof(w->lpt_sig));
+                    }
+                    const int sig[4] = {P.x0 ^ (w->list_off[tk][1] << 8), P.y0, P.ncx, n_int};
+                    if (memcmp(sig, w->lpt_sig[tk], sizeof(sig)) == 0) P.chunk_list = w->d_lpt_list + (size_t)tk * w->lpt_cap;
+                    P.chunk_cost = w->d_lpt_cost + (size_t)tk * w->lpt_cap;
+                }
                 int nl = 0;
-                CK(launch_tick_phase(P, w->list_cnt[tk][1], w->stream, &nl, &w->fork));
+                CK(launch_tick_phase(P, n_int, w->stream, &nl, &w->fork));
+                if (lpt) {
+                    CK(launch_lpt_build(P.chunk_cost, n_int, P.ncx, w->d_lpt_list + (size_t)tk * w->lpt_cap, w->stream, base_list));
+                    nl += 1;
+                    const int sig[4] = {P.x0 ^ (w->list_off[tk][1] << 8), P.y0, P.ncx, n_int};
+                    memcpy(w->lpt_sig[tk], sig, sizeof(sig));
+                    P.chunk_cost = nullptr;
+                }
                 w->ctx->launches += nl;
             }
             if (int r = kt.end(w->stream)) return r;

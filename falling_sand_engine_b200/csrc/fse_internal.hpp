@@ -116,7 +116,7 @@ int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cuda
 int strip_refresh(fse_world* w, cudaStream_t s);
 size_t tick_smem_bytes();
 cudaError_t launch_tick_graph(const GraphParams& G, int grid, cudaStream_t stream);  // whole tick, one launch
-cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream);
+cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream, const int* members = nullptr);
 cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched, const TickFork* fork);  // *launched = kernels enqueued
 cudaError_t launch_compact_active(const uint8_t* awake, int acols, int ci0, int cj0, int ncx, int ncy, int* list, int* count, cudaStream_t s);
 

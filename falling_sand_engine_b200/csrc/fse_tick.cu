@@ -1135,6 +1135,7 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         for (int q = 0; q < parts; q++) {
             cudaStream_t st = q ? fork->aux[q - 1] : stream;
             const int lo = pairs + (int)((long long)rest * q / parts), hi = pairs + (int)((long long)rest * (q + 1) / parts);
+            if (hi <= lo) continue;  // fewer chunks than parts
             Q.chunk_base = P.chunk_base + lo;
             tick_pass_kernel<1><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>) + pad, st>>>(Q);
             tick_pass_kernel<2><<<hi - lo, PassGeom<2>::THREADS, sizeof(SmemPass<2>) + pad, st>>>(Q);
@@ -1177,8 +1178,8 @@ cudaError_t launch_tick_graph(const GraphParams& G, int grid, cudaStream_t strea
     return cudaGetLastError();
 }
 
-cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream) {
-    lpt_build_kernel<<<1, 1024, 0, stream>>>(cost, n, ncx, list);
+cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream, const int* members) {
+    lpt_build_kernel<<<1, 1024, 0, stream>>>(cost, n, ncx, list, members);
     return cudaGetLastError();
 }
 

@@ -1567,18 +1567,21 @@ __global__ void apply_chunk_state_kernel(const TickParams P, int n) {
 // Longest-first launch order for the next tick: chunks of a colour are binned by the cycles pass 1 took on them this tick
 // (64 bins, heaviest bin first).  A phase is ~1.3 waves of CTAs, so starting the expensive chunks first shortens its tail;
 // chunks of a phase are independent, the order cannot change results.
-__global__ void __launch_bounds__(1024) lpt_build_kernel(const unsigned int* cost, int n, int ncx, int* list) {
+// `members` (optional): the n chunks to order, as (cxi | cyi << 16); otherwise all chunks 0..n-1 of the colour's grid.
+__global__ void __launch_bounds__(1024) lpt_build_kernel(const unsigned int* cost, int n, int ncx, int* list, const int* members) {
     __shared__ unsigned int hist[64], base[64], maxc;
     const int tid = threadIdx.x;
     if (tid < 64) hist[tid] = 0;
     if (tid == 0) maxc = 0;
     __syncthreads();
+    auto entry = [&](int i) { return members ? members[i] : ((i % ncx) | ((i / ncx) << 16)); };
+    auto cost_of = [&](int v) { return cost[(v >> 16) * ncx + (v & 0xffff)]; };
     unsigned int m = 0;
-    for (int i = tid; i < n; i += blockDim.x) m = max(m, cost[i]);
+    for (int i = tid; i < n; i += blockDim.x) m = max(m, cost_of(entry(i)));
     atomicMax(&maxc, m);
     __syncthreads();
     const unsigned long long scale = (unsigned long long)maxc + 1;
-    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[63 - (int)((unsigned long long)cost[i] * 64 / scale)], 1u);
+    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[63 - (int)((unsigned long long)cost_of(entry(i)) * 64 / scale)], 1u);
     __syncthreads();
     if (tid == 0) {
         unsigned int acc = 0;
@@ -1589,8 +1592,9 @@ __global__ void __launch_bounds__(1024) lpt_build_kernel(const unsigned int* cos
     }
     __syncthreads();
     for (int i = tid; i < n; i += blockDim.x) {
-        const unsigned int pos = atomicAdd(&base[63 - (int)((unsigned long long)cost[i] * 64 / scale)], 1u);
-        list[pos] = (i % ncx) | ((i / ncx) << 16);
+        const int v = entry(i);
+        const unsigned int pos = atomicAdd(&base[63 - (int)((unsigned long long)cost_of(v) * 64 / scale)], 1u);
+        list[pos] = v;
     }
 }
 

@@ -24,11 +24,13 @@ def _ngpu():
 def test_strips_match_oracle(oracle, table, tmp_path, nranks):
     if _ngpu() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
-    W, H, ticks = 512, 1280, 8
+    W, H, ticks = 1024, 1536, 8
     out = str(tmp_path / "strip")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
            "--master-port", str(29600 + nranks), os.path.join(ROOT, "tests", "strip_gpu_worker.py"), str(W), str(H), str(ticks), out]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    # small strips: force the large-world machinery (per-pass kernels in parts on streams, longest-first order of the interior chunks)
+    env = dict(os.environ, FSE_TICK_MIN_CHUNKS="1", FSE_FUSED_MAX_CHUNKS="0")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     ow = oracle.OracleWorld(W, H, table)
     ow.write_rect(0, 0, G.mixed_band(table, W, H, 0, H, seed=77, blob=32))
