@@ -215,6 +215,7 @@ static void free_world(fse_world* w) {
     if (w->ev_comm) cudaEventDestroy(w->ev_comm);
     cudaFree(w->d_chunk_lists);
     cudaFree(w->d_awake); cudaFree(w->d_active_list); cudaFree(w->d_active_count);
+    cudaFree(w->part_list);
     cudaFree(w->d_pixels); cudaFree(w->d_render_stats); cudaFree(w->scroll_scratch);
     if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
     if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);

@@ -47,6 +47,8 @@ struct fse_world {
     // particle settle scratch (fse_particles.cu)
     void* part_scratch = nullptr;
     size_t part_scratch_bytes = 0;
+    void* part_list = nullptr;  // indices of the particles that take part in the deposit rounds
+    size_t part_list_bytes = 0;
     fse_particle* pbuf2 = nullptr;  // compaction target, swapped with pbuf every fse_particles_tick
     size_t pbuf2_bytes = 0;
     void* claim_keys = nullptr;

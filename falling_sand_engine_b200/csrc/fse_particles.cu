@@ -36,6 +36,8 @@ struct PArgs {
     unsigned int tmask;
     uint8_t* awake;  // active-region flags (null = off)
     int acols, arows;
+    unsigned int* list;    // particles that hit something (indices into st), appended by the integrate kernel
+    unsigned int n_list;   // entries of list the deposit rounds run over
 };
 
 __device__ __forceinline__ int phys_at(const PArgs& a, int x, int y) { return a.T->phys[a.p.mat[(size_t)y * a.W + x]]; }
@@ -96,7 +98,7 @@ __global__ void particles_integrate_kernel(PArgs a) {
     } while (false);
     s.adv = cur;
     a.st[i] = s;
-    if (s.status >= 2) atomicAdd(&a.counters[1], 1u);
+    if (s.status >= 2) a.list[atomicAdd(&a.counters[1], 1u)] = i;  // the deposit rounds only visit these (order is irrelevant: ids decide)
 }
 
 __device__ __forceinline__ unsigned int hash_cell(long long c) {
@@ -105,9 +107,9 @@ __device__ __forceinline__ unsigned int hash_cell(long long c) {
 }
 
 __global__ void particles_propose_kernel(PArgs a) {
-    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    PState* sp = &a.st[i];
+    const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= a.n_list) return;
+    PState* sp = &a.st[a.list[li]];
     int status = sp->status;
     if (status < 2) return;
     const int W = a.W, H = a.H;
@@ -165,9 +167,9 @@ __global__ void particles_propose_kernel(PArgs a) {
 }
 
 __global__ void particles_commit_kernel(PArgs a) {
-    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    PState* sp = &a.st[i];
+    const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= a.n_list) return;
+    PState* sp = &a.st[a.list[li]];
     if (sp->status < 2) return;
     const long long cand = sp->cand;
     unsigned int h = hash_cell(cand) & a.tmask;
@@ -245,6 +247,7 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     if (n == 0) return FSE_OK;
     CK(grow(&w->part_scratch, &w->part_scratch_bytes, sizeof(PState) * (size_t)n));
     CK(grow((void**)&w->pbuf2, &w->pbuf2_bytes, sizeof(fse_particle) * (size_t)w->pcap));
+    CK(grow((void**)&w->part_list, &w->part_list_bytes, sizeof(unsigned int) * (size_t)n));
     PArgs a;
     a.p = w->p;
     a.T = w->ctx->d_tabs;
@@ -257,6 +260,8 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     a.keys = nullptr; a.vals = nullptr; a.tmask = 0;
     a.awake = w->active_on ? w->d_awake : nullptr;
     a.acols = w->acols; a.arows = w->arows;
+    a.list = (unsigned int*)w->part_list;
+    a.n_list = 0;
     const int B = 128;
     const int G = (int)((n + B - 1) / B);
     CK(cudaMemsetAsync(w->pcount + 1, 0, 2 * sizeof(unsigned int), w->stream));
@@ -266,6 +271,8 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     unsigned int pending = 0;
     CK(cudaMemcpyAsync(&pending, w->pcount + 1, sizeof pending, cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
+    a.n_list = pending;  // every particle that hit something; the ones that are done drop out by their status byte
+    const int GL = (int)((pending + B - 1) / B);
     for (int round = 0; round < FSE_PARTICLE_ROUNDS && pending > 0; round++) {
         size_t tsz = 1024;
         while (tsz < (size_t)pending * 2) tsz <<= 1;
@@ -277,9 +284,9 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
         a.keys = (long long*)w->claim_keys;
         a.vals = (unsigned long long*)w->claim_vals;
         a.tmask = (unsigned int)(tsz - 1);
-        particles_propose_kernel<<<G, B, 0, w->stream>>>(a);
+        particles_propose_kernel<<<GL, B, 0, w->stream>>>(a);
         CK(cudaGetLastError());
-        particles_commit_kernel<<<G, B, 0, w->stream>>>(a);
+        particles_commit_kernel<<<GL, B, 0, w->stream>>>(a);
         CK(cudaGetLastError());
         w->ctx->launches += 2;
         CK(cudaMemcpyAsync(&pending, w->pcount + 1, sizeof pending, cudaMemcpyDeviceToHost, w->stream));
