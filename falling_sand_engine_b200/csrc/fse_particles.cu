@@ -38,6 +38,8 @@ struct PArgs {
     int acols, arows;
     unsigned int* list;    // particles that hit something (indices into st), appended by the integrate kernel
     unsigned int n_list;   // entries of list the deposit rounds run over
+    const unsigned int* prev_pending;  // particles still pending after the previous round (null in round 0): 0 = nothing left to do
+    unsigned int* my_pending;          // this round's count
 };
 
 __device__ __forceinline__ int phys_at(const PArgs& a, int x, int y) { return a.T->phys[a.p.mat[(size_t)y * a.W + x]]; }
@@ -108,7 +110,7 @@ __device__ __forceinline__ unsigned int hash_cell(long long c) {
 
 __global__ void particles_propose_kernel(PArgs a) {
     const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= a.n_list) return;
+    if (li >= a.n_list || (a.prev_pending && *a.prev_pending == 0)) return;
     PState* sp = &a.st[a.list[li]];
     int status = sp->status;
     if (status < 2) return;
@@ -168,14 +170,14 @@ __global__ void particles_propose_kernel(PArgs a) {
 
 __global__ void particles_commit_kernel(PArgs a) {
     const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= a.n_list) return;
+    if (li >= a.n_list || (a.prev_pending && *a.prev_pending == 0)) return;
     PState* sp = &a.st[a.list[li]];
     if (sp->status < 2) return;
     const long long cand = sp->cand;
     unsigned int h = hash_cell(cand) & a.tmask;
     while (a.keys[h] != cand) h = (h + 1) & a.tmask;
     if (a.vals[h] != (unsigned long long)sp->adv.id) {
-        atomicAdd(&a.counters[1], 1u);  // still pending
+        atomicAdd(a.my_pending, 1u);  // still pending
         return;
     }
     const size_t g = (size_t)cand;
@@ -247,7 +249,7 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     if (n == 0) return FSE_OK;
     CK(grow(&w->part_scratch, &w->part_scratch_bytes, sizeof(PState) * (size_t)n));
     CK(grow((void**)&w->pbuf2, &w->pbuf2_bytes, sizeof(fse_particle) * (size_t)w->pcap));
-    CK(grow((void**)&w->part_list, &w->part_list_bytes, sizeof(unsigned int) * (size_t)n));
+    CK(grow((void**)&w->part_list, &w->part_list_bytes, sizeof(unsigned int) * ((size_t)n + 32)));  // + one pending counter per round
     PArgs a;
     a.p = w->p;
     a.T = w->ctx->d_tabs;
@@ -273,24 +275,29 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     CK(cudaStreamSynchronize(w->stream));
     a.n_list = pending;  // every particle that hit something; the ones that are done drop out by their status byte
     const int GL = (int)((pending + B - 1) / B);
-    for (int round = 0; round < FSE_PARTICLE_ROUNDS && pending > 0; round++) {
+    if (pending > 0) {
+        // All rounds are enqueued back to back: a round whose predecessor left nothing pending returns at once, so the host does not
+        // have to read a counter between rounds.  The claim table is sized for the first round, the fullest one.
         size_t tsz = 1024;
         while (tsz < (size_t)pending * 2) tsz <<= 1;
         CK(grow((void**)&w->claim_keys, &w->claim_keys_bytes, tsz * sizeof(long long)));
         CK(grow((void**)&w->claim_vals, &w->claim_vals_bytes, tsz * sizeof(unsigned long long)));
-        CK(cudaMemsetAsync(w->claim_keys, 0xff, tsz * sizeof(long long), w->stream));
-        CK(cudaMemsetAsync(w->claim_vals, 0xff, tsz * sizeof(unsigned long long), w->stream));
-        CK(cudaMemsetAsync(w->pcount + 1, 0, sizeof(unsigned int), w->stream));
+        unsigned int* round_cnt = (unsigned int*)w->part_list + n;
+        CK(cudaMemsetAsync(round_cnt, 0, 32 * sizeof(unsigned int), w->stream));
         a.keys = (long long*)w->claim_keys;
         a.vals = (unsigned long long*)w->claim_vals;
         a.tmask = (unsigned int)(tsz - 1);
-        particles_propose_kernel<<<GL, B, 0, w->stream>>>(a);
-        CK(cudaGetLastError());
-        particles_commit_kernel<<<GL, B, 0, w->stream>>>(a);
-        CK(cudaGetLastError());
-        w->ctx->launches += 2;
-        CK(cudaMemcpyAsync(&pending, w->pcount + 1, sizeof pending, cudaMemcpyDeviceToHost, w->stream));
-        CK(cudaStreamSynchronize(w->stream));
+        for (int round = 0; round < FSE_PARTICLE_ROUNDS; round++) {
+            CK(cudaMemsetAsync(w->claim_keys, 0xff, tsz * sizeof(long long), w->stream));
+            CK(cudaMemsetAsync(w->claim_vals, 0xff, tsz * sizeof(unsigned long long), w->stream));
+            a.prev_pending = round ? round_cnt + round - 1 : nullptr;
+            a.my_pending = round_cnt + round;
+            particles_propose_kernel<<<GL, B, 0, w->stream>>>(a);
+            CK(cudaGetLastError());
+            particles_commit_kernel<<<GL, B, 0, w->stream>>>(a);
+            CK(cudaGetLastError());
+            w->ctx->launches += 2;
+        }
     }
     particles_compact_kernel<<<G, B, 0, w->stream>>>(a, w->pbuf2);
     CK(cudaGetLastError());
