@@ -166,7 +166,7 @@ __device__ __forceinline__ CellR ldc(const Ctx& c, int s, int j) {
 // code stores cells at ~40 places and the kernel is instruction-cache bound (profiles/r1_tick_ncu.md), so one copy of the
 // store sequence beats 40 inlined ones.  p0 = mat | stl << 8 | tmp << 16, p1 = moved | setbits << 8.
 __device__ __forceinline__ void stc_raw(const Ctx* cp, int s, int j, uint32_t p0, uint32_t p1, uint32_t col, float fl, float fd) {
-    const Ctx& c = *cp;
+    (void)cp;
     MAT(s, j) = (uint8_t)p0;
     const uint8_t f = FLG(s, j);
     FLG(s, j) = (uint8_t)((f & (F_DIRTY | F_VISITED)) | (p1 & 0xff) | ((p1 >> 8) & 0xff));
