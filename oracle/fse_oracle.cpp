@@ -951,17 +951,15 @@ void World::tick_particles(const Rect& tz) {
 }
 
 // ---- tickCells under the GPU's schedule (see header) ------------------------------------------
-void World::tick_particles_rounds(const Rect& tz, int max_rounds) {
+// The deposit schedule in stages, so that several strip ranks can run it together (tests/strip_particles_cpu_worker.py): every
+// rank integrates and proposes for the particles it owns, the proposals that target the band around a cut are exchanged, and each
+// rank commits its own and its neighbours' proposals — the lowest id wins a cell wherever it came from, and every rank writes the
+// winners' cells it holds.  tick_particles_rounds() below is the single-world composition of the same stages.
+void World::prt_begin(const Rect& tz) {
     const int W = width, H = height;
-    struct St {
-        int status = 0;  // 0 alive, 1 dead, 2 wants its start cell, 3 spiral search
-        Particle adv;
-        int lx = 0, ly = 0;
-        int sx = 0, sy = 0, sdx = 0, sdy = -1, sj = 0;
-        long cand = -1;
-        bool merge = false;
-    };
-    std::vector<St> st(cells.size());
+    typedef PrtState St;
+    std::vector<St>& st = prt;
+    st.assign(cells.size(), St());
     // phase 1: integrate every particle against the unmodified grid (world.cpp:2032-2174)
     for (size_t i = 0; i < cells.size(); i++) {
         St& s = st[i];
@@ -1013,11 +1011,15 @@ void World::tick_particles_rounds(const Rect& tz, int max_rounds) {
         } while (false);
         s.adv = cur;
     }
-    // phase 2: deposit rounds, lowest id wins a contested cell
-    for (int r = 0; r < max_rounds; r++) {
-        std::vector<std::pair<long, uint64_t>> claims;
-        bool any = false;
-        for (size_t i = 0; i < cells.size(); i++) {
+}
+
+int World::prt_propose() {
+    const int W = width, H = height;
+    typedef PrtState St;
+    std::vector<St>& st = prt;
+    prt_props.clear();
+    bool any = false;
+    for (size_t i = 0; i < cells.size(); i++) {
             St& s = st[i];
             if (s.status < 2) continue;
             s.cand = -1;
@@ -1053,33 +1055,91 @@ void World::tick_particles_rounds(const Rect& tz, int max_rounds) {
                     continue;
                 }
             }
-            claims.push_back({s.cand, cur.id});
+            fseo_proposal pr;
+            std::memset(&pr, 0, sizeof pr);
+            pr.cell = s.cand;
+            pr.id = cur.id;
+            pr.tile.mat = (uint16_t)cur.tile.mat->id;
+            pr.tile.color = cur.tile.color;
+            pr.tile.temp = cur.tile.temperature;
+            pr.tile.moved = cur.tile.moved;
+            pr.tile.settle = cur.tile.settleCount;
+            pr.tile.fluid = cur.tile.fluidAmount;
+            pr.tile.fluid_diff = cur.tile.fluidAmountDiff;
+            pr.merge = s.merge ? 1 : 0;
+            prt_props.push_back(pr);
             any = true;
         }
-        if (!any) break;
-        std::sort(claims.begin(), claims.end());
-        auto winner = [&](long cell) {
-            auto it = std::lower_bound(claims.begin(), claims.end(), std::make_pair(cell, (uint64_t)0));
-            return it->second;
-        };
-        for (size_t i = 0; i < cells.size(); i++) {
-            St& s = st[i];
-            if (s.status < 2 || s.cand < 0) continue;
-            if (winner(s.cand) != s.adv.id) continue;
-            if (s.merge) tiles[s.cand].fluidAmount += s.adv.tile.fluidAmount;  // 2131-2136
-            else tiles[s.cand] = s.adv.tile;                                   // 2127 / 2160
-            dirty[s.cand] = 1;
-            s.status = 1;
-        }
+    (void)any;
+    (void)H;
+    return (int)prt_props.size();
+}
+
+// ext: proposals of other ranks (may be null); rows [hold_lo, hold_hi) are the rows this world holds (all of them in a single world)
+void World::prt_commit(const fseo_proposal* ext, int n_ext, int hold_lo, int hold_hi) {
+    typedef PrtState St;
+    std::vector<St>& st = prt;
+    std::vector<std::pair<long, uint64_t>> claims;
+    claims.reserve(prt_props.size() + (size_t)n_ext);
+    for (const fseo_proposal& pr : prt_props) claims.push_back({(long)pr.cell, pr.id});
+    for (int i = 0; i < n_ext; i++) claims.push_back({(long)ext[i].cell, ext[i].id});
+    std::sort(claims.begin(), claims.end());
+    auto winner = [&](long cell) {
+        auto it = std::lower_bound(claims.begin(), claims.end(), std::make_pair(cell, (uint64_t)0));
+        return it->second;
+    };
+    for (size_t i = 0; i < cells.size(); i++) {
+        St& s = st[i];
+        if (s.status < 2 || s.cand < 0) continue;
+        if (winner(s.cand) != s.adv.id) continue;
+        if (s.merge) tiles[s.cand].fluidAmount += s.adv.tile.fluidAmount;  // 2131-2136
+        else tiles[s.cand] = s.adv.tile;                                   // 2127 / 2160
+        dirty[s.cand] = 1;
+        s.status = 1;
     }
+    for (int i = 0; i < n_ext; i++) {  // a neighbour's particle won a cell this world holds a copy of
+        const fseo_proposal& pr = ext[i];
+        const int row = (int)(pr.cell / width);
+        if (row < hold_lo || row >= hold_hi || winner((long)pr.cell) != pr.id) continue;
+        if (pr.merge) {
+            tiles[pr.cell].fluidAmount += pr.tile.fluid;
+        } else {
+            Cell d;
+            d.mat = &mats[pr.tile.mat];
+            d.id = pr.tile.mat;
+            d.color = pr.tile.color;
+            d.temperature = pr.tile.temp;
+            d.moved = pr.tile.moved != 0;
+            d.settleCount = pr.tile.settle;
+            d.fluidAmount = pr.tile.fluid;
+            d.fluidAmountDiff = pr.tile.fluid_diff;
+            tiles[pr.cell] = d;
+        }
+        dirty[pr.cell] = 1;
+    }
+}
+
+void World::prt_end() {
+    const int H = height;
     std::vector<Particle> keep;
     for (size_t i = 0; i < cells.size(); i++) {
-        if (st[i].status == 1) continue;
-        const Particle& p = st[i].status == 0 ? st[i].adv : cells[i];  // still pending: retried next tick from its old state
-        if (p.y > H) continue;                                         // 2190
+        if (prt[i].status == 1) continue;
+        const Particle& p = prt[i].status == 0 ? prt[i].adv : cells[i];  // still pending: retried next tick from its old state
+        if (p.y > H) continue;                                             // 2190
         keep.push_back(p);
     }
     cells.swap(keep);
+    prt.clear();
+    prt_props.clear();
+}
+
+void World::tick_particles_rounds(const Rect& tz, int max_rounds) {
+    prt_begin(tz);
+    for (int r = 0; r < max_rounds; r++) {
+        if (prt_propose() == 0) break;
+        prt_commit(nullptr, 0, 0, height);
+    }
+    prt_end();
 }
 
 // ---- boundary helpers ------------------------------------------------------------------

@@ -149,6 +149,25 @@ struct Particle {
 
 struct Rect { int x = 0, y = 0, w = 0, h = 0; };
 
+// state of a particle inside one tick_particles_rounds call (kept across the stages below)
+struct PrtState {
+    int status = 0;  // 0 alive, 1 dead, 2 wants its start cell, 3 spiral search
+    Particle adv;
+    int lx = 0, ly = 0;
+    int sx = 0, sy = 0, sdx = 0, sdy = -1, sj = 0;
+    long cand = -1;
+    bool merge = false;
+};
+// a deposit proposal as it travels between strip ranks
+struct fseo_proposal {
+    int64_t cell;   // x + y * width
+    uint64_t id;    // particle id: the lowest one wins the cell
+    fse_cell tile;
+    int32_t merge;  // 1: add the tile's fluid to the liquid already there
+    int32_t _pad;
+};
+static_assert(sizeof(fseo_proposal) == 48, "exchanged as raw bytes");
+
 class ThreadPool;
 
 class World {
@@ -181,6 +200,13 @@ public:
     // against the grid as it was at the start of the call, then deposits are resolved in rounds where the lowest
     // particle id wins a contested cell.  Conflict-free particle sets give results identical to tick_particles().
     void tick_particles_rounds(const Rect& zone, int max_rounds);
+    // the same schedule in stages (strip ranks exchange proposals between prt_propose and prt_commit)
+    void prt_begin(const Rect& zone);
+    int prt_propose();
+    void prt_commit(const fseo_proposal* ext, int n_ext, int hold_lo, int hold_hi);
+    void prt_end();
+    std::vector<PrtState> prt;
+    std::vector<fseo_proposal> prt_props;
     void add_particle(const Particle& p) { cells.push_back(p); }
 
     // one chunk task under either schedule (exposed for the multi-process strip test, which

@@ -139,6 +139,32 @@ OAPI int fseo_tick_particles(void* p, const fse_rect* z) {
     return 0;
 }
 
+OAPI int fseo_prt_begin(void* p, const fse_rect* z) {
+    Rect r{z->x, z->y, z->w, z->h};
+    ((World*)p)->prt_begin(r);
+    return 0;
+}
+OAPI int fseo_prt_propose(void* p) { return ((World*)p)->prt_propose(); }
+// copies the proposals whose cell lies in rows [y0, y1) into out (capacity cap); returns how many there are
+OAPI int fseo_prt_get(void* p, int y0, int y1, fseo_proposal* out, int cap) {
+    World* w = (World*)p;
+    int n = 0;
+    for (const fseo_proposal& pr : w->prt_props) {
+        const int row = (int)(pr.cell / w->width);
+        if (row < y0 || row >= y1) continue;
+        if (n < cap) out[n] = pr;
+        n++;
+    }
+    return n;
+}
+OAPI int fseo_prt_commit(void* p, const fseo_proposal* ext, int n_ext, int hold_lo, int hold_hi) {
+    ((World*)p)->prt_commit(ext, n_ext, hold_lo, hold_hi);
+    return 0;
+}
+OAPI int fseo_prt_end(void* p) {
+    ((World*)p)->prt_end();
+    return 0;
+}
 OAPI int fseo_tick_particles_rounds(void* p, const fse_rect* z, int max_rounds) {
     Rect r{z->x, z->y, z->w, z->h};
     ((World*)p)->tick_particles_rounds(r, max_rounds);

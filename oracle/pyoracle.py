@@ -176,6 +176,49 @@ def bodies_raster(world, bodies, xforms, tick=0, seed=1337):
     return fb
 
 
+# a deposit proposal as exchanged between strip ranks (oracle/fse_oracle.hpp fseo_proposal, 48 bytes)
+PROPOSAL_DTYPE = np.dtype({"names": ["cell", "id", "tile", "merge", "_pad"], "formats": [np.int64, np.uint64, T.CELL_DTYPE, np.int32, np.int32],
+                           "offsets": [0, 8, 16, 36, 40], "itemsize": 48})
+
+
+def prt_begin(world, zone=None):
+    """Stage 1 of tick_particles_rounds: integrate every particle of this world against its grid."""
+    z = zone or T.zone_of(world.width, world.height)
+    lib().fseo_prt_begin.argtypes = [C.c_void_p, C.c_void_p]
+    lib().fseo_prt_begin(world.h, C.byref(z))
+
+
+def prt_propose(world):
+    """Stage 2 (one per round): every pending particle proposes a cell; returns the number of proposals."""
+    lib().fseo_prt_propose.argtypes = [C.c_void_p]
+    return int(lib().fseo_prt_propose(world.h))
+
+
+def prt_get(world, y0, y1):
+    """The proposals of this round whose cell lies in rows [y0, y1)."""
+    f = lib().fseo_prt_get
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = int(f(world.h, y0, y1, None, 0))
+    out = np.zeros(n, dtype=PROPOSAL_DTYPE)
+    if n:
+        f(world.h, y0, y1, out.ctypes.data, n)
+    return out
+
+
+def prt_commit(world, ext=None, hold_lo=0, hold_hi=None):
+    """Stage 3: lowest id wins a cell among this world's and the other ranks' proposals (`ext`); winners' cells are written where
+    this world holds them (rows [hold_lo, hold_hi))."""
+    ext = np.zeros(0, dtype=PROPOSAL_DTYPE) if ext is None else np.ascontiguousarray(ext, dtype=PROPOSAL_DTYPE)
+    lib().fseo_prt_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib().fseo_prt_commit(world.h, ext.ctypes.data if len(ext) else None, len(ext), hold_lo, world.height if hold_hi is None else hold_hi)
+
+
+def prt_end(world):
+    """Stage 4: drop the deposited / dead particles, keep the rest."""
+    lib().fseo_prt_end.argtypes = [C.c_void_p]
+    lib().fseo_prt_end(world.h)
+
+
 def render_dirty(world, planes):
     """game.cpp:1994-2060 on the oracle world; planes = (main, fire, emission) uint8 arrays (h, w, 4), updated in place.
     Returns (dirty cells, dirty FIRE cells, movingTiles[n_materials])."""

@@ -64,3 +64,36 @@ def test_strip_protocol_matches_single_world(oracle, table, tmp_path, nranks):
         parts.append(np.load(f"{out}.parts{r}.npy"))
     assert rows == H
     Hh.assert_particles_equal(ow.particles_read(), np.concatenate(parts), "strip particles")
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_strip_particle_protocol_matches_single_world(oracle, table, tmp_path, nranks):
+    """tick + tickCells over strips: particles live on the rank that owns their row, the deposit proposals that target the band
+    around a cut are exchanged every round and committed by both sides (lowest id wins).  Grid and particle pool must equal the
+    single-world tick + tick_particles_rounds (the schedule the CUDA path implements) bit for bit.  This is the host-side
+    protocol for particle migration between GPUs; the CUDA path still refuses particles on multi-rank strips."""
+    W, H, ticks = 384, 896, 8
+    out = str(tmp_path / "pstrip")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29520 + nranks), WORLD_SIZE=str(nranks), OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "strip_particles_cpu_worker.py"), str(W), str(H), str(ticks), out],
+                              env=dict(env, RANK=str(r))) for r in range(nranks)]
+    for p in procs:
+        assert p.wait(timeout=900) == 0
+    ow = oracle.OracleWorld(W, H, table)
+    ow.write_rect(0, 0, G.mixed_band(table, W, H, 0, H, seed=77, blob=32))
+    deposited = 0
+    for t in range(ticks):
+        ow.tick(t, seed=1337)
+        before = ow.particles_count()
+        ow.particles_tick()
+        deposited += before - ow.particles_count()
+    assert deposited > 0  # the run actually settles particles, also next to the cuts
+    ref = ow.read_all()
+    parts = []
+    for r in range(nranks):
+        lo, hi = strips.strip_layout(H, r, nranks)[:2]
+        Hh.assert_cells_equal(ref[lo:hi], np.load(f"{out}.rank{r}.npy"), f"strip {r}/{nranks}")
+        parts.append(np.load(f"{out}.parts{r}.npy"))
+    Hh.assert_particles_equal(ow.particles_read(), np.concatenate(parts), "strip particles")
+    counts = sum(np.load(f"{out}.counts{r}.npy") for r in range(nranks))
+    assert counts[0] > 0 and counts[1] > 0, counts  # proposals crossed a cut and particles changed owner during the run
