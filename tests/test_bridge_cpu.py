@@ -185,3 +185,41 @@ def test_scroll_is_a_shift_that_keeps_unsourced_cells(oracle, table, dx, dy):
         assert np.array_equal(after[f], want), f
     p = ow.particles_read()
     assert np.allclose(np.sort(p["x"]), np.sort(parts["x"] + dx)) and np.allclose(np.sort(p["y"]), np.sort(parts["y"] + dy))
+
+
+def test_body_pixels_with_overlapping_footprints_are_within_the_7x7_stencil():
+    """The fast path of the rigid-body bridge (fse_bodies.cu) finds the earlier pixels a pixel depends on in its 7 x 7 body
+    neighbourhood.  Pin the geometry it relies on with the reference's own transform (game.cpp:1763-1764, float32, int()
+    truncation): two plus-shaped footprints share a cell exactly when their centres are at Manhattan distance <= 2, and body
+    pixels whose centres land that close are never more than 3 apart in either body coordinate."""
+    rng = np.random.default_rng(3)
+    w = h = 40
+    tx, ty = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32), indexing="ij")
+    plus = [(0, 0), (1, 0), (-1, 0), (0, 1), (0, -1)]
+    for trial in range(200):
+        ang = np.float32(rng.uniform(-np.pi, np.pi))
+        x0, y0 = np.float32(rng.uniform(50, 4000)), np.float32(rng.uniform(50, 4000))
+        s, c = np.float32(np.sin(ang)), np.float32(np.cos(ang))
+        wx = (tx * c - (ty + np.float32(1)) * s + x0).astype(np.int32).ravel()  # same operation order as the kernel and the oracle
+        wy = (tx * s + (ty + np.float32(1)) * c + y0).astype(np.int32).ravel()
+        bx, by = tx.astype(np.int32).ravel(), ty.astype(np.int32).ravel()
+        # pairs whose footprints share a cell: bucket pixels by covered cell
+        cover = {}
+        for dx, dy in plus:
+            for i, key in enumerate(zip((wx + dx).tolist(), (wy + dy).tolist())):
+                cover.setdefault(key, []).append(i)
+        worst = 0
+        for idx in cover.values():
+            if len(idx) < 2:
+                continue
+            a = np.array(idx)
+            man = np.abs(wx[a][:, None] - wx[a][None, :]) + np.abs(wy[a][:, None] - wy[a][None, :])
+            assert man.max() <= 2  # sharing a cell implies Manhattan distance <= 2 between the centres
+            worst = max(worst, int(np.abs(bx[a][:, None] - bx[a][None, :]).max()), int(np.abs(by[a][:, None] - by[a][None, :]).max()))
+        assert worst <= 3, (trial, float(ang), worst)
+    # and the converse used by the kernel's test: Manhattan distance <= 2 means the plus shapes do intersect
+    for dx in range(-3, 4):
+        for dy in range(-3, 4):
+            a = {(px, py) for px, py in plus}
+            b = {(dx + px, dy + py) for px, py in plus}
+            assert bool(a & b) == (abs(dx) + abs(dy) <= 2), (dx, dy)
