@@ -86,6 +86,47 @@ def test_temperature_matches_numpy_restatement(oracle, table):
         assert np.array_equal(cells["temp"], want)
 
 
+def test_temperature_zero_neighbours_may_be_added_instead_of_skipped(oracle, table):
+    """The CUDA kernel (fse_aux.cu temperature_kernel) computes (t * factor, factor) once per cell and adds all nine pairs of a
+    neighbourhood, where the reference skips neighbours at temperature 0 (world.cpp:1976).  A skipped neighbour would contribute
+    (+-0, 0): adding it must not change a single bit — including grids where most cells are 0, small |t| < 64 (factor 0, product
+    -0.0 for negative t) and the wrap-around of the i16 result."""
+    W, H = 256, 256
+    rng = np.random.default_rng(5)
+    cells = G.mixed_band(table, W, H, 0, H, seed=3, blob=8)
+    temp = rng.integers(-1100, 1100, size=(H, W))
+    temp[rng.random((H, W)) < 0.6] = 0
+    small = rng.random((H, W)) < 0.2
+    temp[small] = rng.integers(-63, 64, size=int(small.sum()))
+    cells["temp"] = temp.astype(np.int16)
+    zone = T.zone_of(W, H)
+    ow = oracle.OracleWorld(W, H, table)
+    ow.write_rect(0, 0, cells)
+    t = cells["temp"].astype(np.int32)
+    mat = cells["mat"]
+    condO = np.array([m.conduction_other for m in table.mats], dtype=np.float32)[mat]
+    condS = np.array([m.conduction_self for m in table.mats], dtype=np.float32)[mat]
+    addT = np.array([m.add_temp for m in table.mats], dtype=np.uint32)[mat]
+    fac = ((np.abs(t) // 64).astype(np.float32) * condO).astype(np.float32)
+    tv = (t.astype(np.float32) * fac).astype(np.float32)
+    n = np.full((H, W), np.float32(0.01), dtype=np.float32)
+    v = np.zeros((H, W), dtype=np.float32)
+    for xa in (-1, 0, 1):          # the kernel's formulation: no test for t != 0
+        for ya in (-1, 0, 1):
+            v = (v + np.roll(np.roll(tv, -ya, axis=0), -xa, axis=1)).astype(np.float32)
+            n = (n + np.roll(np.roll(fac, -ya, axis=0), -xa, axis=1)).astype(np.float32)
+    a = ((v / n).astype(np.float32) * condS).astype(np.float32)
+    b = (t.astype(np.float32) * (np.float32(1) - condS).astype(np.float32)).astype(np.float32)
+    r = ((addT.astype(np.float32) + a).astype(np.float32) + b).astype(np.float32)
+    new = np.where(v != 0, np.trunc(r).astype(np.int64), (addT.astype(np.int64) + t)).astype(np.int64)
+    want = t.copy()
+    z = zone
+    want[z.y:z.y + z.h, z.x:z.x + z.w] = ((new[z.y:z.y + z.h, z.x:z.x + z.w] + 32768) % 65536 - 32768)
+    ow.tick_temperature()
+    assert np.array_equal(ow.read_all()["temp"], want.astype(np.int16))
+    assert np.array_equal(want.astype(np.int16), _temperature_numpy(table, cells, zone))
+
+
 def test_reaction_gold_ore_melts_above_512(oracle, table):
     """REACT_TEMPERATURE_ABOVE 512 (gds.cpp:254-256): fires iff temperature > 512 and keeps it (world.cpp:1193-1200)."""
     ow = _world(oracle, table)
