@@ -156,3 +156,73 @@ def register_material(table, physics, slipperyness, alpha, density, iterations, 
     t = T.MaterialTable((T.Material * n)(*mats), table.ids, (T.Interaction * max(len(flat), 1))(*flat), (C.c_int32 * len(offs))(*offs),
                         table.react, (C.c_int32 * len(ro))(*ro))
     return t, n0
+
+
+# ---- Lua front door -----------------------------------------------------------------------------------------------------
+# The reference binds three globals for scripts (game_basic.cpp:79-81): materials_init(), materials_register(s_id, name,
+# index_name, physicsType, slipperyness, alpha, density, iterations, emit, emitColor, color) and materials_push()
+# (gds.cpp:117, 282, 291).  A Lua VM is not part of this package (the reference's vendored Lua 5.4 sources do not travel); the
+# declarative subset scripts use for material tables — those three calls with literal arguments, plain `name = literal`
+# assignments used as arguments, and comments — is read here.  Anything else in the script is ignored.
+import re  # noqa: E402
+
+_LUA_CALL = re.compile(r"\b(materials_init|materials_register|materials_push)\s*\(([^()]*)\)")
+_LUA_ASSIGN = re.compile(r"^\s*(?:local\s+)?([A-Za-z_]\w*)\s*=\s*([^=\n][^\n]*?)\s*;?\s*$", re.M)
+_PHYS = {"AIR": T.AIR, "SOLID": T.SOLID, "SAND": T.SAND, "SOUP": T.SOUP, "GAS": T.GAS, "PASSABLE": T.PASSABLE, "OBJECT": T.OBJECT}
+
+
+def _lua_strip_comments(src):
+    src = re.sub(r"--\[\[.*?\]\]", "", src, flags=re.S)
+    return re.sub(r"--[^\n]*", "", src)
+
+
+def _lua_literal(tok, env):
+    tok = tok.strip()
+    if not tok:
+        raise ValueError("empty argument")
+    if tok[0] in "\"'" and tok[-1] == tok[0]:
+        return tok[1:-1]
+    if tok in env:
+        return env[tok]
+    if tok in _PHYS:
+        return _PHYS[tok]
+    if tok in ("true", "false"):
+        return tok == "true"
+    try:
+        return int(tok, 0)
+    except ValueError:
+        return float(tok)
+
+
+def load_lua(source, seed=1337):
+    """Material table from a Lua script: materials_init() gives the stock table (default_materials), every materials_register(...)
+    appends one material (arguments as in gds.cpp:282; physicsType is a number or one of AIR / SOLID / SAND / SOUP / GAS / PASSABLE /
+    OBJECT), materials_push() ends it.  Returns (table, {s_id or name: material id}) ready for Context.set_materials."""
+    src = _lua_strip_comments(source)
+    env = {}
+    for m in _LUA_ASSIGN.finditer(src):
+        try:
+            env[m.group(1)] = _lua_literal(m.group(2), env)
+        except ValueError:
+            pass  # not a literal: not something a materials_register argument can use
+    table, ids, pushed = None, {}, False
+    for m in _LUA_CALL.finditer(src):
+        fn, args = m.group(1), [a for a in m.group(2).split(",")] if m.group(2).strip() else []
+        if fn == "materials_init":
+            table = default_materials(seed)
+        elif fn == "materials_register":
+            if table is None:
+                raise ValueError("materials_register before materials_init")
+            if len(args) != 11:
+                raise ValueError(f"materials_register takes 11 arguments, got {len(args)}: {m.group(0)}")
+            s_id, name, _index, phys, slip, alpha, dens, iters, emit, emit_color, color = (_lua_literal(a, env) for a in args)
+            table, mid = register_material(table, int(phys), int(slip), int(alpha), float(dens), int(iters), int(emit), int(emit_color), int(color))
+            ids[s_id] = mid
+            ids[name] = mid
+        else:
+            pushed = True
+    if table is None:
+        raise ValueError("the script never calls materials_init()")
+    if not pushed:
+        raise ValueError("the script never calls materials_push()")
+    return table, ids

@@ -300,3 +300,46 @@ def test_particles_rounds_equal_reference_when_conflict_free(oracle, table):
     Hh.assert_cells_equal(res[0][0], res[1][0], "particles")
     assert len(res[0][1]) == len(res[1][1]) == 0
     assert int((res[0][0]["mat"] == SAND).sum()) == 20
+
+
+def test_lua_material_script_front_door(oracle):
+    """materials_init / materials_register / materials_push from a Lua script (game_basic.cpp:79-81, gds.cpp:117-300): the declarative
+    subset is read without a Lua VM; the registered materials land behind the stock table with the reference's argument order, and
+    the resulting table drives the oracle like any other (a registered powder falls, a registered liquid spreads)."""
+    from falling_sand_engine_b200 import materials as M
+
+    src = """
+    -- materials of a mod
+    local GLOW = 0x40FFAA00
+    OnGameEngineLoad = function()
+        materials_init()
+        materials_register(1001, "Test Ash", "TEST_ASH", SAND, 12, 255, 6.5, 2, 0, 0, 0x555555)
+        materials_register(1002, 'Glow Oil', 'GLOW_OIL', 3, 0, 0xC0, 1.2, 4, 8, GLOW, 0x332211) --[[ SOUP ]]
+        materials_push()
+    end
+    """
+    tbl, ids = M.load_lua(src)
+    stock = M.default_materials(1337)
+    assert tbl.n == stock.n + 2 and ids["Test Ash"] == ids[1001] == stock.n and ids[1002] == stock.n + 1
+    ash, oil = tbl.mats[ids[1001]], tbl.mats[ids[1002]]
+    assert (ash.physics, ash.slipperyness, ash.alpha, ash.iterations, ash.color) == (T.SAND, 12, 255, 2, 0x555555) and abs(ash.density - 6.5) < 1e-6
+    assert (oil.physics, oil.alpha, oil.iterations, oil.emit, oil.emit_color) == (T.SOUP, 0xC0, 4, 8, 0x40FFAA00)
+    for i in range(stock.n):
+        assert bytes(tbl.mats[i]) == bytes(stock.mats[i])
+    with pytest.raises(ValueError):
+        M.load_lua("materials_register(1, 'x', 'X', SAND, 1, 255, 1.0, 1, 0, 0, 0)")
+    W = H = 384
+    ow = oracle.OracleWorld(W, H, tbl)
+    cells = Hh.empty_world_cells(tbl, W, H)
+    cells["mat"][150, 180:200] = ids[1001]
+    cells["mat"][200:210, 180:200] = ids[1002]
+    cells["mat"][260, 140:240] = STONE
+    ow.write_rect(0, 0, cells)
+    for t in range(8):
+        ow.tick(t)
+        ow.particles_tick()
+    after = ow.read_all()
+    assert (after["mat"][150, 180:200] != ids[1001]).all()          # the powder left its row
+    parts = ow.particles_read()
+    oil_now = int((after["mat"] == ids[1002]).sum()) + int((parts["tile"]["mat"] == ids[1002]).sum())
+    assert oil_now > 0 and (after["mat"][200:210, 180:200] == ids[1002]).sum() < 200  # the liquid is on its way (cells or loose particles)
