@@ -250,6 +250,23 @@ class World:
         return out
 
     # -- fracture outlines (world.cpp:288-720, physics_math.cpp:1766-1965) and physicsCheck flood (world.cpp:3330) ------
+    # -- chunk files (Chunk::ChunkRead / ChunkWrite, chunk.cpp:74-330; the merge of world::frame and chunkSaveCache) ---------
+    def load_chunk(self, path, x, y):
+        """Read a .pack file and merge its object layer into the grid at (x, y), marked dirty like world::frame does
+        (world.cpp:2374-2391).  Returns (generation_phase, layer2, background), which the tick path does not own."""
+        from . import chunkfile
+
+        phase, tiles, layer2, background = chunkfile.read_pack(path)
+        tiles["dirty"] = 1
+        self.write_rect(x, y, tiles)
+        return phase, layer2, background
+
+    def save_chunk(self, path, x, y, layer2=None, background=None, generation_phase=0):
+        """chunkSaveCache (world.cpp:2780-2792) + ChunkWrite: the 128 x 128 cells at (x, y) go to a .pack file."""
+        from . import chunkfile
+
+        chunkfile.write_pack(path, self.read_rect(x, y, T.FSE_CHUNK, T.FSE_CHUNK), layer2, background, generation_phase)
+
     # -- render planes / camera scroll (game.cpp:1994-2060, world.cpp:2454-2478) ---------------------------
     def pixels_enable(self, on=True):
         self.L.fse_pixels_enable.argtypes = [C.c_void_p, C.c_int]

@@ -1,0 +1,99 @@
+"""Chunk files of the reference (`Chunk::ChunkRead / ChunkWrite`, source/engine/chunk.cpp:74-330): the host side of world load /
+save.  A `.pack` file is
+
+    i8   generationPhase
+    i32  src_size   (= 128 * 128 * 2 * 12)     i32 compressed_size
+    i32  src_size2  (= 128 * 128 * 4)          i32 compressed_size2
+    LZ4 block: MaterialInstanceData[2 * 128 * 128] = {u16 index, u32 color, i16 temperature} (12 bytes with padding,
+               game_datastruct.hpp), first the 16384 cells of the object layer, then layer 2
+    LZ4 block: u32 background[128 * 128]
+
+LZ4 and the file format stay on the host; the cells go to / come from the device through fse_write_rect /
+fse_read_rect (`World.load_chunk / save_chunk`).  The codec is the system's liblz4 (1.9.4, the version the reference vendors),
+called like the reference does: LZ4_compress_fast(acceleration 10) / LZ4_decompress_safe.  A loaded cell gets the fields the
+reference restores (material, colour, temperature) and MaterialInstance's defaults for the rest (fluidAmount 2.0, not moved)."""
+import ctypes as C
+import ctypes.util
+import struct
+
+import numpy as np
+
+from . import types as T
+
+CHUNK = T.FSE_CHUNK
+CELLS = CHUNK * CHUNK
+DISK_DTYPE = np.dtype({"names": ["index", "color", "temperature"], "formats": [np.uint16, np.uint32, np.int16], "offsets": [0, 4, 8], "itemsize": 12})
+
+_lz4 = None
+
+
+def _lib():
+    global _lz4
+    if _lz4 is None:
+        name = ctypes.util.find_library("lz4") or "liblz4.so.1"
+        L = C.CDLL(name)
+        L.LZ4_compressBound.argtypes = [C.c_int]
+        L.LZ4_compress_fast.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+        L.LZ4_decompress_safe.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+        _lz4 = L
+    return _lz4
+
+
+def _compress(raw):
+    L = _lib()
+    cap = L.LZ4_compressBound(len(raw))
+    dst = C.create_string_buffer(cap)
+    n = L.LZ4_compress_fast(raw, dst, len(raw), cap, 10)  # chunk.cpp:241 / 262
+    if n <= 0:
+        raise IOError(f"LZ4_compress_fast failed ({n})")
+    return dst.raw[:n]
+
+
+def _decompress(blob, size):
+    dst = C.create_string_buffer(size)
+    n = _lib().LZ4_decompress_safe(blob, dst, len(blob), size)
+    if n != size:
+        raise IOError(f"chunk data is corrupt: decompressed {n} bytes, expected {size}")  # chunk.cpp:153-157
+    return dst.raw
+
+
+def write_pack(path, tiles, layer2=None, background=None, generation_phase=0):
+    """ChunkWrite (chunk.cpp:219-330).  tiles: (128, 128) fse_cell array (mat, color, temp are stored); layer2: the same or None
+    (AIR); background: (128, 128) u32 or None."""
+    buf = np.zeros(2 * CELLS, dtype=DISK_DTYPE)
+    for k, layer in enumerate((tiles, layer2)):
+        if layer is None:
+            continue
+        layer = np.asarray(layer).reshape(CELLS)
+        part = buf[k * CELLS:(k + 1) * CELLS]
+        part["index"], part["color"], part["temperature"] = layer["mat"], layer["color"], layer["temp"]
+    bg = np.zeros(CELLS, dtype=np.uint32) if background is None else np.ascontiguousarray(background, dtype=np.uint32).reshape(CELLS)
+    raw1, raw2 = buf.tobytes(), bg.tobytes()
+    c1, c2 = _compress(raw1), _compress(raw2)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<biiii", generation_phase, len(raw1), len(c1), len(raw2), len(c2)))
+        f.write(c1)
+        f.write(c2)
+
+
+def read_pack(path):
+    """ChunkRead (chunk.cpp:74-217) -> (generation_phase, tiles, layer2, background) with tiles / layer2 as (128, 128) fse_cell
+    arrays and background as (128, 128) u32."""
+    with open(path, "rb") as f:
+        head = f.read(17)
+        phase, src_size, csize, src_size2, csize2 = struct.unpack("<biiii", head)
+        if src_size != 2 * CELLS * DISK_DTYPE.itemsize:
+            raise IOError(f"Chunk src_size was different from expected: {src_size} vs {2 * CELLS * DISK_DTYPE.itemsize}")  # chunk.cpp:126
+        if src_size2 != CELLS * 4:
+            raise IOError(f"Chunk src_size2 was different from expected: {src_size2} vs {CELLS * 4}")  # chunk.cpp:139
+        c1, c2 = f.read(csize), f.read(csize2)
+    disk = np.frombuffer(_decompress(c1, src_size), dtype=DISK_DTYPE)
+    bg = np.frombuffer(_decompress(c2, src_size2), dtype=np.uint32).reshape(CHUNK, CHUNK).copy()
+    layers = []
+    for k in range(2):
+        part = disk[k * CELLS:(k + 1) * CELLS]
+        cells = np.zeros(CELLS, dtype=T.CELL_DTYPE)
+        cells["mat"], cells["color"], cells["temp"] = part["index"], part["color"], part["temperature"]
+        cells["fluid"] = 2.0  # MaterialInstance's default (game_datastruct.hpp:215); moved, settle and fluid_diff stay 0
+        layers.append(cells.reshape(CHUNK, CHUNK))
+    return phase, layers[0], layers[1], bg

@@ -315,3 +315,25 @@ def test_random_worlds_long_runs(oracle, gpu_ctx, table, sched, seed):
             Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), f"{sched} seed {seed} tick {t}")
             for which in range(3):
                 assert np.array_equal(planes[which], gw.pixels_read(which)), (t, which)
+
+
+def test_chunk_save_and_load_through_pack_files(gpu_ctx, table, tmp_path):
+    """World.save_chunk / load_chunk: chunkSaveCache + ChunkWrite and ChunkRead + the frame() merge (world.cpp:2374-2391, 2780-2792;
+    chunk.cpp:74-330).  A ticked chunk written to a .pack file and merged into another world carries material, colour and
+    temperature; the merged cells are dirty and have the reference's defaults for the per-tick fields."""
+    W = H = 512
+    gpu_ctx.set_materials(table)
+    a, b = fse.World(gpu_ctx, W, H), fse.World(gpu_ctx, W, H)
+    Hh.build_mixed(a, table, W, H, seed=31)
+    for t in range(3):
+        a.tick(t)
+    path = str(tmp_path / "c.pack")
+    a.save_chunk(path, 128, 256, generation_phase=2)
+    phase, layer2, background = b.load_chunk(path, 256, 128)
+    assert phase == 2 and not layer2["mat"].any() and not background.any()
+    src, dst = a.read_rect(128, 256, 128, 128), b.read_rect(256, 128, 128, 128)
+    for f in ("mat", "color", "temp"):
+        assert np.array_equal(src[f], dst[f]), f
+    assert dst["dirty"].all() and (dst["fluid"] == 2.0).all() and not dst["moved"].any()
+    a.close()
+    b.close()

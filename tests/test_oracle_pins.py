@@ -343,3 +343,43 @@ def test_lua_material_script_front_door(oracle):
     parts = ow.particles_read()
     oil_now = int((after["mat"] == ids[1002]).sum()) + int((parts["tile"]["mat"] == ids[1002]).sum())
     assert oil_now > 0 and (after["mat"][200:210, 180:200] == ids[1002]).sum() < 200  # the liquid is on its way (cells or loose particles)
+
+
+def test_chunk_pack_files_round_trip(oracle, table, tmp_path):
+    """Chunk::ChunkWrite / ChunkRead (chunk.cpp:74-330): header fields, the 12-byte on-disk cell {u16 index, u32 color, i16
+    temperature}, two LZ4 blocks; what comes back is what the reference restores (material, colour, temperature; fluidAmount 2.0
+    and the other per-tick fields at their defaults).  A saved oracle world reloads into an identical grid apart from those."""
+    import struct
+
+    from falling_sand_engine_b200 import chunkfile
+
+    W = H = 384
+    ow = oracle.OracleWorld(W, H, table)
+    ow.write_rect(0, 0, G.mixed_band(table, W, H, 0, H, seed=4, blob=16))
+    for t in range(3):
+        ow.tick(t)
+    tiles = ow.read_rect(128, 128, 128, 128)
+    layer2 = np.zeros((128, 128), dtype=T.CELL_DTYPE)
+    layer2["mat"][5:9, 7:30] = 7
+    layer2["color"][5:9, 7:30] = 0x445566
+    bg = ((np.arange(128 * 128, dtype=np.uint64) * 2654435761) % (1 << 32)).astype(np.uint32).reshape(128, 128)
+    path = str(tmp_path / "c_1_1.pack")
+    chunkfile.write_pack(path, tiles, layer2, bg, generation_phase=5)
+    raw = open(path, "rb").read()
+    phase, src_size, csize, src_size2, csize2 = struct.unpack("<biiii", raw[:17])
+    assert (phase, src_size, src_size2) == (5, 128 * 128 * 2 * 12, 128 * 128 * 4) and len(raw) == 17 + csize + csize2
+    assert csize < src_size  # LZ4 did compress the cells
+    p2, t2, l2, b2 = chunkfile.read_pack(path)
+    assert p2 == 5 and np.array_equal(b2, bg)
+    for got, want in ((t2, tiles), (l2, layer2)):
+        for f in ("mat", "color", "temp"):
+            assert np.array_equal(got[f], want[f]), f
+        assert (got["fluid"] == 2.0).all() and not got["moved"].any() and not got["settle"].any() and not got["fluid_diff"].any()
+    ow2 = oracle.OracleWorld(W, H, table)
+    ow2.write_rect(128, 128, t2)
+    back = ow2.read_rect(128, 128, 128, 128)
+    for f in ("mat", "color", "temp"):
+        assert np.array_equal(back[f], tiles[f])
+    open(path, "wb").write(raw[:17] + raw[17:17 + csize - 9] + raw[17 + csize:])  # damage the first block
+    with pytest.raises(IOError):
+        chunkfile.read_pack(path)
