@@ -267,6 +267,18 @@ class World:
 
         chunkfile.write_pack(path, self.read_rect(x, y, T.FSE_CHUNK, T.FSE_CHUNK), layer2, background, generation_phase)
 
+    def save_world(self, world_dir, origin=(0, 0)):
+        """world::saveWorld (world.cpp:3431): all chunks of the grid to <world_dir>/chunks/c_<x>_<y>.pack."""
+        from . import chunkfile
+
+        return chunkfile.save_world(self, world_dir, self.width, self.height, origin)
+
+    def load_world(self, world_dir, origin=(0, 0)):
+        """Merge every chunk file found under <world_dir>/chunks into the grid."""
+        from . import chunkfile
+
+        return chunkfile.load_world(self, world_dir, self.width, self.height, origin)
+
     # -- render planes / camera scroll (game.cpp:1994-2060, world.cpp:2454-2478) ---------------------------
     def pixels_enable(self, on=True):
         self.L.fse_pixels_enable.argtypes = [C.c_void_p, C.c_int]

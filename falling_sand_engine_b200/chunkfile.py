@@ -97,3 +97,43 @@ def read_pack(path):
         cells["fluid"] = 2.0  # MaterialInstance's default (game_datastruct.hpp:215); moved, settle and fluid_diff stay 0
         layers.append(cells.reshape(CHUNK, CHUNK))
     return phase, layers[0], layers[1], bg
+
+
+def pack_path(world_dir, cx, cy):
+    """Chunk::ChunkInit (chunk.cpp:20): <world>/chunks/c_<x>_<y>.pack, (x, y) in chunk units."""
+    import os
+
+    return os.path.join(world_dir, "chunks", f"c_{cx}_{cy}.pack")
+
+
+def save_world(world, world_dir, width, height, origin=(0, 0)):
+    """world::saveWorld (world.cpp:3431-3452): every chunk of the grid goes to its .pack file (chunkSaveCache + ChunkWrite).
+    `world` is anything with read_rect(x, y, w, h); `origin` is the chunk coordinate of the grid's top-left chunk.  Returns the
+    number of files written."""
+    import os
+
+    os.makedirs(os.path.join(world_dir, "chunks"), exist_ok=True)
+    n = 0
+    for j in range(height // CHUNK):
+        for i in range(width // CHUNK):
+            write_pack(pack_path(world_dir, origin[0] + i, origin[1] + j), world.read_rect(i * CHUNK, j * CHUNK, CHUNK, CHUNK))
+            n += 1
+    return n
+
+
+def load_world(world, world_dir, width, height, origin=(0, 0)):
+    """The reverse: every chunk file that exists is merged into the grid (ChunkRead + the frame() merge).  `world` is anything with
+    write_rect(x, y, cells).  Returns the number of chunks loaded."""
+    import os
+
+    n = 0
+    for j in range(height // CHUNK):
+        for i in range(width // CHUNK):
+            path = pack_path(world_dir, origin[0] + i, origin[1] + j)
+            if not os.path.exists(path):
+                continue
+            _, tiles, _, _ = read_pack(path)
+            tiles["dirty"] = 1
+            world.write_rect(i * CHUNK, j * CHUNK, tiles)
+            n += 1
+    return n

@@ -383,3 +383,25 @@ def test_chunk_pack_files_round_trip(oracle, table, tmp_path):
     open(path, "wb").write(raw[:17] + raw[17:17 + csize - 9] + raw[17 + csize:])  # damage the first block
     with pytest.raises(IOError):
         chunkfile.read_pack(path)
+
+
+def test_world_save_and_load_directory(oracle, table, tmp_path):
+    """world::saveWorld / chunk loading over a whole grid: one .pack per 128 x 128 chunk named like Chunk::ChunkInit names them;
+    loading them into a fresh world restores material, colour and temperature of every cell."""
+    from falling_sand_engine_b200 import chunkfile
+
+    W, H = 384, 256
+    ow = oracle.OracleWorld(W, H, table)
+    ow.write_rect(0, 0, G.mixed_band(table, W, H, 0, H, seed=8, blob=16))
+    ow.tick(0)
+    d = str(tmp_path / "world")
+    assert chunkfile.save_world(ow, d, W, H, origin=(-1, 4)) == 6
+    import os
+
+    assert sorted(os.listdir(os.path.join(d, "chunks"))) == sorted(f"c_{x}_{y}.pack" for x in (-1, 0, 1) for y in (4, 5))
+    ow2 = oracle.OracleWorld(W, H, table)
+    assert chunkfile.load_world(ow2, d, W, H, origin=(-1, 4)) == 6
+    a, b = ow.read_all(), ow2.read_all()
+    for f in ("mat", "color", "temp"):
+        assert np.array_equal(a[f], b[f]), f
+    assert b["dirty"].all()
