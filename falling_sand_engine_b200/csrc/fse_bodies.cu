@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(BODY_TB, 8) bodies_body_kernel(BodyArgs a) {
 #endif
     const int aw = box.z - box.x + 1, ah = box.w - box.y + 1;
     const bool smem = (long long)aw * ah <= BODY_SCLAIM;
-    const bool fast = smem && npix <= BODY_TB * BODY_PPT;
+    const bool fast = smem && npix <= BODY_TB * BODY_PPT && aw <= 255 && ah <= 255;  // positions inside the box are kept in 8 + 8 bits
     if (smem && !fast)
         for (int i = tid; i < aw * ah; i += BODY_TB) s_claim[i] = 0xffffffffu;
     for (int o = tid; o < npix; o += BODY_TB) {

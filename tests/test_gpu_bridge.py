@@ -61,8 +61,8 @@ def test_large_bodies_use_the_global_claim_plane(oracle, gpu_ctx, table):
     gw, ow = fse.World(gpu_ctx, W, H), oracle.OracleWorld(W, H, table)
     cells = G.mixed_band(table, W, H, 0, H, seed=5, air_frac=0.6, blob=48)
     bodies = [make_body(table, 20, 24, seed=1, fill=0.8), make_body(table, 70, 60, seed=2, fill=0.7), make_body(table, 90, 40, seed=3, fill=1.0),
-              make_body(table, 16, 16, seed=4, fill=1.0)]
-    xf = np.array([(300.0, 300.0, 0.3), (310.0, 290.0, -0.7), (330.0, 320.0, 1.9), (335.0, 300.0, 0.0)], dtype=np.float32)
+              make_body(table, 16, 16, seed=4, fill=1.0), make_body(table, 260, 2, seed=5, fill=0.9)]  # the last: a 267 x 11 box fits the shared-memory map but not 8-bit coordinates
+    xf = np.array([(300.0, 300.0, 0.3), (310.0, 290.0, -0.7), (330.0, 320.0, 1.9), (335.0, 300.0, 0.0), (200.0, 450.0, 0.02)], dtype=np.float32)
     for w in (gw, ow):
         w.write_rect(0, 0, cells)
     ob = [b.copy() for b in bodies]
