@@ -208,7 +208,6 @@ static void free_world(fse_world* w) {
         if (w->fork.ev_join[q]) cudaEventDestroy(w->fork.ev_join[q]);
     }
     if (w->fork.ev_fork) cudaEventDestroy(w->fork.ev_fork);
-    cudaFree(w->fork.pair_sync);
     if (w->stream) cudaStreamDestroy(w->stream);
     if (w->comm_stream) cudaStreamDestroy(w->comm_stream);
     if (w->ev_boundary) cudaEventDestroy(w->ev_boundary);
@@ -219,7 +218,7 @@ static void free_world(fse_world* w) {
     cudaFree(w->d_pixels); cudaFree(w->d_render_stats); cudaFree(w->scroll_scratch);
     if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
     if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);
-    cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list); cudaFree(w->d_chunk_state); cudaFree(w->d_graph_done);
+    cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list); cudaFree(w->d_chunk_state);
     fse_bodies_free(w);
     cudaFree(w->outline_scratch);
     delete w;
@@ -246,8 +245,6 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_stats, dev_stats_bytes());
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
     if (const char* env = getenv("FSE_TICK_LPT")) w->lpt_on = atoi(env) != 0;
-    if (const char* env = getenv("FSE_TICK_GRAPH")) w->graph_on = atoi(env) != 0;
-    if (const char* env = getenv("FSE_GRAPH_CTAS_PER_SM")) w->graph_ctas_per_sm = std::max(1, atoi(env));
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -258,10 +255,6 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     w->fork.min_chunks = 256;
     if (const char* env = getenv("FSE_TICK_MIN_CHUNKS")) w->fork.min_chunks = std::max(1, atoi(env));
     if (const char* env = getenv("FSE_TICK_PARTS")) w->fork.parts = std::min(4, std::max(1, atoi(env)));
-    w->fork.pairs = 0;  // tick_pair_kernel: measured slower than the plain per-pass launches; FSE_TICK_PAIRS=n turns it on
-    if (const char* env = getenv("FSE_TICK_PAIRS")) w->fork.pairs = std::min(4096, std::max(0, atoi(env)));
-    w->fork.pair_sync = nullptr;
-    if (w->fork.pairs > 0 && cudaMalloc((void**)&w->fork.pair_sync, sizeof(unsigned int) * (size_t)(w->fork.pairs + 1)) != cudaSuccess) w->fork.pairs = 0;
     for (int q = 0; q < 3; q++) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->fork.aux[q], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->fork.ev_join[q], cudaEventDisableTiming);
@@ -598,56 +591,6 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
     }
     const bool multi = w->strip && w->ctx->nranks > 1;
     KtScope kt{w};
-    // Whole tick as one task-graph launch (tick_graph_kernel): plain worlds on the per-pass rows schedule whose colour phases are
-    // larger than one wave of the fused kernel.  Chunk-level order, and therefore every result, is that of the per-phase launches.
-    if (w->graph_on && !w->strip && !w->active_on && w->schedule == FSE_SCHEDULE_ROWS && !w->fused && a->cell_iter > 0 && nx >= 2 && ny >= 2 && nx < 4096 && ny < 4096 &&
-        (nx / 2) * (ny / 2) > w->fused_max_chunks) {
-        GraphParams G;
-        memset(&G, 0, sizeof(G));
-        TickParams& P = G.P;
-        P.p = w->p;
-        P.W = w->W;
-        P.H = w->H;
-        P.y_off = w->y_off;
-        P.tick = a->tick;
-        P.pbuf = w->pbuf;
-        P.pcount = w->pcount;
-        P.pcap = w->pcap;
-        P.tabs = w->ctx->d_tabs;
-        P.acols = w->acols;
-        P.arows = w->arows;
-        P.schedule = w->schedule;
-        G.zx = z.x;
-        G.zy = z.y - w->y_off;
-        G.nx = nx;
-        G.ny = ny;
-        G.n_phases = 4 * a->cell_iter;
-        for (int tk = 0; tk < 4; tk++) {
-            const int ofx = tk % 2, ofy = 1 - tk / 2;  // world.cpp:1059-1060
-            G.ncx[tk] = (nx - ofx + 1) / 2;
-            G.ncy[tk] = (ny - ofy + 1) / 2;
-        }
-        for (int p = 0; p < G.n_phases; p++) G.phase_off[p + 1] = G.phase_off[p] + G.ncx[p & 3] * G.ncy[p & 3];
-        for (int it = 0; it < a->cell_iter; it++) G.rkeys[it] = rng_key(a->seed, a->tick, (uint32_t)it);
-        const int total = G.phase_off[G.n_phases];
-        const int sync_words = 2 * nx * ny + 2 + 2 * total;  // credits | pass-1 progress | head | tail | queue
-        if (sync_words > w->graph_cap) {
-            cudaFree(w->d_graph_done);
-            w->d_graph_done = nullptr;
-            w->graph_cap = 0;
-            CK(cudaMalloc((void**)&w->d_graph_done, sizeof(unsigned int) * (size_t)sync_words));
-            w->graph_cap = sync_words;
-        }
-        G.sync = w->d_graph_done;
-        if (int r = kt.begin(w->stream)) return r;
-        const int grid = std::min(2 * total, w->ctx->sm_count * w->graph_ctas_per_sm);
-        CK(launch_tick_graph(G, grid, w->stream));
-        if (int r = kt.end(w->stream)) return r;
-        const int nl = 2;
-        w->ctx->launches += nl;
-        w->ticks++;
-        return FSE_OK;
-    }
     for (int iter = 0; iter < a->cell_iter; iter++) {
         for (int tk = 0; tk < 4; tk++) {
             const int ofx = tk % 2;              // 0 1 0 1   (world.cpp:1059)

@@ -134,26 +134,12 @@ struct TickParams {
     int schedule;           // FSE_SCHEDULE_CLASSES (4 interleaved column classes) or FSE_SCHEDULE_ROWS (simultaneous rows)
 };
 
-// Whole tick in one launch (tick_graph_kernel, fse_tick_rows.cuh): the colour phases as a task graph over the chunks.
-struct GraphParams {
-    TickParams P;            // planes, particles, tables; x0/y0/ncx/ncy/iter/rkey/chunk_* unused
-    int zx, zy;              // origin of the tick zone (local rows)
-    int nx, ny;              // chunks of the zone (both >= 2, <= 4095)
-    int n_phases;            // 4 * cell_iter
-    int phase_off[17];       // first task of each phase
-    uint32_t rkeys[4];       // rng_key per iteration
-    int ncx[4], ncy[4];      // chunks of each colour
-    unsigned int* sync;      // credits[nx * ny] | pass-1 progress[nx * ny] | queue head | queue tail | queue[2 * visits] (graph_init_kernel)
-};
-
 // extra streams + events for running the parts of a colour phase side by side (nullptr: single stream)
 struct TickFork {
     int parts;  // 1..4 parts of a phase run side by side; part 0 on the caller's stream
     int min_chunks;  // phases with fewer chunks are launched whole (default 256; FSE_TICK_MIN_CHUNKS)
     cudaStream_t aux[3];
     cudaEvent_t ev_fork, ev_join[3];
-    int pairs;                // heaviest chunks of a phase run as pipelined pass-1 / pass-2 CTA pairs (tick_pair_kernel); 0 = off
-    unsigned int* pair_sync;  // device: ticket | pass-1 progress per pair (pairs + 1 words)
 };
 
 }  // namespace fse

@@ -70,12 +70,6 @@ struct fse_world {
     int lpt_cap = 0;            // chunks per colour the buffers hold
     int lpt_sig[4][4]{};        // (x0, y0, ncx, ncy) the list of a colour was built for; ncx = 0: no list yet
     bool lpt_on = true;
-    // whole-tick task-graph kernel (FSE_TICK_GRAPH=1; measured slower than the per-phase launches): credit and
-    // progress counters per zone chunk + the ready queue
-    bool graph_on = false;
-    unsigned int* d_graph_done = nullptr;
-    int graph_cap = 0;
-    int graph_ctas_per_sm = 5;
     // rigid-body bridge (fse_bodies.cu) and outline scratch (fse_outline.cu)
     struct fse_bodies* bodies = nullptr;
     int last_bridge_rounds = 0;
@@ -117,7 +111,6 @@ int fse_wake_rect(fse_world* w, int x, int y_local, int rw, int rh);  // wake th
 int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cudaStream_t s);
 int strip_refresh(fse_world* w, cudaStream_t s);
 size_t tick_smem_bytes();
-cudaError_t launch_tick_graph(const GraphParams& G, int grid, cudaStream_t stream);  // whole tick, one launch
 cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream, const int* members = nullptr);
 cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched, const TickFork* fork);  // *launched = kernels enqueued
 cudaError_t launch_compact_active(const uint8_t* awake, int acols, int ci0, int cj0, int ncx, int ncy, int* list, int* count, cudaStream_t s);

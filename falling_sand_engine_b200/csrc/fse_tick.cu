@@ -1113,28 +1113,9 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
             cudaEventRecord(fork->ev_fork, stream);
             for (int q = 1; q < parts; q++) cudaStreamWaitEvent(fork->aux[q - 1], fork->ev_fork, 0);
         }
-        // the heaviest chunks (head of the longest-first list) as pipelined CTA pairs on the spare stream, launched first
-        int pairs = 0;
-        if (parts > 1 && parts <= 3 && fork->pairs > 0 && fork->pair_sync && P.chunk_list && P.chunk_cost && !P.awake && !P.list_count) {
-            pairs = fork->pairs < n_chunks / 4 ? fork->pairs : n_chunks / 4;
-            static bool pair_configured = false;
-            if (!pair_configured) {
-                cudaError_t e = cudaFuncSetAttribute(tick_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-                if (e != cudaSuccess) return e;
-                pair_configured = true;
-            }
-        }
-        if (pairs > 0) {
-            constexpr size_t smem = sizeof(SmemPass<1>) > sizeof(SmemPass<2>) ? sizeof(SmemPass<1>) : sizeof(SmemPass<2>);
-            cudaStreamWaitEvent(fork->aux[2], fork->ev_fork, 0);
-            cudaMemsetAsync(fork->pair_sync, 0, sizeof(unsigned int) * (size_t)(pairs + 1), fork->aux[2]);
-            tick_pair_kernel<<<2 * pairs, PassGeom<1>::THREADS, smem + pad, fork->aux[2]>>>(P, fork->pair_sync);
-            *launched += 1;
-        }
-        const int rest = n_chunks - pairs;
         for (int q = 0; q < parts; q++) {
             cudaStream_t st = q ? fork->aux[q - 1] : stream;
-            const int lo = pairs + (int)((long long)rest * q / parts), hi = pairs + (int)((long long)rest * (q + 1) / parts);
+            const int lo = (int)((long long)n_chunks * q / parts), hi = (int)((long long)n_chunks * (q + 1) / parts);
             if (hi <= lo) continue;  // fewer chunks than parts
             Q.chunk_base = P.chunk_base + lo;
             tick_pass_kernel<1><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>) + pad, st>>>(Q);
@@ -1146,35 +1127,17 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
             cudaEventRecord(fork->ev_join[q - 1], fork->aux[q - 1]);
             cudaStreamWaitEvent(stream, fork->ev_join[q - 1], 0);
         }
-        if (pairs > 0) {
-            cudaEventRecord(fork->ev_join[2], fork->aux[2]);
-            cudaStreamWaitEvent(stream, fork->ev_join[2], 0);
-        }
         if (P.awake && P.chunk_state && P.chunk_list) {  // a sleeping chunk can only be woken by a neighbour's record, so the
             apply_chunk_state_kernel<<<(n_chunks + 127) / 128, 128, 0, stream>>>(P, n_chunks);  // flags change after all passes
             *launched += 1;
         }
-    } else if (P.schedule == FSE_SCHEDULE_ROWS)
-{
+    } else if (P.schedule == FSE_SCHEDULE_ROWS) {
         tick_rows_kernel<<<n_chunks, ROWS_THREADS, sizeof(SmemRows), stream>>>(P);
         *launched = 1;
     } else {
         tick_chunk_kernel<<<n_chunks, 128, sizeof(Smem), stream>>>(P);
         *launched = 1;
     }
-    return cudaGetLastError();
-}
-
-cudaError_t launch_tick_graph(const GraphParams& G, int grid, cudaStream_t stream) {
-    static bool configured = false;
-    constexpr size_t smem = sizeof(SmemPass<1>) > sizeof(SmemPass<2>) ? sizeof(SmemPass<1>) : sizeof(SmemPass<2>);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tick_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    graph_init_kernel<<<64, 256, 0, stream>>>(G);
-    tick_graph_kernel<<<grid, PassGeom<1>::THREADS, smem, stream>>>(G);
     return cudaGetLastError();
 }
 

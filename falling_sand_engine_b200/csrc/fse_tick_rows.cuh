@@ -1061,42 +1061,10 @@ __device__ __forceinline__ void pass_row_load(SmemPass<PASS>& S, const PlaneIO& 
 }
 
 // One pass over one chunk by the whole CTA (4 compute warps + IO warp).  The material LUT is already in shared memory; scratch,
-// mbarriers and the context are (re)initialised here, so a CTA can run several passes / chunks one after the other
-// (tick_graph_kernel).  On return every bulk store of the pass has completed.
-//
-// PIPE (tick_graph_kernel): the passes of a chunk visit run as CTAs side by side.  The pass-1 CTA publishes in *prog how many of
-// its rows (counted from row FULL_LO, bottom-up) have reached HBM for good — prog_base + count, monotonic over the tick — and the
-// pass-2 CTA loads a row only when that count covers it, so it trails pass 1 by about a dozen rows instead of a whole chunk.
-constexpr int PIPE_D = 8;  // bulk groups (= steps) a store may still be in flight when progress is published
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-template <int PASS, bool PIPE = false>
-__device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, int iter, uint32_t rkey, unsigned int* cost_slot,
-                                         unsigned int* prog = nullptr, unsigned int prog_base = 0) {
+// mbarriers and the context are (re)initialised here.  On return every bulk store of the pass has completed.
+template <int PASS>
+__device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, int iter, uint32_t rkey, unsigned int* cost_slot) {
     using G = PassGeom<PASS>;
-    unsigned int prog_seen = 0;  // pass 2, IO lane 0: last value read from *prog
-    // pass 2: row k may be loaded once pass 1 has published it (rows below -5 are never written by pass 1)
-    auto wait_row = [&](int k, int lane_) {
-        if (PIPE && PASS == 2) {
-            bool polled = false;
-            if (lane_ == 0 && k >= PassGeom<1>::FULL_LO) {
-                const unsigned int need = prog_base + (unsigned int)(k - PassGeom<1>::FULL_LO + 1);
-                while (prog_seen < need) {
-                    polled = true;
-                    prog_seen = ld_acquire_u32(prog);
-                    if (prog_seen < need) __nanosleep(64);
-                }
-            }
-            // the proxy fence orders this lane's bulk loads behind lane 0's acquire; rows covered by an earlier poll need none
-            if (__shfl_sync(0xffffffffu, polled ? 1 : 0, 0)) asm volatile("fence.proxy.async;" ::: "memory");
-        }
-    };
     unsigned char* const smem_raw = fse_smem;
     SmemPass<PASS>& S = *reinterpret_cast<SmemPass<PASS>*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1138,7 +1106,6 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     if (io_load) {
 #pragma unroll 1
         for (int k = G::KMIN; k < G::UP + G::PF; k++) {
-            wait_row(k, lane);
             pass_row_load<PASS>(S, pio, lane, k, cy);
         }
     }
@@ -1216,20 +1183,8 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                 FSE_IO_CLOCK(1);
             }
             if (io_load && kl <= G::LAST) {
-                wait_row(kl, lane);
                 pass_row_load<PASS>(S, pio, lane, kl, cy);
                 FSE_IO_CLOCK(2);
-            }
-            if (PIPE && PASS == 1 && io_store && st >= PIPE_D + G::SL && (st & 3) == 0) {
-                // the stores of the steps up to st - PIPE_D have completed: rows FULL_LO .. st - PIPE_D - SL are final in HBM.
-                // Every lane waits for its own plane's bulk groups; lane 0 publishes for all of them (one fence per 4 steps)
-                asm volatile("cp.async.bulk.wait_group %0;" ::"n"(PIPE_D) : "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    __threadfence();
-                    st_release_u32(prog, prog_base + (unsigned int)(st - PIPE_D - G::SL - G::FULL_LO + 1));
-                }
             }
         }
     }
@@ -1254,12 +1209,6 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
         if (lane == 0) *slot = PASS == 1 ? st : (*slot | st);  // pass 1 starts the record, pass 2 adds to it (same stream)
     }
     if (io_store) bulk_wait_all();
-    if (PIPE && PASS == 1 && io_store) {
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release_u32(prog, prog_base + (unsigned int)(G::LAST - G::FULL_LO + 1));
-    }
 }
 
 template <int PASS>
@@ -1291,7 +1240,6 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
 // STEAM and boxed in, condenses with probability 1/10.  All cells decide from the row as pass 2 left it; a contested AIR
 // cell goes to the lower source column, i.e. a left-mover at i loses exactly when cell i-2 moves right.  Visited bits are
 // dropped from the whole row afterwards (the colour phase is over).
-// Plane loads go to L2 (ld.global.cg): inside tick_graph_kernel another SM may have rewritten the line since this SM last read it.
 __device__ __forceinline__ void pass3_row_global(const TickParams& P, uint32_t rkey, int cx, int ym, int lane) {
     const int y = ym + P.y_off;
     const DevTables* T = P.tabs;
@@ -1391,159 +1339,6 @@ __global__ void __launch_bounds__(128) tick_pass3_kernel(const __grid_constant__
         cyi = chunk / P.ncx;
     }
     pass3_row_global(P, P.rkey, P.x0 + cxi * 2 * CHUNK, P.y0 + cyi * 2 * CHUNK + r, lane);
-}
-
-// ======================================================================================================================
-// Whole tick in one launch (tick_graph_kernel).  The 4 x cell_iter colour phases are a task graph, not 12 global barriers: a
-// chunk of phase p only needs its 8 neighbour chunks to have finished their phases < p — the footprint of a chunk (5 columns /
-// 10 rows beyond its border, 16 columns loaded) never reaches past its direct neighbours, and two adjacent chunks always
-// differ in colour, so their relative order is the reference's phase order.  Between two visits of a chunk every neighbour is
-// visited exactly once; a chunk that finishes a visit therefore credits each neighbour's next visit, and the credit that
-// completes a visit's count (n0 + n * nnb: neighbours of a lower colour count once more) appends it to a ready queue.  CTAs pop
-// the queue in order, run pass 1, pass 2 and pass 3 on the chunk, and credit its neighbours.  Only runnable tasks ever hold a
-// CTA slot; every queue slot is written exactly once, so a CTA that claimed a slot waits only for work that is already
-// running.  Results are those of the per-phase launches (same chunk-level order); what goes away is the tail of every phase
-// (a phase is ~1.3 waves of CTAs) and the drain between the passes.
-__host__ __device__ __forceinline__ int graph_colour(int ci, int cj) { return (ci & 1) + 2 * (1 - (cj & 1)); }  // phase index of a chunk's colour
-
-// A visit is two queue entries, taken by two CTAs that run side by side: pass 1, and pass 2 (+ pass 3 at its end) trailing it
-// through the pass-1 progress counter of the chunk (run_pass PIPE).  The pass-1 entry always sits right before its pass-2
-// entry, so whoever holds the second knows the first has been taken by a resident CTA.
-// sync buffer: credits[cells] | prog1[cells] | head | tail | queue[2 * visits]; zeroed, then the visits of phase 0 are queued
-constexpr unsigned int GQ_PASS2 = 1u << 28;
-__global__ void graph_init_kernel(const GraphParams G) {
-    const int total = 2 * G.phase_off[G.n_phases], n0 = 2 * G.phase_off[1], cells = G.nx * G.ny;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * cells + 2 + total; i += gridDim.x * blockDim.x) {
-        unsigned int v = 0;
-        if (i == 2 * cells + 1) v = (unsigned int)n0;  // tail
-        if (i >= 2 * cells + 2 && i - 2 * cells - 2 < n0) {
-            const int e = i - 2 * cells - 2, li = e >> 1;
-            const int ci = 2 * (li % G.ncx[0]), cj = 2 * (li / G.ncx[0]) + 1;  // colour 0 = (even, odd)
-            v = ((unsigned int)(ci | (cj << 12)) | ((e & 1) ? GQ_PASS2 : 0u)) + 1u;
-        }
-        G.sync[i] = v;
-    }
-}
-
-__global__ void __launch_bounds__(PassGeom<1>::THREADS, FSE_PASS_MINB) tick_graph_kernel(const __grid_constant__ GraphParams G) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    volatile unsigned int* s_task = reinterpret_cast<volatile unsigned int*>(fse_smem + offsetof(SmemHead, pad_));
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(&G.P.tabs->lut);
-        uint4* dst = reinterpret_cast<uint4*>(fse_smem);
-        for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    const int total = 2 * G.phase_off[G.n_phases], cells = G.nx * G.ny;
-    unsigned int* const credits = G.sync;
-    unsigned int* const prog1 = G.sync + cells;
-    unsigned int* const head = G.sync + 2 * cells;
-    unsigned int* const tail = head + 1;
-    unsigned int* const queue = head + 2;
-    for (;;) {
-        if (tid == 0) {
-            const unsigned int idx = atomicAdd(head, 1u);
-            unsigned int v = 0xffffffffu;
-            if (idx < (unsigned int)total) {
-                while ((v = ld_acquire_u32(queue + idx)) == 0u) __nanosleep(100);
-                __threadfence();
-            }
-            s_task[0] = v;
-        }
-        __syncthreads();
-        const unsigned int tv = s_task[0];
-        if (tv == 0xffffffffu) break;
-        asm volatile("fence.proxy.async;" ::: "memory");  // neighbours wrote with bulk copies and plain stores; this CTA reads with bulk copies
-        const unsigned int te = tv - 1u;
-        const int ci = (int)(te & 0xfffu), cj = (int)((te >> 12) & 0xfffu), p = (int)((te >> 24) & 0xfu);
-        const int iter = p >> 2, tk = p & 3;
-        const int cx = G.zx + ci * CHUNK, cy = G.zy + cj * CHUNK;
-        const uint32_t rkey = G.rkeys[iter];
-        unsigned int* const prog = prog1 + cj * G.nx + ci;
-        const unsigned int prog_base = (unsigned int)iter * 256u;
-        if (!(te & GQ_PASS2)) {
-            run_pass<1, true>(G.P, cx, cy, iter, rkey, nullptr, prog, prog_base);
-            __syncthreads();
-            if (tid == 0) {
-                SmemPass<1>& S1 = *reinterpret_cast<SmemPass<1>*>(fse_smem);
-                for (int q = 0; q < PassGeom<1>::RN; q++) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S1.bar[q])) : "memory");
-            }
-            continue;
-        }
-        run_pass<2, true>(G.P, cx, cy, iter, rkey, nullptr, prog, prog_base);
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            SmemPass<2>& S2 = *reinterpret_cast<SmemPass<2>*>(fse_smem);
-            for (int q = 0; q < PassGeom<2>::RN; q++) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S2.bar[q])) : "memory");
-        }
-        for (int r = warp; r < CHUNK; r += PassGeom<1>::THREADS / 32) pass3_row_global(G.P, rkey, cx, cy + r, lane);
-        __threadfence();
-        __syncthreads();
-        if (tid < 8) {  // credit the next visit of each neighbour
-            const int q8 = tid < 4 ? tid : tid + 1;
-            const int ni = ci + q8 % 3 - 1, nj = cj + q8 / 3 - 1;
-            if (ni >= 0 && nj >= 0 && ni < G.nx && nj < G.ny) {
-                const int tkc = graph_colour(ni, nj);
-                const int pc = p + ((tkc - tk + 4) & 3);
-                if (pc < G.n_phases) {
-                    int n0 = 0, nnb = 0;
-                    for (int e = 0; e < 9; e++) {
-                        const int ei = ni + e % 3 - 1, ej = nj + e / 3 - 1;
-                        if (e == 4 || ei < 0 || ej < 0 || ei >= G.nx || ej >= G.ny) continue;
-                        nnb++;
-                        if (graph_colour(ei, ej) < tkc) n0++;
-                    }
-                    const unsigned int target = (unsigned int)(n0 + (pc >> 2) * nnb);
-                    __threadfence();
-                    if (atomicAdd(credits + nj * G.nx + ni, 1u) + 1u == target) {
-                        __threadfence();
-                        const unsigned int slot = atomicAdd(tail, 2u);
-                        const unsigned int enc = (unsigned int)(ni | (nj << 12) | (pc << 24));
-                        st_release_u32(queue + slot, enc + 1u);
-                        st_release_u32(queue + slot + 1, (enc | GQ_PASS2) + 1u);
-                    }
-                }
-            }
-        }
-    }
-}
-
-// The heaviest chunks of a colour phase as CTA pairs (per-phase launches, longest-first list).  In the per-pass launches a
-// chunk's pass 2 cannot start before the whole pass-1 kernel of its part has drained, so the heaviest chunks — they decide when
-// the phase ends — run their three passes strictly one after the other.  Here the first `pairs` chunks of the list get two
-// CTAs each: pass 1, and pass 2 trailing it through the progress counter (run_pass PIPE) with pass 3 at its end.  Tickets are
-// handed out in order, so the pass-1 CTA of a pair is always resident before its pass-2 CTA can wait for it.
-__global__ void __launch_bounds__(PassGeom<1>::THREADS, FSE_PASS_MINB) tick_pair_kernel(const __grid_constant__ TickParams P, unsigned int* sync) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    volatile unsigned int* s_task = reinterpret_cast<volatile unsigned int*>(fse_smem + offsetof(SmemHead, pad_));
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(&P.tabs->lut);
-        uint4* dst = reinterpret_cast<uint4*>(fse_smem);
-        for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    if (tid == 0) s_task[0] = atomicAdd(sync, 1u);
-    __syncthreads();
-    const unsigned int t = s_task[0];
-    const int idx = (int)(t >> 1), bid = idx + P.chunk_base;
-    int cxi, cyi;
-    if (P.chunk_list) {
-        const int v = P.chunk_list[bid];
-        cxi = v & 0xffff;
-        cyi = v >> 16;
-    } else {
-        cxi = bid % P.ncx;
-        cyi = bid / P.ncx;
-    }
-    const int cx = P.x0 + cxi * 2 * CHUNK, cy = P.y0 + cyi * 2 * CHUNK;
-    unsigned int* const prog = sync + 1 + idx;
-    if (!(t & 1u)) {
-        run_pass<1, true>(P, cx, cy, P.iter, P.rkey, P.chunk_cost ? P.chunk_cost + cyi * P.ncx + cxi : nullptr, prog, 0u);
-        return;
-    }
-    run_pass<2, true>(P, cx, cy, P.iter, P.rkey, nullptr, prog, 0u);
-    asm volatile("fence.proxy.async;" ::: "memory");
-    __syncthreads();
-    for (int r = warp; r < CHUNK; r += PassGeom<1>::THREADS / 32) pass3_row_global(P, P.rkey, cx, cy + r, lane);
 }
 
 // Active-chunk bookkeeping after the three passes of a phase (per-pass kernels): wake the 3x3 chunks around a chunk whose state

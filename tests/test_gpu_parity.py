@@ -15,28 +15,15 @@ from tests import helpers as Hh
 pytestmark = pytest.mark.gpu
 
 
-# name -> (FSE_SCHEDULE_*, oracle Schedule).  "rows" = one launch per pass and colour phase (default), "rows_graph" = the same
-# schedule with the whole tick as one task-graph launch (tick_graph_kernel, FSE_TICK_GRAPH=1)
-SCHEDULES = {"rows": (1, 2), "rows_graph": (1, 2), "rows_fused": (2, 2), "classes": (0, 1)}
-ALL_SCHEDULES = ["rows", "rows_graph", "rows_fused", "classes"]
+# name -> (FSE_SCHEDULE_*, oracle Schedule).  "rows" = one launch per pass and colour phase (default)
+SCHEDULES = {"rows": (1, 2), "rows_fused": (2, 2), "classes": (0, 1)}
+ALL_SCHEDULES = ["rows", "rows_fused", "classes"]
 
 
 def _pair(oracle, gpu_ctx, table, W, H, sched="rows"):
     ow = oracle.OracleWorld(W, H, table)
     gpu_ctx.set_materials(table)
-    import os
-
-    old = os.environ.get("FSE_TICK_GRAPH")
-    if sched == "rows_graph":
-        os.environ["FSE_TICK_GRAPH"] = "1"  # read by fse_world_create
-    try:
-        gw = fse.World(gpu_ctx, W, H)
-    finally:
-        if sched == "rows_graph":
-            if old is None:
-                del os.environ["FSE_TICK_GRAPH"]
-            else:
-                os.environ["FSE_TICK_GRAPH"] = old
+    gw = fse.World(gpu_ctx, W, H)
     gw.set_schedule(SCHEDULES[sched][0])
     ow.default_schedule = SCHEDULES[sched][1]
     return ow, gw
@@ -244,30 +231,12 @@ def test_phase_parts_and_longest_first_order_do_not_change_results(oracle, gpu_c
     """Large worlds cut a colour phase into parts on separate streams and launch the chunks longest-first (last tick's
     pass-1 cycles).  Chunks of a phase are independent, so neither may change a single bit: force both on a small world."""
     monkeypatch.setenv("FSE_TICK_MIN_CHUNKS", "1")
-    monkeypatch.setenv("FSE_TICK_PAIRS", "6")  # the heaviest chunks of a phase as pipelined pass-1 / pass-2 CTA pairs (tick_pair_kernel)
     W = H = 1280
     tbl, extra = G.bench_table(table)
     ow, gw = _pair(oracle, gpu_ctx, tbl, W, H, "rows")
     Hh.build_mixed(ow, tbl, W, H, seed=5, extra=list(extra.values()))
     Hh.build_mixed(gw, tbl, W, H, seed=5, extra=list(extra.values()))
     _run_and_compare(ow, gw, 6, seed=3, what="parts + longest-first")
-
-
-@pytest.mark.parametrize("ctas_per_sm", ["1", "5"])
-def test_tick_graph_kernel_exact_for_any_grid(oracle, gpu_ctx, table, monkeypatch, ctas_per_sm):
-    """The whole-tick task-graph launch: 12 phases x 16-25 chunks on a 1280^2 world, with 148 CTAs (every CTA pops many
-    tasks off the ready queue) and with more CTAs than tasks of a phase (most of them wait for a queue slot to be filled).
-    Same chunk-level order as the per-phase launches, so bit-exact against the oracle."""
-    monkeypatch.setenv("FSE_GRAPH_CTAS_PER_SM", ctas_per_sm)
-    W = H = 1280
-    tbl, extra = G.bench_table(table)
-    ow, gw = _pair(oracle, gpu_ctx, tbl, W, H, "rows_graph")
-    Hh.build_mixed(ow, tbl, W, H, seed=5, extra=list(extra.values()))
-    Hh.build_mixed(gw, tbl, W, H, seed=5, extra=list(extra.values()))
-    _run_and_compare(ow, gw, 6, seed=3, what="task graph")
-    n0 = gpu_ctx.launch_count()
-    gw.tick(6, seed=3)
-    assert gpu_ctx.launch_count() - n0 == 2  # queue initialisation + the tick kernel
 
 
 def test_small_phases_pick_the_fused_kernel_with_identical_results(oracle, gpu_ctx, table, monkeypatch):
@@ -285,7 +254,7 @@ def test_small_phases_pick_the_fused_kernel_with_identical_results(oracle, gpu_c
 
 
 @pytest.mark.parametrize("seed", [11, 23, 37])
-@pytest.mark.parametrize("sched", ["rows", "rows_graph", "rows_fused"])
+@pytest.mark.parametrize("sched", ["rows", "rows_fused"])
 def test_random_worlds_long_runs(oracle, gpu_ctx, table, sched, seed):
     """Longer runs of the whole game loop (tick + tickCells + tickTemperature every 4th tick + camera scroll + render planes) on
     small-blob worlds of different seeds and shapes: every plane, the particle pool and the textures stay bit-identical."""
