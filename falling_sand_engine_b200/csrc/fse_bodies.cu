@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(BODY_TB, 8) bodies_body_kernel(BodyArgs a) {
                 any = true;
                 const int o = tid + k * BODY_TB;
                 if (*reinterpret_cast<volatile int*>(&s_cnt[o]) != 0) continue;
+                __threadfence_block();  // acquire side of body_release: the releasing pixels' s_mat / grid writes are visible from here on
                 const int tx = o / bhei, ty = o % bhei;
                 body_pixel_act_fast<ERASE>(a, b, tx, ty, (int)(px[k] & 0xff), (int)((px[k] >> 8) & 0xff), box, aw, s_mat, s_cnt, dep[k], bhei);
                 px[k] &= 0xffffu;

@@ -1,0 +1,61 @@
+"""Small run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck); no oracle in the loop.
+
+  compute-sanitizer --tool racecheck python scripts/sanitize_small.py [per_pass|fused|classes|aux]
+
+Worlds are tiny on purpose (the tools slow kernels down 10-100x).  The summaries are kept under profiles/.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+what = sys.argv[1] if len(sys.argv) > 1 else "per_pass"
+if what == "per_pass":
+    os.environ["FSE_FUSED_MAX_CHUNKS"] = "0"  # force tick_pass_kernel<1>/<2> + tick_pass3_kernel on a small world
+    os.environ["FSE_TICK_MIN_CHUNKS"] = "1"
+
+import falling_sand_engine_b200 as fse  # noqa: E402
+from falling_sand_engine_b200 import materials as M  # noqa: E402
+from falling_sand_engine_b200 import worldgen as G  # noqa: E402
+from tests import helpers as Hh  # noqa: E402
+from tests.test_bridge_cpu import make_body  # noqa: E402
+
+base = M.default_materials(1337)
+table, extra = G.bench_table(base)
+ctx = fse.Context(0, table)
+W, H = 640, 512
+w = fse.World(ctx, W, H)
+Hh.build_mixed(w, table, W, H, seed=1337, extra=list(extra.values()), blob=16)
+if what in ("per_pass", "fused", "classes"):
+    w.set_schedule({"per_pass": 1, "fused": 2, "classes": 0}[what])
+    for t in range(2):
+        w.tick(t)
+    if what == "per_pass":
+        w.active_enable(True)
+        w.tick(2)
+else:
+    w.tick(0)
+    w.tick_temperature()
+    w.particles_tick()
+    w.pixels_enable(True)
+    w.render_dirty(want_stats=True)
+    w.clear_dirty()
+    w.explosion(300, 260, 12, tick=1)
+    w.scroll(-128, 0)
+    bodies = [make_body(table, 20, 24, seed=1, fill=0.8), make_body(table, 16, 16, seed=4, fill=1.0), make_body(table, 70, 60, seed=2, fill=0.7)]
+    xf = np.array([(300.0, 300.0, 0.3), (310.0, 290.0, -0.7), (200.0, 200.0, 1.0)], dtype=np.float32)
+    w.bodies_upload(bodies)
+    w.bodies_raster(xf, tick=1)
+    w.bodies_erase(xf)
+    masks = (np.arange(2 * 24 * 20).reshape(2, 24, 20) % 7 != 0).astype(np.uint8)
+    w.mask_outline(masks)
+    w.flood_component(300, 300)
+    w.particles_tick()
+s = w.stats()
+w.sync()
+print(f"sanitize_small {what}: hash={s.hash:016x} particles={w.particles_count()} launches={ctx.launch_count()}")
+w.close()
+ctx.close()
