@@ -27,7 +27,7 @@ EXPORTS = [
     "fse_world_create", "fse_world_destroy", "fse_sync", "fse_write_rect", "fse_read_rect", "fse_clear_dirty", "fse_stats_rect",
     "fse_tick", "fse_tick_temperature", "fse_particles_add", "fse_particles_tick", "fse_particles_count", "fse_particles_read",
     "fse_particles_clear", "fse_particles_reserve", "fse_timer_start", "fse_timer_stop", "fse_launch_count",
-    "fse_kernel_timing_enable", "fse_kernel_timing_read",
+    "fse_kernel_timing_enable", "fse_kernel_timing_read", "fse_kernel_timing_phases",
 ]
 
 
@@ -205,6 +205,12 @@ class World:
             _ck(self.L.fse_particles_read(self.h, out.ctypes.data_as(C.c_void_p), n, C.byref(m)))
         return out
 
+    def particles_dropped(self):
+        n = C.c_int64()
+        self.L.fse_particles_dropped.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        _ck(self.L.fse_particles_dropped(self.h, C.byref(n)))
+        return n.value
+
     def particles_clear(self):
         _ck(self.L.fse_particles_clear(self.h))
 
@@ -228,7 +234,12 @@ class World:
         xf = np.ascontiguousarray(xforms, dtype=np.float32).reshape(-1, 3)
         return xf, len(xf)
 
-    def bodies_raster(self, xforms, tick=0, seed=1337):
+    def bodies_raster(self, xforms, tick=None, seed=1337):
+        """tick keys the ids and velocities of the particles the bodies throw up; without one a per-world call counter is used,
+        so that repeated calls never reissue an id."""
+        if tick is None:
+            self._raster_calls = getattr(self, "_raster_calls", 0) + 1
+            tick = self._raster_calls
         xf, n = self._xf(xforms)
         fb = np.zeros((n, 4), dtype=np.int32)
         self.L.fse_bodies_raster.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]
@@ -368,6 +379,14 @@ class World:
 
     def kernel_timing(self, enable):
         _ck(self.L.fse_kernel_timing_enable(self.h, 1 if enable else 0))
+
+    def kernel_timing_phases(self, cap=1 << 16):
+        """ms of every timed colour phase since kernel_timing(True), in launch order (call before kernel_timing_read)."""
+        out = np.zeros(cap, dtype=np.float32)
+        n = C.c_int64()
+        self.L.fse_kernel_timing_phases.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        _ck(self.L.fse_kernel_timing_phases(self.h, out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value]
 
     def kernel_timing_read(self):
         tot, n = C.c_double(), C.c_int64()

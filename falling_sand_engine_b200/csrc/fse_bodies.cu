@@ -556,6 +556,8 @@ static int run_bridge(fse_world* w, const fse_xform* xf, int32_t n, uint32_t tic
     if (!B || B->n != n) return fail(FSE_ESTATE, "bodies: %d transforms for %d uploaded bodies (fse_bodies_upload first)", n, B ? B->n : 0);
     if (n == 0) return FSE_OK;
     CK(cudaSetDevice(w->ctx->device));
+    if (!ERASE)  // every body pixel may displace a cell into the particle pool
+        if (int r = particles_headroom(w, B->n_pixels, false)) return r;
     std::vector<float4> h(n);
     for (int i = 0; i < n; i++) h[i] = make_float4(xf[i].x, xf[i].y, std::sin(xf[i].angle), std::cos(xf[i].angle));  // game.cpp:1763-1764 on the host's libm
     CK(cudaMemcpyAsync(B->d_xf, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, w->stream));

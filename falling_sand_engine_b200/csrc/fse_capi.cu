@@ -218,7 +218,7 @@ static void free_world(fse_world* w) {
     cudaFree(w->d_pixels); cudaFree(w->d_render_stats); cudaFree(w->scroll_scratch);
     if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
     if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);
-    cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list); cudaFree(w->d_chunk_state);
+    cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list); cudaFree(w->d_chunk_state); cudaFree(w->d_rowmask);
     fse_bodies_free(w);
     cudaFree(w->outline_scratch);
     delete w;
@@ -245,6 +245,7 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_stats, dev_stats_bytes());
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
     if (const char* env = getenv("FSE_TICK_LPT")) w->lpt_on = atoi(env) != 0;
+    if (const char* env = getenv("FSE_ROW_SKIP")) w->rowskip_on = atoi(env) != 0;
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -382,8 +383,12 @@ FSE_API int fse_write_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32
     for (int yy = 0; yy < rh; yy += band) {
         int hb = rh - yy < band ? rh - yy : band;
         const fse_cell* src = cells + (size_t)yy * rw;
-        for (size_t i = 0; i < (size_t)hb * rw; i += 4099)  // cheap sampled validation of material ids
-            if (src[i].mat >= nmat) return fail(FSE_EINVAL, "fse_write_rect: cell material %u >= %d", src[i].mat, nmat);
+        {   // every cell: ids beyond the table would alias zero-filled LUT rows and index the interaction offsets out of range
+            const size_t nb = (size_t)hb * rw;
+            unsigned int worst = 0;
+            for (size_t i = 0; i < nb; i++) worst = src[i].mat > worst ? src[i].mat : worst;
+            if ((int)worst >= nmat) return fail(FSE_EINVAL, "fse_write_rect: cell material %u >= %d (material table size)", worst, nmat);
+        }
         CK(cudaMemcpyAsync(w->d_stage, src, (size_t)hb * rw * sizeof(fse_cell), cudaMemcpyHostToDevice, w->stream));
         CK(launch_write_rect(w->p, w->W, x, y + yy, rw, hb, w->d_stage, w->stream));
         if (int r = wake_rect(w, x, y + yy, rw, hb)) return r;
@@ -590,6 +595,9 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
         if (int r = build_strip_lists(w, z, j0, j1)) return r;
     }
     const bool multi = w->strip && w->ctx->nranks > 1;
+    // falling sand and liquid leave the grid as loose particles: keep an eighth of the pool free per tick (the live count is read
+    // back only when the promises since the last read could exceed the pool)
+    if (int r = particles_headroom(w, (int64_t)(w->pcap / 8), false)) return r;
     KtScope kt{w};
     for (int iter = 0; iter < a->cell_iter; iter++) {
         for (int tk = 0; tk < 4; tk++) {
@@ -624,6 +632,19 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.chunk_base = 0;
             P.chunk_cost = nullptr;
             P.chunk_state = nullptr;
+            P.rowmask = nullptr;
+            if (w->rowskip_on && w->schedule == FSE_SCHEDULE_ROWS && !w->fused) {
+                const int need = ((nx + 1) / 2) * ((ny + 1) / 2);
+                if (need > w->rowmask_cap) {
+                    CK(cudaStreamSynchronize(w->stream));
+                    cudaFree(w->d_rowmask);
+                    w->d_rowmask = nullptr;
+                    w->rowmask_cap = 0;
+                    CK(cudaMalloc((void**)&w->d_rowmask, sizeof(uint32_t) * ROWMASK_WORDS * (size_t)need));
+                    w->rowmask_cap = need;
+                }
+                P.rowmask = w->d_rowmask;
+            }
             if (!w->strip) {
                 const int n_chunks = P.ncx * P.ncy;
                 if (n_chunks <= 0) continue;
@@ -757,10 +778,28 @@ FSE_API int fse_particles_count(fse_world* w, int64_t* out) {
     unsigned int n = 0;
     CK(cudaMemcpyAsync(&n, w->pcount, sizeof n, cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
-    if (n > w->pcap) return fail(FSE_ESTATE, "particle pool overflow: %u spawned, capacity %u (fse_particles_reserve)", n, w->pcap);
+    if (n > w->pcap) {  // the kernels counted particles they had no slot for: the pool holds pcap, the rest is reported as dropped
+        w->particles_dropped += n - w->pcap;
+        n = w->pcap;
+        CK(cudaMemcpyAsync(w->pcount, &n, sizeof n, cudaMemcpyHostToDevice, w->stream));
+        CK(cudaStreamSynchronize(w->stream));
+    }
+    w->particles_seen = n;
     *out = n;
     return FSE_OK;
 }
+
+// Cumulative number of particles the kernels could not store (pool full).  The pool grows on its own (particles_headroom), so
+// this stays 0 unless one call spawns more than the head-room it was given.
+FSE_API int fse_particles_dropped(fse_world* w, int64_t* out) {
+    if (!w || !out) return fail(FSE_EINVAL, "fse_particles_dropped: null argument");
+    int64_t n = 0;
+    if (int r = fse_particles_count(w, &n)) return r;
+    *out = (int64_t)w->particles_dropped;
+    return FSE_OK;
+}
+
+
 
 FSE_API int fse_particles_read(fse_world* w, fse_particle* out, int64_t cap, int64_t* n_out) {
     if (!w || !n_out) return fail(FSE_EINVAL, "fse_particles_read: null argument");
@@ -807,7 +846,7 @@ FSE_API int fse_particles_add(fse_world* w, const fse_particle* p, int32_t n) {
     std::vector<fse_particle> tmp(p, p + n);
     for (int i = 0; i < n; i++) {
         if (tmp[i].tile.mat >= w->ctx->h_tabs.n) return fail(FSE_EINVAL, "fse_particles_add: particle %d material out of range", i);
-        if (tmp[i].id == 0) tmp[i].id = (1ULL << 63) | (w->next_user_particle++);
+        if (tmp[i].id == 0) tmp[i].id = (1ULL << 62) | (w->next_user_particle++);  // id bits 63..62: 00 tick kernels, 01 caller, 10 bridge, 11 explosion
     }
     CK(cudaMemcpy(w->pbuf + have, tmp.data(), sizeof(fse_particle) * (size_t)n, cudaMemcpyHostToDevice));
     unsigned int total = (unsigned int)(have + n);
@@ -839,6 +878,17 @@ FSE_API int fse_kernel_timing_enable(fse_world* w, int enable) {
     return FSE_OK;
 }
 
+// each timed colour phase on its own, in launch order (12 per tick at cell_iter = 3); does not reset the record
+FSE_API int fse_kernel_timing_phases(fse_world* w, float* out_ms, int64_t cap, int64_t* n_out) {
+    if (!w || !n_out || (!out_ms && cap > 0)) return fail(FSE_EINVAL, "fse_kernel_timing_phases: null argument");
+    CK(cudaSetDevice(w->ctx->device));
+    CK(cudaStreamSynchronize(w->stream));
+    int64_t n = 0;
+    for (size_t i = 0; i < w->kt_used && n < cap; i++, n++) CK(cudaEventElapsedTime(&out_ms[i], w->kt_events[i].first, w->kt_events[i].second));
+    *n_out = n;
+    return FSE_OK;
+}
+
 FSE_API int fse_kernel_timing_read(fse_world* w, double* total_ms, int64_t* launches) {
     if (!w || !total_ms || !launches) return fail(FSE_EINVAL, "fse_kernel_timing_read: null argument");
     CK(cudaSetDevice(w->ctx->device));
@@ -856,6 +906,29 @@ FSE_API int fse_kernel_timing_read(fse_world* w, double* total_ms, int64_t* laun
 }
 
 }  // extern "C"
+
+namespace fse {
+// Make room for `need` more particles before a call that spawns them.  exact: read the live count (one stream sync; rare calls
+// such as fse_explosion); otherwise use the count seen by the last call that read it plus what was promised since.
+int particles_headroom(fse_world* w, int64_t need, bool exact) {
+    int64_t have = (int64_t)w->particles_seen + w->particles_promised;
+    if (exact || have + need > (int64_t)w->pcap) {
+        int64_t n = 0;
+        if (int r = fse_particles_count(w, &n)) return r;
+        w->particles_promised = 0;
+        have = n;
+    }
+    if (have + need > (int64_t)w->pcap) {
+        int64_t cap = (int64_t)w->pcap * 2;
+        while (cap < have + need) cap *= 2;
+        if (cap > ((int64_t)1 << 30)) cap = (int64_t)1 << 30;
+        if (cap > (int64_t)w->pcap)
+            if (int r = fse_particles_reserve(w, cap)) return r;
+    }
+    w->particles_promised += need;
+    return FSE_OK;
+}
+}  // namespace fse
 
 namespace fse {
 int fse_wake_rect(fse_world* w, int x, int y_local, int rw, int rh) { return ::wake_rect(w, x, y_local, rw, rh); }

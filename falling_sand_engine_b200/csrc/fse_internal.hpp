@@ -70,6 +70,14 @@ struct fse_world {
     int lpt_cap = 0;            // chunks per colour the buffers hold
     int lpt_sig[4][4]{};        // (x0, y0, ncx, ncy) the list of a colour was built for; ncx = 0: no list yet
     bool lpt_on = true;
+    // settled-row skipping of the per-pass kernels (classify_rows_kernel): ROWMASK_WORDS words per chunk of a colour's grid
+    uint32_t* d_rowmask = nullptr;
+    int rowmask_cap = 0;
+    bool rowskip_on = true;  // FSE_ROW_SKIP=0 steps every row (A/B measurements)
+    // particle pool bookkeeping on the host: count seen by the last call that read it, particles promised to calls since, drops
+    unsigned int particles_seen = 0;
+    int64_t particles_promised = 0;
+    uint64_t particles_dropped = 0;
     // rigid-body bridge (fse_bodies.cu) and outline scratch (fse_outline.cu)
     struct fse_bodies* bodies = nullptr;
     int last_bridge_rounds = 0;
@@ -108,6 +116,7 @@ extern thread_local std::string g_err;
 int fail(int code, const char* fmt, ...);
 int fse_wake_rect(fse_world* w, int x, int y_local, int rw, int rh);  // wake the chunks under a rect of local rows (active tracking)
 
+int particles_headroom(fse_world* w, int64_t need, bool exact);  // grow the particle pool before a call that spawns up to `need`
 int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cudaStream_t s);
 int strip_refresh(fse_world* w, cudaStream_t s);
 size_t tick_smem_bytes();

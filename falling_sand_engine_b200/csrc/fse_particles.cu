@@ -243,9 +243,12 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
         return fail(FSE_ESTATE, "fse_particles_tick: particle migration between strips is not implemented yet (single-GPU worlds only)");
     CK(cudaSetDevice(w->ctx->device));
     unsigned int n = 0;
-    CK(cudaMemcpyAsync(&n, w->pcount, sizeof n, cudaMemcpyDeviceToHost, w->stream));
-    CK(cudaStreamSynchronize(w->stream));
-    if (n > w->pcap) return fail(FSE_ESTATE, "particle pool overflow: %u spawned, capacity %u (fse_particles_reserve)", n, w->pcap);
+    {
+        int64_t n64 = 0;
+        if (int r = fse_particles_count(w, &n64)) return r;  // clamps an overflowed counter and records the drops
+        n = (unsigned int)n64;
+        w->particles_promised = 0;
+    }
     if (n == 0) return FSE_OK;
     CK(grow(&w->part_scratch, &w->part_scratch_bytes, sizeof(PState) * (size_t)n));
     CK(grow((void**)&w->pbuf2, &w->pbuf2_bytes, sizeof(fse_particle) * (size_t)w->pcap));

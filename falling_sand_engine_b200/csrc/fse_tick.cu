@@ -56,7 +56,7 @@ struct SmemHead {
     unsigned char rowmod[32];  // row must be stored back (any plane or the dirty bit changed)
     unsigned char rowchg[32];  // cell state other than the dirty bit changed (active-region tracking)
     unsigned char rowvis[32];  // row got tickVisited marks only (per-pass kernels persist them through HBM)
-    unsigned char pad_[32];
+    unsigned char rowlazy[32]; // pass 1 skipped the row: its tickVisited marks are implicit (iter >= iterations of the cell's material)
 };
 static_assert(sizeof(SmemHead) % 128 == 0, "the row window behind the head must stay 128-byte aligned");
 extern __shared__ __align__(128) unsigned char fse_smem[];
@@ -64,6 +64,7 @@ extern __shared__ __align__(128) unsigned char fse_smem[];
 #define ROWMOD (fse_smem + offsetof(SmemHead, rowmod))
 #define ROWCHG (fse_smem + offsetof(SmemHead, rowchg))
 #define ROWVIS (fse_smem + offsetof(SmemHead, rowvis))
+#define ROWLAZY (fse_smem + offsetof(SmemHead, rowlazy))
 #define RINGP (fse_smem + sizeof(SmemHead))
 
 struct __align__(128) Smem {
@@ -249,7 +250,7 @@ __device__ __forceinline__ CellR fresh_fluid(const CellR& t) {
 }
 
 __device__ __forceinline__ uint64_t particle_id(const Ctx& c, int x, int y, int k) {
-    return ((uint64_t)(c.tick & 0x3fffff) << 42) | ((uint64_t)(c.iter & 3) << 40) | ((uint64_t)(y & 0x3ffff) << 22) |
+    return ((uint64_t)(c.tick & 0xfffff) << 42) | ((uint64_t)(c.iter & 3) << 40) | ((uint64_t)(y & 0x3ffff) << 22) |
            ((uint64_t)(x & 0x3ffff) << 4) | (uint64_t)(k & 15);
 }
 
@@ -1118,6 +1119,10 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
             const int lo = (int)((long long)n_chunks * q / parts), hi = (int)((long long)n_chunks * (q + 1) / parts);
             if (hi <= lo) continue;  // fewer chunks than parts
             Q.chunk_base = P.chunk_base + lo;
+            if (Q.rowmask) {
+                classify_rows_kernel<<<(hi - lo) * 4, 1024, sizeof(Lut), st>>>(Q);
+                *launched += 1;
+            }
             tick_pass_kernel<1><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>) + pad, st>>>(Q);
             tick_pass_kernel<2><<<hi - lo, PassGeom<2>::THREADS, sizeof(SmemPass<2>) + pad, st>>>(Q);
             tick_pass3_kernel<<<(hi - lo) * (CHUNK / 4), 128, 0, st>>>(Q);

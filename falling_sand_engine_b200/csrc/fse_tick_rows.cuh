@@ -1018,6 +1018,8 @@ struct __align__(128) SmemPass {
     unsigned char ring[PassGeom<PASS>::RN * ROW_BYTES];
     Ctx ctx;
     unsigned long long bar[PassGeom<PASS>::RN];
+    uint32_t m_act[4];   // rows of the chunk this pass must run (classify_rows_kernel; pass 2: + what pass 1 changed)
+    uint32_t m_lazy[4];  // pass 2: rows whose pass-1 tickVisited marks are still implicit
     typename PassScratch<PASS>::type rs;
 };
 
@@ -1053,6 +1055,7 @@ __device__ __forceinline__ void pass_row_load(SmemPass<PASS>& S, const PlaneIO& 
         S.h.rowmod[q] = 0;
         S.h.rowchg[q] = 0;
         S.h.rowvis[q] = 0;
+        S.h.rowlazy[q] = 0;
         mbar_expect_tx(bar, mat_only ? P8 : ROW_BYTES);
     }
     __syncwarp();
@@ -1060,10 +1063,127 @@ __device__ __forceinline__ void pass_row_load(SmemPass<PASS>& S, const PlaneIO& 
         bulk_g2s(S.ring + q * ROW_BYTES + io.soff, io.g + (size_t)(cy + CHUNK - 1 - k) * io.row_stride, io.bytes, bar);
 }
 
+// ---- settled-row skipping (north_star: "warp-vote/ballot skips settled tiles", here at chunk-row granularity) -----------------------
+// Before pass 1 of a colour phase classify_rows_kernel reads the material and flag planes of the phase's chunks once, at streaming
+// speed, and votes per chunk row whether pass 1 / pass 2 can change anything in it for ANY random draw:
+//   a cell whose material has used up its iterations (iter >= Material::iterations, world.cpp:1093-1096 — AIR and SOLID always) only
+//     gets its tickVisited mark in pass 1 and is skipped by passes 2 and 3;
+//   SAND acts in pass 1 if it can sink into the cell below, has a pair interaction armed with it or a temperature reaction firing, and
+//     in pass 2 if it is `moved` or can sink into a lower diagonal (1609-1654);
+//   SOUP acts in pass 1 unless it is settled (`moved`, 1307) over a non-AIR cell with a sane amount, and always in pass 2 (1728-1745);
+//   GAS and FIRE always act.
+// A row neither pass must run is not stepped: pass 1 skips row k when its bit is clear and neither row k nor row k - 1 (what the
+// decisions of row k read besides the cell itself) has been changed by an earlier step of this pass.  The tickVisited marks such a
+// row would have received (iterations used up) stay IMPLICIT — nothing is written — until a running row is about to write into
+// it: the running row first materialises the marks of the skipped rows within its write reach (their materials are still the ones
+// they had at their own step), so every positional mark is in place before any cell moves onto it.  Rows that stay implicit to the
+// end of pass 1 are handed to pass 2 as a bit mask; pass 2 materialises them the same way, just before a running row can touch
+// them.  A chunk with no row to run exits before loading anything.  Results are bit-identical to stepping every row.
+__device__ __forceinline__ void materialize_marks(const Ctx& c, int slot, int j) {
+    if (c.iter >= (int)LUTP->iters[MAT(slot, j)]) {
+        FLG(slot, j) = FLG(slot, j) | F_VISITED;
+        ROWVIS[slot] = 1;
+    }
+}
+
+// grid = 4 CTAs per chunk of the launch, 1024 threads: warp w of CTA c votes row k = 32 * c + w (counted from the chunk's bottom row)
+__global__ void __launch_bounds__(1024) classify_rows_kernel(const __grid_constant__ TickParams P) {
+    __shared__ uint32_t s_a1[32], s_a2[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(&P.tabs->lut);
+        uint4* dst = reinterpret_cast<uint4*>(fse_smem);
+        for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int chunk = (int)(blockIdx.x >> 2) + P.chunk_base;
+    if (P.list_count && chunk >= *P.list_count) return;
+    int cxi, cyi;
+    if (P.chunk_list) {
+        const int v = P.chunk_list[chunk];
+        cxi = v & 0xffff;
+        cyi = v >> 16;
+    } else {
+        cxi = chunk % P.ncx;
+        cyi = chunk / P.ncx;
+    }
+    const int cx = P.x0 + cxi * 2 * CHUNK, cy = P.y0 + cyi * 2 * CHUNK;
+    const int k = (int)(blockIdx.x & 3) * 32 + warp;
+    const int ym = cy + CHUNK - 1 - k;  // memory row of chunk row k
+    const DevTables* T = P.tabs;
+    const size_t base = (size_t)ym * P.W + cx;
+    const uint32_t mw = __ldg(reinterpret_cast<const uint32_t*>(P.p.mat + base) + lane);
+    const uint32_t fw = __ldg(reinterpret_cast<const uint32_t*>(P.p.flg + base) + lane);
+    const uint32_t bw = __ldg(reinterpret_cast<const uint32_t*>(P.p.mat + base + P.W) + lane);  // the row below
+    uint32_t bL = __shfl_up_sync(0xffffffffu, bw >> 24, 1), bR = __shfl_down_sync(0xffffffffu, bw & 0xff, 1);
+    if (lane == 0) bL = __ldg(P.p.mat + base + P.W - 1);
+    if (lane == 31) bR = __ldg(P.p.mat + base + P.W + CHUNK);
+    bool a1 = false, a2 = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int m = (mw >> (8 * q)) & 0xff;
+        if (P.iter >= (int)LUTP->iters[m]) continue;  // marked in pass 1 (implicitly), skipped afterwards
+        const int ph = LUTP->phys[m];
+        if (ph == P_AIR || ph == P_SOLID) continue;
+        const bool moved = (fw >> (8 * q)) & F_MOVED;
+        const int mb = (bw >> (8 * q)) & 0xff;
+        const int mbl = q == 0 ? (int)bL : (int)((bw >> (8 * (q - 1))) & 0xff), mbr = q == 3 ? (int)bR : (int)((bw >> (8 * (q + 1))) & 0xff);
+        if (ph == P_PASSABLE) {
+            a1 |= m == T->fire;
+        } else if (ph == P_SAND) {
+            const float d = LUTP->dens[m];
+            auto sink = [&](int mm) { const int t = LUTP->phys[mm]; return t == P_AIR || (t != P_SOLID && LUTP->dens[mm] < d); };
+            const uint8_t mf = LUTP->mflags[m];
+            bool act = sink(mb);
+            if (mf & MF_INTERACT) {
+                if (mf & MF_INTERACT_SLOW) act = act || T->inter_off[m * T->n + mb + 1] > T->inter_off[m * T->n + mb];
+                else {
+                    const int r = LUTP->irow[m];
+                    act = act || (r != 0 && ((LUTP->ibits[r - 1][mb >> 5] >> (mb & 31)) & 1u));
+                }
+            }
+            if (mf & MF_REACT) {
+                if (mf & MF_REACT_MULTI) act = true;
+                else {
+                    const Lut::Rx rx = LUTP->rx[m];
+                    const int16_t t = __ldg(P.p.tmp + base + 4 * lane + q);
+                    act = act || (rx.type == FSE_REACT_TEMPERATURE_BELOW && t < rx.thr) || (rx.type == FSE_REACT_TEMPERATURE_ABOVE && t > rx.thr);
+                }
+            }
+            a1 |= act;
+            a2 |= moved || sink(mbl) || sink(mbr);
+        } else if (ph == P_SOUP) {
+            a2 = true;
+            if (!moved || LUTP->phys[mb] == P_AIR) a1 = true;
+            else {
+                const float fl = __ldg(P.p.fl + base + 4 * lane + q);
+                a1 |= fl != 0.0f && fl < FLUID_MinValue;
+            }
+        } else {
+            a1 = a2 = true;
+        }
+    }
+    const bool r1 = __any_sync(0xffffffffu, a1), r2 = __any_sync(0xffffffffu, a2);
+    if (lane == 0) {
+        s_a1[warp] = r1 ? 1u : 0u;
+        s_a2[warp] = r2 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w1 = __ballot_sync(0xffffffffu, s_a1[lane] != 0), w2 = __ballot_sync(0xffffffffu, s_a2[lane] != 0);
+        if (lane == 0) {
+            uint32_t* o = P.rowmask + (size_t)(cyi * P.ncx + cxi) * ROWMASK_WORDS + (blockIdx.x & 3);
+            o[0] = w1;
+            o[4] = w2;
+            o[8] = 0;
+        }
+    }
+}
+
 // One pass over one chunk by the whole CTA (4 compute warps + IO warp).  The material LUT is already in shared memory; scratch,
 // mbarriers and the context are (re)initialised here.  On return every bulk store of the pass has completed.
 template <int PASS>
-__device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, int iter, uint32_t rkey, unsigned int* cost_slot) {
+__device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, int iter, uint32_t rkey, unsigned int* cost_slot, int mask_idx) {
     using G = PassGeom<PASS>;
     unsigned char* const smem_raw = fse_smem;
     SmemPass<PASS>& S = *reinterpret_cast<SmemPass<PASS>*>(smem_raw);
@@ -1072,6 +1192,30 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     const bool io = warp >= 4, io_store = warp == 4, io_load = warp == (int)(blockDim.x >> 5) - 1;
     const long long t_begin = (PASS == 1 && cost_slot) ? clock64() : 0;
     const DevTables* T = P.tabs;
+    // settled-row skipping (see classify_rows_kernel): the rows this pass must run; a chunk without any is done
+    uint32_t* const gmask = P.rowmask ? P.rowmask + (size_t)mask_idx * ROWMASK_WORDS : nullptr;
+    if (gmask) {
+        const uint32_t* ga = gmask + (PASS == 1 ? 0 : 4);
+        const uint32_t a0 = ga[0], a1 = ga[1], a2 = ga[2], a3 = ga[3];
+        // (with active-chunk tracking pass 2 still walks the chunk: its store warp decides whether the chunk may sleep)
+        if (!(a0 | a1 | a2 | a3) && !(PASS == 2 && P.chunk_state)) {
+            if (PASS == 1) {
+                if (tid < 4) gmask[8 + tid] = 0xffffffffu;  // every row's marks stay implicit
+                if (cost_slot && tid == 0) *cost_slot = 1u;
+                if (P.chunk_state && tid == 0) P.chunk_state[((cy + P.y_off) / CHUNK) * P.acols + cx / CHUNK] = 0u;
+            }
+            return;
+        }
+        if (tid == 0) {
+            S.m_act[0] = a0; S.m_act[1] = a1; S.m_act[2] = a2; S.m_act[3] = a3;
+            for (int q = 0; q < 4; q++) S.m_lazy[q] = PASS == 2 ? gmask[8 + q] : 0u;
+        }
+    } else if (tid == 0) {
+        for (int q = 0; q < 4; q++) {
+            S.m_act[q] = 0xffffffffu;
+            S.m_lazy[q] = 0u;
+        }
+    }
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(&S.rs);
         for (int i = tid; i < (int)(sizeof(S.rs) / 4); i += blockDim.x) z[i] = 0;
@@ -1113,6 +1257,9 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
 
     const int n_steps = G::LAST + G::SL + 1;
     bool io_modified = false, io_inert = true;  // active-chunk tracking (IO warp): see tick_chunk_kernel
+    int last_run = -8;                          // compute warps: last row that was stepped (uniform over the CTA)
+    uint32_t io_lazy = 0, io_chg = 0;           // store warp, lane w < 4 holds word w.  pass 1: rows left implicit / rows pass 2 must run;
+                                                // pass 2: io_lazy = rows that stopped being implicit (marks written or row changed)
 #ifdef FSE_ROLE_CYCLES
     long long dbg_t[4] = {0, 0, 0, 0};  // mbarrier wait, step barrier, step work, steps
     long long dbg_io[3] = {0, 0, 0};    // IO lane 0: store side, wait for the slot's old store to leave shared memory, load issue
@@ -1134,8 +1281,51 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
         FSE_STEP_CLOCK(1, dbg_c);
         if (!io) {
             if (st < CHUNK) {
-                if (PASS == 1) pass1_rows<G::RN>(c, reinterpret_cast<Scratch1&>(S.rs), st, cx, cy, tid);
-                else pass2_rows<G::RN>(c, reinterpret_cast<Scratch2&>(S.rs), st, cx, cy, tid);
+                const int q = (st - G::KMIN) % G::RN, qb = (st - 1 - G::KMIN) % G::RN;
+                // run the row if it was classified active, or if an earlier step of this pass changed it or the row below it
+                const bool run = ((S.m_act[st >> 5] >> (st & 31)) & 1u) || S.h.rowchg[q] || S.h.rowchg[qb];
+                if (run) {
+                    const int j = HX8 + tid;
+                    if (PASS == 1) {
+                        // rows skipped since the last running row, as far down as this row can write (5 rows): marks in place first
+                        int lo = last_run + 1;
+                        if (lo < st - 5) lo = st - 5;
+                        if (lo < 0) lo = 0;  // rows below the chunk belong to other chunks: never marked from here
+                        for (int r = lo; r < st; r++) materialize_marks(c, (r - G::KMIN) % G::RN, j);
+                        pass1_rows<G::RN>(c, reinterpret_cast<Scratch1&>(S.rs), st, cx, cy, tid);
+                    } else {
+                        // rows st - 1 .. st + 1 are the ones this row can write: implicit pass-1 marks become real ones first
+                        int lo = last_run + 2;  // rows up to last_run + 1 were handled by that step
+                        if (lo < st - 1) lo = st - 1;
+                        if (lo < 0) lo = 0;
+                        for (int r = lo; r <= st + 1 && r < CHUNK; r++)
+                            if ((S.m_lazy[r >> 5] >> (r & 31)) & 1u) materialize_marks(c, (r - G::KMIN) % G::RN, j);
+                        pass2_rows<G::RN>(c, reinterpret_cast<Scratch2&>(S.rs), st, cx, cy, tid);
+                    }
+                    last_run = st;
+                } else {
+                    const int par = st & 1;  // what a running step resets for the next row (pass1_rows / pass2_rows)
+                    if (PASS == 1) {
+                        Scratch1& R = reinterpret_cast<Scratch1&>(S.rs);
+                        if (tid == 0) {
+                            R.p1_any[par ^ 1] = 0;
+                            R.p1_area[par ^ 1] = 0;
+                            R.p1_horiz[par ^ 1] = 0;
+                            R.area_mask[par ^ 1][0] = R.area_mask[par ^ 1][1] = R.area_mask[par ^ 1][2] = R.area_mask[par ^ 1][3] = 0;
+                            S.h.rowlazy[q] = 1;
+                        }
+                    } else {
+                        Scratch2& R = reinterpret_cast<Scratch2&>(S.rs);
+                        R.claimDn[par ^ 1][1 + tid] = 1 << 30;
+                        R.claimUp[par ^ 1][1 + tid] = 1 << 30;
+                        if (tid == 0) {
+                            R.claimDn[par ^ 1][0] = R.claimUp[par ^ 1][0] = 1 << 30;
+                            R.claimDn[par ^ 1][CHUNK + 1] = R.claimUp[par ^ 1][CHUNK + 1] = 1 << 30;
+                            R.p2_any[par ^ 1] = 0;
+                            R.p2_poke[par ^ 1] = 0;
+                        }
+                    }
+                }
             }
         } else {
 #ifdef FSE_ROLE_CYCLES
@@ -1151,6 +1341,14 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                 const bool core_row = ks >= 0 && ks < CHUNK;
                 const bool all_store = S.h.rowmod[q] != 0;
                 const bool vis_store = S.h.rowvis[q] != 0;
+                if (PASS == 2 && gmask && core_row && (all_store || vis_store) && lane == (ks >> 5)) io_lazy |= 1u << (ks & 31);
+                if (PASS == 1 && gmask) {
+                    if (core_row && S.h.rowlazy[q] && !all_store && !vis_store && lane == (ks >> 5)) io_lazy |= 1u << (ks & 31);
+                    if (S.h.rowchg[q]) {  // pass 2 reads a row's own cells and the row below them
+                        if (core_row && lane == (ks >> 5)) io_chg |= 1u << (ks & 31);
+                        if (ks + 1 >= 0 && ks + 1 < CHUNK && lane == ((ks + 1) >> 5)) io_chg |= 1u << ((ks + 1) & 31);
+                    }
+                }
                 // tickVisited of the chunk's own cells goes to HBM (the later passes need it); halo cells are cleared.  Only rows
                 // that are stored need it; a core row has 4 + 4 halo words (one word per lane 0..7), other rows are cleared whole
                 if (all_store || vis_store) {
@@ -1208,6 +1406,11 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
         unsigned int* slot = P.chunk_state + ((cy + P.y_off) / CHUNK) * P.acols + cx / CHUNK;
         if (lane == 0) *slot = PASS == 1 ? st : (*slot | st);  // pass 1 starts the record, pass 2 adds to it (same stream)
     }
+    if (PASS == 1 && gmask && io_store && lane < 4) {
+        gmask[8 + lane] = io_lazy;
+        gmask[4 + lane] |= io_chg;
+    }
+    if (PASS == 2 && gmask && io_store && lane < 4 && io_lazy) gmask[8 + lane] &= ~io_lazy;  // pass 3 applies the rule to what is left
     if (io_store) bulk_wait_all();
 }
 
@@ -1232,7 +1435,7 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
         uint4* dst = reinterpret_cast<uint4*>(fse_smem);
         for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    run_pass<PASS>(P, cx, cy, P.iter, P.rkey, (PASS == 1 && P.chunk_cost) ? P.chunk_cost + cyi * P.ncx + cxi : nullptr);
+    run_pass<PASS>(P, cx, cy, P.iter, P.rkey, (PASS == 1 && P.chunk_cost) ? P.chunk_cost + cyi * P.ncx + cxi : nullptr, cyi * P.ncx + cxi);
 }
 
 // ---- pass 3 on global memory: one warp per chunk row, lane l owns columns 4l..4l+3 (world.cpp:1828-1891) ---------------------
@@ -1240,15 +1443,23 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
 // STEAM and boxed in, condenses with probability 1/10.  All cells decide from the row as pass 2 left it; a contested AIR
 // cell goes to the lower source column, i.e. a left-mover at i loses exactly when cell i-2 moves right.  Visited bits are
 // dropped from the whole row afterwards (the colour phase is over).
-__device__ __forceinline__ void pass3_row_global(const TickParams& P, uint32_t rkey, int cx, int ym, int lane) {
+// lazy: the row's pass-1 tickVisited marks are implicit (settled-row skipping): a cell whose material has used up its iterations
+// counts as visited although its flag bit is clear.
+__device__ __forceinline__ void pass3_row_global(const TickParams& P, uint32_t rkey, int cx, int ym, int lane, bool lazy) {
     const int y = ym + P.y_off;
     const DevTables* T = P.tabs;
     const uint8_t* phys = T->lut.phys;
     const size_t base = (size_t)ym * P.W + cx;
     uint32_t* flgw = reinterpret_cast<uint32_t*>(P.p.flg + base) + lane;
-    const uint32_t fw = __ldcg(flgw);
+    uint32_t fw = __ldcg(flgw);
     const uint32_t mw = __ldcg(reinterpret_cast<const uint32_t*>(P.p.mat + base) + lane);
     const bool hadvis = (fw & 0x80808080U) != 0;
+    const uint32_t fw_mem = fw;
+    if (lazy) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (P.iter >= (int)__ldg(T->lut.iters + ((mw >> (8 * q)) & 0xff))) fw |= (uint32_t)F_VISITED << (8 * q);
+    }
     int ph[4];
     bool gas = false;
 #pragma unroll
@@ -1257,7 +1468,7 @@ __device__ __forceinline__ void pass3_row_global(const TickParams& P, uint32_t r
         gas |= ph[q] == P_GAS && !((fw >> (8 * q)) & F_VISITED);
     }
     if (!__any_sync(0xffffffffu, gas)) {
-        if (hadvis) *flgw = fw & 0x7f7f7f7fU;
+        if (hadvis) *flgw = fw_mem & 0x7f7f7f7fU;
         return;
     }
     // phys of the columns left of q = 0 and right of q = 3
@@ -1280,7 +1491,7 @@ __device__ __forceinline__ void pass3_row_global(const TickParams& P, uint32_t r
     }
     uint32_t rmPrev = __shfl_up_sync(0xffffffffu, rm, 1);
     if (lane == 0) rmPrev = 0;
-    if (hadvis) *flgw = fw & 0x7f7f7f7fU;
+    if (hadvis) *flgw = fw_mem & 0x7f7f7f7fU;
     __syncwarp();
     if (P.chunk_state) {  // any decision changes a cell (a lost contest is rare; counting it as a change only keeps the chunk awake)
         const bool acts = d[0] | d[1] | d[2] | d[3];
@@ -1338,7 +1549,12 @@ __global__ void __launch_bounds__(128) tick_pass3_kernel(const __grid_constant__
         cxi = chunk % P.ncx;
         cyi = chunk / P.ncx;
     }
-    pass3_row_global(P, P.rkey, P.x0 + cxi * 2 * CHUNK, P.y0 + cyi * 2 * CHUNK + r, lane);
+    bool lazy = false;
+    if (P.rowmask) {
+        const int k = CHUNK - 1 - r;
+        lazy = (P.rowmask[(size_t)(cyi * P.ncx + cxi) * ROWMASK_WORDS + 8 + (k >> 5)] >> (k & 31)) & 1u;
+    }
+    pass3_row_global(P, P.rkey, P.x0 + cxi * 2 * CHUNK, P.y0 + cyi * 2 * CHUNK + r, lane, lazy);
 }
 
 // Active-chunk bookkeeping after the three passes of a phase (per-pass kernels): wake the 3x3 chunks around a chunk whose state

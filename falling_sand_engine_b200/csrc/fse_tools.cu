@@ -78,6 +78,10 @@ extern "C" FSE_API int fse_explosion(fse_world* w, int32_t cx, int32_t cy, int32
     if (w->strip && w->ctx->nranks > 1) return fail(FSE_ESTATE, "fse_explosion: not available on multi-rank strips");
     cudaError_t e = cudaSetDevice(w->ctx->device);
     if (e != cudaSuccess) return fail(FSE_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    {   // every cell of the blast square may become a loose particle: make room first (the kernels drop what has no slot)
+        const long long side_ = 4LL * radius + 2, cells_ = (long long)w->W * w->H;
+        if (int r = particles_headroom(w, side_ * side_ < cells_ ? side_ * side_ : cells_, true)) return r;
+    }
     ExplArgs a;
     a.p = w->p;
     a.T = w->ctx->d_tabs;

@@ -66,6 +66,14 @@ def border_fill(mat, x0, y0, width, height, solid_id):
     return mat
 
 
+def air_band(table, width, height, y0, rows, seed=1337):
+    """Rows [y0, y0+rows) of an empty world: AIR inside the tickZone, GENERIC_SOLID border.  The do-nothing floor of the tick."""
+    ids = _names(table)
+    mat = np.full((rows, width), ids["AIR"], dtype=np.uint16)
+    border_fill(mat, 0, y0, width, height, ids["GENERIC_SOLID"])
+    return cells_from_mat(table, mat, 0, y0, seed)
+
+
 # ---- config 1: 2048x2048 sand/water/stone column drop -------------------------------------
 def column_drop_band(table, width, height, y0, rows, seed=1337, scale=None):
     """Rows [y0, y0+rows) of the column-drop world.  Coordinates of SURVEY §8d(1) are for

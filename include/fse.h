@@ -215,8 +215,12 @@ FSE_API int fse_particles_tick(fse_world* w, const fse_rect* tick_zone);
 FSE_API int fse_particles_count(fse_world* w, int64_t* out);
 FSE_API int fse_particles_read(fse_world* w, fse_particle* out, int64_t cap, int64_t* n_out);
 FSE_API int fse_particles_clear(fse_world* w);
-/* capacity of the device particle pool (default 1<<20); the reference's std::vector grows unbounded */
+/* capacity of the device particle pool (default 1<<20); the reference's std::vector grows unbounded.  The pool also grows on its
+ * own: fse_tick keeps an eighth of it free, fse_explosion and fse_bodies_raster make room for every cell they may throw up. */
 FSE_API int fse_particles_reserve(fse_world* w, int64_t capacity);
+/* cumulative count of particles a kernel could not store because one call spawned more than the head-room it was given
+ * (their cells are gone from the grid); 0 in normal operation.  fse_particles_count never fails on an overflowed pool. */
+FSE_API int fse_particles_dropped(fse_world* w, int64_t* out);
 
 /* ---- rigid-body bridge: the raster / erase loops of game::tick (game.cpp:1711-1815, 1896-1983) ---------------
  * Box2D stays on the host (north_star); the host keeps b2Body poses and sends one fse_xform per body per tick.
@@ -322,6 +326,7 @@ FSE_API int64_t fse_launch_count(fse_ctx* ctx);
  * last reset, from CUDA events recorded around every launch when enabled. */
 FSE_API int fse_kernel_timing_enable(fse_world* w, int enable);
 FSE_API int fse_kernel_timing_read(fse_world* w, double* total_ms, int64_t* launches);
+FSE_API int fse_kernel_timing_phases(fse_world* w, float* out_ms, int64_t cap, int64_t* n_out);
 /* profiling aid: cycles each warp role of the tick kernel spent working between step barriers (out[0..3]) and chunks (out[4]) */
 FSE_API int fse_debug_role_cycles(fse_world* w, int enable, unsigned long long* out);
 

@@ -169,7 +169,7 @@ inline uint32_t World::draw(uint32_t slot, int x, int y) const {
 }
 
 uint64_t World::particle_id(int x, int y, int iter, int k) const {
-    return ((uint64_t)(curTick & 0x3fffff) << 42) | ((uint64_t)(iter & 3) << 40) | ((uint64_t)(y & 0x3ffff) << 22) |
+    return ((uint64_t)(curTick & 0xfffff) << 42) | ((uint64_t)(iter & 3) << 40) | ((uint64_t)(y & 0x3ffff) << 22) |
            ((uint64_t)(x & 0x3ffff) << 4) | (uint64_t)(k & 15);
 }
 

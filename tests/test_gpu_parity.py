@@ -239,6 +239,32 @@ def test_phase_parts_and_longest_first_order_do_not_change_results(oracle, gpu_c
     _run_and_compare(ow, gw, 6, seed=3, what="parts + longest-first")
 
 
+def test_benched_kernel_path_at_more_than_one_wave(oracle, gpu_ctx, table, monkeypatch):
+    """The path bench.py times, with no override: a 4096 x 2304 world has 480 zone chunks, 120 per colour phase... too few for
+    the default threshold, so the world is 5376 x 4352 (40 x 32 zone chunks, 320 per phase > 2 x 148): every phase runs
+    tick_pass_kernel<1> / <2> / tick_pass3_kernel cut into 3 parts on 3 streams, chunks in longest-first order from the second
+    tick on, more than one wave of CTA slots on pass 1.  Whole-grid state hash, per-material counts, dirty / moved totals and the
+    emitted-particle count must equal the oracle's ROWS schedule; the full planes are compared on a 1024-row band as well."""
+    for k in ("FSE_FUSED_MAX_CHUNKS", "FSE_TICK_MIN_CHUNKS", "FSE_TICK_PARTS", "FSE_TICK_LPT"):
+        monkeypatch.delenv(k, raising=False)
+    W, H = 5376, 4352
+    tbl, extra = G.bench_table(table)
+    ow, gw = _pair(oracle, gpu_ctx, tbl, W, H, "rows")
+    gw.particles_reserve(1 << 23)  # a fresh mixed world drops millions of grains in its first tick (the reference's vector just grows)
+    Hh.build_mixed(ow, tbl, W, H, seed=1337, extra=list(extra.values()), blob=64)
+    Hh.build_mixed(gw, tbl, W, H, seed=1337, extra=list(extra.values()), blob=64)
+    for t in range(3):
+        n0 = gpu_ctx.launch_count()
+        ow.tick(t, seed=1337)
+        gw.tick(t, seed=1337)
+        assert gpu_ctx.launch_count() - n0 >= 12 * 9  # 12 phases x 3 parts x 3 pass kernels (+ the ordering kernels)
+        so, sg = ow.stats(), gw.stats()
+        assert so.hash == sg.hash, t
+        assert list(so.count) == list(sg.count) and so.n_dirty == sg.n_dirty and so.n_moved == sg.n_moved
+        assert ow.particles_count() == gw.particles_count()
+    Hh.assert_cells_equal(ow.read_rect(0, 1500, W, 1024), gw.read_rect(0, 1500, W, 1024), "band of the large world")
+
+
 def test_small_phases_pick_the_fused_kernel_with_identical_results(oracle, gpu_ctx, table, monkeypatch):
     """Default kernel selection (no override): a 640x512 world has 2-3 chunks per colour phase, far below one wave of the fused
     kernel, so the rows schedule runs there; results must not depend on the choice."""
