@@ -218,8 +218,13 @@ static void free_world(fse_world* w) {
     cudaFree(w->d_pixels); cudaFree(w->d_render_stats); cudaFree(w->scroll_scratch);
     if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
     if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);
+    for (int q = 0; q < 4; q++) cudaFree(w->halo_stage[q]);
+    cudaFree(w->d_phase_rows);
+    if (w->h_phase_rows) cudaFreeHost(w->h_phase_rows);
+    if (w->ev_phase_rows) cudaEventDestroy(w->ev_phase_rows);
     cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list); cudaFree(w->d_chunk_state); cudaFree(w->d_rowmask);
     fse_bodies_free(w);
+    particles_strip_free(w);
     cudaFree(w->outline_scratch);
     delete w;
 }
@@ -245,7 +250,15 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_stats, dev_stats_bytes());
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
     if (const char* env = getenv("FSE_TICK_LPT")) w->lpt_on = atoi(env) != 0;
-    if (const char* env = getenv("FSE_ROW_SKIP")) w->rowskip_on = atoi(env) != 0;
+    if (const char* env = getenv("FSE_ROW_SKIP")) w->rowskip_mode = atoi(env);
+    if (const char* env = getenv("FSE_ROW_SKIP_MAX_ACTIVE")) w->rowskip_max_active = (float)atof(env);
+    for (int q = 0; q < 16; q++) {
+        w->phase_active[q] = -1.0f;
+        w->phase_rows_total[q] = 0;
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&w->d_phase_rows, 16 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_phase_rows, 16 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->ev_phase_rows, cudaEventDisableTiming);
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -599,6 +612,18 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
     // back only when the promises since the last read could exceed the pool)
     if (int r = particles_headroom(w, (int64_t)(w->pcap / 8), false)) return r;
     KtScope kt{w};
+    // skip gate: collect the counts of the last tick that finished, then zero the counters for this one
+    if (w->phase_rows_pending && cudaEventQuery(w->ev_phase_rows) == cudaSuccess) {
+        for (int q = 0; q < 16; q++)
+            if (((w->phase_rows_valid >> q) & 1u) && w->phase_rows_total[q] > 0) w->phase_active[q] = (float)w->h_phase_rows[q] / (float)w->phase_rows_total[q];
+        w->phase_rows_pending = false;
+    }
+    const bool gate_probe = (w->ticks % 32) == 0;
+    const bool gate_collect = !w->phase_rows_pending && w->rowskip_mode == 2;  // one copy in flight at a time
+    if (gate_collect) {
+        CK(cudaMemsetAsync(w->d_phase_rows, 0, 16 * sizeof(unsigned int), w->stream));
+        w->phase_rows_counted = 0;
+    }
     for (int iter = 0; iter < a->cell_iter; iter++) {
         for (int tk = 0; tk < 4; tk++) {
             const int ofx = tk % 2;              // 0 1 0 1   (world.cpp:1059)
@@ -633,7 +658,11 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.chunk_cost = nullptr;
             P.chunk_state = nullptr;
             P.rowmask = nullptr;
-            if (w->rowskip_on && w->schedule == FSE_SCHEDULE_ROWS && !w->fused) {
+            P.phase_rows = nullptr;
+            const int ph = iter * 4 + tk;
+            bool skip_here = w->rowskip_mode == 1;
+            if (w->rowskip_mode == 2) skip_here = gate_probe || w->phase_active[ph] < 0.0f || w->phase_active[ph] < w->rowskip_max_active;
+            if (skip_here && w->schedule == FSE_SCHEDULE_ROWS && !w->fused) {
                 const int need = ((nx + 1) / 2) * ((ny + 1) / 2);
                 if (need > w->rowmask_cap) {
                     CK(cudaStreamSynchronize(w->stream));
@@ -644,6 +673,14 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                     w->rowmask_cap = need;
                 }
                 P.rowmask = w->d_rowmask;
+                if (gate_collect) {
+                    P.phase_rows = w->d_phase_rows + ph;
+                    w->phase_rows_counted |= 1u << ph;
+                    // rows the classification covers: the chunks of this colour this rank launches on the per-pass kernels
+                    long long chunks = (long long)((nx - ofx + 1) / 2) * ((ny - ofy + 1) / 2);
+                    if (w->strip) chunks = (long long)w->list_cnt[tk][0] + w->list_cnt[tk][1];
+                    w->phase_rows_total[ph] = chunks * CHUNK;
+                }
             }
             if (!w->strip) {
                 const int n_chunks = P.ncx * P.ncy;
@@ -706,7 +743,12 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                 w->ctx->launches += nl;
             }
             if (multi) {
-                if (int r = strip_exchange(w, ofy, j0, j1, z.y - w->y_off, w->comm_stream)) return r;
+                if (int r = strip_exchange(w, ofy, j0, j1, z.y - w->y_off, w->comm_stream)) {
+                    // the boundary kernels are already enqueued on the side stream: the next call must not race with them
+                    cudaEventRecord(w->ev_comm, w->comm_stream);
+                    cudaStreamWaitEvent(w->stream, w->ev_comm, 0);
+                    return r;
+                }
             }
             CK(cudaEventRecord(w->ev_comm, w->comm_stream));
             if (w->list_cnt[tk][1] > 0) {
@@ -747,6 +789,12 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             if (int r = kt.end(w->stream)) return r;
             CK(cudaStreamWaitEvent(w->stream, w->ev_comm, 0));
         }
+    }
+    if (gate_collect && w->phase_rows_counted) {
+        CK(cudaMemcpyAsync(w->h_phase_rows, w->d_phase_rows, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaEventRecord(w->ev_phase_rows, w->stream));
+        w->phase_rows_valid = w->phase_rows_counted;
+        w->phase_rows_pending = true;
     }
     w->ticks++;
     return FSE_OK;

@@ -6,8 +6,8 @@
 // row just ran owns the freshest copy of the rows around the cut and sends them to its neighbour:
 //     upper rank ran its last chunk row   -> sends rows [cut-5, cut+5)   down   (it can write 5 rows below the cut)
 //     lower rank ran its first chunk row  -> sends rows [cut-5, cut+10)  up     (the upper rank reads 10 rows below)
-// One direction per cut per phase, 7 planes each, grouped in one ncclGroup on a side stream; the boundary chunk rows are
-// launched first and the interior chunk rows overlap the transfer.  The schedule is the global one, so the result is
+// One direction per cut per phase, the seven planes packed into one message, both cuts in one ncclGroup on a side stream; the
+// boundary chunk rows are launched first and the interior chunk rows overlap the transfer.  The schedule is the global one, so the result is
 // bit-identical for any number of strips (tests/test_strips_*.py).
 //
 // NCCL is bound at run time (dlopen of the libnccl.so.2 already in the process, e.g. torch's) so the library has no
@@ -30,6 +30,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -49,6 +50,7 @@ static int load_nccl() {
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(Send, "ncclSend")
     SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -68,15 +70,90 @@ static int load_nccl() {
         if (e__ != cudaSuccess) return fail(FSE_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
     } while (0)
 
-// Send or receive local rows [y_lo, y_hi) of all seven planes to/from `peer` (inside an open ncclGroup).
-static int xfer_rows(fse_world* w, bool send, int peer, int y_lo, int y_hi, cudaStream_t s) {
-    ncclComm_t comm = (ncclComm_t)w->ctx->nccl_comm;
+// ---- packed halo messages --------------------------------------------------------------------------------------------------------
+// The rows [y_lo, y_hi) of the seven planes travel as ONE message per cut and direction: a pack kernel gathers them into a staging
+// buffer (plane after plane, 17 bytes per cell), one ncclSend / ncclRecv moves it, an unpack kernel scatters it on the other side.
+// Full-width rows are contiguous in every plane, so both kernels are straight 16-byte copies.
+struct PackArgs {
+    const unsigned char* src[7];
+    unsigned char* dst[7];
+    size_t bytes[7];  // per plane, multiples of 16 (W is a multiple of 128)
+};
+__global__ void halo_copy_kernel(const PackArgs a) {
+    const int pl = blockIdx.y;
+    const uint4* s = reinterpret_cast<const uint4*>(a.src[pl]);
+    uint4* d = reinterpret_cast<uint4*>(a.dst[pl]);
+    const size_t n = a.bytes[pl] / 16;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+static size_t halo_bytes(const fse_world* w, int rows) { return (size_t)rows * w->W * 17; }
+static void halo_args(fse_world* w, unsigned char* stage, int y_lo, int y_hi, bool pack, PackArgs* a) {
     const size_t off = (size_t)y_lo * w->W, cnt = (size_t)(y_hi - y_lo) * w->W;
     struct { void* base; size_t es; } pl[7] = {{w->p.mat, 1}, {w->p.flg, 1}, {w->p.stl, 1}, {w->p.tmp, 2}, {w->p.col, 4}, {w->p.fl, 4}, {w->p.fd, 4}};
+    size_t so = 0;
     for (int i = 0; i < 7; i++) {
-        char* ptr = (char*)pl[i].base + off * pl[i].es;
-        if (send) NK(g_nccl.Send(ptr, cnt * pl[i].es, ncclUint8_t_, peer, comm, s));
-        else NK(g_nccl.Recv(ptr, cnt * pl[i].es, ncclUint8_t_, peer, comm, s));
+        unsigned char* g = (unsigned char*)pl[i].base + off * pl[i].es;
+        a->src[i] = pack ? g : stage + so;
+        a->dst[i] = pack ? stage + so : g;
+        a->bytes[i] = cnt * pl[i].es;
+        so += cnt * pl[i].es;
+    }
+}
+
+// One side of a cut: what this rank sends and/or receives in one exchange (rows are local y coordinates; lo == hi: nothing)
+struct CutXfer {
+    int peer;
+    int send_lo, send_hi, recv_lo, recv_hi;
+    int slot;  // staging buffers 2 * slot (send), 2 * slot + 1 (recv)
+};
+
+static int ensure_stage(fse_world* w, int idx, size_t bytes) {
+    if (w->halo_stage_bytes[idx] >= bytes) return FSE_OK;
+    CK(cudaStreamSynchronize(w->comm_stream));
+    CK(cudaStreamSynchronize(w->stream));
+    cudaFree(w->halo_stage[idx]);
+    w->halo_stage[idx] = nullptr;
+    w->halo_stage_bytes[idx] = 0;
+    CK(cudaMalloc(&w->halo_stage[idx], bytes));
+    w->halo_stage_bytes[idx] = bytes;
+    return FSE_OK;
+}
+
+// pack -> one grouped send/recv per cut -> unpack, all on stream s.  The NCCL group is closed on every path.
+static int exchange_cuts(fse_world* w, const CutXfer* cuts, int n_cuts, cudaStream_t s) {
+    ncclComm_t comm = (ncclComm_t)w->ctx->nccl_comm;
+    for (int i = 0; i < n_cuts; i++) {
+        const CutXfer& c = cuts[i];
+        if (c.send_hi > c.send_lo) {
+            if (int r = ensure_stage(w, 2 * c.slot, halo_bytes(w, c.send_hi - c.send_lo))) return r;
+            PackArgs a;
+            halo_args(w, (unsigned char*)w->halo_stage[2 * c.slot], c.send_lo, c.send_hi, true, &a);
+            halo_copy_kernel<<<dim3(64, 7), 256, 0, s>>>(a);
+            CK(cudaGetLastError());
+            w->ctx->launches += 1;
+        }
+        if (c.recv_hi > c.recv_lo)
+            if (int r = ensure_stage(w, 2 * c.slot + 1, halo_bytes(w, c.recv_hi - c.recv_lo))) return r;
+    }
+    NK(g_nccl.GroupStart());
+    ncclResult_t bad = 0;
+    for (int i = 0; i < n_cuts && !bad; i++) {
+        const CutXfer& c = cuts[i];
+        if (c.send_hi > c.send_lo) bad = g_nccl.Send(w->halo_stage[2 * c.slot], halo_bytes(w, c.send_hi - c.send_lo), ncclUint8_t_, c.peer, comm, s);
+        if (!bad && c.recv_hi > c.recv_lo) bad = g_nccl.Recv(w->halo_stage[2 * c.slot + 1], halo_bytes(w, c.recv_hi - c.recv_lo), ncclUint8_t_, c.peer, comm, s);
+    }
+    const ncclResult_t end = g_nccl.GroupEnd();  // always: an open group would swallow every later NCCL call of this thread
+    if (bad) return fail(FSE_ENCCL, "ncclSend/ncclRecv: %s", g_nccl.GetErrorString(bad));
+    if (end) return fail(FSE_ENCCL, "ncclGroupEnd: %s", g_nccl.GetErrorString(end));
+    for (int i = 0; i < n_cuts; i++) {
+        const CutXfer& c = cuts[i];
+        if (c.recv_hi > c.recv_lo) {
+            PackArgs a;
+            halo_args(w, (unsigned char*)w->halo_stage[2 * c.slot + 1], c.recv_lo, c.recv_hi, false, &a);
+            halo_copy_kernel<<<dim3(64, 7), 256, 0, s>>>(a);
+            CK(cudaGetLastError());
+            w->ctx->launches += 1;
+        }
     }
     return FSE_OK;
 }
@@ -87,40 +164,60 @@ int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cuda
     fse_ctx* c = w->ctx;
     const bool up = c->rank > 0, down = c->rank + 1 < c->nranks;
     if (!up && !down) return FSE_OK;
-    NK(g_nccl.GroupStart());
+    CutXfer cuts[2];
+    int n = 0;
     if (up) {  // cut above my first owned chunk row j0; the rank above owns j0-1
         const int cut = zone_y_local + j0 * CHUNK;
         const bool mine_ran = (j0 % 2) == ofy;
-        if (mine_ran) { if (int r = xfer_rows(w, true, c->rank - 1, cut - 5, cut + 10, s)) return r; }
-        else          { if (int r = xfer_rows(w, false, c->rank - 1, cut - 5, cut + 5, s)) return r; }
+        cuts[n++] = mine_ran ? CutXfer{c->rank - 1, cut - 5, cut + 10, 0, 0, 0} : CutXfer{c->rank - 1, 0, 0, cut - 5, cut + 5, 0};
     }
     if (down) {  // cut below my last owned chunk row j1-1; the rank below owns j1
         const int cut = zone_y_local + j1 * CHUNK;
         const bool mine_ran = ((j1 - 1) % 2) == ofy;
-        if (mine_ran) { if (int r = xfer_rows(w, true, c->rank + 1, cut - 5, cut + 5, s)) return r; }
-        else          { if (int r = xfer_rows(w, false, c->rank + 1, cut - 5, cut + 10, s)) return r; }
+        cuts[n++] = mine_ran ? CutXfer{c->rank + 1, cut - 5, cut + 5, 0, 0, 1} : CutXfer{c->rank + 1, 0, 0, cut - 5, cut + 10, 1};
     }
-    NK(g_nccl.GroupEnd());
-    return FSE_OK;
+    return exchange_cuts(w, cuts, n, s);
 }
 
-// Owner-authoritative refresh: every rank sends the 16 owned rows next to each cut and receives its neighbour's.
-int strip_refresh(fse_world* w, cudaStream_t s) {
+// Owner-authoritative refresh: every rank sends the R owned rows next to each cut and receives its neighbour's (R <= ghost rows).
+int strip_refresh(fse_world* w, cudaStream_t s, int R) {
     fse_ctx* c = w->ctx;
     if (c->nranks == 1) return FSE_OK;
-    const int R = 16;
-    NK(g_nccl.GroupStart());
+    CutXfer cuts[2];
+    int n = 0;
     if (c->rank > 0) {
         const int cut = w->own_lo - w->y_off;
-        if (int r = xfer_rows(w, true, c->rank - 1, cut, cut + R, s)) return r;
-        if (int r = xfer_rows(w, false, c->rank - 1, cut - R, cut, s)) return r;
+        cuts[n++] = CutXfer{c->rank - 1, cut, cut + R, cut - R, cut, 0};
     }
     if (c->rank + 1 < c->nranks) {
         const int cut = w->own_hi - w->y_off;
-        if (int r = xfer_rows(w, true, c->rank + 1, cut - R, cut, s)) return r;
-        if (int r = xfer_rows(w, false, c->rank + 1, cut, cut + R, s)) return r;
+        cuts[n++] = CutXfer{c->rank + 1, cut - R, cut, cut, cut + R, 1};
     }
-    NK(g_nccl.GroupEnd());
+    return exchange_cuts(w, cuts, n, s);
+}
+
+// Generic neighbour exchange on stream s: up to one send and one receive with each neighbour (null / 0 bytes: none), one ncclGroup.
+int strip_sendrecv(fse_world* w, const void* up_send, size_t up_send_bytes, void* up_recv, size_t up_recv_bytes, const void* down_send,
+                   size_t down_send_bytes, void* down_recv, size_t down_recv_bytes, cudaStream_t s) {
+    fse_ctx* c = w->ctx;
+    ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+    const bool up = c->rank > 0, down = c->rank + 1 < c->nranks;
+    NK(g_nccl.GroupStart());
+    ncclResult_t bad = 0;
+    if (up && up_send_bytes && !bad) bad = g_nccl.Send(up_send, up_send_bytes, ncclUint8_t_, c->rank - 1, comm, s);
+    if (up && up_recv_bytes && !bad) bad = g_nccl.Recv(up_recv, up_recv_bytes, ncclUint8_t_, c->rank - 1, comm, s);
+    if (down && down_send_bytes && !bad) bad = g_nccl.Send(down_send, down_send_bytes, ncclUint8_t_, c->rank + 1, comm, s);
+    if (down && down_recv_bytes && !bad) bad = g_nccl.Recv(down_recv, down_recv_bytes, ncclUint8_t_, c->rank + 1, comm, s);
+    const ncclResult_t end = g_nccl.GroupEnd();
+    if (bad) return fail(FSE_ENCCL, "ncclSend/ncclRecv: %s", g_nccl.GetErrorString(bad));
+    if (end) return fail(FSE_ENCCL, "ncclGroupEnd: %s", g_nccl.GetErrorString(end));
+    return FSE_OK;
+}
+
+// In-place sum of `count` 32-bit unsigned integers over all ranks.
+int strip_allreduce_u32(fse_world* w, unsigned int* dev, size_t count, cudaStream_t s) {
+    ncclComm_t comm = (ncclComm_t)w->ctx->nccl_comm;
+    NK(g_nccl.AllReduce(dev, dev, count, /*ncclUint32*/ 3, /*ncclSum*/ 0, comm, s));
     return FSE_OK;
 }
 

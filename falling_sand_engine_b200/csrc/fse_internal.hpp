@@ -51,6 +51,7 @@ struct fse_world {
     size_t part_list_bytes = 0;
     fse_particle* pbuf2 = nullptr;  // compaction target, swapped with pbuf every fse_particles_tick
     size_t pbuf2_bytes = 0;
+    void* particle_strip = nullptr;  // strips: exchange buffers of the particle protocol (fse_particles.cu StripBufs)
     void* claim_keys = nullptr;
     size_t claim_keys_bytes = 0;
     void* claim_vals = nullptr;
@@ -73,11 +74,27 @@ struct fse_world {
     // settled-row skipping of the per-pass kernels (classify_rows_kernel): ROWMASK_WORDS words per chunk of a colour's grid
     uint32_t* d_rowmask = nullptr;
     int rowmask_cap = 0;
-    bool rowskip_on = true;  // FSE_ROW_SKIP=0 steps every row (A/B measurements)
+    int rowskip_mode = 2;    // FSE_ROW_SKIP: 0 = step every row, 1 = always skip settled rows, 2 (default) = per phase, by the gate below
+    // Skip gate.  A phase is bound by the row chain of its busiest chunk, so skipping settled rows only pays when most rows are
+    // settled; below that the classification costs more than it saves.  Each classified phase counts its active rows on the device;
+    // the counts come back asynchronously (pinned memory + event, never a sync) and a phase uses the skip while less than
+    // rowskip_max_active of its rows were active the last time it was classified.  Every 32nd tick classifies all phases again.
+    unsigned int* d_phase_rows = nullptr;   // 16 counters (4 colours x cell_iter <= 4)
+    unsigned int* h_phase_rows = nullptr;   // pinned copy of the last finished tick
+    cudaEvent_t ev_phase_rows = nullptr;
+    bool phase_rows_pending = false;
+    uint32_t phase_rows_valid = 0;          // bit p: h_phase_rows[p] was counted in the tick that was copied
+    uint32_t phase_rows_counted = 0;        // bit p: phase p is being classified in the tick in flight
+    float phase_active[16];                 // last known active fraction per phase, < 0 = unknown
+    long long phase_rows_total[16];
+    float rowskip_max_active = 0.25f;       // FSE_ROW_SKIP_MAX_ACTIVE
     // particle pool bookkeeping on the host: count seen by the last call that read it, particles promised to calls since, drops
     unsigned int particles_seen = 0;
     int64_t particles_promised = 0;
     uint64_t particles_dropped = 0;
+    // strips: staging buffers of the packed halo messages (fse_comm.cu): [2 * cut] send, [2 * cut + 1] receive
+    void* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t halo_stage_bytes[4] = {0, 0, 0, 0};
     // rigid-body bridge (fse_bodies.cu) and outline scratch (fse_outline.cu)
     struct fse_bodies* bodies = nullptr;
     int last_bridge_rounds = 0;
@@ -118,7 +135,11 @@ int fse_wake_rect(fse_world* w, int x, int y_local, int rw, int rh);  // wake th
 
 int particles_headroom(fse_world* w, int64_t need, bool exact);  // grow the particle pool before a call that spawns up to `need`
 int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cudaStream_t s);
-int strip_refresh(fse_world* w, cudaStream_t s);
+void particles_strip_free(fse_world* w);
+int strip_refresh(fse_world* w, cudaStream_t s, int rows = 16);
+int strip_sendrecv(fse_world* w, const void* up_send, size_t up_send_bytes, void* up_recv, size_t up_recv_bytes, const void* down_send,
+                   size_t down_send_bytes, void* down_recv, size_t down_recv_bytes, cudaStream_t s);
+int strip_allreduce_u32(fse_world* w, unsigned int* dev, size_t count, cudaStream_t s);
 size_t tick_smem_bytes();
 cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream, const int* members = nullptr);
 cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched, const TickFork* fork);  // *launched = kernels enqueued

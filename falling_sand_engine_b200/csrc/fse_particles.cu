@@ -22,10 +22,21 @@ struct PState {
     unsigned char merge;
 };
 
+// proposal of a particle for a cell in the band around a strip cut, as it travels to the neighbour rank
+struct PProp {
+    long long cell;          // x + y * W in global coordinates
+    unsigned long long id;
+    fse_cell tile;
+    int merge;
+};
+static_assert(sizeof(PProp) == 40, "PProp travels over NCCL as raw bytes");
+
 struct PArgs {
     Planes p;
     const DevTables* T;
-    int W, H;
+    int W, H;        // H = height of the whole world (global rows)
+    int y_off, Hl;   // the planes hold global rows [y_off, y_off + Hl) (strip worlds; plain worlds: 0, H)
+    unsigned int* oob;  // counts grid probes outside the held rows (a particle faster than the ghost band; strips only)
     int zx, zy, zw, zh;
     fse_particle* pbuf;
     PState* st;
@@ -40,9 +51,38 @@ struct PArgs {
     unsigned int n_list;   // entries of list the deposit rounds run over
     const unsigned int* prev_pending;  // particles still pending after the previous round (null in round 0): 0 = nothing left to do
     unsigned int* my_pending;          // this round's count
+    // strips (null / 0 on plain worlds)
+    unsigned int* n_props;             // proposals made this round
+    PProp *band_up, *band_down;        // proposals for the band of `ghost` rows on either side of the cut above / below
+    unsigned int* band_cnt;            // [0] up, [1] down
+    int own_lo, own_hi, ghost;         // owned global rows
 };
 
-__device__ __forceinline__ int phys_at(const PArgs& a, int x, int y) { return a.T->phys[a.p.mat[(size_t)y * a.W + x]]; }
+// strips: every particle to the rank that owns its row (world.cpp has one list; here ownership follows int(y))
+__global__ void particles_partition_kernel(const fse_particle* in, unsigned int n, int own_lo, int own_hi, int has_up, int has_down,
+                                           fse_particle* keep, fse_particle* up, fse_particle* down, unsigned int* cnt) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fse_particle p = in[i];
+    const long long row = (long long)floorf(p.y);
+    if (has_up && row < own_lo) up[atomicAdd(&cnt[1], 1u)] = p;
+    else if (has_down && row >= own_hi) down[atomicAdd(&cnt[2], 1u)] = p;
+    else keep[atomicAdd(&cnt[0], 1u)] = p;
+}
+
+// cell index in the local planes of global cell (x, y), or -1 when this rank does not hold the row
+__device__ __forceinline__ long long local_cell(const PArgs& a, int x, int y) {
+    const int r = y - a.y_off;
+    if (r < 0 || r >= a.Hl) {
+        if (a.oob) atomicAdd(a.oob, 1u);
+        return -1;
+    }
+    return (long long)r * a.W + x;
+}
+__device__ __forceinline__ int phys_at(const PArgs& a, int x, int y) {
+    const long long g = local_cell(a, x, y);
+    return g < 0 ? (int)P_SOLID : (int)a.T->phys[a.p.mat[g]];
+}
 
 __global__ void particles_integrate_kernel(PArgs a) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,6 +148,33 @@ __device__ __forceinline__ unsigned int hash_cell(long long c) {
     return (unsigned int)(z >> 32);
 }
 
+// claim: lowest id per cell (open addressing, keys = global cell index)
+__device__ __forceinline__ void claim_cell(const PArgs& a, long long cand, unsigned long long id) {
+    unsigned int h = hash_cell(cand) & a.tmask;
+    for (;;) {
+        long long prev = (long long)atomicCAS((unsigned long long*)&a.keys[h], (unsigned long long)-1LL, (unsigned long long)cand);
+        if (prev == -1LL || prev == cand) {
+            atomicMin(&a.vals[h], id);
+            break;
+        }
+        h = (h + 1) & a.tmask;
+    }
+}
+__device__ __forceinline__ void deposit_cell(const PArgs& a, size_t g, const fse_cell& t, int merge) {
+    if (merge) {
+        a.p.fl[g] += t.fluid;  // 2133
+        a.p.flg[g] |= F_DIRTY;
+    } else {  // real_tiles[...] = cur->tile (2127 / 2160)
+        a.p.mat[g] = (uint8_t)t.mat;
+        a.p.flg[g] = (uint8_t)((t.moved ? F_MOVED : 0) | F_DIRTY);
+        a.p.stl[g] = t.settle;
+        a.p.tmp[g] = t.temp;
+        a.p.col[g] = t.color;
+        a.p.fl[g] = t.fluid;
+        a.p.fd[g] = t.fluid_diff;
+    }
+}
+
 __global__ void particles_propose_kernel(PArgs a) {
     const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= a.n_list || (a.prev_pending && *a.prev_pending == 0)) return;
@@ -130,9 +197,12 @@ __global__ void particles_propose_kernel(PArgs a) {
             if (-16 <= sx && sx <= 16 && -16 <= sy && sy <= 16) {
                 const int px = (int)(cx + sx), py = (int)(cy + sy);
                 if (px >= 0 && py >= 0 && px < W && py < H) {
-                    const int m = a.p.mat[(size_t)py * W + px];
-                    if (a.T->phys[m] == P_AIR) { cand = px + (long long)py * W; break; }
-                    if (amSoup && m == myMat) { cand = px + (long long)py * W; merge = 1; break; }
+                    const long long g = local_cell(a, px, py);
+                    if (g >= 0) {
+                        const int m = a.p.mat[g];
+                        if (a.T->phys[m] == P_AIR) { cand = px + (long long)py * W; break; }
+                        if (amSoup && m == myMat) { cand = px + (long long)py * W; merge = 1; break; }
+                    }
                 }
             }
             if ((sx == sy) || ((sx < 0) && (sx == -sy)) || ((sx > 0) && (sx == 1 - sy))) {
@@ -156,16 +226,37 @@ __global__ void particles_propose_kernel(PArgs a) {
     sp->status = (unsigned char)status;
     sp->cand = cand;
     sp->merge = (unsigned char)merge;
-    // claim: lowest id per cell
-    unsigned int h = hash_cell(cand) & a.tmask;
-    for (;;) {
-        long long prev = (long long)atomicCAS((unsigned long long*)&a.keys[h], (unsigned long long)-1LL, (unsigned long long)cand);
-        if (prev == -1LL || prev == cand) {
-            atomicMin(&a.vals[h], (unsigned long long)sp->adv.id);
-            break;
-        }
-        h = (h + 1) & a.tmask;
+    claim_cell(a, cand, sp->adv.id);
+    if (a.n_props) atomicAdd(a.n_props, 1u);
+    // strips: a proposal for the band around a cut also goes to the neighbour (both ranks pick the same winner)
+    if (a.band_up || a.band_down) {
+        const int row = (int)(cand / a.W);
+        PProp pr;
+        pr.cell = cand;
+        pr.id = sp->adv.id;
+        pr.tile = sp->adv.tile;
+        pr.merge = merge;
+        if (a.band_up && row >= a.own_lo - a.ghost && row < a.own_lo + a.ghost) a.band_up[atomicAdd(&a.band_cnt[0], 1u)] = pr;
+        if (a.band_down && row >= a.own_hi - a.ghost && row < a.own_hi + a.ghost) a.band_down[atomicAdd(&a.band_cnt[1], 1u)] = pr;
     }
+}
+
+// strips: the neighbours' band proposals join the claim table ...
+__global__ void particles_ext_claim_kernel(PArgs a, const PProp* ext, unsigned int n) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) claim_cell(a, ext[i].cell, ext[i].id);
+}
+// ... and the ones that won are written into the rows this rank holds (the owner of the particle writes its own copy)
+__global__ void particles_ext_commit_kernel(PArgs a, const PProp* ext, unsigned int n) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PProp pr = ext[i];
+    unsigned int h = hash_cell(pr.cell) & a.tmask;
+    while (a.keys[h] != pr.cell) h = (h + 1) & a.tmask;
+    if (a.vals[h] != pr.id) return;
+    const int r = (int)(pr.cell / a.W) - a.y_off;
+    if (r < 0 || r >= a.Hl) return;
+    deposit_cell(a, (size_t)r * a.W + (size_t)(pr.cell % a.W), pr.tile, pr.merge);
 }
 
 __global__ void particles_commit_kernel(PArgs a) {
@@ -180,19 +271,9 @@ __global__ void particles_commit_kernel(PArgs a) {
         atomicAdd(a.my_pending, 1u);  // still pending
         return;
     }
-    const size_t g = (size_t)cand;
-    const fse_cell t = sp->adv.tile;
-    if (sp->merge) {
-        a.p.fl[g] += t.fluid;  // 2133
-        a.p.flg[g] |= F_DIRTY;
-    } else {  // real_tiles[...] = cur->tile (2127 / 2160)
-        a.p.mat[g] = (uint8_t)t.mat;
-        a.p.flg[g] = (uint8_t)((t.moved ? F_MOVED : 0) | F_DIRTY);
-        a.p.stl[g] = t.settle;
-        a.p.tmp[g] = t.temp;
-        a.p.col[g] = t.color;
-        a.p.fl[g] = t.fluid;
-        a.p.fd[g] = t.fluid_diff;
+    {
+        const int r = (int)(cand / a.W) - a.y_off;  // a winner outside the held rows is written by the neighbour that holds the cell
+        if (r >= 0 && r < a.Hl) deposit_cell(a, (size_t)r * a.W + (size_t)(cand % a.W), sp->adv.tile, sp->merge);
     }
     if (a.awake) {  // a deposit can un-settle the cells around it: wake the 3x3 chunks
         const int ci = (int)(cand % a.W) / CHUNK, cj = (int)(cand / a.W) / CHUNK;
@@ -237,11 +318,232 @@ using namespace fse;
         if (e__ != cudaSuccess) return fail(FSE_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
     } while (0)
 
+// ---- strips: the protocol of DESIGN.md §5 (validated on the host by tests/test_strips_cpu.py with the oracle's staged schedule) ----
+// 1. ghost rows fresh (32 rows either side of a cut), every particle to the rank that owns its row;
+// 2. each rank integrates its particles against its rows + ghost rows;
+// 3. per deposit round: proposals for the band of 32 rows on either side of a cut travel to that neighbour, both ranks put
+//    them into their claim tables (the lowest id wins whoever owns the particle) and both write the winners' cells they hold;
+// 4. rounds stop when no rank proposed anything (one all-reduce per round).
+// Variable-length arrays travel as two grouped exchanges: the counts, then the payload.
+struct StripBufs {
+    unsigned int* d_cnt = nullptr;   // [0..2] partition keep/up/down, [3..4] band up/down, [5..6] received up/down, [7] proposals, [8] oob
+    unsigned int* h_cnt = nullptr;   // pinned mirror
+    void* send[2] = {nullptr, nullptr};
+    void* recv[2] = {nullptr, nullptr};
+    size_t send_bytes[2] = {0, 0}, recv_bytes[2] = {0, 0};
+};
+static StripBufs* strip_bufs(fse_world* w) {
+    if (!w->particle_strip) {
+        StripBufs* b = new StripBufs();
+        if (cudaMalloc((void**)&b->d_cnt, 16 * sizeof(unsigned int)) != cudaSuccess || cudaMallocHost((void**)&b->h_cnt, 16 * sizeof(unsigned int)) != cudaSuccess) {
+            delete b;
+            return nullptr;
+        }
+        w->particle_strip = b;
+    }
+    return (StripBufs*)w->particle_strip;
+}
+void fse::particles_strip_free(fse_world* w) {
+    StripBufs* b = (StripBufs*)w->particle_strip;
+    if (!b) return;
+    cudaFree(b->d_cnt);
+    cudaFreeHost(b->h_cnt);
+    for (int q = 0; q < 2; q++) {
+        cudaFree(b->send[q]);
+        cudaFree(b->recv[q]);
+    }
+    delete b;
+    w->particle_strip = nullptr;
+}
+
+// send n_up / n_down records of `es` bytes to the neighbours, receive theirs; counts first.  *got_up / *got_down = records received
+// (in b->recv[0] / b->recv[1]).  One host sync for the counts.
+static int exchange_records(fse_world* w, StripBufs* b, const void* up, unsigned int n_up, const void* down, unsigned int n_down, size_t es,
+                            unsigned int* got_up, unsigned int* got_down) {
+    const bool has_up = w->ctx->rank > 0, has_down = w->ctx->rank + 1 < w->ctx->nranks;
+    unsigned int* c = b->d_cnt;
+    b->h_cnt[9] = n_up;
+    b->h_cnt[10] = n_down;
+    CK(cudaMemcpyAsync(c + 9, b->h_cnt + 9, 2 * sizeof(unsigned int), cudaMemcpyHostToDevice, w->stream));
+    CK(cudaMemsetAsync(c + 5, 0, 2 * sizeof(unsigned int), w->stream));
+    if (int r = strip_sendrecv(w, c + 9, has_up ? 4 : 0, c + 5, has_up ? 4 : 0, c + 10, has_down ? 4 : 0, c + 6, has_down ? 4 : 0, w->stream)) return r;
+    CK(cudaMemcpyAsync(b->h_cnt + 5, c + 5, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    const unsigned int in_up = has_up ? b->h_cnt[5] : 0, in_down = has_down ? b->h_cnt[6] : 0;
+    CK(grow(&b->recv[0], &b->recv_bytes[0], (size_t)in_up * es + 64));
+    CK(grow(&b->recv[1], &b->recv_bytes[1], (size_t)in_down * es + 64));
+    if (int r = strip_sendrecv(w, up, has_up ? (size_t)n_up * es : 0, b->recv[0], (size_t)in_up * es, down, has_down ? (size_t)n_down * es : 0, b->recv[1],
+                               (size_t)in_down * es, w->stream))
+        return r;
+    *got_up = in_up;
+    *got_down = in_down;
+    return FSE_OK;
+}
+
+static int particles_tick_strips(fse_world* w, const fse_rect* z) {
+    StripBufs* b = strip_bufs(w);
+    if (!b) return fail(FSE_ENOMEM, "fse_particles_tick: strip buffers");
+    const bool has_up = w->ctx->rank > 0, has_down = w->ctx->rank + 1 < w->ctx->nranks;
+    const int GH = 32;  // ghost rows a strip holds beyond the rows it owns (strips.GHOST)
+    const int B = 128;
+    // 1a. ghost rows: the owner's rows next to each cut
+    if (int r = strip_refresh(w, w->stream, GH)) return r;
+    // 1b. every particle to the rank that owns its row
+    int64_t n64 = 0;
+    if (int r = fse_particles_count(w, &n64)) return r;
+    w->particles_promised = 0;
+    unsigned int n = (unsigned int)n64;
+    CK(grow((void**)&w->pbuf2, &w->pbuf2_bytes, sizeof(fse_particle) * (size_t)w->pcap));
+    CK(grow(&b->send[0], &b->send_bytes[0], sizeof(fse_particle) * (size_t)n + 64));
+    CK(grow(&b->send[1], &b->send_bytes[1], sizeof(fse_particle) * (size_t)n + 64));
+    CK(cudaMemsetAsync(b->d_cnt, 0, 16 * sizeof(unsigned int), w->stream));
+    if (n) {
+        particles_partition_kernel<<<(n + B - 1) / B, B, 0, w->stream>>>(w->pbuf, n, w->own_lo, w->own_hi, has_up, has_down, w->pbuf2, (fse_particle*)b->send[0],
+                                                                     (fse_particle*)b->send[1], b->d_cnt);
+        CK(cudaGetLastError());
+        w->ctx->launches += 1;
+    }
+    CK(cudaMemcpyAsync(b->h_cnt, b->d_cnt, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    const unsigned int n_keep = b->h_cnt[0], go_up = b->h_cnt[1], go_down = b->h_cnt[2];
+    unsigned int in_up = 0, in_down = 0;
+    if (int r = exchange_records(w, b, b->send[0], go_up, b->send[1], go_down, sizeof(fse_particle), &in_up, &in_down)) return r;
+    const size_t total = (size_t)n_keep + in_up + in_down;
+    if (total > w->pcap) {  // arrivals do not fit: grow both pools (pbuf2 holds the kept particles, pbuf is free to go)
+        CK(cudaStreamSynchronize(w->stream));
+        size_t cap = (size_t)w->pcap * 2;
+        while (cap < total) cap *= 2;
+        fse_particle* nb = nullptr;
+        CK(cudaMalloc(&nb, sizeof(fse_particle) * cap));
+        if (n_keep) CK(cudaMemcpy(nb, w->pbuf2, sizeof(fse_particle) * (size_t)n_keep, cudaMemcpyDeviceToDevice));
+        cudaFree(w->pbuf);
+        cudaFree(w->pbuf2);
+        w->pbuf = nullptr;
+        w->pbuf2 = nb;
+        w->pbuf2_bytes = sizeof(fse_particle) * cap;
+        CK(cudaMalloc(&w->pbuf, sizeof(fse_particle) * cap));
+        w->pcap = (unsigned int)cap;
+    }
+    if (in_up) CK(cudaMemcpyAsync(w->pbuf2 + n_keep, b->recv[0], sizeof(fse_particle) * (size_t)in_up, cudaMemcpyDeviceToDevice, w->stream));
+    if (in_down) CK(cudaMemcpyAsync(w->pbuf2 + n_keep + in_up, b->recv[1], sizeof(fse_particle) * (size_t)in_down, cudaMemcpyDeviceToDevice, w->stream));
+    {   // the partitioned pool becomes the live one
+        fse_particle* t = w->pbuf;
+        w->pbuf = w->pbuf2;
+        w->pbuf2 = t;
+        w->pbuf2_bytes = sizeof(fse_particle) * (size_t)w->pcap;
+    }
+    n = (unsigned int)total;
+    // 2. integrate (global coordinates; the planes hold rows [y_off, y_off + H))
+    CK(grow(&w->part_scratch, &w->part_scratch_bytes, sizeof(PState) * ((size_t)n + 1)));
+    CK(grow((void**)&w->part_list, &w->part_list_bytes, sizeof(unsigned int) * ((size_t)n + 32)));
+    PArgs a;
+    memset(&a, 0, sizeof a);
+    a.p = w->p;
+    a.T = w->ctx->d_tabs;
+    a.W = w->W; a.H = w->Hglobal;
+    a.y_off = w->y_off; a.Hl = w->H;
+    a.oob = b->d_cnt + 8;
+    a.zx = z->x; a.zy = z->y; a.zw = z->w; a.zh = z->h;
+    a.pbuf = w->pbuf;
+    a.st = (PState*)w->part_scratch;
+    a.n = n;
+    a.counters = w->pcount;
+    a.list = (unsigned int*)w->part_list;
+    a.own_lo = w->own_lo; a.own_hi = w->own_hi; a.ghost = GH;
+    const int G = (int)((n + B - 1) / B);
+    CK(cudaMemsetAsync(w->pcount + 1, 0, 2 * sizeof(unsigned int), w->stream));
+    if (n) {
+        particles_integrate_kernel<<<G, B, 0, w->stream>>>(a);
+        CK(cudaGetLastError());
+        w->ctx->launches += 1;
+    }
+    unsigned int pending = 0;
+    CK(cudaMemcpyAsync(&pending, w->pcount + 1, sizeof pending, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    a.n_list = pending;
+    const int GL = (int)((pending + B - 1) / B);
+    // band buffers: at most every pending particle proposes into a band
+    CK(grow(&b->send[0], &b->send_bytes[0], sizeof(PProp) * (size_t)pending + 64));
+    CK(grow(&b->send[1], &b->send_bytes[1], sizeof(PProp) * (size_t)pending + 64));
+    a.band_up = has_up ? (PProp*)b->send[0] : nullptr;
+    a.band_down = has_down ? (PProp*)b->send[1] : nullptr;
+    a.band_cnt = b->d_cnt + 3;
+    a.n_props = b->d_cnt + 7;
+    unsigned int* round_cnt = (unsigned int*)w->part_list + n;
+    CK(cudaMemsetAsync(round_cnt, 0, 32 * sizeof(unsigned int), w->stream));
+    // 3. deposit rounds
+    for (int round = 0; round < FSE_PARTICLE_ROUNDS; round++) {
+        size_t tsz = 1024;
+        while (tsz < ((size_t)pending + 4096) * 2) tsz <<= 1;
+        CK(grow((void**)&w->claim_keys, &w->claim_keys_bytes, tsz * sizeof(long long)));
+        CK(grow((void**)&w->claim_vals, &w->claim_vals_bytes, tsz * sizeof(unsigned long long)));
+        a.keys = (long long*)w->claim_keys;
+        a.vals = (unsigned long long*)w->claim_vals;
+        a.tmask = (unsigned int)(tsz - 1);
+        CK(cudaMemsetAsync(w->claim_keys, 0xff, tsz * sizeof(long long), w->stream));
+        CK(cudaMemsetAsync(w->claim_vals, 0xff, tsz * sizeof(unsigned long long), w->stream));
+        CK(cudaMemsetAsync(b->d_cnt + 3, 0, 2 * sizeof(unsigned int), w->stream));
+        CK(cudaMemsetAsync(b->d_cnt + 7, 0, sizeof(unsigned int), w->stream));
+        a.prev_pending = round ? round_cnt + round - 1 : nullptr;
+        a.my_pending = round_cnt + round;
+        if (pending) {
+            particles_propose_kernel<<<GL, B, 0, w->stream>>>(a);
+            CK(cudaGetLastError());
+            w->ctx->launches += 1;
+        }
+        // anything proposed anywhere?  (also tells every rank when to stop)
+        CK(cudaMemcpyAsync(b->d_cnt + 11, b->d_cnt + 7, sizeof(unsigned int), cudaMemcpyDeviceToDevice, w->stream));
+        if (int r = strip_allreduce_u32(w, b->d_cnt + 11, 1, w->stream)) return r;
+        CK(cudaMemcpyAsync(b->h_cnt + 3, b->d_cnt + 3, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaMemcpyAsync(b->h_cnt + 11, b->d_cnt + 11, sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaStreamSynchronize(w->stream));
+        if (b->h_cnt[11] == 0) break;
+        unsigned int ext_up = 0, ext_down = 0;
+        if (int r = exchange_records(w, b, b->send[0], has_up ? b->h_cnt[3] : 0, b->send[1], has_down ? b->h_cnt[4] : 0, sizeof(PProp), &ext_up, &ext_down)) return r;
+        if ((size_t)pending + ext_up + ext_down > tsz / 2)
+            return fail(FSE_ESTATE, "fse_particles_tick: %u + %u band proposals from the neighbours overflow the claim table", ext_up, ext_down);
+        for (int side = 0; side < 2; side++) {
+            const unsigned int ne = side ? ext_down : ext_up;
+            if (!ne) continue;
+            particles_ext_claim_kernel<<<(ne + B - 1) / B, B, 0, w->stream>>>(a, (const PProp*)b->recv[side], ne);
+            CK(cudaGetLastError());
+            w->ctx->launches += 1;
+        }
+        if (pending) {
+            particles_commit_kernel<<<GL, B, 0, w->stream>>>(a);
+            CK(cudaGetLastError());
+            w->ctx->launches += 1;
+        }
+        for (int side = 0; side < 2; side++) {
+            const unsigned int ne = side ? ext_down : ext_up;
+            if (!ne) continue;
+            particles_ext_commit_kernel<<<(ne + B - 1) / B, B, 0, w->stream>>>(a, (const PProp*)b->recv[side], ne);
+            CK(cudaGetLastError());
+            w->ctx->launches += 1;
+        }
+    }
+    // 4. survivors (they change owner at the start of the next call if their row now belongs to a neighbour)
+    if (n) {
+        particles_compact_kernel<<<G, B, 0, w->stream>>>(a, w->pbuf2);
+        CK(cudaGetLastError());
+        w->ctx->launches += 1;
+    }
+    CK(cudaMemcpyAsync(w->pcount, w->pcount + 2, sizeof(unsigned int), cudaMemcpyDeviceToDevice, w->stream));
+    CK(cudaMemcpyAsync(b->h_cnt + 8, b->d_cnt + 8, sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+    fse_particle* t = w->pbuf;
+    w->pbuf = w->pbuf2;
+    w->pbuf2 = t;
+    w->pbuf2_bytes = sizeof(fse_particle) * (size_t)w->pcap;
+    CK(cudaStreamSynchronize(w->stream));
+    w->particles_seen = n;
+    if (b->h_cnt[8]) return fail(FSE_ESTATE, "fse_particles_tick: %u grid probes left the %d ghost rows of the strip (a particle faster than the halo band)", b->h_cnt[8], GH);
+    return FSE_OK;
+}
+
 extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     if (!w || !z) return fail(FSE_EINVAL, "fse_particles_tick: null argument");
-    if (w->strip && w->ctx->nranks > 1)
-        return fail(FSE_ESTATE, "fse_particles_tick: particle migration between strips is not implemented yet (single-GPU worlds only)");
     CK(cudaSetDevice(w->ctx->device));
+    if (w->strip && w->ctx->nranks > 1) return particles_tick_strips(w, z);
     unsigned int n = 0;
     {
         int64_t n64 = 0;
@@ -254,9 +556,11 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     CK(grow((void**)&w->pbuf2, &w->pbuf2_bytes, sizeof(fse_particle) * (size_t)w->pcap));
     CK(grow((void**)&w->part_list, &w->part_list_bytes, sizeof(unsigned int) * ((size_t)n + 32)));  // + one pending counter per round
     PArgs a;
+    memset(&a, 0, sizeof a);
     a.p = w->p;
     a.T = w->ctx->d_tabs;
-    a.W = w->W; a.H = w->H;
+    a.W = w->W; a.H = w->Hglobal ? w->Hglobal : w->H;
+    a.y_off = w->y_off; a.Hl = w->H;
     a.zx = z->x; a.zy = z->y; a.zw = z->w; a.zh = z->h;
     a.pbuf = w->pbuf;
     a.st = (PState*)w->part_scratch;

@@ -1046,16 +1046,15 @@ __device__ __forceinline__ PlaneIO plane_io(const TickParams& P, int lane, int c
 
 // whole IO warp: load row k of the chunk into its slot (rows below FULL_LO: material plane only)
 template <int PASS>
-__device__ __forceinline__ void pass_row_load(SmemPass<PASS>& S, const PlaneIO& io, int lane, int k, int cy) {
+__device__ __forceinline__ void pass_row_load(SmemPass<PASS>& S, const PlaneIO& io, int lane, int k, int cy, int q, int kb) {
     using G = PassGeom<PASS>;
-    const int q = (k - G::KMIN) % G::RN;
     unsigned long long* bar = &S.bar[q];
-    const bool mat_only = k < G::FULL_LO;
+    const bool mat_only = k < kb + G::FULL_LO;  // rows under the segment's writable range are only read for their material
     if (lane == 0) {
         S.h.rowmod[q] = 0;
         S.h.rowchg[q] = 0;
         S.h.rowvis[q] = 0;
-        S.h.rowlazy[q] = 0;
+        S.h.rowlazy[q] = (PASS == 1 && k >= 0 && k < kb) ? 1 : 0;  // rows under the segment's first row were skipped by pass 1
         mbar_expect_tx(bar, mat_only ? P8 : ROW_BYTES);
     }
     __syncwarp();
@@ -1176,6 +1175,7 @@ __global__ void __launch_bounds__(1024) classify_rows_kernel(const __grid_consta
             o[0] = w1;
             o[4] = w2;
             o[8] = 0;
+            if (P.phase_rows) atomicAdd(P.phase_rows, (unsigned int)__popc(w1 | w2));  // rows some pass must run (fse_tick's skip gate)
         }
     }
 }
@@ -1245,45 +1245,103 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
         c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
     }
     __syncthreads();
-    // row k lives in slot (k - KMIN) % RN and is the ((k - KMIN) / RN)-th user of that slot's mbarrier
-    const PlaneIO pio = plane_io(P, lane < 7 ? lane : 0, cx);
-    if (io_load) {
-#pragma unroll 1
-        for (int k = G::KMIN; k < G::UP + G::PF; k++) {
-            pass_row_load<PASS>(S, pio, lane, k, cy);
+    // ---- segments ----------------------------------------------------------------------------------------------------------------
+    // The pass walks the chunk bottom-up in SEGMENTS of consecutive rows.  A segment starts at a row classify_rows_kernel found
+    // active (kb), loads its window like the start of a chunk (rows kb + KMIN ...), and goes on for as long as rows may still run:
+    // up to the highest row a running row could have touched (stop_row = row + UP) and across gaps of at most SEG_GAP settled rows
+    // to the next active one.  Past that the segment drains its stores (SL steps) and the pass jumps to the next active row: the
+    // settled rows in between are neither loaded, stepped nor stored.  Inside a segment row k lives in slot (k - kb - KMIN) % RN and
+    // is the ((k - kb - KMIN) / RN)-th user of that slot's mbarrier.  Every warp derives run / stop_row / the segment end from the
+    // same shared-memory flags after the same step barrier (a skipped step writes none of them, a running step only sets them), so
+    // the control flow is uniform over the CTA.  With active-chunk tracking (the store warp inspects every row) and without row
+    // masks there is one segment, rows 0 .. 127.
+    constexpr int SEG_GAP = 16;
+    static_assert(SEG_GAP >= -G::KMIN + G::UP + G::PF + 1, "a new segment's window must not overlap rows the previous one had in flight");
+    const bool jumps = gmask != nullptr && !P.chunk_state;
+    auto act_bit = [&](int k) -> bool { return (S.m_act[k >> 5] >> (k & 31)) & 1u; };
+    auto next_act = [&](int k) -> int {  // first active row >= k, CHUNK if none
+        while (k < CHUNK) {
+            const uint32_t wbits = S.m_act[k >> 5] >> (k & 31);
+            if (wbits) return k + __ffs(wbits) - 1;
+            k = (k | 31) + 1;
         }
-    }
-    for (int k = G::KMIN; k < G::UP; k++) mbar_wait(&S.bar[(k - G::KMIN) % G::RN], (uint32_t)(((k - G::KMIN) / G::RN) & 1));
-
-    const int n_steps = G::LAST + G::SL + 1;
+        return CHUNK;
+    };
+    const PlaneIO pio = plane_io(P, lane < 7 ? lane : 0, cx);
     bool io_modified = false, io_inert = true;  // active-chunk tracking (IO warp): see tick_chunk_kernel
     int last_run = -8;                          // compute warps: last row that was stepped (uniform over the CTA)
-    uint32_t io_lazy = 0, io_chg = 0;           // store warp, lane w < 4 holds word w.  pass 1: rows left implicit / rows pass 2 must run;
-                                                // pass 2: io_lazy = rows that stopped being implicit (marks written or row changed)
-#ifdef FSE_ROLE_CYCLES
-    long long dbg_t[4] = {0, 0, 0, 0};  // mbarrier wait, step barrier, step work, steps
-    long long dbg_io[3] = {0, 0, 0};    // IO lane 0: store side, wait for the slot's old store to leave shared memory, load issue
-#define FSE_STEP_CLOCK(i, since) do { const long long now_ = clock64(); dbg_t[i] += now_ - (since); (since) = now_; } while (0)
-    long long dbg_c = clock64();
-#else
-#define FSE_STEP_CLOCK(i, since) do { } while (0)
-#endif
-    for (int st = 0; st < n_steps; st++) {
-        FSE_STEP_CLOCK(2, dbg_c);
-        const int kw = st + G::UP;
-        // the IO warp never reads the row that is about to become live: only the compute warps wait for it
-        if (kw <= G::LAST && !io) mbar_wait(&S.bar[(kw - G::KMIN) % G::RN], (uint32_t)(((kw - G::KMIN) / G::RN) & 1));
-        FSE_STEP_CLOCK(0, dbg_c);
-#ifndef FSE_EXP_NO_TOP_FENCE
-        fence_proxy_async();
-#endif
+    // store warp, lane w < 4 holds word w.  pass 1: io_lazy = rows whose marks stay implicit (all of them until a row is seen at its
+    // store), io_chg = rows pass 2 must run on top of its own classification; pass 2: io_lazy = rows that stopped being implicit
+    uint32_t io_lazy = PASS == 1 ? 0xffffffffu : 0u, io_chg = 0;
+    int kb = jumps ? next_act(0) : 0;
+    bool first_segment = true;
+#pragma unroll 1
+    for (;;) {
+        // ---- segment start: slots free, barriers fresh, scratch flags reset, window of row kb loaded ----
+        if (!first_segment) {
+            if (io_store) bulk_wait_read<0>();  // the previous segment's stores have left shared memory
+            __syncthreads();
+            if (tid == 0) {
+                for (int q = 0; q < G::RN; q++) {
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.bar[q])) : "memory");
+                    mbar_init(&S.bar[q], 1);
+                }
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            if (!io) {  // both parities of the per-row scratch flags (a step only resets the next row's)
+                if (PASS == 1) {
+                    Scratch1& R = reinterpret_cast<Scratch1&>(S.rs);
+                    if (tid < 2) {
+                        R.p1_any[tid] = R.p1_area[tid] = R.p1_horiz[tid] = 0;
+                        R.area_mask[tid][0] = R.area_mask[tid][1] = R.area_mask[tid][2] = R.area_mask[tid][3] = 0;
+                    }
+                } else {
+                    Scratch2& R = reinterpret_cast<Scratch2&>(S.rs);
+                    for (int i = tid; i < CHUNK + 2; i += CHUNK)
+                        for (int bb = 0; bb < 2; bb++) R.claimDn[bb][i] = R.claimUp[bb][i] = 1 << 30;
+                    if (tid < 2) R.p2_any[tid] = R.p2_poke[tid] = 0;
+                }
+            }
+        }
+        if (tid == 0) c.koff = -G::KMIN - kb;
         __syncthreads();
-        FSE_STEP_CLOCK(1, dbg_c);
-        if (!io) {
-            if (st < CHUNK) {
-                const int q = (st - G::KMIN) % G::RN, qb = (st - 1 - G::KMIN) % G::RN;
+        first_segment = false;
+        const int k0 = kb + G::KMIN;  // lowest row of the segment's window
+        auto slot_of = [&](int k) -> int { return (k - k0) % G::RN; };
+        auto par_of = [&](int k) -> uint32_t { return (uint32_t)(((k - k0) / G::RN) & 1); };
+        if (io_load) {
+#pragma unroll 1
+            for (int k = k0; k < kb + G::UP + G::PF && k <= G::LAST; k++) pass_row_load<PASS>(S, pio, lane, k, cy, slot_of(k), kb);
+        }
+        for (int k = k0; k < kb + G::UP && k <= G::LAST; k++) mbar_wait(&S.bar[slot_of(k)], par_of(k));
+
+        int stop_row = kb;     // highest row that may still have to run
+        bool ending = false;   // past the segment's last row: drain the stores, load nothing
+        int seg_end = 0;
+        int nA = kb;           // next classified-active row >= st
+#pragma unroll 1
+        for (int st = kb;; st++) {
+            const int kw = st + G::UP;
+            // the IO warp never reads the row that is about to become live: only the compute warps wait for it
+            if (!io && kw <= G::LAST && (!ending || kw < seg_end + G::UP + G::PF)) mbar_wait(&S.bar[slot_of(kw)], par_of(kw));
+            fence_proxy_async();
+            __syncthreads();
+            bool run = false;
+            const int q = slot_of(st), qb = slot_of(st - 1);
+            if (!ending) {
                 // run the row if it was classified active, or if an earlier step of this pass changed it or the row below it
-                const bool run = ((S.m_act[st >> 5] >> (st & 31)) & 1u) || S.h.rowchg[q] || S.h.rowchg[qb];
+                run = st < CHUNK && (act_bit(st) || S.h.rowchg[q] || S.h.rowchg[qb]);
+                if (run && st + G::UP > stop_row) stop_row = st + G::UP;
+                if (nA <= st) nA = next_act(st + 1);
+                int need_hi = stop_row;
+                if (!jumps) need_hi = G::LAST;
+                else if (nA < CHUNK && nA - st <= SEG_GAP && nA > need_hi) need_hi = nA;
+                if (st > need_hi) {
+                    ending = true;
+                    seg_end = st;
+                }
+            }
+            if (!io) {
                 if (run) {
                     const int j = HX8 + tid;
                     if (PASS == 1) {
@@ -1291,7 +1349,7 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                         int lo = last_run + 1;
                         if (lo < st - 5) lo = st - 5;
                         if (lo < 0) lo = 0;  // rows below the chunk belong to other chunks: never marked from here
-                        for (int r = lo; r < st; r++) materialize_marks(c, (r - G::KMIN) % G::RN, j);
+                        for (int r = lo; r < st; r++) materialize_marks(c, slot_of(r), j);
                         pass1_rows<G::RN>(c, reinterpret_cast<Scratch1&>(S.rs), st, cx, cy, tid);
                     } else {
                         // rows st - 1 .. st + 1 are the ones this row can write: implicit pass-1 marks become real ones first
@@ -1299,11 +1357,11 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                         if (lo < st - 1) lo = st - 1;
                         if (lo < 0) lo = 0;
                         for (int r = lo; r <= st + 1 && r < CHUNK; r++)
-                            if ((S.m_lazy[r >> 5] >> (r & 31)) & 1u) materialize_marks(c, (r - G::KMIN) % G::RN, j);
+                            if ((S.m_lazy[r >> 5] >> (r & 31)) & 1u) materialize_marks(c, slot_of(r), j);
                         pass2_rows<G::RN>(c, reinterpret_cast<Scratch2&>(S.rs), st, cx, cy, tid);
                     }
                     last_run = st;
-                } else {
+                } else if (!ending && st < CHUNK) {
                     const int par = st & 1;  // what a running step resets for the next row (pass1_rows / pass2_rows)
                     if (PASS == 1) {
                         Scratch1& R = reinterpret_cast<Scratch1&>(S.rs);
@@ -1326,79 +1384,61 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                         }
                     }
                 }
-            }
-        } else {
-#ifdef FSE_ROLE_CYCLES
-            long long io_c = clock64();
-#define FSE_IO_CLOCK(i) do { const long long now_ = clock64(); dbg_io[i] += now_ - io_c; io_c = now_; } while (0)
-#else
-#define FSE_IO_CLOCK(i) do { } while (0)
-#endif
-            const int ks = st - G::SL;
-            if (io_store && ks >= G::FULL_LO && ks <= G::LAST) {
-                const int q = (ks - G::KMIN) % G::RN;
-                uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + q * ROW_BYTES + OFF_FLG);
-                const bool core_row = ks >= 0 && ks < CHUNK;
-                const bool all_store = S.h.rowmod[q] != 0;
-                const bool vis_store = S.h.rowvis[q] != 0;
-                if (PASS == 2 && gmask && core_row && (all_store || vis_store) && lane == (ks >> 5)) io_lazy |= 1u << (ks & 31);
-                if (PASS == 1 && gmask) {
-                    if (core_row && S.h.rowlazy[q] && !all_store && !vis_store && lane == (ks >> 5)) io_lazy |= 1u << (ks & 31);
-                    if (S.h.rowchg[q]) {  // pass 2 reads a row's own cells and the row below them
-                        if (core_row && lane == (ks >> 5)) io_chg |= 1u << (ks & 31);
-                        if (ks + 1 >= 0 && ks + 1 < CHUNK && lane == ((ks + 1) >> 5)) io_chg |= 1u << ((ks + 1) & 31);
+            } else {
+                const int ks = st - G::SL;
+                if (io_store && ks >= kb + G::FULL_LO && ks <= G::LAST) {
+                    const int qs = slot_of(ks);
+                    uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + qs * ROW_BYTES + OFF_FLG);
+                    const bool core_row = ks >= 0 && ks < CHUNK;
+                    const bool all_store = S.h.rowmod[qs] != 0;
+                    const bool vis_store = S.h.rowvis[qs] != 0;
+                    if (PASS == 2 && gmask && core_row && (all_store || vis_store) && lane == (ks >> 5)) io_lazy |= 1u << (ks & 31);
+                    if (PASS == 1 && gmask) {
+                        if (core_row && !(S.h.rowlazy[qs] && !all_store && !vis_store) && lane == (ks >> 5)) io_lazy &= ~(1u << (ks & 31));
+                        if (S.h.rowchg[qs]) {  // pass 2 reads a row's own cells and the row below them
+                            if (core_row && lane == (ks >> 5)) io_chg |= 1u << (ks & 31);
+                            if (ks + 1 >= 0 && ks + 1 < CHUNK && lane == ((ks + 1) >> 5)) io_chg |= 1u << ((ks + 1) & 31);
+                        }
+                    }
+                    // tickVisited of the chunk's own cells goes to HBM (the later passes need it); halo cells are cleared.  Only rows
+                    // that are stored need it; a core row has 4 + 4 halo words (one word per lane 0..7), other rows are cleared whole
+                    if (all_store || vis_store) {
+                        if (core_row) {
+                            if (lane < 2 * (HX8 / 4)) fw[lane < HX8 / 4 ? lane : (HX8 + CHUNK) / 4 + lane - HX8 / 4] &= 0x7f7f7f7fU;
+                        } else {
+                            for (int w = lane; w < P8 / 4; w += 32) fw[w] &= 0x7f7f7f7fU;
+                        }
+                    }
+                    if (P.chunk_state) {
+                        io_modified |= S.h.rowchg[qs] != 0;
+                        // rows are final for passes 1 and 2 here; pass 3 only moves GAS, which is never inert anyway
+                        if (PASS == 2 && core_row) io_inert &= row_is_inert(c, qs, rsn<G::RN>(qs, 1), lane);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (all_store ? lane < 7 : (vis_store && lane == 1))
+                        bulk_s2g(pio.g + (size_t)(cy + CHUNK - 1 - ks) * pio.row_stride, S.ring + qs * ROW_BYTES + pio.soff, pio.bytes);
+                }
+                const int kl = st + G::UP + G::PF;
+                const bool load = !ending && kl <= G::LAST;
+                if (io_store) {
+                    bulk_commit();  // one (possibly empty) bulk group per lane and step, so wait_group counts steps
+                    if (load) {
+                        // each lane waits until its own stores out of the slot to fill have left shared memory (bulk groups are per
+                        // thread): with one spare row in the window that store was issued a step ago and this does not stall
+                        if (G::UP + G::PF - G::RN < -G::SL) bulk_wait_read<1>();
+                        else bulk_wait_read<0>();
                     }
                 }
-                // tickVisited of the chunk's own cells goes to HBM (the later passes need it); halo cells are cleared.  Only rows
-                // that are stored need it; a core row has 4 + 4 halo words (one word per lane 0..7), other rows are cleared whole
-                if (all_store || vis_store) {
-                    if (core_row) {
-                        if (lane < 2 * (HX8 / 4)) fw[lane < HX8 / 4 ? lane : (HX8 + CHUNK) / 4 + lane - HX8 / 4] &= 0x7f7f7f7fU;
-                    } else {
-                        for (int w = lane; w < P8 / 4; w += 32) fw[w] &= 0x7f7f7f7fU;
-                    }
-                }
-                if (P.chunk_state) {
-                    io_modified |= S.h.rowchg[q] != 0;
-                    // rows are final for passes 1 and 2 here; pass 3 only moves GAS, which is never inert anyway
-                    if (PASS == 2 && core_row) io_inert &= row_is_inert(c, q, rsn<G::RN>(q, 1), lane);
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (all_store ? lane < 7 : (vis_store && lane == 1))
-                    bulk_s2g(pio.g + (size_t)(cy + CHUNK - 1 - ks) * pio.row_stride, S.ring + q * ROW_BYTES + pio.soff, pio.bytes);
+                if (io_load && load) pass_row_load<PASS>(S, pio, lane, kl, cy, slot_of(kl), kb);
             }
-            const int kl = st + G::UP + G::PF;
-            if (io_store) {
-                bulk_commit();  // one (possibly empty) bulk group per lane and step, so wait_group counts steps
-                FSE_IO_CLOCK(0);
-                if (kl <= G::LAST) {
-                    // each lane waits until its own stores out of the slot to fill have left shared memory (bulk groups are per
-                    // thread): with one spare row in the window that store was issued a step ago and this does not stall
-                    if (G::UP + G::PF - G::RN < -G::SL) bulk_wait_read<1>();
-                    else bulk_wait_read<0>();
-                }
-                FSE_IO_CLOCK(1);
-            }
-            if (io_load && kl <= G::LAST) {
-                pass_row_load<PASS>(S, pio, lane, kl, cy);
-                FSE_IO_CLOCK(2);
-            }
+            if (ending && st >= seg_end + G::SL - 1) break;
         }
+        // rows at and above the segment's end: the next classified-active one starts the next segment
+        const int nxt = jumps ? next_act(seg_end) : CHUNK;
+        if (nxt >= CHUNK) break;
+        kb = nxt;
     }
-#ifdef FSE_ROLE_CYCLES
-    if (PASS == 1 && P.dbg && tid == 0) {
-        atomicAdd(&P.dbg[0], 1ULL);
-        for (int q = 0; q < 10; q++) atomicAdd(&P.dbg[1 + q], (unsigned long long)reinterpret_cast<Scratch1&>(S.rs).dbg_phase[q]);
-    }
-    if (P.dbg && (tid == 0 || tid == 128)) {  // compute thread 0 and (store) IO lane 0: where the step time goes
-        unsigned long long* o = P.dbg + 16 + (PASS - 1) * 8 + (tid ? 4 : 0);
-        FSE_STEP_CLOCK(2, dbg_c);
-        for (int q = 0; q < 3; q++) atomicAdd(&o[q], (unsigned long long)dbg_t[q]);
-        atomicAdd(&o[3], 1ULL);
-        if (tid) for (int q = 0; q < 3; q++) atomicAdd(&P.dbg[32 + (PASS - 1) * 4 + q], (unsigned long long)dbg_io[q]);
-    }
-#endif
     if (PASS == 1 && cost_slot && tid == 0) *cost_slot = (unsigned int)(clock64() - t_begin);
     if (io_store && P.chunk_state) {
         const bool inert = __all_sync(0xffffffffu, io_inert);

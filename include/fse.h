@@ -222,6 +222,26 @@ FSE_API int fse_particles_reserve(fse_world* w, int64_t capacity);
  * (their cells are gone from the grid); 0 in normal operation.  fse_particles_count never fails on an overflowed pool. */
 FSE_API int fse_particles_dropped(fse_world* w, int64_t* out);
 
+/* ---- entities <-> grid: world::tickEntities (world.cpp:3010-3247), WorldEntitySystem::process
+ *      (game/player.cpp:173-199), the objectDelete loop (game.cpp:2128-2139).  fse_entity mirrors the value fields of WorldEntity
+ *      (game_datastruct.hpp:42-62); the b2Body the reference moves along (world.cpp:3227-3228) stays with the host.
+ *      load_x / load_y = world::loadZone.x / .y (floats, as in the reference's MErect).  Entities are processed in array order. */
+typedef struct fse_entity {
+    float x, y, vx, vy;
+    int32_t hw, hh;      /* hit box, cells */
+    int32_t ground;      /* out: stood on something this tick */
+    int32_t destroy;     /* out: |v| >= 1024, the reference destroys the entity (world.cpp:3222-3225) */
+} fse_entity;
+/* overlap push-out, gravity, the 8-sub-step horizontal and vertical sweeps with step-up and sand kicks, velocity decay; updates
+ * `ents` in place */
+FSE_API int fse_entities_tick(fse_world* w, fse_entity* ents, int32_t n, float load_x, float load_y, uint32_t tick, uint32_t seed);
+/* AIR under an entity becomes Tiles_OBJECT (material `object_mat`, GENERIC_OBJECT = 6 in the stock table), SAND / SOUP is thrown up
+ * as a particle first; every stamped cell is remembered for fse_object_delete */
+FSE_API int fse_entities_stamp(fse_world* w, const fse_entity* ents, int32_t n, float load_x, float load_y, int32_t object_mat, uint32_t tick,
+                               uint32_t seed);
+/* the stamped cells become Tiles_NOTHING again (end of the game tick) */
+FSE_API int fse_object_delete(fse_world* w);
+
 /* ---- rigid-body bridge: the raster / erase loops of game::tick (game.cpp:1711-1815, 1896-1983) ---------------
  * Box2D stays on the host (north_star); the host keeps b2Body poses and sends one fse_xform per body per tick.
  * fse_body_desc mirrors RigidBody::matWidth / matHeight / tiles (game/player.hpp:15-65); AIR tiles are empty. */

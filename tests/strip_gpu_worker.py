@@ -24,6 +24,7 @@ def main():
     sw.write_rect(0, lo, G.mixed_band(table, W, H, lo, hi - lo, seed=77, blob=32))
     for t in range(ticks):
         sw.tick(t, seed=1337)
+        sw.particles_tick()  # ghost refresh, migration, integration and the deposit rounds with the band proposals exchanged
         if t % 4 == 2:
             sw.tick_temperature()
     sw.sync()

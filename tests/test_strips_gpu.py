@@ -1,4 +1,5 @@
-"""Multi-GPU strips over NCCL vs the single-world oracle (bit-exact for any strip count; SURVEY.md §8c pin 8).
+"""Multi-GPU strips over NCCL vs the single-world oracle (bit-exact for any strip count; SURVEY.md §8c pin 8): world tick, loose
+particles (migration between ranks + deposit rounds with the band proposals exchanged) and temperature.
 Needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_strips_gpu.py -m gpu`."""
 import os
 import subprocess
@@ -34,10 +35,15 @@ def test_strips_match_oracle(oracle, table, tmp_path, nranks):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     ow = oracle.OracleWorld(W, H, table)
     ow.write_rect(0, 0, G.mixed_band(table, W, H, 0, H, seed=77, blob=32))
+    deposited = 0
     for t in range(ticks):
         ow.tick(t, seed=1337)
+        before = ow.particles_count()
+        ow.particles_tick()
+        deposited += before - ow.particles_count()
         if t % 4 == 2:
             ow.tick_temperature()
+    assert deposited > 0
     ref = ow.read_all()
     parts = []
     for k in range(nranks):
