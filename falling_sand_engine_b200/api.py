@@ -322,6 +322,24 @@ class World:
         self.L.fse_explosion.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32]
         _ck(self.L.fse_explosion(self.h, x, y, radius, tick, seed))
 
+    # -- entities <-> grid (world::tickEntities, WorldEntitySystem::process, objectDelete) ----------------------
+    def entities_tick(self, ents, load_zone=(0.0, 0.0), tick=0, seed=1337):
+        """world::tickEntities (world.cpp:3010-3247) on a T.ENTITY_DTYPE array; returns the updated copy (x, y, vx, vy, ground, destroy)."""
+        e = np.ascontiguousarray(ents, dtype=T.ENTITY_DTYPE).copy()
+        self.L.fse_entities_tick.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_uint32, C.c_uint32]
+        _ck(self.L.fse_entities_tick(self.h, e.ctypes.data, len(e), load_zone[0], load_zone[1], tick, seed))
+        return e
+
+    def entities_stamp(self, ents, load_zone=(0.0, 0.0), object_mat=6, tick=0, seed=1337):
+        """WorldEntitySystem::process (game/player.cpp:173-199): cells under the entities become Tiles_OBJECT until object_delete()."""
+        e = np.ascontiguousarray(ents, dtype=T.ENTITY_DTYPE)
+        self.L.fse_entities_stamp.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_uint32, C.c_uint32]
+        _ck(self.L.fse_entities_stamp(self.h, e.ctypes.data, len(e), load_zone[0], load_zone[1], object_mat, tick, seed))
+
+    def object_delete(self):
+        self.L.fse_object_delete.argtypes = [C.c_void_p]
+        _ck(self.L.fse_object_delete(self.h))
+
     def mask_outline(self, masks):
         """masks: (n, h, w) uint8.  Returns (labels (n,h,w) int32, n_components (n,), contours: list per mask of (k,2) float arrays)."""
         masks = np.ascontiguousarray(masks, dtype=np.uint8)

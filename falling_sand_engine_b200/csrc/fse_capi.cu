@@ -225,6 +225,7 @@ static void free_world(fse_world* w) {
     cudaFree(w->d_lpt_cost); cudaFree(w->d_lpt_list); cudaFree(w->d_chunk_state); cudaFree(w->d_rowmask);
     fse_bodies_free(w);
     particles_strip_free(w);
+    entities_free(w);
     cudaFree(w->outline_scratch);
     delete w;
 }

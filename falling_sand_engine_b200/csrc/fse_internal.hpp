@@ -51,6 +51,7 @@ struct fse_world {
     size_t part_list_bytes = 0;
     fse_particle* pbuf2 = nullptr;  // compaction target, swapped with pbuf every fse_particles_tick
     size_t pbuf2_bytes = 0;
+    void* entity_bufs = nullptr;     // fse_entities.cu EntityBufs
     void* particle_strip = nullptr;  // strips: exchange buffers of the particle protocol (fse_particles.cu StripBufs)
     void* claim_keys = nullptr;
     size_t claim_keys_bytes = 0;
@@ -136,6 +137,7 @@ int fse_wake_rect(fse_world* w, int x, int y_local, int rw, int rh);  // wake th
 int particles_headroom(fse_world* w, int64_t need, bool exact);  // grow the particle pool before a call that spawns up to `need`
 int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cudaStream_t s);
 void particles_strip_free(fse_world* w);
+void entities_free(fse_world* w);
 int strip_refresh(fse_world* w, cudaStream_t s, int rows = 16);
 int strip_sendrecv(fse_world* w, const void* up_send, size_t up_send_bytes, void* up_recv, size_t up_recv_bytes, const void* down_send,
                    size_t down_send_bytes, void* down_recv, size_t down_recv_bytes, cudaStream_t s);

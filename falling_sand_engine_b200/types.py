@@ -103,6 +103,10 @@ PARTICLE_DTYPE = np.dtype(
 )
 
 
+# fse_entity (32 bytes): the value fields of WorldEntity (game_datastruct.hpp:42-62)
+ENTITY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("vx", "<f4"), ("vy", "<f4"), ("hw", "<i4"), ("hh", "<i4"), ("ground", "<i4"), ("destroy", "<i4")])
+
+
 def zone_of(width, height):
     """tickZone of the reference: the grid minus a one-chunk border (game.cpp:1629)."""
     return Rect(FSE_CHUNK, FSE_CHUNK, width - 2 * FSE_CHUNK, height - 2 * FSE_CHUNK)

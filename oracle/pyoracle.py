@@ -235,6 +235,27 @@ def scroll(world, dx, dy):
     lib().fseo_scroll(world.h, dx, dy)
 
 
+def entities_tick(world, ents, load_zone=(0.0, 0.0), tick=0, seed=1337):
+    """world::tickEntities (world.cpp:3010-3247); returns the updated entity array."""
+    e = np.ascontiguousarray(ents, dtype=T.ENTITY_DTYPE).copy()
+    lib().fseo_entities_tick.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_uint32, C.c_uint32]
+    lib().fseo_entities_tick(world.h, e.ctypes.data, len(e), load_zone[0], load_zone[1], tick, seed)
+    return e
+
+
+def entities_stamp(world, ents, load_zone=(0.0, 0.0), object_mat=6, tick=0, seed=1337):
+    """WorldEntitySystem::process (game/player.cpp:173-199)."""
+    e = np.ascontiguousarray(ents, dtype=T.ENTITY_DTYPE)
+    lib().fseo_entities_stamp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_uint32, C.c_uint32]
+    lib().fseo_entities_stamp(world.h, e.ctypes.data, len(e), load_zone[0], load_zone[1], object_mat, tick, seed)
+
+
+def object_delete(world):
+    """the objectDelete loop of game::tick (game.cpp:2128-2139)."""
+    lib().fseo_object_delete.argtypes = [C.c_void_p]
+    lib().fseo_object_delete(world.h)
+
+
 def explosion(world, cx, cy, radius, tick=0, seed=1337):
     """world::explosion (world.cpp:2294-2332)."""
     lib().fseo_explosion.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
