@@ -340,6 +340,41 @@ class World:
         self.L.fse_object_delete.argtypes = [C.c_void_p]
         _ck(self.L.fse_object_delete(self.h))
 
+    # -- interactive tools, grid side -----------------------------------------------------------------------
+    def tool_erase_line(self, x0, y0, x1, y1, brush_size=5):
+        """middle-mouse erase brush (game.cpp:593-625)."""
+        self.L.fse_tool_erase_line.argtypes = [C.c_void_p] + [C.c_int32] * 5
+        _ck(self.L.fse_tool_erase_line(self.h, x0, y0, x1, y1, brush_size))
+
+    def tool_pickaxe(self, x, y, break_size):
+        """pickaxe (game.cpp:771-790): returns (ARGB pixels (size, size) of the broken-off body, cells taken)."""
+        size = int(break_size)
+        pix = np.zeros((size, size), dtype=np.uint32)
+        n = C.c_int32()
+        self.L.fse_tool_pickaxe.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.POINTER(C.c_int32)]
+        _ck(self.L.fse_tool_pickaxe(self.h, x, y, break_size, pix.ctypes.data, C.byref(n)))
+        return pix, n.value
+
+    def tool_hammer(self, hammer_x, hammer_y, x, y, sand_mat=2, tick=0, seed=1337):
+        """hammer release (game.cpp:843-890): returns (end_x, end_y, n_changed, broke)."""
+        out = np.zeros(4, dtype=np.int32)
+        self.L.fse_tool_hammer.argtypes = [C.c_void_p] + [C.c_int32] * 5 + [C.c_uint32, C.c_uint32, C.c_void_p]
+        _ck(self.L.fse_tool_hammer(self.h, hammer_x, hammer_y, x, y, sand_mat, tick, seed, out.ctypes.data))
+        return tuple(int(v) for v in out)
+
+    def tool_vacuum(self, wcx, wcy, wmx, wmy, tick=0, seed=1337):
+        """vacuum (game.cpp:2456-2585): returns (x, y, cells sucked, particles caught)."""
+        out = np.zeros(4, dtype=np.int32)
+        self.L.fse_tool_vacuum.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_uint32, C.c_uint32, C.c_void_p]
+        _ck(self.L.fse_tool_vacuum(self.h, wcx, wcy, wmx, wmy, tick, seed, out.ctypes.data))
+        return tuple(int(v) for v in out)
+
+    def particles_vacuum_pull(self, target_x, target_y):
+        n = C.c_int32()
+        self.L.fse_particles_vacuum_pull.argtypes = [C.c_void_p, C.c_float, C.c_float, C.POINTER(C.c_int32)]
+        _ck(self.L.fse_particles_vacuum_pull(self.h, target_x, target_y, C.byref(n)))
+        return n.value
+
     def mask_outline(self, masks):
         """masks: (n, h, w) uint8.  Returns (labels (n,h,w) int32, n_components (n,), contours: list per mask of (k,2) float arrays)."""
         masks = np.ascontiguousarray(masks, dtype=np.uint8)

@@ -226,6 +226,7 @@ static void free_world(fse_world* w) {
     fse_bodies_free(w);
     particles_strip_free(w);
     entities_free(w);
+    cudaFree(w->tool_scratch);
     cudaFree(w->outline_scratch);
     delete w;
 }

@@ -51,6 +51,8 @@ struct fse_world {
     size_t part_list_bytes = 0;
     fse_particle* pbuf2 = nullptr;  // compaction target, swapped with pbuf every fse_particles_tick
     size_t pbuf2_bytes = 0;
+    void* tool_scratch = nullptr;    // fse_tools.cu: cell lists and results of the interactive tools
+    size_t tool_scratch_bytes = 0;
     void* entity_bufs = nullptr;     // fse_entities.cu EntityBufs
     void* particle_strip = nullptr;  // strips: exchange buffers of the particle protocol (fse_particles.cu StripBufs)
     void* claim_keys = nullptr;

@@ -278,7 +278,7 @@ __device__ __noinline__ void emit_particle_raw(fse_particle* pbuf, unsigned int*
     p.phase = 0;
     p.temporary = (uint8_t)((packed >> 24) & 1);
     p.in_object_state = 0;
-    p._pad = 0;
+    p.vacuum = 0;
     p._pad2 = 0;
     p.id = id;
     uint4* dst = reinterpret_cast<uint4*>(pbuf + i);

@@ -94,7 +94,7 @@ CELL_DTYPE = np.dtype(
 PARTICLE_DTYPE = np.dtype(
     {
         "names": ["tile", "x", "y", "vx", "vy", "ax", "ay", "target_x", "target_y", "target_force", "lifetime", "fade_time",
-                  "phase", "temporary", "in_object_state", "_pad", "_pad2", "id"],
+                  "phase", "temporary", "in_object_state", "vacuum", "_pad2", "id"],
         "formats": [CELL_DTYPE, "<f4", "<f4", "<f4", "<f4", "<f4", "<f4", "<f4", "<f4", "<f4", "<i4", "<i4", "u1", "u1", "u1", "u1",
                     "<u4", "<u8"],
         "offsets": [0, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 65, 66, 67, 68, 72],

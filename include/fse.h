@@ -145,7 +145,7 @@ typedef struct fse_particle {
     uint8_t phase;
     uint8_t temporary;
     uint8_t in_object_state;
-    uint8_t _pad;
+    uint8_t vacuum;      /* held by the vacuum tool: member of Item::vacuumCells (game.cpp:2507, 2562) */
     uint32_t _pad2;
     uint64_t id;
 } fse_particle;
@@ -271,6 +271,36 @@ FSE_API int fse_bodies_read(fse_world* w, int32_t body, fse_cell* tiles_out);
  * lower, thrown outward) — and every non-SOLID cell of the ring out to 2*radius is thrown outward as a particle.  Cells decide
  * independently; rand() is replaced by the counter RNG keyed on (seed, tick, x, y).  Not available on multi-rank strips. */
 FSE_API int fse_explosion(fse_world* w, int32_t cx, int32_t cy, int32_t radius, uint32_t tick, uint32_t seed);
+
+/* ---- interactive tools, grid side.  Rigid-body surfaces, Box2D bodies, audio and UI stay with the host. ----------
+ * erase brush (game.cpp:593-625): every non-AIR cell under a brush_size square (corners with |dx| + |dy| == brush_size left out)
+ * stamped along world::forLine from (x0, y0) to (x1, y1) becomes Tiles_NOTHING */
+FSE_API int fse_tool_erase_line(fse_world* w, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int32_t brush_size);
+/* pickaxe (game.cpp:771-790): SOLID cells inside the circle of diameter break_size whose box starts at (x, y) leave the grid; their
+ * colours come back as the int(break_size)^2 ARGB pixels of the rigid body the host makes from them, *n_out = cells taken */
+FSE_API int fse_tool_pickaxe(fse_world* w, int32_t x, int32_t y, float break_size, uint32_t* pixels_out, int32_t* n_out);
+/* hammer release (game.cpp:843-890): a crack from the hammer point away from the release point (x, y) in jittered ~10-cell segments
+ * along world::forLineCornered; SOLID cells on it become `sand_mat` (GENERIC_SAND) at half brightness until the crack leaves the
+ * solid.  The host then probes both sides of the crack's middle with fse_flood_component (game.cpp:892-901). */
+typedef struct fse_hammer_result {
+    int32_t end_x, end_y;   /* last cell changed, -1 if none */
+    int32_t n_changed;
+    int32_t broke;          /* the crack left the solid */
+} fse_hammer_result;
+FSE_API int fse_tool_hammer(fse_world* w, int32_t hammer_x, int32_t hammer_y, int32_t x, int32_t y, int32_t sand_mat, uint32_t tick, uint32_t seed,
+                            fse_hammer_result* out);
+/* vacuum (game.cpp:2456-2585): walk from the screen centre (wcx, wcy) towards the mouse (wmx, wmy) to the first SOLID / SAND / SOUP
+ * cell, turn the matter in the 11 x 11 disc around it into `phase` particles held by the vacuum, and catch the loose particles
+ * already inside it.  Nothing happens when the mouse is more than 256 cells away. */
+typedef struct fse_vacuum_result {
+    int32_t x, y;           /* centre of the disc, -1 when out of reach */
+    int32_t n_sucked;       /* grid cells turned into particles */
+    int32_t n_caught;       /* loose particles caught */
+} fse_vacuum_result;
+FSE_API int fse_tool_vacuum(fse_world* w, int32_t wcx, int32_t wcy, int32_t wmx, int32_t wmy, uint32_t tick, uint32_t seed, fse_vacuum_result* out);
+/* the vacuumCells update (game.cpp:2640-2664): held particles whose lifetime is up fly towards (target_x, target_y); within 10 cells
+ * they are collected (dropped by the next fse_particles_tick).  n_collected may be null. */
+FSE_API int fse_particles_vacuum_pull(fse_world* w, float target_x, float target_y, int32_t* n_collected);
 
 /* ---- render planes: the dirty -> texture loop of game::tick (game.cpp:1994-2060).  Every cell whose dirty
  * flag is set refreshes its texel in three device-resident RGBA8 planes (byte order r, g, b, a as the reference fills

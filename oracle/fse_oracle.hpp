@@ -144,6 +144,7 @@ struct Particle {
     int lifetime = 0;
     int fadeTime = 60;
     uint8_t inObjectState = 0;
+    bool vacuum = false;  // member of the vacuum tool's Item::vacuumCells (game.cpp:2507)
     uint64_t id = 0;
 };
 

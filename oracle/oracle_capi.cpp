@@ -95,7 +95,7 @@ static void to_pod(const World* w, const Particle& s, fse_particle& d) {
     d.x = s.x; d.y = s.y; d.vx = s.vx; d.vy = s.vy; d.ax = s.ax; d.ay = s.ay;
     d.target_x = s.targetX; d.target_y = s.targetY; d.target_force = s.targetForce;
     d.lifetime = s.lifetime; d.fade_time = s.fadeTime;
-    d.phase = s.phase; d.temporary = s.temporary; d.in_object_state = s.inObjectState;
+    d.phase = s.phase; d.temporary = s.temporary; d.in_object_state = s.inObjectState; d.vacuum = s.vacuum ? 1 : 0;
     d.id = s.id;
     (void)w;
 }
@@ -116,7 +116,7 @@ OAPI int fseo_particles_add(void* p, const fse_particle* src, int n) {
         d.x = s.x; d.y = s.y; d.vx = s.vx; d.vy = s.vy; d.ax = s.ax; d.ay = s.ay;
         d.targetX = s.target_x; d.targetY = s.target_y; d.targetForce = s.target_force;
         d.lifetime = s.lifetime; d.fadeTime = s.fade_time;
-        d.phase = s.phase != 0; d.temporary = s.temporary != 0; d.inObjectState = s.in_object_state;
+        d.phase = s.phase != 0; d.temporary = s.temporary != 0; d.inObjectState = s.in_object_state; d.vacuum = s.vacuum != 0;
         d.id = s.id;
         w->add_particle(d);
     }

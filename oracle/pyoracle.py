@@ -256,6 +256,39 @@ def object_delete(world):
     lib().fseo_object_delete(world.h)
 
 
+def tool_erase_line(world, x0, y0, x1, y1, brush_size=5):
+    """erase brush (game.cpp:593-625); returns the number of cells cleared."""
+    lib().fseo_tool_erase_line.argtypes = [C.c_void_p] + [C.c_int] * 5
+    return lib().fseo_tool_erase_line(world.h, x0, y0, x1, y1, brush_size)
+
+
+def tool_pickaxe(world, x, y, break_size):
+    size = int(break_size)
+    pix = np.zeros((size, size), dtype=np.uint32)
+    lib().fseo_tool_pickaxe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    n = lib().fseo_tool_pickaxe(world.h, x, y, break_size, pix.ctypes.data)
+    return pix, n
+
+
+def tool_hammer(world, hammer_x, hammer_y, x, y, sand_mat=2, tick=0, seed=1337):
+    out = np.zeros(4, dtype=np.int32)
+    lib().fseo_tool_hammer.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_uint32, C.c_uint32, C.c_void_p]
+    lib().fseo_tool_hammer(world.h, hammer_x, hammer_y, x, y, sand_mat, tick, seed, out.ctypes.data)
+    return tuple(int(v) for v in out)
+
+
+def tool_vacuum(world, wcx, wcy, wmx, wmy, tick=0, seed=1337):
+    out = np.zeros(4, dtype=np.int32)
+    lib().fseo_tool_vacuum.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_uint32, C.c_uint32, C.c_void_p]
+    lib().fseo_tool_vacuum(world.h, wcx, wcy, wmx, wmy, tick, seed, out.ctypes.data)
+    return tuple(int(v) for v in out)
+
+
+def particles_vacuum_pull(world, target_x, target_y):
+    lib().fseo_particles_vacuum_pull.argtypes = [C.c_void_p, C.c_float, C.c_float]
+    return lib().fseo_particles_vacuum_pull(world.h, target_x, target_y)
+
+
 def explosion(world, cx, cy, radius, tick=0, seed=1337):
     """world::explosion (world.cpp:2294-2332)."""
     lib().fseo_explosion.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
