@@ -422,7 +422,7 @@ def run_ours(args):
             world.particles_tick()
         if have_bodies:
             world.bodies_erase(xf)
-            world.mask_outline(masks)
+            world.mask_outline(masks, want_labels=False, as_lists=False)
         if t % 4 == 2:
             world.tick_temperature()
         if single:
@@ -452,7 +452,7 @@ def run_ours(args):
             a0 = time.perf_counter(); world.bodies_raster(xf, tick=tick_no); world.sync(); a1 = time.perf_counter()
             world.tick(tick_no, seed=args.seed, cell_iter=CELL_ITER); world.sync(); a2 = time.perf_counter()
             world.bodies_erase(xf); world.sync(); a3 = time.perf_counter()
-            world.mask_outline(masks); a4 = time.perf_counter()
+            world.mask_outline(masks, want_labels=False, as_lists=False); a4 = time.perf_counter()
             acc["raster"] += a1 - a0; acc["erase"] += a3 - a2; acc["outline"] += a4 - a3
             tick_no += 1
         body_ms = {k: 1e3 * v / 3 for k, v in acc.items()}

@@ -254,6 +254,19 @@ class World:
         _ck(self.L.fse_bodies_erase(self.h, xf.ctypes.data, n, fb.ctypes.data, need.ctypes.data))
         return fb, need
 
+    def bodies_split(self, i, angle=0.0, weld=(-1, -1)):
+        """Fracture hand-off of uploaded body i (world::updateRigidBodyHitbox, world.cpp:288-720): one (piece record, tile array) per
+        4-connected component of its non-AIR tiles, cropped, with the weld flag and the rotated position shift."""
+        h, w = self._bodies[i].shape
+        pieces = np.zeros(1024, dtype=T.BODY_PIECE_DTYPE)
+        out = np.zeros(4 * h * w + 64, dtype=T.CELL_DTYPE)
+        n = C.c_int32()
+        self.L.fse_bodies_split.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
+                                            C.c_int64]
+        _ck(self.L.fse_bodies_split(self.h, i, angle, weld[0], weld[1], pieces.ctypes.data, len(pieces), C.byref(n), out.ctypes.data, len(out)))
+        return [(pieces[k].copy(), out[pieces[k]["tile_off"]: pieces[k]["tile_off"] + pieces[k]["w"] * pieces[k]["h"]].reshape(pieces[k]["h"], pieces[k]["w"]).copy())
+                for k in range(n.value)]
+
     def bodies_read(self, i):
         out = np.zeros(self._bodies[i].shape, dtype=T.CELL_DTYPE)
         self.L.fse_bodies_read.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -375,11 +388,12 @@ class World:
         _ck(self.L.fse_particles_vacuum_pull(self.h, target_x, target_y, C.byref(n)))
         return n.value
 
-    def mask_outline(self, masks):
-        """masks: (n, h, w) uint8.  Returns (labels (n,h,w) int32, n_components (n,), contours: list per mask of (k,2) float arrays)."""
+    def mask_outline(self, masks, want_labels=True, as_lists=True):
+        """masks: (n, h, w) uint8.  Returns (labels (n,h,w) int32 or None, n_components (n,), contours: list per mask of (k,2) float arrays —
+        or, with as_lists=False, the flat (points, point offsets, mask offsets) arrays of the C ABI)."""
         masks = np.ascontiguousarray(masks, dtype=np.uint8)
         n, h, w = masks.shape
-        labels = np.zeros((n, h, w), dtype=np.int32)
+        labels = np.zeros((n, h, w), dtype=np.int32) if want_labels else None
         ncomp = np.zeros(n, dtype=np.int32)
         cap_pts, cap_c = int(masks.size) * 2 + 64, int(masks.size) // 2 + 64
         pts = np.zeros((cap_pts, 2), dtype=np.float32)
@@ -388,9 +402,11 @@ class World:
         self.L.fse_mask_outline.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         t0 = time.perf_counter()
-        _ck(self.L.fse_mask_outline(self.h, masks.ctypes.data, n, w, h, labels.ctypes.data, ncomp.ctypes.data, pts.ctypes.data, cap_pts,
-                                    pt_off.ctypes.data, cap_c, mask_off.ctypes.data))
-        self.last_outline_s = time.perf_counter() - t0  # the C-ABI call alone (scripts/bench_bodies.py)
+        _ck(self.L.fse_mask_outline(self.h, masks.ctypes.data, n, w, h, labels.ctypes.data if want_labels else None, ncomp.ctypes.data, pts.ctypes.data,
+                                    cap_pts, pt_off.ctypes.data, cap_c, mask_off.ctypes.data))
+        self.last_outline_s = time.perf_counter() - t0  # the C-ABI call alone
+        if not as_lists:
+            return labels, ncomp, (pts, pt_off, mask_off)
         contours = [[pts[pt_off[c]:pt_off[c + 1]].copy() for c in range(mask_off[m], mask_off[m + 1])] for m in range(n)]
         return labels, ncomp, contours
 

@@ -283,6 +283,145 @@ __device__ __noinline__ void body_pixel_act_fast(const BodyArgs& a, int b, int t
     }
 }
 
+// ---- fracture hand-off (world::updateRigidBodyHitbox, world.cpp:288-720, device part) ---------------------------------------------
+// A body whose pixels were carved apart becomes one body per piece.  One CTA per body: the solid mask (tile != AIR, the alpha test of
+// world.cpp:294-303) is labelled in shared memory (4-connected components by membership, north_star; the reference assigns pixels to
+// the nearest triangle centroid instead, world.cpp:587-610), every piece gets its bounding box (the crop of world.cpp:305-320 applied
+// to the piece, as the recursion at world.cpp:700-706 ends up doing), its pixel count and the weld flag (world.cpp:620), and its
+// tiles are gathered into a w x h array of their own (AIR where the box covers another piece).  Pieces are numbered by their first
+// pixel in row-major order.  Triangulation (TPPL) and the b2Body calls stay on the host.
+constexpr int SPLIT_MAX_PIXELS = 128 * 128;
+constexpr int SPLIT_MAX_PIECES = 1024;
+struct SplitArgs {
+    const fse_cell* tiles;  // body tiles, bw x bh
+    int bw, bh, air;
+    int weld_x, weld_y;
+    fse_body_piece* pieces;  // out
+    int cap_pieces;
+    fse_cell* tiles_out;
+    long long cap_tiles;
+    int* result;  // [0] pieces found, [1] tiles used, [2] overflow flags (1 pieces, 2 tiles)
+};
+__global__ void __launch_bounds__(256) bodies_split_kernel(SplitArgs a) {
+    extern __shared__ int split_smem[];
+    int* L = split_smem;                          // labels: root = lowest pixel index of the component, -1 = empty
+    int* box = split_smem + a.bw * a.bh;          // per piece: x0, y0, x1, y1, count, weld, root, tile offset (8 ints)
+    __shared__ int changed, n_roots, s_scan[256];
+    const int tid = threadIdx.x, n = a.bw * a.bh, w = a.bw, h = a.bh;
+    for (int i = tid; i < n; i += 256) L[i] = a.tiles[i].mat != a.air ? i : -1;
+    __syncthreads();
+    for (;;) {  // min-label propagation with pointer jumping
+        if (tid == 0) changed = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) {
+            const int l = L[i];
+            if (l < 0) continue;
+            const int x = i % w, y = i / w;
+            int best = l;
+            if (x + 1 < w && L[i + 1] >= 0) best = min(best, L[i + 1]);
+            if (x > 0 && L[i - 1] >= 0) best = min(best, L[i - 1]);
+            if (y + 1 < h && L[i + w] >= 0) best = min(best, L[i + w]);
+            if (y > 0 && L[i - w] >= 0) best = min(best, L[i - w]);
+            best = min(best, L[best]);
+            if (best < l) {
+                L[i] = best;
+                atomicMin(&L[l], best);
+                changed = 1;
+            }
+        }
+        __syncthreads();
+        if (!changed) break;
+        __syncthreads();
+    }
+    // number the roots in row-major order: per-thread counts over contiguous ranges, scanned across the CTA
+    const int per = (n + 255) / 256, lo = tid * per, hi = min(n, lo + per);
+    int mine = 0;
+    for (int i = lo; i < hi; i++) mine += L[i] == i;
+    s_scan[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int q = 0; q < 256; q++) {
+            const int v = s_scan[q];
+            s_scan[q] = acc;
+            acc += v;
+        }
+        n_roots = acc;
+    }
+    __syncthreads();
+    const int np = n_roots;
+    if (np > a.cap_pieces || np > SPLIT_MAX_PIECES) {
+        if (tid == 0) {
+            a.result[0] = np;
+            a.result[2] = 1;
+        }
+        return;
+    }
+    {
+        int k = s_scan[tid];
+        for (int i = lo; i < hi; i++)
+            if (L[i] == i) {
+                int* b = box + 8 * k;
+                b[0] = w; b[1] = h; b[2] = -1; b[3] = -1; b[4] = 0; b[5] = 0; b[6] = i; b[7] = 0;
+                k++;
+            }
+    }
+    __syncthreads();
+    // root -> piece number: the root pixel's own label slot is free to carry it (stored as -2 - piece; members still point at the root)
+    for (int k = tid; k < np; k += 256) L[box[8 * k + 6]] = -2 - k;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        int l = L[i];
+        if (l == -1) continue;
+        const int k = l <= -2 ? -2 - l : -2 - L[l];
+        int* b = box + 8 * k;
+        const int x = i % w, y = i / w;
+        atomicMin(&b[0], x); atomicMin(&b[1], y); atomicMax(&b[2], x); atomicMax(&b[3], y);
+        atomicAdd(&b[4], 1);
+        if (x == a.weld_x && y == a.weld_y) b[5] = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        long long off = 0;
+        for (int k = 0; k < np; k++) {
+            int* b = box + 8 * k;
+            b[7] = (int)off;
+            off += (long long)(b[2] - b[0] + 1) * (b[3] - b[1] + 1);
+        }
+        a.result[0] = np;
+        a.result[1] = (int)(off > 0x7fffffff ? 0x7fffffff : off);
+        a.result[2] = off > a.cap_tiles ? 2 : 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < np; k += 256) {
+        const int* b = box + 8 * k;
+        fse_body_piece pc;
+        pc.x0 = b[0]; pc.y0 = b[1]; pc.w = b[2] - b[0] + 1; pc.h = b[3] - b[1] + 1;
+        pc.n_pixels = b[4]; pc.weld = b[5]; pc.tile_off = b[7];
+        pc.shift_x = pc.shift_y = 0.0f;  // filled in by the host (sin / cos of the body angle on the host's libm, world.cpp:350-358)
+        a.pieces[k] = pc;
+    }
+    if (a.result[2]) return;
+    for (int k = 0; k < np; k++) {
+        const int* b = box + 8 * k;
+        const int pw = b[2] - b[0] + 1, ph = b[3] - b[1] + 1;
+        for (int c = tid; c < pw * ph; c += 256) {
+            const int x = b[0] + c % pw, y = b[1] + c / pw, i = x + y * w;
+            const int l = L[i];
+            const bool member = l != -1 && (l <= -2 ? -2 - l : -2 - L[l]) == k;
+            fse_cell t;
+            if (member) {
+                t = a.tiles[i];
+            } else {
+                memset(&t, 0, sizeof t);
+                t.mat = (uint16_t)a.air;
+                t.fluid = 2.0f;
+            }
+            a.tiles_out[b[7] + c] = t;
+        }
+    }
+}
+
 constexpr int BODY_TB = 128;
 constexpr int BODY_PPT = 8;   // pixels per thread kept in registers (bodies up to BODY_TB * BODY_PPT pixels)
 constexpr int BODY_SCLAIM = 64 * 64;  // cells of a footprint box whose claim map fits shared memory
@@ -619,5 +758,61 @@ extern "C" FSE_API int fse_bodies_read(fse_world* w, int32_t body, fse_cell* til
     fse_bodies* B = w->bodies;
     CK(cudaMemcpyAsync(tiles_out, B->d_tiles + B->off[body], sizeof(fse_cell) * (size_t)B->bw[body] * B->bh[body], cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
+    return FSE_OK;
+}
+
+extern "C" FSE_API int fse_bodies_split(fse_world* w, int32_t body, float angle, int32_t weld_x, int32_t weld_y, fse_body_piece* pieces, int32_t cap_pieces,
+                                        int32_t* n_pieces, fse_cell* tiles_out, int64_t cap_tiles) {
+    if (!w || !w->bodies || body < 0 || body >= w->bodies->n || !pieces || !n_pieces || !tiles_out || cap_pieces < 1 || cap_tiles < 1)
+        return fail(FSE_EINVAL, "fse_bodies_split: bad argument");
+    CK(cudaSetDevice(w->ctx->device));
+    fse_bodies* B = w->bodies;
+    const int bw = B->bw[body], bh = B->bh[body];
+    if ((long long)bw * bh > SPLIT_MAX_PIXELS) return fail(FSE_EINVAL, "fse_bodies_split: body of %d x %d pixels (at most %d)", bw, bh, SPLIT_MAX_PIXELS);
+    if (cap_pieces > SPLIT_MAX_PIECES) cap_pieces = SPLIT_MAX_PIECES;
+    const size_t o_tiles = ((sizeof(fse_body_piece) * (size_t)cap_pieces + 255) / 256) * 256, o_res = o_tiles + ((sizeof(fse_cell) * (size_t)cap_tiles + 255) / 256) * 256;
+    if (w->outline_scratch_bytes < o_res + 64) {
+        CK(cudaStreamSynchronize(w->stream));
+        cudaFree(w->outline_scratch);
+        w->outline_scratch = nullptr;
+        w->outline_scratch_bytes = 0;
+        CK(cudaMalloc(&w->outline_scratch, o_res + 64));
+        w->outline_scratch_bytes = o_res + 64;
+    }
+    char* base = (char*)w->outline_scratch;
+    SplitArgs a;
+    a.tiles = B->d_tiles + B->off[body];
+    a.bw = bw; a.bh = bh; a.air = w->ctx->h_tabs.air;
+    a.weld_x = weld_x; a.weld_y = weld_y;
+    a.pieces = (fse_body_piece*)base;
+    a.cap_pieces = cap_pieces;
+    a.tiles_out = (fse_cell*)(base + o_tiles);
+    a.cap_tiles = cap_tiles;
+    a.result = (int*)(base + o_res);
+    CK(cudaMemsetAsync(a.result, 0, 16, w->stream));
+    const size_t smem = sizeof(int) * ((size_t)bw * bh + 8 * (size_t)cap_pieces);
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(bodies_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (SPLIT_MAX_PIXELS + 8 * SPLIT_MAX_PIECES))));
+        configured = true;
+    }
+    bodies_split_kernel<<<1, 256, smem, w->stream>>>(a);
+    CK(cudaGetLastError());
+    w->ctx->launches += 1;
+    int res[4];
+    CK(cudaMemcpyAsync(res, a.result, 16, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    *n_pieces = res[0];
+    if (res[2] == 1) return fail(FSE_ENOMEM, "fse_bodies_split: %d pieces exceed the caller's capacity (%d)", res[0], cap_pieces);
+    if (res[2] == 2) return fail(FSE_ENOMEM, "fse_bodies_split: the pieces need %d tiles, the caller gave %lld", res[1], (long long)cap_tiles);
+    if (res[0] > 0) {
+        CK(cudaMemcpy(pieces, a.pieces, sizeof(fse_body_piece) * (size_t)res[0], cudaMemcpyDeviceToHost));
+        if (res[1] > 0) CK(cudaMemcpy(tiles_out, a.tiles_out, sizeof(fse_cell) * (size_t)res[1], cudaMemcpyDeviceToHost));
+    }
+    const float s = std::sin(angle), c = std::cos(angle);  // world.cpp:350-358: the crop moves the body by the rotated corner
+    for (int k = 0; k < res[0]; k++) {
+        pieces[k].shift_x = pieces[k].x0 * c - pieces[k].y0 * s;
+        pieces[k].shift_y = pieces[k].x0 * s + pieces[k].y0 * c;
+    }
     return FSE_OK;
 }

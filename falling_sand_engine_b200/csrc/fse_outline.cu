@@ -84,13 +84,21 @@ struct OutlineArgs {
     unsigned int* n_recs;
     unsigned int rec_cap;
     int* overflow;
+    int want_labels;   // copy the labels out (callers that only need contours and component counts skip 4 bytes per cell)
 };
 
-__global__ void ccl_kernel(OutlineArgs a) {
+// 4-connected component labels of one mask per CTA (label = lowest pixel index of the component, -1 = unset).  Masks of up to
+// CCL_SMEM_CELLS cells (every rigid body of config 4 and every 128 x 96 chunk crop) are labelled in shared memory and only the
+// finished labels go to HBM — and only when the caller asked for them; larger masks iterate on the global array.
+constexpr int CCL_SMEM_CELLS = 12288;
+__global__ void __launch_bounds__(256) ccl_kernel(OutlineArgs a) {
+    extern __shared__ int32_t ccl_smem[];
     const int m = blockIdx.x;
     const uint8_t* d = a.masks + (size_t)m * a.w * a.h;
-    int32_t* L = a.labels + (size_t)m * a.w * a.h;
     const int n = a.w * a.h, w = a.w, h = a.h;
+    const bool in_smem = n <= CCL_SMEM_CELLS;
+    int32_t* G = a.labels + (size_t)m * a.w * a.h;
+    int32_t* L = in_smem ? ccl_smem : G;
     __shared__ int changed;
     for (int i = threadIdx.x; i < n; i += blockDim.x) L[i] = d[i] ? i : -1;
     __syncthreads();
@@ -121,7 +129,10 @@ __global__ void ccl_kernel(OutlineArgs a) {
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
     int mine = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) mine += L[i] == i;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        mine += L[i] == i;
+        if (in_smem && a.want_labels) G[i] = L[i];
+    }
     atomicAdd(&cnt, mine);
     __syncthreads();
     if (threadIdx.x == 0) a.ncomp[m] = cnt;
@@ -337,7 +348,14 @@ extern "C" FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int3
     memcpy(pin, masks, total);
     CK(cudaMemcpyAsync(base + o_masks, pin, total, cudaMemcpyHostToDevice, w->stream));
     CK(cudaMemsetAsync(base + o_cnt, 0, 256, w->stream));
-    ccl_kernel<<<n_masks, 256, 0, w->stream>>>(a);
+    a.want_labels = labels != nullptr;
+    const size_t ccl_smem_bytes = per <= (size_t)CCL_SMEM_CELLS ? per * sizeof(int32_t) : 0;
+    static bool ccl_configured = false;
+    if (!ccl_configured) {
+        CK(cudaFuncSetAttribute(ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CCL_SMEM_CELLS * (int)sizeof(int32_t)));
+        ccl_configured = true;
+    }
+    ccl_kernel<<<n_masks, 256, ccl_smem_bytes, w->stream>>>(a);
     CK(cudaGetLastError());
     contour_kernel<<<(unsigned int)((total + 127) / 128), 128, 0, w->stream>>>(a);
     CK(cudaGetLastError());

@@ -564,8 +564,7 @@ __device__ __noinline__ void area_effects(const Ctx& c, Scratch1& R, int s, int 
 }
 
 template <int RN>
-__device__ void pass1_rows(const Ctx& c, Scratch1& R, int k, int cx, int cy, int t) {
-    const int s = slotk<RN>(c, k);
+__device__ void pass1_rows(const Ctx& c, Scratch1& R, int k, int s, int cx, int cy, int t) {  // s = slot of row k
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
     const int lane = t & 31;
@@ -742,8 +741,7 @@ __device__ void commit2(const Ctx& c, Scratch2& R, uint32_t d, int s, int j, int
 }
 
 template <int RN>
-__device__ void pass2_rows(const Ctx& c, Scratch2& R, int k, int cx, int cy, int t) {
-    const int s = slotk<RN>(c, k);
+__device__ void pass2_rows(const Ctx& c, Scratch2& R, int k, int s, int cx, int cy, int t) {  // s = slot of row k
     const int y = cy + c.yoff + CHUNK - 1 - k;
     const int par = k & 1;
     const int j = HX8 + t;
@@ -905,10 +903,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
             clk0 = max(max(a[0], a[1]), max(a[2], a[3]));
         }
         if (role == 0) {
-            if (st < CHUNK) pass1_rows<RING>(c, S.rs, st, cx, cy, t);
+            if (st < CHUNK) pass1_rows<RING>(c, S.rs, st, slotk<RING>(c, st), cx, cy, t);
         } else if (role == 1) {
             const int k = st - L12;
-            if (k >= 0 && k < CHUNK) pass2_rows<RING>(c, S.rs, k, cx, cy, t);
+            if (k >= 0 && k < CHUNK) pass2_rows<RING>(c, S.rs, k, slotk<RING>(c, k), cx, cy, t);
         } else if (role == 2) {
             const int k = st - L12 - L23;
             if (k >= 0 && k < CHUNK) pass3_rows<RING>(c, S.rs, k, cx, cy, lane);
@@ -1318,27 +1316,35 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
         int stop_row = kb;     // highest row that may still have to run
         bool ending = false;   // past the segment's last row: drain the stores, load nothing
         int seg_end = 0;
-        int nA = kb;           // next classified-active row >= st
+        // slots advance by one per step: kept as counters (the kernel is bound by dependent instructions, a modulo per use shows)
+        auto inc = [](int q) -> int { return q + 1 == G::RN ? 0 : q + 1; };
+        int qs = (-G::KMIN) % G::RN;                                    // slot of row st
+        int qw = (-G::KMIN + G::UP) % G::RN;                            // slot of row st + UP (the row that becomes live)
+        uint32_t pw = (uint32_t)(((-G::KMIN + G::UP) / G::RN) & 1);     // ... and its mbarrier parity
+        int qst = ((-G::KMIN - G::SL) % G::RN + G::RN) % G::RN;         // slot of row st - SL (stored this step)
+        int ql = (-G::KMIN + G::UP + G::PF) % G::RN;                    // slot of row st + UP + PF (loaded this step)
 #pragma unroll 1
         for (int st = kb;; st++) {
             const int kw = st + G::UP;
             // the IO warp never reads the row that is about to become live: only the compute warps wait for it
-            if (!io && kw <= G::LAST && (!ending || kw < seg_end + G::UP + G::PF)) mbar_wait(&S.bar[slot_of(kw)], par_of(kw));
+            if (!io && kw <= G::LAST && (!ending || kw < seg_end + G::UP + G::PF)) mbar_wait(&S.bar[qw], pw);
             fence_proxy_async();
             __syncthreads();
             bool run = false;
-            const int q = slot_of(st), qb = slot_of(st - 1);
+            const int q = qs, qb = qs == 0 ? G::RN - 1 : qs - 1;
             if (!ending) {
                 // run the row if it was classified active, or if an earlier step of this pass changed it or the row below it
                 run = st < CHUNK && (act_bit(st) || S.h.rowchg[q] || S.h.rowchg[qb]);
-                if (run && st + G::UP > stop_row) stop_row = st + G::UP;
-                if (nA <= st) nA = next_act(st + 1);
-                int need_hi = stop_row;
-                if (!jumps) need_hi = G::LAST;
-                else if (nA < CHUNK && nA - st <= SEG_GAP && nA > need_hi) need_hi = nA;
-                if (st > need_hi) {
-                    ending = true;
-                    seg_end = st;
+                if (run) {
+                    if (st + G::UP > stop_row) stop_row = st + G::UP;
+                } else if (st > stop_row) {  // nothing can run here any more unless a classified row follows closely
+                    const int nA = jumps ? next_act(st + 1) : CHUNK;
+                    if (!jumps && st <= G::LAST) stop_row = G::LAST;
+                    else if (nA < CHUNK && nA - st <= SEG_GAP) stop_row = nA;
+                    else {
+                        ending = true;
+                        seg_end = st;
+                    }
                 }
             }
             if (!io) {
@@ -1350,7 +1356,7 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                         if (lo < st - 5) lo = st - 5;
                         if (lo < 0) lo = 0;  // rows below the chunk belong to other chunks: never marked from here
                         for (int r = lo; r < st; r++) materialize_marks(c, slot_of(r), j);
-                        pass1_rows<G::RN>(c, reinterpret_cast<Scratch1&>(S.rs), st, cx, cy, tid);
+                        pass1_rows<G::RN>(c, reinterpret_cast<Scratch1&>(S.rs), st, q, cx, cy, tid);
                     } else {
                         // rows st - 1 .. st + 1 are the ones this row can write: implicit pass-1 marks become real ones first
                         int lo = last_run + 2;  // rows up to last_run + 1 were handled by that step
@@ -1358,7 +1364,7 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                         if (lo < 0) lo = 0;
                         for (int r = lo; r <= st + 1 && r < CHUNK; r++)
                             if ((S.m_lazy[r >> 5] >> (r & 31)) & 1u) materialize_marks(c, slot_of(r), j);
-                        pass2_rows<G::RN>(c, reinterpret_cast<Scratch2&>(S.rs), st, cx, cy, tid);
+                        pass2_rows<G::RN>(c, reinterpret_cast<Scratch2&>(S.rs), st, q, cx, cy, tid);
                     }
                     last_run = st;
                 } else if (!ending && st < CHUNK) {
@@ -1387,15 +1393,15 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
             } else {
                 const int ks = st - G::SL;
                 if (io_store && ks >= kb + G::FULL_LO && ks <= G::LAST) {
-                    const int qs = slot_of(ks);
-                    uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + qs * ROW_BYTES + OFF_FLG);
+                    const int qs_ = qst;
+                    uint32_t* fw = reinterpret_cast<uint32_t*>(S.ring + qs_ * ROW_BYTES + OFF_FLG);
                     const bool core_row = ks >= 0 && ks < CHUNK;
-                    const bool all_store = S.h.rowmod[qs] != 0;
-                    const bool vis_store = S.h.rowvis[qs] != 0;
+                    const bool all_store = S.h.rowmod[qs_] != 0;
+                    const bool vis_store = S.h.rowvis[qs_] != 0;
                     if (PASS == 2 && gmask && core_row && (all_store || vis_store) && lane == (ks >> 5)) io_lazy |= 1u << (ks & 31);
                     if (PASS == 1 && gmask) {
-                        if (core_row && !(S.h.rowlazy[qs] && !all_store && !vis_store) && lane == (ks >> 5)) io_lazy &= ~(1u << (ks & 31));
-                        if (S.h.rowchg[qs]) {  // pass 2 reads a row's own cells and the row below them
+                        if (core_row && !(S.h.rowlazy[qs_] && !all_store && !vis_store) && lane == (ks >> 5)) io_lazy &= ~(1u << (ks & 31));
+                        if (S.h.rowchg[qs_]) {  // pass 2 reads a row's own cells and the row below them
                             if (core_row && lane == (ks >> 5)) io_chg |= 1u << (ks & 31);
                             if (ks + 1 >= 0 && ks + 1 < CHUNK && lane == ((ks + 1) >> 5)) io_chg |= 1u << ((ks + 1) & 31);
                         }
@@ -1410,14 +1416,14 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                         }
                     }
                     if (P.chunk_state) {
-                        io_modified |= S.h.rowchg[qs] != 0;
+                        io_modified |= S.h.rowchg[qs_] != 0;
                         // rows are final for passes 1 and 2 here; pass 3 only moves GAS, which is never inert anyway
-                        if (PASS == 2 && core_row) io_inert &= row_is_inert(c, qs, rsn<G::RN>(qs, 1), lane);
+                        if (PASS == 2 && core_row) io_inert &= row_is_inert(c, qs_, rsn<G::RN>(qs_, 1), lane);
                     }
                     fence_proxy_async();
                     __syncwarp();
                     if (all_store ? lane < 7 : (vis_store && lane == 1))
-                        bulk_s2g(pio.g + (size_t)(cy + CHUNK - 1 - ks) * pio.row_stride, S.ring + qs * ROW_BYTES + pio.soff, pio.bytes);
+                        bulk_s2g(pio.g + (size_t)(cy + CHUNK - 1 - ks) * pio.row_stride, S.ring + qs_ * ROW_BYTES + pio.soff, pio.bytes);
                 }
                 const int kl = st + G::UP + G::PF;
                 const bool load = !ending && kl <= G::LAST;
@@ -1430,9 +1436,14 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                         else bulk_wait_read<0>();
                     }
                 }
-                if (io_load && load) pass_row_load<PASS>(S, pio, lane, kl, cy, slot_of(kl), kb);
+                if (io_load && load) pass_row_load<PASS>(S, pio, lane, kl, cy, ql, kb);
             }
             if (ending && st >= seg_end + G::SL - 1) break;
+            qs = inc(qs);
+            qst = inc(qst);
+            ql = inc(ql);
+            qw = inc(qw);
+            if (qw == 0) pw ^= 1u;
         }
         // rows at and above the segment's end: the next classified-active one starts the next segment
         const int nxt = jumps ? next_act(seg_end) : CHUNK;

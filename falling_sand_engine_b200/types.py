@@ -107,6 +107,11 @@ PARTICLE_DTYPE = np.dtype(
 ENTITY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("vx", "<f4"), ("vy", "<f4"), ("hw", "<i4"), ("hh", "<i4"), ("ground", "<i4"), ("destroy", "<i4")])
 
 
+# fse_body_piece (36 bytes)
+BODY_PIECE_DTYPE = np.dtype([("x0", "<i4"), ("y0", "<i4"), ("w", "<i4"), ("h", "<i4"), ("n_pixels", "<i4"), ("weld", "<i4"), ("tile_off", "<i4"),
+                             ("shift_x", "<f4"), ("shift_y", "<f4")])
+
+
 def zone_of(width, height):
     """tickZone of the reference: the grid minus a one-chunk border (game.cpp:1629)."""
     return Rect(FSE_CHUNK, FSE_CHUNK, width - 2 * FSE_CHUNK, height - 2 * FSE_CHUNK)

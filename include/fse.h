@@ -266,6 +266,23 @@ FSE_API int fse_bodies_raster(fse_world* w, const fse_xform* xf, int32_t n, uint
 FSE_API int fse_bodies_erase(fse_world* w, const fse_xform* xf, int32_t n, fse_body_feedback* out, uint8_t* needs_update);
 FSE_API int fse_bodies_read(fse_world* w, int32_t body, fse_cell* tiles_out);
 
+/* Fracture hand-off (world::updateRigidBodyHitbox, world.cpp:288-720): an uploaded body whose pixels were carved apart is cut into
+ * one piece per 4-connected component of its non-AIR tiles (north_star: connected-component labelling; the reference assigns pixels
+ * by nearest triangle centroid, world.cpp:587-610).  Per piece: bounding box inside the body's tile array (the crop of world.cpp:
+ * 305-320), pixel count, whether it holds the weld pixel (world.cpp:620), the position shift of the new body (the rotated box
+ * corner, world.cpp:350-362; angle = b2Body::GetAngle) and its own w x h tile array in tiles_out (AIR where the box covers another
+ * piece).  Pieces are numbered by their first pixel in row-major order.  The host feeds each piece's mask to fse_mask_outline for
+ * the TPPL / b2PolygonShape step and creates the bodies (pose, velocities and weld copied as in world.cpp:657-707). */
+typedef struct fse_body_piece {
+    int32_t x0, y0, w, h;
+    int32_t n_pixels;
+    int32_t weld;
+    int32_t tile_off;         /* first tile of the piece in tiles_out */
+    float shift_x, shift_y;
+} fse_body_piece;
+FSE_API int fse_bodies_split(fse_world* w, int32_t body, float angle, int32_t weld_x, int32_t weld_y, fse_body_piece* pieces, int32_t cap_pieces,
+                             int32_t* n_pieces, fse_cell* tiles_out, int64_t cap_tiles);
+
 /* `world::explosion(cx, cy, radius)` (world.cpp:2294-2332): every non-AIR cell within `radius` of (cx, cy) is removed — SOLID
  * cells and 6 in 10 of the others vanish, the rest leave as loose particles (colour darkened to a quarter, spawned one cell
  * lower, thrown outward) — and every non-SOLID cell of the ring out to 2*radius is thrown outward as a particle.  Cells decide

@@ -478,6 +478,53 @@ OAPI int fseo_outlines(const uint8_t* data, int w, int h, float* pts, int cap_pt
     return (int)out.size();
 }
 OAPI int fseo_ccl(const uint8_t* data, int w, int h, int32_t* labels) { return ccl(data, w, h, labels); }
+
+// Fracture hand-off restated on the CPU (world::updateRigidBodyHitbox, world.cpp:288-720, with 4-connected membership instead of
+// the nearest-centroid assignment of 587-610): per component, in the order of its first pixel, the cropped tile array (305-320),
+// the weld flag (620) and the rotated shift of the box corner (350-362).  Returns the number of pieces; -1 on overflow.
+OAPI int fseo_body_split(const fse_cell* tiles, int bw, int bh, int air, float angle, int weld_x, int weld_y, fse_body_piece* pieces, int cap_pieces,
+                         fse_cell* tiles_out, long cap_tiles) {
+    std::vector<uint8_t> mask((size_t)bw * bh);
+    for (int i = 0; i < bw * bh; i++) mask[i] = tiles[i].mat != air;
+    std::vector<int32_t> labels((size_t)bw * bh);
+    ccl(mask.data(), bw, bh, labels.data());
+    int n = 0;
+    long off = 0;
+    const float s = std::sin(angle), c = std::cos(angle);
+    for (int root = 0; root < bw * bh; root++) {
+        if (labels[root] != root) continue;
+        if (n >= cap_pieces) return -1;
+        int x0 = bw, y0 = bh, x1 = -1, y1 = -1, cnt = 0, weld = 0;
+        for (int i = 0; i < bw * bh; i++) {
+            if (labels[i] != root) continue;
+            const int x = i % bw, y = i / bw;
+            x0 = std::min(x0, x); y0 = std::min(y0, y); x1 = std::max(x1, x); y1 = std::max(y1, y);
+            cnt++;
+            if (x == weld_x && y == weld_y) weld = 1;
+        }
+        fse_body_piece& pc = pieces[n++];
+        pc.x0 = x0; pc.y0 = y0; pc.w = x1 - x0 + 1; pc.h = y1 - y0 + 1;
+        pc.n_pixels = cnt; pc.weld = weld; pc.tile_off = (int32_t)off;
+        pc.shift_x = x0 * c - y0 * s;
+        pc.shift_y = x0 * s + y0 * c;
+        if (off + (long)pc.w * pc.h > cap_tiles) return -1;
+        for (int y = 0; y < pc.h; y++)
+            for (int x = 0; x < pc.w; x++) {
+                const int i = (x0 + x) + (y0 + y) * bw;
+                fse_cell t;
+                if (labels[i] == root) {
+                    t = tiles[i];
+                } else {
+                    std::memset(&t, 0, sizeof t);
+                    t.mat = (uint16_t)air;
+                    t.fluid = 2.0f;
+                }
+                tiles_out[off + x + (long)y * pc.w] = t;
+            }
+        off += (long)pc.w * pc.h;
+    }
+    return n;
+}
 OAPI int fseo_flood_component(void* p, int x, int y, int cap, int* bbox, int32_t* pixels) {
     return flood_component((World*)p, x, y, cap, bbox, pixels);
 }

@@ -315,6 +315,19 @@ def outlines(mask):
     return [pts[off[k]:off[k + 1]].copy() for k in range(n)]
 
 
+def body_split(tiles, angle=0.0, weld=(-1, -1), air=0):
+    """Fracture hand-off of one body (tiles: (h, w) CELL_DTYPE): list of (piece record, (h', w') tile array)."""
+    tiles = np.ascontiguousarray(tiles, dtype=T.CELL_DTYPE)
+    h, w = tiles.shape
+    pieces = np.zeros(1024, dtype=T.BODY_PIECE_DTYPE)
+    out = np.zeros(4 * h * w + 64, dtype=T.CELL_DTYPE)
+    lib().fseo_body_split.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_long]
+    n = lib().fseo_body_split(tiles.ctypes.data, w, h, air, angle, weld[0], weld[1], pieces.ctypes.data, len(pieces), out.ctypes.data, len(out))
+    assert n >= 0
+    return [(pieces[k].copy(), out[pieces[k]["tile_off"]: pieces[k]["tile_off"] + pieces[k]["w"] * pieces[k]["h"]].reshape(pieces[k]["h"], pieces[k]["w"]).copy())
+            for k in range(n)]
+
+
 def ccl(mask):
     mask = np.ascontiguousarray(mask, dtype=np.uint8)
     h, w = mask.shape

@@ -223,3 +223,34 @@ def test_body_pixels_with_overlapping_footprints_are_within_the_7x7_stencil():
             a = {(px, py) for px, py in plus}
             b = {(dx + px, dy + py) for px, py in plus}
             assert bool(a & b) == (abs(dx) + abs(dy) <= 2), (dx, dy)
+
+
+def test_body_split_cracked_plate(oracle, table):
+    """Fracture hand-off (world::updateRigidBodyHitbox, world.cpp:288-720) on the oracle: a 40 x 24 plate cut by a one-pixel crack and
+    with a loose crumb gives three pieces in first-pixel order; each is cropped to its bounding box (305-320), the pieces' tiles
+    union to the original plate pixel for pixel, the weld pixel flags exactly one piece (620) and the shift is the rotated box
+    corner (350-362)."""
+    plate = make_body(table, 40, 24, fill=1.0)
+    plate["mat"][:, 17] = 0            # the crack
+    plate["mat"][3:6, 25:28] = 0       # a hole with ...
+    plate["mat"][4, 26] = 22           # ... a crumb inside
+    plate["color"] = np.arange(24 * 40, dtype=np.uint32).reshape(24, 40) + 7
+    angle = 0.3
+    pieces = oracle.body_split(plate, angle=angle, weld=(30, 20))
+    assert len(pieces) == 3
+    recs = [p for p, _ in pieces]
+    assert [(int(r["x0"]), int(r["y0"]), int(r["w"]), int(r["h"])) for r in recs] == [(0, 0, 17, 24), (18, 0, 22, 24), (26, 4, 1, 1)]
+    assert [int(r["weld"]) for r in recs] == [0, 1, 0]
+    assert [int(r["n_pixels"]) for r in recs] == [17 * 24, 22 * 24 - 9, 1]
+    back = np.zeros_like(plate)
+    back["fluid"] = 2.0
+    for r, t in pieces:
+        sel = t["mat"] != 0
+        view = back[r["y0"]:r["y0"] + r["h"], r["x0"]:r["x0"] + r["w"]]
+        view[sel] = t[sel]
+        assert np.isclose(r["shift_x"], r["x0"] * np.cos(angle) - r["y0"] * np.sin(angle), atol=1e-5)
+        assert np.isclose(r["shift_y"], r["x0"] * np.sin(angle) + r["y0"] * np.cos(angle), atol=1e-5)
+    want = plate.copy()
+    for f in Hh.FIELDS:
+        assert np.array_equal(back[f][plate["mat"] != 0], want[f][plate["mat"] != 0]), f
+    assert (back["mat"][plate["mat"] == 0] == 0).all()

@@ -237,3 +237,28 @@ def test_scroll_exact(oracle, gpu_ctx, table, dx, dy):
     ow.tick(1)
     gw.tick(1)
     Hh.assert_cells_equal(ow.read_all(), gw.read_all(), "tick after scroll")
+
+
+def test_bodies_split_matches_oracle(oracle, gpu_ctx, table):
+    """fse_bodies_split on uploaded bodies: a cracked plate, a body with hashed holes (dozens of crumbs) and an intact one; pieces,
+    crop boxes, weld flags, shifts and tile arrays equal the oracle's; the pieces of the plate union to the plate."""
+    gpu_ctx.set_materials(table)
+    gw = fse.World(gpu_ctx, 512, 384)
+    plate = make_body(table, 40, 24, fill=1.0)
+    plate["mat"][:, 17] = 0
+    plate["mat"][3:6, 25:28] = 0
+    plate["mat"][4, 26] = 22
+    bodies = [plate, make_body(table, 64, 48, seed=9, fill=0.55), make_body(table, 16, 16, seed=2, fill=1.0), make_body(table, 128, 128, seed=4, fill=0.62)]
+    gw.bodies_upload(bodies)
+    for i, b in enumerate(bodies):
+        want = oracle.body_split(b, angle=0.3 * i, weld=(5, 5))
+        got = gw.bodies_split(i, angle=0.3 * i, weld=(5, 5))
+        assert len(want) == len(got), i
+        for (rw, tw), (rg, tg) in zip(want, got):
+            for f in ("x0", "y0", "w", "h", "n_pixels", "weld", "tile_off"):
+                assert rw[f] == rg[f], (i, f)
+            assert abs(rw["shift_x"] - rg["shift_x"]) < 1e-4 and abs(rw["shift_y"] - rg["shift_y"]) < 1e-4
+            assert tw.tobytes() == tg.tobytes(), i
+    got = gw.bodies_split(0)
+    assert len(got) == 3 and sum(int((t["mat"] != 0).sum()) for _, t in got) == int((plate["mat"] != 0).sum())
+    gw.close()
