@@ -1094,8 +1094,10 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(tick_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemRows));
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(tick_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        e = cudaFuncSetAttribute(tick_pass_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tick_pass_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -1123,8 +1125,13 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
                 classify_rows_kernel<<<(hi - lo) * 4, 1024, sizeof(Lut), st>>>(Q);
                 *launched += 1;
             }
-            tick_pass_kernel<1><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>) + pad, st>>>(Q);
-            tick_pass_kernel<2><<<hi - lo, PassGeom<2>::THREADS, sizeof(SmemPass<2>) + pad, st>>>(Q);
+            if (Q.rowmask) {
+                tick_pass_kernel<1, true><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>) + pad, st>>>(Q);
+                tick_pass_kernel<2, true><<<hi - lo, PassGeom<2>::THREADS, sizeof(SmemPass<2>) + pad, st>>>(Q);
+            } else {
+                tick_pass_kernel<1, false><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>) + pad, st>>>(Q);
+                tick_pass_kernel<2, false><<<hi - lo, PassGeom<2>::THREADS, sizeof(SmemPass<2>) + pad, st>>>(Q);
+            }
             tick_pass3_kernel<<<(hi - lo) * (CHUNK / 4), 128, 0, st>>>(Q);
             *launched += 3;
         }

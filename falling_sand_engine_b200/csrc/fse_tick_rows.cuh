@@ -1180,7 +1180,9 @@ __global__ void __launch_bounds__(1024) classify_rows_kernel(const __grid_consta
 
 // One pass over one chunk by the whole CTA (4 compute warps + IO warp).  The material LUT is already in shared memory; scratch,
 // mbarriers and the context are (re)initialised here.  On return every bulk store of the pass has completed.
-template <int PASS>
+// SKIP = false: the instantiation without row masks (every row is stepped, one segment); the skip gate of fse_tick picks it for phases
+// where too few rows are settled to pay for the classification — none of the mask bookkeeping is compiled into it.
+template <int PASS, bool SKIP>
 __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, int iter, uint32_t rkey, unsigned int* cost_slot, int mask_idx) {
     using G = PassGeom<PASS>;
     unsigned char* const smem_raw = fse_smem;
@@ -1191,7 +1193,7 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     const long long t_begin = (PASS == 1 && cost_slot) ? clock64() : 0;
     const DevTables* T = P.tabs;
     // settled-row skipping (see classify_rows_kernel): the rows this pass must run; a chunk without any is done
-    uint32_t* const gmask = P.rowmask ? P.rowmask + (size_t)mask_idx * ROWMASK_WORDS : nullptr;
+    uint32_t* const gmask = (SKIP && P.rowmask) ? P.rowmask + (size_t)mask_idx * ROWMASK_WORDS : nullptr;
     if (gmask) {
         const uint32_t* ga = gmask + (PASS == 1 ? 0 : 4);
         const uint32_t a0 = ga[0], a1 = ga[1], a2 = ga[2], a3 = ga[3];
@@ -1255,7 +1257,7 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     // masks there is one segment, rows 0 .. 127.
     constexpr int SEG_GAP = 16;
     static_assert(SEG_GAP >= -G::KMIN + G::UP + G::PF + 1, "a new segment's window must not overlap rows the previous one had in flight");
-    const bool jumps = gmask != nullptr && !P.chunk_state;
+    const bool jumps = SKIP && gmask != nullptr && !P.chunk_state;
     auto act_bit = [&](int k) -> bool { return (S.m_act[k >> 5] >> (k & 31)) & 1u; };
     auto next_act = [&](int k) -> int {  // first active row >= k, CHUNK if none
         while (k < CHUNK) {
@@ -1334,7 +1336,7 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
             const int q = qs, qb = qs == 0 ? G::RN - 1 : qs - 1;
             if (!ending) {
                 // run the row if it was classified active, or if an earlier step of this pass changed it or the row below it
-                run = st < CHUNK && (act_bit(st) || S.h.rowchg[q] || S.h.rowchg[qb]);
+                run = st < CHUNK && (!SKIP || act_bit(st) || S.h.rowchg[q] || S.h.rowchg[qb]);
                 if (run) {
                     if (st + G::UP > stop_row) stop_row = st + G::UP;
                 } else if (st > stop_row) {  // nothing can run here any more unless a classified row follows closely
@@ -1352,18 +1354,22 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                     const int j = HX8 + tid;
                     if (PASS == 1) {
                         // rows skipped since the last running row, as far down as this row can write (5 rows): marks in place first
-                        int lo = last_run + 1;
-                        if (lo < st - 5) lo = st - 5;
-                        if (lo < 0) lo = 0;  // rows below the chunk belong to other chunks: never marked from here
-                        for (int r = lo; r < st; r++) materialize_marks(c, slot_of(r), j);
+                        if (SKIP) {
+                            int lo = last_run + 1;
+                            if (lo < st - 5) lo = st - 5;
+                            if (lo < 0) lo = 0;  // rows below the chunk belong to other chunks: never marked from here
+                            for (int r = lo; r < st; r++) materialize_marks(c, slot_of(r), j);
+                        }
                         pass1_rows<G::RN>(c, reinterpret_cast<Scratch1&>(S.rs), st, q, cx, cy, tid);
                     } else {
                         // rows st - 1 .. st + 1 are the ones this row can write: implicit pass-1 marks become real ones first
-                        int lo = last_run + 2;  // rows up to last_run + 1 were handled by that step
-                        if (lo < st - 1) lo = st - 1;
-                        if (lo < 0) lo = 0;
-                        for (int r = lo; r <= st + 1 && r < CHUNK; r++)
-                            if ((S.m_lazy[r >> 5] >> (r & 31)) & 1u) materialize_marks(c, slot_of(r), j);
+                        if (SKIP) {
+                            int lo = last_run + 2;  // rows up to last_run + 1 were handled by that step
+                            if (lo < st - 1) lo = st - 1;
+                            if (lo < 0) lo = 0;
+                            for (int r = lo; r <= st + 1 && r < CHUNK; r++)
+                                if ((S.m_lazy[r >> 5] >> (r & 31)) & 1u) materialize_marks(c, slot_of(r), j);
+                        }
                         pass2_rows<G::RN>(c, reinterpret_cast<Scratch2&>(S.rs), st, q, cx, cy, tid);
                     }
                     last_run = st;
@@ -1465,7 +1471,7 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     if (io_store) bulk_wait_all();
 }
 
-template <int PASS>
+template <int PASS, bool SKIP>
 __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_pass_kernel(const __grid_constant__ TickParams P) {
     const int tid = threadIdx.x;
     int cxi, cyi;
@@ -1486,7 +1492,7 @@ __global__ void __launch_bounds__(PassGeom<PASS>::THREADS, FSE_PASS_MINB) tick_p
         uint4* dst = reinterpret_cast<uint4*>(fse_smem);
         for (int i = tid; i < (int)(sizeof(Lut) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    run_pass<PASS>(P, cx, cy, P.iter, P.rkey, (PASS == 1 && P.chunk_cost) ? P.chunk_cost + cyi * P.ncx + cxi : nullptr, cyi * P.ncx + cxi);
+    run_pass<PASS, SKIP>(P, cx, cy, P.iter, P.rkey, (PASS == 1 && P.chunk_cost) ? P.chunk_cost + cyi * P.ncx + cxi : nullptr, cyi * P.ncx + cxi);
 }
 
 // ---- pass 3 on global memory: one warp per chunk row, lane l owns columns 4l..4l+3 (world.cpp:1828-1891) ---------------------

@@ -77,7 +77,7 @@ private:
 // Mirror of the reference's `class world` for the tick path.
 class world {
 public:
-    uint16_t width = 0, height = 0;  // world.hpp:121-122 (the C ABI itself takes int32)
+    int32_t width = 0, height = 0;   // world.hpp:121-122 has u16; the C ABI takes int32 and so does this shim (65536-wide worlds)
     fse_rect tickZone{};             // world.hpp zone; game.cpp:1629 keeps it one chunk inside the grid
     uint32_t tickCt = 0;
     uint32_t seed = 1337;            // replaces srand(time(NULL)) (game_utils/rng.cpp:9)
@@ -86,8 +86,8 @@ public:
     // world::init(path, w, h, ...) (world.cpp:43-172)
     void init(Context& ctx, int w, int h) {
         check(fse_world_create(ctx.handle(), w, h, &h_));
-        width = (uint16_t)w;
-        height = (uint16_t)h;
+        width = w;
+        height = h;
         tickZone = {FSE_CHUNK, FSE_CHUNK, w - 2 * FSE_CHUNK, h - 2 * FSE_CHUNK};
     }
     ~world() { fse_world_destroy(h_); }
@@ -154,6 +154,35 @@ public:
         check(fse_render_dirty(h_, movingTiles));
         check(fse_clear_dirty(h_));
     }
+    // world::tickEntities (world.cpp:3010-3247), WorldEntitySystem::process (game/player.cpp:173-199), objectDelete (game.cpp:2128-2139)
+    void tickEntities(std::vector<fse_entity>& ents) {
+        if (!ents.empty()) check(fse_entities_tick(h_, ents.data(), (int)ents.size(), loadZoneX, loadZoneY, tickCt, seed));
+    }
+    void stampEntities(const std::vector<fse_entity>& ents, int objectMat = 6) {
+        if (!ents.empty()) check(fse_entities_stamp(h_, ents.data(), (int)ents.size(), loadZoneX, loadZoneY, objectMat, tickCt, seed));
+    }
+    void objectDelete() { check(fse_object_delete(h_)); }
+    float loadZoneX = 0, loadZoneY = 0;  // world::loadZone.x / .y
+
+    // One game tick in the order of game::tick (game.cpp:1659-2201): body raster (1711-1815), tickEntities (1820), entity
+    // stamping (1835), world tick (1838), tickCells (1878-1886, joined at 1892), body erase (1896-1983), tickTemperature on
+    // tick % GameTick == 2 (2157), objectDelete (2128-2139), dirty -> textures + dirty clear (1994-2060, 2153).  `damp` receives the
+    // velocity factors of the raster pass; Box2D itself (world.cpp:2264-2276) is the caller's, between two calls.
+    template <class Damp>
+    void gameTick(const std::vector<fse_xform>& bodies, std::vector<fse_entity>& ents, Damp damp, fse_render_stats* movingTiles = nullptr) {
+        std::vector<uint8_t> needsUpdate;
+        if (!bodies.empty()) rasterBodies(bodies, damp);
+        tickEntities(ents);
+        stampEntities(ents);
+        const uint32_t t = tickCt;
+        tick();  // advances tickCt
+        tickCells();
+        if (!bodies.empty()) eraseBodies(bodies, needsUpdate);
+        if (t % 4 == 2) tickTemperature();
+        objectDelete();
+        renderDirty(movingTiles);
+    }
+    void stats(fse_stats* out) { check(fse_stats_rect(h_, 0, 0, width, height, out)); }
     void sync() { check(fse_sync(h_)); }
     fse_world* handle() const { return h_; }
 

@@ -161,9 +161,12 @@ def register_material(table, physics, slipperyness, alpha, density, iterations, 
 # ---- Lua front door -----------------------------------------------------------------------------------------------------
 # The reference binds three globals for scripts (game_basic.cpp:79-81): materials_init(), materials_register(s_id, name,
 # index_name, physicsType, slipperyness, alpha, density, iterations, emit, emitColor, color) and materials_push()
-# (gds.cpp:117, 282, 291).  A Lua VM is not part of this package (the reference's vendored Lua 5.4 sources do not travel); the
-# declarative subset scripts use for material tables — those three calls with literal arguments, plain `name = literal`
-# assignments used as arguments, and comments — is read here.  Anything else in the script is ignored.
+# (gds.cpp:117, 282, 291).  Scripts run on a real Lua 5.4 VM: csrc/lua_front.c on the reference's vendored Lua 5.4.4, built into
+# libfse_lua.so by csrc/Makefile.lua (lua_run / load_lua(engine="vm")); loops, functions, tables and the `global_def` settings table
+# (cvar.cpp:57-99) work as in the game.  Without that library (it is a built artefact: present wherever __graft_entry__.build() ran
+# with the reference tree at hand, and on the GPU box through the snapshot) load_lua falls back to reading the declarative subset —
+# the three calls with literal arguments, plain `name = literal` assignments, comments — and ignores everything else.
+import os  # noqa: E402
 import re  # noqa: E402
 
 _LUA_CALL = re.compile(r"\b(materials_init|materials_register|materials_push)\s*\(([^()]*)\)")
@@ -194,10 +197,77 @@ def _lua_literal(tok, env):
         return float(tok)
 
 
-def load_lua(source, seed=1337):
+class LuaMaterial(C.Structure):  # fse_lua_material (csrc/lua_front.c)
+    _fields_ = [("s_id", C.c_int32), ("name", C.c_char * 64), ("index_name", C.c_char * 64), ("physics_type", C.c_int32), ("slipperyness", C.c_int32),
+                ("alpha", C.c_int32), ("density", C.c_float), ("iterations", C.c_int32), ("emit", C.c_int32), ("emit_color", C.c_uint32), ("color", C.c_uint32)]
+
+
+class LuaResult(C.Structure):  # fse_lua_result
+    _fields_ = [("n_init", C.c_int32), ("n_register", C.c_int32), ("n_push", C.c_int32), ("has_global_def", C.c_int32), ("cell_iter", C.c_int32),
+                ("brush_size", C.c_int32), ("tick_world", C.c_int32), ("tick_box2d", C.c_int32), ("tick_temperature", C.c_int32), ("error", C.c_char * 256)]
+
+
+_LUA_LIB = None
+
+
+def lua_library():
+    """libfse_lua.so (Lua 5.4 VM + front-door shim) or None when it was not built."""
+    global _LUA_LIB
+    if _LUA_LIB is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfse_lua.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.fse_lua_run.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(LuaMaterial), C.c_int, C.POINTER(LuaResult)]
+        L.fse_lua_version.restype = C.c_char_p
+        _LUA_LIB = L
+    return _LUA_LIB
+
+
+def lua_run(source, is_file=False, entry="OnGameEngineLoad", cap=1024):
+    """Run a script on the VM the way the reference boots its scripts (load, then call OnGameEngineLoad, game_basic.cpp:60-61).
+    Returns (list of registered LuaMaterial records, LuaResult)."""
+    L = lua_library()
+    if L is None:
+        raise RuntimeError("libfse_lua.so is missing: make -C falling_sand_engine_b200/csrc -f Makefile.lua (needs the reference tree)")
+    out = (LuaMaterial * cap)()
+    res = LuaResult()
+    rc = L.fse_lua_run(source.encode(), 1 if is_file else 0, (entry or "").encode(), out, cap, C.byref(res))
+    if rc != 0:
+        raise ValueError("lua: " + res.error.decode(errors="replace"))
+    if res.n_register > cap:
+        raise ValueError(f"the script registers {res.n_register} materials, capacity {cap}")
+    return [out[i] for i in range(res.n_register)], res
+
+
+def load_global_def(source, is_file=False):
+    """The settings the reference reads back from the scripts' `global_def` table (cvar.cpp:57-99): cell_iter, brush_size, tick_*."""
+    _, res = lua_run(source, is_file=is_file, entry=None)
+    if not res.has_global_def:
+        raise ValueError("the script defines no global_def table")
+    return {"cell_iter": res.cell_iter, "brush_size": res.brush_size, "tick_world": res.tick_world, "tick_box2d": res.tick_box2d,
+            "tick_temperature": res.tick_temperature}
+
+
+def load_lua(source, seed=1337, engine="auto"):
     """Material table from a Lua script: materials_init() gives the stock table (default_materials), every materials_register(...)
     appends one material (arguments as in gds.cpp:282; physicsType is a number or one of AIR / SOLID / SAND / SOUP / GAS / PASSABLE /
-    OBJECT), materials_push() ends it.  Returns (table, {s_id or name: material id}) ready for Context.set_materials."""
+    OBJECT), materials_push() ends it.  Returns (table, {s_id or name: material id}) ready for Context.set_materials.
+    engine: "vm" (the Lua VM, required), "declarative" (literal calls only, no VM) or "auto" (the VM when libfse_lua.so exists)."""
+    if engine not in ("auto", "vm", "declarative"):
+        raise ValueError(f"engine {engine!r}")
+    if engine == "vm" or (engine == "auto" and lua_library() is not None):
+        recs, res = lua_run(source)
+        if res.n_init == 0:
+            raise ValueError("the script never calls materials_init()")
+        if res.n_push == 0:
+            raise ValueError("the script never calls materials_push()")
+        table, ids = default_materials(seed), {}
+        for r in recs:
+            table, mid = register_material(table, r.physics_type, r.slipperyness, r.alpha, r.density, r.iterations, r.emit, r.emit_color, r.color)
+            ids[r.s_id] = mid
+            ids[r.name.decode()] = mid
+        return table, ids
     src = _lua_strip_comments(source)
     env = {}
     for m in _LUA_ASSIGN.finditer(src):

@@ -143,6 +143,23 @@ class MaterialTable:
             self.react_offsets,
         )
 
+    def dump(self, path):
+        """Raw dump for a C++ host (csrc/host_demo.cpp): per array an int64 count and the structs; the special ids in between."""
+        import struct
+
+        with open(path, "wb") as f:
+            def arr(a, n):
+                f.write(struct.pack("<q", n))
+                f.write(bytes(a)[: n * (C.sizeof(a) // max(len(a), 1))])
+            arr(self.mats, self.n)
+            f.write(bytes(self.ids))
+            ni = self.inter_offsets[self.n * self.n] if len(self.inter_offsets) else 0
+            nr = self.react_offsets[self.n] if len(self.react_offsets) else 0
+            arr(self.inter, ni)
+            arr(self.inter_offsets, len(self.inter_offsets))
+            arr(self.react, nr)
+            arr(self.react_offsets, len(self.react_offsets))
+
     def copy(self):
         mats = (Material * self.n)(*[Material.from_buffer_copy(bytes(m)) for m in self.mats])
         ids = SpecialIds.from_buffer_copy(bytes(self.ids))
