@@ -478,6 +478,9 @@ OAPI int fseo_outlines(const uint8_t* data, int w, int h, float* pts, int cap_pt
     return (int)out.size();
 }
 OAPI int fseo_ccl(const uint8_t* data, int w, int h, int32_t* labels) { return ccl(data, w, h, labels); }
+// the two leaf functions of the outline path on their own (pinned against the reference's compiled code in tests/test_ref_pins.py)
+OAPI int fseo_ms_value(const uint8_t* data, int w, int h, int x, int y) { return msValue(x, y, w, h, data); }
+OAPI float fseo_p_distance(float x, float y, float x1, float y1, float x2, float y2) { return pDistance(x, y, x1, y1, x2, y2); }
 
 // Fracture hand-off restated on the CPU (world::updateRigidBodyHitbox, world.cpp:288-720, with 4-connected membership instead of
 // the nearest-centroid assignment of 587-610): per component, in the order of its first pixel, the cropped tile array (305-320),

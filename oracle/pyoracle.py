@@ -328,6 +328,20 @@ def body_split(tiles, angle=0.0, weld=(-1, -1), air=0):
             for k in range(n)]
 
 
+def ms_value(mask, x, y):
+    """MarchingSquares::value (physics_math.cpp:1882-1890)."""
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    lib().fseo_ms_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    return lib().fseo_ms_value(mask.ctypes.data, mask.shape[1], mask.shape[0], x, y)
+
+
+def p_distance(x, y, x1, y1, x2, y2):
+    """pDistance (physics_math.cpp:1813-1843)."""
+    lib().fseo_p_distance.restype = C.c_float
+    lib().fseo_p_distance.argtypes = [C.c_float] * 6
+    return lib().fseo_p_distance(x, y, x1, y1, x2, y2)
+
+
 def ccl(mask):
     mask = np.ascontiguousarray(mask, dtype=np.uint8)
     h, w = mask.shape
