@@ -153,7 +153,7 @@ def workload_name(args, W, H, n):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_tick_rate(args, table, extra, threads, budget_s, steps=None, warmup=1):
+def cpu_tick_rate(args, table, extra, threads, budget_s, steps=None, warmup=1, game_ticks=0):
     """Reference-schedule CPU tick (oracle, 16-worker pool as world.cpp:59, libc rand(), AoS cells) on the same
     workload.  Returns (Gcell-updates/s, description, seconds per tick)."""
     from falling_sand_engine_b200 import worldgen as G
@@ -178,12 +178,28 @@ def cpu_tick_rate(args, table, extra, threads, budget_s, steps=None, warmup=1):
     times = []
     for i in range(n_ticks):
         times.append(w.tick(i, schedule=O.REFERENCE, rng=O.RNG_LIBC, threads=threads))
+    game = None
+    if game_ticks:  # the whole game tick on the CPU, in the order bench.py's e2e leg uses on the GPU (game.cpp:1711-2159)
+        import numpy as np
+
+        planes = [np.zeros((size, size, 4), dtype=np.uint8) for _ in range(3)]
+        t0 = time.perf_counter()
+        for i in range(n_ticks, n_ticks + game_ticks):
+            w.tick(i, schedule=O.REFERENCE, rng=O.RNG_LIBC, threads=threads)
+            w.particles_tick(schedule=O.REFERENCE)
+            if i % 4 == 2:
+                w.tick_temperature()
+            O.render_dirty(w, planes)
+            w.clear_dirty()
+        game = (time.perf_counter() - t0) / game_ticks
     w.close()
     timed = times[warmup:] if len(times) > warmup else times
     per_tick = sum(timed) / len(timed)
     val = CELL_ITER * (size - 256) ** 2 / per_tick / 1e9
     desc = (f"oracle reference-schedule tick (4 colours x 128^2 chunks, {threads}-thread pool, libc rand, 40-byte AoS cells), "
             f"{len(timed)} ticks of the same generator at {size}x{size} after {min(warmup, len(times) - 1)} warm-up")
+    if game_ticks:
+        return val, desc, per_tick, size, len(timed), game
     return val, desc, per_tick, size, len(timed)
 
 
@@ -195,7 +211,8 @@ def run_reference(args):
     threads = args.cpu_threads or 16  # world.cpp:59: the reference always uses 16 tick workers
     cores = os.cpu_count() or 1
     t0 = time.time()
-    val, desc, per_tick, size, n = cpu_tick_rate(args, table, extra, threads, budget_s=150.0, steps=args.steps, warmup=max(1, min(args.warmup, 3)))
+    val, desc, per_tick, size, n, game_s = cpu_tick_rate(args, table, extra, threads, budget_s=150.0, steps=args.steps, warmup=max(1, min(args.warmup, 3)),
+                                                         game_ticks=3)
     out = {
         "impl": "reference",
         "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -205,6 +222,9 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": min(threads, cores), "threads": threads, "host_cores": cores,
                          "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # the whole game tick on the CPU (world tick + tickCells + tickTemperature on tick % 4 == 2 + dirty -> textures + dirty clear), the
+        # loop bench.py's own e2e leg runs on the GPU: 3 ticks right after the timed ones
+        "game_loop": {"value": CELL_ITER * (size - 256) ** 2 / game_s / 1e9, "unit": UNIT, "ms_per_step": game_s * 1e3, "steps": 3},
         "wall_s": time.time() - t0,
     }
     print(json.dumps(out))
@@ -317,6 +337,21 @@ def run_ours(args):
     ms = world.timer_stop()
     barrier()
     clocks = sampler.stop()
+    timeline = None
+    if world_size > 1 and os.environ.get("FSE_STRIP_TIMELINE") == "1":
+        tl = world.strip_timeline_read()
+        if len(tl) >= 4 * CELL_ITER * args.steps:  # the timed ticks are the last ones recorded
+            tl = np.asarray(tl[-4 * CELL_ITER * args.steps:], dtype=np.float64)
+            mine = [float(tl[:, q].mean()) for q in range(3)] + [float(np.maximum(tl[:, 1], tl[:, 2]).mean())]
+            tt = torch.tensor(mine, device="cuda", dtype=torch.float64)
+            tmax = tt.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            timeline = {"what": "mean over the timed colour phases, ms after the phase start on the main stream (CUDA events; nsys is not in this image)",
+                        "boundary_chunks_done_ms": {"mean_over_ranks": float(tt[0]) / world_size, "max_over_ranks": float(tmax[0])},
+                        "halo_exchange_done_ms": {"mean_over_ranks": float(tt[1]) / world_size, "max_over_ranks": float(tmax[1])},
+                        "interior_chunks_done_ms": {"mean_over_ranks": float(tt[2]) / world_size, "max_over_ranks": float(tmax[2])},
+                        "phase_done_ms": {"mean_over_ranks": float(tt[3]) / world_size, "max_over_ranks": float(tmax[3])}}
     ph_ms = world.kernel_timing_phases()
     k_ms, k_launches = world.kernel_timing_read()
     world.kernel_timing(False)
@@ -432,7 +467,7 @@ def run_ours(args):
         else:
             world.stats(T.Rect(zone.x, e2e_y0, zone.w, 1024))
 
-    for _ in range(2):  # untimed: texture planes, scratch pools and the body tables reach their size
+    for _ in range(4):  # untimed: texture planes, scratch pools, body tables and (one tick in four) the temperature scratch reach their size
         game_tick(tick_no)
         tick_no += 1
     barrier()
@@ -487,6 +522,17 @@ def run_ours(args):
         }
         if body_ms:
             out["bodies"] = body_ms
+        if timeline:
+            out["strip_timeline"] = timeline
+        if strong:
+            n1 = os.path.join(ROOT, "profiles", "r2_cfg3_32768x33024_n1.json")
+            if os.path.exists(n1) and (W, H) == (32768, 33024):  # the same world on one GPU, measured with this command line (--size 32768 --height 33024)
+                try:
+                    with open(n1) as f:
+                        d1 = json.loads(f.read().strip().splitlines()[-1])
+                    out["one_gpu_same_world"] = {"value": d1["value"], "ms_per_step": d1["ms_per_step"], "source": "profiles/r2_cfg3_32768x33024_n1.json"}
+                except Exception:
+                    pass
         print(json.dumps(out))
     world.close()
     ctx.close()

@@ -27,7 +27,7 @@ EXPORTS = [
     "fse_world_create", "fse_world_destroy", "fse_sync", "fse_write_rect", "fse_read_rect", "fse_clear_dirty", "fse_stats_rect",
     "fse_tick", "fse_tick_temperature", "fse_particles_add", "fse_particles_tick", "fse_particles_count", "fse_particles_read",
     "fse_particles_clear", "fse_particles_reserve", "fse_timer_start", "fse_timer_stop", "fse_launch_count",
-    "fse_kernel_timing_enable", "fse_kernel_timing_read", "fse_kernel_timing_phases",
+    "fse_kernel_timing_enable", "fse_kernel_timing_read", "fse_kernel_timing_phases", "fse_strip_timeline_read",
 ]
 
 
@@ -455,6 +455,13 @@ class World:
         n = C.c_int64()
         self.L.fse_kernel_timing_phases.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         _ck(self.L.fse_kernel_timing_phases(self.h, out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value]
+
+    def strip_timeline_read(self, cap=1 << 14):
+        out = np.zeros((cap, 3), dtype=np.float32)
+        n = C.c_int64()
+        self.L.fse_strip_timeline_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        _ck(self.L.fse_strip_timeline_read(self.h, out.ctypes.data, cap, C.byref(n)))
         return out[: n.value]
 
     def kernel_timing_read(self):

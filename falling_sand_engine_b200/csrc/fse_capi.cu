@@ -219,6 +219,7 @@ static void free_world(fse_world* w) {
     if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
     if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);
     for (int q = 0; q < 4; q++) cudaFree(w->halo_stage[q]);
+    for (cudaEvent_t e_ : w->timeline_ev) cudaEventDestroy(e_);
     cudaFree(w->d_phase_rows);
     if (w->h_phase_rows) cudaFreeHost(w->h_phase_rows);
     if (w->ev_phase_rows) cudaEventDestroy(w->ev_phase_rows);
@@ -252,6 +253,8 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     if (e == cudaSuccess) e = cudaMallocHost(&w->h_stats, dev_stats_bytes());
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
     if (const char* env = getenv("FSE_TICK_LPT")) w->lpt_on = atoi(env) != 0;
+    if (const char* env = getenv("FSE_LPT_DEAL")) w->lpt_deal = atoi(env) != 0;
+    if (const char* env = getenv("FSE_STRIP_TIMELINE")) w->timeline_on = atoi(env) != 0;
     if (const char* env = getenv("FSE_ROW_SKIP")) w->rowskip_mode = atoi(env);
     if (const char* env = getenv("FSE_ROW_SKIP_MAX_ACTIVE")) w->rowskip_max_active = (float)atof(env);
     for (int q = 0; q < 16; q++) {
@@ -661,6 +664,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.chunk_state = nullptr;
             P.rowmask = nullptr;
             P.phase_rows = nullptr;
+            P.lpt_parts = 0;
             const int ph = iter * 4 + tk;
             bool skip_here = w->rowskip_mode == 1;
             if (w->rowskip_mode == 2) skip_here = gate_probe || w->phase_active[ph] < 0.0f || w->phase_active[ph] < w->rowskip_max_active;
@@ -713,14 +717,19 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                         memset(w->lpt_sig, 0, sizeof(w->lpt_sig));
                     }
                     const int sig[4] = {P.x0, P.y0, P.ncx, P.ncy};
-                    if (memcmp(sig, w->lpt_sig[tk], sizeof(sig)) == 0) P.chunk_list = w->d_lpt_list + (size_t)tk * w->lpt_cap;
+                    if (memcmp(sig, w->lpt_sig[tk], sizeof(sig)) == 0) {
+                        P.chunk_list = w->d_lpt_list + (size_t)tk * w->lpt_cap;
+                        P.lpt_parts = w->lpt_parts[tk];
+                    }
                     P.chunk_cost = w->d_lpt_cost + (size_t)tk * w->lpt_cap;
                 }
                 if (int r = kt.begin(w->stream)) return r;
                 int nl = 0;
                 CK(launch_tick_phase(P, n_chunks, w->stream, &nl, &w->fork));
                 if (lpt) {
-                    CK(launch_lpt_build(P.chunk_cost, n_chunks, P.ncx, w->d_lpt_list + (size_t)tk * w->lpt_cap, w->stream));
+                    const int deal = (w->lpt_deal && n_chunks >= w->fork.min_chunks) ? w->fork.parts : 1;
+                    CK(launch_lpt_build(P.chunk_cost, n_chunks, P.ncx, w->d_lpt_list + (size_t)tk * w->lpt_cap, w->stream, nullptr, deal));
+                    w->lpt_parts[tk] = deal;
                     nl += 1;
                     const int sig[4] = {P.x0, P.y0, P.ncx, P.ncy};
                     memcpy(w->lpt_sig[tk], sig, sizeof(sig));
@@ -738,12 +747,25 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             // chunks of a colour phase are independent, only the next phase needs both
             CK(cudaEventRecord(w->ev_boundary, w->stream));
             CK(cudaStreamWaitEvent(w->comm_stream, w->ev_boundary, 0));
+            cudaEvent_t* tl = nullptr;  // FSE_STRIP_TIMELINE=1: phase start | boundary chunks done | halo exchange done | interior chunks done
+            if (w->timeline_on) {
+                if (w->timeline_used + 4 > w->timeline_ev.size())
+                    for (int q = 0; q < 4; q++) {
+                        cudaEvent_t e_;
+                        CK(cudaEventCreate(&e_));
+                        w->timeline_ev.push_back(e_);
+                    }
+                tl = &w->timeline_ev[w->timeline_used];
+                w->timeline_used += 4;
+                CK(cudaEventRecord(tl[0], w->stream));
+            }
             if (w->list_cnt[tk][0] > 0) {
                 P.chunk_list = w->d_chunk_lists + w->list_off[tk][0];
                 int nl = 0;
                 CK(launch_tick_phase(P, w->list_cnt[tk][0], w->comm_stream, &nl, nullptr));
                 w->ctx->launches += nl;
             }
+            if (tl) CK(cudaEventRecord(tl[1], w->comm_stream));
             if (multi) {
                 if (int r = strip_exchange(w, ofy, j0, j1, z.y - w->y_off, w->comm_stream)) {
                     // the boundary kernels are already enqueued on the side stream: the next call must not race with them
@@ -753,6 +775,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                 }
             }
             CK(cudaEventRecord(w->ev_comm, w->comm_stream));
+            if (tl) CK(cudaEventRecord(tl[2], w->comm_stream));
             if (w->list_cnt[tk][1] > 0) {
                 const int n_int = w->list_cnt[tk][1], n_grid = P.ncx * P.ncy;
                 const int* base_list = w->d_chunk_lists + w->list_off[tk][1];
@@ -774,13 +797,18 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                         memset(w->lpt_sig, 0, sizeof(w->lpt_sig));
                     }
                     const int sig[4] = {P.x0 ^ (w->list_off[tk][1] << 8), P.y0, P.ncx, n_int};
-                    if (memcmp(sig, w->lpt_sig[tk], sizeof(sig)) == 0) P.chunk_list = w->d_lpt_list + (size_t)tk * w->lpt_cap;
+                    if (memcmp(sig, w->lpt_sig[tk], sizeof(sig)) == 0) {
+                        P.chunk_list = w->d_lpt_list + (size_t)tk * w->lpt_cap;
+                        P.lpt_parts = w->lpt_parts[tk];
+                    }
                     P.chunk_cost = w->d_lpt_cost + (size_t)tk * w->lpt_cap;
                 }
                 int nl = 0;
                 CK(launch_tick_phase(P, n_int, w->stream, &nl, &w->fork));
                 if (lpt) {
-                    CK(launch_lpt_build(P.chunk_cost, n_int, P.ncx, w->d_lpt_list + (size_t)tk * w->lpt_cap, w->stream, base_list));
+                    const int deal = (w->lpt_deal && n_int >= w->fork.min_chunks) ? w->fork.parts : 1;
+                    CK(launch_lpt_build(P.chunk_cost, n_int, P.ncx, w->d_lpt_list + (size_t)tk * w->lpt_cap, w->stream, base_list, deal));
+                    w->lpt_parts[tk] = deal;
                     nl += 1;
                     const int sig[4] = {P.x0 ^ (w->list_off[tk][1] << 8), P.y0, P.ncx, n_int};
                     memcpy(w->lpt_sig[tk], sig, sizeof(sig));
@@ -789,6 +817,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                 w->ctx->launches += nl;
             }
             if (int r = kt.end(w->stream)) return r;
+            if (tl) CK(cudaEventRecord(tl[3], w->stream));
             CK(cudaStreamWaitEvent(w->stream, w->ev_comm, 0));
         }
     }
@@ -936,6 +965,22 @@ FSE_API int fse_kernel_timing_phases(fse_world* w, float* out_ms, int64_t cap, i
     int64_t n = 0;
     for (size_t i = 0; i < w->kt_used && n < cap; i++, n++) CK(cudaEventElapsedTime(&out_ms[i], w->kt_events[i].first, w->kt_events[i].second));
     *n_out = n;
+    return FSE_OK;
+}
+
+// Strip worlds, FSE_STRIP_TIMELINE=1 at creation: per colour phase since the last read, the times (ms after the phase started on the
+// main stream) at which the cut-adjacent chunks finished, the halo exchange finished (both on the side stream) and the interior
+// chunks finished (main stream).  out = n x 3 floats.  The stand-in for an nsys timeline (nsys is not in this image).
+FSE_API int fse_strip_timeline_read(fse_world* w, float* out, int64_t cap_phases, int64_t* n_out) {
+    if (!w || !n_out || (!out && cap_phases > 0)) return fail(FSE_EINVAL, "fse_strip_timeline_read: null argument");
+    CK(cudaSetDevice(w->ctx->device));
+    CK(cudaStreamSynchronize(w->stream));
+    CK(cudaStreamSynchronize(w->comm_stream));
+    int64_t n = 0;
+    for (size_t i = 0; i + 3 < w->timeline_used && n < cap_phases; i += 4, n++)
+        for (int q = 0; q < 3; q++) CK(cudaEventElapsedTime(&out[3 * n + q], w->timeline_ev[i], w->timeline_ev[i + 1 + q]));
+    *n_out = n;
+    w->timeline_used = 0;
     return FSE_OK;
 }
 

@@ -74,6 +74,8 @@ struct fse_world {
     int lpt_cap = 0;            // chunks per colour the buffers hold
     int lpt_sig[4][4]{};        // (x0, y0, ncx, ncy) the list of a colour was built for; ncx = 0: no list yet
     bool lpt_on = true;
+    bool lpt_deal = false;      // FSE_LPT_DEAL=1: the longest-first order is dealt out over the parts of a phase (lpt_build_kernel)
+    int lpt_parts[4] = {0, 0, 0, 0};  // parts the list of a colour was dealt into (0 / 1: plain order)
     // settled-row skipping of the per-pass kernels (classify_rows_kernel): ROWMASK_WORDS words per chunk of a colour's grid
     uint32_t* d_rowmask = nullptr;
     int rowmask_cap = 0;
@@ -120,6 +122,9 @@ struct fse_world {
     bool kt_enabled = false;
     size_t kt_used = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kt_events;
+    bool timeline_on = false;               // FSE_STRIP_TIMELINE=1: events per strip phase (fse_strip_timeline_read)
+    std::vector<cudaEvent_t> timeline_ev;
+    size_t timeline_used = 0;
     uint64_t ticks = 0;
     int schedule = FSE_SCHEDULE_ROWS;
     unsigned long long* d_dbg = nullptr;
@@ -145,7 +150,7 @@ int strip_sendrecv(fse_world* w, const void* up_send, size_t up_send_bytes, void
                    size_t down_send_bytes, void* down_recv, size_t down_recv_bytes, cudaStream_t s);
 int strip_allreduce_u32(fse_world* w, unsigned int* dev, size_t count, cudaStream_t s);
 size_t tick_smem_bytes();
-cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream, const int* members = nullptr);
+cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream, const int* members = nullptr, int parts = 1);
 cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched, const TickFork* fork);  // *launched = kernels enqueued
 cudaError_t launch_compact_active(const uint8_t* awake, int acols, int ci0, int cj0, int ncx, int ncy, int* list, int* count, cudaStream_t s);
 

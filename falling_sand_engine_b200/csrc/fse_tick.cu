@@ -1118,7 +1118,10 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
         }
         for (int q = 0; q < parts; q++) {
             cudaStream_t st = q ? fork->aux[q - 1] : stream;
-            const int lo = (int)((long long)n_chunks * q / parts), hi = (int)((long long)n_chunks * (q + 1) / parts);
+            // slices of the chunk list; with a dealt-out longest-first list (lpt_build_kernel) they are the parts it was dealt into
+            const bool dealt = P.lpt_parts == parts && parts > 1;
+            const int lo = dealt ? part_lo(n_chunks, parts, q) : (int)((long long)n_chunks * q / parts);
+            const int hi = dealt ? part_lo(n_chunks, parts, q + 1) : (int)((long long)n_chunks * (q + 1) / parts);
             if (hi <= lo) continue;  // fewer chunks than parts
             Q.chunk_base = P.chunk_base + lo;
             if (Q.rowmask) {
@@ -1153,8 +1156,8 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
     return cudaGetLastError();
 }
 
-cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream, const int* members) {
-    lpt_build_kernel<<<1, 1024, 0, stream>>>(cost, n, ncx, list, members);
+cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream, const int* members, int parts) {
+    lpt_build_kernel<<<1, 1024, 0, stream>>>(cost, n, ncx, list, members, parts);
     return cudaGetLastError();
 }
 

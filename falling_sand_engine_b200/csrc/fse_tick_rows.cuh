@@ -1636,7 +1636,11 @@ __global__ void apply_chunk_state_kernel(const TickParams P, int n) {
 // (64 bins, heaviest bin first).  A phase is ~1.3 waves of CTAs, so starting the expensive chunks first shortens its tail;
 // chunks of a phase are independent, the order cannot change results.
 // `members` (optional): the n chunks to order, as (cxi | cyi << 16); otherwise all chunks 0..n-1 of the colour's grid.
-__global__ void __launch_bounds__(1024) lpt_build_kernel(const unsigned int* cost, int n, int ncx, int* list, const int* members) {
+// parts > 1: the sorted order is dealt out to the parts of the phase like cards (rank r goes to part r % parts), so every part holds
+// the same mix of heavy and light chunks, heaviest first, instead of part 0 holding all the heavy ones (part q = list entries
+// [part_lo(n, parts, q), part_lo(n, parts, q + 1)), the slices launch_tick_phase launches).
+__host__ __device__ __forceinline__ int part_lo(int n, int parts, int q) { return q * (n / parts) + (q < n % parts ? q : n % parts); }
+__global__ void __launch_bounds__(1024) lpt_build_kernel(const unsigned int* cost, int n, int ncx, int* list, const int* members, int parts) {
     __shared__ unsigned int hist[64], base[64], maxc;
     const int tid = threadIdx.x;
     if (tid < 64) hist[tid] = 0;
@@ -1662,7 +1666,7 @@ __global__ void __launch_bounds__(1024) lpt_build_kernel(const unsigned int* cos
     for (int i = tid; i < n; i += blockDim.x) {
         const int v = entry(i);
         const unsigned int pos = atomicAdd(&base[63 - (int)((unsigned long long)cost_of(v) * 64 / scale)], 1u);
-        list[pos] = v;
+        list[parts > 1 ? part_lo(n, parts, (int)(pos % parts)) + (int)(pos / parts) : (int)pos] = v;
     }
 }
 

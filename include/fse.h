@@ -393,6 +393,9 @@ FSE_API int64_t fse_launch_count(fse_ctx* ctx);
  * last reset, from CUDA events recorded around every launch when enabled. */
 FSE_API int fse_kernel_timing_enable(fse_world* w, int enable);
 FSE_API int fse_kernel_timing_read(fse_world* w, double* total_ms, int64_t* launches);
+/* strip worlds created with FSE_STRIP_TIMELINE=1: per colour phase, ms after the phase start at which the cut-adjacent chunks, the halo
+ * exchange and the interior chunks finished (out: n x 3 floats); resets the record */
+FSE_API int fse_strip_timeline_read(fse_world* w, float* out, int64_t cap_phases, int64_t* n_out);
 FSE_API int fse_kernel_timing_phases(fse_world* w, float* out_ms, int64_t cap, int64_t* n_out);
 /* profiling aid: cycles each warp role of the tick kernel spent working between step barriers (out[0..3]) and chunks (out[4]) */
 FSE_API int fse_debug_role_cycles(fse_world* w, int enable, unsigned long long* out);
