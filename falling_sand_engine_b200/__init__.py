@@ -6,11 +6,14 @@ CPU fallback — using the API without the built extension or without a GPU rais
 """
 from . import types, worldgen  # noqa: F401
 
-__all__ = ["types", "worldgen", "Context", "World", "load_library", "default_materials"]
+__all__ = ["types", "worldgen", "Context", "World", "FseError", "load_library", "default_materials"]
+
+# fse_pixels_read / fse_pixels_device plane ids (include/fse.h)
+PIXELS_MAIN, PIXELS_FIRE, PIXELS_EMISSION, PIXELS_FLOW, PIXELS_LAYER2, PIXELS_BACKGROUND = range(6)
 
 
 def __getattr__(name):
-    if name in ("Context", "World", "load_library", "default_materials"):
+    if name in ("Context", "World", "FseError", "load_library", "default_materials"):
         from . import api
 
         return getattr(api, name)

@@ -275,20 +275,30 @@ class World:
 
     # -- fracture outlines (world.cpp:288-720, physics_math.cpp:1766-1965) and physicsCheck flood (world.cpp:3330) ------
     # -- chunk files (Chunk::ChunkRead / ChunkWrite, chunk.cpp:74-330; the merge of world::frame and chunkSaveCache) ---------
-    def load_chunk(self, path, x, y):
-        """Read a .pack file and merge its object layer into the grid at (x, y), marked dirty like world::frame does
-        (world.cpp:2374-2391).  Returns (generation_phase, layer2, background), which the tick path does not own."""
+    def load_chunk(self, path, x, y, layers=False):
+        """Read a .pack file and merge it into the grid at (x, y), marked dirty like world::frame does (world.cpp:2374-2391): the
+        object layer always, layer 2 and the background colours into their device planes with layers=True.  Cells must index into
+        the context's material table (IOError otherwise).  Returns (generation_phase, layer2, background)."""
         from . import chunkfile
 
-        phase, tiles, layer2, background = chunkfile.read_pack(path)
+        n = self.ctx.table.n if getattr(self.ctx, "table", None) is not None else None
+        phase, tiles, layer2, background = chunkfile.read_pack(path, n)
         tiles["dirty"] = 1
         self.write_rect(x, y, tiles)
+        if layers:
+            self.layer2_write_rect(x, y, layer2)
+            self.background_write_rect(x, y, background)
         return phase, layer2, background
 
-    def save_chunk(self, path, x, y, layer2=None, background=None, generation_phase=0):
-        """chunkSaveCache (world.cpp:2780-2792) + ChunkWrite: the 128 x 128 cells at (x, y) go to a .pack file."""
+    def save_chunk(self, path, x, y, layer2=None, background=None, generation_phase=0, layers=False):
+        """chunkSaveCache (world.cpp:2780-2792) + ChunkWrite: the 128 x 128 cells at (x, y) go to a .pack file (layers=True: with
+        the device's layer-2 cells and background colours unless given)."""
         from . import chunkfile
 
+        if layers and layer2 is None:
+            layer2 = self.layer2_read_rect(x, y, T.FSE_CHUNK, T.FSE_CHUNK)
+        if layers and background is None:
+            background = self.background_read_rect(x, y, T.FSE_CHUNK, T.FSE_CHUNK)
         chunkfile.write_pack(path, self.read_rect(x, y, T.FSE_CHUNK, T.FSE_CHUNK), layer2, background, generation_phase)
 
     def save_world(self, world_dir, origin=(0, 0)):
@@ -301,22 +311,72 @@ class World:
         """Merge every chunk file found under <world_dir>/chunks into the grid."""
         from . import chunkfile
 
-        return chunkfile.load_world(self, world_dir, self.width, self.height, origin)
+        n = self.ctx.table.n if getattr(self.ctx, "table", None) is not None else None
+        return chunkfile.load_world(self, world_dir, self.width, self.height, origin, n)
 
     # -- render planes / camera scroll (game.cpp:1994-2060, world.cpp:2454-2478) ---------------------------
     def pixels_enable(self, on=True):
         self.L.fse_pixels_enable.argtypes = [C.c_void_p, C.c_int]
         _ck(self.L.fse_pixels_enable(self.h, 1 if on else 0))
 
-    def render_dirty(self, want_stats=True):
-        """Refresh the texels of all dirty cells; returns (dirty, fire, movingTiles) or None when want_stats is False."""
+    def render_dirty(self, want_stats=True, with_flow_count=False):
+        """Refresh the texels of all dirty cells; returns (dirty, fire, movingTiles) [+ dirty liquid cells with with_flow_count] or None
+        when want_stats is False."""
         self.L.fse_render_dirty.argtypes = [C.c_void_p, C.c_void_p]
         if not want_stats:
             _ck(self.L.fse_render_dirty(self.h, None))
             return None
         st = T.RenderStats()
         _ck(self.L.fse_render_dirty(self.h, C.byref(st)))
+        if with_flow_count:
+            return st.dirty, st.fire, np.ctypeslib.as_array(st.moving).copy(), st.flow
         return st.dirty, st.fire, np.ctypeslib.as_array(st.moving).copy()
+
+    # -- liquid flow accumulators (world::flowX / flowY / prevFlowX / prevFlowY) and the flow texture --------------------------
+    def flow_enable(self, on=True):
+        self.L.fse_flow_enable.argtypes = [C.c_void_p, C.c_int]
+        _ck(self.L.fse_flow_enable(self.h, 1 if on else 0))
+
+    def flow_read(self, which, rect=None):
+        """which: 0 flowX, 1 flowY, 2 prevFlowX, 3 prevFlowY."""
+        r = rect or T.Rect(0, 0, self.width, self.height)
+        out = np.zeros((r.h, r.w), dtype=np.float32)
+        self.L.fse_flow_read.argtypes = [C.c_void_p, C.c_int] + [C.c_int32] * 4 + [C.c_void_p]
+        _ck(self.L.fse_flow_read(self.h, which, r.x, r.y, r.w, r.h, out.ctypes.data))
+        return out
+
+    # -- second cell layer and background colours (world::real_layer2 / background) ---------------------------------------------
+    def layer2_write_rect(self, x, y, cells):
+        c = np.ascontiguousarray(cells, dtype=T.CELL_DTYPE)
+        self.L.fse_layer2_write_rect.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]
+        _ck(self.L.fse_layer2_write_rect(self.h, x, y, c.shape[1], c.shape[0], c.ctypes.data))
+
+    def layer2_read_rect(self, x, y, w, h):
+        out = np.zeros((h, w), dtype=T.CELL_DTYPE)
+        self.L.fse_layer2_read_rect.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]
+        _ck(self.L.fse_layer2_read_rect(self.h, x, y, w, h, out.ctypes.data))
+        return out
+
+    def background_write_rect(self, x, y, colors):
+        c = np.ascontiguousarray(colors, dtype=np.uint32)
+        self.L.fse_background_write_rect.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]
+        _ck(self.L.fse_background_write_rect(self.h, x, y, c.shape[1], c.shape[0], c.ctypes.data))
+
+    def background_read_rect(self, x, y, w, h):
+        out = np.zeros((h, w), dtype=np.uint32)
+        self.L.fse_background_read_rect.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]
+        _ck(self.L.fse_background_read_rect(self.h, x, y, w, h, out.ctypes.data))
+        return out
+
+    def render_layers(self, draw_background_grid=False, want_counts=True):
+        """game.cpp:2068-2126: dirty layer-2 / background cells -> FSE_PIXELS_LAYER2 / FSE_PIXELS_BACKGROUND; returns the two counts."""
+        self.L.fse_render_layers.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        if not want_counts:
+            _ck(self.L.fse_render_layers(self.h, 1 if draw_background_grid else 0, None, None))
+            return None
+        a, b = C.c_int64(0), C.c_int64(0)
+        _ck(self.L.fse_render_layers(self.h, 1 if draw_background_grid else 0, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def pixels_read(self, which, rect=None):
         r = rect or T.Rect(0, 0, self.width, self.height)

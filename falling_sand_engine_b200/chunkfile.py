@@ -4,8 +4,8 @@ save.  A `.pack` file is
     i8   generationPhase
     i32  src_size   (= 128 * 128 * 2 * 12)     i32 compressed_size
     i32  src_size2  (= 128 * 128 * 4)          i32 compressed_size2
-    LZ4 block: MaterialInstanceData[2 * 128 * 128] = {u16 index, u32 color, i16 temperature} (12 bytes with padding,
-               game_datastruct.hpp), first the 16384 cells of the object layer, then layer 2
+    LZ4 block: MaterialInstanceData[2 * 128 * 128] = {u32 index, u32 color, i16 temperature} (12 bytes with padding,
+               game_datastruct.hpp:106-107, chunk.hpp:26-30), first the 16384 cells of the object layer, then layer 2
     LZ4 block: u32 background[128 * 128]
 
 LZ4 and the file format stay on the host; the cells go to / come from the device through fse_write_rect /
@@ -22,7 +22,7 @@ from . import types as T
 
 CHUNK = T.FSE_CHUNK
 CELLS = CHUNK * CHUNK
-DISK_DTYPE = np.dtype({"names": ["index", "color", "temperature"], "formats": [np.uint16, np.uint32, np.int16], "offsets": [0, 4, 8], "itemsize": 12})
+DISK_DTYPE = np.dtype({"names": ["index", "color", "temperature"], "formats": ["<u4", "<u4", "<i2"], "offsets": [0, 4, 8], "itemsize": 12})
 
 _lz4 = None
 
@@ -76,18 +76,29 @@ def write_pack(path, tiles, layer2=None, background=None, generation_phase=0):
         f.write(c2)
 
 
-def read_pack(path):
+def read_pack(path, n_materials=None):
     """ChunkRead (chunk.cpp:74-217) -> (generation_phase, tiles, layer2, background) with tiles / layer2 as (128, 128) fse_cell
-    arrays and background as (128, 128) u32."""
+    arrays and background as (128, 128) u32.  n_materials: size of the material table the cells must index into (IOError otherwise)."""
     with open(path, "rb") as f:
         head = f.read(17)
+        if len(head) != 17:
+            raise IOError(f"{path}: truncated chunk header ({len(head)} of 17 bytes)")
         phase, src_size, csize, src_size2, csize2 = struct.unpack("<biiii", head)
         if src_size != 2 * CELLS * DISK_DTYPE.itemsize:
             raise IOError(f"Chunk src_size was different from expected: {src_size} vs {2 * CELLS * DISK_DTYPE.itemsize}")  # chunk.cpp:126
         if src_size2 != CELLS * 4:
             raise IOError(f"Chunk src_size2 was different from expected: {src_size2} vs {CELLS * 4}")  # chunk.cpp:139
+        L = _lib()
+        if not (0 < csize <= L.LZ4_compressBound(src_size)) or not (0 < csize2 <= L.LZ4_compressBound(src_size2)):
+            raise IOError(f"{path}: compressed sizes {csize}, {csize2} are not those of a chunk file")
         c1, c2 = f.read(csize), f.read(csize2)
+        if len(c1) != csize or len(c2) != csize2:
+            raise IOError(f"{path}: truncated chunk data")
     disk = np.frombuffer(_decompress(c1, src_size), dtype=DISK_DTYPE)
+    if n_materials is not None and int(disk["index"].max()) >= n_materials:
+        raise IOError(f"{path}: material index {int(disk['index'].max())} is outside the material table ({n_materials} entries)")
+    if int(disk["index"].max()) > 0xffff:
+        raise IOError(f"{path}: material index {int(disk['index'].max())} does not fit fse_cell.mat")
     bg = np.frombuffer(_decompress(c2, src_size2), dtype=np.uint32).reshape(CHUNK, CHUNK).copy()
     layers = []
     for k in range(2):
@@ -106,34 +117,49 @@ def pack_path(world_dir, cx, cy):
     return os.path.join(world_dir, "chunks", f"c_{cx}_{cy}.pack")
 
 
+def _whole_chunks(width, height, what):
+    if width % CHUNK or height % CHUNK:
+        raise ValueError(f"{what}: the grid must be whole chunks ({width} x {height} is not a multiple of {CHUNK})")
+
+
 def save_world(world, world_dir, width, height, origin=(0, 0)):
     """world::saveWorld (world.cpp:3431-3452): every chunk of the grid goes to its .pack file (chunkSaveCache + ChunkWrite).
-    `world` is anything with read_rect(x, y, w, h); `origin` is the chunk coordinate of the grid's top-left chunk.  Returns the
-    number of files written."""
+    `world` is anything with read_rect(x, y, w, h) (+ layer2_read_rect / background_read_rect when it keeps those planes); `origin` is
+    the chunk coordinate of the grid's top-left chunk.  Returns the number of files written."""
     import os
 
+    _whole_chunks(width, height, "save_world")
     os.makedirs(os.path.join(world_dir, "chunks"), exist_ok=True)
+    layers = hasattr(world, "layer2_read_rect") and hasattr(world, "background_read_rect")
     n = 0
     for j in range(height // CHUNK):
         for i in range(width // CHUNK):
-            write_pack(pack_path(world_dir, origin[0] + i, origin[1] + j), world.read_rect(i * CHUNK, j * CHUNK, CHUNK, CHUNK))
+            l2 = world.layer2_read_rect(i * CHUNK, j * CHUNK, CHUNK, CHUNK) if layers else None
+            bg = world.background_read_rect(i * CHUNK, j * CHUNK, CHUNK, CHUNK) if layers else None
+            write_pack(pack_path(world_dir, origin[0] + i, origin[1] + j), world.read_rect(i * CHUNK, j * CHUNK, CHUNK, CHUNK), l2, bg)
             n += 1
     return n
 
 
-def load_world(world, world_dir, width, height, origin=(0, 0)):
-    """The reverse: every chunk file that exists is merged into the grid (ChunkRead + the frame() merge).  `world` is anything with
-    write_rect(x, y, cells).  Returns the number of chunks loaded."""
+def load_world(world, world_dir, width, height, origin=(0, 0), n_materials=None):
+    """The reverse: every chunk file that exists is merged into the grid (ChunkRead + the frame() merge, world.cpp:2374-2391: cells,
+    layer 2 and background, all marked dirty).  `world` is anything with write_rect(x, y, cells) (+ layer2_write_rect /
+    background_write_rect).  Returns the number of chunks loaded."""
     import os
 
+    _whole_chunks(width, height, "load_world")
+    layers = hasattr(world, "layer2_write_rect") and hasattr(world, "background_write_rect")
     n = 0
     for j in range(height // CHUNK):
         for i in range(width // CHUNK):
             path = pack_path(world_dir, origin[0] + i, origin[1] + j)
             if not os.path.exists(path):
                 continue
-            _, tiles, _, _ = read_pack(path)
+            _, tiles, layer2, bg = read_pack(path, n_materials)
             tiles["dirty"] = 1
             world.write_rect(i * CHUNK, j * CHUNK, tiles)
+            if layers:
+                world.layer2_write_rect(i * CHUNK, j * CHUNK, layer2)
+                world.background_write_rect(i * CHUNK, j * CHUNK, bg)
             n += 1
     return n

@@ -129,7 +129,8 @@ __global__ void stats_kernel(Planes p, int W, int x0, int y0, int rw, int rh, in
 // ---- world::tickTemperature() (world.cpp:1950-2004) -----------------------------------------------------
 // Jacobi 3x3 stencil on the i16 temperature plane: order-independent, so bit-exact against the reference
 // order.  One thread per cell of a 32x8 tile staged (with a 1-cell halo) in shared memory; the new
-// temperatures go to a scratch plane that is then copied back (the reference's newTemps[] two-loop form).
+// temperatures go to a second plane that then becomes the temperature plane (the reference's newTemps[] two-loop form; only the
+// cells around the zone are copied).
 constexpr int TT_W = 128, TT_H = 16, TT_P = TT_W + 4;  // outputs per block; row pitch of the shared-memory tile (130 used)
 
 // Each loaded cell's contribution is computed once — factor = float(abs(t) / 64) * conductionOther(mat), t * factor — and every
@@ -217,10 +218,24 @@ __global__ void __launch_bounds__(256) temperature_kernel(const uint8_t* __restr
     }
 }
 
-__global__ void copy_zone_i16_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int W, int zx, int zy, int zw, int zh) {
-    const size_t n = (size_t)zw * zh;
+// The cells OUTSIDE the zone (top and bottom bands, left and right margins) copied from the old plane into the new one, so the two
+// planes can simply trade places afterwards: the zone itself is never copied back.
+__global__ void copy_outside_zone_i16_kernel(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int W, int H, int zx, int zy, int zw,
+                                             int zh) {
+    const size_t n_top = (size_t)zy * W, n_bot = (size_t)(H - zy - zh) * W, n_left = (size_t)zh * zx, n_right = (size_t)zh * (W - zx - zw);
+    const size_t n = n_top + n_bot + n_left + n_right;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        size_t g = (size_t)(zy + i / zw) * W + (zx + i % zw);
+        size_t g;
+        if (i < n_top) g = i;
+        else if (i < n_top + n_bot) g = (size_t)(zy + zh) * W + (i - n_top);
+        else if (i < n_top + n_bot + n_left) {
+            const size_t k = i - n_top - n_bot;
+            g = (size_t)(zy + k / zx) * W + k % zx;
+        } else {
+            const size_t k = i - n_top - n_bot - n_left;
+            const int mr = W - zx - zw;
+            g = (size_t)(zy + k / mr) * W + zx + zw + k % mr;
+        }
         dst[g] = src[g];
     }
 }
@@ -257,13 +272,15 @@ cudaError_t launch_stats(Planes p, int W, int x0, int y0, int rw, int rh, int yo
 }
 size_t dev_stats_bytes() { return sizeof(DevStats); }
 
+// new temperatures of the zone -> `scratch`, the cells around the zone copied over; the caller swaps p.tmp and scratch afterwards
 cudaError_t launch_temperature(Planes p, int16_t* scratch, int W, int H, int zx, int zy, int zw, int zh, const DevTables* T, uint8_t* awake,
                                int acols, int yoff, cudaStream_t s) {
     dim3 grid((zw + TT_W - 1) / TT_W, (zh + TT_H - 1) / TT_H);
     temperature_kernel<<<grid, 256, 0, s>>>(p.mat, p.tmp, scratch, W, H, zx, zy, zw, zh, T, awake, acols, yoff);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    copy_zone_i16_kernel<<<grid_for((size_t)zw * zh, 256), 256, 0, s>>>(scratch, p.tmp, W, zx, zy, zw, zh);
+    const size_t outside = (size_t)W * H - (size_t)zw * zh;
+    if (outside) copy_outside_zone_i16_kernel<<<grid_for(outside, 256), 256, 0, s>>>(p.tmp, scratch, W, H, zx, zy, zw, zh);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -215,7 +216,7 @@ static void free_world(fse_world* w) {
     cudaFree(w->d_chunk_lists);
     cudaFree(w->d_awake); cudaFree(w->d_active_list); cudaFree(w->d_active_count);
     cudaFree(w->part_list);
-    cudaFree(w->d_pixels); cudaFree(w->d_render_stats); cudaFree(w->scroll_scratch);
+    render_free(w);
     if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
     if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);
     for (int q = 0; q < 4; q++) cudaFree(w->halo_stage[q]);
@@ -255,6 +256,7 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     if (const char* env = getenv("FSE_TICK_LPT")) w->lpt_on = atoi(env) != 0;
     if (const char* env = getenv("FSE_LPT_DEAL")) w->lpt_deal = atoi(env) != 0;
     if (const char* env = getenv("FSE_STRIP_TIMELINE")) w->timeline_on = atoi(env) != 0;
+    if (const char* env = getenv("FSE_STRIP_BOUNDARY_MIN")) w->strip_boundary_min = atoi(env);
     if (const char* env = getenv("FSE_ROW_SKIP")) w->rowskip_mode = atoi(env);
     if (const char* env = getenv("FSE_ROW_SKIP_MAX_ACTIVE")) w->rowskip_max_active = (float)atof(env);
     for (int q = 0; q < 16; q++) {
@@ -364,24 +366,6 @@ FSE_API void fse_world_destroy(fse_world* w) {
 FSE_API int fse_sync(fse_world* w) {
     if (!w) return fail(FSE_EINVAL, "fse_sync: null world");
     CK(cudaStreamSynchronize(w->stream));
-    return FSE_OK;
-}
-
-// Rects are in global coordinates; a strip world holds rows [y_off, y_off + H).
-static int check_rect(fse_world* w, int x, int y, int rw, int rh, const char* who) {
-    if (rw <= 0 || rh <= 0 || x < 0 || y < w->y_off || (int64_t)x + rw > w->W || (int64_t)y + rh > (int64_t)w->y_off + w->H)
-        return fail(FSE_EINVAL, "%s: rect (%d,%d,%d,%d) outside the held rows [%d,%d) of the %dx%d world", who, x, y, rw, rh, w->y_off,
-                    w->y_off + w->H, w->W, w->Hglobal);
-    return FSE_OK;
-}
-
-static int ensure_stage(fse_world* w, size_t cells) {
-    if (w->stage_cells >= cells) return FSE_OK;
-    cudaFree(w->d_stage);
-    w->d_stage = nullptr;
-    w->stage_cells = 0;
-    CK(cudaMalloc(&w->d_stage, cells * sizeof(fse_cell)));
-    w->stage_cells = cells;
     return FSE_OK;
 }
 
@@ -663,6 +647,8 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             P.chunk_cost = nullptr;
             P.chunk_state = nullptr;
             P.rowmask = nullptr;
+            P.flowx = w->d_flow;
+            P.flowy = w->d_flow ? w->d_flow + (size_t)w->W * w->H : nullptr;
             P.phase_rows = nullptr;
             P.lpt_parts = 0;
             const int ph = iter * 4 + tk;
@@ -762,7 +748,12 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             if (w->list_cnt[tk][0] > 0) {
                 P.chunk_list = w->d_chunk_lists + w->list_off[tk][0];
                 int nl = 0;
-                CK(launch_tick_phase(P, w->list_cnt[tk][0], w->comm_stream, &nl, nullptr));
+                // A full chunk row of cut-adjacent chunks runs on the per-pass kernels like the interior (FSE_STRIP_BOUNDARY_MIN, default
+                // 64 chunks): next to the interior's CTAs a fused launch (86 KB, 320 threads per chunk) took 1.16 ms of a 1.75 ms phase
+                // at 8 GPUs and slowed the interior down; short rows (small worlds) keep the fused kernel's shorter chain.
+                TickParams B = P;
+                if (w->list_cnt[tk][0] >= w->strip_boundary_min) B.fused_max_chunks = 0;
+                CK(launch_tick_phase(B, w->list_cnt[tk][0], w->comm_stream, &nl, nullptr));
                 w->ctx->launches += nl;
             }
             if (tl) CK(cudaEventRecord(tl[1], w->comm_stream));
@@ -845,6 +836,7 @@ FSE_API int fse_tick_temperature(fse_world* w, const fse_rect* zg) {
     CK(cudaSetDevice(w->ctx->device));
     CK(launch_temperature(w->p, w->tmp_scratch, w->W, w->H, z->x, z->y - w->y_off, z->w, z->h, w->ctx->d_tabs, w->active_on ? w->d_awake : nullptr,
                           w->acols, w->y_off, w->stream));
+    std::swap(w->p.tmp, w->tmp_scratch);  // the new plane is the temperature plane from here on (later launches read w->p on this stream)
     w->ctx->launches += 2;
     if (w->strip && w->ctx->nranks > 1) return strip_refresh(w, w->stream);
     return FSE_OK;
@@ -1001,6 +993,27 @@ FSE_API int fse_kernel_timing_read(fse_world* w, double* total_ms, int64_t* laun
 }
 
 }  // extern "C"
+
+namespace fse {
+// Rects are in global coordinates; a strip world holds rows [y_off, y_off + H).
+int check_rect(fse_world* w, int x, int y, int rw, int rh, const char* who) {
+    if (rw <= 0 || rh <= 0 || x < 0 || y < w->y_off || (int64_t)x + rw > w->W || (int64_t)y + rh > (int64_t)w->y_off + w->H)
+        return fail(FSE_EINVAL, "%s: rect (%d,%d,%d,%d) outside the held rows [%d,%d) of the %dx%d world", who, x, y, rw, rh, w->y_off,
+                    w->y_off + w->H, w->W, w->Hglobal);
+    return FSE_OK;
+}
+
+int ensure_stage(fse_world* w, size_t cells) {
+    if (w->stage_cells >= cells) return FSE_OK;
+    cudaFree(w->d_stage);
+    w->d_stage = nullptr;
+    w->stage_cells = 0;
+    CK(cudaMalloc(&w->d_stage, cells * sizeof(fse_cell)));
+    w->stage_cells = cells;
+    return FSE_OK;
+}
+}  // namespace fse
+
 
 namespace fse {
 // Make room for `need` more particles before a call that spawns them.  exact: read the live count (one stream sync; rare calls

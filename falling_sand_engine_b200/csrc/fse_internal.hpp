@@ -110,8 +110,21 @@ struct fse_world {
     // render planes (fse_render.cu): main | fire | emission RGBA, W*H words each; scroll scratch (largest plane)
     uint32_t* d_pixels = nullptr;
     void* d_render_stats = nullptr;
-    void* scroll_scratch = nullptr;
-    size_t scroll_scratch_bytes = 0;
+    // scroll: a second set of planes; fse_scroll writes the shifted world into it and swaps the two sets (no copy back)
+    fse::Planes p_shadow{};
+    // liquid flow accumulators (fse_flow_enable): flowX | flowY | prevFlowX | prevFlowY, W*H floats each, + the flow texture
+    float* d_flow = nullptr;
+    uint32_t* d_pixels_flow = nullptr;
+    // second cell layer and background colours (fse_layer2_* / fse_background_*), allocated on first use; layer_dirty: bit 0 layer2Dirty,
+    // bit 1 backgroundDirty; textures: layer 2 | background
+    uint8_t* l2_mat = nullptr;
+    int16_t* l2_tmp = nullptr;
+    uint32_t *l2_col = nullptr, *bg_col = nullptr;
+    uint8_t* layer_dirty = nullptr;
+    uint32_t* d_pixels_layers = nullptr;
+    uint8_t* l2_mat_s = nullptr;   // scroll targets of the layer planes (swapped like p_shadow)
+    int16_t* l2_tmp_s = nullptr;
+    uint32_t *l2_col_s = nullptr, *bg_col_s = nullptr;
     // stats / staging
     void* d_stats = nullptr;
     void* h_stats = nullptr;
@@ -122,6 +135,7 @@ struct fse_world {
     bool kt_enabled = false;
     size_t kt_used = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kt_events;
+    int strip_boundary_min = 64;            // cut-adjacent chunk rows of at least this many chunks use the per-pass kernels
     bool timeline_on = false;               // FSE_STRIP_TIMELINE=1: events per strip phase (fse_strip_timeline_read)
     std::vector<cudaEvent_t> timeline_ev;
     size_t timeline_used = 0;
@@ -141,6 +155,9 @@ extern thread_local std::string g_err;
 int fail(int code, const char* fmt, ...);
 int fse_wake_rect(fse_world* w, int x, int y_local, int rw, int rh);  // wake the chunks under a rect of local rows (active tracking)
 
+int check_rect(fse_world* w, int x, int y, int rw, int rh, const char* who);  // rect in global coordinates inside the held rows
+int ensure_stage(fse_world* w, size_t cells);                                 // w->d_stage holds at least `cells` fse_cell
+void render_free(fse_world* w);                                               // planes owned by fse_render.cu
 int particles_headroom(fse_world* w, int64_t need, bool exact);  // grow the particle pool before a call that spawns up to `need`
 int strip_exchange(fse_world* w, int ofy, int j0, int j1, int zone_y_local, cudaStream_t s);
 void particles_strip_free(fse_world* w);

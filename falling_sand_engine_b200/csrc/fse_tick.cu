@@ -95,6 +95,8 @@ struct Ctx {
     int yoff;  // global y of local row 0 (strip worlds), 0 otherwise
     int ringn, ringmask, koff;  // ring geometry of the running kernel (rows kernels): slot(k) = (k + koff) mod ringn
     int air, fire, water, lava, steam, obsidian;
+    float *flowx, *flowy;  // world::flowX / flowY (render-only accumulators), null when the world does not keep them
+    int W;                 // cells per world row (index of a cell in the flow planes)
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------
@@ -986,6 +988,8 @@ __global__ void __launch_bounds__(128, 3) tick_chunk_kernel(const __grid_constan
     c.nmat = T->n;
     c.yoff = P.y_off;
     c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
+    c.flowx = c.flowy = nullptr;  // the classes schedule keeps no flow accumulators (fse_flow_enable refuses it)
+    c.W = P.W;
 
     // prologue: rows -HALO_DN .. HALO_UP+PF-1
     if (warp == 3 && lane == 0) {

@@ -81,6 +81,11 @@ __device__ __forceinline__ int slotk(const Ctx& c, int k) { return (RN & (RN - 1
 #define FSE_P1_PHASE(slot, since) do { } while (0)
 #endif
 
+// fire-and-forget float add to global memory (RED.E.ADD.F32; nothing is returned, so no latency is exposed).  Like every global f32
+// atomic it flushes subnormals to zero; liquid flows are differences of amounts >= FLUID_MinValue (>= 5e-11), far above that range.
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
 __device__ __forceinline__ void pass_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 __device__ __forceinline__ float clampflow(float flow, float cap, bool speed) {
@@ -385,6 +390,14 @@ __device__ void commit1(const Ctx& c, Scratch1& R, const Dec1& d, int s, int j, 
             }
             oL = d.fL;
             oR = d.fR;
+            if (c.flowx) {  // world.cpp:1334, 1374, 1402, 1432 — the flows as decided; fire-and-forget reductions (RED.ADD.F32), same
+                            // thread and address in program order, so flowY gets +down before -up and flowX -left before +right
+                const size_t g = (size_t)(y - c.yoff) * c.W + x;
+                if (d.fD != 0) red_add_f32(c.flowy + g, d.fD);
+                if (d.fL != 0) red_add_f32(c.flowx + g, -d.fL);
+                if (d.fR != 0) red_add_f32(c.flowx + g, d.fR);
+                if (d.fU != 0) red_add_f32(c.flowy + g, -d.fU);
+            }
             break;
         }
         case A_GAS_UP: {
@@ -881,6 +894,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 2) tick_rows_kernel(const __grid
         c.ringmask = 0;
         c.koff = HALO_DN;
         c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
+        c.flowx = P.flowx; c.flowy = P.flowy; c.W = P.W;
     }
     __syncthreads();
 
@@ -1243,6 +1257,7 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
         c.ringmask = 0;
         c.koff = -G::KMIN;
         c.air = T->air; c.fire = T->fire; c.water = T->water; c.lava = T->lava; c.steam = T->steam; c.obsidian = T->obsidian;
+        c.flowx = P.flowx; c.flowy = P.flowy; c.W = P.W;
     }
     __syncthreads();
     // ---- segments ----------------------------------------------------------------------------------------------------------------

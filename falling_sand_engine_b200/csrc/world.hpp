@@ -148,12 +148,23 @@ public:
     void explosion(int x, int y, int r) { check(fse_explosion(h_, x, y, r, tickCt, seed)); }
     // world::tickChunks() grid + particle shift (world.cpp:2454-2478, 2579-2582); chunk load / save stays with the caller
     void scroll(int changeX, int changeY) { check(fse_scroll(h_, changeX, changeY)); }
-    // the dirty -> texture loop of game::tick (game.cpp:1994-2060) followed by memset(dirty) (game.cpp:2153)
-    void renderDirty(fse_render_stats* movingTiles = nullptr) {
+    // the dirty -> texture loops of game::tick (game.cpp:1994-2126) followed by the dirty clears (game.cpp:2153-2155)
+    void renderDirty(fse_render_stats* movingTiles = nullptr, bool drawBackgroundGrid = false) {
         check(fse_pixels_enable(h_, 1));
         check(fse_render_dirty(h_, movingTiles));
+        check(fse_render_layers(h_, drawBackgroundGrid ? 1 : 0, nullptr, nullptr));
         check(fse_clear_dirty(h_));
     }
+    // world::flowX / flowY (world.hpp:116-119): kept by the tick from now on, drawn into the flow texture by renderDirty
+    void enableFlow(bool on = true) { check(fse_flow_enable(h_, on ? 1 : 0)); }
+    // setTileLayer2 (world.cpp:1015-1019) and the background part of the chunk merge (world.cpp:2384-2389)
+    void setTileLayer2(int x, int y, const fse_cell& c) { check(fse_layer2_write_rect(h_, x, y, 1, 1, &c)); }
+    fse_cell getTileLayer2(int x, int y) {
+        fse_cell c{};
+        check(fse_layer2_read_rect(h_, x, y, 1, 1, &c));
+        return c;
+    }
+    void setBackground(int x, int y, int w, int h, const uint32_t* argb) { check(fse_background_write_rect(h_, x, y, w, h, argb)); }
     // world::tickEntities (world.cpp:3010-3247), WorldEntitySystem::process (game/player.cpp:173-199), objectDelete (game.cpp:2128-2139)
     void tickEntities(std::vector<fse_entity>& ents) {
         if (!ents.empty()) check(fse_entities_tick(h_, ents.data(), (int)ents.size(), loadZoneX, loadZoneY, tickCt, seed));

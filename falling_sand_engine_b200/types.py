@@ -77,7 +77,7 @@ class Stats(C.Structure):
 
 
 class RenderStats(C.Structure):
-    _fields_ = [("dirty", C.c_int64), ("fire", C.c_int64), ("moving", C.c_int64 * FSE_MAX_MATERIALS)]
+    _fields_ = [("dirty", C.c_int64), ("fire", C.c_int64), ("moving", C.c_int64 * FSE_MAX_MATERIALS), ("flow", C.c_int64)]
 
 
 # fse_cell (20 bytes)

@@ -319,31 +319,54 @@ FSE_API int fse_tool_vacuum(fse_world* w, int32_t wcx, int32_t wcy, int32_t wmx,
  * they are collected (dropped by the next fse_particles_tick).  n_collected may be null. */
 FSE_API int fse_particles_vacuum_pull(fse_world* w, float target_x, float target_y, int32_t* n_collected);
 
-/* ---- render planes: the dirty -> texture loop of game::tick (game.cpp:1994-2060).  Every cell whose dirty
- * flag is set refreshes its texel in three device-resident RGBA8 planes (byte order r, g, b, a as the reference fills
+/* ---- render planes: the dirty -> texture loops of game::tick (game.cpp:1994-2126).  Every cell whose dirty
+ * flag is set refreshes its texel in device-resident RGBA8 planes (byte order r, g, b, a as the reference fills
  * dpixels_ar): main (colour + material alpha; AIR = transparent black), fire (only FIRE cells write it, AIR clears it,
- * other materials leave it alone) and emission (Material::emitColor).  movingTiles[mat] counts the dirty cells per
- * material (game.cpp:1998-2000).  The flow texture is not produced (the tick does not keep flowX / flowY).  Dirty flags
- * are left set, as in the reference (fse_clear_dirty = game.cpp:2153). */
+ * other materials leave it alone), emission (Material::emitColor) and — with fse_flow_enable — flow (game.cpp:2040-2062:
+ * the smoothed flowX / flowY of dirty liquid cells, r = x, g = y, b = 0, a = 255).  movingTiles[mat] counts the dirty cells
+ * per material (game.cpp:1998-2000).  Dirty flags are left set, as in the reference (fse_clear_dirty = game.cpp:2153). */
 typedef struct fse_render_stats {
     int64_t dirty;                       /* hadDirty: number of dirty cells */
     int64_t fire;                        /* hadFire: dirty FIRE cells */
     int64_t moving[FSE_MAX_MATERIALS];   /* movingTiles */
+    int64_t flow;                        /* hadFlow: dirty liquid cells (0 unless fse_flow_enable) */
 } fse_render_stats;
-enum { FSE_PIXELS_MAIN = 0, FSE_PIXELS_FIRE = 1, FSE_PIXELS_EMISSION = 2 };
-/* allocate (zeroed: transparent) / free the three planes */
+enum { FSE_PIXELS_MAIN = 0, FSE_PIXELS_FIRE = 1, FSE_PIXELS_EMISSION = 2, FSE_PIXELS_FLOW = 3, FSE_PIXELS_LAYER2 = 4, FSE_PIXELS_BACKGROUND = 5 };
+/* allocate (zeroed: transparent) / free the main, fire and emission planes */
 FSE_API int fse_pixels_enable(fse_world* w, int enable);
 /* refresh the texels of all dirty cells; `out` may be null (no host sync then) */
 FSE_API int fse_render_dirty(fse_world* w, fse_render_stats* out);
 /* copy a rect of one plane to the host, rw*rh*4 bytes */
 FSE_API int fse_pixels_read(fse_world* w, int which, int32_t x, int32_t y, int32_t rw, int32_t rh, uint8_t* rgba);
-/* device pointer of a plane (W*H RGBA8, row-major) for CUDA-GL interop or further kernels; null when disabled */
+/* device pointer of a plane (W*H RGBA8, row-major) for CUDA-GL interop or further kernels; null when that plane is not allocated */
 FSE_API void* fse_pixels_device(fse_world* w, int which);
 
+/* ---- liquid flow accumulators: world::flowX / flowY / prevFlowX / prevFlowY (world.hpp:116-119).  While enabled, pass 1 of
+ * fse_tick adds every liquid flow it decides to the source cell (flowY += down, flowX -= left, flowX += right, flowY -= up;
+ * world.cpp:1334, 1374, 1402, 1432) and fse_render_dirty turns them into the flow texture and resets them.  Render-only
+ * state: 16 B per cell + the texture, rows schedule only, off by default. */
+FSE_API int fse_flow_enable(fse_world* w, int enable);
+/* which: 0 flowX, 1 flowY, 2 prevFlowX, 3 prevFlowY; rw*rh floats */
+FSE_API int fse_flow_read(fse_world* w, int which, int32_t x, int32_t y, int32_t rw, int32_t rh, float* out);
+
+/* ---- second cell layer and background colours: world::real_layer2 / background (world.hpp:112-113), written by
+ * setTileLayer2 (world.cpp:1015-1019) and the chunk merge (world.cpp:2384-2389), read by the renderer only (the tick never
+ * touches them).  Allocated on first use (13 B per cell + two textures).  A write sets layer2Dirty / backgroundDirty;
+ * fse_render_layers (game.cpp:2068-2126 + the clears of 2154-2155) refreshes FSE_PIXELS_LAYER2 / FSE_PIXELS_BACKGROUND from the
+ * dirty cells and clears the marks.  Of an fse_cell the layer keeps mat, color and temp (what a chunk file holds). */
+FSE_API int fse_layer2_write_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, const fse_cell* cells);
+FSE_API int fse_layer2_read_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, fse_cell* cells);
+FSE_API int fse_background_write_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, const uint32_t* argb);
+FSE_API int fse_background_read_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, uint32_t* argb);
+/* draw_background_grid = globaldef.draw_background_grid; the counts (hadLayer2Dirty / hadBackgroundDirty as cell counts) may be null */
+FSE_API int fse_render_layers(fse_world* w, int draw_background_grid, int64_t* n_layer2, int64_t* n_background);
+
 /* ---- camera scroll: the grid shift of world::tickChunks (world.cpp:2454-2478, 2579-2582).  Every cell
- * moves by (dx, dy); cells whose source lies outside the world keep their old content (the reference's in-place copy),
- * dirty flags stay where they are (world::dirty is not shifted), loose particles move along.  Chunk load / save around
- * the scroll stays with the host (fse_write_rect / fse_read_rect).  Not available on multi-rank strips. */
+ * (and its layer-2 cell and background colour, when those planes exist) moves by (dx, dy); cells whose source lies outside the
+ * world keep their old content (the reference's in-place copy), dirty flags stay where they are (world::dirty is not
+ * shifted), loose particles move along.  The shifted world is written into a second set of planes which then becomes the
+ * world (one read + one write per cell).  Chunk load / save around the scroll stays with the host (fse_write_rect /
+ * fse_read_rect).  Not available on multi-rank strips. */
 FSE_API int fse_scroll(fse_world* w, int32_t dx, int32_t dy);
 
 /* ---- fracture / hitbox outlines: updateRigidBodyHitbox, updateChunkMesh (world.cpp:288-720, 722-959) with

@@ -389,10 +389,12 @@ OAPI int fseo_bodies_raster(void* p, int n, const int* bw, const int* bh, fse_ce
     bodies_raster((World*)p, n, bw, bh, tiles, xf, tick, seed, feedback);
     return 0;
 }
-// The dirty -> texture loop of game::tick (game.cpp:1994-2060), flow texture left out (the tick keeps no flowX / flowY).
-// px_main / px_fire / px_emis: width*height RGBA8 texels in the reference's byte order (r, g, b, a).
-void render_dirty(const World* w, uint8_t* px_main, uint8_t* px_fire, uint8_t* px_emis, int64_t* moving, int64_t* had) {
-    had[0] = had[1] = 0;
+// The dirty -> texture loop of game::tick (game.cpp:1994-2066).  px_main / px_fire / px_emis / px_flow: width*height RGBA8 texels in the
+// reference's byte order (r, g, b, a).  The flow texture and the flowX / flowY reset (2017-2018, 2040-2062) run when the world carries
+// the flow accumulators (World::enable_flows) and px_flow is given; had[2] counts the dirty SOUP cells (hadFlow).
+void render_dirty(World* w, uint8_t* px_main, uint8_t* px_fire, uint8_t* px_emis, uint8_t* px_flow, int64_t* moving, int64_t* had) {
+    had[0] = had[1] = had[2] = 0;
+    const bool flows = w->flowX_ != nullptr && px_flow != nullptr;
     for (int i = 0; i < w->n_materials(); i++) moving[i] = 0;
     for (int i = 0; i < w->width * w->height; i++) {
         const unsigned int offset = (unsigned int)i * 4;
@@ -402,6 +404,7 @@ void render_dirty(const World* w, uint8_t* px_main, uint8_t* px_fire, uint8_t* p
         moving[t.mat->id]++;
         if (t.mat->physicsType == AIR) {
             for (int q = 0; q < 4; q++) px_main[offset + q] = px_fire[offset + q] = px_emis[offset + q] = 0;  // ME_ALPHA_TRANSPARENT = 0
+            if (flows) w->flowY_[i] = w->flowX_[i] = 0;  // 2017-2018
             continue;
         }
         const uint32_t color = t.color, emit = t.mat->emitColor;
@@ -420,7 +423,109 @@ void render_dirty(const World* w, uint8_t* px_main, uint8_t* px_fire, uint8_t* p
             px_fire[offset + 3] = t.mat->alpha;
             had[1]++;
         }
+        if (!flows) continue;
+        if (t.mat->physicsType == SOUP) {  // 2040-2059: the literals 0.25, 0.5, 3.0, 4.0 are doubles in the reference
+            float newFlowX = w->prevFlowX[i] + (w->flowX_[i] - w->prevFlowX[i]) * 0.25;
+            float newFlowY = w->prevFlowY[i] + (w->flowY_[i] - w->prevFlowY[i]) * 0.25;
+            if (newFlowY < 0) newFlowY *= 0.5;
+            double a;
+            px_flow[offset + 2] = 0;
+            a = newFlowY * (3.0 / t.mat->iterations + 0.5) / 4.0 + 0.5;
+            px_flow[offset + 1] = std::min(std::max(a, 0.0), 1.0) * 255;
+            a = newFlowX * (3.0 / t.mat->iterations + 0.5) / 4.0 + 0.5;
+            px_flow[offset + 0] = std::min(std::max(a, 0.0), 1.0) * 255;
+            px_flow[offset + 3] = 0xff;
+            had[2]++;
+            w->prevFlowX[i] = newFlowX;
+            w->prevFlowY[i] = newFlowY;
+        }
+        w->flowY_[i] = 0;
+        w->flowX_[i] = 0;
     }
+}
+
+// The layer-2 and background loops of the same function (game.cpp:2068-2126): dirty layer-2 cells -> RGBA (AIR: transparent, or the
+// grey checker of globaldef.draw_background_grid), dirty background cells -> their ARGB colour; had[0] / had[1] = cells of each kind.
+// Clears the two dirty planes afterwards like game.cpp:2154-2155.
+void render_layers(World* w, int draw_background_grid, uint8_t* px_layer2, uint8_t* px_bg, int64_t* had) {
+    had[0] = had[1] = 0;
+    if (w->layer2Id.empty()) return;
+    for (int i = 0; i < w->width * w->height; i++) {
+        const unsigned int offset = (unsigned int)i * 4;
+        if (w->layer2Dirty[i]) {
+            had[0]++;
+            const Material& m = w->mats[w->layer2Id[i]];
+            if (m.physicsType == AIR) {
+                if (draw_background_grid) {
+                    const uint32_t color = (i % 2) == 0 ? 0x888888 : 0x444444;
+                    px_layer2[offset + 2] = (color >> 0) & 0xff;
+                    px_layer2[offset + 1] = (color >> 8) & 0xff;
+                    px_layer2[offset + 0] = (color >> 16) & 0xff;
+                    px_layer2[offset + 3] = 0xff;  // ME_ALPHA_OPAQUE
+                } else {
+                    for (int q = 0; q < 4; q++) px_layer2[offset + q] = 0;
+                }
+            } else {
+                const uint32_t color = w->layer2Color[i];
+                px_layer2[offset + 2] = (color >> 0) & 0xff;
+                px_layer2[offset + 1] = (color >> 8) & 0xff;
+                px_layer2[offset + 0] = (color >> 16) & 0xff;
+                px_layer2[offset + 3] = m.alpha;
+            }
+        }
+        if (w->backgroundDirty[i]) {
+            had[1]++;
+            const uint32_t color = w->background[i];
+            px_bg[offset + 2] = (color >> 0) & 0xff;
+            px_bg[offset + 1] = (color >> 8) & 0xff;
+            px_bg[offset + 0] = (color >> 16) & 0xff;
+            px_bg[offset + 3] = (color >> 24) & 0xff;
+        }
+    }
+    if (had[0]) std::fill(w->layer2Dirty.begin(), w->layer2Dirty.end(), 0);
+    if (had[1]) std::fill(w->backgroundDirty.begin(), w->backgroundDirty.end(), 0);
+}
+
+// setTileLayer2 over a rectangle / the layer-2 and background part of the chunk merge (world.cpp:1015-1019, 2384-2389)
+void layer2_write_rect(World* w, int x0, int y0, int rw, int rh, const fse_cell* src) {
+    w->enable_layers();
+    for (int y = 0; y < rh; y++)
+        for (int x = 0; x < rw; x++) {
+            const fse_cell& s = src[x + (size_t)y * rw];
+            const size_t i = (size_t)(x0 + x) + (size_t)(y0 + y) * w->width;
+            w->layer2Id[i] = s.mat;
+            w->layer2Color[i] = s.color;
+            w->layer2Temp[i] = s.temp;
+            w->layer2Dirty[i] = 1;
+        }
+}
+void layer2_read_rect(World* w, int x0, int y0, int rw, int rh, fse_cell* dst) {
+    w->enable_layers();
+    for (int y = 0; y < rh; y++)
+        for (int x = 0; x < rw; x++) {
+            fse_cell& d = dst[x + (size_t)y * rw];
+            const size_t i = (size_t)(x0 + x) + (size_t)(y0 + y) * w->width;
+            std::memset(&d, 0, sizeof d);
+            d.mat = (uint16_t)w->layer2Id[i];
+            d.color = w->layer2Color[i];
+            d.temp = w->layer2Temp[i];
+            d.fluid = 2.0f;  // MaterialInstance default (game_datastruct.hpp:216); chunk files do not keep it
+            d.dirty = w->layer2Dirty[i];
+        }
+}
+void background_write_rect(World* w, int x0, int y0, int rw, int rh, const uint32_t* src) {
+    w->enable_layers();
+    for (int y = 0; y < rh; y++)
+        for (int x = 0; x < rw; x++) {
+            const size_t i = (size_t)(x0 + x) + (size_t)(y0 + y) * w->width;
+            w->background[i] = src[x + (size_t)y * rw];
+            w->backgroundDirty[i] = 1;
+        }
+}
+void background_read_rect(World* w, int x0, int y0, int rw, int rh, uint32_t* dst) {
+    w->enable_layers();
+    for (int y = 0; y < rh; y++)
+        for (int x = 0; x < rw; x++) dst[x + (size_t)y * rw] = w->background[(size_t)(x0 + x) + (size_t)(y0 + y) * w->width];
 }
 
 // The grid shift of world::tickChunks (world.cpp:2454-2478) and the particle shift (2579-2582), loops as in the reference.
@@ -435,7 +540,15 @@ void scroll(World* w, int changeX, int changeY) {
             for (int x = 0; x < width; x++) {
                 const int oldX = revX ? (width - x - 1) : x;
                 const int newX = oldX + changeX;
-                if (newX >= 0 && newX < width) w->tiles[newX + newY * width] = w->tiles[oldX + oldY * width];
+                if (newX >= 0 && newX < width) {
+                    w->tiles[newX + newY * width] = w->tiles[oldX + oldY * width];
+                    if (!w->layer2Id.empty()) {  // background and real_layer2 move with the grid (2475-2476); their dirty planes do not
+                        w->background[newX + newY * width] = w->background[oldX + oldY * width];
+                        w->layer2Id[newX + newY * width] = w->layer2Id[oldX + oldY * width];
+                        w->layer2Color[newX + newY * width] = w->layer2Color[oldX + oldY * width];
+                        w->layer2Temp[newX + newY * width] = w->layer2Temp[oldX + oldY * width];
+                    }
+                }
             }
         }
         for (auto& p : w->cells) {
@@ -445,8 +558,25 @@ void scroll(World* w, int changeX, int changeY) {
     }
 }
 
-OAPI int fseo_render_dirty(void* p, uint8_t* px_main, uint8_t* px_fire, uint8_t* px_emis, int64_t* moving, int64_t* had) {
-    render_dirty((const World*)p, px_main, px_fire, px_emis, moving, had);
+OAPI int fseo_render_dirty(void* p, uint8_t* px_main, uint8_t* px_fire, uint8_t* px_emis, uint8_t* px_flow, int64_t* moving, int64_t* had) {
+    render_dirty((World*)p, px_main, px_fire, px_emis, px_flow, moving, had);
+    return 0;
+}
+OAPI int fseo_render_layers(void* p, int grid, uint8_t* px_layer2, uint8_t* px_bg, int64_t* had) {
+    render_layers((World*)p, grid, px_layer2, px_bg, had);
+    return 0;
+}
+OAPI int fseo_layer2_write_rect(void* p, int x, int y, int w, int h, const fse_cell* c) { layer2_write_rect((World*)p, x, y, w, h, c); return 0; }
+OAPI int fseo_layer2_read_rect(void* p, int x, int y, int w, int h, fse_cell* c) { layer2_read_rect((World*)p, x, y, w, h, c); return 0; }
+OAPI int fseo_background_write_rect(void* p, int x, int y, int w, int h, const uint32_t* c) { background_write_rect((World*)p, x, y, w, h, c); return 0; }
+OAPI int fseo_background_read_rect(void* p, int x, int y, int w, int h, uint32_t* c) { background_read_rect((World*)p, x, y, w, h, c); return 0; }
+OAPI int fseo_flow_enable(void* p) { ((World*)p)->enable_flows(); return 0; }
+// which: 0 flowX, 1 flowY, 2 prevFlowX, 3 prevFlowY; whole planes
+OAPI int fseo_flow_read(void* p, int which, float* out) {
+    World* w = (World*)p;
+    if (!w->flowX_) return -1;
+    const std::vector<float>& v = which == 0 ? w->flowX : which == 1 ? w->flowY : which == 2 ? w->prevFlowX : w->prevFlowY;
+    std::memcpy(out, v.data(), v.size() * sizeof(float));
     return 0;
 }
 OAPI int fseo_scroll(void* p, int dx, int dy) {

@@ -413,6 +413,7 @@ void World::visit1(int x, int y, int iter, std::vector<Particle>& out) {
                 }
                 d.fluidAmountDiff += flow;
             }
+            if (flowY_) flowY_[idx] += flow;  // 1334
         } else if (iter == 0 && bottom.mat->physicsType == SOUP && (bottom.mat->id != tile.mat->id)) {  // 1335-1341
             if (draw(S_SOUP_SWAP_DOWN, x, y) % 10 == 0) {
                 tiles[idx] = bottom;
@@ -451,6 +452,7 @@ void World::visit1(int x, int y, int iter, std::vector<Particle>& out) {
                 }
                 d.fluidAmountDiff += flow;
             }
+            if (flowX_) flowX_[idx] -= flow;  // 1374
         }
         if (remainingValue < FLUID_MinValue) {  // 1377-1381
             tile.fluidAmountDiff -= remainingValue;
@@ -477,6 +479,7 @@ void World::visit1(int x, int y, int iter, std::vector<Particle>& out) {
                 }
                 d.fluidAmountDiff += flow;
             }
+            if (flowX_) flowX_[idx] += flow;  // 1402
         }
         if (remainingValue < FLUID_MinValue) {  // 1405-1409
             tile.fluidAmountDiff -= remainingValue;
@@ -505,6 +508,7 @@ void World::visit1(int x, int y, int iter, std::vector<Particle>& out) {
                 }
                 d.fluidAmountDiff += flow;
             }
+            if (flowY_) flowY_[idx] -= flow;  // 1432
         } else if (iter == 0 && top.mat->physicsType == SOUP && (top.mat->id != tile.mat->id)) {  // 1433-1439
             if (draw(S_SOUP_SWAP_UP, x, y) % 10 == 0) {
                 tiles[idx] = top;

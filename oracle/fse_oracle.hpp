@@ -222,6 +222,31 @@ public:
     std::vector<uint8_t> visitedA, visitedB;
     uint8_t* visited = nullptr;  // current tickVisited plane
     std::vector<int32_t> newTemps;
+    // render-only liquid flow accumulators (world.hpp:116-119; written at world.cpp:1334, 1374, 1402, 1432, consumed and reset by the
+    // dirty -> texture loop, game.cpp:2017-2062).  Off (null) until enable_flows(): the timed CPU baseline does not carry them.
+    std::vector<float> flowX, flowY, prevFlowX, prevFlowY;
+    float *flowX_ = nullptr, *flowY_ = nullptr;
+    void enable_flows() {
+        const size_t n = (size_t)width * height;
+        flowX.assign(n, 0.0f); flowY.assign(n, 0.0f); prevFlowX.assign(n, 0.0f); prevFlowY.assign(n, 0.0f);
+        flowX_ = flowX.data(); flowY_ = flowY.data();
+    }
+    // second cell layer and background colours (world.hpp:112-113 real_layer2 / background, world.cpp:1012-1019 setTileLayer2): static
+    // planes next to the grid that only the chunk merge and the renderer touch; allocated on first use
+    // (kept as id / colour / temperature — what a chunk file holds of it, chunk.hpp:26-30 — so a material-table rebuild leaves it alone)
+    std::vector<uint32_t> layer2Id, layer2Color, background;
+    std::vector<int16_t> layer2Temp;
+    std::vector<uint8_t> layer2Dirty, backgroundDirty;
+    void enable_layers() {
+        if (!layer2Id.empty()) return;
+        const size_t n = (size_t)width * height;
+        layer2Id.assign(n, (uint32_t)ids.air);  // Tiles_NOTHING (world.cpp:117-119)
+        layer2Color.assign(n, 0u);
+        layer2Temp.assign(n, 0);
+        background.assign(n, 0u);
+        layer2Dirty.assign(n, 0);
+        backgroundDirty.assign(n, 0);
+    }
     std::vector<Particle> cells;  // world::cells
     std::vector<Material> mats;
     fse_special_ids ids{};

@@ -219,14 +219,67 @@ def prt_end(world):
     lib().fseo_prt_end(world.h)
 
 
-def render_dirty(world, planes):
-    """game.cpp:1994-2060 on the oracle world; planes = (main, fire, emission) uint8 arrays (h, w, 4), updated in place.
-    Returns (dirty cells, dirty FIRE cells, movingTiles[n_materials])."""
+def render_dirty(world, planes, with_flow_count=False):
+    """game.cpp:1994-2066 on the oracle world; planes = (main, fire, emission[, flow]) uint8 arrays (h, w, 4), updated in place (the
+    flow texture and the flowX / flowY reset need flow_enable(world) and a fourth plane).
+    Returns (dirty cells, dirty FIRE cells, movingTiles[n_materials]) [+ dirty SOUP cells with with_flow_count]."""
     moving = np.zeros(256, dtype=np.int64)
-    had = np.zeros(2, dtype=np.int64)
-    lib().fseo_render_dirty.argtypes = [C.c_void_p] + [C.c_void_p] * 5
-    lib().fseo_render_dirty(world.h, planes[0].ctypes.data, planes[1].ctypes.data, planes[2].ctypes.data, moving.ctypes.data, had.ctypes.data)
+    had = np.zeros(3, dtype=np.int64)
+    lib().fseo_render_dirty.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    flow = planes[3].ctypes.data if len(planes) > 3 else None
+    lib().fseo_render_dirty(world.h, planes[0].ctypes.data, planes[1].ctypes.data, planes[2].ctypes.data, flow, moving.ctypes.data, had.ctypes.data)
+    if with_flow_count:
+        return int(had[0]), int(had[1]), moving, int(had[2])
     return int(had[0]), int(had[1]), moving
+
+
+def flow_enable(world):
+    """Carry flowX / flowY / prevFlowX / prevFlowY (world.hpp:116-119) from now on."""
+    lib().fseo_flow_enable.argtypes = [C.c_void_p]
+    lib().fseo_flow_enable(world.h)
+
+
+def flow_read(world, which):
+    """Whole plane: 0 flowX, 1 flowY, 2 prevFlowX, 3 prevFlowY."""
+    out = np.zeros((world.height, world.width), dtype=np.float32)
+    lib().fseo_flow_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    assert lib().fseo_flow_read(world.h, which, out.ctypes.data) == 0, "flow_enable first"
+    return out
+
+
+def layer2_write_rect(world, x, y, cells):
+    c = np.ascontiguousarray(cells, dtype=T.CELL_DTYPE)
+    lib().fseo_layer2_write_rect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib().fseo_layer2_write_rect(world.h, x, y, c.shape[1], c.shape[0], c.ctypes.data)
+
+
+def layer2_read_rect(world, x, y, w, h):
+    out = np.zeros((h, w), dtype=T.CELL_DTYPE)
+    lib().fseo_layer2_read_rect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib().fseo_layer2_read_rect(world.h, x, y, w, h, out.ctypes.data)
+    return out
+
+
+def background_write_rect(world, x, y, colors):
+    c = np.ascontiguousarray(colors, dtype=np.uint32)
+    lib().fseo_background_write_rect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib().fseo_background_write_rect(world.h, x, y, c.shape[1], c.shape[0], c.ctypes.data)
+
+
+def background_read_rect(world, x, y, w, h):
+    out = np.zeros((h, w), dtype=np.uint32)
+    lib().fseo_background_read_rect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib().fseo_background_read_rect(world.h, x, y, w, h, out.ctypes.data)
+    return out
+
+
+def render_layers(world, planes, draw_background_grid=False):
+    """game.cpp:2068-2126 + the dirty clears of 2154-2155; planes = (layer2, background) uint8 arrays (h, w, 4), updated in place.
+    Returns (dirty layer-2 cells, dirty background cells)."""
+    had = np.zeros(2, dtype=np.int64)
+    lib().fseo_render_layers.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib().fseo_render_layers(world.h, 1 if draw_background_grid else 0, planes[0].ctypes.data, planes[1].ctypes.data, had.ctypes.data)
+    return int(had[0]), int(had[1])
 
 
 def scroll(world, dx, dy):

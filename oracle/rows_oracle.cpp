@@ -392,6 +392,14 @@ struct RowsImpl {
                         if (d.botSoup) T(x, y + 1).moved = false;
                     }
                 }
+                if (W.flowY_) {  // world.cpp:1334, 1374, 1402, 1432: the flows as decided (a flow handed back in C2 still counts)
+                    float& fy = W.flowY_[idx];
+                    float& fx = W.flowX_[idx];
+                    if (d.flowD != 0) fy += d.flowD;
+                    if (d.flowL != 0) fx -= d.flowL;
+                    if (d.flowR != 0) fx += d.flowR;
+                    if (d.flowU != 0) fy -= d.flowU;
+                }
                 outL[k] = d.flowL;
                 outR[k] = d.flowR;
                 chg[k] = d.changed ? (uint8_t)((d.leftSoup ? 1 : 0) | (d.rightSoup ? 2 : 0)) : 0;

@@ -330,5 +330,21 @@ def test_chunk_save_and_load_through_pack_files(gpu_ctx, table, tmp_path):
     for f in ("mat", "color", "temp"):
         assert np.array_equal(src[f], dst[f]), f
     assert dst["dirty"].all() and (dst["fluid"] == 2.0).all() and not dst["moved"].any()
+    # with the layer planes: layer-2 cells and background colours travel through the file into the other world's planes
+    l2 = np.zeros((128, 128), dtype=T.CELL_DTYPE)
+    l2["mat"][10:20, 5:50], l2["color"][10:20, 5:50], l2["temp"][10:20, 5:50] = 7, 0x334455, 12
+    bg = (np.arange(128 * 128, dtype=np.uint32).reshape(128, 128) * np.uint32(40503)) | np.uint32(0xFF000000)
+    a.layer2_write_rect(128, 256, l2)
+    a.background_write_rect(128, 256, bg)
+    a.save_chunk(path, 128, 256, layers=True)
+    b.load_chunk(path, 256, 128, layers=True)
+    got = b.layer2_read_rect(256, 128, 128, 128)
+    for f in ("mat", "color", "temp"):
+        assert np.array_equal(got[f], l2[f]), f
+    assert got["dirty"].all() and np.array_equal(b.background_read_rect(256, 128, 128, 128), bg)
+    assert b.render_layers() == (128 * 128, 128 * 128)
+    d = str(tmp_path / "world")
+    assert a.save_world(d) == 16 and b.load_world(d) == 16
+    assert np.array_equal(b.layer2_read_rect(128, 256, 128, 128)["color"], l2["color"])
     a.close()
     b.close()

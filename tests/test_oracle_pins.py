@@ -346,7 +346,7 @@ def test_lua_material_script_front_door(oracle):
 
 
 def test_chunk_pack_files_round_trip(oracle, table, tmp_path):
-    """Chunk::ChunkWrite / ChunkRead (chunk.cpp:74-330): header fields, the 12-byte on-disk cell {u16 index, u32 color, i16
+    """Chunk::ChunkWrite / ChunkRead (chunk.cpp:74-330): header fields, the 12-byte on-disk cell {u32 index, u32 color, i16
     temperature}, two LZ4 blocks; what comes back is what the reference restores (material, colour, temperature; fluidAmount 2.0
     and the other per-tick fields at their defaults).  A saved oracle world reloads into an identical grid apart from those."""
     import struct
@@ -380,9 +380,20 @@ def test_chunk_pack_files_round_trip(oracle, table, tmp_path):
     back = ow2.read_rect(128, 128, 128, 128)
     for f in ("mat", "color", "temp"):
         assert np.array_equal(back[f], tiles[f])
+    with pytest.raises(IOError):
+        chunkfile.read_pack(path, n_materials=5)  # cells index past a 5-entry material table
+    assert chunkfile.read_pack(path, n_materials=table.n)[0] == 5
     open(path, "wb").write(raw[:17] + raw[17:17 + csize - 9] + raw[17 + csize:])  # damage the first block
     with pytest.raises(IOError):
         chunkfile.read_pack(path)
+    open(path, "wb").write(raw[:9])  # truncated header
+    with pytest.raises(IOError):
+        chunkfile.read_pack(path)
+    open(path, "wb").write(struct.pack("<biiii", 5, src_size, -1, src_size2, csize2) + raw[17:])  # a negative size must not slurp the file
+    with pytest.raises(IOError):
+        chunkfile.read_pack(path)
+    with pytest.raises(ValueError):
+        chunkfile.save_world(ow, str(tmp_path / "w"), 384, 200)  # not whole chunks
 
 
 def test_world_save_and_load_directory(oracle, table, tmp_path):
