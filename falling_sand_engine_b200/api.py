@@ -274,6 +274,18 @@ class World:
         return out
 
     # -- fracture outlines (world.cpp:288-720, physics_math.cpp:1766-1965) and physicsCheck flood (world.cpp:3330) ------
+    def physics_check(self, x, y, cap_tiles=1 << 20):
+        """world::physicsCheck (world.cpp:3330-3411): returns (count, action, (x, y, w, h), tiles or None) — action 0 nothing, 1 the
+        1..10-cell crumb was deleted, 2 the 11..1000-cell component was cut out into `tiles` (h x w fse_cell array of the new body)."""
+        class Res(C.Structure):
+            _fields_ = [(n, C.c_int32) for n in ("count", "action", "x", "y", "w", "h")]
+        res = Res()
+        tiles = np.zeros(cap_tiles, dtype=T.CELL_DTYPE)
+        self.L.fse_physics_check.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        _ck(self.L.fse_physics_check(self.h, x, y, C.byref(res), tiles.ctypes.data, cap_tiles))
+        box = (res.x, res.y, res.w, res.h)
+        return res.count, res.action, box, (tiles[:res.w * res.h].reshape(res.h, res.w).copy() if res.action == 2 else None)
+
     # -- chunk files (Chunk::ChunkRead / ChunkWrite, chunk.cpp:74-330; the merge of world::frame and chunkSaveCache) ---------
     def load_chunk(self, path, x, y, layers=False):
         """Read a .pack file and merge it into the grid at (x, y), marked dirty like world::frame does (world.cpp:2374-2391): the

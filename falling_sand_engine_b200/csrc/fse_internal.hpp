@@ -21,6 +21,7 @@ struct fse_ctx {
     // multi-GPU (fse_comm.cu)
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    bool spiral_ready = false;  // fse_particles.cu: the deposit spiral's offset table is in constant memory
 };
 
 struct fse_world {

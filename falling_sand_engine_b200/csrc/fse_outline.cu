@@ -287,6 +287,39 @@ __global__ void flood_kernel(const uint8_t* mat, const DevTables* T, int W, int 
     if (threadIdx.x == 0) *out_count = q_tail > cap ? cap + 1 : q_tail;
 }
 
+// world::physicsCheck, the cut (world.cpp:3352-3395): every cell of the component becomes Tiles_NOTHING (dirty); with `tiles` the cell's
+// colour goes into the w x h tile array of the new body as OBSIDIAN (what makeRigidBody builds from the colour surface, world.cpp:191-209).
+__global__ void physcheck_cut_kernel(Planes p, const DevTables* T, int W, const int* pixels, int n, int minx, int miny, int bw, fse_cell* tiles) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = pixels[i];
+    if (tiles) {
+        fse_cell t;
+        memset(&t, 0, sizeof t);
+        t.mat = (uint16_t)T->obsidian;
+        t.color = p.col[g];
+        t.temp = T->ctemp[T->obsidian];
+        t.fluid = 2.0f;
+        tiles[(g % W - minx) + (g / W - miny) * bw] = t;
+    }
+    p.mat[g] = (uint8_t)T->air;
+    p.flg[g] = F_DIRTY;
+    p.stl[g] = 0;
+    p.tmp[g] = 0;
+    p.col[g] = 0;
+    p.fl[g] = 2.0f;
+    p.fd[g] = 0.0f;
+}
+__global__ void fill_air_tiles_kernel(fse_cell* tiles, int n, uint16_t air) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fse_cell t;
+    memset(&t, 0, sizeof t);
+    t.mat = air;
+    t.fluid = 2.0f;
+    tiles[i] = t;
+}
+
 static cudaError_t grow_scratch(fse_world* w, size_t need) {
     if (w->outline_scratch_bytes >= need) return cudaSuccess;
     cudaFree(w->outline_scratch);
@@ -444,5 +477,65 @@ extern "C" FSE_API int fse_flood_component(fse_world* w, int32_t x, int32_t y, i
         if (pixels) pixels[i] = cx + cy * w->W;
     }
     if (bbox) memcpy(bbox, bb, sizeof bb);
+    return FSE_OK;
+}
+
+// world::physicsCheck(x, y) (world.cpp:3330-3411) as one call: flood, then delete (1..10 cells) or cut out into a body (11..1000).
+extern "C" FSE_API int fse_physics_check(fse_world* w, int32_t x, int32_t y, fse_physcheck_result* out, fse_cell* tiles_out, int32_t cap_tiles) {
+    if (!w || !out) return fail(FSE_EINVAL, "fse_physics_check: null argument");
+    if (w->strip && w->ctx->nranks > 1) return fail(FSE_ESTATE, "fse_physics_check: not available on multi-rank strips");
+    memset(out, 0, sizeof *out);
+    if (x < 0 || y < w->y_off || x >= w->W || y >= w->y_off + w->H) return FSE_OK;
+    CK(cudaSetDevice(w->ctx->device));
+    const int cap = 1000;
+    // scratch: [pixels cap + 4][count 4] ... tiles behind them
+    CK(grow_scratch(w, sizeof(int) * (size_t)(cap + 8)));
+    int* d_pix = (int*)w->outline_scratch;
+    int* d_cnt = d_pix + cap + 4;
+    flood_kernel<<<1, 256, 0, w->stream>>>(w->p.mat, w->ctx->d_tabs, w->W, w->H, x, y - w->y_off, cap, d_pix, d_cnt);
+    CK(cudaGetLastError());
+    w->ctx->launches += 1;
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, d_cnt, sizeof n, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    out->count = n;
+    if (n == 0 || n > cap) return FSE_OK;
+    std::vector<int> px(n);
+    CK(cudaMemcpy(px.data(), d_pix, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    int bb[4] = {w->W, w->H, 0, 0};
+    for (int i = 0; i < n; i++) {
+        const int cx = px[i] % w->W, cy = px[i] / w->W;
+        bb[0] = std::min(bb[0], cx); bb[1] = std::min(bb[1], cy); bb[2] = std::max(bb[2], cx); bb[3] = std::max(bb[3], cy);
+    }
+    out->x = bb[0]; out->y = bb[1] + w->y_off; out->w = bb[2] - bb[0] + 1; out->h = bb[3] - bb[1] + 1;
+    const bool body = n > 10;
+    fse_cell* d_tiles = nullptr;
+    const size_t area = (size_t)out->w * out->h;
+    if (body) {
+        if (!tiles_out || (int64_t)area > (int64_t)cap_tiles)
+            return fail(FSE_EINVAL, "fse_physics_check: the component's %d x %d box needs %zu tiles (cap_tiles = %d); nothing was changed", out->w, out->h,
+                        area, cap_tiles);
+        // the pixel list must survive growing the scratch: put list and tiles into one allocation
+        const size_t off = (sizeof(int) * (size_t)(cap + 8) + 63) / 64 * 64;
+        if (w->outline_scratch_bytes < off + area * sizeof(fse_cell)) {
+            CK(grow_scratch(w, off + area * sizeof(fse_cell)));
+            d_pix = (int*)w->outline_scratch;
+            CK(cudaMemcpyAsync(d_pix, px.data(), sizeof(int) * n, cudaMemcpyHostToDevice, w->stream));
+        }
+        d_tiles = (fse_cell*)((char*)w->outline_scratch + off);
+        fill_air_tiles_kernel<<<(int)((area + 255) / 256), 256, 0, w->stream>>>(d_tiles, (int)area, (uint16_t)w->ctx->h_tabs.air);
+        CK(cudaGetLastError());
+        w->ctx->launches += 1;
+    }
+    physcheck_cut_kernel<<<(n + 255) / 256, 256, 0, w->stream>>>(w->p, w->ctx->d_tabs, w->W, d_pix, n, bb[0], bb[1], out->w, d_tiles);
+    CK(cudaGetLastError());
+    w->ctx->launches += 1;
+    if (w->active_on)
+        if (int r = fse_wake_rect(w, bb[0], bb[1], out->w, out->h)) return r;
+    if (body) {
+        CK(cudaMemcpyAsync(tiles_out, d_tiles, area * sizeof(fse_cell), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaStreamSynchronize(w->stream));
+    }
+    out->action = body ? 2 : 1;
     return FSE_OK;
 }

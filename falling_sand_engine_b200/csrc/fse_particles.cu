@@ -175,46 +175,81 @@ __device__ __forceinline__ void deposit_cell(const PArgs& a, size_t g, const fse
     }
 }
 
+// The reference's 32 x 32 square spiral (world.cpp:2116-2147) as a table: SPIRAL[j] = the (sx, sy) offset tested at step j.  Filled on
+// the host by the very loop of the reference (spiral_table_init) so that a warp can test 32 consecutive steps at once.
+__constant__ signed char SPIRAL[1024][2];
+
 __global__ void particles_propose_kernel(PArgs a) {
     const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= a.n_list || (a.prev_pending && *a.prev_pending == 0)) return;
-    PState* sp = &a.st[a.list[li]];
-    int status = sp->status;
-    if (status < 2) return;
+    const int lane = threadIdx.x & 31;
+    const bool live = li < a.n_list && !(a.prev_pending && *a.prev_pending == 0);
+    PState* sp = live ? &a.st[a.list[li]] : nullptr;
+    int status = live ? sp->status : 0;
+    if (status < 2) status = 0;
     const int W = a.W, H = a.H;
-    const float cx = sp->adv.x, cy = sp->adv.y;
+    float cx = 0.0f, cy = 0.0f;
     long long cand = -1;
-    int merge = 0;
+    int merge = 0, sj = 0, myMat = 0;
+    if (status) {
+        cx = sp->adv.x;
+        cy = sp->adv.y;
+        myMat = sp->adv.tile.mat;
+        sj = sp->sj;
+    }
     if (status == 2) {
         if (phys_at(a, sp->lx, sp->ly) == P_AIR) cand = sp->lx + (long long)sp->ly * W;
         else status = 3;
     }
-    if (status == 3) {
-        int sx = sp->sx, sy = sp->sy, sdx = sp->sdx, sdy = sp->sdy, sj = sp->sj;
-        const int myMat = sp->adv.tile.mat;
-        const bool amSoup = a.T->phys[myMat] == P_SOUP;
-        while (sj < 32 * 32) {  // 2116-2147
-            if (-16 <= sx && sx <= 16 && -16 <= sy && sy <= 16) {
-                const int px = (int)(cx + sx), py = (int)(cy + sy);
-                if (px >= 0 && py >= 0 && px < W && py < H) {
-                    const long long g = local_cell(a, px, py);
-                    if (g >= 0) {
-                        const int m = a.p.mat[g];
-                        if (a.T->phys[m] == P_AIR) { cand = px + (long long)py * W; break; }
-                        if (amSoup && m == myMat) { cand = px + (long long)py * W; merge = 1; break; }
+    // Spiral searches, one particle at a time by the whole warp: lane l tests step sj + l of the spiral, the lowest step that finds AIR
+    // (or the particle's own liquid to merge into) wins — exactly the cell the reference's sequential loop stops at, in 1/32 of the
+    // dependent loads.  (A single thread walking up to 1024 steps of two dependent global loads each made this kernel's time.)
+    unsigned need = __ballot_sync(0xffffffffu, status == 3);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const float bcx = __shfl_sync(0xffffffffu, cx, src), bcy = __shfl_sync(0xffffffffu, cy, src);
+        const int bmat = __shfl_sync(0xffffffffu, myMat, src);
+        int base = __shfl_sync(0xffffffffu, sj, src);
+        const bool amSoup = a.T->phys[bmat] == P_SOUP;
+        int found = 32 * 32, fmerge = 0;
+        while (base < 32 * 32) {
+            const int j = base + lane;
+            int hit = 0;  // 1 AIR, 2 same liquid
+            if (j < 32 * 32) {
+                const int sx = SPIRAL[j][0], sy = SPIRAL[j][1];
+                if (-16 <= sx && sx <= 16 && -16 <= sy && sy <= 16) {
+                    const int px = (int)(bcx + sx), py = (int)(bcy + sy);
+                    if (px >= 0 && py >= 0 && px < W && py < H) {
+                        const long long g = local_cell(a, px, py);
+                        if (g >= 0) {
+                            const int m = a.p.mat[g];
+                            if (a.T->phys[m] == P_AIR) hit = 1;
+                            else if (amSoup && m == bmat) hit = 2;
+                        }
                     }
                 }
             }
-            if ((sx == sy) || ((sx < 0) && (sx == -sy)) || ((sx > 0) && (sx == 1 - sy))) {
-                int t = sdx;
-                sdx = -sdy;
-                sdy = t;
+            const unsigned hb = __ballot_sync(0xffffffffu, hit != 0);
+            if (hb) {
+                const int l = __ffs(hb) - 1;
+                found = base + l;
+                fmerge = __shfl_sync(0xffffffffu, hit, l) == 2;
+                break;
             }
-            sx += sdx;
-            sy += sdy;
-            sj++;
+            base += 32;
         }
-        sp->sx = (short)sx; sp->sy = (short)sy; sp->sdx = (short)sdx; sp->sdy = (short)sdy; sp->sj = sj;
+        if (lane == src) {
+            sj = found;
+            if (found < 32 * 32) {
+                const int sx = SPIRAL[found][0], sy = SPIRAL[found][1];
+                cand = (int)(cx + sx) + (long long)(int)(cy + sy) * W;
+                merge = fmerge;
+            }
+        }
+    }
+    if (!status) return;
+    if (status == 3) {
+        sp->sj = sj;
         if (cand < 0) {  // 2154-2157: bounce
             sp->adv.vy = -4.0f;
             sp->adv.y -= 16.0f;
@@ -295,6 +330,28 @@ __global__ void particles_compact_kernel(PArgs a, fse_particle* out) {
     if (p.y > (float)a.H) return;                                  // 2190
     const unsigned int o = atomicAdd(&a.counters[2], 1u);
     out[o] = p;
+}
+
+// SPIRAL <- the offsets the loop of world.cpp:2116-2147 visits, step by step (once per device)
+static cudaError_t spiral_table_init(fse_ctx* c) {
+    if (c->spiral_ready) return cudaSuccess;
+    signed char t[1024][2];
+    int sx = 0, sy = 0, sdx = 0, sdy = -1;
+    for (int j = 0; j < 32 * 32; j++) {
+        // offsets beyond +-16 are never used by the reference (its range check); clamp so they stay out of range in 8 bits
+        t[j][0] = (signed char)(sx < -17 ? -17 : (sx > 17 ? 17 : sx));
+        t[j][1] = (signed char)(sy < -17 ? -17 : (sy > 17 ? 17 : sy));
+        if ((sx == sy) || ((sx < 0) && (sx == -sy)) || ((sx > 0) && (sx == 1 - sy))) {
+            int q = sdx;
+            sdx = -sdy;
+            sdy = q;
+        }
+        sx += sdx;
+        sy += sdy;
+    }
+    cudaError_t e = cudaMemcpyToSymbol(SPIRAL, t, sizeof t);
+    if (e == cudaSuccess) c->spiral_ready = true;
+    return e;
 }
 
 static cudaError_t grow(void** p, size_t* have, size_t need) {
@@ -543,6 +600,7 @@ static int particles_tick_strips(fse_world* w, const fse_rect* z) {
 extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     if (!w || !z) return fail(FSE_EINVAL, "fse_particles_tick: null argument");
     CK(cudaSetDevice(w->ctx->device));
+    CK(spiral_table_init(w->ctx));
     if (w->strip && w->ctx->nranks > 1) return particles_tick_strips(w, z);
     unsigned int n = 0;
     {

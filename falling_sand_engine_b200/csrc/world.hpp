@@ -144,6 +144,19 @@ public:
         pixels.resize(n <= 1000 ? n : 0);
         return n;
     }
+    // the whole of world::physicsCheck: crumbs are deleted, a loose component of 11..1000 cells leaves the grid as the tile array of a
+    // new body (the caller makes the b2Body at (res.x, res.y) and runs updateRigidBodyHitbox on it); returns true when a body was cut out
+    bool physicsCheckCut(int x, int y, fse_physcheck_result& res, std::vector<fse_cell>& tiles) {
+        tiles.assign(1 << 16, fse_cell{});
+        int rc = fse_physics_check(h_, x, y, &res, tiles.data(), (int32_t)tiles.size());
+        if (rc == FSE_EINVAL && res.count > 10 && res.count <= 1000) {  // a sprawling component: its box did not fit, nothing was changed
+            tiles.assign((size_t)res.w * res.h, fse_cell{});
+            rc = fse_physics_check(h_, x, y, &res, tiles.data(), (int32_t)tiles.size());
+        }
+        check(rc);
+        tiles.resize(res.action == 2 ? (size_t)res.w * res.h : 0);
+        return res.action == 2;
+    }
     // world::explosion(x, y, r) (world.cpp:2294)
     void explosion(int x, int y, int r) { check(fse_explosion(h_, x, y, r, tickCt, seed)); }
     // world::tickChunks() grid + particle shift (world.cpp:2454-2478, 2579-2582); chunk load / save stays with the caller

@@ -383,6 +383,18 @@ FSE_API int fse_solid_mask(fse_world* w, int32_t x, int32_t y, int32_t rw, int32
 /* physicsCheck(x,y): size / bbox {minx,miny,maxx,maxy} / sorted pixel indices (x + y*width) of the 4-connected SOLID
  * component at (x,y); *count = cap+1 when it exceeds cap, 0 when the seed is not SOLID.  pixels may be NULL. */
 FSE_API int fse_flood_component(fse_world* w, int32_t x, int32_t y, int32_t cap, int32_t* count, int32_t* bbox, int32_t* pixels);
+/* world::physicsCheck(x, y) (world.cpp:3330-3411) as one call.  The 4-connected SOLID component at (x, y), abandoned beyond 1000 cells
+ * like the reference's flood: 1..10 cells are deleted (Tiles_NOTHING, dirty); 11..1000 cells are cut out of the grid into the tile
+ * array of a new rigid body — OBSIDIAN carrying each cell's colour, AIR elsewhere in the bounding box, what makeRigidBody builds from
+ * the colour surface (world.cpp:191-209; membership by component, not by the colour's alpha byte).  The host creates the b2Body at
+ * (x, y) with its random velocity and calls updateRigidBodyHitbox (fse_bodies_split).  tiles_out: w * h cells, row-major, written
+ * for action 2; when cap_tiles is too small the call fails with the box in *out and changes nothing. */
+typedef struct fse_physcheck_result {
+    int32_t count;   /* cells of the component; 1001 = abandoned (> 1000), 0 = (x, y) is not SOLID or outside the world */
+    int32_t action;  /* 0 nothing, 1 deleted, 2 cut out into tiles_out */
+    int32_t x, y, w, h;  /* bounding box of the component (count 1..1000) */
+} fse_physcheck_result;
+FSE_API int fse_physics_check(fse_world* w, int32_t x, int32_t y, fse_physcheck_result* out, fse_cell* tiles_out, int32_t cap_tiles);
 
 /* ---- active-region tracking: world::active/lastActive (world.hpp:131-133) are allocated but dead in the reference
  * (every writer is commented out), so the only contract is "same cells as a full sweep".  When

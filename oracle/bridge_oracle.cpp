@@ -335,10 +335,53 @@ int flood_component(World* W, int x, int y, int cap, int* bbox, int32_t* pixels)
     return (int)seen.size();
 }
 
+// world::physicsCheck (world.cpp:3330-3411): the 4-connected SOLID component at (x, y), abandoned beyond 1000 cells; 11..1000 cells
+// are cut out of the grid (Tiles_NOTHING, dirty) into the tile array of a new rigid body — what makeRigidBody builds from the
+// surface of their colours (world.cpp:191-209): OBSIDIAN carrying the cell's colour, AIR elsewhere in the bounding box; 1..10 cells
+// are simply deleted.  res = {count (1001 = abandoned, 0 = seed not SOLID), action (0 none, 1 deleted, 2 cut out), min x, min y, w, h};
+// tiles (w * h, row-major) is written for action 2 when it holds at least w * h cells, otherwise nothing is changed and -1 returned.
+int physics_check(World* W, int x, int y, int32_t* res, fse_cell* tiles, int cap_tiles) {
+    for (int q = 0; q < 6; q++) res[q] = 0;
+    std::vector<int32_t> px(1001);
+    int bbox[4];
+    const int count = flood_component(W, x, y, 1000, bbox, px.data());
+    res[0] = count;
+    if (count <= 0 || count > 1000) return 0;
+    res[2] = bbox[0]; res[3] = bbox[1]; res[4] = bbox[2] - bbox[0] + 1; res[5] = bbox[3] - bbox[1] + 1;
+    if (count > 10) {
+        if ((long long)res[4] * res[5] > cap_tiles) return -1;
+        fse_cell air;
+        std::memset(&air, 0, sizeof air);
+        air.mat = (uint16_t)W->ids.air;
+        air.fluid = 2.0f;
+        for (int i = 0; i < res[4] * res[5]; i++) tiles[i] = air;
+        const Material& ob = W->mats[W->ids.obsidian];
+        for (int k = 0; k < count; k++) {
+            const int cx = px[k] % W->width, cy = px[k] / W->width;
+            fse_cell t = air;
+            t.mat = (uint16_t)ob.id;
+            t.color = W->tiles[px[k]].color;
+            t.temp = ob.createTemp;
+            tiles[(cx - res[2]) + (cy - res[3]) * res[4]] = t;
+        }
+        res[1] = 2;
+    } else {
+        res[1] = 1;
+    }
+    for (int k = 0; k < count; k++) {
+        W->tiles[px[k]] = W->nothing();
+        W->dirty[px[k]] = 1;
+    }
+    return 0;
+}
+
 }  // namespace fseo
 
 using namespace fseo;
 extern "C" {
+__attribute__((visibility("default"))) int fseo_physics_check(void* p, int x, int y, int32_t* res, fse_cell* tiles, int cap_tiles) {
+    return physics_check((World*)p, x, y, res, tiles, cap_tiles);
+}
 // world::explosion (world.cpp:2294-2332) with rand() replaced by the counter RNG keyed on (seed, tick, x, y) — cells decide
 // independently, so the loop order is immaterial.
 void explosion(World* w, int cx, int cy, int radius, uint32_t tick, uint32_t seed) {

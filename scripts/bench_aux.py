@@ -61,9 +61,25 @@ row("render_dirty_kernel (clean world)", ms, cells * 1, "flag plane only")
 ms = timed(lambda: w.clear_dirty())
 row("clear_dirty_kernel", ms, cells * 2, "flag plane read + written")
 ms = timed(lambda: w.tick_temperature())
-row("temperature_kernel", ms, zone * (2 + 1 + 2) + zone * 4, "temperature + material in, temperature out, + the scratch copy of the plane (2 B in, 2 B out)")
+row("temperature_kernel", ms, zone * (2 + 1 + 2) + (cells - zone) * 4, "temperature + material in, temperature out; the cells around the zone are copied, then the planes trade places")
 ms = timed(lambda: w.scroll(128, 0))
-row("fse_scroll (7 planes)", ms, cells * 17 * 4, "each plane: copy to scratch (read + write) and shifted copy back (read + write)")
+row("fse_scroll (7 planes)", ms, cells * 17 * 2, "one pass: every plane read once and written once into the second plane set, which then becomes the world")
+w.flow_enable(True)
+w.tick(90)
+ms = timed(lambda: w.render_dirty(want_stats=False), before=lambda: None)
+row("render_dirty_kernel (+ flow texture)", ms, cells * 1 + d * (1 + 4 + 8), "same accounting as above; liquid cells add 16 B of accumulators in and 12 B out")
+w.flow_enable(False)
+l2 = np.zeros((1024, N), dtype=T.CELL_DTYPE)
+l2["mat"], l2["color"] = 7, 0x808080
+bg = np.full((1024, N), 0xFF102030, dtype=np.uint32)
+def dirty_layers():
+    for y0 in range(0, N, 1024):
+        w.layer2_write_rect(0, y0, l2)
+        w.background_write_rect(0, y0, bg)
+ms = timed(lambda: w.render_layers(want_counts=False), reps=3, before=dirty_layers)
+row("render_layers_kernel (all dirty)", ms, cells * (1 + 1 + 4 + 4 + 8 + 1), "dirty byte + layer-2 material and colour + background colour in, two texels + the cleared dirty byte out")
+ms = timed(lambda: w.render_layers(want_counts=False))
+row("render_layers_kernel (clean)", ms, cells * 1, "dirty plane only")
 w.particles_clear()
 w.tick(3)
 w.particles_tick()  # first call allocates the scratch pools

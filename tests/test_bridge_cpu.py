@@ -254,3 +254,52 @@ def test_body_split_cracked_plate(oracle, table):
     for f in Hh.FIELDS:
         assert np.array_equal(back[f][plate["mat"] != 0], want[f][plate["mat"] != 0]), f
     assert (back["mat"][plate["mat"] == 0] == 0).all()
+
+
+def _physcheck_world(table, W=768, H=640):
+    """Floating blobs over AIR: a 12 x 9 block with a hole (105 cells), a 3-cell crumb, a 40 x 30 block (1200 cells: too big) and a thin
+    L of 60 cells that sprawls over a 30 x 31 box."""
+    cells = Hh.empty_world_cells(table, W, H)
+    mat = cells["mat"]
+    mat[200:209, 300:312] = 7
+    mat[203:206, 304:305] = 0
+    mat[250, 160:163] = 11
+    mat[300:330, 400:440] = 22
+    mat[350:381, 200] = 7
+    mat[380, 200:230] = 7
+    cells["color"] = (np.arange(W * H, dtype=np.uint32).reshape(H, W) * np.uint32(2246822519)) & np.uint32(0xFFFFFF)
+    return cells
+
+
+def test_physics_check_known_answers(oracle, table):
+    """world::physicsCheck (world.cpp:3330-3411): not SOLID -> nothing; 1..10 cells -> deleted; 11..1000 -> cut out (cells become
+    Tiles_NOTHING and dirty, the body's tiles are OBSIDIAN with the cells' colours inside the bounding box, AIR elsewhere); more than
+    1000 -> the flood is abandoned and nothing changes."""
+    from oracle import pyoracle as O
+    W, H = 768, 640
+    ow = oracle.OracleWorld(W, H, table)
+    cells = _physcheck_world(table, W, H)
+    ow.write_rect(0, 0, cells)
+    ow.clear_dirty()
+    assert O.physics_check(ow, 150, 150)[:2] == (0, 0)                    # AIR seed
+    assert O.physics_check(ow, 420, 315)[:2] == (1001, 0)                 # 1200 cells: abandoned
+    assert O.physics_check(ow, 5, 5)[:2] == (1001, 0)                     # the world's border
+    assert np.array_equal(ow.read_all()["mat"], cells["mat"]) and not ow.read_all()["dirty"].any()
+    n, act, box, tiles = O.physics_check(ow, 161, 250)
+    assert (n, act, box, tiles) == (3, 1, (160, 250, 3, 1), None)
+    after = ow.read_all()
+    assert (after["mat"][250, 160:163] == 0).all() and after["dirty"][250, 160:163].all() and after["dirty"].sum() == 3
+    n, act, box, tiles = O.physics_check(ow, 305, 208)
+    assert (n, act, box) == (12 * 9 - 3, 2, (300, 200, 12, 9)) and tiles.shape == (9, 12)
+    want = cells["mat"][200:209, 300:312] != 0
+    assert np.array_equal(tiles["mat"] == 22, want) and (tiles["mat"][~want] == 0).all()   # OBSIDIAN where the component was
+    assert np.array_equal(tiles["color"][want], cells["color"][200:209, 300:312][want])
+    assert (tiles["fluid"] == 2.0).all()
+    after = ow.read_all()
+    assert (after["mat"][200:209, 300:312] == 0).all() and int(after["dirty"].sum()) == 3 + 105
+    n, act, box, tiles = O.physics_check(ow, 200, 360)
+    assert (n, act, box) == (60, 2, (200, 350, 30, 31)) and int((tiles["mat"] == 22).sum()) == 60
+    ow.write_rect(0, 0, cells)
+    with pytest.raises(ValueError):
+        O.physics_check(ow, 200, 360, cap_tiles=100)
+    assert np.array_equal(ow.read_all()["mat"], cells["mat"])             # too small a tile buffer: nothing was changed

@@ -262,3 +262,32 @@ def test_bodies_split_matches_oracle(oracle, gpu_ctx, table):
     got = gw.bodies_split(0)
     assert len(got) == 3 and sum(int((t["mat"] != 0).sum()) for _, t in got) == int((plate["mat"] != 0).sum())
     gw.close()
+
+
+def test_physics_check_cut_out_exact(oracle, gpu_ctx, table):
+    """fse_physics_check vs the oracle's world::physicsCheck: AIR seed, abandoned flood, deleted crumb, two cut-outs (block with a hole,
+    sprawling L); result records, body tiles and the grid afterwards are identical; a tile buffer that is too small changes nothing."""
+    from oracle import pyoracle as O
+    from tests.test_bridge_cpu import _physcheck_world
+    W, H = 768, 640
+    gpu_ctx.set_materials(table)
+    ow, gw = oracle.OracleWorld(W, H, table), fse.World(gpu_ctx, W, H)
+    cells = _physcheck_world(table, W, H)
+    for w in (ow, gw):
+        w.write_rect(0, 0, cells)
+        w.clear_dirty()
+    for (x, y) in [(150, 150), (420, 315), (5, 5), (161, 250), (305, 208), (200, 360), (200, 360), (-3, 10), (100, 9999)]:
+        a, b = O.physics_check(ow, x, y) if 0 <= x < W and 0 <= y < H else (0, 0, (0, 0, 0, 0), None), gw.physics_check(x, y)
+        assert a[:3] == b[:3], ((x, y), a[:3], b[:3])
+        assert (a[3] is None) == (b[3] is None)
+        if a[3] is not None:
+            Hh.assert_cells_equal(a[3], b[3], f"body tiles of the cut-out at {(x, y)}")
+        Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"grid after physicsCheck{(x, y)}")
+    gw.write_rect(0, 0, cells)
+    ow.write_rect(0, 0, cells)
+    with pytest.raises(fse.FseError):
+        gw.physics_check(200, 360, cap_tiles=100)
+    assert np.array_equal(gw.read_all()["mat"], cells["mat"])
+    assert gw.physics_check(305, 208)[:2] == O.physics_check(ow, 305, 208)[:2] == (105, 2)
+    ow.tick(0); gw.tick(0)
+    Hh.assert_cells_equal(ow.read_all(), gw.read_all(), "tick after the cut-outs")

@@ -64,7 +64,7 @@ def test_layers_render_and_scroll_exact(oracle, gpu_ctx, table):
     """fse_layer2_* / fse_background_* / fse_render_layers / fse_scroll against the oracle: random layer-2 cells and background colours
     written in rects, rendered with and without the background grid, scrolled with the grid, read back."""
     from oracle import pyoracle as O
-    W, H = 384, 256
+    W, H = 512, 384
     gpu_ctx.set_materials(table)
     ow, gw = oracle.OracleWorld(W, H, table), fse.World(gpu_ctx, W, H)
     Hh.build_mixed(ow, table, W, H, seed=3)
