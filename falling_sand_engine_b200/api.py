@@ -286,6 +286,19 @@ class World:
         box = (res.x, res.y, res.w, res.h)
         return res.count, res.action, box, (tiles[:res.w * res.h].reshape(res.h, res.w).copy() if res.action == 2 else None)
 
+    def probe_position(self, tick, seed=1337, zone=None):
+        z = zone or self.tickZone
+        x, y = C.c_int32(0), C.c_int32(0)
+        self.L.fse_probe_position.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.fse_probe_position.restype = None
+        self.L.fse_probe_position(seed, tick, C.byref(z), C.byref(x), C.byref(y))
+        return x.value, y.value
+
+    def physics_probe(self, tick, seed=1337, zone=None):
+        """The probe at the end of world::tick (world.cpp:1929-1934): physicsCheck at a random cell of the tickZone."""
+        x, y = self.probe_position(tick, seed, zone)
+        return self.physics_check(x, y)
+
     # -- chunk files (Chunk::ChunkRead / ChunkWrite, chunk.cpp:74-330; the merge of world::frame and chunkSaveCache) ---------
     def load_chunk(self, path, x, y, layers=False):
         """Read a .pack file and merge it into the grid at (x, y), marked dirty like world::frame does (world.cpp:2374-2391): the

@@ -68,7 +68,8 @@ int main(int argc, char** argv) {
         w.stats(&st);
         int64_t np = 0;
         fse_host::check(fse_particles_count(w.handle(), &np));
-        std::printf("hash=%016llx particles=%lld dirty_last_tick=%lld", (unsigned long long)st.hash, (long long)np, (long long)moving.dirty);
+        std::printf("hash=%016llx particles=%lld dirty_last_tick=%lld cut_outs=%zu", (unsigned long long)st.hash, (long long)np, (long long)moving.dirty,
+                    w.cutOuts.size());
         for (const fse_entity& e : ents) std::printf(" ent=%.6f,%.6f,%.6f,%.6f,%d", e.x, e.y, e.vx, e.vy, e.ground);
         std::printf("\n");
     } catch (const std::exception& e) {

@@ -113,11 +113,23 @@ public:
     void writeChunk(int cx, int cy, const Cell* cells) { check(fse_write_rect(h_, cx, cy, FSE_CHUNK, FSE_CHUNK, cells)); }
     void readChunk(int cx, int cy, Cell* cells) { check(fse_read_rect(h_, cx, cy, FSE_CHUNK, FSE_CHUNK, cells)); }
 
-    // world::tick() (world.cpp:1036-1948)
+    // a body the physicsCheck probe cut loose: the caller makes the b2Body at (res.x, res.y), gives it the random velocity of
+    // world.cpp:3377 and runs updateRigidBodyHitbox on it
+    struct CutOut {
+        fse_physcheck_result res;
+        std::vector<fse_cell> tiles;
+    };
+    std::vector<CutOut> cutOuts;  // since the caller last drained it
+
+    // world::tick() (world.cpp:1036-1948), with the probe at its end (1929-1934)
     void tick() {
         fse_tick_args a{tickCt, seed, cell_iter, tickZone};
         check(fse_tick(h_, &a));
+        int32_t px = 0, py = 0;
+        fse_probe_position(seed, tickCt, &tickZone, &px, &py);
         tickCt++;
+        CutOut c;
+        if (physicsCheckCut(px, py, c.res, c.tiles)) cutOuts.push_back(std::move(c));
     }
     void tickTemperature() { check(fse_tick_temperature(h_, &tickZone)); }  // world.cpp:1950
     void tickCells() { check(fse_particles_tick(h_, &tickZone)); }          // world.cpp:2030

@@ -389,6 +389,10 @@ FSE_API int fse_flood_component(fse_world* w, int32_t x, int32_t y, int32_t cap,
  * the colour surface (world.cpp:191-209; membership by component, not by the colour's alpha byte).  The host creates the b2Body at
  * (x, y) with its random velocity and calls updateRigidBodyHitbox (fse_bodies_split).  tiles_out: w * h cells, row-major, written
  * for action 2; when cap_tiles is too small the call fails with the box in *out and changes nothing. */
+/* The probe at the end of world::tick (world.cpp:1929-1934): physicsCheck(tickZone.x + rand() % tickZone.w, tickZone.y + rand() %
+ * tickZone.h), with rand() replaced by the counter RNG — draws S_PROBE_X / S_PROBE_Y of cell (0, 0) under rng_key(seed, tick, 15).
+ * Pure host function; the caller passes the position to fse_physics_check. */
+FSE_API void fse_probe_position(uint32_t seed, uint32_t tick, const fse_rect* tick_zone, int32_t* x, int32_t* y);
 typedef struct fse_physcheck_result {
     int32_t count;   /* cells of the component; 1001 = abandoned (> 1000), 0 = (x, y) is not SOLID or outside the world */
     int32_t action;  /* 0 nothing, 1 deleted, 2 cut out into tiles_out */

@@ -245,6 +245,23 @@ def physics_check(world, x, y, cap_tiles=1 << 20):
     return int(res[0]), int(res[1]), box, (tiles[:box[2] * box[3]].reshape(box[3], box[2]).copy() if res[1] == 2 else None)
 
 
+S_PROBE_X, S_PROBE_Y = 69, 70
+
+
+def probe_position(world, tick, seed=1337, zone=None):
+    """world.cpp:1930-1931 with the counter RNG: draws S_PROBE_X / S_PROBE_Y of cell (0, 0) under rng_key(seed, tick, 15)."""
+    z = zone or T.Rect(T.FSE_CHUNK, T.FSE_CHUNK, world.width - 2 * T.FSE_CHUNK, world.height - 2 * T.FSE_CHUNK)
+    L = lib()
+    L.fseo_rng_draw.restype = C.c_uint32
+    L.fseo_rng_draw.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32]
+    return (z.x + L.fseo_rng_draw(seed, tick, 15, 0, 0, S_PROBE_X) % max(z.w, 1), z.y + L.fseo_rng_draw(seed, tick, 15, 0, 0, S_PROBE_Y) % max(z.h, 1))
+
+
+def physics_probe(world, tick, seed=1337, zone=None):
+    """The probe at the end of world::tick (world.cpp:1929-1934)."""
+    return physics_check(world, *probe_position(world, tick, seed, zone))
+
+
 def flow_enable(world):
     """Carry flowX / flowY / prevFlowX / prevFlowY (world.hpp:116-119) from now on."""
     lib().fseo_flow_enable.argtypes = [C.c_void_p]

@@ -52,18 +52,19 @@ def test_cpp_host_game_loop_matches_the_python_binding(gpu_ctx, table, tmp_path)
     for i in range(n_ent):
         ents[i] = (150.0 + 37.0 * i, 150.0 + 11.0 * i, 1.5 if i % 2 else -1.0, 0.0, 8 + i, 14 + 2 * i, 0, 0)
     gw.pixels_enable(True)
-    dirty = 0
+    dirty = cuts = 0
     for t in range(ticks):
         ents = gw.entities_tick(ents, tick=t)
         gw.entities_stamp(ents, tick=t)
         gw.tick(t)
+        cuts += gw.physics_probe(t)[1] == 2
         gw.particles_tick()
         if t % 4 == 2:
             gw.tick_temperature()
         gw.object_delete()
         dirty = gw.render_dirty(want_stats=True)[0]
         gw.clear_dirty()
-    want = f"hash={gw.stats().hash:016x} particles={gw.particles_count()} dirty_last_tick={dirty}"
+    want = f"hash={gw.stats().hash:016x} particles={gw.particles_count()} dirty_last_tick={dirty} cut_outs={cuts}"
     for e in ents:
         want += f" ent={e['x']:.6f},{e['y']:.6f},{e['vx']:.6f},{e['vy']:.6f},{int(e['ground'])}"
     assert r.stdout.strip() == want

@@ -292,9 +292,18 @@ def test_random_worlds_long_runs(oracle, gpu_ctx, table, sched, seed):
     Hh.build_mixed(gw, tbl, W, H, seed=seed, extra=list(extra.values()), blob=16)
     gw.pixels_enable(True)
     planes = [np.zeros((H, W, 4), dtype=np.uint8) for _ in range(3)]
+    probes = []
     for t in range(30):
         for w in (ow, gw):
             w.tick(t, seed=seed)
+        # the physicsCheck probe at the end of world::tick (world.cpp:1929-1934), several per tick here so that some hit SOLID blobs
+        for k in range(6):
+            a, b = O.physics_probe(ow, 100 * t + k, seed), gw.physics_probe(100 * t + k, seed)
+            assert a[:3] == b[:3], (t, k, a[:3], b[:3])
+            if a[3] is not None:
+                Hh.assert_cells_equal(a[3], b[3], f"cut-out tiles, tick {t}")
+            probes.append(a[1])
+        for w in (ow, gw):
             w.particles_tick()
             if t % 4 == 2:
                 w.tick_temperature()
@@ -310,6 +319,7 @@ def test_random_worlds_long_runs(oracle, gpu_ctx, table, sched, seed):
             Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), f"{sched} seed {seed} tick {t}")
             for which in range(3):
                 assert np.array_equal(planes[which], gw.pixels_read(which)), (t, which)
+    assert 1 in probes or 2 in probes, "no probe of the run hit a loose SOLID component"
 
 
 def test_chunk_save_and_load_through_pack_files(gpu_ctx, table, tmp_path):
