@@ -20,7 +20,9 @@ struct ExplArgs {
     Planes p;
     const DevTables* T;
     int W, H;
-    int cx, cy, radius;
+    int cx, cy, radius;  // centre in global coordinates
+    int y_off;           // global row of local row 0 (strip worlds)
+    int own_lo, own_hi;  // global rows whose cells this rank turns into particles (every rank clears the rows it holds)
     uint32_t rkey, tick;
     fse_particle* pbuf;
     unsigned int* pcount;
@@ -32,9 +34,10 @@ __global__ void explosion_kernel(const ExplArgs a) {
     const int outer = a.radius * 2;
     const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y;
     if (ix >= 2 * outer) return;
-    const int x = a.cx - outer + ix, y = a.cy - outer + iy;
-    if (x < 0 || y < 0 || x >= a.W || y >= a.H) return;  // getTile out of bounds is TEST_SOLID, setTile out of bounds is ignored
-    const size_t g = (size_t)y * a.W + x;
+    const int x = a.cx - outer + ix, y = a.cy - outer + iy;  // global
+    const int yl = y - a.y_off;
+    if (x < 0 || yl < 0 || x >= a.W || yl >= a.H) return;  // getTile out of bounds is TEST_SOLID, setTile out of bounds is ignored
+    const size_t g = (size_t)yl * a.W + x;
     const uint8_t m = a.p.mat[g];
     const int ph = a.T->phys[m];
     if (ph == P_AIR) return;
@@ -43,7 +46,7 @@ __global__ void explosion_kernel(const ExplArgs a) {
     const bool inner = d2 < a.radius * a.radius;
     if (!inner && !(d2 < outer * outer && ph != P_SOLID)) return;
     const uint32_t cb = rng_cell(a.rkey, x, y);
-    if (!inner || !(ph == P_SOLID || rng_draw(cb, S_EXPL_KEEP) % 10 < 6)) {
+    if ((!inner || !(ph == P_SOLID || rng_draw(cb, S_EXPL_KEEP) % 10 < 6)) && y >= a.own_lo && y < a.own_hi) {
         const unsigned int i = atomicAdd(a.pcount, 1u);
         if (i < a.pcap) {
             fse_particle q;
@@ -92,14 +95,14 @@ __device__ __forceinline__ void tool_set_nothing(Planes p, size_t g, int air) { 
 }
 
 // erase brush: thread (point, brush cell); a cell under several stamps is cleared by each of them with the same result
-__global__ void tool_brush_kernel(Planes p, const DevTables* T, int W, int H, const long long* pts, int n_pts, int brush) {
+__global__ void tool_brush_kernel(Planes p, const DevTables* T, int W, int H, int y_off, const long long* pts, int n_pts, int brush) {
     const int lo = -brush / 2, hi = (int)ceil(brush / 2.0), side = hi - lo;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (side <= 0 || i >= (long long)n_pts * side * side) return;
     const int c = (int)(i % (side * side)), pi = (int)(i / (side * side));
     const int xx = lo + c / side, yy = lo + c % side;
     if (abs(xx) + abs(yy) == brush) return;
-    const int x = (int)(pts[pi] % W) + xx, y = (int)(pts[pi] / W) + yy;
+    const int x = (int)(pts[pi] % W) + xx, y = (int)(pts[pi] / W) + yy - y_off;  // points are global cells, planes hold rows from y_off
     if (x < 0 || y < 0 || x >= W || y >= H) return;
     const size_t g = (size_t)y * W + x;
     if (T->phys[p.mat[g]] != P_AIR) tool_set_nothing(p, g, T->air);
@@ -355,7 +358,6 @@ using namespace fse;
 extern "C" FSE_API int fse_explosion(fse_world* w, int32_t cx, int32_t cy, int32_t radius, uint32_t tick, uint32_t seed) {
     if (!w) return fail(FSE_EINVAL, "fse_explosion: null world");
     if (radius <= 0 || radius > 4096) return fail(FSE_EINVAL, "fse_explosion: radius %d out of range (1..4096)", radius);
-    if (w->strip && w->ctx->nranks > 1) return fail(FSE_ESTATE, "fse_explosion: not available on multi-rank strips");
     cudaError_t e = cudaSetDevice(w->ctx->device);
     if (e != cudaSuccess) return fail(FSE_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     {   // every cell of the blast square may become a loose particle: make room first (the kernels drop what has no slot)
@@ -368,7 +370,12 @@ extern "C" FSE_API int fse_explosion(fse_world* w, int32_t cx, int32_t cy, int32
     a.W = w->W;
     a.H = w->H;
     a.cx = cx;
-    a.cy = cy - w->y_off;
+    a.cy = cy;
+    a.y_off = w->y_off;
+    // Multi-rank strips: every rank makes the call with the same arguments.  Cells decide independently from their own state and the
+    // position-keyed RNG, so each rank clears the part of the blast it holds; the particles come from the rank that owns the row.
+    a.own_lo = w->strip ? w->own_lo : 0;
+    a.own_hi = w->strip ? w->own_hi : w->H;
     a.radius = radius;
     a.rkey = rng_key(seed, tick, 7u);  // the tick's own iterations use 0..cell_iter-1
     a.tick = tick;
@@ -381,9 +388,12 @@ extern "C" FSE_API int fse_explosion(fse_world* w, int32_t cx, int32_t cy, int32
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(FSE_ECUDA, "explosion_kernel: %s", cudaGetErrorString(e));
     w->ctx->launches += 1;
-    const int x0 = cx - 2 * radius < 0 ? 0 : cx - 2 * radius, y0 = a.cy - 2 * radius < 0 ? 0 : a.cy - 2 * radius;
-    const int x1 = cx + 2 * radius > w->W ? w->W : cx + 2 * radius, y1 = a.cy + 2 * radius > w->H ? w->H : a.cy + 2 * radius;
-    if (x1 > x0 && y1 > y0) return fse_wake_rect(w, x0, y0, x1 - x0, y1 - y0);
+    const int cyl = cy - w->y_off;
+    const int x0 = cx - 2 * radius < 0 ? 0 : cx - 2 * radius, y0 = cyl - 2 * radius < 0 ? 0 : cyl - 2 * radius;
+    const int x1 = cx + 2 * radius > w->W ? w->W : cx + 2 * radius, y1 = cyl + 2 * radius > w->H ? w->H : cyl + 2 * radius;
+    if (x1 > x0 && y1 > y0)
+        if (int r = fse_wake_rect(w, x0, y0, x1 - x0, y1 - y0)) return r;
+    if (w->strip && w->ctx->nranks > 1) return strip_refresh(w, w->stream, 32);  // ghost rows are the owner's again
     return FSE_OK;
 }
 
@@ -403,9 +413,9 @@ static int tool_scratch(fse_world* w, size_t bytes) {  // device scratch of the 
     w->tool_scratch_bytes = bytes + 4096;
     return FSE_OK;
 }
-static int tool_common(fse_world* w, const char* who) {
+static int tool_common(fse_world* w, const char* who, bool strips_ok = false) {
     if (!w) return fail(FSE_EINVAL, "%s: null world", who);
-    if (w->strip && w->ctx->nranks > 1) return fail(FSE_ESTATE, "%s: not available on multi-rank strips", who);
+    if (w->strip && w->ctx->nranks > 1 && !strips_ok) return fail(FSE_ESTATE, "%s: not available on multi-rank strips", who);
     CKT(cudaSetDevice(w->ctx->device));
     return FSE_OK;
 }
@@ -418,9 +428,11 @@ static int tool_wake(fse_world* w, int x0, int y0, int x1, int y1) {
 }
 
 extern "C" FSE_API int fse_tool_erase_line(fse_world* w, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int32_t brush_size) {
-    if (int r = tool_common(w, "fse_tool_erase_line")) return r;
+    // multi-rank strips: every rank makes the call; a rank clears the cells of the stroke it holds (the cells decide independently)
+    if (int r = tool_common(w, "fse_tool_erase_line", true)) return r;
     if (brush_size < 1 || brush_size > 256) return fail(FSE_EINVAL, "fse_tool_erase_line: brush size %d (1..256)", brush_size);
-    if (x0 < 0 || y0 < 0 || x1 < 0 || y1 < 0 || x0 >= w->W || x1 >= w->W || y0 >= w->H || y1 >= w->H)
+    const int Hg = w->strip ? w->Hglobal : w->H;
+    if (x0 < 0 || y0 < 0 || x1 < 0 || y1 < 0 || x0 >= w->W || x1 >= w->W || y0 >= Hg || y1 >= Hg)
         return fail(FSE_EINVAL, "fse_tool_erase_line: end points outside the world");
     std::vector<long long> pts;
     line_cells(w->W, x0, y0, x1, y1, pts);
@@ -428,11 +440,14 @@ extern "C" FSE_API int fse_tool_erase_line(fse_world* w, int32_t x0, int32_t y0,
     CKT(cudaMemcpyAsync(w->tool_scratch, pts.data(), pts.size() * sizeof(long long), cudaMemcpyHostToDevice, w->stream));
     const int lo = -brush_size / 2, hi = (int)std::ceil(brush_size / 2.0), side = hi - lo;
     const long long total = (long long)pts.size() * side * side;
-    tool_brush_kernel<<<(unsigned)((total + 255) / 256), 256, 0, w->stream>>>(w->p, w->ctx->d_tabs, w->W, w->H, (const long long*)w->tool_scratch, (int)pts.size(), brush_size);
+    tool_brush_kernel<<<(unsigned)((total + 255) / 256), 256, 0, w->stream>>>(w->p, w->ctx->d_tabs, w->W, w->H, w->y_off, (const long long*)w->tool_scratch, (int)pts.size(), brush_size);
     CKT(cudaGetLastError());
     w->ctx->launches += 1;
     CKT(cudaStreamSynchronize(w->stream));  // pts is a local
-    return tool_wake(w, std::min(x0, x1) - brush_size, std::min(y0, y1) - brush_size, std::max(x0, x1) + brush_size, std::max(y0, y1) + brush_size);
+    if (int r = tool_wake(w, std::min(x0, x1) - brush_size, std::min(y0, y1) - brush_size - w->y_off, std::max(x0, x1) + brush_size,
+                          std::max(y0, y1) + brush_size - w->y_off)) return r;
+    if (w->strip && w->ctx->nranks > 1) return strip_refresh(w, w->stream, 32);
+    return FSE_OK;
 }
 
 extern "C" FSE_API int fse_tool_pickaxe(fse_world* w, int32_t x, int32_t y, float break_size, uint32_t* pixels_out, int32_t* n_out) {

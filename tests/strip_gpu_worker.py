@@ -24,6 +24,9 @@ def main():
     sw.write_rect(0, lo, G.mixed_band(table, W, H, lo, hi - lo, seed=77, blob=32))
     for t in range(ticks):
         sw.tick(t, seed=1337)
+        if t == 2:  # a blast and an eraser stroke across the cuts: every rank makes the call, each clears the rows it holds
+            sw.explosion(W // 2, H // 2 + 5, 40, tick=t, seed=1337)
+            sw.tool_erase_line(200, H // 4 - 30, 700, 3 * H // 4 + 20, 9)
         sw.particles_tick()  # ghost refresh, migration, integration and the deposit rounds with the band proposals exchanged
         if t % 4 == 2:
             sw.tick_temperature()

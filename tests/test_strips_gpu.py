@@ -1,5 +1,6 @@
 """Multi-GPU strips over NCCL vs the single-world oracle (bit-exact for any strip count; SURVEY.md §8c pin 8): world tick, loose
-particles (migration between ranks + deposit rounds with the band proposals exchanged) and temperature.
+particles (migration between ranks + deposit rounds with the band proposals exchanged), temperature, and an explosion and an eraser
+stroke across the cuts.
 Needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_strips_gpu.py -m gpu`."""
 import os
 import subprocess
@@ -36,8 +37,12 @@ def test_strips_match_oracle(oracle, table, tmp_path, nranks):
     ow = oracle.OracleWorld(W, H, table)
     ow.write_rect(0, 0, G.mixed_band(table, W, H, 0, H, seed=77, blob=32))
     deposited = 0
+    from oracle import pyoracle as O
     for t in range(ticks):
         ow.tick(t, seed=1337)
+        if t == 2:
+            O.explosion(ow, W // 2, H // 2 + 5, 40, tick=t, seed=1337)
+            O.tool_erase_line(ow, 200, H // 4 - 30, 700, 3 * H // 4 + 20, 9)
         before = ow.particles_count()
         ow.particles_tick()
         deposited += before - ow.particles_count()
