@@ -440,7 +440,8 @@ def run_ours(args):
         h2d += 2 * xf.nbytes + masks.nbytes
         d2h += 2 * 16 * len(bodies)  # feedback of raster and erase (outline results come back as well, size varies)
     stages = (["fse_bodies_raster"] if have_bodies else []) + [f"{n_chunks} chunk merges from pinned host memory (fse_write_rect)", "fse_tick"]
-    stages += (["fse_particles_tick"] if single else []) + (["fse_bodies_erase", "fse_mask_outline of every body"] if have_bodies else [])
+    strip_particles = (not single) and os.environ.get("FSE_E2E_STRIP_PARTICLES", "1") != "0"  # tickCells over the strips (migration + band proposals)
+    stages += (["fse_particles_tick"] if single or strip_particles else []) + (["fse_bodies_erase", "fse_mask_outline of every body"] if have_bodies else [])
     stages += ["fse_tick_temperature on tick % 4 == 2"] + (["fse_render_dirty + movingTiles histogram readback", "fse_clear_dirty"] if single else ["fse_stats_rect readback"])
     moving = 0
 
@@ -453,7 +454,7 @@ def run_ours(args):
         for i in range(n_chunks):  # left border column of chunks (outside the tickZone), where scrolled-in chunks land
             world.write_rect_ptr(0, e2e_y0 + T.FSE_CHUNK * i, T.FSE_CHUNK, T.FSE_CHUNK, pinned_np[i].ctypes.data)
         world.tick(t, seed=args.seed, cell_iter=CELL_ITER)
-        if single:
+        if single or strip_particles:
             world.particles_tick()
         if have_bodies:
             world.bodies_erase(xf)

@@ -80,8 +80,20 @@ struct OutlineArgs {
     float* pool;
     unsigned int* pool_used;
     unsigned int pool_cap;  // floats
-    int4* recs;        // {mask, candidate index, pool offset of the simplified points, n points}
-    unsigned int* n_recs;
+    // Per cell of every mask (index mask * w * h + cell): the contour that starts at this candidate cell, if it survived.  The contours
+    // come out ordered by (mask, candidate index) — the reference's discovery order — through two scans on the device, so the host
+    // neither sorts records nor copies scratch: cell_kept -> rank inside the mask and point offset inside the mask (contour_rank_kernel)
+    // -> offsets of the masks (mask_scan_kernel) -> compacted points and offsets (contour_scatter_kernel).
+    int* cell_kept;          // points of the simplified contour, 0 = no contour starts here (zeroed before the launch)
+    unsigned int* cell_off;  // pool offset of its points
+    int* cell_rank;          // contours of the same mask with a lower candidate index
+    int* cell_ptoff;         // points of those contours
+    int* mask_cnt;           // [n] contours per mask, [n] points per mask behind them
+    int* mask_off;           // [n + 1] first contour of each mask, [n] first point of each mask behind them
+    int* pt_off;             // [contours + 1] first point of each contour (output)
+    float* out_pts;          // compacted points (output)
+    unsigned int out_cap;    // floats
+    unsigned int* n_recs;    // [0] contours, [1] points (set by mask_scan_kernel)
     unsigned int rec_cap;
     int* overflow;
     int want_labels;   // copy the labels out (callers that only need contours and component counts skip 4 bytes per cell)
@@ -218,12 +230,96 @@ __global__ void contour_kernel(OutlineArgs a) {
             kept++;
         }
     if (kept < 3) return;  // world.cpp:490
-    const unsigned int r = atomicAdd(a.n_recs, 1u);
-    if (r >= a.rec_cap) {
-        atomicExch(a.overflow, 1);
-        return;
+    a.cell_kept[gi] = kept;
+    a.cell_off[gi] = off + 5u * (unsigned int)runs;
+}
+
+// exclusive scan of (flag, value) pairs over the 256 threads of a CTA; returns this thread's offsets, *tot_f / *tot_v get the CTA totals
+__device__ __forceinline__ void block_scan2(int f, int v, int& ex_f, int& ex_v, int& tot_f, int& tot_v, int* ws /* 16 ints of shared memory */) {
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    int inf = f, inv = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int tf = __shfl_up_sync(0xffffffffu, inf, d), tv = __shfl_up_sync(0xffffffffu, inv, d);
+        if (lane >= d) { inf += tf; inv += tv; }
     }
-    a.recs[r] = make_int4(m, i, (int)(off + 5u * (unsigned int)runs), kept);
+    if (lane == 31) { ws[wp] = inf; ws[8 + wp] = inv; }
+    __syncthreads();
+    int of = 0, ov = 0, sf = 0, sv = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (q < wp) { of += ws[q]; ov += ws[8 + q]; }
+        sf += ws[q]; sv += ws[8 + q];
+    }
+    ex_f = of + inf - f;
+    ex_v = ov + inv - v;
+    tot_f = sf;
+    tot_v = sv;
+    __syncthreads();
+}
+
+// one CTA per mask: rank and point offset of every contour inside its mask, contour and point totals of the mask
+__global__ void __launch_bounds__(256) contour_rank_kernel(OutlineArgs a) {
+    __shared__ int ws[16];
+    const int m = blockIdx.x, per = a.w * a.h;
+    const size_t base = (size_t)m * per;
+    int carry_c = 0, carry_p = 0;
+    for (int tile = 0; tile < per; tile += 256) {
+        const int i = tile + threadIdx.x;
+        const int k = i < per ? a.cell_kept[base + i] : 0;
+        int ec, ep, tc, tp;
+        block_scan2(k > 0, k, ec, ep, tc, tp, ws);
+        if (k > 0) {
+            a.cell_rank[base + i] = carry_c + ec;
+            a.cell_ptoff[base + i] = carry_p + ep;
+        }
+        carry_c += tc;
+        carry_p += tp;
+    }
+    if (threadIdx.x == 0) {
+        a.mask_cnt[m] = carry_c;
+        a.mask_cnt[a.n + m] = carry_p;
+    }
+}
+
+// one CTA: offsets of the masks (exclusive scans of the per-mask totals), the grand totals
+__global__ void __launch_bounds__(256) mask_scan_kernel(OutlineArgs a) {
+    __shared__ int ws[16];
+    int carry_c = 0, carry_p = 0;
+    for (int tile = 0; tile < a.n; tile += 256) {
+        const int m = tile + threadIdx.x;
+        const int c = m < a.n ? a.mask_cnt[m] : 0, p = m < a.n ? a.mask_cnt[a.n + m] : 0;
+        int ec, ep, tc, tp;
+        block_scan2(c, p, ec, ep, tc, tp, ws);
+        if (m < a.n) {
+            a.mask_off[m] = carry_c + ec;
+            a.mask_off[a.n + 1 + m] = carry_p + ep;
+        }
+        carry_c += tc;
+        carry_p += tp;
+    }
+    if (threadIdx.x == 0) {
+        a.mask_off[a.n] = carry_c;
+        a.n_recs[0] = (unsigned int)carry_c;
+        a.n_recs[1] = (unsigned int)carry_p;
+        if ((unsigned int)carry_c > a.rec_cap || 2u * (unsigned int)carry_p > a.out_cap) atomicExch(a.overflow, 1);
+        else a.pt_off[carry_c] = carry_p;
+    }
+}
+
+// one thread per candidate cell with a contour: its points go to their final place
+__global__ void contour_scatter_kernel(OutlineArgs a) {
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = a.w * a.h;
+    if (gi >= a.n * per || *a.overflow) return;
+    const int kept = a.cell_kept[gi];
+    if (kept <= 0) return;
+    const int m = gi / per;
+    const int c = a.mask_off[m] + a.cell_rank[gi], o = a.mask_off[a.n + 1 + m] + a.cell_ptoff[gi];
+    a.pt_off[c] = o;
+    const float* src = a.pool + a.cell_off[gi];
+    float* dst = a.out_pts + 2 * (size_t)o;
+    for (int q = 0; q < 2 * kept; q++) dst[q] = src[q];
 }
 
 __global__ void solid_mask_kernel(const uint8_t* mat, const DevTables* T, int W, int x0, int y0, int rw, int rh, uint8_t* out) {
@@ -347,12 +443,16 @@ extern "C" FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int3
         return fail(FSE_EINVAL, "fse_mask_outline: bad argument");
     CK(cudaSetDevice(w->ctx->device));
     const size_t per = (size_t)mw * mh, total = per * n_masks;
+    if (total > ((size_t)1 << 30)) return fail(FSE_EINVAL, "fse_mask_outline: %zu mask cells in one call (at most 2^30)", total);
     const unsigned int pool_cap = (unsigned int)std::min<size_t>((size_t)1 << 30, 16 * total + 4096);
     const unsigned int rec_cap = (unsigned int)std::min<size_t>((size_t)1 << 26, total / 2 + 1024);
-    // scratch layout: masks | labels | ncomp | counters | recs | pool
+    const unsigned int out_cap = pool_cap / 7 * 2 + 64;  // a contour's scratch is 7 x its runs, its output at most 2 x its runs
+    // scratch layout: masks | labels | ncomp | counters | cell arrays | mask totals / offsets | contour offsets | output points | pool
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    size_t o_masks = 0, o_labels = up(total), o_ncomp = up(o_labels + total * 4), o_cnt = up(o_ncomp + (size_t)n_masks * 4),
-           o_recs = o_cnt + 256, o_pool = up(o_recs + (size_t)rec_cap * 16), bytes = o_pool + (size_t)pool_cap * 4;
+    const size_t o_masks = 0, o_labels = up(total), o_ncomp = up(o_labels + total * 4), o_cnt = up(o_ncomp + (size_t)n_masks * 4),
+                 o_kept = o_cnt + 256, o_coff = up(o_kept + total * 4), o_rank = up(o_coff + total * 4), o_ptoff = up(o_rank + total * 4),
+                 o_mcnt = up(o_ptoff + total * 4), o_moff = up(o_mcnt + (size_t)n_masks * 8), o_poff = up(o_moff + ((size_t)n_masks * 2 + 1) * 4),
+                 o_out = up(o_poff + ((size_t)rec_cap + 1) * 4), o_pool = up(o_out + (size_t)out_cap * 4), bytes = o_pool + (size_t)pool_cap * 4;
     CK(grow_scratch(w, bytes));
     char* base = (char*)w->outline_scratch;
     OutlineArgs a;
@@ -361,15 +461,24 @@ extern "C" FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int3
     a.labels = (int32_t*)(base + o_labels);
     a.ncomp = (int*)(base + o_ncomp);
     a.pool_used = (unsigned int*)(base + o_cnt);
-    a.n_recs = a.pool_used + 1;
-    a.overflow = (int*)(a.pool_used + 2);
-    a.recs = (int4*)(base + o_recs);
+    a.n_recs = a.pool_used + 1;                // [1] contours, [2] points
+    a.overflow = (int*)(a.pool_used + 3);
+    a.cell_kept = (int*)(base + o_kept);
+    a.cell_off = (unsigned int*)(base + o_coff);
+    a.cell_rank = (int*)(base + o_rank);
+    a.cell_ptoff = (int*)(base + o_ptoff);
+    a.mask_cnt = (int*)(base + o_mcnt);
+    a.mask_off = (int*)(base + o_moff);
+    a.pt_off = (int*)(base + o_poff);
+    a.out_pts = (float*)(base + o_out);
+    a.out_cap = out_cap;
     a.rec_cap = rec_cap;
     a.pool = (float*)(base + o_pool);
     a.pool_cap = pool_cap;
-    // host traffic goes through one pinned staging buffer (masks in; counters, labels, component counts out in one batch;
-    // contour records and points after the counts are known): pageable cudaMemcpy calls cost several ms on 2000 masks
-    const size_t st_labels = up(total), st_ncomp = up(st_labels + total * 4), st_cnt = up(st_ncomp + (size_t)n_masks * 4), st_fixed = st_cnt + 256;
+    // host traffic goes through pinned staging buffers (masks in; counters, labels, component counts and mask offsets out in one batch;
+    // contour offsets and points — already in their final order and place — once the counts are known)
+    const size_t st_labels = up(total), st_ncomp = up(st_labels + total * 4), st_moff = up(st_ncomp + (size_t)n_masks * 4),
+                 st_cnt = up(st_moff + ((size_t)n_masks + 1) * 4), st_fixed = st_cnt + 256;
     if (w->outline_pinned_bytes < st_fixed) {
         if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
         w->outline_pinned = nullptr;
@@ -381,6 +490,7 @@ extern "C" FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int3
     memcpy(pin, masks, total);
     CK(cudaMemcpyAsync(base + o_masks, pin, total, cudaMemcpyHostToDevice, w->stream));
     CK(cudaMemsetAsync(base + o_cnt, 0, 256, w->stream));
+    CK(cudaMemsetAsync(a.cell_kept, 0, total * 4, w->stream));
     a.want_labels = labels != nullptr;
     const size_t ccl_smem_bytes = per <= (size_t)CCL_SMEM_CELLS ? per * sizeof(int32_t) : 0;
     static bool ccl_configured = false;
@@ -392,16 +502,25 @@ extern "C" FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int3
     CK(cudaGetLastError());
     contour_kernel<<<(unsigned int)((total + 127) / 128), 128, 0, w->stream>>>(a);
     CK(cudaGetLastError());
-    w->ctx->launches += 2;
-    CK(cudaMemcpyAsync(pin + st_cnt, base + o_cnt, 12, cudaMemcpyDeviceToHost, w->stream));
+    contour_rank_kernel<<<n_masks, 256, 0, w->stream>>>(a);
+    CK(cudaGetLastError());
+    mask_scan_kernel<<<1, 256, 0, w->stream>>>(a);
+    CK(cudaGetLastError());
+    contour_scatter_kernel<<<(unsigned int)((total + 127) / 128), 128, 0, w->stream>>>(a);
+    CK(cudaGetLastError());
+    w->ctx->launches += 5;
+    CK(cudaMemcpyAsync(pin + st_cnt, base + o_cnt, 16, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(pin + st_moff, a.mask_off, ((size_t)n_masks + 1) * 4, cudaMemcpyDeviceToHost, w->stream));
     if (labels) CK(cudaMemcpyAsync(pin + st_labels, a.labels, total * 4, cudaMemcpyDeviceToHost, w->stream));
     if (n_components) CK(cudaMemcpyAsync(pin + st_ncomp, a.ncomp, (size_t)n_masks * 4, cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
-    unsigned int hc[3];
+    unsigned int hc[4];
     memcpy(hc, pin + st_cnt, sizeof hc);
-    if (hc[2]) return fail(FSE_ENOMEM, "fse_mask_outline: contour scratch overflow (%u floats, %u contours)", hc[0], hc[1]);
-    const unsigned int nrec = hc[1];
-    const size_t var_bytes = up(sizeof(int4) * (size_t)nrec) + sizeof(float) * (size_t)hc[0];
+    if (hc[3]) return fail(FSE_ENOMEM, "fse_mask_outline: contour scratch overflow (%u scratch floats, %u contours, %u points)", hc[0], hc[1], hc[2]);
+    const unsigned int nrec = hc[1], npts = hc[2];
+    if ((int64_t)nrec > cap_contours || (int64_t)npts > cap_pts)
+        return fail(FSE_ENOMEM, "fse_mask_outline: %u contours / %u points exceed the caller's capacity (%d / %d)", nrec, npts, cap_contours, cap_pts);
+    const size_t v_off = up(sizeof(float) * 2 * (size_t)npts), var_bytes = v_off + sizeof(int) * ((size_t)nrec + 1);
     if (w->outline_pinned2_bytes < var_bytes) {
         if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);
         w->outline_pinned2 = nullptr;
@@ -409,32 +528,15 @@ extern "C" FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int3
         CK(cudaMallocHost(&w->outline_pinned2, var_bytes + var_bytes / 2 + 4096));
         w->outline_pinned2_bytes = var_bytes + var_bytes / 2 + 4096;
     }
-    int4* recs_p = (int4*)w->outline_pinned2;
-    const float* pool_p = (const float*)((char*)w->outline_pinned2 + up(sizeof(int4) * (size_t)nrec));
-    if (nrec) CK(cudaMemcpyAsync(recs_p, a.recs, sizeof(int4) * nrec, cudaMemcpyDeviceToHost, w->stream));
-    if (hc[0]) CK(cudaMemcpyAsync((void*)pool_p, a.pool, sizeof(float) * hc[0], cudaMemcpyDeviceToHost, w->stream));
+    char* pin2 = (char*)w->outline_pinned2;
+    if (npts) CK(cudaMemcpyAsync(pin2, a.out_pts, sizeof(float) * 2 * (size_t)npts, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(pin2 + v_off, a.pt_off, sizeof(int) * ((size_t)nrec + 1), cudaMemcpyDeviceToHost, w->stream));
     if (labels) memcpy(labels, pin + st_labels, total * 4);  // overlaps the two copies above
     if (n_components) memcpy(n_components, pin + st_ncomp, (size_t)n_masks * 4);
+    memcpy(mask_off, pin + st_moff, ((size_t)n_masks + 1) * 4);
     CK(cudaStreamSynchronize(w->stream));
-    std::vector<int4> recs(recs_p, recs_p + nrec);
-    struct { const float* p; const float* data() const { return p; } } pool{pool_p};
-    std::sort(recs.begin(), recs.end(), [](const int4& p, const int4& q) { return p.x != q.x ? p.x < q.x : p.y < q.y; });  // discovery order
-    size_t npts = 0;
-    for (auto& r : recs) npts += r.w;
-    if ((int64_t)nrec > cap_contours || (int64_t)npts > cap_pts)
-        return fail(FSE_ENOMEM, "fse_mask_outline: %u contours / %zu points exceed the caller's capacity (%d / %d)", nrec, npts, cap_contours, cap_pts);
-    size_t c = 0, o = 0;
-    for (int m = 0; m < n_masks; m++) {
-        mask_off[m] = (int32_t)c;
-        while (c < nrec && recs[c].x == m) {
-            pt_off[c] = (int32_t)o;
-            memcpy(pts + 2 * o, pool.data() + recs[c].z, sizeof(float) * 2 * recs[c].w);
-            o += recs[c].w;
-            c++;
-        }
-    }
-    mask_off[n_masks] = (int32_t)c;
-    pt_off[c] = (int32_t)o;
+    if (npts) memcpy(pts, pin2, sizeof(float) * 2 * (size_t)npts);
+    memcpy(pt_off, pin2 + v_off, sizeof(int) * ((size_t)nrec + 1));
     return FSE_OK;
 }
 
