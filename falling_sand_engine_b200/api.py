@@ -77,6 +77,23 @@ def _ck(rc):
         raise FseError(f"fse error {rc}: {load_library().fse_last_error().decode()}")
 
 
+def hitbox_triangles(contours):
+    """The host half of updateRigidBodyHitbox / updateChunkMesh (world.cpp:497-563; csrc/polygons.hpp): the outlines of one mask
+    (list of (k, 2) arrays as fse_mask_outline returns them) -> list of (n, 3, 2) float64 triangle arrays, one per outer polygon."""
+    L = load_library()
+    pts = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float32).reshape(-1, 2) for c in contours]) if len(contours) else
+                               np.zeros((0, 2), np.float32))
+    off = np.zeros(len(contours) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(c) for c in contours])
+    cap_t, cap_g = 2 * len(pts) + 16, len(contours) + 1
+    tris = np.zeros((cap_t, 3, 2), dtype=np.float64)
+    goff = np.zeros(cap_g + 1, dtype=np.int32)
+    ng = C.c_int32(0)
+    L.fse_hitbox_triangles.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    _ck(L.fse_hitbox_triangles(pts.ctypes.data, off.ctypes.data, len(contours), tris.ctypes.data, cap_t, goff.ctypes.data, cap_g, C.byref(ng)))
+    return [tris[goff[g]:goff[g + 1]].copy() for g in range(ng.value)]
+
+
 class Context:
     def __init__(self, device=0, table=None):
         self.L = load_library()
@@ -266,6 +283,16 @@ class World:
         _ck(self.L.fse_bodies_split(self.h, i, angle, weld[0], weld[1], pieces.ctypes.data, len(pieces), C.byref(n), out.ctypes.data, len(out)))
         return [(pieces[k].copy(), out[pieces[k]["tile_off"]: pieces[k]["tile_off"] + pieces[k]["w"] * pieces[k]["h"]].reshape(pieces[k]["h"], pieces[k]["w"]).copy())
                 for k in range(n.value)]
+
+    def update_rigid_body_hitbox(self, i, angle=0.0, weld=(-1, -1)):
+        """world::updateRigidBodyHitbox (world.cpp:288-720) for uploaded body i: the pieces (device), their outlines (device) and the
+        triangle groups of their colliders (host: hitbox_triangles).  Returns a list of (piece record, tiles, [triangles (k, 3, 2)])."""
+        out = []
+        for rec, tiles in self.bodies_split(i, angle, weld):
+            mask = (tiles["mat"] != 0).astype(np.uint8)[None]
+            _, _, contours = self.mask_outline(mask, want_labels=False)
+            out.append((rec, tiles, hitbox_triangles(contours[0])))
+        return out
 
     def bodies_read(self, i):
         out = np.zeros(self._bodies[i].shape, dtype=T.CELL_DTYPE)

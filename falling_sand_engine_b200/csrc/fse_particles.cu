@@ -20,6 +20,7 @@ struct PState {
     int sj;
     unsigned char status;  // 0 alive, 1 dead, 2 wants start cell, 3 spiral
     unsigned char merge;
+    unsigned int src;      // index of the particle in the pool the call started from (its state before integration)
 };
 
 // proposal of a particle for a cell in the band around a strip cut, as it travels to the neighbour rank
@@ -47,8 +48,8 @@ struct PArgs {
     unsigned int tmask;
     uint8_t* awake;  // active-region flags (null = off)
     int acols, arows;
-    unsigned int* list;    // particles that hit something (indices into st), appended by the integrate kernel
-    unsigned int n_list;   // entries of list the deposit rounds run over
+    fse_particle* out;     // the pool of the next tick: survivors are appended as soon as their fate is known (counters[2])
+    unsigned int n_list;   // particles that hit something: st[0 .. n_list), appended by the integrate kernel (counters[1])
     const unsigned int* prev_pending;  // particles still pending after the previous round (null in round 0): 0 = nothing left to do
     unsigned int* my_pending;          // this round's count
     // strips (null / 0 on plain worlds)
@@ -84,11 +85,27 @@ __device__ __forceinline__ int phys_at(const PArgs& a, int x, int y) {
     return g < 0 ? (int)P_SOLID : (int)a.T->phys[a.p.mat[g]];
 }
 
+// slot for one more record behind *counter for every thread that wants one: one atomic per warp.  All 32 lanes must call.
+__device__ __forceinline__ unsigned int warp_append(unsigned int* counter, bool want) {
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return 0;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (unsigned int)__popc(m & ((1u << lane) - 1u));
+}
+
+// One thread per particle.  A particle that simply flew on (the bulk of a pool of millions) goes straight into the next tick's pool:
+// 80 bytes in, 80 bytes out.  Only the ones that hit something get a PState record for the deposit rounds.
 __global__ void particles_integrate_kernel(PArgs a) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    fse_particle cur = a.pbuf[i];
+    const bool valid = i < a.n;
+    fse_particle cur;
+    if (valid) cur = a.pbuf[i];
     PState s;
+    s.status = 1;
+    if (valid) {
     s.cand = -1;
     s.sx = 0; s.sy = 0; s.sdx = 0; s.sdy = -1; s.sj = 0;
     s.merge = 0;
@@ -138,9 +155,17 @@ __global__ void particles_integrate_kernel(PArgs a) {
         if (done) break;
         if (cur.lifetime > 0) cur.lifetime--;  // 2170
     } while (false);
-    s.adv = cur;
-    a.st[i] = s;
-    if (s.status >= 2) a.list[atomicAdd(&a.counters[1], 1u)] = i;  // the deposit rounds only visit these (order is irrelevant: ids decide)
+    }
+    const bool alive = valid && s.status == 0 && !(cur.y > (float)a.H);  // 2190: particles below the world are dropped
+    const bool pend = valid && s.status >= 2;
+    const unsigned int o = warp_append(&a.counters[2], alive);
+    if (alive) a.out[o] = cur;
+    const unsigned int q = warp_append(&a.counters[1], pend);  // the deposit rounds only visit these (order is irrelevant: ids decide)
+    if (pend) {
+        s.adv = cur;
+        s.src = i;
+        a.st[q] = s;
+    }
 }
 
 __device__ __forceinline__ unsigned int hash_cell(long long c) {
@@ -183,7 +208,7 @@ __global__ void particles_propose_kernel(PArgs a) {
     const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool live = li < a.n_list && !(a.prev_pending && *a.prev_pending == 0);
-    PState* sp = live ? &a.st[a.list[li]] : nullptr;
+    PState* sp = live ? &a.st[li] : nullptr;
     int status = live ? sp->status : 0;
     if (status < 2) status = 0;
     const int W = a.W, H = a.H;
@@ -297,7 +322,7 @@ __global__ void particles_ext_commit_kernel(PArgs a, const PProp* ext, unsigned 
 __global__ void particles_commit_kernel(PArgs a) {
     const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= a.n_list || (a.prev_pending && *a.prev_pending == 0)) return;
-    PState* sp = &a.st[a.list[li]];
+    PState* sp = &a.st[li];
     if (sp->status < 2) return;
     const long long cand = sp->cand;
     unsigned int h = hash_cell(cand) & a.tmask;
@@ -321,15 +346,17 @@ __global__ void particles_commit_kernel(PArgs a) {
     sp->status = 1;
 }
 
-__global__ void particles_compact_kernel(PArgs a, fse_particle* out) {
-    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    const PState* sp = &a.st[i];
-    if (sp->status == 1) return;
-    const fse_particle p = sp->status == 0 ? sp->adv : a.pbuf[i];  // still pending: retried next tick from its old state
-    if (p.y > (float)a.H) return;                                  // 2190
-    const unsigned int o = atomicAdd(&a.counters[2], 1u);
-    out[o] = p;
+// After the rounds: a particle that deposited is gone; one that bounced flies on; one that is still pending is retried next tick from
+// the state it had before this call.
+__global__ void particles_finish_kernel(PArgs a) {
+    const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
+    const PState* sp = li < a.n_list ? &a.st[li] : nullptr;
+    const bool keep = sp && sp->status != 1;
+    fse_particle p;
+    if (keep) p = sp->status == 0 ? sp->adv : a.pbuf[sp->src];
+    const bool alive = keep && !(p.y > (float)a.H);  // 2190
+    const unsigned int o = warp_append(&a.counters[2], alive);
+    if (alive) a.out[o] = p;
 }
 
 // SPIRAL <- the offsets the loop of world.cpp:2116-2147 visits, step by step (once per device)
@@ -505,7 +532,7 @@ static int particles_tick_strips(fse_world* w, const fse_rect* z) {
     a.st = (PState*)w->part_scratch;
     a.n = n;
     a.counters = w->pcount;
-    a.list = (unsigned int*)w->part_list;
+    a.out = w->pbuf2;
     a.own_lo = w->own_lo; a.own_hi = w->own_hi; a.ghost = GH;
     const int G = (int)((n + B - 1) / B);
     CK(cudaMemsetAsync(w->pcount + 1, 0, 2 * sizeof(unsigned int), w->stream));
@@ -579,9 +606,9 @@ static int particles_tick_strips(fse_world* w, const fse_rect* z) {
             w->ctx->launches += 1;
         }
     }
-    // 4. survivors (they change owner at the start of the next call if their row now belongs to a neighbour)
-    if (n) {
-        particles_compact_kernel<<<G, B, 0, w->stream>>>(a, w->pbuf2);
+    // 4. survivors of the rounds (they change owner at the start of the next call if their row now belongs to a neighbour)
+    if (pending) {
+        particles_finish_kernel<<<GL, B, 0, w->stream>>>(a);
         CK(cudaGetLastError());
         w->ctx->launches += 1;
     }
@@ -627,7 +654,7 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
     a.keys = nullptr; a.vals = nullptr; a.tmask = 0;
     a.awake = w->active_on ? w->d_awake : nullptr;
     a.acols = w->acols; a.arows = w->arows;
-    a.list = (unsigned int*)w->part_list;
+    a.out = w->pbuf2;
     a.n_list = 0;
     const int B = 128;
     const int G = (int)((n + B - 1) / B);
@@ -664,9 +691,11 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
             w->ctx->launches += 2;
         }
     }
-    particles_compact_kernel<<<G, B, 0, w->stream>>>(a, w->pbuf2);
-    CK(cudaGetLastError());
-    w->ctx->launches += 1;
+    if (pending > 0) {
+        particles_finish_kernel<<<GL, B, 0, w->stream>>>(a);
+        CK(cudaGetLastError());
+        w->ctx->launches += 1;
+    }
     // live count <- compacted count; swap pools
     CK(cudaMemcpyAsync(w->pcount, w->pcount + 2, sizeof(unsigned int), cudaMemcpyDeviceToDevice, w->stream));
     fse_particle* t = w->pbuf;

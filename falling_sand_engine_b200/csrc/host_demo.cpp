@@ -64,12 +64,39 @@ int main(int argc, char** argv) {
         std::vector<fse_xform> no_bodies;
         fse_render_stats moving{};
         for (int t = 0; t < ticks; t++) w.gameTick(no_bodies, ents, [](size_t, float, float) {}, &moving);
+        // fracture hand-off from C++: a cracked plate goes through updateRigidBodyHitbox (device pieces + outlines, host triangles)
+        size_t hb_pieces = 0, hb_tris = 0;
+        double hb_sum = 0;
+        {
+            const int bw = 40, bh = 24;
+            std::vector<fse_cell> plate((size_t)bw * bh);
+            for (int y = 0; y < bh; y++)
+                for (int x = 0; x < bw; x++) {
+                    fse_cell c{};
+                    const bool solid = x != 17 && !(y >= 3 && y < 6 && x >= 25 && x < 28) && !((x * 7 + y * 13) % 11 == 0 && x > 30);
+                    c.mat = solid ? 22 : 0;
+                    c.color = 0x404040u + (uint32_t)(x + y * bw);
+                    c.fluid = 2.0f;
+                    plate[(size_t)x + (size_t)y * bw] = c;
+                }
+            fse_body_desc d{bw, bh, plate.data()};
+            fse_host::check(fse_bodies_upload(w.handle(), &d, 1));
+            for (const auto& pc : w.updateRigidBodyHitbox(0, bw, bh, 0.3f, 5, 5)) {
+                hb_pieces++;
+                for (const auto& grp : pc.shapes)
+                    for (const auto& t : grp) {
+                        hb_tris++;
+                        for (int k = 0; k < 3; k++) hb_sum += t.p[k].x * (k + 1) + t.p[k].y * (k + 4) + pc.rec.x0 + 2.0 * pc.rec.y0;
+                    }
+            }
+        }
         fse_stats st{};
         w.stats(&st);
         int64_t np = 0;
         fse_host::check(fse_particles_count(w.handle(), &np));
         std::printf("hash=%016llx particles=%lld dirty_last_tick=%lld cut_outs=%zu", (unsigned long long)st.hash, (long long)np, (long long)moving.dirty,
                     w.cutOuts.size());
+        std::printf(" hitbox=%zu,%zu,%.3f", hb_pieces, hb_tris, hb_sum);
         for (const fse_entity& e : ents) std::printf(" ent=%.6f,%.6f,%.6f,%.6f,%d", e.x, e.y, e.vx, e.vy, e.ground);
         std::printf("\n");
     } catch (const std::exception& e) {

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/fse.h"
+#include "polygons.hpp"
 
 namespace fse_host {
 
@@ -168,6 +169,39 @@ public:
         check(rc);
         tiles.resize(res.action == 2 ? (size_t)res.w * res.h : 0);
         return res.action == 2;
+    }
+    // world::updateRigidBodyHitbox (world.cpp:288-720) for an uploaded body: the device cuts it into connected pieces (crop box,
+    // rotated shift, weld flag, tile arrays: fse_bodies_split), traces and simplifies the outlines of every piece (fse_mask_outline)
+    // and polygons.hpp turns them into the triangles of the new bodies' b2PolygonShapes.  The caller creates the b2Bodies (pose and
+    // velocities copied, weld joint where `rec.weld`, world.cpp:657-707) and destroys the old one.
+    struct HitboxPiece {
+        fse_body_piece rec;
+        std::vector<fse_cell> tiles;                         // rec.w x rec.h
+        std::vector<std::vector<Triangle>> shapes;           // one group per outer polygon of the piece
+    };
+    std::vector<HitboxPiece> updateRigidBodyHitbox(int body, int bodyW, int bodyH, float angle, int weldX = -1, int weldY = -1) {
+        std::vector<fse_body_piece> recs(1024);
+        std::vector<fse_cell> tiles((size_t)4 * bodyW * bodyH + 64);
+        int32_t n = 0;
+        check(fse_bodies_split(h_, body, angle, weldX, weldY, recs.data(), (int32_t)recs.size(), &n, tiles.data(), (int64_t)tiles.size()));
+        std::vector<HitboxPiece> out((size_t)n);
+        for (int k = 0; k < n; k++) {
+            HitboxPiece& p = out[(size_t)k];
+            p.rec = recs[(size_t)k];
+            const size_t cells = (size_t)p.rec.w * p.rec.h;
+            p.tiles.assign(tiles.begin() + p.rec.tile_off, tiles.begin() + p.rec.tile_off + (long)cells);
+            std::vector<uint8_t> mask(cells);
+            for (size_t i = 0; i < cells; i++) mask[i] = p.tiles[i].mat != 0;  // data[] = "alpha != 0" (world.cpp:395-402); AIR is material 0
+            std::vector<float> pts(4 * cells + 128);
+            std::vector<int32_t> ptOff(cells / 2 + 66), maskOff(2);
+            check(fse_mask_outline(h_, mask.data(), 1, p.rec.w, p.rec.h, nullptr, nullptr, pts.data(), (int32_t)(pts.size() / 2), ptOff.data(),
+                                   (int32_t)ptOff.size() - 1, maskOff.data()));
+            std::vector<std::vector<Vec2d>> outlines((size_t)maskOff[1]);
+            for (int c = 0; c < maskOff[1]; c++)
+                for (int q = ptOff[c]; q < ptOff[c + 1]; q++) outlines[(size_t)c].push_back(Vec2d{pts[2 * q], pts[2 * q + 1]});
+            p.shapes = hitbox_triangles(outlines);
+        }
+        return out;
     }
     // world::explosion(x, y, r) (world.cpp:2294)
     void explosion(int x, int y, int r) { check(fse_explosion(h_, x, y, r, tickCt, seed)); }

@@ -286,7 +286,8 @@ FSE_API int fse_bodies_split(fse_world* w, int32_t body, float angle, int32_t we
 /* `world::explosion(cx, cy, radius)` (world.cpp:2294-2332): every non-AIR cell within `radius` of (cx, cy) is removed — SOLID
  * cells and 6 in 10 of the others vanish, the rest leave as loose particles (colour darkened to a quarter, spawned one cell
  * lower, thrown outward) — and every non-SOLID cell of the ring out to 2*radius is thrown outward as a particle.  Cells decide
- * independently; rand() is replaced by the counter RNG keyed on (seed, tick, x, y).  Not available on multi-rank strips. */
+ * independently; rand() is replaced by the counter RNG keyed on (seed, tick, x, y).  On multi-rank strips every rank makes the call
+ * with the same arguments: each clears the part of the blast it holds, the particles come from the rank that owns the row. */
 FSE_API int fse_explosion(fse_world* w, int32_t cx, int32_t cy, int32_t radius, uint32_t tick, uint32_t seed);
 
 /* ---- interactive tools, grid side.  Rigid-body surfaces, Box2D bodies, audio and UI stay with the host. ----------
@@ -379,6 +380,14 @@ FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int32_t n_masks
                              int32_t* n_components, float* pts, int32_t cap_pts, int32_t* pt_off, int32_t cap_contours,
                              int32_t* mask_off);
 /* SOLID mask of a world rect (updateChunkMesh's input, world.cpp:722-760), written to `mask` (rw*rh bytes) */
+/* The host half of updateRigidBodyHitbox / updateChunkMesh (world.cpp:497-563) for the outlines of ONE mask as fse_mask_outline
+ * returns them (pts / pt_off of the mask's contours): each outline reversed is a polygon, clockwise ones are holes, holes are bridged
+ * into their outer polygons and every outer polygon is ear-clipped — the same choices, in the same order, as the reference's
+ * TPPLPartition::RemoveHoles / Triangulate_EC (physics_math.cpp:297-580; csrc/polygons.hpp) — and triangles whose three x or three y
+ * coincide are dropped.  tris: 6 doubles per triangle (x0 y0 x1 y1 x2 y2); group_off[g] .. group_off[g + 1]: the triangles of the
+ * g-th polygon = the b2PolygonShapes of one body; *n_groups polygons kept at least one triangle.  Pure host code. */
+FSE_API int fse_hitbox_triangles(const float* pts, const int32_t* pt_off, int32_t n_contours, double* tris, int32_t cap_tris,
+                                 int32_t* group_off, int32_t cap_groups, int32_t* n_groups);
 FSE_API int fse_solid_mask(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, uint8_t* mask);
 /* physicsCheck(x,y): size / bbox {minx,miny,maxx,maxy} / sorted pixel indices (x + y*width) of the 4-connected SOLID
  * component at (x,y); *count = cap+1 when it exceeds cap, 0 when the seed is not SOLID.  pixels may be NULL. */
@@ -389,16 +398,16 @@ FSE_API int fse_flood_component(fse_world* w, int32_t x, int32_t y, int32_t cap,
  * the colour surface (world.cpp:191-209; membership by component, not by the colour's alpha byte).  The host creates the b2Body at
  * (x, y) with its random velocity and calls updateRigidBodyHitbox (fse_bodies_split).  tiles_out: w * h cells, row-major, written
  * for action 2; when cap_tiles is too small the call fails with the box in *out and changes nothing. */
-/* The probe at the end of world::tick (world.cpp:1929-1934): physicsCheck(tickZone.x + rand() % tickZone.w, tickZone.y + rand() %
- * tickZone.h), with rand() replaced by the counter RNG — draws S_PROBE_X / S_PROBE_Y of cell (0, 0) under rng_key(seed, tick, 15).
- * Pure host function; the caller passes the position to fse_physics_check. */
-FSE_API void fse_probe_position(uint32_t seed, uint32_t tick, const fse_rect* tick_zone, int32_t* x, int32_t* y);
 typedef struct fse_physcheck_result {
     int32_t count;   /* cells of the component; 1001 = abandoned (> 1000), 0 = (x, y) is not SOLID or outside the world */
     int32_t action;  /* 0 nothing, 1 deleted, 2 cut out into tiles_out */
     int32_t x, y, w, h;  /* bounding box of the component (count 1..1000) */
 } fse_physcheck_result;
 FSE_API int fse_physics_check(fse_world* w, int32_t x, int32_t y, fse_physcheck_result* out, fse_cell* tiles_out, int32_t cap_tiles);
+/* The probe at the end of world::tick (world.cpp:1929-1934): physicsCheck(tickZone.x + rand() % tickZone.w, tickZone.y + rand() %
+ * tickZone.h), with rand() replaced by the counter RNG — draws S_PROBE_X / S_PROBE_Y of cell (0, 0) under rng_key(seed, tick, 15).
+ * Pure host function; the caller passes the position to fse_physics_check. */
+FSE_API void fse_probe_position(uint32_t seed, uint32_t tick, const fse_rect* tick_zone, int32_t* x, int32_t* y);
 
 /* ---- active-region tracking: world::active/lastActive (world.hpp:131-133) are allocated but dead in the reference
  * (every writer is commented out), so the only contract is "same cells as a full sweep".  When

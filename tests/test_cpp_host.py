@@ -64,7 +64,24 @@ def test_cpp_host_game_loop_matches_the_python_binding(gpu_ctx, table, tmp_path)
         gw.object_delete()
         dirty = gw.render_dirty(want_stats=True)[0]
         gw.clear_dirty()
-    want = f"hash={gw.stats().hash:016x} particles={gw.particles_count()} dirty_last_tick={dirty} cut_outs={cuts}"
+    # the fracture hand-off the demo runs from C++ (world.hpp updateRigidBodyHitbox), here through the Python binding
+    bw, bh = 40, 24
+    plate = np.zeros((bh, bw), dtype=T.CELL_DTYPE)
+    ys, xs = np.mgrid[0:bh, 0:bw]
+    solid = (xs != 17) & ~((ys >= 3) & (ys < 6) & (xs >= 25) & (xs < 28)) & ~(((xs * 7 + ys * 13) % 11 == 0) & (xs > 30))
+    plate["mat"], plate["color"], plate["fluid"] = np.where(solid, 22, 0), 0x404040 + xs + ys * bw, 2.0
+    gw.bodies_upload([plate])
+    pieces = tris = 0
+    hsum = 0.0
+    for rec, _, groups in gw.update_rigid_body_hitbox(0, angle=np.float32(0.3), weld=(5, 5)):
+        pieces += 1
+        for grp in groups:
+            for t in grp:
+                tris += 1
+                for k in range(3):
+                    hsum += t[k, 0] * (k + 1) + t[k, 1] * (k + 4) + int(rec["x0"]) + 2.0 * int(rec["y0"])
+    assert pieces >= 2 and tris > 10
+    want = f"hash={gw.stats().hash:016x} particles={gw.particles_count()} dirty_last_tick={dirty} cut_outs={cuts} hitbox={pieces},{tris},{hsum:.3f}"
     for e in ents:
         want += f" ent={e['x']:.6f},{e['y']:.6f},{e['vx']:.6f},{e['vy']:.6f},{int(e['ground'])}"
     assert r.stdout.strip() == want
