@@ -411,6 +411,12 @@ def run_ours(args):
     if len(ph_ms) == 4 * CELL_ITER * args.steps:  # mean ms of the 4 colour phases of each automaton iteration
         pm = np.asarray(ph_ms, dtype=np.float64).reshape(args.steps, CELL_ITER, 4).mean(axis=0)
         roof["phase_ms_by_iteration"] = [[round(float(v), 4) for v in row] for row in pm]
+    if use_active:  # bytes actually touched: only awake chunks are streamed; their share of the zone's chunks scales the rate
+        aw, tot = world.active_stats()
+        if tot:
+            roof["awake_chunk_fraction"] = aw / tot
+            roof["achieved_touched"] = achieved * aw / tot
+            roof["frac_touched"] = achieved * aw / tot / peak
     if args.workload in ("sparse", "air") or use_active:
         roof["dense_equivalent"] = True
         roof["note"] = ("settled rows / sleeping chunks are neither loaded nor stored, so `achieved` counts bytes the kernels did not move: it is the "

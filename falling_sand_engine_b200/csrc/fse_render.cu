@@ -204,6 +204,27 @@ __global__ void __launch_bounds__(256) scroll_planes_kernel(Planes dst, Planes s
         dst.fd[g] = src.fd[f];
     }
 }
+// The same for shifts by a multiple of 4 columns on a world whose width is one (every chunk-aligned camera move): a thread moves 4
+// cells of every plane with one 4 / 8 / 16-byte access each — a group of 4 cells has its source entirely inside or outside the world.
+__global__ void __launch_bounds__(256) scroll_planes4_kernel(Planes dst, Planes src, int W, int H, int dx, int dy) {
+    const int X = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (X >= W) return;
+    const int sx = X - dx;
+    const bool okx = sx >= 0 && sx + 4 <= W;
+    for (int Y = blockIdx.y; Y < H; Y += gridDim.y) {
+        const int sy = Y - dy;
+        const size_t g = ((size_t)Y * W + X) >> 2;
+        const size_t f = (okx && sy >= 0 && sy < H) ? ((size_t)sy * W + sx) >> 2 : g;
+        reinterpret_cast<uint32_t*>(dst.mat)[g] = reinterpret_cast<const uint32_t*>(src.mat)[f];
+        const uint32_t dirty = 0x01010101u * F_DIRTY;
+        reinterpret_cast<uint32_t*>(dst.flg)[g] = (reinterpret_cast<const uint32_t*>(src.flg)[f] & ~dirty) | (reinterpret_cast<const uint32_t*>(src.flg)[g] & dirty);
+        reinterpret_cast<uint32_t*>(dst.stl)[g] = reinterpret_cast<const uint32_t*>(src.stl)[f];
+        reinterpret_cast<uint2*>(dst.tmp)[g] = reinterpret_cast<const uint2*>(src.tmp)[f];
+        reinterpret_cast<uint4*>(dst.col)[g] = reinterpret_cast<const uint4*>(src.col)[f];
+        reinterpret_cast<uint4*>(dst.fl)[g] = reinterpret_cast<const uint4*>(src.fl)[f];
+        reinterpret_cast<uint4*>(dst.fd)[g] = reinterpret_cast<const uint4*>(src.fd)[f];
+    }
+}
 // background and real_layer2 move with the grid (world.cpp:2475-2476); layer2Dirty / backgroundDirty do not
 __global__ void __launch_bounds__(256) scroll_layers_kernel(uint8_t* d_mat, int16_t* d_tmp, uint32_t* d_col, uint32_t* d_bg, const uint8_t* s_mat,
                                                             const int16_t* s_tmp, const uint32_t* s_col, const uint32_t* s_bg, int W, int H, int dx,
@@ -494,7 +515,12 @@ extern "C" FSE_API int fse_scroll(fse_world* w, int32_t dx, int32_t dy) {
             CK(cudaMalloc((void**)&q.fd, n * 4));
         }
         dim3 grid((w->W + 255) / 256, w->H < 2048 ? w->H : 2048);
-        scroll_planes_kernel<<<grid, 256, 0, w->stream>>>(w->p_shadow, w->p, w->W, w->H, dx, dy);
+        if (dx % 4 == 0 && w->W % 4 == 0) {
+            dim3 grid4((w->W / 4 + 255) / 256, w->H < 4096 ? w->H : 4096);
+            scroll_planes4_kernel<<<grid4, 256, 0, w->stream>>>(w->p_shadow, w->p, w->W, w->H, dx, dy);
+        } else {
+            scroll_planes_kernel<<<grid, 256, 0, w->stream>>>(w->p_shadow, w->p, w->W, w->H, dx, dy);
+        }
         CK(cudaGetLastError());
         std::swap(w->p, w->p_shadow);  // kernels take the planes from the world at launch time; the stream orders them after the shift
         w->ctx->launches += 1;
