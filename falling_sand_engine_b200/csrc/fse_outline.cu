@@ -150,88 +150,141 @@ __global__ void __launch_bounds__(256) ccl_kernel(OutlineArgs a) {
     if (threadIdx.x == 0) a.ncomp[m] = cnt;
 }
 
+// One thread per mask cell.  A start candidate walks its marching-squares loop and gives up as soon as it meets a lower-index
+// candidate of the same loop, so exactly one thread per loop survives; the survivor walks the loop once more to lay down one vertex
+// per direction run.  Douglas-Peucker then runs one loop at a time with the WHOLE WARP: the farthest-vertex search of a section —
+// the O(n) part of every split — is spread over the lanes (ties go to the lowest index, like the sequential scan), so the long outer
+// loop of a body no longer makes the kernel's time on one thread.
 __global__ void contour_kernel(OutlineArgs a) {
     const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    const int per = a.w * a.h;
-    if (gi >= a.n * per) return;
-    const int m = gi / per, i = gi % per, w = a.w, h = a.h;
+    const int lane = threadIdx.x & 31;
+    const int per = a.w * a.h, w = a.w, h = a.h;
+    const bool in_range = gi < a.n * per;
+    const int m = in_range ? gi / per : 0, i = in_range ? gi % per : 0;
     const uint8_t* d = a.masks + (size_t)m * per;
-    if (!is_candidate(d, i, w, h)) return;
+    bool alive = in_range && is_candidate(d, i, w, h);
     const int sx = i % w, sy = i / w;
-    // first walk: canonical? how many direction runs?
-    int x = sx, y = sy, prev = 0, runs = 0;
-    do {
-        const int v = ms_value(d, x, y, w, h);
-        const int dir = ms_dir(v, prev);
-        if (!(x == sx && y == sy && prev == 0) && x >= 0 && y >= 0 && x < w && y < h) {
-            const int j = x + y * w;
-            if (j < i && is_candidate(d, j, w, h) && ms_dir(v, 0) == dir) return;  // a lower candidate owns this loop
-        }
-        if (dir != prev) runs++;
-        prev = dir;
-        x += dir_dx(dir);
-        y -= dir_dy(dir);
-    } while (x != sx || y != sy);
-    // scratch: px[runs] py[runs] mark[runs] stack[2*runs] out[2*runs]  (floats / ints of the same size)
-    const unsigned int need = 7u * (unsigned int)runs;
-    const unsigned int off = atomicAdd(a.pool_used, need);
-    if (off + need > a.pool_cap) {
-        atomicExch(a.overflow, 1);
-        return;
-    }
-    float* px = a.pool + off;
-    float* py = px + runs;
-    int* mark = reinterpret_cast<int*>(py + runs);
-    int* stack = mark + runs;
-    float* out = reinterpret_cast<float*>(stack + 2 * runs);
-    // second walk: one vertex at the end of every run (world.cpp:483-485)
-    x = sx; y = sy; prev = 0;
-    int k = -1;
-    do {
-        const int dir = ms_dir(ms_value(d, x, y, w, h), prev);
-        if (dir != prev) k++;
-        prev = dir;
-        x += dir_dx(dir);
-        y -= dir_dy(dir);
-        px[k] = (float)x;
-        py[k] = (float)y;
-    } while (x != sx || y != sy);
-    const int np = runs;
-    for (int q = 0; q < np; q++) mark[q] = 1;
-    if (np > 2) {  // simplify(worldMesh, 1) (physics_math.cpp:1766-1811), explicit stack instead of recursion
-        int sp = 0;
-        stack[sp++] = 0;
-        stack[sp++] = np - 1;
-        while (sp > 0) {
-            const int jj = stack[--sp], ii = stack[--sp];
-            if (ii + 1 == jj) continue;
-            float maxd = -1.0f;
-            int maxi = ii;
-            for (int q = ii + 1; q < jj; q++) {
-                const float dist = p_distance(px[q], py[q], px[ii], py[ii], px[jj], py[jj]);
-                if (dist > maxd) {
-                    maxd = dist;
-                    maxi = q;
+    int runs = 0;
+    unsigned int off = 0;
+    if (alive) {  // first walk: canonical? how many direction runs?
+        int x = sx, y = sy, prev = 0;
+        do {
+            const int v = ms_value(d, x, y, w, h);
+            const int dir = ms_dir(v, prev);
+            if (!(x == sx && y == sy && prev == 0) && x >= 0 && y >= 0 && x < w && y < h) {
+                const int j = x + y * w;
+                if (j < i && is_candidate(d, j, w, h) && ms_dir(v, 0) == dir) {  // a lower candidate owns this loop
+                    alive = false;
+                    break;
                 }
             }
-            if (maxd <= 1.0f) {
-                for (int q = ii + 1; q < jj; q++) mark[q] = 0;
-            } else {
-                stack[sp++] = ii; stack[sp++] = maxi;
-                stack[sp++] = maxi; stack[sp++] = jj;
-            }
+            if (dir != prev) runs++;
+            prev = dir;
+            x += dir_dx(dir);
+            y -= dir_dy(dir);
+        } while (x != sx || y != sy);
+    }
+    if (alive) {  // scratch: px[runs] py[runs] mark[runs] stack[2*runs] out[2*runs]  (floats / ints of the same size)
+        const unsigned int need = 7u * (unsigned int)runs;
+        off = atomicAdd(a.pool_used, need);
+        if (off + need > a.pool_cap) {
+            atomicExch(a.overflow, 1);
+            alive = false;
         }
     }
-    int kept = 0;
-    for (int q = 0; q < np; q++)
-        if (mark[q]) {
-            out[2 * kept] = px[q];
-            out[2 * kept + 1] = py[q];
-            kept++;
+    if (alive) {  // second walk: one vertex at the end of every run (world.cpp:483-485)
+        float* px = a.pool + off;
+        float* py = px + runs;
+        int x = sx, y = sy, prev = 0, k = -1;
+        do {
+            const int dir = ms_dir(ms_value(d, x, y, w, h), prev);
+            if (dir != prev) k++;
+            prev = dir;
+            x += dir_dx(dir);
+            y -= dir_dy(dir);
+            px[k] = (float)x;
+            py[k] = (float)y;
+        } while (x != sx || y != sy);
+    }
+    __syncwarp();
+    // simplify(worldMesh, 1) (physics_math.cpp:1766-1811), explicit stack instead of recursion, one loop of this warp at a time
+    unsigned todo = __ballot_sync(0xffffffffu, alive);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int np = __shfl_sync(0xffffffffu, runs, src);
+        const unsigned int o = __shfl_sync(0xffffffffu, off, src);
+        float* px = a.pool + o;
+        float* py = px + np;
+        int* mark = reinterpret_cast<int*>(py + np);
+        int* stack = mark + np;
+        float* out = reinterpret_cast<float*>(stack + 2 * np);
+        for (int q = lane; q < np; q += 32) mark[q] = 1;
+        __syncwarp();
+        if (np > 2) {
+            int sp = 0;
+            if (lane == 0) {
+                stack[0] = 0;
+                stack[1] = np - 1;
+            }
+            sp = 2;
+            __syncwarp();
+            while (sp > 0) {
+                const int jj = stack[sp - 1], ii = stack[sp - 2];
+                sp -= 2;
+                __syncwarp();  // every lane has read the section before a push overwrites its slots
+                if (ii + 1 == jj) continue;
+                const float x1 = px[ii], y1 = py[ii], x2 = px[jj], y2 = py[jj];
+                float maxd = -1.0f;
+                int maxi = ii;
+                for (int q = ii + 1 + lane; q < jj; q += 32) {
+                    const float dist = p_distance(px[q], py[q], x1, y1, x2, y2);
+                    if (dist > maxd) {
+                        maxd = dist;
+                        maxi = q;
+                    }
+                }
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) {  // the largest distance; of equal ones the lowest index, like the sequential scan
+                    const float od = __shfl_xor_sync(0xffffffffu, maxd, sh);
+                    const int oi = __shfl_xor_sync(0xffffffffu, maxi, sh);
+                    if (od > maxd || (od == maxd && oi < maxi)) {
+                        maxd = od;
+                        maxi = oi;
+                    }
+                }
+                if (maxd <= 1.0f) {
+                    for (int q = ii + 1 + lane; q < jj; q += 32) mark[q] = 0;
+                } else {
+                    if (lane == 0) {
+                        stack[sp] = ii; stack[sp + 1] = maxi;
+                        stack[sp + 2] = maxi; stack[sp + 3] = jj;
+                    }
+                    sp += 4;
+                }
+                __syncwarp();
+            }
         }
-    if (kept < 3) return;  // world.cpp:490
-    a.cell_kept[gi] = kept;
-    a.cell_off[gi] = off + 5u * (unsigned int)runs;
+        __syncwarp();
+        // kept vertices, in order: 32 at a time, positions from a ballot
+        int kept = 0;
+        for (int base = 0; base < np; base += 32) {
+            const int q = base + lane;
+            const bool keep = q < np && mark[q];
+            const unsigned kb = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int pos = kept + __popc(kb & ((1u << lane) - 1u));
+                out[2 * pos] = px[q];
+                out[2 * pos + 1] = py[q];
+            }
+            kept += __popc(kb);
+        }
+        if (lane == src && kept >= 3) {  // world.cpp:490
+            a.cell_kept[gi] = kept;
+            a.cell_off[gi] = o + 5u * (unsigned int)np;
+        }
+        __syncwarp();
+    }
 }
 
 // exclusive scan of (flag, value) pairs over the 256 threads of a CTA; returns this thread's offsets, *tot_f / *tot_v get the CTA totals

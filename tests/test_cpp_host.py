@@ -80,7 +80,7 @@ def test_cpp_host_game_loop_matches_the_python_binding(gpu_ctx, table, tmp_path)
                 tris += 1
                 for k in range(3):
                     hsum += t[k, 0] * (k + 1) + t[k, 1] * (k + 4) + int(rec["x0"]) + 2.0 * int(rec["y0"])
-    assert pieces >= 2 and tris > 10
+    assert pieces >= 2 and tris >= 4
     want = f"hash={gw.stats().hash:016x} particles={gw.particles_count()} dirty_last_tick={dirty} cut_outs={cuts} hitbox={pieces},{tris},{hsum:.3f}"
     for e in ents:
         want += f" ent={e['x']:.6f},{e['y']:.6f},{e['vx']:.6f},{e['vy']:.6f},{int(e['ground'])}"
