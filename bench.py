@@ -32,8 +32,7 @@ if ROOT not in sys.path:
 
 CELL_ITER = 3
 ALGO_BYTES_PER_CELL_UPDATE = 36  # 18 B state read + 18 B written per cell per iteration
-KERNEL_OF = {"default": "one colour phase = fse::tick_pass_kernel<1> + tick_pass_kernel<2> + tick_pass3_kernel", "rows_fused": "fse::tick_rows_kernel",
-             "classes": "fse::tick_chunk_kernel"}
+KERNEL_OF = {"default": "one colour phase = fse::tick_pass_kernel<1> + tick_pass_kernel<2> + tick_pass3_kernel", "rows_fused": "fse::tick_rows_kernel"}
 KERNEL_OF["rows"] = KERNEL_OF["default"]
 METRIC = "Gcell-updates/sec (device-timed) at 1/2/4/8 B200; % HBM roofline"
 UNIT = "Gcell-updates/s"
@@ -53,7 +52,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
-    ap.add_argument("--schedule", default="default", choices=["default", "rows", "rows_fused", "classes"], help="in-row schedule of the tick kernel")
+    ap.add_argument("--schedule", default="default", choices=["default", "rows", "rows_fused"], help="in-row schedule of the tick kernel")
     ap.add_argument("--active", type=int, default=-1, help="active-chunk tracking: 1 on, 0 off, -1 = on for --workload sparse")
     return ap.parse_args()
 
@@ -294,7 +293,7 @@ def run_ours(args):
     zone_cells_total = (W - 2 * T.FSE_CHUNK) * (H - 2 * T.FSE_CHUNK)
     world.particles_reserve(1 << 25)
     if args.schedule != "default":
-        world.set_schedule({"classes": 0, "rows": 1, "rows_fused": 2}[args.schedule])
+        world.set_schedule({"rows": 1, "rows_fused": 2}[args.schedule])
     use_active = (args.active == 1 or (args.active < 0 and args.workload == "sparse")) and world_size == 1
     if use_active:
         world.active_enable(True)

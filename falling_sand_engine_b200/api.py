@@ -185,7 +185,7 @@ class World:
         _ck(self.L.fse_tick(self.h, C.byref(a)))
 
     def set_schedule(self, schedule):
-        """0 = 4 interleaved column classes (oracle PARTITIONED), 1 = simultaneous rows (oracle ROWS, default)."""
+        """1 = rows schedule, one kernel per pass (default); 2 = the same results from the fused kernel (oracle ROWS either way)."""
         self.L.fse_set_schedule.argtypes = [C.c_void_p, C.c_int]
         _ck(self.L.fse_set_schedule(self.h, schedule))
         self.schedule = schedule

@@ -579,7 +579,8 @@ FSE_API int fse_debug_role_cycles(fse_world* w, int enable, unsigned long long* 
 }
 
 FSE_API int fse_set_schedule(fse_world* w, int schedule) {
-    if (!w || schedule < FSE_SCHEDULE_CLASSES || schedule > FSE_SCHEDULE_ROWS_FUSED) return fail(FSE_EINVAL, "fse_set_schedule: bad argument");
+    if (!w || schedule < FSE_SCHEDULE_ROWS || schedule > FSE_SCHEDULE_ROWS_FUSED)
+        return fail(FSE_EINVAL, "fse_set_schedule: schedule %d (1 = rows, 2 = rows fused; the classes schedule 0 was removed)", schedule);
     w->schedule = schedule == FSE_SCHEDULE_ROWS_FUSED ? FSE_SCHEDULE_ROWS : schedule;
     w->fused = schedule == FSE_SCHEDULE_ROWS_FUSED;
     return FSE_OK;

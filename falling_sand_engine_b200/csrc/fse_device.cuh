@@ -131,7 +131,7 @@ struct TickParams {
     int chunk_base;         // first chunk (index into the phase's chunk grid or list) of this launch
     int fused;              // rows schedule: 1 = single fused kernel (all passes pipelined), 0 = one kernel per pass
     int fused_max_chunks;   // rows schedule: phases of at most this many chunks run in the fused kernel anyway (one wave of it)
-    int schedule;           // FSE_SCHEDULE_CLASSES (4 interleaved column classes) or FSE_SCHEDULE_ROWS (simultaneous rows)
+    int schedule;           // FSE_SCHEDULE_ROWS (simultaneous rows); kept in the parameters for the launch logic
     int lpt_parts;          // parts the chunk_list was dealt into by lpt_build_kernel (0 / 1: plain longest-first order)
     unsigned int* phase_rows; // optional counter: chunk rows of this phase that pass 1 or pass 2 must run (classify_rows_kernel)
     uint32_t* rowmask;      // per-pass kernels: ROWMASK_WORDS words per chunk of the colour's grid (index cyi * ncx + cxi), see classify_rows_kernel

@@ -303,7 +303,6 @@ extern "C" FSE_API int fse_flow_enable(fse_world* w, int enable) {
     CK(cudaSetDevice(w->ctx->device));
     const size_t n = (size_t)w->W * w->H;
     if (enable && !w->d_flow) {
-        if (w->schedule != FSE_SCHEDULE_ROWS) return fail(FSE_ESTATE, "fse_flow_enable: the flow accumulators are kept by the rows schedule only");
         CK(cudaMalloc((void**)&w->d_flow, 4 * n * sizeof(float)));
         CK(cudaMemsetAsync(w->d_flow, 0, 4 * n * sizeof(float), w->stream));
         CK(cudaMalloc((void**)&w->d_pixels_flow, n * sizeof(uint32_t)));

@@ -196,10 +196,11 @@ FSE_API int fse_clear_dirty(fse_world* w);
 FSE_API int fse_stats_rect(fse_world* w, int32_t x, int32_t y, int32_t rw, int32_t rh, fse_stats* out);
 
 /* ---- the tick ------------------------------------------------------------------ */
-/* In-row visiting order of the chunk tick: both keep the reference's chunk colours, passes and
- * bottom-up rows; each has a bit-exact CPU restatement in oracle/. */
-#define FSE_SCHEDULE_CLASSES 0 /* 4 interleaved column classes, rules executed in place           */
-#define FSE_SCHEDULE_ROWS 1    /* whole row decides from the pre-step state, then commits (default) */
+/* In-row visiting order of the chunk tick: the reference's chunk colours, passes and bottom-up rows are kept; inside
+ * a row every cell decides from the state before the row step, then the row commits ("rows" schedule, bit-exact CPU restatement in
+ * oracle/rows_oracle.cpp).  The two values pick the kernels, not the results.  (Value 0 was round 1's in-place "classes" schedule;
+ * it was removed — slower at every size — and fse_set_schedule refuses it.) */
+#define FSE_SCHEDULE_ROWS 1    /* one kernel per pass and colour phase (default)                        */
 #define FSE_SCHEDULE_ROWS_FUSED 2 /* same results as ROWS, all three passes pipelined in one kernel      */
 FSE_API int fse_set_schedule(fse_world* w, int schedule);
 /* world::tick() (world.cpp:1036-1948) without the physicsCheck tail (see

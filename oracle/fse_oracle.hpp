@@ -20,7 +20,8 @@
 // Two visiting orders over the same per-cell rule code:
 //   * Schedule::REFERENCE   — the reference's: 4 chunk colours x 128x128 chunks, three
 //     passes per chunk, rows bottom-up, columns left-to-right (world.cpp:1057-1086).
-//   * Schedule::PARTITIONED — the GPU's deterministic partitioned schedule: identical at
+//   * Schedule::PARTITIONED — round 1's GPU schedule (its kernel was removed from the product in round 2; the order stays here as a
+//     third visiting order for the schedule-independence pins of tests/test_oracle_pins.py): identical at
 //     chunk/pass/row level; inside a row the 128 columns are visited as 4 interleaved
 //     classes (x mod 4 = 0,1,2,3), with FIRE cells and interacting SAND cells of a class
 //     deferred to sub-phases whose members are >= 8 / >= 12 columns apart.

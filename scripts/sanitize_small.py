@@ -1,6 +1,6 @@
 """Small run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck); no oracle in the loop.
 
-  compute-sanitizer --tool racecheck python scripts/sanitize_small.py [per_pass|fused|classes|aux]
+  compute-sanitizer --tool racecheck python scripts/sanitize_small.py [per_pass|fused|aux]
 
 Worlds are tiny on purpose (the tools slow kernels down 10-100x).  The summaries are kept under profiles/.
 """
@@ -29,8 +29,8 @@ ctx = fse.Context(0, table)
 W, H = 640, 512
 w = fse.World(ctx, W, H)
 Hh.build_mixed(w, table, W, H, seed=1337, extra=list(extra.values()), blob=16)
-if what in ("per_pass", "fused", "classes"):
-    w.set_schedule({"per_pass": 1, "fused": 2, "classes": 0}[what])
+if what in ("per_pass", "fused"):
+    w.set_schedule({"per_pass": 1, "fused": 2}[what])
     for t in range(2):
         w.tick(t)
     if what == "per_pass":

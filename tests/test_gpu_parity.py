@@ -16,8 +16,8 @@ pytestmark = pytest.mark.gpu
 
 
 # name -> (FSE_SCHEDULE_*, oracle Schedule).  "rows" = one launch per pass and colour phase (default)
-SCHEDULES = {"rows": (1, 2), "rows_fused": (2, 2), "classes": (0, 1)}
-ALL_SCHEDULES = ["rows", "rows_fused", "classes"]
+SCHEDULES = {"rows": (1, 2), "rows_fused": (2, 2)}
+ALL_SCHEDULES = ["rows", "rows_fused"]
 
 
 def _pair(oracle, gpu_ctx, table, W, H, sched="rows"):
