@@ -152,9 +152,9 @@ __device__ __forceinline__ CellR ldc(const Ctx& c, int s, int j) {
     r.fd = FD(s, j);
     return r;
 }
-// real_tiles[i] = cell (+ dirty[i] / tickVisited[i] = true as requested by `setbits`).  Out of line on purpose: the rule
-// code stores cells at ~40 places and the kernel is instruction-cache bound (profiles/r1_tick_ncu.md), so one copy of the
-// store sequence beats 40 inlined ones.  p0 = mat | stl << 8 | tmp << 16, p1 = moved | setbits << 8.
+// real_tiles[i] = cell (+ dirty[i] / tickVisited[i] = true as requested by `setbits`).  p0 = mat | stl << 8 | tmp << 16,
+// p1 = moved | setbits << 8.  Inlined at ~20 sites: out-of-line copies (tried in both rounds) make the kernel LARGER — 4832 / 4904 SASS
+// instructions instead of 4744 — because every call site then saves and restores registers around the call.
 __device__ __forceinline__ void stc_raw(const Ctx* cp, int s, int j, uint32_t p0, uint32_t p1, uint32_t col, float fl, float fd) {
     (void)cp;
     MAT(s, j) = (uint8_t)p0;

@@ -34,11 +34,15 @@ def launches(path, out_md, traffic_json):
         lines.append(f"| `{k}` | {len(t)} | {sum(t) / 1e6:.2f} | {100 * sum(t) / tot:.1f} % | {sum(t) / len(t) / 1e3:.1f} | {sum(rd) / len(rd) / 1e6:.1f} | {sum(wr) / len(wr) / 1e6:.1f} |")
         traffic[k] = (sum(rd) / len(rd) + sum(wr) / len(wr))
     open(out_md, "w").write("\n".join(lines) + "\n")
-    # one colour phase of the 8192^2 world = 3 part-launches of each tick kernel (+ classify when the skip gate is on)
-    tick = {k: v for k, v in traffic.items() if "tick_pass" in k or "classify" in k}
-    phase = 3 * sum(tick.values())
-    json.dump({"tick_phase_bytes_per_launch": phase, "per_kernel_bytes_per_launch": {k: 3 * v for k, v in tick.items()},
-               "source": f"{path} (ncu dram__bytes_read.sum + dram__bytes_write.sum of `bench.py --steps 2 --warmup 1 --no-cpu-baseline`, 8192x8192 mixed; a colour phase = 961 chunks is launched as 3 parts, so one phase = 3 launches of each kernel)",
+    # one colour phase of the 8192^2 world = 3 part-launches of pass 1, pass 2 and pass 3 — of the plain instantiation <PASS, 0> (what the
+    # skip gate picks on the mixed world) or of the row-skipping one <PASS, 1> with its classification (the gate's probe ticks)
+    def pick(tag):
+        return {k: v for k, v in traffic.items() if f", {tag}>" in k or "tick_pass3" in k or (tag == 1 and "classify" in k)}
+    plain, skip = pick(0), pick(1)
+    phase = 3 * sum(plain.values())
+    json.dump({"tick_phase_bytes_per_launch": phase, "per_kernel_bytes_per_launch": {k: 3 * v for k, v in plain.items()},
+               "row_skipping_phase_bytes_per_launch": 3 * sum(skip.values()),
+               "source": f"{path} (ncu dram__bytes_read.sum + dram__bytes_write.sum of `bench.py --steps 2 --warmup 1 --no-cpu-baseline`, 8192x8192 mixed; a colour phase = 961 chunks is launched as 3 parts, so one phase = 3 launches of each kernel; <PASS, 0> = the instantiation the skip gate uses on this world)",
                "algorithmic_bytes_per_launch": 36 * 7936 * 7936 // 4}, open(traffic_json, "w"))
     print("\n".join(lines))
     print("phase MB", phase / 1e6)
