@@ -258,13 +258,16 @@ static int make_world(fse_ctx* c, int32_t width, int32_t height, fse_world** out
     if (const char* env = getenv("FSE_STRIP_TIMELINE")) w->timeline_on = atoi(env) != 0;
     if (const char* env = getenv("FSE_STRIP_BOUNDARY_MIN")) w->strip_boundary_min = atoi(env);
     if (const char* env = getenv("FSE_ROW_SKIP")) w->rowskip_mode = atoi(env);
+    if (const char* env = getenv("FSE_P2_SPLIT")) w->p2_split = atoi(env);
+    if (const char* env = getenv("FSE_P2_SPLIT_MAX_SEQ")) w->p2_split_max_seq = (float)atof(env);
     if (const char* env = getenv("FSE_ROW_SKIP_MAX_ACTIVE")) w->rowskip_max_active = (float)atof(env);
     for (int q = 0; q < 16; q++) {
         w->phase_active[q] = -1.0f;
+        w->phase_seq[q] = -1.0f;
         w->phase_rows_total[q] = 0;
     }
-    if (e == cudaSuccess) e = cudaMalloc((void**)&w->d_phase_rows, 16 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_phase_rows, 16 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&w->d_phase_rows, 32 * sizeof(unsigned int));  // [0..15] active rows, [16..31] rows with live powder / gas
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_phase_rows, 32 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->ev_phase_rows, cudaEventDisableTiming);
     {
         int sms = 148;
@@ -611,13 +614,16 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
     // skip gate: collect the counts of the last tick that finished, then zero the counters for this one
     if (w->phase_rows_pending && cudaEventQuery(w->ev_phase_rows) == cudaSuccess) {
         for (int q = 0; q < 16; q++)
-            if (((w->phase_rows_valid >> q) & 1u) && w->phase_rows_total[q] > 0) w->phase_active[q] = (float)w->h_phase_rows[q] / (float)w->phase_rows_total[q];
+            if (((w->phase_rows_valid >> q) & 1u) && w->phase_rows_total[q] > 0) {
+                w->phase_active[q] = (float)w->h_phase_rows[q] / (float)w->phase_rows_total[q];
+                w->phase_seq[q] = (float)w->h_phase_rows[16 + q] / (float)w->phase_rows_total[q];
+            }
         w->phase_rows_pending = false;
     }
     const bool gate_probe = (w->ticks % 32) == 0;
     const bool gate_collect = !w->phase_rows_pending && w->rowskip_mode == 2;  // one copy in flight at a time
     if (gate_collect) {
-        CK(cudaMemsetAsync(w->d_phase_rows, 0, 16 * sizeof(unsigned int), w->stream));
+        CK(cudaMemsetAsync(w->d_phase_rows, 0, 32 * sizeof(unsigned int), w->stream));
         w->phase_rows_counted = 0;
     }
     for (int iter = 0; iter < a->cell_iter; iter++) {
@@ -661,7 +667,16 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
             const int ph = iter * 4 + tk;
             bool skip_here = w->rowskip_mode == 1;
             if (w->rowskip_mode == 2) skip_here = gate_probe || w->phase_active[ph] < 0.0f || w->phase_active[ph] < w->rowskip_max_active;
-            if (skip_here && w->schedule == FSE_SCHEDULE_ROWS && !w->fused) {
+            // without row skipping pass 1 still sorts the rows for pass 2 (liquid-only rows are applied by a row-parallel kernel, pass 2
+            // steps only rows with powder or gas: tick_pass2_apply_kernel); not with active-chunk tracking, whose pass 2 walks every row
+            // Measured on the 8192^2 mixed world: phases in which powder still acts lose 3-8 % to the split (the row-skipping instantiation of
+            // pass 2 and the extra launch cost more than the skipped rows save), phases in which only liquid acts gain 10 %.  So the split
+            // is used where the last classification of the phase (the skip gate's probe ticks) found live powder or gas in fewer than
+            // p2_split_max_seq of the rows (FSE_P2_SPLIT = 0 never, 1 = this rule, 2 = always).  Correct in any phase either way.
+            const bool split_here = !skip_here && !w->active_on &&
+                                    (w->p2_split == 2 || (w->p2_split == 1 && w->phase_seq[ph] >= 0.0f && w->phase_seq[ph] < w->p2_split_max_seq));
+            P.split = split_here ? 1 : 0;
+            if ((skip_here || split_here) && w->schedule == FSE_SCHEDULE_ROWS && !w->fused) {
                 const int need = ((nx + 1) / 2) * ((ny + 1) / 2);
                 if (need > w->rowmask_cap) {
                     CK(cudaStreamSynchronize(w->stream));
@@ -672,7 +687,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
                     w->rowmask_cap = need;
                 }
                 P.rowmask = w->d_rowmask;
-                if (gate_collect) {
+                if (gate_collect && skip_here) {
                     P.phase_rows = w->d_phase_rows + ph;
                     w->phase_rows_counted |= 1u << ph;
                     // rows the classification covers: the chunks of this colour this rank launches on the per-pass kernels
@@ -820,7 +835,7 @@ FSE_API int fse_tick(fse_world* w, const fse_tick_args* a) {
         }
     }
     if (gate_collect && w->phase_rows_counted) {
-        CK(cudaMemcpyAsync(w->h_phase_rows, w->d_phase_rows, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaMemcpyAsync(w->h_phase_rows, w->d_phase_rows, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
         CK(cudaEventRecord(w->ev_phase_rows, w->stream));
         w->phase_rows_valid = w->phase_rows_counted;
         w->phase_rows_pending = true;

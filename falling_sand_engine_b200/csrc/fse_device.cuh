@@ -135,6 +135,7 @@ struct TickParams {
     int lpt_parts;          // parts the chunk_list was dealt into by lpt_build_kernel (0 / 1: plain longest-first order)
     unsigned int* phase_rows; // optional counter: chunk rows of this phase that pass 1 or pass 2 must run (classify_rows_kernel)
     uint32_t* rowmask;      // per-pass kernels: ROWMASK_WORDS words per chunk of the colour's grid (index cyi * ncx + cxi), see classify_rows_kernel
+    int split;              // per-pass kernels without row skipping: pass 1 classifies the rows for pass 2 (see tick_pass2_apply_kernel)
     float* flowx;           // optional render-only accumulators world::flowX / flowY (world.cpp:1334, 1374, 1402, 1432), W x H floats each,
     float* flowy;           // null = not kept (fse_flow_enable)
 };

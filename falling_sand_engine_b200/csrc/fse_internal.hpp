@@ -80,6 +80,7 @@ struct fse_world {
     // settled-row skipping of the per-pass kernels (classify_rows_kernel): ROWMASK_WORDS words per chunk of a colour's grid
     uint32_t* d_rowmask = nullptr;
     int rowmask_cap = 0;
+    int p2_split = 1;        // FSE_P2_SPLIT: 0 never, 1 (default) from the iteration on in which no powder / gas acts, 2 always: pass 2 as a row-parallel liquid apply + sequential powder / gas rows
     int rowskip_mode = 2;    // FSE_ROW_SKIP: 0 = step every row, 1 = always skip settled rows, 2 (default) = per phase, by the gate below
     // Skip gate.  A phase is bound by the row chain of its busiest chunk, so skipping settled rows only pays when most rows are
     // settled; below that the classification costs more than it saves.  Each classified phase counts its active rows on the device;
@@ -92,6 +93,8 @@ struct fse_world {
     uint32_t phase_rows_valid = 0;          // bit p: h_phase_rows[p] was counted in the tick that was copied
     uint32_t phase_rows_counted = 0;        // bit p: phase p is being classified in the tick in flight
     float phase_active[16];                 // last known active fraction per phase, < 0 = unknown
+    float phase_seq[16];                    // last known fraction of rows with live powder / gas per phase, < 0 = unknown (pass-2 split gate)
+    float p2_split_max_seq = 0.10f;         // FSE_P2_SPLIT_MAX_SEQ
     long long phase_rows_total[16];
     float rowskip_max_active = 0.25f;       // FSE_ROW_SKIP_MAX_ACTIVE
     // particle pool bookkeeping on the host: count seen by the last call that read it, particles promised to calls since, drops

@@ -477,11 +477,18 @@ cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t st
             const int hi = dealt ? part_lo(n_chunks, parts, q + 1) : (int)((long long)n_chunks * (q + 1) / parts);
             if (hi <= lo) continue;  // fewer chunks than parts
             Q.chunk_base = P.chunk_base + lo;
-            if (Q.rowmask) {
+            if (Q.rowmask && !Q.split) {
                 classify_rows_kernel<<<(hi - lo) * 4, 1024, sizeof(Lut), st>>>(Q);
                 *launched += 1;
             }
-            if (Q.rowmask) {
+            if (Q.rowmask && Q.split) {
+                // no settled-row skipping in pass 1, but pass 1 sorts the rows for pass 2: liquid-only rows are applied by a row-parallel
+                // kernel, and pass 2 steps only the rows that still hold powder or gas (its row-skipping instantiation, fed by pass 1)
+                tick_pass_kernel<1, false><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>) + pad, st>>>(Q);
+                tick_pass2_apply_kernel<<<(hi - lo) * (CHUNK / 4), 128, 0, st>>>(Q);
+                tick_pass_kernel<2, true><<<hi - lo, PassGeom<2>::THREADS, sizeof(SmemPass<2>) + pad, st>>>(Q);
+                *launched += 1;
+            } else if (Q.rowmask) {
                 tick_pass_kernel<1, true><<<hi - lo, PassGeom<1>::THREADS, sizeof(SmemPass<1>) + pad, st>>>(Q);
                 tick_pass_kernel<2, true><<<hi - lo, PassGeom<2>::THREADS, sizeof(SmemPass<2>) + pad, st>>>(Q);
             } else {

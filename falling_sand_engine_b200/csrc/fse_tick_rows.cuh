@@ -1032,6 +1032,7 @@ struct __align__(128) SmemPass {
     unsigned long long bar[PassGeom<PASS>::RN];
     uint32_t m_act[4];   // rows of the chunk this pass must run (classify_rows_kernel; pass 2: + what pass 1 changed)
     uint32_t m_lazy[4];  // pass 2: rows whose pass-1 tickVisited marks are still implicit
+    uint32_t m_out[3][4];  // pass 1 in split mode (store warp only): rows with unvisited powder / gas, with unvisited gas, with unvisited liquid
     typename PassScratch<PASS>::type rs;
 };
 
@@ -1099,7 +1100,7 @@ __device__ __forceinline__ void materialize_marks(const Ctx& c, int slot, int j)
 
 // grid = 4 CTAs per chunk of the launch, 1024 threads: warp w of CTA c votes row k = 32 * c + w (counted from the chunk's bottom row)
 __global__ void __launch_bounds__(1024) classify_rows_kernel(const __grid_constant__ TickParams P) {
-    __shared__ uint32_t s_a1[32], s_a2[32];
+    __shared__ uint32_t s_a1[32], s_a2[32], s_a3[32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     {
         const uint4* src = reinterpret_cast<const uint4*>(&P.tabs->lut);
@@ -1129,13 +1130,14 @@ __global__ void __launch_bounds__(1024) classify_rows_kernel(const __grid_consta
     uint32_t bL = __shfl_up_sync(0xffffffffu, bw >> 24, 1), bR = __shfl_down_sync(0xffffffffu, bw & 0xff, 1);
     if (lane == 0) bL = __ldg(P.p.mat + base + P.W - 1);
     if (lane == 31) bR = __ldg(P.p.mat + base + P.W + CHUNK);
-    bool a1 = false, a2 = false;
+    bool a1 = false, a2 = false, a3 = false;  // a3: powder or gas that still acts (pass 2 needs its sequential row steps for those)
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int m = (mw >> (8 * q)) & 0xff;
         if (P.iter >= (int)LUTP->iters[m]) continue;  // marked in pass 1 (implicitly), skipped afterwards
         const int ph = LUTP->phys[m];
         if (ph == P_AIR || ph == P_SOLID) continue;
+        a3 |= ph == P_SAND || ph == P_GAS;
         const bool moved = (fw >> (8 * q)) & F_MOVED;
         const int mb = (bw >> (8 * q)) & 0xff;
         const int mbl = q == 0 ? (int)bL : (int)((bw >> (8 * (q - 1))) & 0xff), mbr = q == 3 ? (int)bR : (int)((bw >> (8 * (q + 1))) & 0xff);
@@ -1174,20 +1176,25 @@ __global__ void __launch_bounds__(1024) classify_rows_kernel(const __grid_consta
             a1 = a2 = true;
         }
     }
-    const bool r1 = __any_sync(0xffffffffu, a1), r2 = __any_sync(0xffffffffu, a2);
+    const bool r1 = __any_sync(0xffffffffu, a1), r2 = __any_sync(0xffffffffu, a2), r3 = __any_sync(0xffffffffu, a3);
     if (lane == 0) {
         s_a1[warp] = r1 ? 1u : 0u;
         s_a2[warp] = r2 ? 1u : 0u;
+        s_a3[warp] = r3 ? 1u : 0u;
     }
     __syncthreads();
     if (warp == 0) {
         const uint32_t w1 = __ballot_sync(0xffffffffu, s_a1[lane] != 0), w2 = __ballot_sync(0xffffffffu, s_a2[lane] != 0);
+        const uint32_t w3 = __ballot_sync(0xffffffffu, s_a3[lane] != 0);
         if (lane == 0) {
             uint32_t* o = P.rowmask + (size_t)(cyi * P.ncx + cxi) * ROWMASK_WORDS + (blockIdx.x & 3);
             o[0] = w1;
             o[4] = w2;
             o[8] = 0;
-            if (P.phase_rows) atomicAdd(P.phase_rows, (unsigned int)__popc(w1 | w2));  // rows some pass must run (fse_tick's skip gate)
+            if (P.phase_rows) {
+                atomicAdd(P.phase_rows, (unsigned int)__popc(w1 | w2));  // rows some pass must run (fse_tick's skip gate)
+                if (w3) atomicAdd(P.phase_rows + 16, (unsigned int)__popc(w3));  // rows with live powder / gas (fse_tick's pass-2 split gate)
+            }
         }
     }
 }
@@ -1208,6 +1215,11 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     const DevTables* T = P.tabs;
     // settled-row skipping (see classify_rows_kernel): the rows this pass must run; a chunk without any is done
     uint32_t* const gmask = (SKIP && P.rowmask) ? P.rowmask + (size_t)mask_idx * ROWMASK_WORDS : nullptr;
+    // pass 1 without row skipping, split mode: the store warp looks at every row as it becomes final and tells pass 2 which rows still
+    // hold powder or gas that has not moved (they need pass 2's sequential row steps) and which hold nothing but liquid waiting for its
+    // fluidAmountDiff (tick_pass2_apply_kernel takes those, all at once)
+    uint32_t* const omask = (PASS == 1 && !SKIP && P.split && P.rowmask) ? P.rowmask + (size_t)mask_idx * ROWMASK_WORDS : nullptr;
+    if (omask && tid < 12) (&S.m_out[0][0])[tid] = 0u;  // (a __syncthreads follows before the first row is stored)
     if (gmask) {
         const uint32_t* ga = gmask + (PASS == 1 ? 0 : 4);
         const uint32_t a0 = ga[0], a1 = ga[1], a2 = ga[2], a3 = ga[3];
@@ -1419,6 +1431,25 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
                     const bool core_row = ks >= 0 && ks < CHUNK;
                     const bool all_store = S.h.rowmod[qs_] != 0;
                     const bool vis_store = S.h.rowvis[qs_] != 0;
+                    if (PASS == 1 && !SKIP && omask && core_row) {  // lane l: columns 4l .. 4l + 3 of the chunk's own cells
+                        const uint32_t mw4 = *reinterpret_cast<const uint32_t*>(S.ring + qs_ * ROW_BYTES + OFF_MAT + HX8 + 4 * lane);
+                        const uint32_t fw4 = *reinterpret_cast<const uint32_t*>(S.ring + qs_ * ROW_BYTES + OFF_FLG + HX8 + 4 * lane);
+                        bool sg = false, gs = false, sp = false;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            if ((fw4 >> (8 * b)) & F_VISITED) continue;  // pass 2 skips visited cells (world.cpp:1600)
+                            const int ph = LUTP->phys[(mw4 >> (8 * b)) & 0xffu];
+                            sg |= ph == P_SAND || ph == P_GAS;
+                            gs |= ph == P_GAS;
+                            sp |= ph == P_SOUP;
+                        }
+                        const bool r_sg = __any_sync(0xffffffffu, sg), r_gs = __any_sync(0xffffffffu, gs), r_sp = __any_sync(0xffffffffu, sp);
+                        if (lane == 0) {  // the store warp is the only writer of these words
+                            if (r_sg) S.m_out[0][ks >> 5] |= 1u << (ks & 31);
+                            if (r_gs) S.m_out[1][ks >> 5] |= 1u << (ks & 31);
+                            if (r_sp) S.m_out[2][ks >> 5] |= 1u << (ks & 31);
+                        }
+                    }
                     if (PASS == 2 && gmask && core_row && (all_store || vis_store) && lane == (ks >> 5)) io_lazy |= 1u << (ks & 31);
                     if (PASS == 1 && gmask) {
                         if (core_row && !(S.h.rowlazy[qs_] && !all_store && !vis_store) && lane == (ks >> 5)) io_lazy &= ~(1u << (ks & 31));
@@ -1481,6 +1512,18 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     if (PASS == 1 && gmask && io_store && lane < 4) {
         gmask[8 + lane] = io_lazy;
         gmask[4 + lane] |= io_chg;
+    }
+    if (PASS == 1 && !SKIP && omask && io_store) {
+        // a row of liquid may be applied ahead of the sequential rows unless gas in the row below could still move up into it (pass 2,
+        // world.cpp:1799-1819, reads the row above before that row's own step)
+        __syncwarp();
+        if (lane < 4) {
+            const uint32_t o_seq = S.m_out[0][lane], o_gas = S.m_out[1][lane], o_soup = S.m_out[2][lane];
+            const uint32_t gas_below = (o_gas << 1) | (lane ? S.m_out[1][lane - 1] >> 31 : 0u);
+            omask[lane] = o_soup & ~o_seq & ~gas_below;  // rows tick_pass2_apply_kernel takes
+            omask[4 + lane] = o_seq | (o_soup & gas_below);  // rows pass 2 must step (liquid rows gas may enter stay in the chain)
+            omask[8 + lane] = 0;                           // pass 1 stepped every row: no tickVisited mark is implicit
+        }
     }
     if (PASS == 2 && gmask && io_store && lane < 4 && io_lazy) gmask[8 + lane] &= ~io_lazy;  // pass 3 applies the rule to what is left
     if (io_store) bulk_wait_all();
@@ -1627,6 +1670,56 @@ __global__ void __launch_bounds__(128) tick_pass3_kernel(const __grid_constant__
         lazy = (P.rowmask[(size_t)(cyi * P.ncx + cxi) * ROWMASK_WORDS + 8 + (k >> 5)] >> (k & 31)) & 1u;
     }
     pass3_row_global(P, P.rkey, P.x0 + cxi * 2 * CHUNK, P.y0 + cyi * 2 * CHUNK + r, lane, lazy);
+}
+
+// Pass 2 of a liquid cell (world.cpp:1728-1745) touches nothing but the cell itself: fluidAmount += fluidAmountDiff, or the cell dies.
+// Rows whose unvisited cells are all liquid (and that no gas from the row below can still enter) therefore do not need pass 2's
+// bottom-up row chain: one warp per row applies them straight on global memory, before the sequential rows run — a row above sees them
+// applied either way, and a row below neither reads nor writes them.  Pass 1's store warp made the row lists (run_pass, omask).
+__global__ void __launch_bounds__(128) tick_pass2_apply_kernel(const __grid_constant__ TickParams P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = (int)(blockIdx.x >> 5) + P.chunk_base;
+    const int r = ((blockIdx.x & 31) << 2) + warp;  // memory row inside the chunk
+    int cxi, cyi;
+    if (P.list_count && chunk >= *P.list_count) return;
+    if (P.chunk_list) {
+        int v = P.chunk_list[chunk];
+        cxi = v & 0xffff;
+        cyi = v >> 16;
+    } else {
+        cxi = chunk % P.ncx;
+        cyi = chunk / P.ncx;
+    }
+    const int k = CHUNK - 1 - r;
+    if (!((P.rowmask[(size_t)(cyi * P.ncx + cxi) * ROWMASK_WORDS + (k >> 5)] >> (k & 31)) & 1u)) return;
+    const DevTables* T = P.tabs;
+    const size_t base = (size_t)(P.y0 + cyi * 2 * CHUNK + r) * P.W + (P.x0 + cxi * 2 * CHUNK);
+    uint32_t* flgw = reinterpret_cast<uint32_t*>(P.p.flg + base) + lane;
+    const uint32_t mw = __ldcg(reinterpret_cast<const uint32_t*>(P.p.mat + base) + lane);
+    uint32_t fw = __ldcg(flgw);
+    const uint32_t fw0 = fw;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        if ((fw >> (8 * b)) & F_VISITED) continue;
+        if (__ldg(T->lut.phys + ((mw >> (8 * b)) & 0xffu)) != P_SOUP) continue;
+        const size_t g = base + 4 * lane + b;
+        const float fd = __ldcg(P.p.fd + g);
+        const float a = __fadd_rn(__ldcg(P.p.fl + g), fd);
+        if (a < FLUID_MinValue) {  // stc(nothing, F_DIRTY | F_VISITED)
+            P.p.mat[g] = (uint8_t)T->air;
+            P.p.stl[g] = 0;
+            P.p.tmp[g] = 0;
+            P.p.col[g] = 0;
+            P.p.fl[g] = 2.0f;
+            P.p.fd[g] = 0.0f;
+            fw = (fw & ~(0xffu << (8 * b))) | ((uint32_t)(F_DIRTY | F_VISITED) << (8 * b));
+        } else {
+            P.p.fl[g] = a;
+            P.p.fd[g] = 0.0f;
+            fw |= (uint32_t)(F_DIRTY | F_VISITED) << (8 * b);
+        }
+    }
+    if (fw != fw0) *flgw = fw;
 }
 
 // Active-chunk bookkeeping after the three passes of a phase (per-pass kernels): wake the 3x3 chunks around a chunk whose state

@@ -265,6 +265,27 @@ def test_benched_kernel_path_at_more_than_one_wave(oracle, gpu_ctx, table, monke
     Hh.assert_cells_equal(ow.read_rect(0, 1500, W, 1024), gw.read_rect(0, 1500, W, 1024), "band of the large world")
 
 
+@pytest.mark.parametrize("split", ["0", "2"])
+def test_pass2_split_modes_exact(oracle, gpu_ctx, table, monkeypatch, split):
+    """Pass 2 as one chain of row steps (FSE_P2_SPLIT=0) or split into a row-parallel liquid apply + the rows that still hold powder or
+    gas (FSE_P2_SPLIT=2: in every phase; the default uses it only where few rows hold live powder): bit-identical to the oracle either
+    way, on a world with liquids over gas pockets, steam made over lava in mid-tick and sand sliding into liquid."""
+    monkeypatch.setenv("FSE_P2_SPLIT", split)
+    monkeypatch.setenv("FSE_ROW_SKIP", "0")  # no settled-row skipping: the phases the split is for
+    W, H = 768, 640
+    tbl, extra = G.bench_table(table)
+    ow, gw = _pair(oracle, gpu_ctx, tbl, W, H, "rows")
+    Hh.build_mixed(ow, tbl, W, H, seed=19, extra=list(extra.values()), blob=16)
+    Hh.build_mixed(gw, tbl, W, H, seed=19, extra=list(extra.values()), blob=16)
+    for t in range(12):
+        for w in (ow, gw):
+            w.tick(t, seed=5)
+            w.particles_tick()
+        if t % 3 == 2:
+            Hh.assert_cells_equal(ow.read_all(), gw.read_all(), f"split {split} tick {t}")
+            Hh.assert_particles_equal(ow.particles_read(), gw.particles_read(), f"split {split} tick {t}")
+
+
 def test_small_phases_pick_the_fused_kernel_with_identical_results(oracle, gpu_ctx, table, monkeypatch):
     """Default kernel selection (no override): a 640x512 world has 2-3 chunks per colour phase, far below one wave of the fused
     kernel, so the rows schedule runs there; results must not depend on the choice."""
