@@ -367,6 +367,7 @@ FSE_API void fse_world_destroy(fse_world* w) {
 }
 
 FSE_API void fse_probe_position(uint32_t seed, uint32_t tick, const fse_rect* z, int32_t* x, int32_t* y) {
+    if (!z) return;
     const uint32_t cb = rng_cell(rng_key(seed, tick, 15u), 0, 0);
     if (x) *x = z->x + (int32_t)(rng_draw(cb, S_PROBE_X) % (uint32_t)(z->w > 0 ? z->w : 1));
     if (y) *y = z->y + (int32_t)(rng_draw(cb, S_PROBE_Y) % (uint32_t)(z->h > 0 ? z->h : 1));

@@ -11,6 +11,7 @@ extern "C" FSE_API int fse_hitbox_triangles(const float* pts, const int32_t* pt_
                                             int32_t* group_off, int32_t cap_groups, int32_t* n_groups) {
     if (!pts || !pt_off || n_contours < 0 || !tris || !group_off || !n_groups || cap_groups < 0 || cap_tris < 0)
         return fail(FSE_EINVAL, "fse_hitbox_triangles: bad argument");
+    if (n_contours > 0 && pt_off[0] < 0) return fail(FSE_EINVAL, "fse_hitbox_triangles: negative point offset");
     std::vector<std::vector<fse_host::Vec2d>> outlines((size_t)n_contours);
     for (int c = 0; c < n_contours; c++) {
         if (pt_off[c + 1] < pt_off[c]) return fail(FSE_EINVAL, "fse_hitbox_triangles: point offsets must not decrease");

@@ -303,9 +303,16 @@ extern "C" FSE_API int fse_flow_enable(fse_world* w, int enable) {
     CK(cudaSetDevice(w->ctx->device));
     const size_t n = (size_t)w->W * w->H;
     if (enable && !w->d_flow) {
-        CK(cudaMalloc((void**)&w->d_flow, 4 * n * sizeof(float)));
+        float* fl = nullptr;
+        uint32_t* px = nullptr;
+        if (cudaMalloc((void**)&fl, 4 * n * sizeof(float)) != cudaSuccess || cudaMalloc((void**)&px, n * sizeof(uint32_t)) != cudaSuccess) {
+            cudaFree(fl);  // all or nothing: a world with accumulators but no texture would make fse_render_dirty write through null
+            cudaGetLastError();
+            return fail(FSE_ENOMEM, "fse_flow_enable: no memory for %zu cells of flow planes", n);
+        }
+        w->d_flow = fl;
+        w->d_pixels_flow = px;
         CK(cudaMemsetAsync(w->d_flow, 0, 4 * n * sizeof(float), w->stream));
-        CK(cudaMalloc((void**)&w->d_pixels_flow, n * sizeof(uint32_t)));
         CK(cudaMemsetAsync(w->d_pixels_flow, 0, n * sizeof(uint32_t), w->stream));
     } else if (!enable && w->d_flow) {
         CK(cudaStreamSynchronize(w->stream));
@@ -381,12 +388,18 @@ static int ensure_layers(fse_world* w) {
     if (w->l2_mat) return FSE_OK;
     if (!w->ctx->has_materials) return fail(FSE_ESTATE, "layer planes: fse_materials_set first");
     const size_t n = (size_t)w->W * w->H;
-    CK(cudaMalloc((void**)&w->l2_mat, n));
-    CK(cudaMalloc((void**)&w->l2_tmp, n * 2));
-    CK(cudaMalloc((void**)&w->l2_col, n * 4));
-    CK(cudaMalloc((void**)&w->bg_col, n * 4));
-    CK(cudaMalloc((void**)&w->layer_dirty, n));
-    CK(cudaMalloc((void**)&w->d_pixels_layers, 2 * n * 4));
+    {   // all or nothing: l2_mat != null is what "the layer planes exist" means everywhere else
+        void* q[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        const size_t bytes[6] = {n, n * 2, n * 4, n * 4, n, 2 * n * 4};
+        for (int i = 0; i < 6; i++)
+            if (cudaMalloc(&q[i], bytes[i]) != cudaSuccess) {
+                for (int j = 0; j < i; j++) cudaFree(q[j]);
+                cudaGetLastError();
+                return fail(FSE_ENOMEM, "layer planes: no memory for %zu cells", n);
+            }
+        w->l2_mat = (uint8_t*)q[0]; w->l2_tmp = (int16_t*)q[1]; w->l2_col = (uint32_t*)q[2]; w->bg_col = (uint32_t*)q[3];
+        w->layer_dirty = (uint8_t*)q[4]; w->d_pixels_layers = (uint32_t*)q[5];
+    }
     fill_u8_kernel<<<grid_sm(w), 256, 0, w->stream>>>(w->l2_mat, n, (uint8_t)w->ctx->h_tabs.air);  // Tiles_NOTHING (world.cpp:117-119)
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(w->l2_tmp, 0, n * 2, w->stream));
@@ -507,11 +520,17 @@ extern "C" FSE_API int fse_scroll(fse_world* w, int32_t dx, int32_t dy) {
     CK(cudaSetDevice(w->ctx->device));
     const size_t n = (size_t)w->W * w->H;
     if (dx > -w->W && dx < w->W && dy > -w->H && dy < w->H) {  // otherwise no cell has a source inside the world
-        if (!w->p_shadow.mat) {
-            Planes& q = w->p_shadow;
-            CK(cudaMalloc((void**)&q.mat, n)); CK(cudaMalloc((void**)&q.flg, n)); CK(cudaMalloc((void**)&q.stl, n));
-            CK(cudaMalloc((void**)&q.tmp, n * 2)); CK(cudaMalloc((void**)&q.col, n * 4)); CK(cudaMalloc((void**)&q.fl, n * 4));
-            CK(cudaMalloc((void**)&q.fd, n * 4));
+        if (!w->p_shadow.mat) {  // all or nothing
+            void* q[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            const size_t bytes[7] = {n, n, n, n * 2, n * 4, n * 4, n * 4};
+            for (int i = 0; i < 7; i++)
+                if (cudaMalloc(&q[i], bytes[i]) != cudaSuccess) {
+                    for (int j = 0; j < i; j++) cudaFree(q[j]);
+                    cudaGetLastError();
+                    return fail(FSE_ENOMEM, "fse_scroll: no memory for the second plane set (%zu cells)", n);
+                }
+            w->p_shadow.mat = (uint8_t*)q[0]; w->p_shadow.flg = (uint8_t*)q[1]; w->p_shadow.stl = (uint8_t*)q[2]; w->p_shadow.tmp = (int16_t*)q[3];
+            w->p_shadow.col = (uint32_t*)q[4]; w->p_shadow.fl = (float*)q[5]; w->p_shadow.fd = (float*)q[6];
         }
         dim3 grid((w->W + 255) / 256, w->H < 2048 ? w->H : 2048);
         if (dx % 4 == 0 && w->W % 4 == 0) {
@@ -525,8 +544,15 @@ extern "C" FSE_API int fse_scroll(fse_world* w, int32_t dx, int32_t dy) {
         w->ctx->launches += 1;
         if (w->l2_mat) {
             if (!w->l2_mat_s) {
-                CK(cudaMalloc((void**)&w->l2_mat_s, n)); CK(cudaMalloc((void**)&w->l2_tmp_s, n * 2));
-                CK(cudaMalloc((void**)&w->l2_col_s, n * 4)); CK(cudaMalloc((void**)&w->bg_col_s, n * 4));
+                void* q[4] = {nullptr, nullptr, nullptr, nullptr};
+                const size_t bytes[4] = {n, n * 2, n * 4, n * 4};
+                for (int i = 0; i < 4; i++)
+                    if (cudaMalloc(&q[i], bytes[i]) != cudaSuccess) {
+                        for (int j = 0; j < i; j++) cudaFree(q[j]);
+                        cudaGetLastError();
+                        return fail(FSE_ENOMEM, "fse_scroll: no memory for the second set of layer planes (%zu cells); the grid was shifted, the layers were not", n);
+                    }
+                w->l2_mat_s = (uint8_t*)q[0]; w->l2_tmp_s = (int16_t*)q[1]; w->l2_col_s = (uint32_t*)q[2]; w->bg_col_s = (uint32_t*)q[3];
             }
             scroll_layers_kernel<<<grid, 256, 0, w->stream>>>(w->l2_mat_s, w->l2_tmp_s, w->l2_col_s, w->bg_col_s, w->l2_mat, w->l2_tmp, w->l2_col,
                                                               w->bg_col, w->W, w->H, dx, dy);
