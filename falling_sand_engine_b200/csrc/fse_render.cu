@@ -515,7 +515,9 @@ extern "C" FSE_API int fse_render_layers(fse_world* w, int draw_background_grid,
 
 extern "C" FSE_API int fse_scroll(fse_world* w, int32_t dx, int32_t dy) {
     if (!w) return fail(FSE_EINVAL, "fse_scroll: null world");
-    if (w->strip && w->ctx->nranks > 1) return fail(FSE_ESTATE, "fse_scroll: not available on multi-rank strips");
+    // multi-rank strips: a horizontal shift never leaves a rank's rows (every rank makes the call and shifts what it holds, ghost rows
+    // included); a vertical one would move rows between ranks and is left to the host (save, shift, reload)
+    if (w->strip && w->ctx->nranks > 1 && dy != 0) return fail(FSE_ESTATE, "fse_scroll: on multi-rank strips only horizontal shifts (dy = 0) are available");
     if (dx == 0 && dy == 0) return FSE_OK;
     CK(cudaSetDevice(w->ctx->device));
     const size_t n = (size_t)w->W * w->H;

@@ -27,6 +27,8 @@ def main():
         if t == 2:  # a blast and an eraser stroke across the cuts: every rank makes the call, each clears the rows it holds
             sw.explosion(W // 2, H // 2 + 5, 40, tick=t, seed=1337)
             sw.tool_erase_line(200, H // 4 - 30, 700, 3 * H // 4 + 20, 9)
+        if t == 4:  # the camera moves one chunk to the right: a horizontal shift stays inside every rank's rows
+            sw.scroll(-128, 0)
         sw.particles_tick()  # ghost refresh, migration, integration and the deposit rounds with the band proposals exchanged
         if t % 4 == 2:
             sw.tick_temperature()

@@ -1,6 +1,6 @@
 """Multi-GPU strips over NCCL vs the single-world oracle (bit-exact for any strip count; SURVEY.md §8c pin 8): world tick, loose
-particles (migration between ranks + deposit rounds with the band proposals exchanged), temperature, and an explosion and an eraser
-stroke across the cuts.
+particles (migration between ranks + deposit rounds with the band proposals exchanged), temperature, an explosion and an eraser
+stroke across the cuts, and a horizontal camera scroll.
 Needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_strips_gpu.py -m gpu`."""
 import os
 import subprocess
@@ -43,6 +43,8 @@ def test_strips_match_oracle(oracle, table, tmp_path, nranks):
         if t == 2:
             O.explosion(ow, W // 2, H // 2 + 5, 40, tick=t, seed=1337)
             O.tool_erase_line(ow, 200, H // 4 - 30, 700, 3 * H // 4 + 20, 9)
+        if t == 4:
+            O.scroll(ow, -128, 0)
         before = ow.particles_count()
         ow.particles_tick()
         deposited += before - ow.particles_count()
