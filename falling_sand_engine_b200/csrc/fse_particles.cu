@@ -98,11 +98,26 @@ __device__ __forceinline__ unsigned int warp_append(unsigned int* counter, bool 
 
 // One thread per particle.  A particle that simply flew on (the bulk of a pool of millions) goes straight into the next tick's pool:
 // 80 bytes in, 80 bytes out.  Only the ones that hit something get a PState record for the deposit rounds.
-__global__ void particles_integrate_kernel(PArgs a) {
-    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+// The 80-byte AoS records move through shared memory: the CTA's 128 records are loaded as 640 consecutive 16-byte words (a thread
+// reading its own record straight from global memory touches 32 different sectors per warp instruction: the kernel was bound by L1
+// wavefronts, not by DRAM), a thread takes its record from there (stride 80 B = 20 banks: conflict-free for 128-bit accesses), and a
+// warp's survivors are packed back into the warp's slice and leave as one contiguous run to the slots its single atomic reserved.
+constexpr int PINT_THREADS = 128;
+constexpr int PREC_WORDS = (int)(sizeof(fse_particle) / 16);
+static_assert(sizeof(fse_particle) % 16 == 0, "particle records move as 16-byte words");
+__global__ void __launch_bounds__(PINT_THREADS) particles_integrate_kernel(PArgs a) {
+    __shared__ uint4 stage[PINT_THREADS * PREC_WORDS];
+    const unsigned int base = blockIdx.x * PINT_THREADS;
+    const unsigned int i = base + threadIdx.x;
     const bool valid = i < a.n;
+    {
+        const unsigned int nrec = a.n - base < (unsigned int)PINT_THREADS ? a.n - base : (unsigned int)PINT_THREADS;
+        const uint4* src = reinterpret_cast<const uint4*>(a.pbuf + base);
+        for (unsigned int q = threadIdx.x; q < nrec * PREC_WORDS; q += PINT_THREADS) stage[q] = src[q];
+    }
+    __syncthreads();
     fse_particle cur;
-    if (valid) cur = a.pbuf[i];
+    if (valid) cur = *reinterpret_cast<const fse_particle*>(&stage[threadIdx.x * PREC_WORDS]);
     PState s;
     s.status = 1;
     if (valid) {
@@ -158,8 +173,22 @@ __global__ void particles_integrate_kernel(PArgs a) {
     }
     const bool alive = valid && s.status == 0 && !(cur.y > (float)a.H);  // 2190: particles below the world are dropped
     const bool pend = valid && s.status >= 2;
-    const unsigned int o = warp_append(&a.counters[2], alive);
-    if (alive) a.out[o] = cur;
+    {   // survivors of this warp: packed into the warp's slice of the stage, then out as one contiguous run
+        const int lane = threadIdx.x & 31;
+        const unsigned am = __ballot_sync(0xffffffffu, alive);
+        const int k = __popc(am);
+        if (k) {
+            uint4* slice = &stage[(threadIdx.x & ~31) * PREC_WORDS];
+            __syncwarp();  // every lane has taken its record out of the slice
+            if (alive) *reinterpret_cast<fse_particle*>(&slice[__popc(am & ((1u << lane) - 1u)) * PREC_WORDS]) = cur;
+            unsigned int o = 0;
+            if (lane == 0) o = atomicAdd(&a.counters[2], (unsigned int)k);
+            o = __shfl_sync(0xffffffffu, o, 0);
+            __syncwarp();
+            uint4* dst = reinterpret_cast<uint4*>(a.out + o);
+            for (int q = lane; q < k * PREC_WORDS; q += 32) dst[q] = slice[q];
+        }
+    }
     const unsigned int q = warp_append(&a.counters[1], pend);  // the deposit rounds only visit these (order is irrelevant: ids decide)
     if (pend) {
         s.adv = cur;
