@@ -46,6 +46,7 @@ struct PArgs {
     long long* keys;
     unsigned long long* vals;
     unsigned int tmask;
+    int round;       // deposit round: part of every claim key, so the table is cleared once per call, not once per round
     uint8_t* awake;  // active-region flags (null = off)
     int acols, arows;
     fse_particle* out;     // the pool of the next tick: survivors are appended as soon as their fate is known (counters[2])
@@ -202,8 +203,18 @@ __device__ __forceinline__ unsigned int hash_cell(long long c) {
     return (unsigned int)(z >> 32);
 }
 
-// claim: lowest id per cell (open addressing, keys = global cell index)
-__device__ __forceinline__ void claim_cell(const PArgs& a, long long cand, unsigned long long id) {
+// claim: lowest id per cell (open addressing).  Keys are (global cell index, round): entries of earlier rounds never match and only
+// take up room — every proposed cell has exactly one winner, so all rounds together insert at most as many keys as particles were
+// pending at the start, which is what the table is sized for.
+__device__ __forceinline__ long long claim_key(const PArgs& a, long long cell) { return cell * 32 + a.round; }
+__device__ __forceinline__ unsigned int claim_slot(const PArgs& a, long long cell) {  // slot of a key that is in the table
+    const long long key = claim_key(a, cell);
+    unsigned int h = hash_cell(key) & a.tmask;
+    while (a.keys[h] != key) h = (h + 1) & a.tmask;
+    return h;
+}
+__device__ __forceinline__ void claim_cell(const PArgs& a, long long cell, unsigned long long id) {
+    const long long cand = claim_key(a, cell);
     unsigned int h = hash_cell(cand) & a.tmask;
     for (;;) {
         long long prev = (long long)atomicCAS((unsigned long long*)&a.keys[h], (unsigned long long)-1LL, (unsigned long long)cand);
@@ -233,10 +244,9 @@ __device__ __forceinline__ void deposit_cell(const PArgs& a, size_t g, const fse
 // the host by the very loop of the reference (spiral_table_init) so that a warp can test 32 consecutive steps at once.
 __constant__ signed char SPIRAL[1024][2];
 
-__global__ void particles_propose_kernel(PArgs a) {
-    const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void propose_one(const PArgs& a, unsigned int li) {
     const int lane = threadIdx.x & 31;
-    const bool live = li < a.n_list && !(a.prev_pending && *a.prev_pending == 0);
+    const bool live = li < a.n_list;
     PState* sp = live ? &a.st[li] : nullptr;
     int status = live ? sp->status : 0;
     if (status < 2) status = 0;
@@ -329,6 +339,14 @@ __global__ void particles_propose_kernel(PArgs a) {
         if (a.band_down && row >= a.own_hi - a.ghost && row < a.own_hi + a.ghost) a.band_down[atomicAdd(&a.band_cnt[1], 1u)] = pr;
     }
 }
+// Grid-stride over the pending list in whole warps (the spiral search is warp-cooperative).  Rounds after the first are launched with a
+// small grid: a round whose predecessor left nothing pending returns at once, and the few losers of a contested cell do not need a
+// thread per particle of the first round.
+__global__ void particles_propose_kernel(PArgs a) {
+    if (a.prev_pending && *a.prev_pending == 0) return;
+    const unsigned int up = (a.n_list + 31u) & ~31u;
+    for (unsigned int base = blockIdx.x * blockDim.x; base < up; base += gridDim.x * blockDim.x) propose_one(a, base + threadIdx.x);
+}
 
 // strips: the neighbours' band proposals join the claim table ...
 __global__ void particles_ext_claim_kernel(PArgs a, const PProp* ext, unsigned int n) {
@@ -340,22 +358,19 @@ __global__ void particles_ext_commit_kernel(PArgs a, const PProp* ext, unsigned 
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const PProp pr = ext[i];
-    unsigned int h = hash_cell(pr.cell) & a.tmask;
-    while (a.keys[h] != pr.cell) h = (h + 1) & a.tmask;
+    const unsigned int h = claim_slot(a, pr.cell);
     if (a.vals[h] != pr.id) return;
     const int r = (int)(pr.cell / a.W) - a.y_off;
     if (r < 0 || r >= a.Hl) return;
     deposit_cell(a, (size_t)r * a.W + (size_t)(pr.cell % a.W), pr.tile, pr.merge);
 }
 
-__global__ void particles_commit_kernel(PArgs a) {
-    const unsigned int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= a.n_list || (a.prev_pending && *a.prev_pending == 0)) return;
+__device__ __forceinline__ void commit_one(const PArgs& a, unsigned int li) {
+    if (li >= a.n_list) return;
     PState* sp = &a.st[li];
     if (sp->status < 2) return;
     const long long cand = sp->cand;
-    unsigned int h = hash_cell(cand) & a.tmask;
-    while (a.keys[h] != cand) h = (h + 1) & a.tmask;
+    const unsigned int h = claim_slot(a, cand);
     if (a.vals[h] != (unsigned long long)sp->adv.id) {
         atomicAdd(a.my_pending, 1u);  // still pending
         return;
@@ -373,6 +388,10 @@ __global__ void particles_commit_kernel(PArgs a) {
             }
     }
     sp->status = 1;
+}
+__global__ void particles_commit_kernel(PArgs a) {
+    if (a.prev_pending && *a.prev_pending == 0) return;
+    for (unsigned int li = blockIdx.x * blockDim.x + threadIdx.x; li < a.n_list; li += gridDim.x * blockDim.x) commit_one(a, li);
 }
 
 // After the rounds: a particle that deposited is gone; one that bounced flies on; one that is still pending is retried next tick from
@@ -597,6 +616,7 @@ static int particles_tick_strips(fse_world* w, const fse_rect* z) {
         CK(cudaMemsetAsync(w->claim_vals, 0xff, tsz * sizeof(unsigned long long), w->stream));
         CK(cudaMemsetAsync(b->d_cnt + 3, 0, 2 * sizeof(unsigned int), w->stream));
         CK(cudaMemsetAsync(b->d_cnt + 7, 0, sizeof(unsigned int), w->stream));
+        a.round = round;
         a.prev_pending = round ? round_cnt + round - 1 : nullptr;
         a.my_pending = round_cnt + round;
         if (pending) {
@@ -708,14 +728,16 @@ extern "C" FSE_API int fse_particles_tick(fse_world* w, const fse_rect* z) {
         a.keys = (long long*)w->claim_keys;
         a.vals = (unsigned long long*)w->claim_vals;
         a.tmask = (unsigned int)(tsz - 1);
+        CK(cudaMemsetAsync(w->claim_keys, 0xff, tsz * sizeof(long long), w->stream));  // once: the keys carry the round
+        CK(cudaMemsetAsync(w->claim_vals, 0xff, tsz * sizeof(unsigned long long), w->stream));
+        const int GS = GL < 592 ? GL : 592;  // rounds after the first: a few losers, or nothing at all
         for (int round = 0; round < FSE_PARTICLE_ROUNDS; round++) {
-            CK(cudaMemsetAsync(w->claim_keys, 0xff, tsz * sizeof(long long), w->stream));
-            CK(cudaMemsetAsync(w->claim_vals, 0xff, tsz * sizeof(unsigned long long), w->stream));
+            a.round = round;
             a.prev_pending = round ? round_cnt + round - 1 : nullptr;
             a.my_pending = round_cnt + round;
-            particles_propose_kernel<<<GL, B, 0, w->stream>>>(a);
+            particles_propose_kernel<<<round ? GS : GL, B, 0, w->stream>>>(a);
             CK(cudaGetLastError());
-            particles_commit_kernel<<<GL, B, 0, w->stream>>>(a);
+            particles_commit_kernel<<<round ? GS : GL, B, 0, w->stream>>>(a);
             CK(cudaGetLastError());
             w->ctx->launches += 2;
         }
