@@ -306,33 +306,11 @@ __global__ void __launch_bounds__(256) bodies_split_kernel(SplitArgs a) {
     extern __shared__ int split_smem[];
     int* L = split_smem;                          // labels: root = lowest pixel index of the component, -1 = empty
     int* box = split_smem + a.bw * a.bh;          // per piece: x0, y0, x1, y1, count, weld, root, tile offset (8 ints)
-    __shared__ int changed, n_roots, s_scan[256];
+    __shared__ int n_roots, s_scan[256];
     const int tid = threadIdx.x, n = a.bw * a.bh, w = a.bw, h = a.bh;
     for (int i = tid; i < n; i += 256) L[i] = a.tiles[i].mat != a.air ? i : -1;
     __syncthreads();
-    for (;;) {  // min-label propagation with pointer jumping
-        if (tid == 0) changed = 0;
-        __syncthreads();
-        for (int i = tid; i < n; i += 256) {
-            const int l = L[i];
-            if (l < 0) continue;
-            const int x = i % w, y = i / w;
-            int best = l;
-            if (x + 1 < w && L[i + 1] >= 0) best = min(best, L[i + 1]);
-            if (x > 0 && L[i - 1] >= 0) best = min(best, L[i - 1]);
-            if (y + 1 < h && L[i + w] >= 0) best = min(best, L[i + w]);
-            if (y > 0 && L[i - w] >= 0) best = min(best, L[i - w]);
-            best = min(best, L[best]);
-            if (best < l) {
-                L[i] = best;
-                atomicMin(&L[l], best);
-                changed = 1;
-            }
-        }
-        __syncthreads();
-        if (!changed) break;
-        __syncthreads();
-    }
+    L = ccl_relax(L, split_smem + a.bw * a.bh + 8 * a.cap_pieces, n, w, h);  // second label buffer behind the piece boxes
     // number the roots in row-major order: per-thread counts over contiguous ranges, scanned across the CTA
     const int per = (n + 255) / 256, lo = tid * per, hi = min(n, lo + per);
     int mine = 0;
@@ -790,10 +768,10 @@ extern "C" FSE_API int fse_bodies_split(fse_world* w, int32_t body, float angle,
     a.cap_tiles = cap_tiles;
     a.result = (int*)(base + o_res);
     CK(cudaMemsetAsync(a.result, 0, 16, w->stream));
-    const size_t smem = sizeof(int) * ((size_t)bw * bh + 8 * (size_t)cap_pieces);
+    const size_t smem = sizeof(int) * (2 * (size_t)bw * bh + 8 * (size_t)cap_pieces);  // labels, piece boxes, second label buffer (ccl_relax)
     static bool configured = false;
     if (!configured) {
-        CK(cudaFuncSetAttribute(bodies_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (SPLIT_MAX_PIXELS + 8 * SPLIT_MAX_PIECES))));
+        CK(cudaFuncSetAttribute(bodies_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * (2 * SPLIT_MAX_PIXELS + 8 * SPLIT_MAX_PIECES))));
         configured = true;
     }
     bodies_split_kernel<<<1, 256, smem, w->stream>>>(a);

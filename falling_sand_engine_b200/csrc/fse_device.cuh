@@ -151,4 +151,34 @@ struct TickFork {
     cudaEvent_t ev_fork, ev_join[3];
 };
 
+// 4-connected component labels (label = lowest cell index of the component, -1 = unset cell) by min-label propagation with pointer
+// jumping, Jacobi style: every sweep reads one buffer and writes the other, so no thread reads a label another thread is writing
+// (compute-sanitizer racecheck clean; an in-place sweep reaches the same fixed point through a benign race).  A holds the initial
+// labels (own index for set cells, -1 otherwise), B is scratch of the same size; returns the buffer with the result.  All threads of
+// the CTA must call.
+__device__ inline int* ccl_relax(int* A, int* B, int n, int w, int h) {
+    for (;;) {
+        int changed = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int l = A[i];
+            int best = l;
+            if (l >= 0) {
+                const int x = i % w, y = i / w;
+                if (x + 1 < w && A[i + 1] >= 0) best = min(best, A[i + 1]);
+                if (x > 0 && A[i - 1] >= 0) best = min(best, A[i - 1]);
+                if (y + 1 < h && A[i + w] >= 0) best = min(best, A[i + w]);
+                if (y > 0 && A[i - w] >= 0) best = min(best, A[i - w]);
+                best = min(best, A[best]);  // pointer jumping
+                changed |= best < l;
+            }
+            B[i] = best;
+        }
+        int* t = A;
+        A = B;
+        B = t;
+        if (!__syncthreads_or(changed)) break;  // the barrier also orders this sweep's writes before the next sweep's reads
+    }
+    return A;
+}
+
 }  // namespace fse

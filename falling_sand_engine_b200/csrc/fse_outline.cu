@@ -104,38 +104,42 @@ struct OutlineArgs {
 // finished labels go to HBM — and only when the caller asked for them; larger masks iterate on the global array.
 constexpr int CCL_SMEM_CELLS = 12288;
 __global__ void __launch_bounds__(256) ccl_kernel(OutlineArgs a) {
-    extern __shared__ int32_t ccl_smem[];
+    extern __shared__ int ccl_smem[];
     const int m = blockIdx.x;
     const uint8_t* d = a.masks + (size_t)m * a.w * a.h;
     const int n = a.w * a.h, w = a.w, h = a.h;
     const bool in_smem = n <= CCL_SMEM_CELLS;
     int32_t* G = a.labels + (size_t)m * a.w * a.h;
-    int32_t* L = in_smem ? ccl_smem : G;
-    __shared__ int changed;
+    int* L = in_smem ? reinterpret_cast<int*>(ccl_smem) : reinterpret_cast<int*>(G);
     for (int i = threadIdx.x; i < n; i += blockDim.x) L[i] = d[i] ? i : -1;
     __syncthreads();
-    for (;;) {
-        if (threadIdx.x == 0) changed = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            int l = L[i];
-            if (l < 0) continue;
-            const int x = i % w, y = i / w;
-            int best = l;
-            if (x + 1 < w && L[i + 1] >= 0) best = min(best, L[i + 1]);
-            if (x > 0 && L[i - 1] >= 0) best = min(best, L[i - 1]);
-            if (y + 1 < h && L[i + w] >= 0) best = min(best, L[i + w]);
-            if (y > 0 && L[i - w] >= 0) best = min(best, L[i - w]);
-            best = min(best, L[best]);  // pointer jumping
-            if (best < l) {
-                L[i] = best;
-                atomicMin(&L[l], best);  // pull the old representative along
-                changed = 1;
+    if (in_smem) {
+        L = ccl_relax(L, ccl_smem + n, n, w, h);  // two label buffers in shared memory, one read and one written per sweep
+    } else {
+        __shared__ int changed;
+        for (;;) {  // labels in global memory: in-place sweeps (monotone: every order of updates ends at the same labels)
+            if (threadIdx.x == 0) changed = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int l = L[i];
+                if (l < 0) continue;
+                const int x = i % w, y = i / w;
+                int best = l;
+                if (x + 1 < w && L[i + 1] >= 0) best = min(best, L[i + 1]);
+                if (x > 0 && L[i - 1] >= 0) best = min(best, L[i - 1]);
+                if (y + 1 < h && L[i + w] >= 0) best = min(best, L[i + w]);
+                if (y > 0 && L[i - w] >= 0) best = min(best, L[i - w]);
+                best = min(best, L[best]);  // pointer jumping
+                if (best < l) {
+                    L[i] = best;
+                    atomicMin(&L[l], best);  // pull the old representative along
+                    changed = 1;
+                }
             }
+            __syncthreads();
+            if (!changed) break;
+            __syncthreads();
         }
-        __syncthreads();
-        if (!changed) break;
-        __syncthreads();
     }
     __shared__ int cnt;
     if (threadIdx.x == 0) cnt = 0;
@@ -545,10 +549,10 @@ extern "C" FSE_API int fse_mask_outline(fse_world* w, const uint8_t* masks, int3
     CK(cudaMemsetAsync(base + o_cnt, 0, 256, w->stream));
     CK(cudaMemsetAsync(a.cell_kept, 0, total * 4, w->stream));
     a.want_labels = labels != nullptr;
-    const size_t ccl_smem_bytes = per <= (size_t)CCL_SMEM_CELLS ? per * sizeof(int32_t) : 0;
+    const size_t ccl_smem_bytes = per <= (size_t)CCL_SMEM_CELLS ? 2 * per * sizeof(int32_t) : 0;  // two label buffers (ccl_relax)
     static bool ccl_configured = false;
     if (!ccl_configured) {
-        CK(cudaFuncSetAttribute(ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CCL_SMEM_CELLS * (int)sizeof(int32_t)));
+        CK(cudaFuncSetAttribute(ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CCL_SMEM_CELLS * (int)sizeof(int32_t)));
         ccl_configured = true;
     }
     ccl_kernel<<<n_masks, 256, ccl_smem_bytes, w->stream>>>(a);

@@ -2,12 +2,13 @@
 //
 // Schedule.  The reference walks its std::vector<CellData*> in order and every deposit is seen by
 // the particles after it.  Here (1) every particle is integrated — target attraction, v += a, sub-stepped collision,
-// object pass-through state machine — against the grid as it was when the call started, one thread per particle;
-// (2) particles that hit something resolve their deposit in rounds: each proposes its start cell or the first free
-// cell of the reference's 32x32 square spiral (or a same-material liquid cell to merge into), an open-addressing
-// claim table keeps the LOWEST particle id per contested cell, winners write the cell, losers look again next round;
-// (3) survivors are compacted into a fresh buffer.  Everything is keyed on particle ids, so the result does not
-// depend on thread scheduling or on the order of the pool.
+// object pass-through state machine — against the grid as it was when the call started, one thread per particle; a
+// particle that simply flew on goes straight into the next tick's pool; (2) particles that hit something resolve their
+// deposit in rounds: each proposes its start cell or the first free cell of the reference's 32x32 square spiral (or a
+// same-material liquid cell to merge into; the whole warp searches one particle's spiral), an open-addressing claim
+// table keeps the LOWEST particle id per contested cell, winners write the cell, losers look again next round;
+// (3) what is left of them (bounced, or still pending: retried next tick from the old state) joins the new pool.
+// Everything is keyed on particle ids, so the result does not depend on thread scheduling or on the order of the pool.
 #include "fse_internal.hpp"
 
 namespace fse {

@@ -1,13 +1,15 @@
-// fse_tick_rows.cuh — "simultaneous rows" schedule of the chunk tick (DESIGN.md §3.1b); included by fse_tick.cu.
+// fse_tick_rows.cuh — "simultaneous rows" schedule of the chunk tick (DESIGN.md §3.1); included by fse_tick.cu.
 //
-// Same chunk colours, passes, bottom-up rows and pass lags as tick_chunk_kernel, but a row step of a pass is executed by
-// 64 threads (2 columns each) that first DECIDE from the state before the step and then COMMIT:
+// The reference's chunk colours, passes and bottom-up rows; a row step of a pass is executed by 128 threads (one per column) that
+// first DECIDE from the state before the step and then COMMIT:
 //   pass 1:  D | bar | C1 own column + publish horizontal flows/pokes | bar | C2 targets gather (left then right), hand
-//            back what no longer fits | bar | refunds + C3 area effects (FIRE, water-on-lava, pair interactions; serial,
-//            lowest source column first — rare)
+//            back what no longer fits | bar | refunds + C3 area effects (FIRE, water-on-lava, pair interactions; claims by
+//            the lowest source column — rare)
 //   pass 2:  D + destination claims (atomicMin of the source column) | bar | C winners move, liquid diff applied | bar | pokes
-//   pass 3:  D + claims | bar | C
+//   pass 3:  D + claims | C   (rows do not depend on each other: one warp per row)
 // The CPU oracle restates exactly this (oracle/rows_oracle.cpp, Schedule::ROWS); tests require bit-equality.
+// Kernels: tick_rows_kernel (all three passes pipelined in one CTA: small worlds), tick_pass_kernel<PASS, SKIP> + tick_pass3_kernel
+// (one kernel per pass: the default), classify_rows_kernel (settled-row skipping), tick_pass2_apply_kernel (pass 2 split).
 #pragma once
 #include <cstddef>
 
@@ -1302,19 +1304,23 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     uint32_t io_lazy = PASS == 1 ? 0xffffffffu : 0u, io_chg = 0;
     int kb = jumps ? next_act(0) : 0;
     bool first_segment = true;
+    // Phase of every slot's mbarrier as the compute warps have seen it (bit q = parity the next wait on slot q expects).  Each load arms
+    // its slot's barrier once and the compute warps wait for every loaded row exactly once, segment after segment, so the barriers are
+    // initialised once per pass and never invalidated.
+    static_assert(G::PF <= G::SL, "the drain of a segment must cover the rows that were loaded ahead");
+    uint32_t ph = 0;
+    auto wait_slot = [&](int q) {
+        mbar_wait(&S.bar[q], (ph >> q) & 1u);
+        ph ^= 1u << q;
+    };
 #pragma unroll 1
     for (;;) {
-        // ---- segment start: slots free, barriers fresh, scratch flags reset, window of row kb loaded ----
+        // ---- segment start: slots free, scratch flags reset, window of row kb loaded ----
         if (!first_segment) {
             if (io_store) bulk_wait_read<0>();  // the previous segment's stores have left shared memory
             __syncthreads();
-            if (tid == 0) {
-                for (int q = 0; q < G::RN; q++) {
-                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.bar[q])) : "memory");
-                    mbar_init(&S.bar[q], 1);
-                }
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            }
+            // (the mbarriers carry on: every row a segment loads is waited for by the compute warps before the segment ends — the drain
+            // lasts SL >= PF steps — so each slot's barrier has completed as many phases as the warps have counted in `ph`)
             if (!io) {  // both parities of the per-row scratch flags (a step only resets the next row's)
                 if (PASS == 1) {
                     Scratch1& R = reinterpret_cast<Scratch1&>(S.rs);
@@ -1335,12 +1341,12 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
         first_segment = false;
         const int k0 = kb + G::KMIN;  // lowest row of the segment's window
         auto slot_of = [&](int k) -> int { return (k - k0) % G::RN; };
-        auto par_of = [&](int k) -> uint32_t { return (uint32_t)(((k - k0) / G::RN) & 1); };
         if (io_load) {
 #pragma unroll 1
             for (int k = k0; k < kb + G::UP + G::PF && k <= G::LAST; k++) pass_row_load<PASS>(S, pio, lane, k, cy, slot_of(k), kb);
         }
-        for (int k = k0; k < kb + G::UP && k <= G::LAST; k++) mbar_wait(&S.bar[slot_of(k)], par_of(k));
+        if (!io)
+            for (int k = k0; k < kb + G::UP && k <= G::LAST; k++) wait_slot(slot_of(k));
 
         int stop_row = kb;     // highest row that may still have to run
         bool ending = false;   // past the segment's last row: drain the stores, load nothing
@@ -1349,14 +1355,13 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
         auto inc = [](int q) -> int { return q + 1 == G::RN ? 0 : q + 1; };
         int qs = (-G::KMIN) % G::RN;                                    // slot of row st
         int qw = (-G::KMIN + G::UP) % G::RN;                            // slot of row st + UP (the row that becomes live)
-        uint32_t pw = (uint32_t)(((-G::KMIN + G::UP) / G::RN) & 1);     // ... and its mbarrier parity
         int qst = ((-G::KMIN - G::SL) % G::RN + G::RN) % G::RN;         // slot of row st - SL (stored this step)
         int ql = (-G::KMIN + G::UP + G::PF) % G::RN;                    // slot of row st + UP + PF (loaded this step)
 #pragma unroll 1
         for (int st = kb;; st++) {
             const int kw = st + G::UP;
             // the IO warp never reads the row that is about to become live: only the compute warps wait for it
-            if (!io && kw <= G::LAST && (!ending || kw < seg_end + G::UP + G::PF)) mbar_wait(&S.bar[qw], pw);
+            if (!io && kw <= G::LAST && (!ending || kw < seg_end + G::UP + G::PF)) wait_slot(qw);
             fence_proxy_async();
             __syncthreads();
             bool run = false;
@@ -1495,7 +1500,6 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
             qst = inc(qst);
             ql = inc(ql);
             qw = inc(qw);
-            if (qw == 0) pw ^= 1u;
         }
         // rows at and above the segment's end: the next classified-active one starts the next segment
         const int nxt = jumps ? next_act(seg_end) : CHUNK;
