@@ -301,15 +301,23 @@ class World:
         return out
 
     # -- fracture outlines (world.cpp:288-720, physics_math.cpp:1766-1965) and physicsCheck flood (world.cpp:3330) ------
-    def physics_check(self, x, y, cap_tiles=1 << 20):
+    def physics_check(self, x, y, cap_tiles=None):
         """world::physicsCheck (world.cpp:3330-3411): returns (count, action, (x, y, w, h), tiles or None) — action 0 nothing, 1 the
-        1..10-cell crumb was deleted, 2 the 11..1000-cell component was cut out into `tiles` (h x w fse_cell array of the new body)."""
+        1..10-cell crumb was deleted, 2 the 11..1000-cell component was cut out into `tiles` (h x w fse_cell array of the new body).
+        cap_tiles: capacity of the tile buffer (default: 65536, retried with the component's box when that is too small — the call
+        changes nothing when the buffer does not fit)."""
         class Res(C.Structure):
             _fields_ = [(n, C.c_int32) for n in ("count", "action", "x", "y", "w", "h")]
         res = Res()
-        tiles = np.zeros(cap_tiles, dtype=T.CELL_DTYPE)
         self.L.fse_physics_check.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
-        _ck(self.L.fse_physics_check(self.h, x, y, C.byref(res), tiles.ctypes.data, cap_tiles))
+        cap = cap_tiles or (1 << 16)
+        tiles = np.zeros(cap, dtype=T.CELL_DTYPE)
+        rc = self.L.fse_physics_check(self.h, x, y, C.byref(res), tiles.ctypes.data, cap)
+        if rc != 0 and cap_tiles is None and 10 < res.count <= 1000 and res.w * res.h > cap:
+            cap = res.w * res.h
+            tiles = np.zeros(cap, dtype=T.CELL_DTYPE)
+            rc = self.L.fse_physics_check(self.h, x, y, C.byref(res), tiles.ctypes.data, cap)
+        _ck(rc)
         box = (res.x, res.y, res.w, res.h)
         return res.count, res.action, box, (tiles[:res.w * res.h].reshape(res.h, res.w).copy() if res.action == 2 else None)
 

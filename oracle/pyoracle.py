@@ -233,14 +233,20 @@ def render_dirty(world, planes, with_flow_count=False):
     return int(had[0]), int(had[1]), moving
 
 
-def physics_check(world, x, y, cap_tiles=1 << 20):
-    """world::physicsCheck (world.cpp:3330-3411).  Returns (count, action, (x, y, w, h), tiles or None)."""
+def physics_check(world, x, y, cap_tiles=None):
+    """world::physicsCheck (world.cpp:3330-3411).  Returns (count, action, (x, y, w, h), tiles or None).  cap_tiles: capacity of the
+    tile buffer (default 65536, retried with the component's box when that is too small; nothing changes when it does not fit)."""
     res = np.zeros(6, dtype=np.int32)
-    tiles = np.zeros(cap_tiles, dtype=T.CELL_DTYPE)
+    cap = cap_tiles or (1 << 16)
+    tiles = np.zeros(cap, dtype=T.CELL_DTYPE)
     lib().fseo_physics_check.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-    rc = lib().fseo_physics_check(world.h, x, y, res.ctypes.data, tiles.ctypes.data, cap_tiles)
+    rc = lib().fseo_physics_check(world.h, x, y, res.ctypes.data, tiles.ctypes.data, cap)
+    if rc != 0 and cap_tiles is None:
+        cap = int(res[4]) * int(res[5])
+        tiles = np.zeros(cap, dtype=T.CELL_DTYPE)
+        rc = lib().fseo_physics_check(world.h, x, y, res.ctypes.data, tiles.ctypes.data, cap)
     if rc != 0:
-        raise ValueError(f"physics_check: the {res[4]} x {res[5]} box does not fit {cap_tiles} tiles")
+        raise ValueError(f"physics_check: the {res[4]} x {res[5]} box does not fit {cap} tiles")
     box = tuple(int(v) for v in res[2:6])
     return int(res[0]), int(res[1]), box, (tiles[:box[2] * box[3]].reshape(box[3], box[2]).copy() if res[1] == 2 else None)
 
