@@ -1214,6 +1214,9 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
     // warps 0-3 compute; warp 4 stores rows back; the last warp loads rows (the same warp in a 160-thread CTA)
     const bool io = warp >= 4, io_store = warp == 4, io_load = warp == (int)(blockDim.x >> 5) - 1;
     const long long t_begin = (PASS == 1 && cost_slot) ? clock64() : 0;
+#ifdef FSE_ROLE_CYCLES
+    const long long t_begin_dbg = clock64();
+#endif
     const DevTables* T = P.tabs;
     // settled-row skipping (see classify_rows_kernel): the rows this pass must run; a chunk without any is done
     uint32_t* const gmask = (SKIP && P.rowmask) ? P.rowmask + (size_t)mask_idx * ROWMASK_WORDS : nullptr;
@@ -1507,6 +1510,14 @@ __device__ __forceinline__ void run_pass(const TickParams& P, int cx, int cy, in
         kb = nxt;
     }
     if (PASS == 1 && cost_slot && tid == 0) *cost_slot = (unsigned int)(clock64() - t_begin);
+#ifdef FSE_ROLE_CYCLES
+    if (PASS == 1 && P.dbg && tid == 0) {  // scripts/role_cycles.py: words 32..41 = pass-1 phase cycles and row counts, 30 = chunks, 31 = pass cycles
+        const Scratch1& R1 = reinterpret_cast<const Scratch1&>(S.rs);
+        for (int q = 0; q < 10; q++) atomicAdd(&P.dbg[32 + q], (unsigned long long)R1.dbg_phase[q]);
+        atomicAdd(&P.dbg[30], 1ULL);
+        atomicAdd(&P.dbg[31], (unsigned long long)(clock64() - t_begin_dbg));
+    }
+#endif
     if (io_store && P.chunk_state) {
         const bool inert = __all_sync(0xffffffffu, io_inert);
         const unsigned int st = (io_modified ? 1u : 0u) | ((PASS == 2 && !inert) ? 2u : 0u);
