@@ -12,6 +12,7 @@
 // bodies whose footprint box overlaps its own to finish — bodies that do not overlap commute, overlapping ones keep the
 // reference's body order — and then runs the rounds of its own pixels between block barriers, with the claim map of its
 // footprint box in shared memory (boxes up to 64x64 cells; larger bodies use a claim plane in global memory).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -47,12 +48,17 @@ struct BodyArgs {
     int4* aabb;              // per body: footprint box (x0, y0, x1, y1), inclusive
     unsigned int* done;      // per body: 1 once all its pixels have acted
     unsigned int* ticket;    // [0] next body, [1] most rounds any body needed
+    // strip worlds: the planes hold global rows [y_off, y_off + H); transforms stay global (the float -> int truncation must see the same
+    // sums as on one world) and the row offset is taken off the integer result.  exec (null on one world): the rank that runs body b
+    int y_off;
+    const int* exec;
+    int rank;
 };
 
 __device__ __forceinline__ void world_pos(const BodyArgs& a, int b, int tx, int ty, int& wx, int& wy) {
     const float4 t = a.xf[b];  // x, y, s, c
     wx = (int)(tx * t.w - (ty + 1) * t.z + t.x);  // game.cpp:1763
-    wy = (int)(tx * t.z + (ty + 1) * t.w + t.y);  // game.cpp:1764
+    wy = (int)(tx * t.z + (ty + 1) * t.w + t.y) - a.y_off;  // game.cpp:1764
 }
 __constant__ int c_dirs[5][2] = {{0, 0}, {1, 0}, {-1, 0}, {0, 1}, {0, -1}};  // game.cpp:1766
 
@@ -72,13 +78,13 @@ __global__ void bodies_aabb_kernel(BodyArgs a) {
     const float lim = 1.0e9f;
     x0 = fmaxf(fminf(x0, lim), -lim); x1 = fmaxf(fminf(x1, lim), -lim);
     y0 = fmaxf(fminf(y0, lim), -lim); y1 = fmaxf(fminf(y1, lim), -lim);
-    a.aabb[b] = make_int4((int)floorf(x0) - 3, (int)floorf(y0) - 3, (int)ceilf(x1) + 3, (int)ceilf(y1) + 3);
+    a.aabb[b] = make_int4((int)floorf(x0) - 3, (int)floorf(y0) - 3 - a.y_off, (int)ceilf(x1) + 3, (int)ceilf(y1) + 3 - a.y_off);
     a.done[b] = 0;
 }
 
 __device__ __forceinline__ void wake3x3(const BodyArgs& a, int x, int y) {
     if (!a.awake) return;
-    const int ci = x / CHUNK, cj = y / CHUNK;
+    const int ci = x / CHUNK, cj = (y + a.y_off) / CHUNK;
     for (int dj = -1; dj <= 1; dj++)
         for (int di = -1; di <= 1; di++) {
             const int ni = ci + di, nj = cj + dj;
@@ -140,7 +146,7 @@ __device__ __noinline__ void body_pixel_act(const BodyArgs& a, int b, int tx, in
                     memset(&p, 0, sizeof p);
                     p.tile = read_cell(a, g);
                     p.x = (float)x;
-                    p.y = (float)(y - 3);
+                    p.y = (float)(y + a.y_off - 3);  // particles carry global coordinates
                     const int pix = tx + ty * a.bw[b];
                     const uint32_t cb = rng_cell(a.rkey, b, pix);
                     p.vx = (float)(((int)(rng_draw(cb, S_BRIDGE_VX) % 10) - 5) / 10.0f);
@@ -225,7 +231,7 @@ __device__ __noinline__ void body_pixel_act_fast(const BodyArgs& a, int b, int t
                     memset(&p, 0, sizeof p);
                     p.tile = read_cell(a, g);
                     p.x = (float)x;
-                    p.y = (float)(y - 3);
+                    p.y = (float)(y + a.y_off - 3);  // particles carry global coordinates
                     const int pix = tx + ty * a.bw[b];
                     const uint32_t cb = rng_cell(a.rkey, b, pix);
                     p.vx = (float)(((int)(rng_draw(cb, S_BRIDGE_VX) % 10) - 5) / 10.0f);
@@ -413,6 +419,10 @@ __global__ void __launch_bounds__(BODY_TB, 8) bodies_body_kernel(BodyArgs a) {
     __syncthreads();
     const int b = s_b;
     if (b >= a.n_bodies) return;
+    if (a.exec && a.exec[b] != a.rank) {  // strips: another rank runs this body (and every body it could share cells with)
+        if (tid == 0) atomicExch(a.done + b, 1u);
+        return;
+    }
 
     const int4 box = a.aabb[b];
     const int bwid = a.bw[b], bhei = a.bh[b], npix = bwid * bhei, off = a.off[b];
@@ -465,7 +475,7 @@ __global__ void __launch_bounds__(BODY_TB, 8) bodies_body_kernel(BodyArgs a) {
             if (o < npix) {
                 const int tx = o / bhei, ty = o % bhei;
                 const int wx = (int)(tx * t.w - (ty + 1) * t.z + t.x);  // game.cpp:1763
-                const int wy = (int)(tx * t.z + (ty + 1) * t.w + t.y);  // game.cpp:1764
+                const int wy = (int)(tx * t.z + (ty + 1) * t.w + t.y) - a.y_off;  // game.cpp:1764
                 px[k] = (uint32_t)(wx - box.x) | ((uint32_t)(wy - box.y) << 8) | ((uint32_t)a.pending[off + o] << 16);
                 s_pos[o] = px[k];
                 s_cnt[o] = 0;
@@ -580,6 +590,56 @@ __global__ void __launch_bounds__(BODY_TB, 8) bodies_body_kernel(BodyArgs a) {
     }
 }
 
+
+// ---- multi-rank strips ---------------------------------------------------------------------------------------------------------------
+// Every rank makes the call with the same transforms.  A body is run by ONE rank — the owner of the middle row of its footprint box —
+// together with every body whose box overlaps its own (transitively: overlapping bodies keep the reference's body order, so they must
+// meet on one rank; bodies that do not overlap commute).  The executing rank holds the whole box (own rows + GHOST rows, refreshed
+// before the call); afterwards the part of the box that lies in a neighbour's rows travels there as a rectangle of cells, so both
+// ranks agree on every row they share again.  Feedback is summed over the ranks (the others contribute zeros), and after an erase the
+// tile arrays — replicated on every rank — are brought back in step the same way.
+struct RectArgs {
+    Planes p;
+    int W;
+    const int4* rects;     // x0, y0 (local rows), w, h
+    const int* cell_off;   // first cell of each rectangle in the message
+    unsigned char* stage;  // per rectangle: its cells plane after plane (17 bytes per cell)
+    int pack;
+};
+__global__ void bodies_rect_copy_kernel(RectArgs a) {
+    const int4 r = a.rects[blockIdx.x];
+    const int n = r.z * r.w;
+    unsigned char* st = a.stage + (size_t)a.cell_off[blockIdx.x] * 17;
+    unsigned char* pl[7] = {(unsigned char*)a.p.mat, (unsigned char*)a.p.flg, (unsigned char*)a.p.stl, (unsigned char*)a.p.tmp,
+                            (unsigned char*)a.p.col, (unsigned char*)a.p.fl, (unsigned char*)a.p.fd};
+    const int es[7] = {1, 1, 1, 2, 4, 4, 4};
+    size_t so = 0;
+    for (int q = 0; q < 7; q++) {
+        for (int i = threadIdx.x; i < n * es[q]; i += blockDim.x) {  // byte-wise: the message is not aligned for the wider planes
+            const int c = i / es[q], bq = i % es[q];
+            const size_t g = ((size_t)(r.y + c / r.z) * a.W + (size_t)(r.x + c % r.z)) * es[q] + bq;
+            if (a.pack) st[so + i] = pl[q][g];
+            else pl[q][g] = st[so + i];
+        }
+        so += (size_t)n * es[q];
+    }
+}
+// x[i] = word i of the tiles if this rank ran the body the word belongs to, 0 otherwise (the sum over the ranks is the runner's copy)
+__global__ void bodies_tiles_select_kernel(const uint32_t* tiles, uint32_t* x, const int* off, const int* exec, int n_bodies, int rank, int n_pixels) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    constexpr int CW = (int)(sizeof(fse_cell) / 4);  // words per body pixel
+    static_assert(sizeof(fse_cell) % 4 == 0, "body tiles are exchanged as 32-bit words");
+    if (i >= (size_t)n_pixels * CW) return;
+    const int pix = (int)(i / CW);
+    int lo = 0, hi = n_bodies;  // body of the pixel: off[lo] <= pix < off[lo + 1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= pix) lo = mid;
+        else hi = mid;
+    }
+    x[i] = exec[lo] == rank ? tiles[i] : 0u;
+}
+
 }  // namespace fse
 
 using namespace fse;
@@ -602,9 +662,20 @@ struct fse_bodies {
     int4* d_aabb = nullptr;
     unsigned int* d_done = nullptr;  // [n] done flags, then the ticket and the round maximum
     bool big = false;                // some body's footprint box may exceed the shared-memory claim map: claim plane in global memory
+    // multi-rank strips
+    int* d_exec = nullptr;           // [n] rank that runs each body in this call
+    uint32_t* d_tiles_x = nullptr;   // n_pixels fse_cell (as words): the executed bodies' tiles, summed over the ranks after an erase
+    int4* d_rects = nullptr;         // rectangles pushed to / taken from the neighbours (x0, y0 local, w, h) + their cell offsets
+    int* d_rect_off = nullptr;
+    size_t rects_cap = 0;
+    unsigned char* push_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // up send, up recv, down send, down recv
+    size_t push_stage_bytes[4] = {0, 0, 0, 0};
     void release() {
         cudaFree(d_off); cudaFree(d_bw); cudaFree(d_bh); cudaFree(d_tiles); cudaFree(d_xf); cudaFree(d_pending); cudaFree(d_claim);
         cudaFree(d_feedback); cudaFree(d_aabb); cudaFree(d_done);
+        cudaFree(d_exec); cudaFree(d_tiles_x); cudaFree(d_rects); cudaFree(d_rect_off);
+        d_exec = nullptr; d_tiles_x = nullptr; d_rects = nullptr; d_rect_off = nullptr; rects_cap = 0;
+        for (int i = 0; i < 4; i++) { cudaFree(push_stage[i]); push_stage[i] = nullptr; push_stage_bytes[i] = 0; }
         d_off = d_bw = d_bh = nullptr; d_tiles = nullptr; d_xf = nullptr; d_pending = nullptr; d_claim = nullptr; d_feedback = nullptr;
         d_aabb = nullptr; d_done = nullptr;
     }
@@ -620,7 +691,7 @@ void fse_bodies_free(fse_world* w) {
 
 extern "C" FSE_API int fse_bodies_upload(fse_world* w, const fse_body_desc* bodies, int32_t n) {
     if (!w || (!bodies && n > 0) || n < 0) return fail(FSE_EINVAL, "fse_bodies_upload: bad argument");
-    if (w->strip && w->ctx->nranks > 1) return fail(FSE_ESTATE, "fse_bodies_upload: bodies on multi-rank strip worlds are not implemented");
+    // multi-rank strips: every rank uploads every body (the tile arrays are replicated; fse_bodies_erase brings them back in step)
     CK(cudaSetDevice(w->ctx->device));
     if (!w->bodies) w->bodies = new fse_bodies();
     fse_bodies* B = w->bodies;
@@ -667,6 +738,99 @@ extern "C" FSE_API int fse_bodies_upload(fse_world* w, const fse_body_desc* bodi
     return FSE_OK;
 }
 
+
+// ---- multi-rank strips: who runs which body, and which rectangles travel afterwards (host; every rank computes the same plan) -------
+static const int BGHOST = 32;  // ghost rows of a strip (fse_strip_create)
+static void strip_rows_of(int Hglobal, int rank, int nranks, int* own_lo, int* own_hi, int* held_lo, int* held_hi) {
+    const int nz = (Hglobal - 2 * CHUNK) / CHUNK;
+    const int j0 = (int)((int64_t)nz * rank / nranks), j1 = (int)((int64_t)nz * (rank + 1) / nranks);
+    *own_lo = rank == 0 ? 0 : CHUNK + CHUNK * j0;
+    *own_hi = rank == nranks - 1 ? Hglobal : CHUNK + CHUNK * j1;
+    *held_lo = *own_lo - BGHOST < 0 ? 0 : *own_lo - BGHOST;
+    *held_hi = *own_hi + BGHOST > Hglobal ? Hglobal : *own_hi + BGHOST;
+}
+struct StripPlan {
+    std::vector<int> exec;
+    std::vector<int4> rect[4];  // up send, up recv, down send, down recv (x0, y0 in local rows, w, h)
+};
+static int plan_strip_bodies(fse_world* w, const fse_bodies* B, const fse_xform* xf, int n, StripPlan& P, const char* who) {
+    const int nranks = w->ctx->nranks, me = w->ctx->rank, Hg = w->Hglobal, W = w->W;
+    std::vector<int4> box(n);
+    for (int b = 0; b < n; b++) {  // the box of bodies_aabb_kernel, in global rows
+        const float sn = std::sin(xf[b].angle), cs = std::cos(xf[b].angle);
+        float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f;
+        for (int q = 0; q < 4; q++) {
+            const float tx = (q & 1) ? (float)(B->bw[b] - 1) : 0.0f, ty1 = (q & 2) ? (float)B->bh[b] : 1.0f;
+            const float fx = tx * cs - ty1 * sn + xf[b].x, fy = tx * sn + ty1 * cs + xf[b].y;
+            x0 = std::fmin(x0, fx); x1 = std::fmax(x1, fx);
+            y0 = std::fmin(y0, fy); y1 = std::fmax(y1, fy);
+        }
+        const float lim = 1.0e9f;
+        x0 = std::fmax(std::fmin(x0, lim), -lim); x1 = std::fmax(std::fmin(x1, lim), -lim);
+        y0 = std::fmax(std::fmin(y0, lim), -lim); y1 = std::fmax(std::fmin(y1, lim), -lim);
+        box[b] = make_int4((int)std::floor(x0) - 3, (int)std::floor(y0) - 3, (int)std::ceil(x1) + 3, (int)std::ceil(y1) + 3);
+    }
+    // groups of bodies whose boxes overlap (transitively); the root of a group is its lowest body index
+    std::vector<int> parent(n);
+    for (int i = 0; i < n; i++) parent[i] = i;
+    auto find = [&](int i) {
+        while (parent[i] != i) i = parent[i] = parent[parent[i]];
+        return i;
+    };
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a_, int b_) { return box[a_].y < box[b_].y; });
+    std::vector<int> active;
+    for (int oi = 0; oi < n; oi++) {
+        const int i = order[oi];
+        size_t keep = 0;
+        for (size_t k = 0; k < active.size(); k++) {
+            const int j = active[k];
+            if (box[j].w < box[i].y) continue;  // ends above: never overlaps anything that starts later
+            active[keep++] = j;
+            if (box[j].x <= box[i].z && box[i].x <= box[j].z) {
+                const int ri = find(i), rj = find(j);
+                if (ri != rj) parent[ri > rj ? ri : rj] = ri > rj ? rj : ri;
+            }
+        }
+        active.resize(keep);
+        active.push_back(i);
+    }
+    std::vector<int> olo(nranks), ohi(nranks), hlo(nranks), hhi(nranks);
+    for (int r = 0; r < nranks; r++) strip_rows_of(Hg, r, nranks, &olo[r], &ohi[r], &hlo[r], &hhi[r]);
+    P.exec.assign(n, 0);
+    for (int b = 0; b < n; b++) {
+        const int root = find(b);
+        int mid = (box[root].y + box[root].w) / 2;
+        mid = mid < 0 ? 0 : (mid >= Hg ? Hg - 1 : mid);
+        int e = 0;
+        while (e + 1 < nranks && mid >= ohi[e]) e++;
+        P.exec[b] = e;
+        const int ya = box[b].y < 0 ? 0 : box[b].y, yb = box[b].w >= Hg ? Hg - 1 : box[b].w;
+        if (ya <= yb && (ya < hlo[e] || yb >= hhi[e]))
+            return fail(FSE_ESTATE, "%s: body %d (rows %d..%d, with the bodies it overlaps) does not fit the rows rank %d holds (%d..%d): on multi-rank strips a group of "
+                        "overlapping bodies must lie within %d rows of one strip", who, b, ya, yb, e, hlo[e], hhi[e] - 1, BGHOST);
+    }
+    for (int q = 0; q < 4; q++) P.rect[q].clear();
+    for (int b = 0; b < n; b++) {
+        const int e = P.exec[b];
+        const int xa = box[b].x < 0 ? 0 : box[b].x, xb = box[b].z >= W ? W - 1 : box[b].z;
+        if (xa > xb) continue;
+        for (int side = 0; side < 2; side++) {  // 0: the neighbour above the runner, 1: the one below
+            const int nb = side == 0 ? e - 1 : e + 1;
+            if (nb < 0 || nb >= nranks || (me != e && me != nb)) continue;
+            int ya = box[b].y < 0 ? 0 : box[b].y, yb = box[b].w >= Hg ? Hg - 1 : box[b].w;
+            if (ya < hlo[nb]) ya = hlo[nb];
+            if (yb >= hhi[nb]) yb = hhi[nb] - 1;
+            if (ya > yb) continue;
+            const int4 r = make_int4(xa, ya - w->y_off, xb - xa + 1, yb - ya + 1);
+            if (me == e) P.rect[side == 0 ? 0 : 2].push_back(r);  // I ran it: send towards that neighbour
+            else P.rect[side == 0 ? 3 : 1].push_back(r);          // my neighbour ran it: the runner is below me (side 0) or above me (side 1)
+        }
+    }
+    return FSE_OK;
+}
+
 template <bool ERASE>
 static int run_bridge(fse_world* w, const fse_xform* xf, int32_t n, uint32_t tick, uint32_t seed, fse_body_feedback* out) {
     fse_bodies* B = w->bodies;
@@ -675,6 +839,15 @@ static int run_bridge(fse_world* w, const fse_xform* xf, int32_t n, uint32_t tic
     CK(cudaSetDevice(w->ctx->device));
     if (!ERASE)  // every body pixel may displace a cell into the particle pool
         if (int r = particles_headroom(w, B->n_pixels, false)) return r;
+    const bool multi = w->strip && w->ctx->nranks > 1;
+    StripPlan plan;
+    if (multi) {
+        // the runner of a body works on its ghost rows as well: they must be the owner's rows first
+        if (int r = strip_refresh(w, w->stream, BGHOST)) return r;
+        if (int r = plan_strip_bodies(w, B, xf, n, plan, ERASE ? "fse_bodies_erase" : "fse_bodies_raster")) return r;
+        if (!B->d_exec) CK(cudaMalloc(&B->d_exec, sizeof(int) * n));
+        CK(cudaMemcpyAsync(B->d_exec, plan.exec.data(), sizeof(int) * n, cudaMemcpyHostToDevice, w->stream));
+    }
     std::vector<float4> h(n);
     for (int i = 0; i < n; i++) h[i] = make_float4(xf[i].x, xf[i].y, std::sin(xf[i].angle), std::cos(xf[i].angle));  // game.cpp:1763-1764 on the host's libm
     CK(cudaMemcpyAsync(B->d_xf, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, w->stream));
@@ -688,10 +861,81 @@ static int run_bridge(fse_world* w, const fse_xform* xf, int32_t n, uint32_t tic
     a.awake = w->active_on ? w->d_awake : nullptr; a.acols = w->acols; a.arows = w->arows;
     a.n_pixels = B->n_pixels;
     a.aabb = B->d_aabb; a.done = B->d_done; a.ticket = B->d_done + n;
+    a.y_off = w->y_off; a.exec = multi ? B->d_exec : nullptr; a.rank = w->ctx->rank;
     bodies_aabb_kernel<<<(n + 127) / 128, 128, 0, w->stream>>>(a);
     bodies_body_kernel<ERASE><<<n, BODY_TB, 0, w->stream>>>(a);
     CK(cudaGetLastError());
     w->ctx->launches += 2;
+    if (multi) {
+        // the boxes of the bodies this rank ran, as far as they lie in a neighbour's rows, travel there (and the neighbours' come here)
+        size_t cells[4] = {0, 0, 0, 0}, total_rects = 0;
+        for (int q = 0; q < 4; q++) {
+            for (const int4& r : plan.rect[q]) cells[q] += (size_t)r.z * r.w;
+            total_rects += plan.rect[q].size();
+        }
+        if (total_rects > B->rects_cap) {
+            CK(cudaStreamSynchronize(w->stream));
+            cudaFree(B->d_rects); cudaFree(B->d_rect_off);
+            B->d_rects = nullptr; B->d_rect_off = nullptr; B->rects_cap = 0;
+            CK(cudaMalloc(&B->d_rects, sizeof(int4) * (total_rects + 64)));
+            CK(cudaMalloc(&B->d_rect_off, sizeof(int) * (total_rects + 64)));
+            B->rects_cap = total_rects + 64;
+        }
+        std::vector<int4> all_r;
+        std::vector<int> all_o;
+        size_t first[4];
+        for (int q = 0; q < 4; q++) {
+            first[q] = all_r.size();
+            int o = 0;
+            for (const int4& r : plan.rect[q]) {
+                all_r.push_back(r);
+                all_o.push_back(o);
+                o += r.z * r.w;
+            }
+            if (cells[q] * 17 > B->push_stage_bytes[q]) {
+                CK(cudaStreamSynchronize(w->stream));
+                cudaFree(B->push_stage[q]);
+                B->push_stage[q] = nullptr; B->push_stage_bytes[q] = 0;
+                CK(cudaMalloc(&B->push_stage[q], cells[q] * 17 + 4096));
+                B->push_stage_bytes[q] = cells[q] * 17 + 4096;
+            }
+        }
+        if (total_rects) {
+            CK(cudaMemcpyAsync(B->d_rects, all_r.data(), sizeof(int4) * total_rects, cudaMemcpyHostToDevice, w->stream));
+            CK(cudaMemcpyAsync(B->d_rect_off, all_o.data(), sizeof(int) * total_rects, cudaMemcpyHostToDevice, w->stream));
+        }
+        RectArgs ra;
+        ra.p = w->p; ra.W = w->W;
+        for (int q = 0; q < 4; q += 2)  // pack what goes up (0) and down (2)
+            if (!plan.rect[q].empty()) {
+                ra.rects = B->d_rects + first[q]; ra.cell_off = B->d_rect_off + first[q]; ra.stage = B->push_stage[q]; ra.pack = 1;
+                bodies_rect_copy_kernel<<<(unsigned)plan.rect[q].size(), 128, 0, w->stream>>>(ra);
+                w->ctx->launches += 1;
+            }
+        CK(cudaGetLastError());
+        if (int r = strip_sendrecv(w, B->push_stage[0], cells[0] * 17, B->push_stage[1], cells[1] * 17, B->push_stage[2], cells[2] * 17, B->push_stage[3],
+                                   cells[3] * 17, w->stream))
+            return r;
+        for (int q = 1; q < 4; q += 2)  // unpack what came from above (1) and from below (3)
+            if (!plan.rect[q].empty()) {
+                ra.rects = B->d_rects + first[q]; ra.cell_off = B->d_rect_off + first[q]; ra.stage = B->push_stage[q]; ra.pack = 0;
+                bodies_rect_copy_kernel<<<(unsigned)plan.rect[q].size(), 128, 0, w->stream>>>(ra);
+                w->ctx->launches += 1;
+            }
+        CK(cudaGetLastError());
+        // feedback: the runner's numbers on every rank
+        if (int r = strip_allreduce_u32(w, (unsigned int*)B->d_feedback, (size_t)4 * n, w->stream)) return r;
+        if (ERASE) {  // the erase rewrote the tiles of the bodies this rank ran: every rank gets every runner's copy
+            if (!B->d_tiles_x) CK(cudaMalloc(&B->d_tiles_x, sizeof(fse_cell) * (size_t)B->n_pixels));
+            const size_t words = (size_t)B->n_pixels * (sizeof(fse_cell) / 4);
+            bodies_tiles_select_kernel<<<(unsigned)((words + 255) / 256), 256, 0, w->stream>>>((const uint32_t*)B->d_tiles, B->d_tiles_x, B->d_off, B->d_exec, n,
+                                                                                                w->ctx->rank, B->n_pixels);
+            CK(cudaGetLastError());
+            w->ctx->launches += 1;
+            if (int r = strip_allreduce_u32(w, B->d_tiles_x, words, w->stream)) return r;
+            CK(cudaMemcpyAsync(B->d_tiles, B->d_tiles_x, sizeof(fse_cell) * (size_t)B->n_pixels, cudaMemcpyDeviceToDevice, w->stream));
+        }
+    }
     if (out) {  // the feedback read below joins the stream anyway: report the rounds of the slowest body with it
         unsigned int rounds = 0;
         CK(cudaMemcpyAsync(&rounds, B->d_done + n + 1, sizeof rounds, cudaMemcpyDeviceToHost, w->stream));

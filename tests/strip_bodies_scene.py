@@ -1,0 +1,29 @@
+"""Bodies of tests/test_strips_gpu.py::test_strip_bodies_match_oracle: random ones all over the world plus, around every strip cut, a body
+just above it, one just below it, and a pair that overlaps ACROSS the cut (cross-body order matters there, so one rank must run both)."""
+import numpy as np
+
+from falling_sand_engine_b200 import strips
+from tests.test_bridge_cpu import make_body
+
+
+def scene(table, W, H, nranks):
+    rng = np.random.default_rng(7)
+    bodies, xf = [], []
+
+    def add(x, y, ang, w=None, h=None, fill=0.8):
+        w = int(rng.integers(12, 30)) if w is None else w
+        h = int(rng.integers(12, 30)) if h is None else h
+        bodies.append(make_body(table, w, h, seed=100 + len(bodies), fill=fill))
+        xf.append((float(x), float(y), float(ang)))
+
+    for _ in range(40):
+        add(rng.uniform(160, W - 160), rng.uniform(160, H - 160), rng.uniform(-3.1, 3.1))
+    for r in range(1, nranks):
+        cut = strips.strip_layout(H, r, nranks)[0]
+        x0 = 200 + 150 * r
+        add(x0, cut - 22, 0.2, 20, 18)          # above the cut, reaches a few rows below it
+        add(x0 + 120, cut + 2, -0.4, 16, 20)    # starts in the lower strip's first rows, reaches above the cut when turned
+        add(x0 + 300, cut - 14, 0.0, 18, 16, fill=1.0)   # a pair that overlaps across the cut
+        add(x0 + 306, cut + 1, 0.1, 18, 16, fill=1.0)
+        add(x0 + 480, cut - 9, 1.2, 14, 14)     # drifts across the cut during the run: its runner changes
+    return bodies, np.array(xf, dtype=np.float32)

@@ -58,3 +58,46 @@ def test_strips_match_oracle(oracle, table, tmp_path, nranks):
         Hh.assert_cells_equal(ref[lo:hi], np.load(f"{out}.rank{k}.npy"), f"strip {k}/{nranks}")
         parts.append(np.load(f"{out}.parts{k}.npy"))
     Hh.assert_particles_equal(ow.particles_read(), np.concatenate(parts), "strip particles")
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_strip_bodies_match_oracle(oracle, table, tmp_path, nranks):
+    """The rigid-body bridge on multi-rank strips (game.cpp:1711-1815 raster, 1896-1983 erase, around the tick and tickCells): every rank
+    makes every call; a body — with every body whose footprint box overlaps its own — is run by the rank that holds the box, the part of
+    the box in a neighbour's rows travels there afterwards, feedback and the rewritten body tiles are shared over the ranks.  Grid,
+    particle pool, feedback of every call and the tiles of every body must equal the single-world oracle on every rank."""
+    if _ngpu() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    from oracle import pyoracle as O
+    from tests.strip_bodies_scene import scene
+    W, H, ticks = 1024, 1536, 6
+    out = str(tmp_path / "sb")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29650 + nranks), os.path.join(ROOT, "tests", "strip_bodies_gpu_worker.py"), str(W), str(H), str(ticks), out]
+    env = dict(os.environ, FSE_TICK_MIN_CHUNKS="1", FSE_FUSED_MAX_CHUNKS="0")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    ow = oracle.OracleWorld(W, H, table)
+    ow.write_rect(0, 0, G.mixed_band(table, W, H, 0, H, seed=21, air_frac=0.6, blob=48))
+    bodies, xf = scene(table, W, H, nranks)
+    ob = [b.copy() for b in bodies]
+    fbs = []
+    for t in range(ticks):
+        fbs.append(O.bodies_raster(ow, ob, xf, tick=t))
+        ow.tick(t, seed=1337)
+        ow.particles_tick()
+        fbs.append(O.bodies_erase(ow, ob, xf))
+        xf[:, 1] += 1.5
+        xf[:, 2] += 0.05
+    fbs = np.stack(fbs)
+    assert fbs[:, :, 2].sum() > 0 and (fbs[0::2, :, 0] + fbs[0::2, :, 1]).sum() > 0  # pixels were placed and grains / liquid were displaced
+    ref = ow.read_all()
+    tiles = np.concatenate([b.reshape(-1) for b in ob])
+    parts = []
+    for k in range(nranks):
+        lo, hi = strips.strip_layout(H, k, nranks)[:2]
+        assert np.array_equal(fbs, np.load(f"{out}.fb{k}.npy")), f"feedback on rank {k}"
+        assert tiles.tobytes() == np.load(f"{out}.tiles{k}.npy").tobytes(), f"body tiles on rank {k}"
+        Hh.assert_cells_equal(ref[lo:hi], np.load(f"{out}.rank{k}.npy"), f"strip {k}/{nranks}")
+        parts.append(np.load(f"{out}.parts{k}.npy"))
+    Hh.assert_particles_equal(ow.particles_read(), np.concatenate(parts), "strip particles")
