@@ -245,7 +245,11 @@ FSE_API int fse_object_delete(fse_world* w);
 
 /* ---- rigid-body bridge: the raster / erase loops of game::tick (game.cpp:1711-1815, 1896-1983) ---------------
  * Box2D stays on the host (north_star); the host keeps b2Body poses and sends one fse_xform per body per tick.
- * fse_body_desc mirrors RigidBody::matWidth / matHeight / tiles (game/player.hpp:15-65); AIR tiles are empty. */
+ * fse_body_desc mirrors RigidBody::matWidth / matHeight / tiles (game/player.hpp:15-65); AIR tiles are empty.
+ * On multi-rank strips every rank uploads every body and makes every call with the same transforms (global coordinates); a body is
+ * run by the rank that holds its footprint box, together with every body whose box overlaps its own, the rows shared with a
+ * neighbour are brought back in step afterwards, and every rank gets the same feedback and the same tiles.  A group of overlapping
+ * bodies that does not fit the rows of one strip plus its 32 ghost rows is refused (FSE_ESTATE). */
 typedef struct fse_body_desc {
     int32_t w, h;
     const fse_cell* tiles; /* w*h, index tx + ty*w */
