@@ -214,6 +214,35 @@ int strip_sendrecv(fse_world* w, const void* up_send, size_t up_send_bytes, void
     return FSE_OK;
 }
 
+// Vertical camera scroll: the local rows [send_lo, send_hi) of the seven planes, packed plane after plane like a halo message, travel to
+// the neighbour below (send_down) or above, while the same number of rows arrives from the neighbour on the other side.  *recv_out = the
+// packed rows that arrived (staging buffer, valid until the next exchange on this world), null when there is no neighbour on that side.
+int strip_shift_rows(fse_world* w, int send_lo, int send_hi, bool send_down, unsigned char** recv_out, cudaStream_t s) {
+    fse_ctx* c = w->ctx;
+    const bool up = c->rank > 0, down = c->rank + 1 < c->nranks;
+    const bool sends = send_down ? down : up, recvs = send_down ? up : down;
+    const size_t bytes = halo_bytes(w, send_hi - send_lo);
+    *recv_out = nullptr;
+    if (sends) {
+        if (int r = ensure_stage(w, 0, bytes)) return r;
+        PackArgs a;
+        halo_args(w, (unsigned char*)w->halo_stage[0], send_lo, send_hi, true, &a);
+        halo_copy_kernel<<<dim3(64, 7), 256, 0, s>>>(a);
+        CK(cudaGetLastError());
+        w->ctx->launches += 1;
+    }
+    if (recvs)
+        if (int r = ensure_stage(w, 1, bytes)) return r;
+    const void* snd = sends ? w->halo_stage[0] : nullptr;
+    void* rcv = recvs ? w->halo_stage[1] : nullptr;
+    int r;
+    if (send_down) r = strip_sendrecv(w, nullptr, 0, rcv, recvs ? bytes : 0, snd, sends ? bytes : 0, nullptr, 0, s);
+    else r = strip_sendrecv(w, snd, sends ? bytes : 0, nullptr, 0, nullptr, 0, rcv, recvs ? bytes : 0, s);
+    if (r) return r;
+    *recv_out = (unsigned char*)rcv;
+    return FSE_OK;
+}
+
 // In-place sum of `count` 32-bit unsigned integers over all ranks.
 int strip_allreduce_u32(fse_world* w, unsigned int* dev, size_t count, cudaStream_t s) {
     ncclComm_t comm = (ncclComm_t)w->ctx->nccl_comm;

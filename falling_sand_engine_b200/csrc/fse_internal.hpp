@@ -170,6 +170,7 @@ int strip_refresh(fse_world* w, cudaStream_t s, int rows = 16);
 int strip_sendrecv(fse_world* w, const void* up_send, size_t up_send_bytes, void* up_recv, size_t up_recv_bytes, const void* down_send,
                    size_t down_send_bytes, void* down_recv, size_t down_recv_bytes, cudaStream_t s);
 int strip_allreduce_u32(fse_world* w, unsigned int* dev, size_t count, cudaStream_t s);
+int strip_shift_rows(fse_world* w, int send_lo, int send_hi, bool send_down, unsigned char** recv_out, cudaStream_t s);
 size_t tick_smem_bytes();
 cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream, const int* members = nullptr, int parts = 1);
 cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched, const TickFork* fork);  // *launched = kernels enqueued

@@ -225,6 +225,52 @@ __global__ void __launch_bounds__(256) scroll_planes4_kernel(Planes dst, Planes 
         reinterpret_cast<uint4*>(dst.fd)[g] = reinterpret_cast<const uint4*>(src.fd)[f];
     }
 }
+// Vertical shifts on multi-rank strips: the source row of a local row may belong to a neighbour.  Those rows arrive packed plane after
+// plane (strip_shift_rows): ext.pl[q] = plane q of the global rows [ext.lo, ext.lo + ext.rows).  "Inside the world" is decided on
+// GLOBAL rows, so every rank shifts exactly the cells the single world would.
+struct ExtRows {
+    const unsigned char* pl[7];
+    int lo, rows;
+};
+__global__ void __launch_bounds__(256) scroll_planes_strip_kernel(Planes dst, Planes src, ExtRows ext, int W, int H, int dx, int dy, int y_off, int Hg) {
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    if (X >= W) return;
+    const int sx = X - dx;
+    const bool okx = sx >= 0 && sx < W;
+    for (int Y = blockIdx.y; Y < H; Y += gridDim.y) {
+        const int sg = Y + y_off - dy;  // global source row
+        const size_t g = (size_t)Y * W + X;
+        const int sl = sg - y_off, se = sg - ext.lo;
+        const uint8_t own_flg = src.flg[g];
+        if (okx && sg >= 0 && sg < Hg && sl >= 0 && sl < H) {
+            const size_t f = (size_t)sl * W + sx;
+            dst.mat[g] = src.mat[f];
+            dst.flg[g] = (uint8_t)((src.flg[f] & ~F_DIRTY) | (own_flg & F_DIRTY));
+            dst.stl[g] = src.stl[f];
+            dst.tmp[g] = src.tmp[f];
+            dst.col[g] = src.col[f];
+            dst.fl[g] = src.fl[f];
+            dst.fd[g] = src.fd[f];
+        } else if (okx && sg >= 0 && sg < Hg && se >= 0 && se < ext.rows) {
+            const size_t f = (size_t)se * W + sx;
+            dst.mat[g] = ext.pl[0][f];
+            dst.flg[g] = (uint8_t)((ext.pl[1][f] & ~F_DIRTY) | (own_flg & F_DIRTY));
+            dst.stl[g] = ext.pl[2][f];
+            dst.tmp[g] = reinterpret_cast<const int16_t*>(ext.pl[3])[f];
+            dst.col[g] = reinterpret_cast<const uint32_t*>(ext.pl[4])[f];
+            dst.fl[g] = reinterpret_cast<const float*>(ext.pl[5])[f];
+            dst.fd[g] = reinterpret_cast<const float*>(ext.pl[6])[f];
+        } else {  // no source inside the world: the cell stays (the reference's in-place loop leaves it alone)
+            dst.mat[g] = src.mat[g];
+            dst.flg[g] = own_flg;
+            dst.stl[g] = src.stl[g];
+            dst.tmp[g] = src.tmp[g];
+            dst.col[g] = src.col[g];
+            dst.fl[g] = src.fl[g];
+            dst.fd[g] = src.fd[g];
+        }
+    }
+}
 // background and real_layer2 move with the grid (world.cpp:2475-2476); layer2Dirty / backgroundDirty do not
 __global__ void __launch_bounds__(256) scroll_layers_kernel(uint8_t* d_mat, int16_t* d_tmp, uint32_t* d_col, uint32_t* d_bg, const uint8_t* s_mat,
                                                             const int16_t* s_tmp, const uint32_t* s_col, const uint32_t* s_bg, int W, int H, int dx,
@@ -517,11 +563,42 @@ extern "C" FSE_API int fse_scroll(fse_world* w, int32_t dx, int32_t dy) {
     if (!w) return fail(FSE_EINVAL, "fse_scroll: null world");
     // multi-rank strips: a horizontal shift never leaves a rank's rows (every rank makes the call and shifts what it holds, ghost rows
     // included); a vertical one would move rows between ranks and is left to the host (save, shift, reload)
-    if (w->strip && w->ctx->nranks > 1 && dy != 0) return fail(FSE_ESTATE, "fse_scroll: on multi-rank strips only horizontal shifts (dy = 0) are available");
+    const bool strip_dy = w->strip && w->ctx->nranks > 1 && dy != 0;
     if (dx == 0 && dy == 0) return FSE_OK;
     CK(cudaSetDevice(w->ctx->device));
     const size_t n = (size_t)w->W * w->H;
-    if (dx > -w->W && dx < w->W && dy > -w->H && dy < w->H) {  // otherwise no cell has a source inside the world
+    unsigned char* ext_rows = nullptr;
+    int ext_lo = 0, ext_n = 0;
+    if (strip_dy) {
+        // A vertical shift moves rows between ranks: every rank sends the |dy| rows its neighbour's window slides onto and receives as
+        // many from the other side (one message each way), then shifts what it holds, ghost rows included, reading the rows beyond its
+        // own window from the message.  The same limit on every rank (so that all of them make the same NCCL calls): |dy| must stay
+        // inside the shortest strip.
+        if (w->l2_mat) return fail(FSE_ESTATE, "fse_scroll: vertical shifts of the layer-2 / background planes on multi-rank strips are not available");
+        const int nr = w->ctx->nranks, nz = (w->Hglobal - 2 * CHUNK) / CHUNK;
+        int min_own = w->Hglobal;
+        for (int r = 0; r < nr; r++) {
+            const int j0 = (int)((int64_t)nz * r / nr), j1 = (int)((int64_t)nz * (r + 1) / nr);
+            const int lo = r == 0 ? 0 : CHUNK + CHUNK * j0, hi = r == nr - 1 ? w->Hglobal : CHUNK + CHUNK * j1;
+            min_own = hi - lo < min_own ? hi - lo : min_own;
+        }
+        const int ghost = w->own_lo - w->y_off > 0 ? w->own_lo - w->y_off : (w->y_off + w->H) - w->own_hi;  // one of the two exists on a multi-rank strip
+        const int nrows = dy > 0 ? dy : -dy;
+        if (nrows > min_own - ghost)
+            return fail(FSE_ESTATE, "fse_scroll: a vertical shift of %d rows on strips whose shortest one owns %d rows (at most %d)", dy, min_own, min_own - ghost);
+        if (int r = strip_refresh(w, w->stream, ghost)) return r;  // every local row is the owner's before it becomes somebody's source
+        int lo;
+        if (dy > 0) {  // content moves down: the neighbour below needs the rows above its window
+            lo = (w->own_hi - ghost - nrows) - w->y_off;
+            ext_lo = w->y_off - nrows;
+        } else {       // content moves up: the neighbour above needs the rows below its window
+            lo = (w->own_lo + ghost) - w->y_off;
+            ext_lo = w->y_off + w->H;
+        }
+        if (int r = strip_shift_rows(w, lo, lo + nrows, dy > 0, &ext_rows, w->stream)) return r;
+        ext_n = ext_rows ? nrows : 0;
+    }
+    if (dx > -w->W && dx < w->W && (strip_dy || (dy > -w->H && dy < w->H))) {  // otherwise no cell has a source inside the world
         if (!w->p_shadow.mat) {  // all or nothing
             void* q[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             const size_t bytes[7] = {n, n, n, n * 2, n * 4, n * 4, n * 4};
@@ -535,7 +612,18 @@ extern "C" FSE_API int fse_scroll(fse_world* w, int32_t dx, int32_t dy) {
             w->p_shadow.col = (uint32_t*)q[4]; w->p_shadow.fl = (float*)q[5]; w->p_shadow.fd = (float*)q[6];
         }
         dim3 grid((w->W + 255) / 256, w->H < 2048 ? w->H : 2048);
-        if (dx % 4 == 0 && w->W % 4 == 0) {
+        if (strip_dy) {
+            ExtRows ext;
+            size_t so = 0;
+            const size_t es[7] = {1, 1, 1, 2, 4, 4, 4};
+            for (int q = 0; q < 7; q++) {
+                ext.pl[q] = ext_rows ? ext_rows + so : nullptr;
+                so += (size_t)ext_n * w->W * es[q];
+            }
+            ext.lo = ext_lo;
+            ext.rows = ext_n;
+            scroll_planes_strip_kernel<<<grid, 256, 0, w->stream>>>(w->p_shadow, w->p, ext, w->W, w->H, dx, dy, w->y_off, w->Hglobal);
+        } else if (dx % 4 == 0 && w->W % 4 == 0) {
             dim3 grid4((w->W / 4 + 255) / 256, w->H < 4096 ? w->H : 4096);
             scroll_planes4_kernel<<<grid4, 256, 0, w->stream>>>(w->p_shadow, w->p, w->W, w->H, dx, dy);
         } else {

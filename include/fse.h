@@ -372,7 +372,9 @@ FSE_API int fse_render_layers(fse_world* w, int draw_background_grid, int64_t* n
  * world keep their old content (the reference's in-place copy), dirty flags stay where they are (world::dirty is not
  * shifted), loose particles move along.  The shifted world is written into a second set of planes which then becomes the
  * world (one read + one write per cell).  Chunk load / save around the scroll stays with the host (fse_write_rect /
- * fse_read_rect).  On multi-rank strips only horizontal shifts (dy = 0): every rank makes the call and shifts the rows it holds. */
+ * fse_read_rect).  On multi-rank strips every rank makes the call and shifts the rows it holds; for a vertical shift the |dy| rows that
+ * change ranks travel as one message to each neighbour first (|dy| at most the shortest strip's own rows minus the ghost rows; the
+ * layer-2 / background planes do not take vertical shifts on strips yet). */
 FSE_API int fse_scroll(fse_world* w, int32_t dx, int32_t dy);
 
 /* ---- fracture / hitbox outlines: updateRigidBodyHitbox, updateChunkMesh (world.cpp:288-720, 722-959) with

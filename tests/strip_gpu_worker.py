@@ -29,6 +29,10 @@ def main():
             sw.tool_erase_line(200, H // 4 - 30, 700, 3 * H // 4 + 20, 9)
         if t == 4:  # the camera moves one chunk to the right: a horizontal shift stays inside every rank's rows
             sw.scroll(-128, 0)
+        if t == 5:  # ... one chunk down: rows change ranks (one message of 128 rows each way, the rest is shifted in place)
+            sw.scroll(0, 128)
+        if t == 6:  # ... and up and to the right by odd amounts
+            sw.scroll(36, -97)
         sw.particles_tick()  # ghost refresh, migration, integration and the deposit rounds with the band proposals exchanged
         if t % 4 == 2:
             sw.tick_temperature()

@@ -1,6 +1,6 @@
 """Multi-GPU strips over NCCL vs the single-world oracle (bit-exact for any strip count; SURVEY.md §8c pin 8): world tick, loose
 particles (migration between ranks + deposit rounds with the band proposals exchanged), temperature, an explosion and an eraser
-stroke across the cuts, and a horizontal camera scroll.
+stroke across the cuts, camera scrolls (horizontal, vertical — rows change ranks — and both at once), and the rigid-body bridge.
 Needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_strips_gpu.py -m gpu`."""
 import os
 import subprocess
@@ -45,6 +45,10 @@ def test_strips_match_oracle(oracle, table, tmp_path, nranks):
             O.tool_erase_line(ow, 200, H // 4 - 30, 700, 3 * H // 4 + 20, 9)
         if t == 4:
             O.scroll(ow, -128, 0)
+        if t == 5:
+            O.scroll(ow, 0, 128)
+        if t == 6:
+            O.scroll(ow, 36, -97)
         before = ow.particles_count()
         ow.particles_tick()
         deposited += before - ow.particles_count()
