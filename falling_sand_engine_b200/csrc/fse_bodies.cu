@@ -598,32 +598,6 @@ __global__ void __launch_bounds__(BODY_TB, 8) bodies_body_kernel(BodyArgs a) {
 // before the call); afterwards the part of the box that lies in a neighbour's rows travels there as a rectangle of cells, so both
 // ranks agree on every row they share again.  Feedback is summed over the ranks (the others contribute zeros), and after an erase the
 // tile arrays — replicated on every rank — are brought back in step the same way.
-struct RectArgs {
-    Planes p;
-    int W;
-    const int4* rects;     // x0, y0 (local rows), w, h
-    const int* cell_off;   // first cell of each rectangle in the message
-    unsigned char* stage;  // per rectangle: its cells plane after plane (17 bytes per cell)
-    int pack;
-};
-__global__ void bodies_rect_copy_kernel(RectArgs a) {
-    const int4 r = a.rects[blockIdx.x];
-    const int n = r.z * r.w;
-    unsigned char* st = a.stage + (size_t)a.cell_off[blockIdx.x] * 17;
-    unsigned char* pl[7] = {(unsigned char*)a.p.mat, (unsigned char*)a.p.flg, (unsigned char*)a.p.stl, (unsigned char*)a.p.tmp,
-                            (unsigned char*)a.p.col, (unsigned char*)a.p.fl, (unsigned char*)a.p.fd};
-    const int es[7] = {1, 1, 1, 2, 4, 4, 4};
-    size_t so = 0;
-    for (int q = 0; q < 7; q++) {
-        for (int i = threadIdx.x; i < n * es[q]; i += blockDim.x) {  // byte-wise: the message is not aligned for the wider planes
-            const int c = i / es[q], bq = i % es[q];
-            const size_t g = ((size_t)(r.y + c / r.z) * a.W + (size_t)(r.x + c % r.z)) * es[q] + bq;
-            if (a.pack) st[so + i] = pl[q][g];
-            else pl[q][g] = st[so + i];
-        }
-        so += (size_t)n * es[q];
-    }
-}
 // x[i] = word i of the tiles if this rank ran the body the word belongs to, 0 otherwise (the sum over the ranks is the runner's copy)
 __global__ void bodies_tiles_select_kernel(const uint32_t* tiles, uint32_t* x, const int* off, const int* exec, int n_bodies, int rank, int n_pixels) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -665,17 +639,11 @@ struct fse_bodies {
     // multi-rank strips
     int* d_exec = nullptr;           // [n] rank that runs each body in this call
     uint32_t* d_tiles_x = nullptr;   // n_pixels fse_cell (as words): the executed bodies' tiles, summed over the ranks after an erase
-    int4* d_rects = nullptr;         // rectangles pushed to / taken from the neighbours (x0, y0 local, w, h) + their cell offsets
-    int* d_rect_off = nullptr;
-    size_t rects_cap = 0;
-    unsigned char* push_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // up send, up recv, down send, down recv
-    size_t push_stage_bytes[4] = {0, 0, 0, 0};
     void release() {
         cudaFree(d_off); cudaFree(d_bw); cudaFree(d_bh); cudaFree(d_tiles); cudaFree(d_xf); cudaFree(d_pending); cudaFree(d_claim);
         cudaFree(d_feedback); cudaFree(d_aabb); cudaFree(d_done);
-        cudaFree(d_exec); cudaFree(d_tiles_x); cudaFree(d_rects); cudaFree(d_rect_off);
-        d_exec = nullptr; d_tiles_x = nullptr; d_rects = nullptr; d_rect_off = nullptr; rects_cap = 0;
-        for (int i = 0; i < 4; i++) { cudaFree(push_stage[i]); push_stage[i] = nullptr; push_stage_bytes[i] = 0; }
+        cudaFree(d_exec); cudaFree(d_tiles_x);
+        d_exec = nullptr; d_tiles_x = nullptr;
         d_off = d_bw = d_bh = nullptr; d_tiles = nullptr; d_xf = nullptr; d_pending = nullptr; d_claim = nullptr; d_feedback = nullptr;
         d_aabb = nullptr; d_done = nullptr;
     }
@@ -740,15 +708,6 @@ extern "C" FSE_API int fse_bodies_upload(fse_world* w, const fse_body_desc* bodi
 
 
 // ---- multi-rank strips: who runs which body, and which rectangles travel afterwards (host; every rank computes the same plan) -------
-static const int BGHOST = 32;  // ghost rows of a strip (fse_strip_create)
-static void strip_rows_of(int Hglobal, int rank, int nranks, int* own_lo, int* own_hi, int* held_lo, int* held_hi) {
-    const int nz = (Hglobal - 2 * CHUNK) / CHUNK;
-    const int j0 = (int)((int64_t)nz * rank / nranks), j1 = (int)((int64_t)nz * (rank + 1) / nranks);
-    *own_lo = rank == 0 ? 0 : CHUNK + CHUNK * j0;
-    *own_hi = rank == nranks - 1 ? Hglobal : CHUNK + CHUNK * j1;
-    *held_lo = *own_lo - BGHOST < 0 ? 0 : *own_lo - BGHOST;
-    *held_hi = *own_hi + BGHOST > Hglobal ? Hglobal : *own_hi + BGHOST;
-}
 struct StripPlan {
     std::vector<int> exec;
     std::vector<int4> rect[4];  // up send, up recv, down send, down recv (x0, y0 in local rows, w, h)
@@ -796,38 +755,26 @@ static int plan_strip_bodies(fse_world* w, const fse_bodies* B, const fse_xform*
         active.resize(keep);
         active.push_back(i);
     }
-    std::vector<int> olo(nranks), ohi(nranks), hlo(nranks), hhi(nranks);
-    for (int r = 0; r < nranks; r++) strip_rows_of(Hg, r, nranks, &olo[r], &ohi[r], &hlo[r], &hhi[r]);
     P.exec.assign(n, 0);
     for (int b = 0; b < n; b++) {
         const int root = find(b);
-        int mid = (box[root].y + box[root].w) / 2;
-        mid = mid < 0 ? 0 : (mid >= Hg ? Hg - 1 : mid);
         int e = 0;
-        while (e + 1 < nranks && mid >= ohi[e]) e++;
+        if (root == b) {
+            if (int r = strip_runner_of_rows(w, box[b].y, box[b].w, nullptr, &e)) return r;  // owner of the middle row; the fit is checked per body below
+        } else {
+            e = P.exec[root];  // root < b: already known
+        }
         P.exec[b] = e;
+        int hlo, hhi;
+        strip_rows_of(Hg, e, nranks, nullptr, nullptr, &hlo, &hhi);
         const int ya = box[b].y < 0 ? 0 : box[b].y, yb = box[b].w >= Hg ? Hg - 1 : box[b].w;
-        if (ya <= yb && (ya < hlo[e] || yb >= hhi[e]))
+        if (ya <= yb && (ya < hlo || yb >= hhi))
             return fail(FSE_ESTATE, "%s: body %d (rows %d..%d, with the bodies it overlaps) does not fit the rows rank %d holds (%d..%d): on multi-rank strips a group of "
-                        "overlapping bodies must lie within %d rows of one strip", who, b, ya, yb, e, hlo[e], hhi[e] - 1, BGHOST);
+                        "overlapping bodies must lie within %d rows of one strip", who, b, ya, yb, e, hlo, hhi - 1, STRIP_GHOST);
     }
     for (int q = 0; q < 4; q++) P.rect[q].clear();
-    for (int b = 0; b < n; b++) {
-        const int e = P.exec[b];
-        const int xa = box[b].x < 0 ? 0 : box[b].x, xb = box[b].z >= W ? W - 1 : box[b].z;
-        if (xa > xb) continue;
-        for (int side = 0; side < 2; side++) {  // 0: the neighbour above the runner, 1: the one below
-            const int nb = side == 0 ? e - 1 : e + 1;
-            if (nb < 0 || nb >= nranks || (me != e && me != nb)) continue;
-            int ya = box[b].y < 0 ? 0 : box[b].y, yb = box[b].w >= Hg ? Hg - 1 : box[b].w;
-            if (ya < hlo[nb]) ya = hlo[nb];
-            if (yb >= hhi[nb]) yb = hhi[nb] - 1;
-            if (ya > yb) continue;
-            const int4 r = make_int4(xa, ya - w->y_off, xb - xa + 1, yb - ya + 1);
-            if (me == e) P.rect[side == 0 ? 0 : 2].push_back(r);  // I ran it: send towards that neighbour
-            else P.rect[side == 0 ? 3 : 1].push_back(r);          // my neighbour ran it: the runner is below me (side 0) or above me (side 1)
-        }
-    }
+    for (int b = 0; b < n; b++) strip_rects_of_box(w, P.exec[b], box[b].x, box[b].y, box[b].z, box[b].w, P.rect);
+    (void)me; (void)W;
     return FSE_OK;
 }
 
@@ -843,7 +790,7 @@ static int run_bridge(fse_world* w, const fse_xform* xf, int32_t n, uint32_t tic
     StripPlan plan;
     if (multi) {
         // the runner of a body works on its ghost rows as well: they must be the owner's rows first
-        if (int r = strip_refresh(w, w->stream, BGHOST)) return r;
+        if (int r = strip_refresh(w, w->stream, STRIP_GHOST)) return r;
         if (int r = plan_strip_bodies(w, B, xf, n, plan, ERASE ? "fse_bodies_erase" : "fse_bodies_raster")) return r;
         if (!B->d_exec) CK(cudaMalloc(&B->d_exec, sizeof(int) * n));
         CK(cudaMemcpyAsync(B->d_exec, plan.exec.data(), sizeof(int) * n, cudaMemcpyHostToDevice, w->stream));
@@ -868,61 +815,7 @@ static int run_bridge(fse_world* w, const fse_xform* xf, int32_t n, uint32_t tic
     w->ctx->launches += 2;
     if (multi) {
         // the boxes of the bodies this rank ran, as far as they lie in a neighbour's rows, travel there (and the neighbours' come here)
-        size_t cells[4] = {0, 0, 0, 0}, total_rects = 0;
-        for (int q = 0; q < 4; q++) {
-            for (const int4& r : plan.rect[q]) cells[q] += (size_t)r.z * r.w;
-            total_rects += plan.rect[q].size();
-        }
-        if (total_rects > B->rects_cap) {
-            CK(cudaStreamSynchronize(w->stream));
-            cudaFree(B->d_rects); cudaFree(B->d_rect_off);
-            B->d_rects = nullptr; B->d_rect_off = nullptr; B->rects_cap = 0;
-            CK(cudaMalloc(&B->d_rects, sizeof(int4) * (total_rects + 64)));
-            CK(cudaMalloc(&B->d_rect_off, sizeof(int) * (total_rects + 64)));
-            B->rects_cap = total_rects + 64;
-        }
-        std::vector<int4> all_r;
-        std::vector<int> all_o;
-        size_t first[4];
-        for (int q = 0; q < 4; q++) {
-            first[q] = all_r.size();
-            int o = 0;
-            for (const int4& r : plan.rect[q]) {
-                all_r.push_back(r);
-                all_o.push_back(o);
-                o += r.z * r.w;
-            }
-            if (cells[q] * 17 > B->push_stage_bytes[q]) {
-                CK(cudaStreamSynchronize(w->stream));
-                cudaFree(B->push_stage[q]);
-                B->push_stage[q] = nullptr; B->push_stage_bytes[q] = 0;
-                CK(cudaMalloc(&B->push_stage[q], cells[q] * 17 + 4096));
-                B->push_stage_bytes[q] = cells[q] * 17 + 4096;
-            }
-        }
-        if (total_rects) {
-            CK(cudaMemcpyAsync(B->d_rects, all_r.data(), sizeof(int4) * total_rects, cudaMemcpyHostToDevice, w->stream));
-            CK(cudaMemcpyAsync(B->d_rect_off, all_o.data(), sizeof(int) * total_rects, cudaMemcpyHostToDevice, w->stream));
-        }
-        RectArgs ra;
-        ra.p = w->p; ra.W = w->W;
-        for (int q = 0; q < 4; q += 2)  // pack what goes up (0) and down (2)
-            if (!plan.rect[q].empty()) {
-                ra.rects = B->d_rects + first[q]; ra.cell_off = B->d_rect_off + first[q]; ra.stage = B->push_stage[q]; ra.pack = 1;
-                bodies_rect_copy_kernel<<<(unsigned)plan.rect[q].size(), 128, 0, w->stream>>>(ra);
-                w->ctx->launches += 1;
-            }
-        CK(cudaGetLastError());
-        if (int r = strip_sendrecv(w, B->push_stage[0], cells[0] * 17, B->push_stage[1], cells[1] * 17, B->push_stage[2], cells[2] * 17, B->push_stage[3],
-                                   cells[3] * 17, w->stream))
-            return r;
-        for (int q = 1; q < 4; q += 2)  // unpack what came from above (1) and from below (3)
-            if (!plan.rect[q].empty()) {
-                ra.rects = B->d_rects + first[q]; ra.cell_off = B->d_rect_off + first[q]; ra.stage = B->push_stage[q]; ra.pack = 0;
-                bodies_rect_copy_kernel<<<(unsigned)plan.rect[q].size(), 128, 0, w->stream>>>(ra);
-                w->ctx->launches += 1;
-            }
-        CK(cudaGetLastError());
+        if (int r = strip_push_rects(w, plan.rect, w->stream)) return r;
         // feedback: the runner's numbers on every rank
         if (int r = strip_allreduce_u32(w, (unsigned int*)B->d_feedback, (size_t)4 * n, w->stream)) return r;
         if (ERASE) {  // the erase rewrote the tiles of the bodies this rank ran: every rank gets every runner's copy

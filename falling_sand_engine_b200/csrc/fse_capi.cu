@@ -220,6 +220,8 @@ static void free_world(fse_world* w) {
     if (w->outline_pinned) cudaFreeHost(w->outline_pinned);
     if (w->outline_pinned2) cudaFreeHost(w->outline_pinned2);
     for (int q = 0; q < 4; q++) cudaFree(w->halo_stage[q]);
+    cudaFree(w->d_push_rects);
+    cudaFree(w->d_push_off);
     for (cudaEvent_t e_ : w->timeline_ev) cudaEventDestroy(e_);
     cudaFree(w->d_phase_rows);
     if (w->h_phase_rows) cudaFreeHost(w->h_phase_rows);

@@ -14,6 +14,8 @@
 // link-time NCCL dependency and never mixes two NCCL builds in one process.
 #include <dlfcn.h>
 
+#include <vector>
+
 #include "fse_internal.hpp"
 
 namespace fse {
@@ -240,6 +242,145 @@ int strip_shift_rows(fse_world* w, int send_lo, int send_hi, bool send_down, uns
     else r = strip_sendrecv(w, snd, sends ? bytes : 0, nullptr, 0, nullptr, 0, rcv, recvs ? bytes : 0, s);
     if (r) return r;
     *recv_out = (unsigned char*)rcv;
+    return FSE_OK;
+}
+
+// ---- edits by ONE rank that reach into a neighbour's rows (rigid bodies, tools) -----------------------------------------------------
+// Every rank makes the call with the same arguments and derives the same plan: the rank that holds the middle row of the edit's box
+// runs it on its own rows + ghost rows (refreshed first); afterwards the part of the box that lies in a neighbour's rows travels
+// there as a rectangle of cells, so both ranks agree on every row they share again.
+void strip_rows_of(int Hglobal, int rank, int nranks, int* own_lo, int* own_hi, int* held_lo, int* held_hi) {
+    const int nz = (Hglobal - 2 * CHUNK) / CHUNK;
+    const int j0 = (int)((int64_t)nz * rank / nranks), j1 = (int)((int64_t)nz * (rank + 1) / nranks);
+    const int lo = rank == 0 ? 0 : CHUNK + CHUNK * j0, hi = rank == nranks - 1 ? Hglobal : CHUNK + CHUNK * j1;
+    if (own_lo) *own_lo = lo;
+    if (own_hi) *own_hi = hi;
+    if (held_lo) *held_lo = lo - STRIP_GHOST < 0 ? 0 : lo - STRIP_GHOST;
+    if (held_hi) *held_hi = hi + STRIP_GHOST > Hglobal ? Hglobal : hi + STRIP_GHOST;
+}
+// runner of an edit whose box spans the global rows [ya, yb]: the owner of the middle row.  who != null: fails when the box does not
+// lie inside the rows the runner holds.
+int strip_runner_of_rows(fse_world* w, int ya, int yb, const char* who, int* exec) {
+    const int nranks = w->ctx->nranks, Hg = w->Hglobal;
+    int mid = (ya + yb) / 2;
+    mid = mid < 0 ? 0 : (mid >= Hg ? Hg - 1 : mid);
+    int e = 0, hi = 0;
+    for (;; e++) {
+        strip_rows_of(Hg, e, nranks, nullptr, &hi, nullptr, nullptr);
+        if (e + 1 >= nranks || mid < hi) break;
+    }
+    *exec = e;
+    if (who) {
+        int hlo, hhi;
+        strip_rows_of(Hg, e, nranks, nullptr, nullptr, &hlo, &hhi);
+        const int a = ya < 0 ? 0 : ya, b = yb >= Hg ? Hg - 1 : yb;
+        if (a <= b && (a < hlo || b >= hhi))
+            return fail(FSE_ESTATE, "%s: rows %d..%d do not fit the rows rank %d holds (%d..%d): on multi-rank strips the call must stay within %d rows of one strip",
+                        who, a, b, e, hlo, hhi - 1, STRIP_GHOST);
+    }
+    return FSE_OK;
+}
+// the rectangles of box [xa, xb] x [ya, yb] (global, inclusive) run by rank `exec` that this rank sends or receives:
+// rect[0] up send, [1] up recv, [2] down send, [3] down recv; (x0, y0 in local rows, w, h)
+void strip_rects_of_box(fse_world* w, int exec, int xa, int ya, int xb, int yb, std::vector<int4> rect[4]) {
+    const int nranks = w->ctx->nranks, me = w->ctx->rank, Hg = w->Hglobal;
+    xa = xa < 0 ? 0 : xa;
+    xb = xb >= w->W ? w->W - 1 : xb;
+    if (xa > xb) return;
+    for (int side = 0; side < 2; side++) {  // 0: the neighbour above the runner, 1: the one below
+        const int nb = side == 0 ? exec - 1 : exec + 1;
+        if (nb < 0 || nb >= nranks || (me != exec && me != nb)) continue;
+        int hlo, hhi;
+        strip_rows_of(Hg, nb, nranks, nullptr, nullptr, &hlo, &hhi);
+        int a = ya < 0 ? 0 : ya, b = yb >= Hg ? Hg - 1 : yb;
+        if (a < hlo) a = hlo;
+        if (b >= hhi) b = hhi - 1;
+        if (a > b) continue;
+        const int4 r = make_int4(xa, a - w->y_off, xb - xa + 1, b - a + 1);
+        if (me == exec) rect[side == 0 ? 0 : 2].push_back(r);  // I ran it: send towards that neighbour
+        else rect[side == 0 ? 3 : 1].push_back(r);             // my neighbour ran it: the runner is below me (side 0) or above me (side 1)
+    }
+}
+struct RectArgs {
+    Planes p;
+    int W;
+    const int4* rects;     // x0, y0 (local rows), w, h
+    const int* cell_off;   // first cell of each rectangle in the message
+    unsigned char* stage;  // per rectangle: its cells plane after plane (17 bytes per cell)
+    int pack;
+};
+__global__ void rect_copy_kernel(RectArgs a) {
+    const int4 r = a.rects[blockIdx.x];
+    const int n = r.z * r.w;
+    unsigned char* st = a.stage + (size_t)a.cell_off[blockIdx.x] * 17;
+    unsigned char* pl[7] = {(unsigned char*)a.p.mat, (unsigned char*)a.p.flg, (unsigned char*)a.p.stl, (unsigned char*)a.p.tmp,
+                            (unsigned char*)a.p.col, (unsigned char*)a.p.fl, (unsigned char*)a.p.fd};
+    const int es[7] = {1, 1, 1, 2, 4, 4, 4};
+    size_t so = 0;
+    for (int q = 0; q < 7; q++) {
+        for (int i = threadIdx.x; i < n * es[q]; i += blockDim.x) {  // byte-wise: the message is not aligned for the wider planes
+            const int c = i / es[q], bq = i % es[q];
+            const size_t g = ((size_t)(r.y + c / r.z) * a.W + (size_t)(r.x + c % r.z)) * es[q] + bq;
+            if (a.pack) st[so + i] = pl[q][g];
+            else pl[q][g] = st[so + i];
+        }
+        so += (size_t)n * es[q];
+    }
+}
+// pack -> one send / receive with each neighbour -> unpack, on stream s.  Both sides of a cut derive the same rectangles in the same
+// order, so the messages need no header.
+int strip_push_rects(fse_world* w, const std::vector<int4> rect[4], cudaStream_t s) {
+    size_t cells[4] = {0, 0, 0, 0}, total = 0, first[4];
+    std::vector<int4> all_r;
+    std::vector<int> all_o;
+    for (int q = 0; q < 4; q++) {
+        first[q] = all_r.size();
+        int o = 0;
+        for (const int4& r : rect[q]) {
+            all_r.push_back(r);
+            all_o.push_back(o);
+            o += r.z * r.w;
+        }
+        cells[q] = (size_t)o;
+        total += rect[q].size();
+        if (cells[q])
+            if (int r = ensure_stage(w, q, cells[q] * 17)) return r;
+    }
+    if (total > w->push_rects_cap) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(w->d_push_rects);
+        cudaFree(w->d_push_off);
+        w->d_push_rects = nullptr;
+        w->d_push_off = nullptr;
+        w->push_rects_cap = 0;
+        CK(cudaMalloc((void**)&w->d_push_rects, sizeof(int4) * (total + 64)));
+        CK(cudaMalloc((void**)&w->d_push_off, sizeof(int) * (total + 64)));
+        w->push_rects_cap = total + 64;
+    }
+    if (total) {
+        CK(cudaMemcpyAsync(w->d_push_rects, all_r.data(), sizeof(int4) * total, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->d_push_off, all_o.data(), sizeof(int) * total, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));  // all_r / all_o are locals
+    }
+    RectArgs ra;
+    ra.p = w->p;
+    ra.W = w->W;
+    for (int q = 0; q < 4; q += 2)  // pack what goes up (0) and down (2)
+        if (!rect[q].empty()) {
+            ra.rects = (const int4*)w->d_push_rects + first[q]; ra.cell_off = w->d_push_off + first[q]; ra.stage = (unsigned char*)w->halo_stage[q]; ra.pack = 1;
+            rect_copy_kernel<<<(unsigned)rect[q].size(), 128, 0, s>>>(ra);
+            w->ctx->launches += 1;
+        }
+    CK(cudaGetLastError());
+    if (int r = strip_sendrecv(w, w->halo_stage[0], cells[0] * 17, w->halo_stage[1], cells[1] * 17, w->halo_stage[2], cells[2] * 17, w->halo_stage[3], cells[3] * 17, s))
+        return r;
+    for (int q = 1; q < 4; q += 2)  // unpack what came from above (1) and from below (3)
+        if (!rect[q].empty()) {
+            ra.rects = (const int4*)w->d_push_rects + first[q]; ra.cell_off = w->d_push_off + first[q]; ra.stage = (unsigned char*)w->halo_stage[q]; ra.pack = 0;
+            rect_copy_kernel<<<(unsigned)rect[q].size(), 128, 0, s>>>(ra);
+            w->ctx->launches += 1;
+        }
+    CK(cudaGetLastError());
     return FSE_OK;
 }
 

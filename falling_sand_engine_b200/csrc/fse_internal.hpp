@@ -103,6 +103,9 @@ struct fse_world {
     uint64_t particles_dropped = 0;
     // strips: staging buffers of the packed halo messages (fse_comm.cu): [2 * cut] send, [2 * cut + 1] receive
     void* halo_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    void* d_push_rects = nullptr;  // rectangles of strip_push_rects (int4) and their cell offsets
+    int* d_push_off = nullptr;
+    size_t push_rects_cap = 0;
     size_t halo_stage_bytes[4] = {0, 0, 0, 0};
     // rigid-body bridge (fse_bodies.cu) and outline scratch (fse_outline.cu)
     struct fse_bodies* bodies = nullptr;
@@ -171,6 +174,12 @@ int strip_sendrecv(fse_world* w, const void* up_send, size_t up_send_bytes, void
                    size_t down_send_bytes, void* down_recv, size_t down_recv_bytes, cudaStream_t s);
 int strip_allreduce_u32(fse_world* w, unsigned int* dev, size_t count, cudaStream_t s);
 int strip_shift_rows(fse_world* w, int send_lo, int send_hi, bool send_down, unsigned char** recv_out, cudaStream_t s);
+// edits by one rank that reach into a neighbour's rows (fse_comm.cu): layout of any rank, runner of a box, rectangles to exchange, the exchange
+constexpr int STRIP_GHOST = 32;  // ghost rows of a strip (fse_strip_create)
+void strip_rows_of(int Hglobal, int rank, int nranks, int* own_lo, int* own_hi, int* held_lo, int* held_hi);
+int strip_runner_of_rows(fse_world* w, int ya, int yb, const char* who, int* exec);
+void strip_rects_of_box(fse_world* w, int exec, int xa, int ya, int xb, int yb, std::vector<int4> rect[4]);
+int strip_push_rects(fse_world* w, const std::vector<int4> rect[4], cudaStream_t s);
 size_t tick_smem_bytes();
 cudaError_t launch_lpt_build(const unsigned int* cost, int n, int ncx, int* list, cudaStream_t stream, const int* members = nullptr, int parts = 1);
 cudaError_t launch_tick_phase(const TickParams& P, int n_chunks, cudaStream_t stream, int* launched, const TickFork* fork);  // *launched = kernels enqueued

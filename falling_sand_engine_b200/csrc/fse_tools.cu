@@ -108,7 +108,8 @@ __global__ void tool_brush_kernel(Planes p, const DevTables* T, int W, int H, in
     if (T->phys[p.mat[g]] != P_AIR) tool_set_nothing(p, g, T->air);
 }
 
-__global__ void tool_pickaxe_kernel(Planes p, const DevTables* T, int W, int H, int x, int y, float breakSize, uint32_t* pixels, int* n_out) {
+// oy0 / oy1: the local rows whose cells this rank reports (strips: its own rows — ghost cells are cleared as well, but reported by their owner)
+__global__ void tool_pickaxe_kernel(Planes p, const DevTables* T, int W, int H, int x, int y, float breakSize, uint32_t* pixels, int* n_out, int oy0, int oy1) {
     const int size = (int)breakSize, span = (int)ceilf(breakSize);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= span * span) return;
@@ -118,16 +119,17 @@ __global__ void tool_pickaxe_kernel(Planes p, const DevTables* T, int W, int H, 
     if (x + xx < 0 || y + yy < 0 || x + xx >= W || y + yy >= H) return;
     const size_t g = (size_t)(y + yy) * W + (x + xx);
     if (T->phys[p.mat[g]] != P_SOLID) return;
-    if (xx < size && yy < size) pixels[xx + yy * size] = p.col[g];
+    const bool report = y + yy >= oy0 && y + yy < oy1;
+    if (report && xx < size && yy < size) pixels[xx + yy * size] = p.col[g];
     tool_set_nothing(p, g, T->air);
-    atomicAdd(n_out, 1);
+    if (report) atomicAdd(n_out, 1);
 }
 
 // hammer: one warp walks the segments in order, 32 cells of the crack at a time.  A segment's cells are distinct (the host removed
 // repeats like the reference's visited list), so they classify independently; what is sequential — "solid seen yet", the break at
 // the first non-solid cell more than one step from the segment start — is two ballots.
 __global__ void tool_hammer_kernel(Planes p, const DevTables* T, int W, int H, const long long* pts, const int* seg_off, const int* seg_start, int n_seg,
-                                   int sand_mat, int* out) {
+                                   int sand_mat, int* out, int y_off) {
     const int lane = threadIdx.x;
     long long endInd = -1;
     int changed = 0, broke = 0;
@@ -169,7 +171,7 @@ __global__ void tool_hammer_kernel(Planes p, const DevTables* T, int W, int H, c
     }
     if (lane == 0) {
         out[0] = endInd < 0 ? -1 : (int)(endInd % W);
-        out[1] = endInd < 0 ? -1 : (int)(endInd / W);
+        out[1] = endInd < 0 ? -1 : (int)(endInd / W) + y_off;  // global row
         out[2] = changed;
         out[3] = broke;
     }
@@ -451,26 +453,36 @@ extern "C" FSE_API int fse_tool_erase_line(fse_world* w, int32_t x0, int32_t y0,
 }
 
 extern "C" FSE_API int fse_tool_pickaxe(fse_world* w, int32_t x, int32_t y, float break_size, uint32_t* pixels_out, int32_t* n_out) {
-    if (int r = tool_common(w, "fse_tool_pickaxe")) return r;
+    // multi-rank strips: every rank makes the call; the cells decide independently, so a rank clears the cells of the circle it holds
+    // and reports the ones it owns; the reports are summed over the ranks (every pixel has one owner)
+    if (int r = tool_common(w, "fse_tool_pickaxe", true)) return r;
     if (!(break_size >= 1.0f) || break_size > 1024.0f || !pixels_out || !n_out) return fail(FSE_EINVAL, "fse_tool_pickaxe: bad argument");
+    const bool multi = w->strip && w->ctx->nranks > 1;
     const int size = (int)break_size, span = (int)std::ceil(break_size);
-    const size_t pix_bytes = sizeof(uint32_t) * (size_t)size * size;
-    if (int r = tool_scratch(w, pix_bytes + 16)) return r;
+    const size_t pix_bytes = sizeof(uint32_t) * (size_t)size * size, pix_al = (pix_bytes + 15) & ~(size_t)15;
+    if (int r = tool_scratch(w, pix_al + 16)) return r;
     uint32_t* d_pix = (uint32_t*)w->tool_scratch;
-    int* d_n = (int*)((char*)w->tool_scratch + ((pix_bytes + 15) & ~(size_t)15));
-    CKT(cudaMemsetAsync(w->tool_scratch, 0, ((pix_bytes + 15) & ~(size_t)15) + 16, w->stream));
-    tool_pickaxe_kernel<<<(span * span + 127) / 128, 128, 0, w->stream>>>(w->p, w->ctx->d_tabs, w->W, w->H, x, y - w->y_off, break_size, d_pix, d_n);
+    int* d_n = (int*)((char*)w->tool_scratch + pix_al);
+    CKT(cudaMemsetAsync(w->tool_scratch, 0, pix_al + 16, w->stream));
+    if (multi)
+        if (int r = strip_refresh(w, w->stream, STRIP_GHOST)) return r;
+    tool_pickaxe_kernel<<<(span * span + 127) / 128, 128, 0, w->stream>>>(w->p, w->ctx->d_tabs, w->W, w->H, x, y - w->y_off, break_size, d_pix, d_n,
+                                                                           multi ? w->own_lo - w->y_off : 0, multi ? w->own_hi - w->y_off : w->H);
     CKT(cudaGetLastError());
     w->ctx->launches += 1;
+    if (multi)
+        if (int r = strip_allreduce_u32(w, (unsigned int*)w->tool_scratch, pix_al / 4 + 1, w->stream)) return r;
     CKT(cudaMemcpyAsync(pixels_out, d_pix, pix_bytes, cudaMemcpyDeviceToHost, w->stream));
     CKT(cudaMemcpyAsync(n_out, d_n, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
     CKT(cudaStreamSynchronize(w->stream));
-    return tool_wake(w, x - 1, y - 1, x + span + 1, y + span + 1);
+    return tool_wake(w, x - 1, y - 1 - w->y_off, x + span + 1, y + span + 1 - w->y_off);
 }
 
 extern "C" FSE_API int fse_tool_hammer(fse_world* w, int32_t hammer_x, int32_t hammer_y, int32_t x, int32_t y, int32_t sand_mat, uint32_t tick, uint32_t seed,
                                        fse_hammer_result* out) {
-    if (int r = tool_common(w, "fse_tool_hammer")) return r;
+    // multi-rank strips: the crack is walked in order, so ONE rank runs it — the one that holds the middle row of its box — and the
+    // box travels to the neighbours it reaches into afterwards; every rank gets the same result
+    if (int r = tool_common(w, "fse_tool_hammer", true)) return r;
     if (!out || sand_mat < 0 || sand_mat >= w->ctx->h_tabs.n) return fail(FSE_EINVAL, "fse_tool_hammer: bad argument");
     const int dx = hammer_x - x, dy = hammer_y - y;
     if (std::abs(dx) > 4096 || std::abs(dy) > 4096) return fail(FSE_EINVAL, "fse_tool_hammer: crack longer than 4096 cells");
@@ -493,17 +505,38 @@ extern "C" FSE_API int fse_tool_hammer(fse_world* w, int32_t hammer_x, int32_t h
         px = sx;
         py = sy;
     }
+    const bool multi = w->strip && w->ctx->nranks > 1;
+    // the crack runs from the hammer AWAY from (x, y): hammer .. hammer + (dx, dy), segment ends jittered by one cell
+    const int bx0 = std::min(hammer_x, hammer_x + dx) - 4, by0 = std::min(hammer_y, hammer_y + dy) - 4, bx1 = std::max(hammer_x, hammer_x + dx) + 4,
+              by1 = std::max(hammer_y, hammer_y + dy) + 4;
+    int runner = w->ctx->rank;
+    if (multi) {
+        if (int r = strip_runner_of_rows(w, by0, by1, "fse_tool_hammer", &runner)) return r;
+        if (int r = strip_refresh(w, w->stream, STRIP_GHOST)) return r;
+        const long long shift = (long long)w->y_off * w->W;  // cells and segment starts in the runner's local rows
+        for (long long& c : pts) c = c >= 0 ? c - shift : c;
+        for (size_t i = 1; i < seg_start.size(); i += 2) seg_start[i] -= w->y_off;
+    }
     const size_t b0 = pts.size() * sizeof(long long), b1 = seg_off.size() * sizeof(int), b2 = seg_start.size() * sizeof(int);
     const size_t o1 = (b0 + 15) & ~(size_t)15, o2 = o1 + ((b1 + 15) & ~(size_t)15), o3 = o2 + ((b2 + 15) & ~(size_t)15);
     if (int r = tool_scratch(w, o3 + 16)) return r;
     char* base = (char*)w->tool_scratch;
-    if (b0) CKT(cudaMemcpyAsync(base, pts.data(), b0, cudaMemcpyHostToDevice, w->stream));
-    CKT(cudaMemcpyAsync(base + o1, seg_off.data(), b1, cudaMemcpyHostToDevice, w->stream));
-    CKT(cudaMemcpyAsync(base + o2, seg_start.data(), b2, cudaMemcpyHostToDevice, w->stream));
-    tool_hammer_kernel<<<1, 32, 0, w->stream>>>(w->p, w->ctx->d_tabs, w->W, w->H, (const long long*)base, (const int*)(base + o1), (const int*)(base + o2), nSegments,
-                                               sand_mat, (int*)(base + o3));
-    CKT(cudaGetLastError());
-    w->ctx->launches += 1;
+    CKT(cudaMemsetAsync(base + o3, 0, 16, w->stream));
+    if (runner == w->ctx->rank) {
+        if (b0) CKT(cudaMemcpyAsync(base, pts.data(), b0, cudaMemcpyHostToDevice, w->stream));
+        CKT(cudaMemcpyAsync(base + o1, seg_off.data(), b1, cudaMemcpyHostToDevice, w->stream));
+        CKT(cudaMemcpyAsync(base + o2, seg_start.data(), b2, cudaMemcpyHostToDevice, w->stream));
+        tool_hammer_kernel<<<1, 32, 0, w->stream>>>(w->p, w->ctx->d_tabs, w->W, w->H, (const long long*)base, (const int*)(base + o1), (const int*)(base + o2), nSegments,
+                                                   sand_mat, (int*)(base + o3), w->y_off);
+        CKT(cudaGetLastError());
+        w->ctx->launches += 1;
+    }
+    if (multi) {
+        std::vector<int4> rect[4];
+        strip_rects_of_box(w, runner, bx0, by0, bx1, by1, rect);
+        if (int r = strip_push_rects(w, rect, w->stream)) return r;
+        if (int r = strip_allreduce_u32(w, (unsigned int*)(base + o3), 4, w->stream)) return r;  // the others contribute zeros
+    }
     int res[4];
     CKT(cudaMemcpyAsync(res, base + o3, sizeof res, cudaMemcpyDeviceToHost, w->stream));
     CKT(cudaStreamSynchronize(w->stream));
@@ -511,7 +544,7 @@ extern "C" FSE_API int fse_tool_hammer(fse_world* w, int32_t hammer_x, int32_t h
     out->end_y = res[1];
     out->n_changed = res[2];
     out->broke = res[3];
-    return tool_wake(w, std::min(hammer_x, hammer_x + dx) - 4, std::min(hammer_y, hammer_y + dy) - 4, std::max(hammer_x, hammer_x + dx) + 4, std::max(hammer_y, hammer_y + dy) + 4);
+    return tool_wake(w, bx0, by0 - w->y_off, bx1, by1 - w->y_off);
 }
 
 extern "C" FSE_API int fse_tool_vacuum(fse_world* w, int32_t wcx, int32_t wcy, int32_t wmx, int32_t wmy, uint32_t tick, uint32_t seed, fse_vacuum_result* out) {
@@ -550,16 +583,22 @@ extern "C" FSE_API int fse_tool_vacuum(fse_world* w, int32_t wcx, int32_t wcy, i
 }
 
 extern "C" FSE_API int fse_particles_vacuum_pull(fse_world* w, float target_x, float target_y, int32_t* n_collected) {
-    if (int r = tool_common(w, "fse_particles_vacuum_pull")) return r;
+    // multi-rank strips: every rank pulls the particles of its own pool, the collected ones are summed
+    if (int r = tool_common(w, "fse_particles_vacuum_pull", true)) return r;
+    const bool multi = w->strip && w->ctx->nranks > 1;
     int64_t n = 0;
     if (int r = fse_particles_count(w, &n)) return r;
     if (n_collected) *n_collected = 0;
-    if (n == 0) return FSE_OK;
+    if (n == 0 && !multi) return FSE_OK;
     if (int r = tool_scratch(w, 64)) return r;
     CKT(cudaMemsetAsync(w->tool_scratch, 0, 16, w->stream));
-    vacuum_pull_kernel<<<(unsigned)((n + 127) / 128), 128, 0, w->stream>>>(w->pbuf, (unsigned int)n, target_x, target_y, (int*)w->tool_scratch);
-    CKT(cudaGetLastError());
-    w->ctx->launches += 1;
+    if (n) {
+        vacuum_pull_kernel<<<(unsigned)((n + 127) / 128), 128, 0, w->stream>>>(w->pbuf, (unsigned int)n, target_x, target_y, (int*)w->tool_scratch);
+        CKT(cudaGetLastError());
+        w->ctx->launches += 1;
+    }
+    if (multi)  // every rank takes part, also one whose pool is empty
+        if (int r = strip_allreduce_u32(w, (unsigned int*)w->tool_scratch, 1, w->stream)) return r;
     if (n_collected) {
         CKT(cudaMemcpyAsync(n_collected, w->tool_scratch, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
         CKT(cudaStreamSynchronize(w->stream));

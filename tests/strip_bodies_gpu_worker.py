@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import falling_sand_engine_b200 as fse  # noqa: E402
 from falling_sand_engine_b200 import materials as M, strips, worldgen as G  # noqa: E402
-from tests.strip_bodies_scene import scene  # noqa: E402
+from tests.strip_bodies_scene import scene, stone_blocks, tool_calls, run_tool  # noqa: E402
 
 
 def main():
@@ -25,12 +25,19 @@ def main():
     lo, hi = sw.owned_rows()
     sw.write_rect(0, lo, G.mixed_band(table, W, H, lo, hi - lo, seed=21, air_frac=0.6, blob=48))
     bodies, xf = scene(table, W, H, world)
+    for (x0, y0, cells) in stone_blocks(table, H, world):  # something for the pickaxe and the hammer to work on, right on the cuts
+        sw.write_rect(x0, y0, cells)
     sw.bodies_upload(bodies)
-    fbs = []
+    fbs, tools = [], []
     for t in range(ticks):
         fbs.append(sw.bodies_raster(xf, tick=t))
         sw.tick(t, seed=1337)
+        if t == 1:  # tools across the cuts: every rank makes the call and gets the same answer
+            for call in tool_calls(H, world, t):
+                tools.append(np.asarray(run_tool(sw, call), dtype=np.int64).reshape(-1))
         sw.particles_tick()
+        if t == 3:
+            tools.append(np.array([sw.particles_vacuum_pull(500.0, 700.0)], dtype=np.int64))
         fe, need = sw.bodies_erase(xf)
         fbs.append(fe)
         xf[:, 1] += 1.5   # the host's Box2D step: bodies drift down (some change strips on the way) and turn
@@ -39,6 +46,7 @@ def main():
     np.save(f"{out}.rank{rank}.npy", sw.read_owned())
     np.save(f"{out}.parts{rank}.npy", sw.particles_read())
     np.save(f"{out}.fb{rank}.npy", np.stack(fbs))
+    np.save(f"{out}.tools{rank}.npy", np.concatenate(tools))
     np.save(f"{out}.tiles{rank}.npy", np.concatenate([sw.bodies_read(i).reshape(-1) for i in range(len(bodies))]))
     dist.barrier()
     sw.close()

@@ -3,6 +3,7 @@ just above it, one just below it, and a pair that overlaps ACROSS the cut (cross
 import numpy as np
 
 from falling_sand_engine_b200 import strips
+from falling_sand_engine_b200 import worldgen as G
 from tests.test_bridge_cpu import make_body
 
 
@@ -27,3 +28,38 @@ def scene(table, W, H, nranks):
         add(x0 + 306, cut + 1, 0.1, 18, 16, fill=1.0)
         add(x0 + 480, cut - 9, 1.2, 14, 14)     # drifts across the cut during the run: its runner changes
     return bodies, np.array(xf, dtype=np.float32)
+
+
+def _cuts(H, nranks):
+    return [strips.strip_layout(H, r, nranks)[0] for r in range(1, nranks)]
+
+
+def stone_blocks(table, H, nranks):
+    """(x0, y0, cells) of an 80 x 44 STONE block across every cut (what the pickaxe and the hammer of tool_calls hit)."""
+    ids = G._names(table)
+    out = []
+    for k, cut in enumerate(_cuts(H, nranks)):
+        mat = np.full((44, 80), ids["STONE"], dtype=np.uint16)
+        out.append((60, cut - 22, G.cells_from_mat(table, mat, 60, cut - 22, 5 + k)))
+    return out
+
+
+def tool_calls(H, nranks, tick):
+    """Pickaxe circles and hammer cracks whose boxes cross the cuts."""
+    calls = []
+    for cut in _cuts(H, nranks):
+        calls.append(("pickaxe", 70, cut - 9, 19.0))
+        calls.append(("hammer", 100, cut - 12, 90, cut - 24, tick))   # the crack runs away from the target: down across the cut
+        calls.append(("hammer", 126, cut + 10, 134, cut + 22, tick))  # ... and up across it
+    return calls
+
+
+def run_tool(world_or_oracle, call, oracle_mod=None):
+    """Runs one call of tool_calls on a (Strip)World, or on an OracleWorld through oracle/pyoracle; returns the numbers it reports."""
+    kind = call[0]
+    if kind == "pickaxe":
+        pix, n = (oracle_mod.tool_pickaxe(world_or_oracle, *call[1:]) if oracle_mod else world_or_oracle.tool_pickaxe(*call[1:]))
+        return np.concatenate([np.asarray(pix, dtype=np.int64).reshape(-1), [int(n)]])
+    hx, hy, x, y, tick = call[1:]
+    res = (oracle_mod.tool_hammer(world_or_oracle, hx, hy, x, y, tick=tick) if oracle_mod else world_or_oracle.tool_hammer(hx, hy, x, y, tick=tick))
+    return np.asarray(res, dtype=np.int64).reshape(-1)

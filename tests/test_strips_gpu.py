@@ -73,7 +73,7 @@ def test_strip_bodies_match_oracle(oracle, table, tmp_path, nranks):
     if _ngpu() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
     from oracle import pyoracle as O
-    from tests.strip_bodies_scene import scene
+    from tests.strip_bodies_scene import scene, stone_blocks, tool_calls, run_tool
     W, H, ticks = 1024, 1536, 6
     out = str(tmp_path / "sb")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
@@ -84,16 +84,24 @@ def test_strip_bodies_match_oracle(oracle, table, tmp_path, nranks):
     ow = oracle.OracleWorld(W, H, table)
     ow.write_rect(0, 0, G.mixed_band(table, W, H, 0, H, seed=21, air_frac=0.6, blob=48))
     bodies, xf = scene(table, W, H, nranks)
+    for (x0, y0, cells) in stone_blocks(table, H, nranks):
+        ow.write_rect(x0, y0, cells)
     ob = [b.copy() for b in bodies]
-    fbs = []
+    fbs, tools = [], []
     for t in range(ticks):
         fbs.append(O.bodies_raster(ow, ob, xf, tick=t))
         ow.tick(t, seed=1337)
+        if t == 1:
+            for call in tool_calls(H, nranks, t):
+                tools.append(np.asarray(run_tool(ow, call, O), dtype=np.int64).reshape(-1))
         ow.particles_tick()
+        if t == 3:
+            tools.append(np.array([O.particles_vacuum_pull(ow, 500.0, 700.0)], dtype=np.int64))
         fbs.append(O.bodies_erase(ow, ob, xf))
         xf[:, 1] += 1.5
         xf[:, 2] += 0.05
-    fbs = np.stack(fbs)
+    fbs, tools = np.stack(fbs), np.concatenate(tools)
+    assert (tools[:-1] != 0).sum() > 50  # the pickaxe took pixels, the hammers cracked stone
     assert fbs[:, :, 2].sum() > 0 and (fbs[0::2, :, 0] + fbs[0::2, :, 1]).sum() > 0  # pixels were placed and grains / liquid were displaced
     ref = ow.read_all()
     tiles = np.concatenate([b.reshape(-1) for b in ob])
@@ -101,6 +109,7 @@ def test_strip_bodies_match_oracle(oracle, table, tmp_path, nranks):
     for k in range(nranks):
         lo, hi = strips.strip_layout(H, k, nranks)[:2]
         assert np.array_equal(fbs, np.load(f"{out}.fb{k}.npy")), f"feedback on rank {k}"
+        assert np.array_equal(tools, np.load(f"{out}.tools{k}.npy")), f"tool results on rank {k}"
         assert tiles.tobytes() == np.load(f"{out}.tiles{k}.npy").tobytes(), f"body tiles on rank {k}"
         Hh.assert_cells_equal(ref[lo:hi], np.load(f"{out}.rank{k}.npy"), f"strip {k}/{nranks}")
         parts.append(np.load(f"{out}.parts{k}.npy"))
