@@ -640,10 +640,12 @@ extern "C" FSE_API int fse_flood_component(fse_world* w, int32_t x, int32_t y, i
 }
 
 // world::physicsCheck(x, y) (world.cpp:3330-3411) as one call: flood, then delete (1..10 cells) or cut out into a body (11..1000).
-extern "C" FSE_API int fse_physics_check(fse_world* w, int32_t x, int32_t y, fse_physcheck_result* out, fse_cell* tiles_out, int32_t cap_tiles) {
-    if (!w || !out) return fail(FSE_EINVAL, "fse_physics_check: null argument");
-    if (w->strip && w->ctx->nranks > 1) return fail(FSE_ESTATE, "fse_physics_check: not available on multi-rank strips");
+// d_tiles_out: where the cut-out tiles lie on the device afterwards (action 2).  strip_edges: fail when a component of <= 1000 cells touches a
+// row edge of this rank's window that is not an edge of the world (the flood could not follow it there)
+static int physics_check_local(fse_world* w, int32_t x, int32_t y, fse_physcheck_result* out, fse_cell* tiles_out, int32_t cap_tiles, fse_cell** d_tiles_out,
+                               bool strip_edges) {
     memset(out, 0, sizeof *out);
+    *d_tiles_out = nullptr;
     if (x < 0 || y < w->y_off || x >= w->W || y >= w->y_off + w->H) return FSE_OK;
     CK(cudaSetDevice(w->ctx->device));
     const int cap = 1000;
@@ -667,6 +669,9 @@ extern "C" FSE_API int fse_physics_check(fse_world* w, int32_t x, int32_t y, fse
         bb[0] = std::min(bb[0], cx); bb[1] = std::min(bb[1], cy); bb[2] = std::max(bb[2], cx); bb[3] = std::max(bb[3], cy);
     }
     out->x = bb[0]; out->y = bb[1] + w->y_off; out->w = bb[2] - bb[0] + 1; out->h = bb[3] - bb[1] + 1;
+    if (strip_edges && ((w->y_off > 0 && bb[1] == 0) || (w->y_off + w->H < w->Hglobal && bb[3] == w->H - 1)))
+        return fail(FSE_ESTATE, "fse_physics_check: the component at (%d, %d) reaches the edge of the rows rank %d holds (rows %d..%d); nothing was changed", x, y,
+                    w->ctx->rank, w->y_off, w->y_off + w->H - 1);
     const bool body = n > 10;
     fse_cell* d_tiles = nullptr;
     const size_t area = (size_t)out->w * out->h;
@@ -696,5 +701,60 @@ extern "C" FSE_API int fse_physics_check(fse_world* w, int32_t x, int32_t y, fse
         CK(cudaStreamSynchronize(w->stream));
     }
     out->action = body ? 2 : 1;
+    *d_tiles_out = d_tiles;
     return FSE_OK;
+}
+
+extern "C" FSE_API int fse_physics_check(fse_world* w, int32_t x, int32_t y, fse_physcheck_result* out, fse_cell* tiles_out, int32_t cap_tiles) {
+    if (!w || !out) return fail(FSE_EINVAL, "fse_physics_check: null argument");
+    fse_cell* d_tiles = nullptr;
+    if (!(w->strip && w->ctx->nranks > 1)) return physics_check_local(w, x, y, out, tiles_out, cap_tiles, &d_tiles, false);
+    // multi-rank strips: every rank makes the call; the owner of row y floods, deletes or cuts on its rows + ghost rows (refreshed first), the
+    // result and the cut-out tiles are summed over the ranks (the others contribute zeros), the component's box travels to the neighbours
+    memset(out, 0, sizeof *out);
+    if (x < 0 || y < 0 || x >= w->W || y >= w->Hglobal) return FSE_OK;
+    CK(cudaSetDevice(w->ctx->device));
+    int runner = 0;
+    if (int r = strip_runner_of_rows(w, y, y, nullptr, &runner)) return r;
+    if (int r = strip_refresh(w, w->stream, STRIP_GHOST)) return r;
+    int share[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (runner == w->ctx->rank) {
+        const int rc = physics_check_local(w, x, y, out, tiles_out, cap_tiles, &d_tiles, true);
+        share[0] = out->count; share[1] = out->action; share[2] = out->x; share[3] = out->y; share[4] = out->w; share[5] = out->h; share[6] = rc;
+    }
+    unsigned int* d_share = nullptr;  // (a small allocation of its own: the scratch holds the runner's tiles)
+    CK(cudaMalloc((void**)&d_share, sizeof share));
+    cudaError_t ce = cudaMemcpyAsync(d_share, share, sizeof share, cudaMemcpyHostToDevice, w->stream);
+    int rr = ce == cudaSuccess ? strip_allreduce_u32(w, d_share, 8, w->stream) : fail(FSE_ECUDA, "fse_physics_check: %s", cudaGetErrorString(ce));
+    if (!rr) {
+        ce = cudaMemcpyAsync(share, d_share, sizeof share, cudaMemcpyDeviceToHost, w->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(w->stream);
+        if (ce != cudaSuccess) rr = fail(FSE_ECUDA, "fse_physics_check: %s", cudaGetErrorString(ce));
+    }
+    cudaFree(d_share);
+    if (rr) return rr;
+    if (share[6]) {  // the runner refused (tile buffer too small, component at the edge of its rows): every rank reports it, nothing was changed
+        out->count = share[0]; out->x = share[2]; out->y = share[3]; out->w = share[4]; out->h = share[5];
+        if (runner == w->ctx->rank) return share[6];  // the thread-local message is the runner's own
+        return fail(share[6], "fse_physics_check: rank %d, which holds row %d, refused the call (component of %d cells, box %d x %d)", runner, y, share[0], share[4], share[5]);
+    }
+    out->count = share[0]; out->action = share[1]; out->x = share[2]; out->y = share[3]; out->w = share[4]; out->h = share[5];
+    if (out->action == 0) return FSE_OK;
+    if (out->action == 2) {  // the new body's tiles on every rank
+        const size_t area = (size_t)out->w * out->h, words = area * (sizeof(fse_cell) / 4);
+        if (runner != w->ctx->rank) {
+            if (!tiles_out || (int64_t)area > (int64_t)cap_tiles) return fail(FSE_EINVAL, "fse_physics_check: cap_tiles differs between the ranks");
+            CK(grow_scratch(w, area * sizeof(fse_cell)));
+            d_tiles = (fse_cell*)w->outline_scratch;
+            CK(cudaMemsetAsync(d_tiles, 0, area * sizeof(fse_cell), w->stream));
+        }
+        if (int r = strip_allreduce_u32(w, (unsigned int*)d_tiles, words, w->stream)) return r;
+        if (runner != w->ctx->rank) {
+            CK(cudaMemcpyAsync(tiles_out, d_tiles, area * sizeof(fse_cell), cudaMemcpyDeviceToHost, w->stream));
+            CK(cudaStreamSynchronize(w->stream));
+        }
+    }
+    std::vector<int4> rect[4];
+    strip_rects_of_box(w, runner, out->x, out->y, out->x + out->w - 1, out->y + out->h - 1, rect);
+    return strip_push_rects(w, rect, w->stream);
 }

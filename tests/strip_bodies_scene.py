@@ -41,6 +41,11 @@ def stone_blocks(table, H, nranks):
     for k, cut in enumerate(_cuts(H, nranks)):
         mat = np.full((44, 80), ids["STONE"], dtype=np.uint16)
         out.append((60, cut - 22, G.cells_from_mat(table, mat, 60, cut - 22, 5 + k)))
+        # two loose pieces of stone in a pocket of AIR, both lying across the cut: 30 cells (physicsCheck cuts it out into a body) and 6 (deleted)
+        mat = np.full((30, 44), ids["AIR"], dtype=np.uint16)
+        mat[12:17, 12:18] = ids["STONE"]
+        mat[14:16, 30:33] = ids["STONE"]
+        out.append((8, cut - 15, G.cells_from_mat(table, mat, 8, cut - 15, 9 + k)))
     return out
 
 
@@ -51,6 +56,9 @@ def tool_calls(H, nranks, tick):
         calls.append(("pickaxe", 70, cut - 9, 19.0))
         calls.append(("hammer", 100, cut - 12, 90, cut - 24, tick))   # the crack runs away from the target: down across the cut
         calls.append(("hammer", 126, cut + 10, 134, cut + 22, tick))  # ... and up across it
+        calls.append(("physcheck", 22, cut - 1))   # the 30-cell piece: probed in the upper strip, reaches into the lower one
+        calls.append(("physcheck", 39, cut))       # the 6-cell crumb: probed in the lower strip
+        calls.append(("physcheck", 45, cut + 8))   # AIR: nothing
     return calls
 
 
@@ -60,6 +68,10 @@ def run_tool(world_or_oracle, call, oracle_mod=None):
     if kind == "pickaxe":
         pix, n = (oracle_mod.tool_pickaxe(world_or_oracle, *call[1:]) if oracle_mod else world_or_oracle.tool_pickaxe(*call[1:]))
         return np.concatenate([np.asarray(pix, dtype=np.int64).reshape(-1), [int(n)]])
+    if kind == "physcheck":
+        count, action, box, tiles = (oracle_mod.physics_check(world_or_oracle, *call[1:]) if oracle_mod else world_or_oracle.physics_check(*call[1:]))
+        t = np.zeros(0, dtype=np.int64) if tiles is None else np.frombuffer(np.ascontiguousarray(tiles).tobytes(), dtype=np.uint8).astype(np.int64)
+        return np.concatenate([np.array([count, action, *box], dtype=np.int64), t])
     hx, hy, x, y, tick = call[1:]
     res = (oracle_mod.tool_hammer(world_or_oracle, hx, hy, x, y, tick=tick) if oracle_mod else world_or_oracle.tool_hammer(hx, hy, x, y, tick=tick))
     return np.asarray(res, dtype=np.int64).reshape(-1)
