@@ -713,7 +713,6 @@ struct StripPlan {
     std::vector<int4> rect[4];  // up send, up recv, down send, down recv (x0, y0 in local rows, w, h)
 };
 static int plan_strip_bodies(fse_world* w, const fse_bodies* B, const fse_xform* xf, int n, StripPlan& P, const char* who) {
-    const int nranks = w->ctx->nranks, me = w->ctx->rank, Hg = w->Hglobal, W = w->W;
     std::vector<int4> box(n);
     for (int b = 0; b < n; b++) {  // the box of bodies_aabb_kernel, in global rows
         const float sn = std::sin(xf[b].angle), cs = std::cos(xf[b].angle);
@@ -729,52 +728,9 @@ static int plan_strip_bodies(fse_world* w, const fse_bodies* B, const fse_xform*
         y0 = std::fmax(std::fmin(y0, lim), -lim); y1 = std::fmax(std::fmin(y1, lim), -lim);
         box[b] = make_int4((int)std::floor(x0) - 3, (int)std::floor(y0) - 3, (int)std::ceil(x1) + 3, (int)std::ceil(y1) + 3);
     }
-    // groups of bodies whose boxes overlap (transitively); the root of a group is its lowest body index
-    std::vector<int> parent(n);
-    for (int i = 0; i < n; i++) parent[i] = i;
-    auto find = [&](int i) {
-        while (parent[i] != i) i = parent[i] = parent[parent[i]];
-        return i;
-    };
-    std::vector<int> order(n);
-    for (int i = 0; i < n; i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](int a_, int b_) { return box[a_].y < box[b_].y; });
-    std::vector<int> active;
-    for (int oi = 0; oi < n; oi++) {
-        const int i = order[oi];
-        size_t keep = 0;
-        for (size_t k = 0; k < active.size(); k++) {
-            const int j = active[k];
-            if (box[j].w < box[i].y) continue;  // ends above: never overlaps anything that starts later
-            active[keep++] = j;
-            if (box[j].x <= box[i].z && box[i].x <= box[j].z) {
-                const int ri = find(i), rj = find(j);
-                if (ri != rj) parent[ri > rj ? ri : rj] = ri > rj ? rj : ri;
-            }
-        }
-        active.resize(keep);
-        active.push_back(i);
-    }
-    P.exec.assign(n, 0);
-    for (int b = 0; b < n; b++) {
-        const int root = find(b);
-        int e = 0;
-        if (root == b) {
-            if (int r = strip_runner_of_rows(w, box[b].y, box[b].w, nullptr, &e)) return r;  // owner of the middle row; the fit is checked per body below
-        } else {
-            e = P.exec[root];  // root < b: already known
-        }
-        P.exec[b] = e;
-        int hlo, hhi;
-        strip_rows_of(Hg, e, nranks, nullptr, nullptr, &hlo, &hhi);
-        const int ya = box[b].y < 0 ? 0 : box[b].y, yb = box[b].w >= Hg ? Hg - 1 : box[b].w;
-        if (ya <= yb && (ya < hlo || yb >= hhi))
-            return fail(FSE_ESTATE, "%s: body %d (rows %d..%d, with the bodies it overlaps) does not fit the rows rank %d holds (%d..%d): on multi-rank strips a group of "
-                        "overlapping bodies must lie within %d rows of one strip", who, b, ya, yb, e, hlo, hhi - 1, STRIP_GHOST);
-    }
+    if (int r = strip_group_runners(w, box, who, "body", P.exec)) return r;
     for (int q = 0; q < 4; q++) P.rect[q].clear();
     for (int b = 0; b < n; b++) strip_rects_of_box(w, P.exec[b], box[b].x, box[b].y, box[b].z, box[b].w, P.rect);
-    (void)me; (void)W;
     return FSE_OK;
 }
 

@@ -14,6 +14,7 @@
 // link-time NCCL dependency and never mixes two NCCL builds in one process.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "fse_internal.hpp"
@@ -277,6 +278,52 @@ int strip_runner_of_rows(fse_world* w, int ya, int yb, const char* who, int* exe
         if (a <= b && (a < hlo || b >= hhi))
             return fail(FSE_ESTATE, "%s: rows %d..%d do not fit the rows rank %d holds (%d..%d): on multi-rank strips the call must stay within %d rows of one strip",
                         who, a, b, e, hlo, hhi - 1, STRIP_GHOST);
+    }
+    return FSE_OK;
+}
+// Runners of n edits with boxes (x0, y0, x1, y1; global, inclusive) that are applied in index order: boxes that overlap (transitively)
+// form a group that one rank must run — the order between them matters — and a group is run by the owner of the middle row of its
+// lowest-index box; edits that do not overlap commute.  Fails when a box does not fit the rows its runner holds.
+int strip_group_runners(fse_world* w, const std::vector<int4>& box, const char* who, const char* what, std::vector<int>& exec) {
+    const int n = (int)box.size(), nranks = w->ctx->nranks, Hg = w->Hglobal;
+    std::vector<int> parent(n), order(n), active;
+    for (int i = 0; i < n; i++) parent[i] = order[i] = i;
+    auto find = [&](int i) {
+        while (parent[i] != i) i = parent[i] = parent[parent[i]];
+        return i;
+    };
+    std::sort(order.begin(), order.end(), [&](int a_, int b_) { return box[a_].y < box[b_].y; });
+    for (int oi = 0; oi < n; oi++) {
+        const int i = order[oi];
+        size_t keep = 0;
+        for (size_t k = 0; k < active.size(); k++) {
+            const int j = active[k];
+            if (box[j].w < box[i].y) continue;  // ends above: never overlaps anything that starts later
+            active[keep++] = j;
+            if (box[j].x <= box[i].z && box[i].x <= box[j].z) {
+                const int ri = find(i), rj = find(j);
+                if (ri != rj) parent[ri > rj ? ri : rj] = ri > rj ? rj : ri;  // the root of a group is its lowest index
+            }
+        }
+        active.resize(keep);
+        active.push_back(i);
+    }
+    exec.assign(n, 0);
+    for (int b = 0; b < n; b++) {
+        const int root = find(b);
+        int e = 0;
+        if (root == b) {
+            if (int r = strip_runner_of_rows(w, box[b].y, box[b].w, nullptr, &e)) return r;
+        } else {
+            e = exec[root];  // root < b: already known
+        }
+        exec[b] = e;
+        int hlo, hhi;
+        strip_rows_of(Hg, e, nranks, nullptr, nullptr, &hlo, &hhi);
+        const int ya = box[b].y < 0 ? 0 : box[b].y, yb = box[b].w >= Hg ? Hg - 1 : box[b].w;
+        if (ya <= yb && (ya < hlo || yb >= hhi))
+            return fail(FSE_ESTATE, "%s: %s %d (rows %d..%d, with the ones it overlaps) does not fit the rows rank %d holds (%d..%d): on multi-rank strips a group of "
+                        "overlapping ones must lie within %d rows of one strip", who, what, b, ya, yb, e, hlo, hhi - 1, STRIP_GHOST);
     }
     return FSE_OK;
 }

@@ -36,6 +36,12 @@ struct EntArgs {
     long long* objdel;         // indices stamped since the last fse_object_delete
     unsigned int* objdel_cnt;
     unsigned int objdel_cap;
+    // strip worlds: the kernels work in GLOBAL rows — W x H is the whole world, the plane pointers are moved back by the rows above this
+    // rank's window, so (sy * W + sx) addresses the window where it holds the row.  [ylo, yhi): rows of the window, [own_lo, own_hi): rows
+    // this rank owns (their kicked grains are its particles), exec[i] (null on one world): the rank that runs entity i
+    int ylo, yhi, own_lo, own_hi;
+    const int* exec;
+    int rank;
 };
 
 __device__ __forceinline__ uint64_t entity_particle_id(uint32_t tick, int kind, int x, int y) {
@@ -99,6 +105,11 @@ __global__ void __launch_bounds__(ENT_THREADS) entities_tick_kernel(EntArgs a) {
         if (S.tw > 0 && lx >= 0 && ly >= 0 && lx < S.tw && ly < S.th) ent_tile[ly * S.tw + lx] = P_AIR;
     };
     for (int ei = 0; ei < a.n; ei++) {
+        if (a.exec && a.exec[ei] != a.rank) {  // strips: another rank runs this entity; its record here becomes zeros for the sum over the ranks
+            uint32_t* z = reinterpret_cast<uint32_t*>(&a.ents[ei]);
+            for (int q = tid; q < (int)(sizeof(fse_entity) / 4); q += ENT_THREADS) z[q] = 0u;
+            continue;
+        }
         if (tid == 0) {
             S.e = a.ents[ei];
             S.e.destroy = 0;
@@ -259,11 +270,13 @@ __global__ void __launch_bounds__(ENT_THREADS) entities_stamp_kernel(EntArgs a) 
             const int tx = c / pl.hh, ty = c % pl.hh;
             const int wx = (int)(tx + pl.x + a.lzx), wy = (int)(ty + pl.y + a.lzy);
             if (wx < 0 || wy < 0 || wx >= a.W || wy >= a.H) continue;
+            if (wy < a.ylo || wy >= a.yhi) continue;  // strips: a rank stamps the cells of its window (cells are independent), ghost rows included
             const size_t g = (size_t)wy * a.W + wx;
             const int t = a.T->phys[a.p.mat[g]];
             if (t != P_AIR && t != P_SAND && t != P_SOUP) continue;
             uint8_t flg = a.p.flg[g] & F_DIRTY;
-            if (t != P_AIR) {
+            if (t != P_AIR && !(wy >= a.own_lo && wy < a.own_hi)) flg = F_DIRTY;  // a ghost cell: its owner makes the particle
+            else if (t != P_AIR) {
                 const uint32_t cb = rng_cell(a.rkey, wx, wy);
                 const float px = (float)(wx + (int)(rng_draw(cb, S_STAMP_X) % 3) - 1 - pl.vx);
                 const float py = (float)(wy - fabsf(pl.vy));
@@ -298,6 +311,8 @@ struct EntityBufs {
     int cap = 0;
     long long* d_objdel = nullptr;
     unsigned int* d_cnt = nullptr;
+    int* d_exec = nullptr;                    // strips: runner of every entity of the current fse_entities_tick
+    int exec_cap = 0;
     unsigned int objdel_cap = 0;
     unsigned int stamped = 0;                 // upper bound of the entries in d_objdel
     std::vector<fse_rect> rects;              // boxes stamped since the last delete (active-chunk wake-up)
@@ -309,6 +324,7 @@ void entities_free(fse_world* w) {
     cudaFree(b->d_ents);
     cudaFree(b->d_objdel);
     cudaFree(b->d_cnt);
+    cudaFree(b->d_exec);
     delete b;
     w->entity_bufs = nullptr;
 }
@@ -325,7 +341,6 @@ using namespace fse;
 
 static int entity_setup(fse_world* w, const fse_entity* ents, int32_t n, const char* who, EntityBufs** out) {
     if (!w || (!ents && n > 0) || n < 0) return fail(FSE_EINVAL, "%s: bad argument", who);
-    if (w->strip && w->ctx->nranks > 1) return fail(FSE_ESTATE, "%s: not available on multi-rank strips", who);
     for (int i = 0; i < n; i++)
         if (ents[i].hw < 0 || ents[i].hh < 0 || ents[i].hw > 4096 || ents[i].hh > 4096 || !std::isfinite(ents[i].x) || !std::isfinite(ents[i].y) ||
             !std::isfinite(ents[i].vx) || !std::isfinite(ents[i].vy))
@@ -357,6 +372,14 @@ static void entity_args(fse_world* w, EntityBufs* b, int32_t n, float lx, float 
     a->T = w->ctx->d_tabs;
     a->W = w->W;
     a->H = w->H;
+    a->ylo = 0; a->yhi = w->H; a->own_lo = 0; a->own_hi = w->H;
+    if (w->strip) {  // global rows (see EntArgs)
+        const size_t back = (size_t)w->y_off * w->W;
+        a->p.mat -= back; a->p.flg -= back; a->p.stl -= back; a->p.tmp -= back; a->p.col -= back; a->p.fl -= back; a->p.fd -= back;
+        a->H = w->Hglobal;
+        a->ylo = w->y_off; a->yhi = w->y_off + w->H; a->own_lo = w->own_lo; a->own_hi = w->own_hi;
+    }
+    a->rank = w->ctx->rank;
     a->ents = b->d_ents;
     a->n = n;
     a->lzx = lx;
@@ -386,19 +409,50 @@ extern "C" FSE_API int fse_entities_tick(fse_world* w, fse_entity* ents, int32_t
     }
     EntArgs a;
     entity_args(w, b, n, load_x, load_y, tick, seed, &a);
-    for (int i = 0; i < n; i++) {  // active-chunk tracking: whatever a sweep can reach is awake afterwards
-        const int m = (int)std::ceil(std::fabs(ents[i].vx)) + (int)std::ceil(std::fabs(ents[i].vy)) + 12;
-        int x0 = (int)(ents[i].x + load_x) - m, y0 = (int)(ents[i].y + load_y) - m, x1 = x0 + ents[i].hw + 2 * m, y1 = y0 + ents[i].hh + 2 * m;
-        x0 = x0 < 0 ? 0 : x0;
-        y0 = y0 < 0 ? 0 : y0;
-        x1 = x1 > w->W ? w->W : x1;
-        y1 = y1 > w->H ? w->H : y1;
-        if (x1 > x0 && y1 > y0)
-            if (int r = fse_wake_rect(w, x0, y0, x1 - x0, y1 - y0)) return r;
+    const bool multi = w->strip && w->ctx->nranks > 1;
+    std::vector<int4> box(n);
+    for (int i = 0; i < n; i++) {  // whatever a sweep can reach (the kernel's tile, + the push-out step and the gravity it adds first)
+        const int m = (int)std::ceil(std::fabs(ents[i].vx)) + (int)std::ceil(std::fabs(ents[i].vy)) + 12 + 2;
+        const int x0 = (int)(ents[i].x + load_x) - m, y0 = (int)(ents[i].y + load_y) - m;
+        box[i] = make_int4(x0, y0, x0 + ents[i].hw + 2 * m, y0 + ents[i].hh + 2 * m);
+    }
+    std::vector<int> exec;
+    if (multi) {
+        // multi-rank strips: every rank makes the call with the same entities; an entity — with every entity whose reach overlaps its own, they
+        // see each other's kicks — is run by the rank that holds its reach box (ghost rows refreshed first); the records are summed over the
+        // ranks afterwards (a rank zeroes the ones it did not run) and the boxes travel to the neighbours they reach into
+        if (int r = strip_group_runners(w, box, "fse_entities_tick", "entity", exec)) return r;
+        if (int r = strip_refresh(w, w->stream, STRIP_GHOST)) return r;
+        if (n > b->exec_cap) {
+            CK(cudaStreamSynchronize(w->stream));
+            cudaFree(b->d_exec);
+            b->d_exec = nullptr;
+            b->exec_cap = 0;
+            CK(cudaMalloc((void**)&b->d_exec, sizeof(int) * (size_t)(n + 16)));
+            b->exec_cap = n + 16;
+        }
+        CK(cudaMemcpyAsync(b->d_exec, exec.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, w->stream));
+        a.exec = b->d_exec;
+    } else {
+        for (int i = 0; i < n; i++) {  // active-chunk tracking: whatever a sweep can reach is awake afterwards
+            int x0 = box[i].x, y0 = box[i].y - w->y_off, x1 = box[i].z, y1 = box[i].w - w->y_off;
+            x0 = x0 < 0 ? 0 : x0;
+            y0 = y0 < 0 ? 0 : y0;
+            x1 = x1 > w->W ? w->W : x1;
+            y1 = y1 > w->H ? w->H : y1;
+            if (x1 > x0 && y1 > y0)
+                if (int r = fse_wake_rect(w, x0, y0, x1 - x0, y1 - y0)) return r;
+        }
     }
     entities_tick_kernel<<<1, ENT_THREADS, ENT_TILE_CAP, w->stream>>>(a);
     CK(cudaGetLastError());
     w->ctx->launches += 1;
+    if (multi) {
+        if (int r = strip_allreduce_u32(w, (unsigned int*)b->d_ents, (size_t)n * (sizeof(fse_entity) / 4), w->stream)) return r;
+        std::vector<int4> rect[4];
+        for (int i = 0; i < n; i++) strip_rects_of_box(w, exec[i], box[i].x, box[i].y, box[i].z, box[i].w, rect);
+        if (int r = strip_push_rects(w, rect, w->stream)) return r;
+    }
     CK(cudaMemcpyAsync(ents, b->d_ents, sizeof(fse_entity) * (size_t)n, cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
     return FSE_OK;
@@ -427,8 +481,10 @@ extern "C" FSE_API int fse_entities_stamp(fse_world* w, const fse_entity* ents, 
     EntArgs a;
     entity_args(w, b, n, load_x, load_y, tick, seed, &a);
     a.object_mat = object_mat;
+    if (w->strip && w->ctx->nranks > 1)  // every rank stamps the cells of its window (they are independent); ghost rows must be the owner's first
+        if (int r = strip_refresh(w, w->stream, STRIP_GHOST)) return r;
     for (int i = 0; i < n; i++) {
-        fse_rect r{(int)(ents[i].x + load_x) - 1, (int)(ents[i].y + load_y) - 1, ents[i].hw + 2, ents[i].hh + 2};
+        fse_rect r{(int)(ents[i].x + load_x) - 1, (int)(ents[i].y + load_y) - 1 - w->y_off, ents[i].hw + 2, ents[i].hh + 2};
         if (r.x < 0) r.x = 0;
         if (r.y < 0) r.y = 0;
         if (r.x + r.w > w->W) r.w = w->W - r.x;
@@ -453,7 +509,12 @@ extern "C" FSE_API int fse_object_delete(fse_world* w) {
     CK(cudaStreamSynchronize(w->stream));
     if (n > b->objdel_cap) n = b->objdel_cap;
     if (n) {
-        object_delete_kernel<<<(n + 255) / 256, 256, 0, w->stream>>>(w->p, b->d_objdel, n, w->ctx->h_tabs.air);
+        Planes p = w->p;
+        if (w->strip) {  // the list holds global cell indices (see EntArgs)
+            const size_t back = (size_t)w->y_off * w->W;
+            p.mat -= back; p.flg -= back; p.stl -= back; p.tmp -= back; p.col -= back; p.fl -= back; p.fd -= back;
+        }
+        object_delete_kernel<<<(n + 255) / 256, 256, 0, w->stream>>>(p, b->d_objdel, n, w->ctx->h_tabs.air);
         CK(cudaGetLastError());
         w->ctx->launches += 1;
     }

@@ -178,6 +178,7 @@ int strip_shift_rows(fse_world* w, int send_lo, int send_hi, bool send_down, uns
 constexpr int STRIP_GHOST = 32;  // ghost rows of a strip (fse_strip_create)
 void strip_rows_of(int Hglobal, int rank, int nranks, int* own_lo, int* own_hi, int* held_lo, int* held_hi);
 int strip_runner_of_rows(fse_world* w, int ya, int yb, const char* who, int* exec);
+int strip_group_runners(fse_world* w, const std::vector<int4>& box, const char* who, const char* what, std::vector<int>& exec);
 void strip_rects_of_box(fse_world* w, int exec, int xa, int ya, int xb, int yb, std::vector<int4> rect[4]);
 int strip_push_rects(fse_world* w, const std::vector<int4> rect[4], cudaStream_t s);
 size_t tick_smem_bytes();

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import falling_sand_engine_b200 as fse  # noqa: E402
 from falling_sand_engine_b200 import materials as M, strips, worldgen as G  # noqa: E402
-from tests.strip_bodies_scene import scene, stone_blocks, tool_calls, run_tool  # noqa: E402
+from tests.strip_bodies_scene import scene, stone_blocks, tool_calls, run_tool, entities  # noqa: E402
 
 
 def main():
@@ -29,7 +29,10 @@ def main():
         sw.write_rect(x0, y0, cells)
     sw.bodies_upload(bodies)
     fbs, tools = [], []
+    ents = entities(H, world)
     for t in range(ticks):
+        ents = sw.entities_tick(ents, tick=t)   # world::tickEntities, then the entities become OBJECT cells for the rest of the game tick
+        sw.entities_stamp(ents, tick=t)
         fbs.append(sw.bodies_raster(xf, tick=t))
         sw.tick(t, seed=1337)
         if t == 1:  # tools across the cuts: every rank makes the call and gets the same answer
@@ -40,6 +43,7 @@ def main():
             tools.append(np.array([sw.particles_vacuum_pull(500.0, 700.0)], dtype=np.int64))
         fe, need = sw.bodies_erase(xf)
         fbs.append(fe)
+        sw.object_delete()
         xf[:, 1] += 1.5   # the host's Box2D step: bodies drift down (some change strips on the way) and turn
         xf[:, 2] += 0.05
     sw.sync()
@@ -47,6 +51,7 @@ def main():
     np.save(f"{out}.parts{rank}.npy", sw.particles_read())
     np.save(f"{out}.fb{rank}.npy", np.stack(fbs))
     np.save(f"{out}.tools{rank}.npy", np.concatenate(tools))
+    np.save(f"{out}.ents{rank}.npy", ents)
     np.save(f"{out}.tiles{rank}.npy", np.concatenate([sw.bodies_read(i).reshape(-1) for i in range(len(bodies))]))
     dist.barrier()
     sw.close()

@@ -3,6 +3,7 @@ just above it, one just below it, and a pair that overlaps ACROSS the cut (cross
 import numpy as np
 
 from falling_sand_engine_b200 import strips
+from falling_sand_engine_b200 import types as T
 from falling_sand_engine_b200 import worldgen as G
 from tests.test_bridge_cpu import make_body
 
@@ -75,3 +76,18 @@ def run_tool(world_or_oracle, call, oracle_mod=None):
     hx, hy, x, y, tick = call[1:]
     res = (oracle_mod.tool_hammer(world_or_oracle, hx, hy, x, y, tick=tick) if oracle_mod else world_or_oracle.tool_hammer(hx, hy, x, y, tick=tick))
     return np.asarray(res, dtype=np.int64).reshape(-1)
+
+
+def entities(H, nranks):
+    """Entities (players / NPCs: AABBs that collide with the grid, kick sand and are stamped as OBJECT cells) all over the world and, around
+    every cut: one falling through it, one walking along it, and two whose reach overlaps across it (they see each other's kicks)."""
+    rng = np.random.default_rng(3)
+    rows = []
+    for _ in range(10):
+        rows.append((rng.uniform(160, 860), rng.uniform(160, H - 200), rng.uniform(-3, 3), rng.uniform(-3, 3), 8, 14, 0, 0))
+    for cut in _cuts(H, nranks):
+        rows.append((150.0, cut - 20.0, 0.4, 3.5, 8, 14, 0, 0))     # falls across the cut
+        rows.append((185.0, cut - 7.0, 2.5, -0.2, 8, 14, 0, 0))     # walks along it, its box on both sides
+        rows.append((240.0, cut - 16.0, 1.0, 1.0, 8, 14, 0, 0))     # two whose reach boxes overlap across the cut
+        rows.append((246.0, cut - 9.0, -1.0, -1.5, 8, 14, 0, 0))
+    return np.array(rows, dtype=T.ENTITY_DTYPE)

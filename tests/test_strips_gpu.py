@@ -73,7 +73,7 @@ def test_strip_bodies_match_oracle(oracle, table, tmp_path, nranks):
     if _ngpu() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
     from oracle import pyoracle as O
-    from tests.strip_bodies_scene import scene, stone_blocks, tool_calls, run_tool
+    from tests.strip_bodies_scene import scene, stone_blocks, tool_calls, run_tool, entities
     W, H, ticks = 1024, 1536, 6
     out = str(tmp_path / "sb")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
@@ -88,7 +88,10 @@ def test_strip_bodies_match_oracle(oracle, table, tmp_path, nranks):
         ow.write_rect(x0, y0, cells)
     ob = [b.copy() for b in bodies]
     fbs, tools = [], []
+    ents = entities(H, nranks)
     for t in range(ticks):
+        ents = O.entities_tick(ow, ents, tick=t)
+        O.entities_stamp(ow, ents, tick=t)
         fbs.append(O.bodies_raster(ow, ob, xf, tick=t))
         ow.tick(t, seed=1337)
         if t == 1:
@@ -98,6 +101,7 @@ def test_strip_bodies_match_oracle(oracle, table, tmp_path, nranks):
         if t == 3:
             tools.append(np.array([O.particles_vacuum_pull(ow, 500.0, 700.0)], dtype=np.int64))
         fbs.append(O.bodies_erase(ow, ob, xf))
+        O.object_delete(ow)
         xf[:, 1] += 1.5
         xf[:, 2] += 0.05
     fbs, tools = np.stack(fbs), np.concatenate(tools)
@@ -110,6 +114,7 @@ def test_strip_bodies_match_oracle(oracle, table, tmp_path, nranks):
         lo, hi = strips.strip_layout(H, k, nranks)[:2]
         assert np.array_equal(fbs, np.load(f"{out}.fb{k}.npy")), f"feedback on rank {k}"
         assert np.array_equal(tools, np.load(f"{out}.tools{k}.npy")), f"tool results on rank {k}"
+        assert ents.tobytes() == np.load(f"{out}.ents{k}.npy").tobytes(), f"entities on rank {k}"
         assert tiles.tobytes() == np.load(f"{out}.tiles{k}.npy").tobytes(), f"body tiles on rank {k}"
         Hh.assert_cells_equal(ref[lo:hi], np.load(f"{out}.rank{k}.npy"), f"strip {k}/{nranks}")
         parts.append(np.load(f"{out}.parts{k}.npy"))
