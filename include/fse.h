@@ -428,7 +428,11 @@ FSE_API int fse_active_stats(fse_world* w, int64_t* awake_chunks, int64_t* total
  * fse_comm_init; fse_strip_create then gives each rank the strip of chunk rows it owns plus ghost rows.  All rect /
  * zone arguments stay in GLOBAL cell coordinates.  fse_tick on a strip world exchanges the rows around each cut after
  * every colour phase (ncclSend/ncclRecv on a side stream, overlapped with the interior chunk rows); the result is
- * bit-identical to the unpartitioned world. */
+ * bit-identical to the unpartitioned world.  The game loop is SPMD on strips: every rank makes every call (tick, particles,
+ * temperature, explosion, tools, scroll, bodies, entities, physicsCheck) with the same arguments and gets the same results; calls
+ * that edit the grid from one place (a body, an entity, a crack, a probed component) are run by the rank that holds the place's box
+ * and the box travels to the neighbours it reaches into — such a box, with the ones it overlaps, must lie within 32 rows of one
+ * strip (FSE_ESTATE otherwise).  Only fse_tool_vacuum is not available on multi-rank strips. */
 FSE_API int fse_comm_unique_id(void* out128);
 FSE_API int fse_comm_init(fse_ctx* ctx, int rank, int nranks, const void* id128);
 FSE_API int fse_comm_destroy(fse_ctx* ctx);
