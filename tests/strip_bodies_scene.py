@@ -83,8 +83,11 @@ def entities(H, nranks):
     every cut: one falling through it, one walking along it, and two whose reach overlaps across it (they see each other's kicks)."""
     rng = np.random.default_rng(3)
     rows = []
-    for _ in range(10):
-        rows.append((rng.uniform(160, 860), rng.uniform(160, H - 200), rng.uniform(-3, 3), rng.uniform(-3, 3), 8, 14, 0, 0))
+    cuts = _cuts(H, nranks)
+    while len(rows) < 10:  # the random ones keep clear of the cuts: what happens AT the cuts is placed by hand below
+        x, y = rng.uniform(300, 860), rng.uniform(160, H - 200)
+        if all(abs(y - c) > 110 for c in cuts):
+            rows.append((x, y, rng.uniform(-3, 3), rng.uniform(-3, 3), 8, 14, 0, 0))
     for cut in _cuts(H, nranks):
         rows.append((150.0, cut - 20.0, 0.4, 3.5, 8, 14, 0, 0))     # falls across the cut
         rows.append((185.0, cut - 7.0, 2.5, -0.2, 8, 14, 0, 0))     # walks along it, its box on both sides
