@@ -71,6 +71,15 @@ else:
     w.mask_outline(masks)
     w.update_rigid_body_hitbox(0, angle=0.3)
     w.flood_component(300, 300)
+    ents = np.array([(250.0, 220.0, 1.5, 2.0, 8, 14, 0, 0), (256.0, 228.0, -1.0, -2.5, 8, 14, 0, 0), (400.0, 300.0, 0.0, 3.0, 6, 10, 0, 0)], dtype=fse.types.ENTITY_DTYPE)
+    ents = w.entities_tick(ents, tick=2)
+    w.entities_stamp(ents, tick=2)
+    w.tool_erase_line(120, 150, 380, 330, 7)
+    w.tool_pickaxe(280, 250, 19.0)
+    w.tool_hammer(300, 280, 290, 268, tick=2)
+    w.tool_vacuum(320, 300, 350, 330, tick=2)
+    w.particles_vacuum_pull(320.0, 300.0)
+    w.object_delete()
     w.particles_tick()
 s = w.stats()
 w.sync()
