@@ -445,6 +445,42 @@ using namespace fse;
 extern "C" {
 
 // 128-byte ncclUniqueId for rank 0 to broadcast (any out-of-band channel: torch.distributed, MPI, a file ...).
+FSE_API int fse_strip_plan(int32_t width, int32_t height_global, int32_t rank, int32_t nranks, const int32_t* boxes, int32_t n, int32_t* runner,
+                           int32_t* rects_out, int32_t cap_rects, int32_t* n_rects) {
+    if (!boxes || !runner || !rects_out || !n_rects || n < 0 || cap_rects < 0 || nranks < 1 || rank < 0 || rank >= nranks || width < 1 ||
+        height_global % CHUNK || (height_global - 2 * CHUNK) / CHUNK < nranks)
+        return fail(FSE_EINVAL, "fse_strip_plan: bad argument");
+    fse_ctx c;  // what the planning functions read of a strip world; nothing here touches a device
+    c.rank = rank;
+    c.nranks = nranks;
+    fse_world w;
+    w.ctx = &c;
+    w.W = width;
+    w.strip = true;
+    w.Hglobal = height_global;
+    int held_lo, held_hi;
+    strip_rows_of(height_global, rank, nranks, &w.own_lo, &w.own_hi, &held_lo, &held_hi);
+    w.y_off = held_lo;
+    w.H = held_hi - held_lo;
+    std::vector<int4> box(n);
+    for (int i = 0; i < n; i++) box[i] = make_int4(boxes[4 * i], boxes[4 * i + 1], boxes[4 * i + 2], boxes[4 * i + 3]);
+    std::vector<int> exec;
+    if (int r = strip_group_runners(&w, box, "fse_strip_plan", "box", exec)) return r;
+    std::vector<int4> rect[4];
+    for (int i = 0; i < n; i++) {
+        runner[i] = exec[i];
+        strip_rects_of_box(&w, exec[i], box[i].x, box[i].y, box[i].z, box[i].w, rect);
+    }
+    for (int q = 0; q < 4; q++) {
+        n_rects[q] = (int32_t)rect[q].size();
+        for (int k = 0; k < (int)rect[q].size() && k < cap_rects; k++) {
+            int32_t* o = rects_out + ((size_t)q * cap_rects + k) * 4;
+            o[0] = rect[q][k].x; o[1] = rect[q][k].y; o[2] = rect[q][k].z; o[3] = rect[q][k].w;
+        }
+    }
+    return FSE_OK;
+}
+
 FSE_API int fse_comm_unique_id(void* out128) {
     if (!out128) return fail(FSE_EINVAL, "fse_comm_unique_id: null");
     if (int r = load_nccl()) return r;

@@ -456,6 +456,13 @@ FSE_API int fse_kernel_timing_read(fse_world* w, double* total_ms, int64_t* laun
  * exchange and the interior chunks finished (out: n x 3 floats); resets the record */
 FSE_API int fse_strip_timeline_read(fse_world* w, float* out, int64_t cap_phases, int64_t* n_out);
 FSE_API int fse_kernel_timing_phases(fse_world* w, float* out_ms, int64_t cap, int64_t* n_out);
+/* The host-side plan of a call that edits the grid from n boxes on multi-rank strips (bodies, entities, cracks; boxes = n x (x0, y0, x1,
+ * y1), global and inclusive, applied in index order), as rank `rank` of `nranks` computes it for a `width` x `height_global` world — pure
+ * host code, no device needed: runner[i] = the rank that runs box i (overlapping boxes share one), and the rectangles (x0, y0 in the
+ * rank's LOCAL rows, w, h) this rank sends up / receives from above / sends down / receives from below, at most cap_rects of each in
+ * rects_out[4][cap_rects][4] with their counts in n_rects[4].  FSE_ESTATE when a box does not fit the rows its runner holds. */
+FSE_API int fse_strip_plan(int32_t width, int32_t height_global, int32_t rank, int32_t nranks, const int32_t* boxes, int32_t n, int32_t* runner,
+                           int32_t* rects_out, int32_t cap_rects, int32_t* n_rects);
 /* profiling aid: cycles each warp role of the tick kernel spent working between step barriers (out[0..3]) and chunks (out[4]) */
 FSE_API int fse_debug_role_cycles(fse_world* w, int enable, unsigned long long* out);
 
