@@ -188,7 +188,23 @@ struct VacArgs {
     unsigned int pcap;
     unsigned int n_before;  // particles in the pool before the call
     int* out;               // x, y, cells sucked, particles re-energised
+    // strips: global rows (W x H is the whole world, the plane pointers are moved back by the rows above this rank's window); the walk
+    // was done by the host from the types along the line (preset: out[0..1] already hold the hit); a rank empties the cells of the
+    // square in its window [ylo, yhi) and makes the particles of the rows it owns [own_lo, own_hi)
+    int preset, ylo, yhi, own_lo, own_hi;
 };
+// strips: physics type + 1 of the line cells this rank owns (0 elsewhere; the sum over the ranks is the whole line)
+__global__ void vacuum_line_types_kernel(Planes p, const DevTables* T, int W, const long long* cells, int n, int own_lo, int own_hi, unsigned int* types) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long c = cells[i];
+    unsigned int t = 0;
+    if (c >= 0) {
+        const int y = (int)(c / W);
+        if (y >= own_lo && y < own_hi) t = 1u + (unsigned int)T->phys[p.mat[c]];
+    }
+    types[i] = t;
+}
 __device__ __forceinline__ void vac_energise(fse_particle& q, uint32_t cb) {  // game.cpp:2492-2505 / 2548-2560
     q.vx = ((int)(rng_draw(cb, S_VAC_VX) % 10) - 5) / 5.0f * 1.0f;
     q.vy = ((int)(rng_draw(cb, S_VAC_VY) % 10) - 5) / 5.0f * 1.0f;
@@ -203,7 +219,10 @@ __device__ __forceinline__ void vac_energise(fse_particle& q, uint32_t cb) {  //
 // stops at the first hit, so it is sequential); then one thread per cell of the 11 x 11 square (2525-2541)
 __global__ void __launch_bounds__(128) tool_vacuum_kernel(VacArgs a) {
     __shared__ int s_x, s_y;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && a.preset) {
+        s_x = a.out[0];
+        s_y = a.out[1];
+    } else if (threadIdx.x == 0) {
         const int dx = a.wmx - a.wcx, dy = a.wmy - a.wcy;
         int dLong = abs(dx), dShort = abs(dy);
         long long offsetLong = dx > 0 ? 1 : -1, offsetShort = dy > 0 ? a.W : -a.W;
@@ -248,9 +267,14 @@ __global__ void __launch_bounds__(128) tool_vacuum_kernel(VacArgs a) {
     if ((yy == -rad || yy == rad) && (xx == -rad || xx == rad)) return;
     const int x = s_x + xx, y = s_y + yy;
     if (x < 0 || y < 0 || x >= a.W || y >= a.H) return;
+    if (y < a.ylo || y >= a.yhi) return;
     const size_t g = (size_t)y * a.W + x;
     const int t = a.T->phys[a.p.mat[g]];
     if (!(t == P_SOLID || t == P_SAND || t == P_SOUP)) return;
+    if (!(y >= a.own_lo && y < a.own_hi)) {  // a ghost cell: emptied here as well, its owner makes the particle and counts it
+        tool_set_nothing(a.p, g, a.T->air);
+        return;
+    }
     const unsigned int i = atomicAdd(a.pcount, 1u);
     if (i < a.pcap) {
         fse_particle q;
@@ -548,25 +572,91 @@ extern "C" FSE_API int fse_tool_hammer(fse_world* w, int32_t hammer_x, int32_t h
 }
 
 extern "C" FSE_API int fse_tool_vacuum(fse_world* w, int32_t wcx, int32_t wcy, int32_t wmx, int32_t wmy, uint32_t tick, uint32_t seed, fse_vacuum_result* out) {
-    if (int r = tool_common(w, "fse_tool_vacuum")) return r;
+    // multi-rank strips: every rank makes the call.  The walk from the screen centre towards the mouse only reads: every rank reports the
+    // physics types of the line cells it owns, the sum over the ranks is the whole line, and the host of every rank finds the same hit
+    // on it; the cells of the 11 x 11 square are independent (a rank empties the ones in its window and makes the particles of the
+    // rows it owns), the loose particles are caught by the rank whose pool they are in; the counts are summed.
+    if (int r = tool_common(w, "fse_tool_vacuum", true)) return r;
     if (!out) return fail(FSE_EINVAL, "fse_tool_vacuum: null result");
     out->x = out->y = -1;
     out->n_sucked = out->n_caught = 0;
+    const bool multi = w->strip && w->ctx->nranks > 1;
+    const int Hg = w->strip ? w->Hglobal : w->H;
     const int mdx = wmx - wcx, mdy = wmy - wcy;
     if (mdx * mdx + mdy * mdy > 256 * 256) return FSE_OK;  // game.cpp:2465: out of reach
-    if (wcx < 0 || wcy < 0 || wcx >= w->W || wcy >= w->H) return fail(FSE_EINVAL, "fse_tool_vacuum: centre outside the world");
+    if (wcx < 0 || wcy < 0 || wcx >= w->W || wcy >= Hg) return fail(FSE_EINVAL, "fse_tool_vacuum: centre outside the world");
     int64_t n_before = 0;
     if (int r = particles_headroom(w, 121, true)) return r;
     if (int r = fse_particles_count(w, &n_before)) return r;
-    if (int r = tool_scratch(w, 64)) return r;
-    CKT(cudaMemsetAsync(w->tool_scratch, 0, 16, w->stream));
     VacArgs a;
+    memset(&a, 0, sizeof a);
     a.p = w->p; a.T = w->ctx->d_tabs; a.W = w->W; a.H = w->H;
     a.wcx = wcx; a.wcy = wcy; a.wmx = wmx; a.wmy = wmy;
     a.rkey = rng_key(seed, tick, 10u); a.tick = tick;
     a.pbuf = w->pbuf; a.pcount = w->pcount; a.pcap = w->pcap;
     a.n_before = (unsigned int)n_before;
-    a.out = (int*)w->tool_scratch;
+    a.ylo = 0; a.yhi = w->H; a.own_lo = 0; a.own_hi = w->H;
+    if (!multi) {
+        if (int r = tool_scratch(w, 64)) return r;
+        CKT(cudaMemsetAsync(w->tool_scratch, 0, 16, w->stream));
+        a.out = (int*)w->tool_scratch;
+    } else {
+        if (int r = strip_refresh(w, w->stream, STRIP_GHOST)) return r;
+        const size_t back = (size_t)w->y_off * w->W;  // global rows from here on
+        a.p.mat -= back; a.p.flg -= back; a.p.stl -= back; a.p.tmp -= back; a.p.col -= back; a.p.fl -= back; a.p.fd -= back;
+        a.H = Hg;
+        a.ylo = w->y_off; a.yhi = w->y_off + w->H; a.own_lo = w->own_lo; a.own_hi = w->own_hi;
+        // the cells of the walk (game.cpp:2468-2486: forLine on linear cell indices), then their types from the ranks that own them
+        int dLong = std::abs(mdx), dShort = std::abs(mdy);
+        long long offsetLong = mdx > 0 ? 1 : -1, offsetShort = mdy > 0 ? w->W : -w->W;
+        if (dLong < dShort) {
+            std::swap(dLong, dShort);
+            std::swap(offsetLong, offsetShort);
+        }
+        std::vector<long long> cells((size_t)dLong + 1);
+        int error = dLong / 2;
+        long long index = (long long)wcy * w->W + wcx;
+        for (int i = 0; i <= dLong; ++i) {
+            cells[i] = (index >= 0 && index < (long long)w->W * Hg) ? index : -1;
+            const int big = error >= dLong;
+            index += big ? offsetLong + offsetShort : offsetLong;
+            error += big ? dShort - dLong : dShort;
+        }
+        const size_t nb = cells.size() * sizeof(long long), o_types = (nb + 15) & ~(size_t)15, o_out = o_types + ((cells.size() * 4 + 15) & ~(size_t)15);
+        if (int r = tool_scratch(w, o_out + 64)) return r;
+        char* base = (char*)w->tool_scratch;
+        unsigned int* d_types = (unsigned int*)(base + o_types);
+        a.out = (int*)(base + o_out);
+        CKT(cudaMemcpyAsync(base, cells.data(), nb, cudaMemcpyHostToDevice, w->stream));
+        vacuum_line_types_kernel<<<(unsigned)((cells.size() + 127) / 128), 128, 0, w->stream>>>(a.p, a.T, w->W, (const long long*)base, (int)cells.size(), w->own_lo, w->own_hi, d_types);
+        CKT(cudaGetLastError());
+        w->ctx->launches += 1;
+        if (int r = strip_allreduce_u32(w, d_types, cells.size(), w->stream)) return r;
+        std::vector<unsigned int> types(cells.size());
+        CKT(cudaMemcpyAsync(types.data(), d_types, cells.size() * 4, cudaMemcpyDeviceToHost, w->stream));
+        CKT(cudaStreamSynchronize(w->stream));
+        long long sind = -1;
+        bool inObject = true;
+        for (size_t i = 0; i < cells.size(); i++) {
+            if (cells[i] < 0) continue;
+            const int t = (int)types[i] - 1;
+            bool stop = false;
+            if (t == P_PASSABLE) {  // OBJECT: the player's own stamp is skipped until the walk has left it
+                if (!inObject) stop = true;
+            } else {
+                inObject = false;
+            }
+            if (t == P_SOLID || t == P_SAND || t == P_SOUP) stop = true;
+            if (stop) {
+                sind = cells[i];
+                break;
+            }
+        }
+        int hit[4] = {sind == -1 ? wmx : (int)(sind % w->W), sind == -1 ? wmy : (int)(sind / w->W), 0, 0};
+        CKT(cudaMemcpyAsync(a.out, hit, sizeof hit, cudaMemcpyHostToDevice, w->stream));
+        CKT(cudaStreamSynchronize(w->stream));  // hit is a local
+        a.preset = 1;
+    }
     tool_vacuum_kernel<<<1, 128, 0, w->stream>>>(a);
     CKT(cudaGetLastError());
     w->ctx->launches += 1;
@@ -575,11 +665,13 @@ extern "C" FSE_API int fse_tool_vacuum(fse_world* w, int32_t wcx, int32_t wcy, i
         CKT(cudaGetLastError());
         w->ctx->launches += 1;
     }
+    if (multi)
+        if (int r = strip_allreduce_u32(w, (unsigned int*)a.out + 2, 2, w->stream)) return r;  // cells sucked, particles caught
     int res[4];
-    CKT(cudaMemcpyAsync(res, w->tool_scratch, sizeof res, cudaMemcpyDeviceToHost, w->stream));
+    CKT(cudaMemcpyAsync(res, a.out, sizeof res, cudaMemcpyDeviceToHost, w->stream));
     CKT(cudaStreamSynchronize(w->stream));
     out->x = res[0]; out->y = res[1]; out->n_sucked = res[2]; out->n_caught = res[3];
-    return tool_wake(w, res[0] - 7, res[1] - 7, res[0] + 7, res[1] + 7);
+    return tool_wake(w, res[0] - 7, res[1] - 7 - w->y_off, res[0] + 7, res[1] + 7 - w->y_off);
 }
 
 extern "C" FSE_API int fse_particles_vacuum_pull(fse_world* w, float target_x, float target_y, int32_t* n_collected) {

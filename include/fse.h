@@ -432,7 +432,7 @@ FSE_API int fse_active_stats(fse_world* w, int64_t* awake_chunks, int64_t* total
  * temperature, explosion, tools, scroll, bodies, entities, physicsCheck) with the same arguments and gets the same results; calls
  * that edit the grid from one place (a body, an entity, a crack, a probed component) are run by the rank that holds the place's box
  * and the box travels to the neighbours it reaches into — such a box, with the ones it overlaps, must lie within 32 rows of one
- * strip (FSE_ESTATE otherwise).  Only fse_tool_vacuum is not available on multi-rank strips. */
+ * strip (FSE_ESTATE otherwise). */
 FSE_API int fse_comm_unique_id(void* out128);
 FSE_API int fse_comm_init(fse_ctx* ctx, int rank, int nranks, const void* id128);
 FSE_API int fse_comm_destroy(fse_ctx* ctx);

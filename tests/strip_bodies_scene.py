@@ -60,6 +60,9 @@ def tool_calls(H, nranks, tick):
         calls.append(("physcheck", 22, cut - 1))   # the 30-cell piece: probed in the upper strip, reaches into the lower one
         calls.append(("physcheck", 39, cut))       # the 6-cell crumb: probed in the lower strip
         calls.append(("physcheck", 45, cut + 8))   # AIR: nothing
+        calls.append(("vacuum", 80, cut, 130, cut, tick))          # along the cut inside the pickaxe's hole: the square it empties lies on both sides
+        calls.append(("vacuum", 100, cut - 70, 104, cut + 60, tick))   # the walk starts in the upper strip and crosses the cut region
+        calls.append(("vacuum", 120, cut + 80, 110, cut - 40, tick))   # ... and from below
     return calls
 
 
@@ -73,6 +76,10 @@ def run_tool(world_or_oracle, call, oracle_mod=None):
         count, action, box, tiles = (oracle_mod.physics_check(world_or_oracle, *call[1:]) if oracle_mod else world_or_oracle.physics_check(*call[1:]))
         t = np.zeros(0, dtype=np.int64) if tiles is None else np.frombuffer(np.ascontiguousarray(tiles).tobytes(), dtype=np.uint8).astype(np.int64)
         return np.concatenate([np.array([count, action, *box], dtype=np.int64), t])
+    if kind == "vacuum":
+        wcx, wcy, wmx, wmy, tick = call[1:]
+        res = (oracle_mod.tool_vacuum(world_or_oracle, wcx, wcy, wmx, wmy, tick=tick) if oracle_mod else world_or_oracle.tool_vacuum(wcx, wcy, wmx, wmy, tick=tick))
+        return np.asarray(res, dtype=np.int64).reshape(-1)
     hx, hy, x, y, tick = call[1:]
     res = (oracle_mod.tool_hammer(world_or_oracle, hx, hy, x, y, tick=tick) if oracle_mod else world_or_oracle.tool_hammer(hx, hy, x, y, tick=tick))
     return np.asarray(res, dtype=np.int64).reshape(-1)
