@@ -104,3 +104,43 @@ def test_a_box_that_no_strip_can_hold_is_refused_on_every_rank():
     boxes = [(300, cut - 40, 340, cut - 4), (320, cut - 8, 360, cut + 38)]
     rcs = [_plan(L, H, r, nranks, boxes)[0] for r in range(nranks)]
     assert len(set(rcs)) == 1 and rcs[0] != 0
+
+
+@pytest.mark.parametrize("nranks,H", [(2, 1536), (4, 1536), (8, 4352)])
+def test_planned_exchange_brings_every_window_in_step(nranks, H):
+    """The plan executed on data: every rank holds its window (own + ghost rows) of a global array; the runner of a box rewrites the box in
+    its window; the planned rectangles are copied from the sender's window into the receiver's, in list order.  Afterwards every window
+    must equal the global array with all boxes rewritten (later boxes over earlier ones where they overlap — they share a runner)."""
+    L = api.load_library()
+    rng = np.random.default_rng(7 + nranks)
+    lay = [strips.strip_layout(H, r, nranks) for r in range(nranks)]
+    for trial in range(4):
+        boxes = _boxes(rng, H, nranks, 50)
+        world = rng.integers(0, 1000, size=(H, W), dtype=np.int32)
+        win = [world[lay[r][2]:lay[r][3]].copy() for r in range(nranks)]
+        plans = [_plan(L, H, r, nranks, boxes) for r in range(nranks)]
+        assert all(p[0] == 0 for p in plans)
+        runner = plans[0][1]
+        for i, (x0, y0, x1, y1) in enumerate(boxes):  # the edit: box i becomes 10000 + i, on the single world and in its runner's window
+            xa, xb, ya, yb = max(x0, 0), min(x1, W - 1), max(y0, 0), min(y1, H - 1)
+            if xa > xb or ya > yb:
+                continue
+            world[ya:yb + 1, xa:xb + 1] = 10000 + i
+            e = runner[i]
+            win[e][ya - lay[e][2]:yb + 1 - lay[e][2], xa:xb + 1] = 10000 + i
+        msgs = {}
+        for r in range(nranks):  # pack: up send (0) and down send (2), from the windows as the runners left them
+            for q, peer in ((0, r - 1), (2, r + 1)):
+                msgs[(r, peer)] = [win[r][y0:y0 + h, x0:x0 + w].copy() for (x0, y0, w, h) in plans[r][2][q]]
+        for r in range(nranks):  # unpack: from above (1) and from below (3)
+            for q, peer in ((1, r - 1), (3, r + 1)):
+                rects = plans[r][2][q]
+                if len(rects) == 0:
+                    continue
+                got = msgs[(peer, r)]
+                assert len(got) == len(rects)
+                for (x0, y0, w, h), data in zip(rects, got):
+                    assert data.shape == (h, w)
+                    win[r][y0:y0 + h, x0:x0 + w] = data
+        for r in range(nranks):
+            assert np.array_equal(win[r], world[lay[r][2]:lay[r][3]]), (trial, r)
