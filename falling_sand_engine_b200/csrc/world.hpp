@@ -70,6 +70,10 @@ public:
                                 t.react_offsets.empty() ? nullptr : t.react_offsets.data()));
     }
     fse_ctx* handle() const { return h_; }
+    // multi-GPU (one process per GPU, include/fse.h "multi-GPU"): rank 0 makes the 128-byte id, the host carries it to the other
+    // ranks by whatever channel it has (MPI, a socket, a file), every rank joins
+    static void commUniqueId(void* out128) { check(fse_comm_unique_id(out128)); }
+    void commInit(int rank, int nranks, const void* id128) { check(fse_comm_init(h_, rank, nranks, id128)); }
 
 private:
     fse_ctx* h_ = nullptr;
@@ -91,6 +95,16 @@ public:
         height = h;
         tickZone = {FSE_CHUNK, FSE_CHUNK, w - 2 * FSE_CHUNK, h - 2 * FSE_CHUNK};
     }
+    // one strip of a w x hGlobal world on this rank (after Context::commInit); width / height / tickZone and every coordinate of every
+    // method stay GLOBAL, every rank makes the same calls in the same order (gameTick is SPMD), results are those of the single world
+    void initStrip(Context& ctx, int w, int hGlobal) {
+        check(fse_strip_create(ctx.handle(), w, hGlobal, &h_));
+        width = w;
+        height = hGlobal;
+        tickZone = {FSE_CHUNK, FSE_CHUNK, w - 2 * FSE_CHUNK, hGlobal - 2 * FSE_CHUNK};
+        check(fse_strip_rows(h_, &ownLo, &ownHi, &heldLo, &heldHi));
+    }
+    int32_t ownLo = 0, ownHi = 0, heldLo = 0, heldHi = 0;  // strips: rows this rank owns / holds (owned + ghost); chunk loads go to the rank that holds them
     ~world() { fse_world_destroy(h_); }
 
     // world.cpp:999-1008
