@@ -97,3 +97,44 @@ def test_strip_particle_protocol_matches_single_world(oracle, table, tmp_path, n
     Hh.assert_particles_equal(ow.particles_read(), np.concatenate(parts), "strip particles")
     counts = sum(np.load(f"{out}.counts{r}.npy") for r in range(nranks))
     assert counts[0] > 0 and counts[1] > 0, counts  # proposals crossed a cut and particles changed owner during the run
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_strip_box_edit_protocol_matches_single_world(oracle, table, tmp_path, nranks):
+    """The protocol of the calls that edit the grid from one place on strips (rigid-body raster / erase, tickEntities), over gloo with
+    oracle worlds: the product's own plan (`fse_strip_plan`, host code of libfse_b200.so) says who runs which body / entity and which
+    rectangles travel; every rank holds only its window (junk elsewhere).  Grid, particles, feedback, body tiles and entity records
+    must equal the single-world oracle — with bodies lying across the cuts, overlapping across them and drifting from strip to strip."""
+    from oracle import pyoracle as O
+    from tests.strip_bodies_scene import scene, entities
+    W, H, ticks = 1024, 1024, 4
+    out = str(tmp_path / "sbox")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29540 + nranks), WORLD_SIZE=str(nranks), OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "strip_bodies_cpu_worker.py"), str(W), str(H), str(ticks), out],
+                              env=dict(env, RANK=str(r))) for r in range(nranks)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    ow = oracle.OracleWorld(W, H, table)
+    ow.write_rect(0, 0, G.mixed_band(table, W, H, 0, H, seed=21, air_frac=0.6, blob=48))
+    bodies, xf = scene(table, W, H, nranks)
+    ents = entities(H, nranks)
+    fbs = []
+    for t in range(ticks):
+        ents = O.entities_tick(ow, ents, tick=t)
+        fbs.append(O.bodies_raster(ow, bodies, xf, tick=t))
+        fbs.append(O.bodies_erase(ow, bodies, xf))
+        xf[:, 1] += 1.5
+        xf[:, 2] += 0.05
+    fbs = np.stack(fbs)
+    assert fbs[:, :, 2].sum() > 0 and (fbs[0::2, :, 0] + fbs[0::2, :, 1]).sum() > 0
+    ref = ow.read_all()
+    tiles = np.concatenate([b.reshape(-1) for b in bodies])
+    parts = []
+    for r in range(nranks):
+        lo, hi = strips.strip_layout(H, r, nranks)[:2]
+        assert np.array_equal(fbs, np.load(f"{out}.fb{r}.npy")), f"feedback on rank {r}"
+        assert tiles.tobytes() == np.load(f"{out}.tiles{r}.npy").tobytes(), f"body tiles on rank {r}"
+        assert ents.tobytes() == np.load(f"{out}.ents{r}.npy").tobytes(), f"entities on rank {r}"
+        Hh.assert_cells_equal(ref[lo:hi], np.load(f"{out}.rank{r}.npy"), f"strip {r}/{nranks}")
+        parts.append(np.load(f"{out}.parts{r}.npy"))
+    Hh.assert_particles_equal(ow.particles_read(), np.concatenate(parts), "strip particles")
